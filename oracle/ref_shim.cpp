@@ -1,0 +1,272 @@
+// oracle/ref_shim.cpp -- TEST INFRASTRUCTURE ONLY (see oracle/README.md).
+//
+// extern "C" wrappers around the UNMODIFIED reference's public cv:: entry points for the
+// dense-imgproc hot path, so that tests/ and bench.py's cpu_baseline leg can call the real
+// reference (built by oracle/build_ref.py into oracle/_ref/libocvref.so) through ctypes.
+// Every wrapper only builds cv::Mat headers over caller memory and forwards; no arithmetic
+// lives here.  Reference entry points forwarded to:
+//   cv::GaussianBlur        modules/imgproc/src/smooth.dispatch.cpp:609
+//   cv::sepFilter2D         modules/imgproc/src/filter.dispatch.cpp:1555
+//   cv::filter2D            modules/imgproc/src/filter.dispatch.cpp:1521
+//   cv::resize              modules/imgproc/src/resize.cpp:4201
+//   cv::warpAffine          modules/imgproc/src/imgwarp.cpp:2788
+//   cv::warpPerspective     modules/imgproc/src/imgwarp.cpp:3370
+//   cv::cvtColor            modules/imgproc/src/color.cpp:192
+//   cv::matchTemplate       modules/imgproc/src/templmatch.cpp:1158
+//   cv::cornerHarris        modules/imgproc/src/corner.cpp:634
+//   cv::goodFeaturesToTrack modules/imgproc/src/featureselect.cpp:382
+//   SIFT_Impl::{createInitialImage,buildGaussianPyramid,buildDoGPyramid}
+//                           modules/features2d/src/sift.dispatch.cpp:176,224,302
+#include <cstring>
+#include <vector>
+#include "opencv2/core.hpp"
+#include "opencv2/core/softfloat.hpp"
+#include "opencv2/imgproc.hpp"
+
+// The SIFT pyramid builders live inside the reference's translation unit; compile that TU as
+// part of this one (by path, nothing copied) so they can be called directly.
+#include REF_SIFT_DISPATCH_CPP
+
+#define API extern "C" __attribute__((visibility("default")))
+
+using namespace cv;
+
+static inline Mat hdr(const void* p, size_t step, int w, int h, int type)
+{
+    return Mat(h, w, type, const_cast<void*>(p), step);
+}
+
+#define GUARD_BEGIN try {
+#define GUARD_END } catch (const cv::Exception& e) { std::fprintf(stderr, "ref_shim: %s\n", e.what()); return -1; } \
+                    catch (...) { return -2; } return 0;
+
+API int ref_set_num_threads(int n) { cv::setNumThreads(n); return cv::getNumThreads(); }
+API int ref_get_num_threads(void) { return cv::getNumThreads(); }
+API int ref_get_num_cpus(void) { return cv::getNumberOfCPUs(); }
+API const char* ref_build_info(void) { static String s = cv::getBuildInformation(); return s.c_str(); }
+
+// cv::RNG(seed).fill(UNIFORM, lo, hi) -- used to regenerate the reference tests' inputs
+API int ref_rng_fill(void* p, size_t step, int w, int h, int type, unsigned long long seed, double lo, double hi)
+{
+    GUARD_BEGIN
+    Mat m = hdr(p, step, w, h, type);
+    RNG rng(seed);
+    rng.fill(m, RNG::UNIFORM, lo, hi);
+    GUARD_END
+}
+
+API int ref_gaussian_kernel(int n, double sigma, int ktype, void* out)
+{
+    GUARD_BEGIN
+    Mat k = getGaussianKernel(n, sigma, ktype);
+    std::memcpy(out, k.data, (size_t)n * k.elemSize());
+    GUARD_END
+}
+
+API int ref_gaussian_blur(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int type,
+                          int kw, int kh, double sx, double sy, int border)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, w, h, type), d = hdr(dst, dstep, w, h, type);
+    GaussianBlur(s, d, Size(kw, kh), sx, sy, border);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+API int ref_sep_filter2d(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int stype, int ddepth,
+                         const float* kx, int kxlen, const float* ky, int kylen, int ax, int ay, double delta, int border)
+{
+    GUARD_BEGIN
+    int dtype = CV_MAKETYPE(ddepth < 0 ? CV_MAT_DEPTH(stype) : ddepth, CV_MAT_CN(stype));
+    Mat s = hdr(src, sstep, w, h, stype), d = hdr(dst, dstep, w, h, dtype);
+    Mat mkx(1, kxlen, CV_32F, (void*)kx), mky(kylen, 1, CV_32F, (void*)ky);
+    sepFilter2D(s, d, ddepth, mkx, mky, Point(ax, ay), delta, border);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+API int ref_filter2d(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int stype, int ddepth,
+                     const float* kernel, int kw, int kh, int ax, int ay, double delta, int border)
+{
+    GUARD_BEGIN
+    int dtype = CV_MAKETYPE(ddepth < 0 ? CV_MAT_DEPTH(stype) : ddepth, CV_MAT_CN(stype));
+    Mat s = hdr(src, sstep, w, h, stype), d = hdr(dst, dstep, w, h, dtype);
+    Mat k(kh, kw, CV_32F, (void*)kernel);
+    filter2D(s, d, ddepth, k, Point(ax, ay), delta, border);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+API int ref_sobel(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int stype, int ddepth,
+                  int dx, int dy, int ksize, double scale, double delta, int border)
+{
+    GUARD_BEGIN
+    int dtype = CV_MAKETYPE(ddepth < 0 ? CV_MAT_DEPTH(stype) : ddepth, CV_MAT_CN(stype));
+    Mat s = hdr(src, sstep, w, h, stype), d = hdr(dst, dstep, w, h, dtype);
+    Sobel(s, d, ddepth, dx, dy, ksize, scale, delta, border);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+API int ref_resize(const void* src, size_t sstep, int sw, int sh, void* dst, size_t dstep, int dw, int dh, int type, int interp)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, sw, sh, type), d = hdr(dst, dstep, dw, dh, type);
+    resize(s, d, Size(dw, dh), 0, 0, interp);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+API int ref_warp_affine(const void* src, size_t sstep, int sw, int sh, void* dst, size_t dstep, int dw, int dh, int type,
+                        const double* M, int flags, int border, const double* bv)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, sw, sh, type), d = hdr(dst, dstep, dw, dh, type);
+    Mat m(2, 3, CV_64F, (void*)M);
+    warpAffine(s, d, m, Size(dw, dh), flags, border, Scalar(bv[0], bv[1], bv[2], bv[3]));
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+API int ref_warp_perspective(const void* src, size_t sstep, int sw, int sh, void* dst, size_t dstep, int dw, int dh, int type,
+                             const double* M, int flags, int border, const double* bv)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, sw, sh, type), d = hdr(dst, dstep, dw, dh, type);
+    Mat m(3, 3, CV_64F, (void*)M);
+    warpPerspective(s, d, m, Size(dw, dh), flags, border, Scalar(bv[0], bv[1], bv[2], bv[3]));
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+API int ref_invert_affine(const double* M, double* iM)
+{
+    GUARD_BEGIN
+    Mat m(2, 3, CV_64F, (void*)M), im(2, 3, CV_64F, iM);
+    invertAffineTransform(m, im);
+    GUARD_END
+}
+
+API int ref_invert3x3(const double* M, double* iM)
+{
+    GUARD_BEGIN
+    Mat m(3, 3, CV_64F, (void*)M), im(3, 3, CV_64F, iM);
+    invert(m, im);
+    CV_Assert(im.data == (uchar*)iM);
+    GUARD_END
+}
+
+API int ref_get_rotation_matrix2d(double cx, double cy, double angle, double scale, double* M)
+{
+    GUARD_BEGIN
+    Mat m = getRotationMatrix2D(Point2f((float)cx, (float)cy), angle, scale);
+    std::memcpy(M, m.data, 6 * sizeof(double));
+    GUARD_END
+}
+
+API int ref_cvt_color(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int stype, int dtype, int code)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, w, h, stype), d = hdr(dst, dstep, w, h, dtype);
+    cvtColor(s, d, code, CV_MAT_CN(dtype));
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+API int ref_match_template(const void* img, size_t istep, int iw, int ih, const void* templ, size_t tstep, int tw, int th,
+                           int type, float* result, size_t rstep, int method)
+{
+    GUARD_BEGIN
+    Mat i = hdr(img, istep, iw, ih, type), t = hdr(templ, tstep, tw, th, type);
+    Mat r = hdr(result, rstep, iw - tw + 1, ih - th + 1, CV_32F);
+    matchTemplate(i, t, r, method);
+    CV_Assert(r.data == (uchar*)result);
+    GUARD_END
+}
+
+API int ref_corner_harris(const void* src, size_t sstep, int w, int h, int type, float* dst, size_t dstep,
+                          int blockSize, int ksize, double k, int border)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, w, h, type), d = hdr(dst, dstep, w, h, CV_32F);
+    cornerHarris(s, d, blockSize, ksize, k, border);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+API int ref_corner_min_eigen_val(const void* src, size_t sstep, int w, int h, int type, float* dst, size_t dstep,
+                                 int blockSize, int ksize, int border)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, w, h, type), d = hdr(dst, dstep, w, h, CV_32F);
+    cornerMinEigenVal(s, d, blockSize, ksize, border);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+// corners: out array of 2*maxOut floats (x,y); quality: optional out array of maxOut floats; returns count in *n
+API int ref_good_features_to_track(const void* src, size_t sstep, int w, int h, int type, float* corners, float* quality,
+                                   int maxOut, int* n, int maxCorners, double qualityLevel, double minDistance,
+                                   int blockSize, int gradientSize, int useHarris, double k)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, w, h, type);
+    std::vector<Point2f> pts;
+    std::vector<float> q;
+    goodFeaturesToTrack(s, pts, maxCorners, qualityLevel, minDistance, noArray(), q, blockSize, gradientSize, useHarris != 0, k);
+    int cnt = (int)std::min<size_t>(pts.size(), (size_t)maxOut);
+    for (int i = 0; i < cnt; i++) {
+        corners[2 * i] = pts[i].x; corners[2 * i + 1] = pts[i].y;
+        if (quality) quality[i] = q[i];
+    }
+    *n = (int)pts.size();
+    GUARD_END
+}
+
+// ---- SIFT Gaussian pyramid + DoG (sift.dispatch.cpp:176-310, :501-545 for the octave count) ----
+// gray: 8UC1 w x h.  Outputs are packed tightly, image after image, octave-major:
+//   gauss: nOctaves*(nOctaveLayers+3) images, dog: nOctaves*(nOctaveLayers+2) images, all CV_32F.
+// dims (optional): per-octave (w,h) pairs, 2*nOctaves ints.  Pass gauss/dog = NULL to query sizes only:
+//   *gauss_elems / *dog_elems receive the total float counts, *n_octaves the octave count.
+API int ref_sift_pyramid(const void* gray, size_t step, int w, int h, int nOctaveLayers, double sigma, int firstOctave_upscale,
+                         float* gauss, size_t* gauss_elems, float* dog, size_t* dog_elems, int* n_octaves, int* dims)
+{
+    GUARD_BEGIN
+    Mat image = hdr(gray, step, w, h, CV_8UC1);
+    int firstOctave = firstOctave_upscale ? -1 : 0;
+    Ptr<SIFT> sp = SIFT::create(0, nOctaveLayers, 0.04, 10, sigma);
+    SIFT_Impl* impl = dynamic_cast<SIFT_Impl*>(sp.get());
+    CV_Assert(impl);
+    Mat base = createInitialImage(image, firstOctave < 0, (float)sigma, true);
+    int nOctaves = cvRound(std::log((double)std::min(base.cols, base.rows)) / std::log(2.) - 2) - firstOctave;
+    // NB: the expression above mirrors sift.dispatch.cpp:538 (actualNOctaves == 0 branch)
+    std::vector<Mat> gpyr, dogpyr;
+    size_t ge = 0, de = 0;
+    if (gauss || dog) {
+        impl->buildGaussianPyramid(base, gpyr, nOctaves);
+        impl->buildDoGPyramid(gpyr, dogpyr);
+        for (size_t i = 0; i < gpyr.size(); i++) {
+            const Mat& m = gpyr[i];
+            if (gauss) for (int y = 0; y < m.rows; y++) std::memcpy(gauss + ge + (size_t)y * m.cols, m.ptr<float>(y), m.cols * sizeof(float));
+            ge += (size_t)m.rows * m.cols;
+            if (dims && i % (nOctaveLayers + 3) == 0) { dims[2 * (i / (nOctaveLayers + 3))] = m.cols; dims[2 * (i / (nOctaveLayers + 3)) + 1] = m.rows; }
+        }
+        for (size_t i = 0; i < dogpyr.size(); i++) {
+            const Mat& m = dogpyr[i];
+            if (dog) for (int y = 0; y < m.rows; y++) std::memcpy(dog + de + (size_t)y * m.cols, m.ptr<float>(y), m.cols * sizeof(float));
+            de += (size_t)m.rows * m.cols;
+        }
+    } else {
+        int cw = base.cols, ch = base.rows;
+        for (int o = 0; o < nOctaves; o++) {
+            ge += (size_t)cw * ch * (nOctaveLayers + 3);
+            de += (size_t)cw * ch * (nOctaveLayers + 2);
+            if (dims) { dims[2 * o] = cw; dims[2 * o + 1] = ch; }
+            cw /= 2; ch /= 2;
+        }
+    }
+    if (gauss_elems) *gauss_elems = ge;
+    if (dog_elems) *dog_elems = de;
+    if (n_octaves) *n_octaves = nOctaves;
+    GUARD_END
+}
