@@ -1,0 +1,192 @@
+/*
+ * b200cv.h -- C ABI of the B200-native dense-imgproc hot path (OpenCV drop-in boundary).
+ *
+ * Plain C: pointers, sizes, ints, doubles.  No C++ / torch / OpenCV types cross this line.
+ * Everything above it (the cv::-signature C++ mirror in opencv_b200/host/, the cv_hal_*
+ * replacement header include/b200cv_hal.h, the Python ctypes binding) is a thin caller.
+ *
+ * Two families of entry points:
+ *
+ *  (1) b200cv_*        -- DEVICE API.  Images are b200cvMat descriptors over device memory
+ *                         (row-major, interleaved channels, `step` bytes per row -- the cv::Mat /
+ *                         cv::cuda::GpuMat layout, reference: modules/core/include/opencv2/core/mat.hpp:2151-2178,
+ *                         modules/core/include/opencv2/core/cuda.hpp:105-340).  A descriptor can describe a
+ *                         BATCH of `frames` equally-shaped frames `frame_step` bytes apart: independent
+ *                         frames are processed by one launch (grid z / persistent tile loop).  Work is
+ *                         enqueued on `stream` (a cudaStream_t passed as void*, NULL = legacy default
+ *                         stream) and the call returns without synchronising, like cv::cuda::* functions
+ *                         taking a cv::cuda::Stream& (cuda.hpp:909-975).
+ *
+ *  (2) b200cv_hal_*    -- HOST API with the exact argument lists of the reference's imgproc HAL seam
+ *                         (modules/imgproc/src/hal_replacement.hpp): raw host pointers + step, synchronous,
+ *                         result in `dst` on return.  Declared in include/b200cv_hal.h.
+ *
+ * Return convention = the HAL's (modules/core/include/opencv2/core/hal/interface.h:9-11):
+ *   0  B200CV_OK               done
+ *   1  B200CV_NOT_IMPLEMENTED  unsupported type/border/size: caller should use its own path
+ *  <0  error (bad argument / CUDA failure); b200cv_last_error() returns a thread-local message.
+ * There is NO CPU fallback anywhere behind this ABI.
+ *
+ * Type / border / interpolation / colour codes are numerically OpenCV's:
+ *   type   = CV_MAKETYPE(depth, cn)   depth: CV_8U=0 CV_16S=3 CV_32F=5        (core/hal/interface.h:70-85)
+ *   border = CV_HAL_BORDER_*          CONSTANT 0 REPLICATE 1 REFLECT 2 WRAP 3 REFLECT_101 4 (:151-157)
+ *   interp = CV_HAL_INTER_*           NEAREST 0 LINEAR 1 CUBIC 2 AREA 3; WARP_INVERSE_MAP 16 (imgproc/hal/interface.h:10-20)
+ *   code   = cv::ColorConversionCodes (imgproc.hpp:538-642)
+ *   method = cv::TemplateMatchModes   (imgproc.hpp:3845-3879)
+ */
+#ifndef B200CV_H
+#define B200CV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200CV_API __attribute__((visibility("default")))
+#else
+#define B200CV_API
+#endif
+
+#define B200CV_OK 0
+#define B200CV_NOT_IMPLEMENTED 1
+#define B200CV_ERR_BAD_ARG (-2)
+#define B200CV_ERR_CUDA (-3)
+#define B200CV_ERR_NO_DEVICE (-4)
+
+/* depth / type codes (== CV_8U ...) */
+#define B200CV_8U 0
+#define B200CV_16S 3
+#define B200CV_32F 5
+#define B200CV_MAKETYPE(depth, cn) (((depth) & 7) + (((cn) - 1) << 3))
+#define B200CV_DEPTH(type) ((type) & 7)
+#define B200CV_CN(type) ((((type) >> 3) & 511) + 1)
+
+#define B200CV_BORDER_CONSTANT 0
+#define B200CV_BORDER_REPLICATE 1
+#define B200CV_BORDER_REFLECT 2
+#define B200CV_BORDER_WRAP 3
+#define B200CV_BORDER_REFLECT_101 4
+#define B200CV_BORDER_TRANSPARENT 5
+#define B200CV_BORDER_ISOLATED 16
+
+#define B200CV_INTER_NEAREST 0
+#define B200CV_INTER_LINEAR 1
+#define B200CV_INTER_CUBIC 2
+#define B200CV_INTER_AREA 3
+#define B200CV_WARP_INVERSE_MAP 16
+
+#define B200CV_TM_SQDIFF 0
+#define B200CV_TM_SQDIFF_NORMED 1
+#define B200CV_TM_CCORR 2
+#define B200CV_TM_CCORR_NORMED 3
+#define B200CV_TM_CCOEFF 4
+#define B200CV_TM_CCOEFF_NORMED 5
+
+/* A (batch of) device image(s).  frames<=1 means a single frame (frame_step ignored). */
+typedef struct b200cvMat {
+    void*  data;        /* device pointer to pixel (0,0) of frame 0 */
+    size_t step;        /* bytes per row */
+    int    cols;        /* width in pixels */
+    int    rows;        /* height in pixels */
+    int    type;        /* CV_MAKETYPE(depth, cn) */
+    int    frames;      /* number of frames in the batch (>=1) */
+    size_t frame_step;  /* bytes between consecutive frames */
+} b200cvMat;
+
+/* ---- runtime ---------------------------------------------------------------------------------------------- */
+/* replaces: cv::cuda::setDevice / getCudaEnabledDeviceCount (core/include/opencv2/core/cuda.hpp:1040-1060) */
+B200CV_API int b200cv_init(int device);
+B200CV_API int b200cv_device_count(void);
+B200CV_API const char* b200cv_last_error(void);
+B200CV_API const char* b200cv_version(void);
+/* number of b200cv kernels launched by this process so far (bench.py's gpu_launches) */
+B200CV_API unsigned long long b200cv_launch_count(void);
+
+/* replaces: cv::cuda::GpuMat::Allocator::allocate/free (cuda.hpp:108-115; default = cudaMallocPitch, core/src/cuda/gpu_mat.cu:116).
+ * Pitch is rounded up to 256 B so every row is TMA-addressable. */
+B200CV_API int b200cv_malloc_pitch(void** dptr, size_t* step, size_t width_bytes, size_t rows);
+B200CV_API int b200cv_free(void* dptr);
+/* replaces: cv::cuda::HostMem (cuda.hpp:791-870): page-locked host allocation */
+B200CV_API int b200cv_host_alloc(void** hptr, size_t bytes);
+B200CV_API int b200cv_host_free(void* hptr);
+/* replaces: GpuMat::upload / download (cuda.hpp:160-190; core/src/cuda/gpu_mat.cu:228-288) */
+B200CV_API int b200cv_upload(const void* hsrc, size_t hstep, void* ddst, size_t dstep, size_t width_bytes, size_t rows, void* stream);
+B200CV_API int b200cv_download(const void* dsrc, size_t dstep, void* hdst, size_t hstep, size_t width_bytes, size_t rows, void* stream);
+
+/* replaces: cv::cuda::Stream (cuda.hpp:909-975) and cv::cuda::Event (cuda.hpp:984-1016) */
+B200CV_API int b200cv_stream_create(void** stream);
+B200CV_API int b200cv_stream_destroy(void* stream);
+B200CV_API int b200cv_stream_query(void* stream);              /* 0 = complete, 1 = still running (Stream::queryIfComplete) */
+B200CV_API int b200cv_stream_synchronize(void* stream);        /* Stream::waitForCompletion */
+B200CV_API int b200cv_stream_wait_event(void* stream, void* event); /* Stream::waitEvent */
+B200CV_API int b200cv_stream_add_callback(void* stream, void (*fn)(int status, void* user), void* user); /* enqueueHostCallback */
+B200CV_API int b200cv_event_create(void** event);
+B200CV_API int b200cv_event_destroy(void* event);
+B200CV_API int b200cv_event_record(void* event, void* stream);
+B200CV_API int b200cv_event_synchronize(void* event);
+B200CV_API int b200cv_event_elapsed_ms(void* start, void* end, float* ms);
+
+/* ---- host-side exact tables (pure host code; exported so callers/tests can inspect them) ----------------------- */
+/* cv::getGaussianKernel (imgproc/src/smooth.dispatch.cpp:81-221): n taps as double, bit-exact softdouble arithmetic */
+B200CV_API int b200cv_get_gaussian_kernel(int n, double sigma, double* out);
+/* 8.8 fixed-point taps with error diffusion (smooth.dispatch.cpp:224-277) */
+B200CV_API int b200cv_get_gaussian_kernel_fixed8(int n, double sigma, uint16_t* out);
+
+/* ---- device ops ------------------------------------------------------------------------------------------------
+ * All take b200cvMat descriptors over DEVICE memory; small operands (taps, matrices) are HOST pointers, copied at
+ * call time into kernel parameters.  dst must be pre-allocated with the right size/type (as the HAL guarantees). */
+
+/* replaces cv::GaussianBlur (imgproc.hpp:1544; smooth.dispatch.cpp:609-826). u8: bit-exact 8.8 fixed point; f32: float. */
+B200CV_API int b200cv_gaussian_blur(const b200cvMat* src, const b200cvMat* dst, int ksize_w, int ksize_h,
+                                    double sigma_x, double sigma_y, int border, void* stream);
+/* replaces cv::sepFilter2D (imgproc.hpp:1723; filter.dispatch.cpp:1555-1594). kx/ky: float taps on the host. */
+B200CV_API int b200cv_sep_filter2d(const b200cvMat* src, const b200cvMat* dst, const float* kx, int kx_len,
+                                   const float* ky, int ky_len, int anchor_x, int anchor_y, double delta,
+                                   int border, void* stream);
+/* replaces cv::filter2D (imgproc.hpp:1702; filter.dispatch.cpp:1521-1553). kernel: kh x kw float taps (correlation). */
+B200CV_API int b200cv_filter2d(const b200cvMat* src, const b200cvMat* dst, const float* kernel, int kw, int kh,
+                               int anchor_x, int anchor_y, double delta, int border, void* stream);
+/* replaces cv::Sobel (imgproc.hpp:1862; deriv.cpp:414-465) for ksize 1/3/5/7 */
+B200CV_API int b200cv_sobel(const b200cvMat* src, const b200cvMat* dst, int dx, int dy, int ksize, double scale,
+                            double delta, int border, void* stream);
+/* replaces cv::resize (imgproc.hpp:2422; resize.cpp:4201-4246).  Scale factors are dst/src sizes (fx=fy=0 form). */
+B200CV_API int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int interpolation, void* stream);
+/* replaces cv::warpAffine (imgproc.hpp:2450; imgwarp.cpp:2788-2902). M: 2x3 doubles; inverted unless WARP_INVERSE_MAP. */
+B200CV_API int b200cv_warp_affine(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags,
+                                  int border, const double* border_value, void* stream);
+/* replaces cv::warpPerspective (imgproc.hpp:2482; imgwarp.cpp:3370-3466). M: 3x3 doubles. */
+B200CV_API int b200cv_warp_perspective(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags,
+                                       int border, const double* border_value, void* stream);
+/* replaces cv::cvtColor (imgproc.hpp:3736; color.cpp:192-400) for BGR/RGB(A) <-> GRAY / YUV / YCrCb / HSV(_FULL) / BGR(A) */
+B200CV_API int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int code, void* stream);
+/* replaces cv::matchTemplate (imgproc.hpp:3916; templmatch.cpp:1158-1194), 1-channel u8/f32, all six methods.
+ * result: CV_32FC1 (W-w+1) x (H-h+1).  The CCORR numerator of u8 images runs on tcgen05 tensor cores. */
+B200CV_API int b200cv_match_template(const b200cvMat* image, const b200cvMat* templ, const b200cvMat* result,
+                                     int method, void* stream);
+/* replaces cv::cornerHarris / cv::cornerMinEigenVal (imgproc.hpp:1948,1921; corner.cpp:634-654,610-632) */
+B200CV_API int b200cv_corner_harris(const b200cvMat* src, const b200cvMat* dst, int block_size, int ksize, double k,
+                                    int border, void* stream);
+B200CV_API int b200cv_corner_min_eigen_val(const b200cvMat* src, const b200cvMat* dst, int block_size, int ksize,
+                                           int border, void* stream);
+/* replaces cv::goodFeaturesToTrack (imgproc.hpp:2096; featureselect.cpp:382-548).  Synchronous (returns host data).
+ * corners: host array of 2*max_out floats (x,y pairs) per frame, laid out frame after frame; counts[f] = corners found
+ * in frame f (may exceed max_out; only the first max_out are stored). */
+B200CV_API int b200cv_good_features_to_track(const b200cvMat* src, float* corners, float* quality, int max_out,
+                                             int* counts, int max_corners, double quality_level, double min_distance,
+                                             int block_size, int gradient_size, int use_harris, double k, void* stream);
+/* SIFT Gaussian pyramid + DoG (features2d/src/sift.dispatch.cpp:176-310).
+ * src: 8UC1 batch.  gauss / dog: device float buffers, per frame packed image after image, octave-major
+ * (n_octaves*(n_layers+3) Gaussian images, n_octaves*(n_layers+2) DoG images); per-frame strides in floats.
+ * Query sizes first with b200cv_sift_pyramid_layout. dog may be NULL (Gaussian only). */
+B200CV_API int b200cv_sift_pyramid_layout(int width, int height, int n_octave_layers, int upscale,
+                                          int* n_octaves, size_t* gauss_elems, size_t* dog_elems, int* dims /*2*n_octaves or NULL*/);
+B200CV_API int b200cv_sift_pyramid(const b200cvMat* src, int n_octave_layers, double sigma, int upscale,
+                                   float* gauss, size_t gauss_frame_elems, float* dog, size_t dog_frame_elems, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CV_H */

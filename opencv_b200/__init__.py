@@ -1,0 +1,255 @@
+"""opencv_b200 -- Python face of the B200-native dense-imgproc hot path (libb200cv.so, sm_100a).
+
+The functions mirror the cv2 / cv:: names and argument meaning of the reference
+(modules/imgproc/include/opencv2/imgproc.hpp) for the calls on the hot path:
+
+    GaussianBlur, sepFilter2D, filter2D, Sobel, resize, warpAffine, warpPerspective, cvtColor,
+    matchTemplate, cornerHarris, cornerMinEigenVal, goodFeaturesToTrack, sift_pyramid
+
+Inputs are torch CUDA tensors laid out like a cv::Mat -- (H, W) or (H, W, C), or a batch
+(N, H, W[, C]) of independent frames -- and go to the device C ABI (include/b200cv.h) without a
+copy; numpy arrays go through the synchronous host C ABI (include/b200cv_hal.h), which uploads,
+runs the same kernels and downloads.  There is NO CPU fallback: if the CUDA library is missing or
+no B200 is visible every call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libb200cv.so")
+_lib = None
+
+# ---- OpenCV-compatible constants -------------------------------------------------------------------------------
+CV_8U, CV_16S, CV_32F = 0, 3, 5
+BORDER_CONSTANT, BORDER_REPLICATE, BORDER_REFLECT, BORDER_WRAP, BORDER_REFLECT_101 = 0, 1, 2, 3, 4
+BORDER_DEFAULT = BORDER_REFLECT_101
+BORDER_REFLECT101 = BORDER_REFLECT_101
+BORDER_TRANSPARENT, BORDER_ISOLATED = 5, 16
+INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_AREA = 0, 1, 2, 3
+WARP_INVERSE_MAP = 16
+TM_SQDIFF, TM_SQDIFF_NORMED, TM_CCORR, TM_CCORR_NORMED, TM_CCOEFF, TM_CCOEFF_NORMED = range(6)
+COLOR_BGR2BGRA, COLOR_BGRA2BGR, COLOR_BGR2RGBA, COLOR_RGBA2BGR, COLOR_BGR2RGB, COLOR_BGRA2RGBA = range(6)
+COLOR_RGB2BGRA, COLOR_BGRA2RGB, COLOR_RGB2BGR, COLOR_RGBA2BGRA = COLOR_BGR2RGBA, COLOR_RGBA2BGR, COLOR_BGR2RGB, COLOR_BGRA2RGBA
+COLOR_BGR2GRAY, COLOR_RGB2GRAY, COLOR_GRAY2BGR, COLOR_GRAY2BGRA, COLOR_BGRA2GRAY, COLOR_RGBA2GRAY = 6, 7, 8, 9, 10, 11
+COLOR_GRAY2RGB, COLOR_GRAY2RGBA = COLOR_GRAY2BGR, COLOR_GRAY2BGRA
+COLOR_BGR2YCrCb, COLOR_RGB2YCrCb, COLOR_YCrCb2BGR, COLOR_YCrCb2RGB = 36, 37, 38, 39
+COLOR_BGR2HSV, COLOR_RGB2HSV, COLOR_HSV2BGR, COLOR_HSV2RGB = 40, 41, 54, 55
+COLOR_BGR2HSV_FULL, COLOR_RGB2HSV_FULL, COLOR_HSV2BGR_FULL, COLOR_HSV2RGB_FULL = 66, 67, 70, 71
+COLOR_BGR2YUV, COLOR_RGB2YUV, COLOR_YUV2BGR, COLOR_YUV2RGB = 82, 83, 84, 85
+
+OK, NOT_IMPLEMENTED = 0, 1
+
+
+class B200cvError(RuntimeError):
+    pass
+
+
+class NotImplementedOnDevice(B200cvError):
+    """The C ABI returned CV_HAL_ERROR_NOT_IMPLEMENTED (unsupported type/border/size combination)."""
+
+
+class Mat(ctypes.Structure):
+    """struct b200cvMat (include/b200cv.h)"""
+    _fields_ = [("data", ctypes.c_void_p), ("step", ctypes.c_size_t), ("cols", ctypes.c_int), ("rows", ctypes.c_int),
+                ("type", ctypes.c_int), ("frames", ctypes.c_int), ("frame_step", ctypes.c_size_t)]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def lib():
+    """Load libb200cv.so (built in-tree by `python -m opencv_b200.build`); fail loudly if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise B200cvError("libb200cv.so not built (%s): run `python -m opencv_b200.build`; "
+                              "there is no CPU fallback for this path" % _LIB_PATH)
+        L = ctypes.CDLL(_LIB_PATH)
+        L.b200cv_last_error.restype = ctypes.c_char_p
+        L.b200cv_version.restype = ctypes.c_char_p
+        L.b200cv_launch_count.restype = ctypes.c_ulonglong
+        _lib = L
+    return _lib
+
+
+def _check(rc, what):
+    if rc == OK:
+        return
+    if rc == NOT_IMPLEMENTED:
+        raise NotImplementedOnDevice("%s: combination not implemented on the device path" % what)
+    raise B200cvError("%s failed (%d): %s" % (what, rc, lib().b200cv_last_error().decode()))
+
+
+def init(device=0):
+    _check(lib().b200cv_init(int(device)), "b200cv_init")
+
+
+def launch_count():
+    return int(lib().b200cv_launch_count())
+
+
+_DEPTH_OF = {"torch.uint8": CV_8U, "torch.int16": CV_16S, "torch.float32": CV_32F,
+             "uint8": CV_8U, "int16": CV_16S, "float32": CV_32F}
+_ESZ = {CV_8U: 1, CV_16S: 2, CV_32F: 4}
+
+
+def make_type(depth, cn):
+    return (depth & 7) + ((cn - 1) << 3)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if hasattr(stream, "cuda_stream"):
+        return ctypes.c_void_p(stream.cuda_stream)
+    return ctypes.c_void_p(int(stream))
+
+
+def describe(t):
+    """b200cvMat over a torch CUDA tensor laid out like a cv::Mat / GpuMat:
+    (H,W) single channel, (H,W,C) interleaved channels, or (N,H,W,C) a batch of N independent frames.
+    Rows may be padded (stride(-3) >= W*C); pixels and channels must be dense."""
+    assert _is_torch(t) and t.is_cuda, "device API needs a torch CUDA tensor"
+    depth = _DEPTH_OF[str(t.dtype)]
+    esz = _ESZ[depth]
+    nd = t.dim()
+    if nd == 2:
+        n, h, w, c = 1, t.shape[0], t.shape[1], 1
+        fs, rs = 0, t.stride(0)
+        assert t.stride(1) == 1 or w == 1
+    elif nd == 3:
+        n, (h, w, c) = 1, t.shape
+        fs, rs = 0, t.stride(0)
+        assert (t.stride(2) == 1 or c == 1) and (t.stride(1) == c or w == 1)
+    elif nd == 4:
+        n, h, w, c = t.shape
+        fs, rs = t.stride(0), t.stride(1)
+        assert (t.stride(3) == 1 or c == 1) and (t.stride(2) == c or w == 1)
+    else:
+        raise ValueError("unsupported tensor rank %d" % nd)
+    return Mat(t.data_ptr(), rs * esz, w, h, make_type(depth, c), n, fs * esz)
+
+
+def _cn(m):
+    return ((m.type >> 3) & 511) + 1
+
+
+def _new(src, dtype=None, channels=None, size=None):
+    """output tensor for `src`: same rank convention, optionally other dtype / channel count / (w, h)"""
+    import torch
+    m = describe(src)
+    c = _cn(m) if channels is None else channels
+    w, h = (m.cols, m.rows) if size is None else size
+    if src.dim() == 4:
+        shape = [max(m.frames, 1), h, w, c]
+    elif c == 1:
+        shape = [h, w]
+    else:
+        shape = [h, w, c]
+    return torch.empty(shape, dtype=dtype or src.dtype, device=src.device)
+
+
+def _pair(src, dst):
+    return describe(src), describe(dst)
+
+
+# ---- ops -----------------------------------------------------------------------------------------------------------
+def GaussianBlur(src, ksize, sigmaX, sigmaY=0, borderType=BORDER_DEFAULT, dst=None, stream=None):
+    """cv::GaussianBlur (imgproc.hpp:1544)"""
+    if not _is_torch(src):
+        from . import hal
+        return hal.GaussianBlur(src, ksize, sigmaX, sigmaY, borderType)
+    dst = dst if dst is not None else _new(src)
+    ms, md = _pair(src, dst)
+    _check(lib().b200cv_gaussian_blur(ctypes.byref(ms), ctypes.byref(md), int(ksize[0]), int(ksize[1]),
+                                      ctypes.c_double(sigmaX), ctypes.c_double(sigmaY), int(borderType), _stream_ptr(stream)),
+           "GaussianBlur")
+    return dst
+
+
+def _f32(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def _f64(a):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1))
+    return a, a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _ddepth_dtype(src, ddepth):
+    import torch
+    if ddepth is None or ddepth < 0:
+        return src.dtype
+    return {CV_8U: torch.uint8, CV_16S: torch.int16, CV_32F: torch.float32}[ddepth]
+
+
+def sepFilter2D(src, ddepth, kernelX, kernelY, anchor=(-1, -1), delta=0.0, borderType=BORDER_DEFAULT, dst=None, stream=None):
+    """cv::sepFilter2D (imgproc.hpp:1723)"""
+    dst = dst if dst is not None else _new(src, dtype=_ddepth_dtype(src, ddepth))
+    ms, md = _pair(src, dst)
+    kx, pkx = _f32(kernelX)
+    ky, pky = _f32(kernelY)
+    _check(lib().b200cv_sep_filter2d(ctypes.byref(ms), ctypes.byref(md), pkx, len(kx), pky, len(ky), int(anchor[0]), int(anchor[1]),
+                                     ctypes.c_double(delta), int(borderType), _stream_ptr(stream)), "sepFilter2D")
+    return dst
+
+
+def filter2D(src, ddepth, kernel, anchor=(-1, -1), delta=0.0, borderType=BORDER_DEFAULT, dst=None, stream=None):
+    """cv::filter2D (imgproc.hpp:1702)"""
+    dst = dst if dst is not None else _new(src, dtype=_ddepth_dtype(src, ddepth))
+    ms, md = _pair(src, dst)
+    k = np.asarray(kernel, dtype=np.float32)
+    kh, kw = k.shape
+    kk, pk = _f32(k)
+    _check(lib().b200cv_filter2d(ctypes.byref(ms), ctypes.byref(md), pk, kw, kh, int(anchor[0]), int(anchor[1]),
+                                 ctypes.c_double(delta), int(borderType), _stream_ptr(stream)), "filter2D")
+    return dst
+
+
+def Sobel(src, ddepth, dx, dy, ksize=3, scale=1.0, delta=0.0, borderType=BORDER_DEFAULT, dst=None, stream=None):
+    """cv::Sobel (imgproc.hpp:1862)"""
+    dst = dst if dst is not None else _new(src, dtype=_ddepth_dtype(src, ddepth))
+    ms, md = _pair(src, dst)
+    _check(lib().b200cv_sobel(ctypes.byref(ms), ctypes.byref(md), int(dx), int(dy), int(ksize), ctypes.c_double(scale),
+                              ctypes.c_double(delta), int(borderType), _stream_ptr(stream)), "Sobel")
+    return dst
+
+
+_CVT_DCN = {COLOR_BGR2BGRA: 4, COLOR_BGRA2BGR: 3, COLOR_BGR2RGBA: 4, COLOR_RGBA2BGR: 3, COLOR_BGR2RGB: 3, COLOR_BGRA2RGBA: 4,
+            COLOR_BGR2GRAY: 1, COLOR_RGB2GRAY: 1, COLOR_BGRA2GRAY: 1, COLOR_RGBA2GRAY: 1, COLOR_GRAY2BGR: 3, COLOR_GRAY2BGRA: 4}
+
+
+def cvtColor(src, code, dstCn=0, dst=None, stream=None):
+    """cv::cvtColor (imgproc.hpp:3736)"""
+    if not _is_torch(src):
+        from . import hal
+        return hal.cvtColor(src, code, dstCn)
+    dcn = dstCn if dstCn > 0 else _CVT_DCN.get(code, 3)
+    dst = dst if dst is not None else _new(src, channels=dcn)
+    ms, md = _pair(src, dst)
+    _check(lib().b200cv_cvt_color(ctypes.byref(ms), ctypes.byref(md), int(code), _stream_ptr(stream)), "cvtColor")
+    return dst
+
+
+def getGaussianKernel(ksize, sigma):
+    """cv::getGaussianKernel as float64 (bit-exact softdouble arithmetic on the host)"""
+    out = np.zeros(ksize, np.float64)
+    _check(lib().b200cv_get_gaussian_kernel(int(ksize), ctypes.c_double(sigma), out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))),
+           "getGaussianKernel")
+    return out
+
+
+def getGaussianKernelFixed8(ksize, sigma):
+    out = np.zeros(ksize, np.uint16)
+    _check(lib().b200cv_get_gaussian_kernel_fixed8(int(ksize), ctypes.c_double(sigma), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16))),
+           "getGaussianKernelFixed8")
+    return out

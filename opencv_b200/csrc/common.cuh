@@ -1,0 +1,118 @@
+// common.cuh -- shared device/host helpers for the b200cv kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/b200cv.h"
+
+namespace b200cv {
+
+typedef unsigned char uchar;
+
+// ---- error plumbing -------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+void count_launch(int n = 1);
+
+#define B200_CUDA(call)                                                         \
+    do {                                                                        \
+        cudaError_t e__ = (call);                                               \
+        if (e__ != cudaSuccess) return ::b200cv::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define B200_REQUIRE(cond, msg)                                                 \
+    do {                                                                        \
+        if (!(cond)) { ::b200cv::set_error("%s (%s)", msg, #cond); return B200CV_ERR_BAD_ARG; } \
+    } while (0)
+
+#define B200_LAUNCH_CHECK()                                                     \
+    do {                                                                        \
+        ::b200cv::count_launch();                                               \
+        cudaError_t e__ = cudaGetLastError();                                   \
+        if (e__ != cudaSuccess) return ::b200cv::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
+int num_sms();
+
+// ---- device image descriptor (kernel parameter) -----------------------------------------------------------------
+struct Img {
+    uchar* data;
+    size_t step;
+    size_t fstep;
+    int cols, rows, frames;
+    template <typename T> __host__ __device__ __forceinline__ T* row(int f, int y) const {
+        return (T*)(data + (size_t)f * fstep + (size_t)y * step);
+    }
+};
+
+static inline Img make_img(const b200cvMat* m)
+{
+    Img i;
+    i.data = (uchar*)m->data; i.step = m->step; i.cols = m->cols; i.rows = m->rows;
+    i.frames = m->frames > 1 ? m->frames : 1;
+    i.fstep = i.frames > 1 ? m->frame_step : 0;
+    return i;
+}
+
+int check_mat(const b200cvMat* m, const char* name);
+static inline size_t elem_size(int type) { int d = B200CV_DEPTH(type); return (size_t)B200CV_CN(type) * (d == 0 || d == 1 ? 1 : d == 2 || d == 3 ? 2 : d == 6 ? 8 : 4); }
+
+// ---- cv::borderInterpolate (reference: modules/core/src/copy.cpp:748-793) --------------------------------------------
+// returns -1 for BORDER_CONSTANT outside the image
+__host__ __device__ __forceinline__ int border_interpolate(int p, int len, int border)
+{
+    if ((unsigned)p < (unsigned)len) return p;
+    if (border == B200CV_BORDER_REPLICATE) return p < 0 ? 0 : len - 1;
+    if (border == B200CV_BORDER_REFLECT || border == B200CV_BORDER_REFLECT_101) {
+        int delta = border == B200CV_BORDER_REFLECT_101;
+        if (len == 1) return 0;
+        do {
+            if (p < 0) p = -p - 1 + delta;
+            else p = len - 1 - (p - len) - delta;
+        } while ((unsigned)p >= (unsigned)len);
+        return p;
+    }
+    if (border == B200CV_BORDER_WRAP) {
+        if (p < 0) p -= ((p - len + 1) / len) * len;
+        if (p >= len) p %= len;
+        return p;
+    }
+    return -1;  // CONSTANT
+}
+
+// ---- saturate_cast family (reference: modules/core/include/opencv2/core/saturate.hpp:103-133) ---------------------------
+__device__ __forceinline__ uchar sat_u8(int v) { return (uchar)min(max(v, 0), 255); }
+// saturate_cast<uchar>(float) = cvRound (round-half-even) then clamp
+__device__ __forceinline__ uchar sat_u8(float v) { return sat_u8(__float2int_rn(v)); }
+__device__ __forceinline__ short sat_s16(int v) { return (short)min(max(v, -32768), 32767); }
+__device__ __forceinline__ short sat_s16(float v) { return sat_s16(__float2int_rn(v)); }
+
+template <typename T> struct OutCast;
+template <> struct OutCast<uchar> { __device__ __forceinline__ static uchar from(float v) { return sat_u8(v); } };
+template <> struct OutCast<short> { __device__ __forceinline__ static short from(float v) { return sat_s16(v); } };
+template <> struct OutCast<float> { __device__ __forceinline__ static float from(float v) { return v; } };
+
+// streaming (evict-first) 128-bit global accesses: every pixel is touched once per launch
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
+static inline size_t div_up_sz(size_t a, size_t b) { return (a + b - 1) / b; }
+
+// ---- per-op implementation entry points (defined in the .cu files) -------------------------------------------------
+struct SepTaps {           // up to 33 taps per direction, by value in kernel params
+    float kx[33];
+    float ky[33];
+    int nx, ny, ax, ay;
+};
+
+}  // namespace b200cv

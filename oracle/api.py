@@ -1,0 +1,224 @@
+"""oracle/api.py -- numpy-level access to the two CPU oracles.  TEST INFRASTRUCTURE ONLY.
+
+    Oracle("ref")   the UNMODIFIED reference built by oracle/build_ref.py  (oracle/_ref/libocvref.so, prefix ref_)
+    Oracle("port")  the plain-C restatement in oracle/port/*.c            (oracle/_build/liboracle_port.so, prefix port_)
+
+Both export the same C signatures (see oracle/ref_shim.cpp), so every test can run against either.
+Nothing under opencv_b200/ imports this module.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_LIB = os.path.join(HERE, "_ref", "libocvref.so")
+PORT_LIB = os.path.join(HERE, "_build", "liboracle_port.so")
+
+CV_8U, CV_16S, CV_32F = 0, 3, 5
+_DEPTH = {np.dtype(np.uint8): CV_8U, np.dtype(np.int16): CV_16S, np.dtype(np.float32): CV_32F}
+_NP = {CV_8U: np.uint8, CV_16S: np.int16, CV_32F: np.float32}
+
+vp, sz, dbl = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_double
+
+
+def cvtype(a):
+    cn = 1 if a.ndim == 2 else a.shape[2]
+    return _DEPTH[a.dtype] + ((cn - 1) << 3)
+
+
+def _p(a):
+    return a.ctypes.data_as(vp)
+
+
+def available(kind):
+    return os.path.exists(REF_LIB if kind == "ref" else PORT_LIB)
+
+
+class Oracle:
+    def __init__(self, kind="ref"):
+        self.kind = kind
+        path = REF_LIB if kind == "ref" else PORT_LIB
+        if not os.path.exists(path):
+            raise FileNotFoundError("%s oracle not built: %s" % (kind, path))
+        self.lib = ctypes.CDLL(path)
+        self.pfx = "ref_" if kind == "ref" else "port_"
+
+    def has(self, name):
+        return hasattr(self.lib, self.pfx + name)
+
+    def fn(self, name):
+        return getattr(self.lib, self.pfx + name)
+
+    @staticmethod
+    def _ok(rc, what):
+        if rc != 0:
+            raise RuntimeError("oracle %s failed: %d" % (what, rc))
+
+    # ---- helpers only the real reference has -------------------------------------------------------------
+    def set_num_threads(self, n):
+        return self.fn("set_num_threads")(int(n))
+
+    def num_threads(self):
+        return self.fn("get_num_threads")()
+
+    def rng_fill(self, shape, dtype, seed, lo, hi):
+        a = np.zeros(shape, dtype)
+        h, w = shape[0], shape[1]
+        self._ok(self.fn("rng_fill")(_p(a), sz(a.strides[0]), w, h, cvtype(a), ctypes.c_ulonglong(seed), dbl(lo), dbl(hi)), "rng_fill")
+        return a
+
+    def getGaussianKernel(self, n, sigma, ktype=np.float64):
+        out = np.zeros(n, ktype)
+        self._ok(self.fn("gaussian_kernel")(int(n), dbl(sigma), 6 if ktype == np.float64 else 5, _p(out)), "gaussian_kernel")
+        return out
+
+    def getRotationMatrix2D(self, center, angle, scale):
+        m = np.zeros((2, 3), np.float64)
+        self._ok(self.fn("get_rotation_matrix2d")(dbl(center[0]), dbl(center[1]), dbl(angle), dbl(scale), _p(m)), "rot")
+        return m
+
+    # ---- hot-path ops -----------------------------------------------------------------------------------------
+    def GaussianBlur(self, src, ksize, sigmaX, sigmaY=0, borderType=4):
+        src = np.ascontiguousarray(src)
+        dst = np.empty_like(src)
+        h, w = src.shape[:2]
+        self._ok(self.fn("gaussian_blur")(_p(src), sz(src.strides[0]), _p(dst), sz(dst.strides[0]), w, h, cvtype(src),
+                                          int(ksize[0]), int(ksize[1]), dbl(sigmaX), dbl(sigmaY), int(borderType)), "GaussianBlur")
+        return dst
+
+    def _dst_like(self, src, ddepth):
+        return np.empty(src.shape, _NP[ddepth] if ddepth is not None and ddepth >= 0 else src.dtype)
+
+    def sepFilter2D(self, src, ddepth, kx, ky, anchor=(-1, -1), delta=0.0, borderType=4):
+        src = np.ascontiguousarray(src)
+        dst = self._dst_like(src, ddepth)
+        kx = np.ascontiguousarray(kx, np.float32).reshape(-1)
+        ky = np.ascontiguousarray(ky, np.float32).reshape(-1)
+        h, w = src.shape[:2]
+        self._ok(self.fn("sep_filter2d")(_p(src), sz(src.strides[0]), _p(dst), sz(dst.strides[0]), w, h, cvtype(src),
+                                         -1 if ddepth is None else int(ddepth), _p(kx), len(kx), _p(ky), len(ky),
+                                         int(anchor[0]), int(anchor[1]), dbl(delta), int(borderType)), "sepFilter2D")
+        return dst
+
+    def filter2D(self, src, ddepth, kernel, anchor=(-1, -1), delta=0.0, borderType=4):
+        src = np.ascontiguousarray(src)
+        dst = self._dst_like(src, ddepth)
+        k = np.ascontiguousarray(kernel, np.float32)
+        h, w = src.shape[:2]
+        self._ok(self.fn("filter2d")(_p(src), sz(src.strides[0]), _p(dst), sz(dst.strides[0]), w, h, cvtype(src),
+                                     -1 if ddepth is None else int(ddepth), _p(k), k.shape[1], k.shape[0],
+                                     int(anchor[0]), int(anchor[1]), dbl(delta), int(borderType)), "filter2D")
+        return dst
+
+    def Sobel(self, src, ddepth, dx, dy, ksize=3, scale=1.0, delta=0.0, borderType=4):
+        src = np.ascontiguousarray(src)
+        dst = self._dst_like(src, ddepth)
+        h, w = src.shape[:2]
+        self._ok(self.fn("sobel")(_p(src), sz(src.strides[0]), _p(dst), sz(dst.strides[0]), w, h, cvtype(src),
+                                  -1 if ddepth is None else int(ddepth), int(dx), int(dy), int(ksize), dbl(scale), dbl(delta),
+                                  int(borderType)), "Sobel")
+        return dst
+
+    def resize(self, src, dsize, interpolation=1):
+        src = np.ascontiguousarray(src)
+        dw, dh = dsize
+        dst = np.empty((dh, dw) + src.shape[2:], src.dtype)
+        sh, sw = src.shape[:2]
+        self._ok(self.fn("resize")(_p(src), sz(src.strides[0]), sw, sh, _p(dst), sz(dst.strides[0]), dw, dh, cvtype(src),
+                                   int(interpolation)), "resize")
+        return dst
+
+    def _warp(self, name, src, M, dsize, flags, borderMode, borderValue):
+        src = np.ascontiguousarray(src)
+        dw, dh = dsize
+        dst = np.zeros((dh, dw) + src.shape[2:], src.dtype)
+        sh, sw = src.shape[:2]
+        M = np.ascontiguousarray(M, np.float64)
+        bv = np.zeros(4, np.float64)
+        bv[:len(np.atleast_1d(borderValue))] = np.atleast_1d(borderValue)
+        self._ok(self.fn(name)(_p(src), sz(src.strides[0]), sw, sh, _p(dst), sz(dst.strides[0]), dw, dh, cvtype(src),
+                               _p(M), int(flags), int(borderMode), _p(bv)), name)
+        return dst
+
+    def warpAffine(self, src, M, dsize, flags=1, borderMode=0, borderValue=0):
+        return self._warp("warp_affine", src, M, dsize, flags, borderMode, borderValue)
+
+    def warpPerspective(self, src, M, dsize, flags=1, borderMode=0, borderValue=0):
+        return self._warp("warp_perspective", src, M, dsize, flags, borderMode, borderValue)
+
+    def cvtColor(self, src, code, dcn):
+        src = np.ascontiguousarray(src)
+        h, w = src.shape[:2]
+        dst = np.empty((h, w) if dcn == 1 else (h, w, dcn), src.dtype)
+        self._ok(self.fn("cvt_color")(_p(src), sz(src.strides[0]), _p(dst), sz(dst.strides[0]), w, h, cvtype(src), cvtype(dst),
+                                      int(code)), "cvtColor")
+        return dst
+
+    def matchTemplate(self, image, templ, method):
+        image = np.ascontiguousarray(image)
+        templ = np.ascontiguousarray(templ)
+        ih, iw = image.shape[:2]
+        th, tw = templ.shape[:2]
+        res = np.empty((ih - th + 1, iw - tw + 1), np.float32)
+        self._ok(self.fn("match_template")(_p(image), sz(image.strides[0]), iw, ih, _p(templ), sz(templ.strides[0]), tw, th,
+                                           cvtype(image), _p(res), sz(res.strides[0]), int(method)), "matchTemplate")
+        return res
+
+    def cornerHarris(self, src, blockSize, ksize, k, borderType=4):
+        src = np.ascontiguousarray(src)
+        h, w = src.shape[:2]
+        dst = np.empty((h, w), np.float32)
+        self._ok(self.fn("corner_harris")(_p(src), sz(src.strides[0]), w, h, cvtype(src), _p(dst), sz(dst.strides[0]),
+                                          int(blockSize), int(ksize), dbl(k), int(borderType)), "cornerHarris")
+        return dst
+
+    def cornerMinEigenVal(self, src, blockSize, ksize=3, borderType=4):
+        src = np.ascontiguousarray(src)
+        h, w = src.shape[:2]
+        dst = np.empty((h, w), np.float32)
+        self._ok(self.fn("corner_min_eigen_val")(_p(src), sz(src.strides[0]), w, h, cvtype(src), _p(dst), sz(dst.strides[0]),
+                                                 int(blockSize), int(ksize), int(borderType)), "cornerMinEigenVal")
+        return dst
+
+    def goodFeaturesToTrack(self, src, maxCorners, qualityLevel, minDistance, blockSize=3, gradientSize=3, useHarrisDetector=False,
+                            k=0.04, max_out=100000):
+        src = np.ascontiguousarray(src)
+        h, w = src.shape[:2]
+        pts = np.zeros((max_out, 2), np.float32)
+        q = np.zeros(max_out, np.float32)
+        n = ctypes.c_int(0)
+        self._ok(self.fn("good_features_to_track")(_p(src), sz(src.strides[0]), w, h, cvtype(src), _p(pts), _p(q), int(max_out),
+                                                   ctypes.byref(n), int(maxCorners), dbl(qualityLevel), dbl(minDistance),
+                                                   int(blockSize), int(gradientSize), int(bool(useHarrisDetector)), dbl(k)), "gftt")
+        cnt = min(n.value, max_out)
+        return pts[:cnt].copy(), q[:cnt].copy()
+
+    def sift_pyramid(self, gray, nOctaveLayers=3, sigma=1.6, upscale=True):
+        """returns (gauss list-of-lists [octave][layer], dog list-of-lists)"""
+        gray = np.ascontiguousarray(gray)
+        h, w = gray.shape
+        ge, de, no = sz(0), sz(0), ctypes.c_int(0)
+        f = self.fn("sift_pyramid")
+        self._ok(f(_p(gray), sz(gray.strides[0]), w, h, int(nOctaveLayers), dbl(sigma), int(bool(upscale)), None, ctypes.byref(ge),
+                   None, ctypes.byref(de), ctypes.byref(no), None), "sift_pyramid(query)")
+        G = np.zeros(ge.value, np.float32)
+        D = np.zeros(de.value, np.float32)
+        dims = np.zeros(2 * no.value, np.int32)
+        self._ok(f(_p(gray), sz(gray.strides[0]), w, h, int(nOctaveLayers), dbl(sigma), int(bool(upscale)), _p(G), ctypes.byref(ge),
+                   _p(D), ctypes.byref(de), ctypes.byref(no), _p(dims)), "sift_pyramid")
+        return unpack_pyramid(G, D, dims, no.value, nOctaveLayers)
+
+
+def unpack_pyramid(G, D, dims, n_octaves, n_layers):
+    gauss, dog = [], []
+    go = do = 0
+    for o in range(n_octaves):
+        w, h = int(dims[2 * o]), int(dims[2 * o + 1])
+        gl, dl = [], []
+        for _ in range(n_layers + 3):
+            gl.append(G[go:go + w * h].reshape(h, w)); go += w * h
+        for _ in range(n_layers + 2):
+            dl.append(D[do:do + w * h].reshape(h, w)); do += w * h
+        gauss.append(gl); dog.append(dl)
+    return gauss, dog

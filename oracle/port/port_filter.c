@@ -1,0 +1,256 @@
+/* oracle/port/port_filter.c -- GaussianBlur / sepFilter2D / filter2D / Sobel restated in scalar C.
+ * TEST INFRASTRUCTURE ONLY (see port_common.h).
+ *   cv::GaussianBlur          modules/imgproc/src/smooth.dispatch.cpp:609-826
+ *   fixedSmoothInvoker (u8)   modules/imgproc/src/smooth.simd.hpp:1925-2197  == the evaluator of
+ *                             modules/imgproc/test/test_smooth_bitexact.cpp:40-53
+ *   createSeparableLinearFilter modules/imgproc/src/filter.dispatch.cpp:305-383 (bit-exact int mode :334-362)
+ *   RowFilter / ColumnFilter  modules/imgproc/src/filter.simd.hpp:2386-2447, 2580-2757
+ *   Filter2D                  modules/imgproc/src/filter.simd.hpp:3103-3175
+ *   cv::Sobel                 modules/imgproc/src/deriv.cpp:414-465, getSobelKernels :96-160
+ */
+#include "port_common.h"
+
+static float load_f(const void* row, int depth, int idx)
+{
+    return depth == P_8U ? (float)((const uchar*)row)[idx] : depth == P_16S ? (float)((const short*)row)[idx] : ((const float*)row)[idx];
+}
+
+static void store_f(void* row, int depth, int idx, float v)
+{
+    if (depth == P_8U) ((uchar*)row)[idx] = port_sat_u8f(v);
+    else if (depth == P_16S) ((short*)row)[idx] = port_sat_s16f(v);
+    else ((float*)row)[idx] = v;
+}
+
+/* kernel classification: getKernelType, filter.dispatch.cpp:225-259 */
+enum { KT_SYMM = 1, KT_ASYMM = 2, KT_SMOOTH = 4, KT_INT = 8 };
+static int ktype_of(const float* k, int n, int anchor)
+{
+    int t = KT_SMOOTH | KT_INT;
+    double sum = 0;
+    if (anchor * 2 + 1 == n) t |= KT_SYMM | KT_ASYMM;
+    for (int i = 0; i < n; i++) {
+        double a = k[i], b = k[n - 1 - i];
+        if (a != b) t &= ~KT_SYMM;
+        if (a != -b) t &= ~KT_ASYMM;
+        if (a < 0) t &= ~KT_SMOOTH;
+        if (a != (double)port_round(a)) t &= ~KT_INT;
+        sum += a;
+    }
+    if (fabs(sum - 1) > 1.1920928955078125e-07 * (fabs(sum) + 1)) t &= ~KT_SMOOTH;
+    return t;
+}
+
+static int exact_int_kernel(const float* k, int n, int bits, int* out)
+{
+    double eps = 10 * 1.1920928955078125e-07 * (1 << bits);
+    for (int i = 0; i < n; i++) {
+        double a = (double)k[i] * (1 << bits);
+        out[i] = port_round(a);
+        if (fabs(a - out[i]) > eps) return 0;
+    }
+    return 1;
+}
+
+/* integer separable pass: dst = cast((sum_j ky[j] * sum_i kx[i]*src + delta + round) >> shift) */
+static void sep_int(const uchar* src, size_t sstep, void* dst, size_t dstep, int w, int h, int cn, int ddepth,
+                    const long long* kx, int nx, const long long* ky, int ny, int ax, int ay, long long delta, int shift, int border,
+                    int even_limit)
+{
+    long long rnd = shift ? (1LL << (shift - 1)) : 0;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            for (int c = 0; c < cn; c++) {
+                long long acc = 0;
+                for (int j = 0; j < ny; j++) {
+                    int sy = port_border(y + j - ay, h, border);
+                    if (sy < 0) continue;
+                    const uchar* row = src + (size_t)sy * sstep;
+                    long long line = 0;
+                    for (int i = 0; i < nx; i++) {
+                        int sx = port_border(x + i - ax, w, border);
+                        if (sx >= 0) line += kx[i] * row[sx * cn + c];
+                    }
+                    acc += ky[j] * line;
+                }
+                long long v = (acc + delta + rnd) >> shift;
+                if (x * cn + c < even_limit) {      /* vector body of SymmColumnVec_32s8u rounds the exact value half-to-even */
+                    long long t = acc + delta, q = t >> shift, r = t & ((1LL << shift) - 1), half = 1LL << (shift - 1);
+                    v = q + (r > half || (r == half && (q & 1)));
+                }
+                if (ddepth == P_8U) ((uchar*)((char*)dst + (size_t)y * dstep))[x * cn + c] = (uchar)(v < 0 ? 0 : v > 255 ? 255 : v);
+                else ((short*)((char*)dst + (size_t)y * dstep))[x * cn + c] = (short)(v < -32768 ? -32768 : v > 32767 ? 32767 : v);
+            }
+}
+
+/* float separable pass: rows first (s = 0; s = fma(src, kx[i], s)), then columns starting from delta */
+static void sep_float(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int cn, int sdepth, int ddepth,
+                      const float* kx, int nx, const float* ky, int ny, int ax, int ay, float delta, int border)
+{
+    int we = w * cn;
+    float* mid = (float*)malloc(sizeof(float) * (size_t)we * h);
+    for (int y = 0; y < h; y++) {
+        const void* row = (const char*)src + (size_t)y * sstep;
+        for (int x = 0; x < w; x++)
+            for (int c = 0; c < cn; c++) {
+                float s = 0.f;
+                for (int i = 0; i < nx; i++) {
+                    int sx = port_border(x + i - ax, w, border);
+                    float v = sx < 0 ? 0.f : load_f(row, sdepth, sx * cn + c);
+                    s = fmaf(v, kx[i], s);
+                }
+                mid[(size_t)y * we + x * cn + c] = s;
+            }
+    }
+    for (int y = 0; y < h; y++) {
+        void* drow = (char*)dst + (size_t)y * dstep;
+        for (int e = 0; e < we; e++) {
+            float s = delta;
+            for (int j = 0; j < ny; j++) {
+                int sy = port_border(y + j - ay, h, border);
+                float v = sy < 0 ? 0.f : mid[(size_t)sy * we + e];
+                s = fmaf(v, ky[j], s);
+            }
+            store_f(drow, ddepth, e, s);
+        }
+    }
+    free(mid);
+}
+
+int port_sep_filter_core(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int stype, int ddepth,
+                         const float* kx, int nx, const float* ky, int ny, int ax, int ay, double delta, int border)
+{
+    int sdepth = P_DEPTH(stype), cn = P_CN(stype);
+    if (ddepth < 0) ddepth = sdepth;
+    if (ax < 0) ax = nx / 2;
+    if (ay < 0) ay = ny / 2;
+    border &= ~16;
+    if (sdepth == P_8U && (ddepth == P_8U || ddepth == P_16S)) {
+        int rt = ktype_of(kx, nx, ax), ct = ktype_of(ky, ny, ay);
+        int smooth8 = ddepth == P_8U && rt == (KT_SMOOTH | KT_SYMM) && ct == (KT_SMOOTH | KT_SYMM);
+        int int16 = ddepth == P_16S && (rt & (KT_SYMM | KT_ASYMM)) && (ct & (KT_SYMM | KT_ASYMM)) && (rt & ct & KT_INT);
+        if (smooth8 || int16) {
+            int bits = ddepth == P_8U ? 8 : 0;
+            int ikx[64], iky[64];
+            if (nx <= 64 && ny <= 64 && exact_int_kernel(kx, nx, bits, ikx) && exact_int_kernel(ky, ny, bits, iky)) {
+                long long lkx[64], lky[64];
+                for (int i = 0; i < nx; i++) lkx[i] = ikx[i];
+                for (int i = 0; i < ny; i++) lky[i] = iky[i];
+                double dd = delta * (double)(1 << (2 * bits));
+                long long di = llrint(dd);
+                if (di > 2147483647LL) di = 2147483647LL; if (di < -2147483648LL) di = -2147483648LL;
+                /* SymmColumnVec_32s8u (filter.simd.hpp:1011-1100): the first floor16(w*cn) elements of a row go through a float
+                   vector body that rounds half-to-even; the scalar tail uses FixedPtCastEx (half-up), :2937-2946 */
+                int even_limit = (bits && ny > 1) ? ((w * cn) / 16) * 16 : 0;
+                sep_int((const uchar*)src, sstep, dst, dstep, w, h, cn, ddepth, lkx, nx, lky, ny, ax, ay, di, 2 * bits, border, even_limit);
+                return 0;
+            }
+        }
+    }
+    sep_float(src, sstep, dst, dstep, w, h, cn, sdepth, ddepth, kx, nx, ky, ny, ax, ay, (float)delta, border);
+    return 0;
+}
+
+PORT_API int port_sep_filter2d(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int stype, int ddepth,
+                               const float* kx, int nx, const float* ky, int ny, int ax, int ay, double delta, int border)
+{
+    return port_sep_filter_core(src, sstep, dst, dstep, w, h, stype, ddepth, kx, nx, ky, ny, ax, ay, delta, border);
+}
+
+PORT_API int port_gaussian_blur(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int type,
+                                int kw, int kh, double s1, double s2, int border)
+{
+    int depth = P_DEPTH(type), cn = P_CN(type);
+    int b = border & ~16;
+    if (b != PB_CONSTANT) { if (h == 1) kh = 1; if (w == 1) kw = 1; }
+    if (kw == 1 && kh == 1) {
+        for (int y = 0; y < h; y++) memcpy((char*)dst + (size_t)y * dstep, (const char*)src + (size_t)y * sstep, (size_t)w * cn * port_esz(depth));
+        return 0;
+    }
+    if (s2 <= 0) s2 = s1;
+    if (kw <= 0 && s1 > 0) kw = port_round(s1 * (depth == P_8U ? 3 : 4) * 2 + 1) | 1;
+    if (kh <= 0 && s2 > 0) kh = port_round(s2 * (depth == P_8U ? 3 : 4) * 2 + 1) | 1;
+    if (kw <= 0 || kh <= 0 || !(kw & 1) || !(kh & 1) || kw > 255 || kh > 255) return -1;
+    if (s1 < 0) s1 = 0; if (s2 < 0) s2 = 0;
+    if (depth == P_8U) {
+        long long fx[256], fy[256];
+        port_gaussian_taps_fixed(kw, s1, 8, fx);
+        port_gaussian_taps_fixed(kh, s2, 8, fy);
+        sep_int((const uchar*)src, sstep, dst, dstep, w, h, cn, P_8U, fx, kw, fy, kh, kw / 2, kh / 2, 0, 16, b, 0);
+        return 0;
+    }
+    double dx[256], dy[256];
+    float kx[256], ky[256];
+    port_gaussian_taps(kw, s1, dx);
+    port_gaussian_taps(kh, s2, dy);
+    for (int i = 0; i < kw; i++) kx[i] = (float)dx[i];
+    for (int i = 0; i < kh; i++) ky[i] = (float)dy[i];
+    return port_sep_filter_core(src, sstep, dst, dstep, w, h, type, depth, kx, kw, ky, kh, kw / 2, kh / 2, 0.0, b);
+}
+
+PORT_API int port_filter2d(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int stype, int ddepth,
+                           const float* k, int kw, int kh, int ax, int ay, double delta, int border)
+{
+    int sdepth = P_DEPTH(stype), cn = P_CN(stype);
+    if (ddepth < 0) ddepth = sdepth;
+    if (ax < 0) ax = kw / 2;
+    if (ay < 0) ay = kh / 2;
+    border &= ~16;
+    for (int y = 0; y < h; y++) {
+        void* drow = (char*)dst + (size_t)y * dstep;
+        for (int x = 0; x < w; x++)
+            for (int c = 0; c < cn; c++) {
+                float s = (float)delta;
+                for (int j = 0; j < kh; j++) {
+                    int sy = port_border(y + j - ay, h, border);
+                    const void* row = sy < 0 ? NULL : (const char*)src + (size_t)sy * sstep;
+                    for (int i = 0; i < kw; i++) {
+                        float kv = k[j * kw + i];
+                        if (kv == 0) continue;
+                        int sx = port_border(x + i - ax, w, border);
+                        float v = (row && sx >= 0) ? load_f(row, sdepth, sx * cn + c) : 0.f;
+                        s = fmaf(kv, v, s);
+                    }
+                }
+                store_f(drow, ddepth, x * cn + c, s);
+            }
+    }
+    return 0;
+}
+
+/* (1+z)^(n-d-1) (z-1)^d */
+static void sobel_taps_1d(int n, int d, float* out)
+{
+    long long p[40] = {1};
+    int len = 1;
+    if (n > 1) {
+        for (int i = 0; i < n - d - 1; i++) { p[len] = 0; for (int j = len; j > 0; j--) p[j] += p[j - 1]; len++; }
+        for (int i = 0; i < d; i++) { p[len] = 0; for (int j = len; j > 0; j--) p[j] = p[j - 1] - p[j]; p[0] = -p[0]; len++; }
+    }
+    for (int i = 0; i < len; i++) out[i] = (float)p[i];
+}
+
+PORT_API int port_sobel(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int stype, int ddepth,
+                        int dx, int dy, int ksize, double scale, double delta, int border)
+{
+    float kx[40], ky[40];
+    int nx, ny;
+    if (ksize == -1) {
+        static const float d[] = {-1, 0, 1}, s[] = {3, 10, 3};
+        memcpy(kx, dx ? d : s, sizeof(d)); memcpy(ky, dy ? d : s, sizeof(d));
+        nx = ny = 3;
+    } else {
+        nx = ny = ksize;
+        if (nx == 1 && dx > 0) nx = 3;
+        if (ny == 1 && dy > 0) ny = 3;
+        sobel_taps_1d(nx, dx, kx);
+        sobel_taps_1d(ny, dy, ky);
+    }
+    if (scale != 1) {
+        float fs = (float)scale;
+        float* k = dx == 0 ? kx : ky;
+        int n = dx == 0 ? nx : ny;
+        for (int i = 0; i < n; i++) k[i] = k[i] * fs;
+    }
+    return port_sep_filter_core(src, sstep, dst, dstep, w, h, stype, ddepth, kx, nx, ky, ny, -1, -1, delta, border);
+}

@@ -1,0 +1,117 @@
+"""GPU parity: GaussianBlur / sepFilter2D / filter2D / Sobel through the device C ABI vs the CPU oracle.
+
+Tolerances
+  u8 GaussianBlur, u8 sepFilter2D (8-bit-exact symmetric taps), u8->s16 integer kernels: BIT-EXACT
+  f32 paths: |d| <= 1e-5 * max(1, |ref|) * taps-scale  (reference's own bar: test_filter.cpp:826-830 uses 1e-5 relative for GaussianBlur f32)
+  filter2D u8: <= 1 LSB (the CPU uses a DFT for >= 130 taps; its own test allows 2, test_filter.cpp:420-425)
+"""
+import numpy as np
+import pytest
+
+from util import assert_close, assert_exact, cpu, gpu, rand_u8
+
+pytestmark = pytest.mark.gpu
+
+BORDERS = [0, 1, 2, 3, 4]
+
+
+@pytest.mark.parametrize("shape", [(97, 131, 1), (61, 77, 3), (33, 300, 1), (270, 520, 1), (5, 7, 1), (64, 64, 4)])
+@pytest.mark.parametrize("ks", [(3, 0), (5, 0), (7, 0), (9, 0), (5, 1.1), (11, 2.0), (15, 0), (21, 3.3), (31, 5.0), (0, 1.3)])
+def test_gaussian_u8_bitexact(cvb, oracle, rng, shape, ks):
+    h, w, cn = shape
+    img = rand_u8(rng, h, w, cn)
+    k, s = ks
+    for b in BORDERS:
+        want = oracle.GaussianBlur(img, (k, k), s, s, b)
+        got = cpu(cvb.GaussianBlur(gpu(img), (k, k), s, s, b))
+        assert_exact(got, want, "GaussianBlur u8 %s k=%d s=%g border=%d" % (shape, k, s, b))
+
+
+def test_gaussian_u8_rect_kernel_and_batch(cvb, oracle, rng):
+    imgs = np.stack([rand_u8(rng, 120, 333) for _ in range(3)])[..., None]
+    got = cpu(cvb.GaussianBlur(gpu(imgs), (7, 3), 1.2, 0.7, 4))
+    for i in range(3):
+        want = oracle.GaussianBlur(imgs[i, :, :, 0], (7, 3), 1.2, 0.7, 4)
+        assert_exact(got[i, :, :, 0], want, "batch frame %d" % i)
+
+
+def test_gaussian_u8_1080p_c3(cvb, ref, rng):
+    """BASELINE config C1: GaussianBlur 5x5 on one 1920x1080 CV_8UC3 frame"""
+    img = rand_u8(rng, 1080, 1920, 3)
+    assert_exact(cpu(cvb.GaussianBlur(gpu(img), (5, 5), 0)), ref.GaussianBlur(img, (5, 5), 0), "C1")
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 13, 15, 21, 31])
+def test_gaussian_u8_4k(cvb, ref, rng, k):
+    """BASELINE config C2 (u8 leg) at full size against the real reference"""
+    img = rand_u8(rng, 2160, 3840)
+    assert_exact(cpu(cvb.GaussianBlur(gpu(img), (k, k), 0)), ref.GaussianBlur(img, (k, k), 0), "4K u8 k=%d" % k)
+
+
+@pytest.mark.parametrize("shape", [(97, 131, 1), (61, 77, 3), (270, 520, 1)])
+@pytest.mark.parametrize("ks", [(3, 0), (5, 0), (7, 1.5), (11, 2.0), (13, 0), (17, 2.5), (27, 3.09), (31, 5.0), (0, 1.6)])
+def test_gaussian_f32(cvb, oracle, rng, shape, ks):
+    h, w, cn = shape
+    img = rand_u8(rng, h, w, cn).astype(np.float32)
+    k, s = ks
+    for b in (0, 1, 2, 4):
+        want = oracle.GaussianBlur(img, (k, k), s, s, b)
+        got = cpu(cvb.GaussianBlur(gpu(img), (k, k), s, s, b))
+        assert_close(got, want, atol=1e-4, rtol=1e-5, what="GaussianBlur f32 %s k=%d border=%d" % (shape, k, b))
+
+
+@pytest.mark.parametrize("k", [3, 9, 31])
+def test_gaussian_f32_4k(cvb, ref, rng, k):
+    img = rand_u8(rng, 2160, 3840).astype(np.float32)
+    assert_close(cpu(cvb.GaussianBlur(gpu(img), (k, k), 0)), ref.GaussianBlur(img, (k, k), 0), atol=1e-4, rtol=1e-5, what="4K f32 k=%d" % k)
+
+
+def test_sepfilter_variants(cvb, oracle, rng):
+    img1 = rand_u8(rng, 97, 131); img3 = rand_u8(rng, 61, 77, 3); f1 = img1.astype(np.float32)
+    kx = rng.random(5).astype(np.float32); ky = rng.random(7).astype(np.float32)
+    CV_8U, CV_16S, CV_32F = 0, 3, 5
+    assert_close(cpu(cvb.sepFilter2D(gpu(f1), -1, kx, ky)), oracle.sepFilter2D(f1, -1, kx, ky), atol=2e-3, rtol=1e-5, what="sep f32")
+    # u8 -> u8 float path (non-symmetric taps): saturate_cast rounding, allow 1 LSB at exact .5 ties of differently-rounded sums
+    a = cpu(cvb.sepFilter2D(gpu(img1), -1, kx / kx.sum(), ky / ky.sum())); b = oracle.sepFilter2D(img1, -1, kx / kx.sum(), ky / ky.sum())
+    assert_close(a, b, atol=1, what="sep u8 float path")
+    # u8 -> u8 bit-exact mode (symmetric, 8-bit exact) incl. delta and the half-even/half-up split of the reference
+    for img in (img1, img3):
+        for delta in (0, 3, -2.5):
+            a = cpu(cvb.sepFilter2D(gpu(img), -1, [.25, .5, .25], [.125, .75, .125], delta=delta))
+            b = oracle.sepFilter2D(img, -1, [.25, .5, .25], [.125, .75, .125], delta=delta)
+            assert_exact(a, b, "sep u8 bit-exact mode delta=%g %s" % (delta, img.shape))
+    assert_close(cpu(cvb.sepFilter2D(gpu(img1), CV_32F, kx, ky, delta=1.5, borderType=1)),
+                 oracle.sepFilter2D(img1, CV_32F, kx, ky, delta=1.5, borderType=1), atol=2e-3, rtol=1e-5, what="sep u8->f32")
+    # anchors / even sizes go to the generic kernel
+    kx4 = rng.random(4).astype(np.float32)
+    assert_close(cpu(cvb.sepFilter2D(gpu(f1), -1, kx4, ky, anchor=(1, 5))), oracle.sepFilter2D(f1, -1, kx4, ky, anchor=(1, 5)),
+                 atol=2e-3, rtol=1e-5, what="sep anchor")
+
+
+@pytest.mark.parametrize("ksize", [1, 3, 5, 7])
+def test_sobel(cvb, oracle, rng, ksize):
+    img = rand_u8(rng, 97, 131)
+    for dx, dy in ((1, 0), (0, 1), (1, 1), (2, 0)):
+        if ksize == 1 and dx + dy > 1:
+            continue
+        assert_exact(cpu(cvb.Sobel(gpu(img), 3, dx, dy, ksize)), oracle.Sobel(img, 3, dx, dy, ksize), "Sobel s16 k%d %d%d" % (ksize, dx, dy))
+        a = cpu(cvb.Sobel(gpu(img), 5, dx, dy, ksize, scale=1 / 2040.)); b = oracle.Sobel(img, 5, dx, dy, ksize, scale=1 / 2040.)
+        assert_close(a, b, atol=1e-6, rtol=2e-5, what="Sobel f32 k%d %d%d" % (ksize, dx, dy))
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 13, 15, 21, 31])
+def test_filter2d(cvb, oracle, rng, k):
+    img = rand_u8(rng, 97, 131); f = img.astype(np.float32)
+    ker = rng.random((k, k)).astype(np.float32); ker /= ker.sum()
+    for b in (0, 1, 2, 4):
+        assert_close(cpu(cvb.filter2D(gpu(img), -1, ker, borderType=b)), oracle.filter2D(img, -1, ker, borderType=b), atol=1, what="filter2D u8 k=%d b=%d" % (k, b))
+        assert_close(cpu(cvb.filter2D(gpu(f), -1, ker, borderType=b)), oracle.filter2D(f, -1, ker, borderType=b), atol=5e-4, rtol=1e-5,
+                     what="filter2D f32 k=%d b=%d" % (k, b))
+
+
+def test_filter2d_generic(cvb, oracle, rng):
+    img3 = rand_u8(rng, 61, 77, 3)
+    ker = rng.random((4, 6)).astype(np.float32) - 0.3
+    assert_close(cpu(cvb.filter2D(gpu(img3), -1, ker, anchor=(1, 2), delta=7)), oracle.filter2D(img3, -1, ker, anchor=(1, 2), delta=7), atol=1,
+                 what="filter2D generic")
+    assert_close(cpu(cvb.filter2D(gpu(img3), 5, ker)), oracle.filter2D(img3, 5, ker), atol=1e-3, rtol=1e-5, what="filter2D u8->f32")
