@@ -253,3 +253,40 @@ def getGaussianKernelFixed8(ksize, sigma):
     _check(lib().b200cv_get_gaussian_kernel_fixed8(int(ksize), ctypes.c_double(sigma), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint16))),
            "getGaussianKernelFixed8")
     return out
+
+
+def resize(src, dsize, fx=0, fy=0, interpolation=INTER_LINEAR, dst=None, stream=None):
+    """cv::resize (imgproc.hpp:2422).  dsize=(w,h); or dsize=None and fx, fy."""
+    if not _is_torch(src):
+        from . import hal
+        return hal.resize(src, dsize, fx, fy, interpolation)
+    m = describe(src)
+    if not dsize or dsize[0] <= 0:
+        dsize = (int(round(m.cols * fx)), int(round(m.rows * fy)))    # saturate_cast<int>(cols*fx): round-half-even like Python's round
+    dst = dst if dst is not None else _new(src, size=(int(dsize[0]), int(dsize[1])))
+    ms, md = _pair(src, dst)
+    _check(lib().b200cv_resize(ctypes.byref(ms), ctypes.byref(md), int(interpolation), _stream_ptr(stream)), "resize")
+    return dst
+
+
+def _warp(fn, name, src, M, dsize, flags, borderMode, borderValue, dst, stream, n):
+    dst = dst if dst is not None else _new(src, size=(int(dsize[0]), int(dsize[1])))
+    ms, md = _pair(src, dst)
+    m, pm = _f64(M)
+    assert len(m) == n
+    bv = np.zeros(4, np.float64)
+    b = np.atleast_1d(np.asarray(borderValue, np.float64))
+    bv[:len(b)] = b
+    _check(fn(ctypes.byref(ms), ctypes.byref(md), pm, int(flags), int(borderMode), bv.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+              _stream_ptr(stream)), name)
+    return dst
+
+
+def warpAffine(src, M, dsize, flags=INTER_LINEAR, borderMode=BORDER_CONSTANT, borderValue=0, dst=None, stream=None):
+    """cv::warpAffine (imgproc.hpp:2450)"""
+    return _warp(lib().b200cv_warp_affine, "warpAffine", src, M, dsize, flags, borderMode, borderValue, dst, stream, 6)
+
+
+def warpPerspective(src, M, dsize, flags=INTER_LINEAR, borderMode=BORDER_CONSTANT, borderValue=0, dst=None, stream=None):
+    """cv::warpPerspective (imgproc.hpp:2482)"""
+    return _warp(lib().b200cv_warp_perspective, "warpPerspective", src, M, dsize, flags, borderMode, borderValue, dst, stream, 9)

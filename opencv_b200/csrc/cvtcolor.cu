@@ -36,20 +36,22 @@ struct OpGray2BGR {   // 1 -> 3|4
     }
 };
 
+// NOTE: every channel index below is a compile-time constant (template parameters): run-time indices into the
+// per-pixel register arrays would demote them to local memory.
+template <int SWAP, int SRC_ALPHA>
 struct OpBGR2BGR {    // 3|4 -> 3|4, optional R<->B swap (cvtBGRtoBGR)
-    int swap;
-    bool src_has_alpha;
     __device__ __forceinline__ void px(const uchar* s, uchar* d) const
     {
-        d[0] = s[swap ? 2 : 0];
+        d[0] = s[SWAP ? 2 : 0];
         d[1] = s[1];
-        d[2] = s[swap ? 0 : 2];
-        d[3] = src_has_alpha ? s[3] : (uchar)255;
+        d[2] = s[SWAP ? 0 : 2];
+        d[3] = SRC_ALPHA ? s[3] : (uchar)255;
     }
 };
 
+template <int bidx, int yuvOrder>
 struct OpBGR2YCrCb {  // 3|4 -> 3
-    int c0, c1, c2, c3, c4, bidx, yuvOrder;
+    int c0, c1, c2, c3, c4;
     __device__ __forceinline__ void px(const uchar* s, uchar* d) const
     {
         const int delta = 128 * (1 << 14);
@@ -62,8 +64,9 @@ struct OpBGR2YCrCb {  // 3|4 -> 3
     }
 };
 
+template <int bidx, int yuvOrder>
 struct OpYCrCb2BGR {  // 3 -> 3|4
-    int c0, c1, c2, c3, bidx, yuvOrder;
+    int c0, c1, c2, c3;
     __device__ __forceinline__ void px(const uchar* s, uchar* d) const
     {
         int Y = s[0], Cr = s[1 + yuvOrder], Cb = s[2 - yuvOrder];
@@ -82,8 +85,9 @@ __device__ int g_sdiv_table[256];
 __device__ int g_hdiv_table180[256];
 __device__ int g_hdiv_table256[256];
 
+template <int bidx>
 struct OpBGR2HSV {    // 3|4 -> 3
-    int bidx, hrange;
+    int hrange;
     const int* sdiv;   // shared-memory copies
     const int* hdiv;
     __device__ __forceinline__ void px(const uchar* s, uchar* d) const
@@ -104,8 +108,8 @@ struct OpBGR2HSV {    // 3|4 -> 3
     }
 };
 
+template <int bidx>
 struct OpHSV2BGR {    // 3 -> 3|4 ; float arithmetic mirroring the reference's vector body
-    int bidx;
     float hscale;
     int trunc_cols;     // pixels x < trunc_cols are truncated after scaling (vector body), the rest rounded (scalar tail)
     __device__ __forceinline__ void px_at(const uchar* s, uchar* d, int x) const
@@ -123,14 +127,9 @@ struct OpHSV2BGR {    // 3 -> 3|4 ; float arithmetic mirroring the reference's v
         float sec = truncf(__fmul_rn(pre, 1.0f / 6.0f));
         int sector = (int)__fsub_rn(pre, __fmul_rn(sec, 6.0f));
         // sector_data rows {b,g,r} = {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}
-        switch (sector) {
-        case 0: b = tab1; g = tab3; r = tab0; break;
-        case 1: b = tab1; g = tab0; r = tab2; break;
-        case 2: b = tab3; g = tab0; r = tab1; break;
-        case 3: b = tab0; g = tab2; r = tab1; break;
-        case 4: b = tab0; g = tab1; r = tab3; break;
-        default: b = tab2; g = tab1; r = tab0; break;
-        }
+        b = sector <= 1 ? tab1 : sector == 2 ? tab3 : sector <= 4 ? tab0 : tab2;
+        g = sector == 0 ? tab3 : sector <= 2 ? tab0 : sector == 3 ? tab2 : tab1;
+        r = sector == 0 ? tab0 : sector == 1 ? tab2 : sector <= 3 ? tab1 : sector == 4 ? tab3 : tab0;
         b = __fmul_rn(b, 255.0f); g = __fmul_rn(g, 255.0f); r = __fmul_rn(r, 255.0f);
         uchar ub, ug, ur;
         if (x < trunc_cols) {
@@ -268,11 +267,14 @@ extern "C" int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int 
         int want_s = (code == 0 || code == 2 || code == 4) ? 3 : 4;
         int want_d = (code == 1 || code == 3 || code == 4) ? 3 : 4;
         NEED(scn == want_s, dcn == want_d);
-        OpBGR2BGR op{code >= 2, scn == 4};
-        if (scn == 3 && dcn == 3) return launch_cvt<3, 3>(s, d, op, st);
-        if (scn == 3 && dcn == 4) return launch_cvt<3, 4>(s, d, op, st);
-        if (scn == 4 && dcn == 3) return launch_cvt<4, 3>(s, d, op, st);
-        return launch_cvt<4, 4>(s, d, op, st);
+        switch (code) {
+        case 0: return launch_cvt<3, 4>(s, d, OpBGR2BGR<0, 0>(), st);
+        case 1: return launch_cvt<4, 3>(s, d, OpBGR2BGR<0, 1>(), st);
+        case 2: return launch_cvt<3, 4>(s, d, OpBGR2BGR<1, 0>(), st);
+        case 3: return launch_cvt<4, 3>(s, d, OpBGR2BGR<1, 1>(), st);
+        case 4: return launch_cvt<3, 3>(s, d, OpBGR2BGR<1, 0>(), st);
+        default: return launch_cvt<4, 4>(s, d, OpBGR2BGR<1, 1>(), st);
+        }
     }
     case 6: case 7: case 10: case 11: {   // BGR2GRAY RGB2GRAY BGRA2GRAY RGBA2GRAY
         NEED(scn == ((code == 6 || code == 7) ? 3 : 4), dcn == 1);
@@ -292,39 +294,48 @@ extern "C" int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int 
         NEED(scn == 3 || scn == 4, dcn == 3);
         bool isCrCb = (code == 36 || code == 37);
         int bidx = (code == 36 || code == 82) ? 0 : 2;
-        OpBGR2YCrCb op;
         int c[5] = {4899, 9617, 1868, isCrCb ? 11682 : 14369, isCrCb ? 9241 : 8061};
         if (bidx == 0) { int t = c[0]; c[0] = c[2]; c[2] = t; }
-        op.c0 = c[0]; op.c1 = c[1]; op.c2 = c[2]; op.c3 = c[3]; op.c4 = c[4];
-        op.bidx = bidx; op.yuvOrder = !isCrCb;
-        return scn == 3 ? launch_cvt<3, 3>(s, d, op, st) : launch_cvt<4, 3>(s, d, op, st);
+#define GO(B, Y) do { OpBGR2YCrCb<B, Y> op; op.c0 = c[0]; op.c1 = c[1]; op.c2 = c[2]; op.c3 = c[3]; op.c4 = c[4]; \
+                      return scn == 3 ? launch_cvt<3, 3>(s, d, op, st) : launch_cvt<4, 3>(s, d, op, st); } while (0)
+        if (bidx == 0 && isCrCb) GO(0, 0);
+        if (bidx == 0) GO(0, 1);
+        if (isCrCb) GO(2, 0);
+        GO(2, 1);
+#undef GO
     }
     case 38: case 39: case 84: case 85: {   // YCrCb2BGR YCrCb2RGB YUV2BGR YUV2RGB
         NEED(scn == 3, dcn == 3 || dcn == 4);
         bool isCrCb = (code == 38 || code == 39);
-        OpYCrCb2BGR op;
-        op.c0 = isCrCb ? 22987 : 18678; op.c1 = isCrCb ? -11698 : -9519;
-        op.c2 = isCrCb ? -5636 : -6472; op.c3 = isCrCb ? 29049 : 33292;
-        op.bidx = (code == 38 || code == 84) ? 0 : 2; op.yuvOrder = !isCrCb;
-        return dcn == 3 ? launch_cvt<3, 3>(s, d, op, st) : launch_cvt<3, 4>(s, d, op, st);
+        int bidx = (code == 38 || code == 84) ? 0 : 2;
+#define GO(B, Y) do { OpYCrCb2BGR<B, Y> op; op.c0 = isCrCb ? 22987 : 18678; op.c1 = isCrCb ? -11698 : -9519; \
+                      op.c2 = isCrCb ? -5636 : -6472; op.c3 = isCrCb ? 29049 : 33292; \
+                      return dcn == 3 ? launch_cvt<3, 3>(s, d, op, st) : launch_cvt<3, 4>(s, d, op, st); } while (0)
+        if (bidx == 0 && isCrCb) GO(0, 0);
+        if (bidx == 0) GO(0, 1);
+        if (isCrCb) GO(2, 0);
+        GO(2, 1);
+#undef GO
     }
     case 40: case 41: case 66: case 67: {   // BGR2HSV RGB2HSV BGR2HSV_FULL RGB2HSV_FULL
         NEED(scn == 3 || scn == 4, dcn == 3);
         if ((rc = ensure_hsv_tables())) return rc;
-        OpBGR2HSV op;
-        op.bidx = (code == 40 || code == 66) ? 0 : 2;
-        op.hrange = (code == 40 || code == 41) ? 180 : 256;
-        op.sdiv = op.hdiv = nullptr;
-        return scn == 3 ? launch_cvt<3, 3, OpBGR2HSV, false, true>(s, d, op, st)
-                        : launch_cvt<4, 3, OpBGR2HSV, false, true>(s, d, op, st);
+        int hrange = (code == 40 || code == 41) ? 180 : 256;
+#define GO(B) do { OpBGR2HSV<B> op; op.hrange = hrange; op.sdiv = op.hdiv = nullptr; \
+                   return scn == 3 ? launch_cvt<3, 3, OpBGR2HSV<B>, false, true>(s, d, op, st) \
+                                   : launch_cvt<4, 3, OpBGR2HSV<B>, false, true>(s, d, op, st); } while (0)
+        if (code == 40 || code == 66) GO(0);
+        GO(2);
+#undef GO
     }
     case 54: case 55: case 70: case 71: {   // HSV2BGR HSV2RGB HSV2BGR_FULL HSV2RGB_FULL
         NEED(scn == 3, dcn == 3 || dcn == 4);
-        OpHSV2BGR op;
-        op.bidx = (code == 54 || code == 70) ? 0 : 2;
-        op.hscale = 6.0f / ((code == 54 || code == 55) ? 180 : 255);   // inverse _FULL uses 255 (color_hsv.simd.hpp:1302)
-        op.trunc_cols = hsv_trunc_cols(src->cols);
-        return dcn == 3 ? launch_cvt<3, 3, OpHSV2BGR, true>(s, d, op, st) : launch_cvt<3, 4, OpHSV2BGR, true>(s, d, op, st);
+        float hscale = 6.0f / ((code == 54 || code == 55) ? 180 : 255);   // inverse _FULL uses 255 (color_hsv.simd.hpp:1302)
+#define GO(B) do { OpHSV2BGR<B> op; op.hscale = hscale; op.trunc_cols = hsv_trunc_cols(src->cols); \
+                   return dcn == 3 ? launch_cvt<3, 3, OpHSV2BGR<B>, true>(s, d, op, st) : launch_cvt<3, 4, OpHSV2BGR<B>, true>(s, d, op, st); } while (0)
+        if (code == 54 || code == 70) GO(0);
+        GO(2);
+#undef GO
     }
     default:
         return B200CV_NOT_IMPLEMENTED;

@@ -133,3 +133,69 @@ int gaussian_auto_ksize(double sigma, bool is_u8)
 }
 
 }  // namespace b200cv
+
+// ---- cv::remap interpolation tables (reference behaviour: initInterTab2D, modules/imgproc/src/imgwarp.cpp:213-287) ----
+// 32 x 32 sub-pixel positions; entry (iy*32+ix) holds the outer product of the 1-D tap vectors for fy=iy/32, fx=ix/32.
+// Fixed-point version: taps scaled by 2^15 and rounded, then the rounding residue of the whole ksize x ksize block is
+// pushed into the largest (residue < 0) or smallest (residue > 0) of the four central taps so that the block sums to 2^15.
+namespace b200cv {
+
+static void cubic_taps(float x, float* c)
+{
+    const float A = -0.75f;
+    c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+    c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+    c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+static void inter_tab_2d(int ksize, std::vector<float>& ftab, std::vector<short>& itab)
+{
+    const int N = 32;
+    std::vector<float> t1(N * ksize);
+    const float step = 1.f / N;
+    for (int i = 0; i < N; i++) {
+        float x = i * step;
+        if (ksize == 2) { t1[i * 2] = 1.f - x; t1[i * 2 + 1] = x; }
+        else cubic_taps(x, &t1[i * 4]);
+    }
+    const int kk = ksize * ksize, c0 = ksize / 2;
+    ftab.assign((size_t)N * N * kk, 0.f);
+    itab.assign((size_t)N * N * kk, 0);
+    for (int iy = 0; iy < N; iy++)
+        for (int ix = 0; ix < N; ix++) {
+            float* f = &ftab[(size_t)(iy * N + ix) * kk];
+            short* q = &itab[(size_t)(iy * N + ix) * kk];
+            int total = 0;
+            for (int a = 0; a < ksize; a++)
+                for (int b = 0; b < ksize; b++) {
+                    float v = t1[iy * ksize + a] * t1[ix * ksize + b];
+                    f[a * ksize + b] = v;
+                    long r = lrintf(v * 32768.f);
+                    r = r < -32768 ? -32768 : r > 32767 ? 32767 : r;
+                    q[a * ksize + b] = (short)r;
+                    total += (int)r;
+                }
+            int residue = total - 32768;
+            if (residue != 0 && ksize == 2) {
+                // 2x2 block: the reference's scan starts at the last tap and only ever meets zeros beyond the block,
+                // so the residue (only -1 at the all-integer position, where 32768 saturates to 32767) lands on tap 3
+                q[3] = (short)(q[3] - residue);
+            } else if (residue != 0) {
+                int lo = c0 * ksize + c0, hi = lo;          // scan taps (2..3, 2..3) in row-major order
+                for (int a = c0; a < c0 + 2; a++)
+                    for (int b = c0; b < c0 + 2; b++) {
+                        int idx = a * ksize + b;
+                        if (q[idx] < q[lo]) lo = idx;
+                        else if (q[idx] > q[hi]) hi = idx;
+                    }
+                int tgt = residue < 0 ? hi : lo;
+                q[tgt] = (short)(q[tgt] - residue);
+            }
+        }
+}
+
+void bilinear_tab(std::vector<float>& f, std::vector<short>& i) { inter_tab_2d(2, f, i); }
+void bicubic_tab(std::vector<float>& f, std::vector<short>& i) { inter_tab_2d(4, f, i); }
+
+}  // namespace b200cv

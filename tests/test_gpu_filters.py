@@ -96,7 +96,7 @@ def test_sobel(cvb, oracle, rng, ksize):
             continue
         assert_exact(cpu(cvb.Sobel(gpu(img), 3, dx, dy, ksize)), oracle.Sobel(img, 3, dx, dy, ksize), "Sobel s16 k%d %d%d" % (ksize, dx, dy))
         a = cpu(cvb.Sobel(gpu(img), 5, dx, dy, ksize, scale=1 / 2040.)); b = oracle.Sobel(img, 5, dx, dy, ksize, scale=1 / 2040.)
-        assert_close(a, b, atol=1e-6, rtol=2e-5, what="Sobel f32 k%d %d%d" % (ksize, dx, dy))
+        assert_close(a, b, atol=1e-4, rtol=2e-5, what="Sobel f32 k%d %d%d" % (ksize, dx, dy))
 
 
 @pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 13, 15, 21, 31])

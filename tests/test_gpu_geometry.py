@@ -1,0 +1,123 @@
+"""GPU parity: resize / warpAffine / warpPerspective through the device C ABI vs the CPU oracle.
+
+Bars (the reference's own strict test allows |d| <= 1 for LINEAR/CUBIC, test_imgwarp_strict.cpp:231-243):
+  resize NEAREST, LINEAR u8, AREA 2x2 u8, CUBIC u8 ......... BIT-EXACT (the SSE vector-body / scalar-tail split of the
+                                                             reference's u8 CUBIC column pass is reproduced)
+  warp* u8 (NEAREST/LINEAR/CUBIC) .......................... BIT-EXACT (fixed-point coordinates + 2^15 tap tables)
+  f32 ...................................................... |d| <= 1e-4 (values 0..255): same operation order, fp32
+"""
+import numpy as np
+import pytest
+
+import opencv_b200 as C
+from util import assert_close, assert_exact, cpu, gpu, rand_u8
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [((97, 131), (61, 77)), ((64, 48), (128, 96)), ((120, 160), (60, 80)), ((33, 300), (100, 41)), ((50, 50), (75, 33)), ((7, 9), (31, 45))]
+
+
+@pytest.mark.parametrize("ssz,dsz", SIZES)
+@pytest.mark.parametrize("cn", [1, 3, 4])
+@pytest.mark.parametrize("interp", [C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC])
+def test_resize_u8(cvb, oracle, rng, ssz, dsz, cn, interp):
+    img = rand_u8(rng, ssz[0], ssz[1], cn)
+    want = oracle.resize(img, (dsz[1], dsz[0]), interp)
+    got = cpu(cvb.resize(gpu(img), (dsz[1], dsz[0]), interpolation=interp))
+    assert_exact(got, want, "resize u8 %s->%s cn=%d interp=%d" % (ssz, dsz, cn, interp))
+
+
+@pytest.mark.parametrize("ssz,dsz", SIZES)
+@pytest.mark.parametrize("cn", [1, 3])
+@pytest.mark.parametrize("interp", [C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC])
+def test_resize_f32(cvb, oracle, rng, ssz, dsz, cn, interp):
+    img = rand_u8(rng, ssz[0], ssz[1], cn).astype(np.float32)
+    want = oracle.resize(img, (dsz[1], dsz[0]), interp)
+    got = cpu(cvb.resize(gpu(img), (dsz[1], dsz[0]), interpolation=interp))
+    assert_close(got, want, atol=1e-4, rtol=1e-6, what="resize f32 %s->%s cn=%d interp=%d" % (ssz, dsz, cn, interp))
+
+
+@pytest.mark.parametrize("interp", [C.INTER_LINEAR, C.INTER_AREA])
+def test_resize_half_area(cvb, oracle, rng, interp):
+    for cn in (1, 3, 4):
+        img = rand_u8(rng, 122, 250, cn)
+        assert_exact(cpu(cvb.resize(gpu(img), (125, 61), interpolation=interp)), oracle.resize(img, (125, 61), interp), "half u8 cn=%d" % cn)
+        f = img.astype(np.float32)
+        assert_close(cpu(cvb.resize(gpu(f), (125, 61), interpolation=interp)), oracle.resize(f, (125, 61), interp), atol=1e-4, what="half f32 cn=%d" % cn)
+
+
+@pytest.mark.parametrize("dsize,interp", [((3840, 2160), C.INTER_NEAREST), ((3840, 2160), C.INTER_LINEAR), ((5120, 2880), C.INTER_LINEAR),
+                                          ((5120, 2880), C.INTER_CUBIC), ((5120, 2880), C.INTER_NEAREST)])
+def test_resize_8k(cvb, ref, rng, dsize, interp):
+    """BASELINE config C3 (resize leg): 7680x4320 8UC3 source"""
+    img = rand_u8(rng, 4320, 7680, 3)
+    assert_exact(cpu(cvb.resize(gpu(img), dsize, interpolation=interp)), ref.resize(img, dsize, interp), "8K -> %s interp %d" % (dsize, interp))
+
+
+def test_resize_4k_to_8k(cvb, ref, rng):
+    img = rand_u8(rng, 2160, 3840, 3)
+    for interp in (C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC):
+        assert_exact(cpu(cvb.resize(gpu(img), (7680, 4320), interpolation=interp)), ref.resize(img, (7680, 4320), interp), "4K->8K interp %d" % interp)
+
+
+def _rot(oracle, w, h, ang=7.0, sc=0.9):
+    return oracle.getRotationMatrix2D((w / 2.0, h / 2.0), ang, sc) if oracle.has("get_rotation_matrix2d") else \
+        np.array([[sc * np.cos(np.deg2rad(ang)), sc * np.sin(np.deg2rad(ang)), 3.0], [-sc * np.sin(np.deg2rad(ang)), sc * np.cos(np.deg2rad(ang)), 5.0]])
+
+
+H0 = np.array([[0.95, 0.02, 5.0], [-0.015, 0.97, 3.0], [1e-5, 2e-5, 1.0]])
+
+
+@pytest.mark.parametrize("cn", [1, 3, 4])
+@pytest.mark.parametrize("interp", [C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC])
+@pytest.mark.parametrize("border", [C.BORDER_CONSTANT, C.BORDER_REPLICATE, C.BORDER_REFLECT, C.BORDER_REFLECT_101, C.BORDER_WRAP])
+def test_warp_affine_u8(cvb, oracle, rng, cn, interp, border):
+    img = rand_u8(rng, 131, 157, cn)
+    M = _rot(oracle, 157, 131)
+    for flags in (interp, interp | C.WARP_INVERSE_MAP):
+        want = oracle.warpAffine(img, M, (170, 140), flags, border, (10, 20, 30, 40))
+        got = cpu(cvb.warpAffine(gpu(img), M, (170, 140), flags, border, (10, 20, 30, 40)))
+        assert_exact(got, want, "warpAffine u8 cn=%d flags=%d border=%d" % (cn, flags, border))
+
+
+@pytest.mark.parametrize("cn", [1, 3])
+@pytest.mark.parametrize("interp", [C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC])
+@pytest.mark.parametrize("border", [C.BORDER_CONSTANT, C.BORDER_REPLICATE, C.BORDER_REFLECT_101])
+def test_warp_perspective_u8(cvb, oracle, rng, cn, interp, border):
+    img = rand_u8(rng, 131, 157, cn)
+    for flags in (interp, interp | C.WARP_INVERSE_MAP):
+        want = oracle.warpPerspective(img, H0, (170, 140), flags, border, (10, 20, 30, 40))
+        got = cpu(cvb.warpPerspective(gpu(img), H0, (170, 140), flags, border, (10, 20, 30, 40)))
+        assert_exact(got, want, "warpPerspective u8 cn=%d flags=%d border=%d" % (cn, flags, border))
+
+
+@pytest.mark.parametrize("interp", [C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC])
+@pytest.mark.parametrize("border", [C.BORDER_CONSTANT, C.BORDER_REPLICATE, C.BORDER_REFLECT])
+def test_warp_f32(cvb, oracle, rng, interp, border):
+    img = rand_u8(rng, 131, 157, 1).astype(np.float32)
+    M = _rot(oracle, 157, 131)
+    assert_close(cpu(cvb.warpAffine(gpu(img), M, (170, 140), interp, border, 7.5)), oracle.warpAffine(img, M, (170, 140), interp, border, 7.5),
+                 atol=2e-4, what="warpAffine f32 interp=%d border=%d" % (interp, border))
+    assert_close(cpu(cvb.warpPerspective(gpu(img), H0, (170, 140), interp, border, 7.5)), oracle.warpPerspective(img, H0, (170, 140), interp, border, 7.5),
+                 atol=2e-4, what="warpPerspective f32 interp=%d border=%d" % (interp, border))
+
+
+def test_sift_upsample_warp(cvb, oracle, rng):
+    """the 2x upsample SIFT uses: warpAffine(INTER_LINEAR | WARP_INVERSE_MAP, BORDER_REFLECT) on f32 (sift.dispatch.cpp:196-202)"""
+    img = rand_u8(rng, 67, 91, 1).astype(np.float32)
+    M = np.array([[0.5, 0, 0], [0, 0.5, 0]])
+    want = oracle.warpAffine(img, M, (182, 134), C.INTER_LINEAR | C.WARP_INVERSE_MAP, C.BORDER_REFLECT)
+    got = cpu(cvb.warpAffine(gpu(img), M, (182, 134), C.INTER_LINEAR | C.WARP_INVERSE_MAP, C.BORDER_REFLECT))
+    assert_exact(got, want, "sift upsample")
+
+
+@pytest.mark.parametrize("interp", [C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC])
+def test_warp_8k(cvb, ref, rng, interp):
+    """BASELINE config C3 (warp leg): 7680x4320 8UC3, rotation 7 deg x0.9 about the centre; projective H"""
+    img = rand_u8(rng, 4320, 7680, 3)
+    M = ref.getRotationMatrix2D((3840, 2160), 7.0, 0.9)
+    for border in (C.BORDER_CONSTANT, C.BORDER_REPLICATE):
+        assert_exact(cpu(cvb.warpAffine(gpu(img), M, (7680, 4320), interp, border)), ref.warpAffine(img, M, (7680, 4320), interp, border), "8K affine %d %d" % (interp, border))
+    H = np.array([[0.95, 0.02, 50], [-0.015, 0.97, 30], [1e-6, 2e-6, 1]])
+    assert_exact(cpu(cvb.warpPerspective(gpu(img), H, (7680, 4320), interp, C.BORDER_CONSTANT)), ref.warpPerspective(img, H, (7680, 4320), interp, C.BORDER_CONSTANT),
+                 "8K perspective %d" % interp)
