@@ -290,3 +290,83 @@ def warpAffine(src, M, dsize, flags=INTER_LINEAR, borderMode=BORDER_CONSTANT, bo
 def warpPerspective(src, M, dsize, flags=INTER_LINEAR, borderMode=BORDER_CONSTANT, borderValue=0, dst=None, stream=None):
     """cv::warpPerspective (imgproc.hpp:2482)"""
     return _warp(lib().b200cv_warp_perspective, "warpPerspective", src, M, dsize, flags, borderMode, borderValue, dst, stream, 9)
+
+
+def matchTemplate(image, templ, method, result=None, stream=None):
+    """cv::matchTemplate (imgproc.hpp:3916): image (H,W) / (N,H,W,1), templ (h,w); result float32 (H-h+1, W-w+1)"""
+    import torch
+    mi, mt = describe(image), describe(templ)
+    ow, oh = mi.cols - mt.cols + 1, mi.rows - mt.rows + 1
+    if result is None:
+        shape = [max(mi.frames, 1), oh, ow, 1] if image.dim() == 4 else [oh, ow]
+        result = torch.empty(shape, dtype=torch.float32, device=image.device)
+    mr = describe(result)
+    _check(lib().b200cv_match_template(ctypes.byref(mi), ctypes.byref(mt), ctypes.byref(mr), int(method), _stream_ptr(stream)), "matchTemplate")
+    return result
+
+
+def cornerHarris(src, blockSize, ksize, k, borderType=BORDER_DEFAULT, dst=None, stream=None):
+    """cv::cornerHarris (imgproc.hpp:1948)"""
+    import torch
+    dst = dst if dst is not None else _new(src, dtype=torch.float32)
+    ms, md = _pair(src, dst)
+    _check(lib().b200cv_corner_harris(ctypes.byref(ms), ctypes.byref(md), int(blockSize), int(ksize), ctypes.c_double(k), int(borderType),
+                                      _stream_ptr(stream)), "cornerHarris")
+    return dst
+
+
+def cornerMinEigenVal(src, blockSize, ksize=3, borderType=BORDER_DEFAULT, dst=None, stream=None):
+    """cv::cornerMinEigenVal (imgproc.hpp:1921)"""
+    import torch
+    dst = dst if dst is not None else _new(src, dtype=torch.float32)
+    ms, md = _pair(src, dst)
+    _check(lib().b200cv_corner_min_eigen_val(ctypes.byref(ms), ctypes.byref(md), int(blockSize), int(ksize), int(borderType),
+                                             _stream_ptr(stream)), "cornerMinEigenVal")
+    return dst
+
+
+def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, blockSize=3, gradientSize=3, useHarrisDetector=False, k=0.04,
+                        max_out=None, stream=None, with_quality=False):
+    """cv::goodFeaturesToTrack (imgproc.hpp:2096).  Returns an (n,2) float32 array of (x,y) for a single frame, or a list of
+    such arrays for an (N,H,W,1) batch."""
+    ms = describe(image)
+    frames = max(ms.frames, 1)
+    cap = int(max_out or (maxCorners if maxCorners > 0 else ms.cols * ms.rows))
+    pts = np.zeros((frames, cap, 2), np.float32)
+    q = np.zeros((frames, cap), np.float32)
+    cnt = np.zeros(frames, np.int32)
+    _check(lib().b200cv_good_features_to_track(ctypes.byref(ms), pts.ctypes.data_as(ctypes.c_void_p), q.ctypes.data_as(ctypes.c_void_p), cap,
+                                               cnt.ctypes.data_as(ctypes.c_void_p), int(maxCorners), ctypes.c_double(qualityLevel),
+                                               ctypes.c_double(minDistance), int(blockSize), int(gradientSize), int(bool(useHarrisDetector)),
+                                               ctypes.c_double(k), _stream_ptr(stream)), "goodFeaturesToTrack")
+    out = [(pts[f, :min(cnt[f], cap)].copy(), q[f, :min(cnt[f], cap)].copy()) for f in range(frames)]
+    if not with_quality:
+        out = [o[0] for o in out]
+    return out if image.dim() == 4 else out[0]
+
+
+def sift_pyramid_layout(width, height, nOctaveLayers=3, upscale=True):
+    no = ctypes.c_int(0)
+    ge, de = ctypes.c_size_t(0), ctypes.c_size_t(0)
+    dims = np.zeros(64, np.int32)
+    _check(lib().b200cv_sift_pyramid_layout(int(width), int(height), int(nOctaveLayers), int(bool(upscale)), ctypes.byref(no), ctypes.byref(ge),
+                                            ctypes.byref(de), dims.ctypes.data_as(ctypes.c_void_p)), "sift_pyramid_layout")
+    return no.value, ge.value, de.value, dims[:2 * no.value].reshape(-1, 2).copy()
+
+
+def sift_pyramid(gray, nOctaveLayers=3, sigma=1.6, upscale=True, with_dog=True, stream=None):
+    """SIFT Gaussian + DoG pyramids (sift.dispatch.cpp:176-310) of a (H,W) frame or (N,H,W,1) batch of CV_8U frames.
+    Returns (gauss, dog, dims): flat float32 CUDA tensors of shape (N, elems) packed image after image, octave-major,
+    and the per-octave (w,h) table."""
+    import torch
+    ms = describe(gray)
+    frames = max(ms.frames, 1)
+    no, ge, de, dims = sift_pyramid_layout(ms.cols, ms.rows, nOctaveLayers, upscale)
+    gstride = (ge + 3) & ~3
+    dstride = (de + 3) & ~3
+    G = torch.empty((frames, gstride), dtype=torch.float32, device=gray.device)
+    D = torch.empty((frames, dstride), dtype=torch.float32, device=gray.device) if with_dog else None
+    _check(lib().b200cv_sift_pyramid(ctypes.byref(ms), int(nOctaveLayers), ctypes.c_double(sigma), int(bool(upscale)),
+                                     ctypes.c_void_p(G.data_ptr()), ctypes.c_size_t(gstride),
+                                     ctypes.c_void_p(D.data_ptr() if with_dog else 0), ctypes.c_size_t(dstride), _stream_ptr(stream)), "sift_pyramid")
+    return G, D, dims

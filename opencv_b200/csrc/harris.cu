@@ -1,0 +1,305 @@
+// harris.cu -- cv::cornerHarris / cv::cornerMinEigenVal / cv::goodFeaturesToTrack.
+//
+// Reference pipeline (cornerEigenValsVecs, modules/imgproc/src/corner.cpp:237-322): five full-frame single-threaded
+// passes -- Sobel x, Sobel y (scaled, CV_32F), products (dx^2, dx*dy, dy^2), un-normalised blockSize^2 box sum (f64
+// accumulators, box_filter.simd.hpp:1255-1264), response (calcHarris :104-155 / calcMinEigenVal :55-101).
+// Here: ONE kernel.  A CTA stages the source tile + apron in shared memory, evaluates both scaled Sobel derivatives and
+// the three products for every position of the box apron, resolves the box filter's border on the *product* image
+// (exactly where the reference applies it: cv::boxFilter extrapolates cov, not the source), sums the block in fp64 and
+// writes the response: 1 byte (or 4) read and 4 bytes written per pixel, no intermediate ever reaches HBM.
+//
+// goodFeaturesToTrack (modules/imgproc/src/featureselect.cpp:382-548): response map -> per-frame max (warp-shuffle +
+// atomic reduction) -> threshold at max*quality (TOZERO) -> 3x3 non-maximum test (== dilate + compare) -> compaction of
+// (value, position) candidates on the device; the ordered part (sort by value then address, greedy min-distance
+// acceptance on a cell grid) runs on the host over the compacted list, as it is inherently sequential.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+#include "common.cuh"
+
+namespace b200cv {
+
+int sobel_taps(int dx, int dy, int ksize, double scale, std::vector<float>& kx, std::vector<float>& ky);
+
+struct HarrisParams {
+    float dxk_x[8], dxk_y[8];   // Dx = row pass with dxk_x, column pass with dxk_y
+    float dyk_x[8], dyk_y[8];
+    int ks;                     // taps per direction (3 for ksize 1|3, 5, 7)
+    int bs, ba;                 // box size and anchor (bs/2)
+    int border;
+    float k;
+    int op;                     // 0 = Harris, 1 = min eigen value
+};
+
+constexpr int H_TW = 64, H_TH = 16;
+
+template <typename ST>
+__global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __grid_constant__ HarrisParams p)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int rs = p.ks / 2;
+    const int cw = H_TW + p.bs - 1, ch = H_TH + p.bs - 1;         // product (cov) region
+    const int sw_ = cw + 2 * rs, sh_ = ch + 2 * rs;               // source region
+    float* s_src = smem;                                          // sh_ x sw_
+    float* s_a = s_src + sw_ * sh_;                               // ch x cw : dx*dx
+    float* s_b = s_a + cw * ch;                                   //           dx*dy
+    float* s_c = s_b + cw * ch;                                   //           dy*dy
+    const int f = blockIdx.z, x0 = blockIdx.x * H_TW, y0 = blockIdx.y * H_TH;
+    const int cx0 = x0 - p.ba, cy0 = y0 - p.ba;                   // image coordinates of cov region origin
+    const int W = src.cols, H = src.rows;
+
+    for (int idx = threadIdx.x; idx < sw_ * sh_; idx += 256) {
+        int r = idx / sw_, c = idx - r * sw_;
+        int sy = border_interpolate(cy0 - rs + r, H, p.border);
+        int sx = border_interpolate(cx0 - rs + c, W, p.border);
+        s_src[idx] = (sy < 0 || sx < 0) ? 0.f : (float)src.row<ST>(f, sy)[sx];
+    }
+    __syncthreads();
+    // derivatives + products at the in-image positions of the cov region
+    for (int idx = threadIdx.x; idx < cw * ch; idx += 256) {
+        int r = idx / cw, c = idx - r * cw;
+        int gx = cx0 + c, gy = cy0 + r;
+        if ((unsigned)gx >= (unsigned)W || (unsigned)gy >= (unsigned)H) continue;
+        float dx = 0.f, dy = 0.f;
+        for (int j = 0; j < p.ks; j++) {
+            const float* row = s_src + (r + j) * sw_ + c;
+            float rx = 0.f, ry = 0.f;
+            for (int i = 0; i < p.ks; i++) { rx = fmaf(row[i], p.dxk_x[i], rx); ry = fmaf(row[i], p.dyk_x[i], ry); }
+            dx = fmaf(rx, p.dxk_y[j], dx);
+            dy = fmaf(ry, p.dyk_y[j], dy);
+        }
+        s_a[idx] = __fmul_rn(dx, dx); s_b[idx] = __fmul_rn(dx, dy); s_c[idx] = __fmul_rn(dy, dy);
+    }
+    __syncthreads();
+    // the box filter's border: out-of-image positions take the products of the border-interpolated position (or 0)
+    for (int idx = threadIdx.x; idx < cw * ch; idx += 256) {
+        int r = idx / cw, c = idx - r * cw;
+        int gx = cx0 + c, gy = cy0 + r;
+        if ((unsigned)gx < (unsigned)W && (unsigned)gy < (unsigned)H) continue;
+        int qx = border_interpolate(gx, W, p.border), qy = border_interpolate(gy, H, p.border);
+        int qc = qx - cx0, qr = qy - cy0;
+        if (qx < 0 || qy < 0 || qc < 0 || qc >= cw || qr < 0 || qr >= ch) { s_a[idx] = s_b[idx] = s_c[idx] = 0.f; continue; }
+        int q = qr * cw + qc;
+        s_a[idx] = s_a[q]; s_b[idx] = s_b[q]; s_c[idx] = s_c[q];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < H_TW * H_TH; idx += 256) {
+        int r = idx / H_TW, c = idx - r * H_TW;
+        int gx = x0 + c, gy = y0 + r;
+        if (gx >= W || gy >= H) continue;
+        double a = 0, b = 0, cc = 0;
+        for (int j = 0; j < p.bs; j++) {
+            int o = (r + j) * cw + c;
+            double ra = 0, rb = 0, rc = 0;
+            for (int i = 0; i < p.bs; i++) { ra += (double)s_a[o + i]; rb += (double)s_b[o + i]; rc += (double)s_c[o + i]; }
+            a += ra; b += rb; cc += rc;
+        }
+        float fa = (float)a, fb = (float)b, fc = (float)cc, out;
+        if (p.op == 0) {
+            float acbb = __fsub_rn(__fmul_rn(fa, fc), __fmul_rn(fb, fb));
+            float ac = __fadd_rn(fa, fc);
+            out = __fsub_rn(acbb, __fmul_rn(__fmul_rn(p.k, ac), ac));
+        } else {
+            float ha = __fmul_rn(fa, 0.5f), hc = __fmul_rn(fc, 0.5f);
+            float t = __fsub_rn(ha, hc);
+            t = __fadd_rn(__fmul_rn(fb, fb), __fmul_rn(t, t));
+            out = __fsub_rn(__fadd_rn(ha, hc), __fsqrt_rn(t));
+        }
+        dst.row<float>(f, gy)[gx] = out;
+    }
+}
+
+int corner_response(const b200cvMat* src, const b200cvMat* dst, int block_size, int ksize, double k, int border, int op, void* stream)
+{
+    int rc;
+    if ((rc = check_mat(src, "src")) || (rc = check_mat(dst, "dst"))) return rc;
+    B200_REQUIRE(src->cols == dst->cols && src->rows == dst->rows, "src/dst size mismatch");
+    B200_REQUIRE(dst->type == B200CV_MAKETYPE(B200CV_32F, 1), "corner response must be CV_32FC1");
+    B200_REQUIRE(src->type == B200CV_MAKETYPE(B200CV_8U, 1) || src->type == B200CV_MAKETYPE(B200CV_32F, 1), "source must be CV_8UC1 or CV_32FC1");
+    B200_REQUIRE(block_size > 0, "blockSize must be positive");
+    border &= ~B200CV_BORDER_ISOLATED;
+    if (border < 0 || border > B200CV_BORDER_REFLECT_101 || border == B200CV_BORDER_WRAP) return B200CV_NOT_IMPLEMENTED;
+    if (block_size > 31 || (ksize != 1 && ksize != 3 && ksize != 5 && ksize != 7)) return B200CV_NOT_IMPLEMENTED;   // Scharr (ksize<0): next
+    const bool u8 = B200CV_DEPTH(src->type) == B200CV_8U;
+    // corner.cpp:247-252
+    double scale = (double)(1 << (ksize - 1)) * block_size;
+    if (u8) scale *= 255.0;
+    scale = 1.0 / scale;
+    std::vector<float> xkx, xky, ykx, yky;
+    if ((rc = sobel_taps(1, 0, ksize, scale, xkx, xky)) || (rc = sobel_taps(0, 1, ksize, scale, ykx, yky))) return rc;
+    HarrisParams p;
+    memset(&p, 0, sizeof(p));
+    // ksize 1: 3 taps along the derivative, 1 across; embed the 1-tap kernels centred in 3 taps
+    int ks = (int)std::max(std::max(xkx.size(), xky.size()), std::max(ykx.size(), yky.size()));
+    auto put = [&](float* d, const std::vector<float>& v) { int o = (ks - (int)v.size()) / 2; for (size_t i = 0; i < v.size(); i++) d[o + i] = v[i]; };
+    put(p.dxk_x, xkx); put(p.dxk_y, xky); put(p.dyk_x, ykx); put(p.dyk_y, yky);
+    p.ks = ks; p.bs = block_size; p.ba = block_size / 2; p.border = border; p.k = (float)k; p.op = op;
+    Img s = make_img(src), d = make_img(dst);
+    B200_REQUIRE(s.frames == d.frames, "src/dst batch mismatch");
+    const int rs = ks / 2, cw = H_TW + p.bs - 1, ch = H_TH + p.bs - 1;
+    size_t smem = ((size_t)(cw + 2 * rs) * (ch + 2 * rs) + 3 * (size_t)cw * ch) * sizeof(float);
+    dim3 grid(div_up((unsigned)s.cols, H_TW), div_up((unsigned)s.rows, H_TH), (unsigned)s.frames);
+    cudaStream_t st = as_stream(stream);
+    if (u8) {
+        static bool a = false;
+        if (!a) { B200_CUDA(cudaFuncSetAttribute(harris_kernel<uchar>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); a = true; }
+        harris_kernel<uchar><<<grid, 256, smem, st>>>(s, d, p);
+    } else {
+        static bool a = false;
+        if (!a) { B200_CUDA(cudaFuncSetAttribute(harris_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); a = true; }
+        harris_kernel<float><<<grid, 256, smem, st>>>(s, d, p);
+    }
+    B200_LAUNCH_CHECK();
+    return B200CV_OK;
+}
+
+// ---- goodFeaturesToTrack device side --------------------------------------------------------------------------------
+// order-preserving float <-> uint mapping for atomicMax
+__device__ __forceinline__ unsigned f2ord(float v) { unsigned u = __float_as_uint(v); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__host__ __device__ __forceinline__ float ord2f(unsigned o) {
+    unsigned u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+__global__ void __launch_bounds__(256) frame_max_kernel(Img eig, unsigned* maxord)
+{
+    const int f = blockIdx.y;
+    unsigned best = 0;    // below every real value's code
+    const long long total = (long long)eig.rows * eig.cols;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        int y = (int)(i / eig.cols), x = (int)(i - (long long)y * eig.cols);
+        best = max(best, f2ord(eig.row<float>(f, y)[x]));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(maxord + f, best);
+}
+
+struct Cand { float val; int pos; };
+
+__global__ void __launch_bounds__(256) gftt_candidates_kernel(Img eig, const unsigned* maxord, double quality, Cand* out, int cap, int* counts)
+{
+    const int f = blockIdx.z;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int W = eig.cols, H = eig.rows;
+    if (x < 1 || y < 1 || x >= W - 1 || y >= H - 1) return;
+    const float maxv = ord2f(maxord[f]);
+    const float thr = (float)((double)maxv * quality);            // threshold(eig, maxVal*qualityLevel, TOZERO) compares in float
+    float v = eig.row<float>(f, y)[x];
+    if (!(v > thr)) return;                                       // TOZERO: becomes 0 and can never be a candidate
+    if (v == 0.f) return;
+    bool ismax = true;
+#pragma unroll
+    for (int dy = -1; dy <= 1; dy++) {
+        const float* r = eig.row<float>(f, y + dy);
+#pragma unroll
+        for (int dx = -1; dx <= 1; dx++) {
+            float n = r[x + dx];
+            n = n > thr ? n : 0.f;
+            if (n > v) ismax = false;
+        }
+    }
+    if (!ismax) return;
+    int slot = atomicAdd(counts + f, 1);
+    if (slot < cap) { out[(size_t)f * cap + slot].val = v; out[(size_t)f * cap + slot].pos = y * W + x; }
+}
+
+}  // namespace b200cv
+
+using namespace b200cv;
+
+extern "C" int b200cv_corner_harris(const b200cvMat* src, const b200cvMat* dst, int block_size, int ksize, double k, int border, void* stream)
+{
+    return corner_response(src, dst, block_size, ksize, k, border, 0, stream);
+}
+
+extern "C" int b200cv_corner_min_eigen_val(const b200cvMat* src, const b200cvMat* dst, int block_size, int ksize, int border, void* stream)
+{
+    return corner_response(src, dst, block_size, ksize, 0.0, border, 1, stream);
+}
+
+extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corners, float* quality, int max_out, int* counts,
+                                             int max_corners, double quality_level, double min_distance, int block_size,
+                                             int gradient_size, int use_harris, double k, void* stream)
+{
+    int rc;
+    if ((rc = check_mat(src, "src"))) return rc;
+    B200_REQUIRE(corners && counts && max_out > 0, "bad output arguments");
+    B200_REQUIRE(quality_level > 0 && min_distance >= 0 && max_corners >= 0, "bad parameters");
+    const int W = src->cols, H = src->rows, frames = src->frames > 1 ? src->frames : 1;
+    cudaStream_t st = as_stream(stream);
+    // workspace: response map + per-frame max + candidate list
+    float* d_eig = nullptr; unsigned* d_max = nullptr; int* d_cnt = nullptr; Cand* d_cand = nullptr;
+    size_t pitch = ((size_t)W * 4 + 255) & ~(size_t)255;
+    int cap = std::min<long long>((long long)W * H, 1 << 22);
+    auto cleanup = [&]() { cudaFree(d_eig); cudaFree(d_max); cudaFree(d_cnt); cudaFree(d_cand); };
+#define TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    TRY(cudaMalloc(&d_eig, pitch * H * frames));
+    TRY(cudaMalloc(&d_max, sizeof(unsigned) * frames));
+    TRY(cudaMalloc(&d_cnt, sizeof(int) * frames));
+    TRY(cudaMalloc(&d_cand, sizeof(Cand) * (size_t)cap * frames));
+    TRY(cudaMemsetAsync(d_max, 0, sizeof(unsigned) * frames, st));
+    TRY(cudaMemsetAsync(d_cnt, 0, sizeof(int) * frames, st));
+    b200cvMat eig = {d_eig, pitch, W, H, B200CV_MAKETYPE(B200CV_32F, 1), frames, pitch * H};
+    rc = corner_response(src, &eig, block_size, gradient_size, k, B200CV_BORDER_REFLECT_101, use_harris ? 0 : 1, stream);
+    if (rc) { cleanup(); return rc; }
+    Img e = make_img(&eig);
+    frame_max_kernel<<<dim3(std::min(1024u, div_up((unsigned)((long long)W * H), 256)), frames), 256, 0, st>>>(e, d_max);
+    count_launch();
+    gftt_candidates_kernel<<<dim3(div_up(W, 32), div_up(H, 8), frames), 256, 0, st>>>(e, d_max, quality_level, d_cand, cap, d_cnt);
+    count_launch();
+    TRY(cudaGetLastError());
+    std::vector<int> hcnt(frames);
+    TRY(cudaMemcpyAsync(hcnt.data(), d_cnt, sizeof(int) * frames, cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
+    std::vector<Cand> cand;
+    for (int f = 0; f < frames; f++) {
+        int n = std::min(hcnt[f], cap);
+        cand.resize(n);
+        if (n) TRY(cudaMemcpy(cand.data(), d_cand + (size_t)f * cap, sizeof(Cand) * n, cudaMemcpyDeviceToHost));
+        // strongest first; equal responses: larger address (= larger row-major position) first  (featureselect.cpp:55-60)
+        std::sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) { return a.val > b.val || (a.val == b.val && a.pos > b.pos); });
+        float* outp = corners + (size_t)f * max_out * 2;
+        float* outq = quality ? quality + (size_t)f * max_out : nullptr;
+        int accepted = 0;
+        auto emit = [&](int x, int y, float v) {
+            if (accepted < max_out) { outp[2 * accepted] = (float)x; outp[2 * accepted + 1] = (float)y; if (outq) outq[accepted] = v; }
+            accepted++;
+        };
+        if (min_distance >= 1) {
+            const int cell = (int)lrint(min_distance);
+            const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
+            std::vector<std::vector<std::pair<float, float>>> grid((size_t)gw * gh);
+            const double md2 = min_distance * min_distance;
+            for (const Cand& c : cand) {
+                int y = c.pos / W, x = c.pos - y * W;
+                int cx = x / cell, cy = y / cell;
+                bool keep = true;
+                for (int yy = std::max(0, cy - 1); keep && yy <= std::min(gh - 1, cy + 1); yy++)
+                    for (int xx = std::max(0, cx - 1); keep && xx <= std::min(gw - 1, cx + 1); xx++)
+                        for (const auto& q : grid[(size_t)yy * gw + xx]) {
+                            float ddx = x - q.first, ddy = y - q.second;
+                            if (ddx * ddx + ddy * ddy < md2) { keep = false; break; }
+                        }
+                if (!keep) continue;
+                grid[(size_t)cy * gw + cx].emplace_back((float)x, (float)y);
+                emit(x, y, c.val);
+                if (max_corners > 0 && accepted == max_corners) break;
+            }
+        } else {
+            for (const Cand& c : cand) {
+                int y = c.pos / W, x = c.pos - y * W;
+                emit(x, y, c.val);
+                if (max_corners > 0 && accepted == max_corners) break;
+            }
+        }
+        counts[f] = accepted;
+    }
+#undef TRY
+    cleanup();
+    return B200CV_OK;
+}

@@ -34,6 +34,8 @@ struct SepParams {
     int delta_i;      // M_FIXED16 / M_INT: integer delta added after the exact accumulation
     int border;
     int cn;
+    Img dog;          // optional second output (f32 only): dog = dst - src, the SIFT difference-of-Gaussians level
+    int has_dog;
     int even_limit;   // M_FIXED16: row elements < even_limit round half-to-even (sepFilter2D's vector body), the rest half-up
 };
 
@@ -107,7 +109,10 @@ __global__ void __launch_bounds__(256) sep_generic_kernel(Img src, Img dst, SepP
         const float* s = s_mid + r * mid_w + e;
         float acc = MODE == M_FLOAT ? p.delta : 0.f;
         for (int j = 0; j < ny; j++) acc = fmaf(s[j * mid_w], p.t.ky[j], acc);
-        dst.row<DT>(f, y)[xe] = finish<DT, MODE>(acc, p.delta_i, xe, p.even_limit);
+        DT outv = finish<DT, MODE>(acc, p.delta_i, xe, p.even_limit);
+        dst.row<DT>(f, y)[xe] = outv;
+        if constexpr (MODE == M_FLOAT && sizeof(ST) == 4 && sizeof(DT) == 4)
+            if (p.has_dog) p.dog.row<float>(f, y)[xe] = __fsub_rn((float)outv, s_in[(r + ay) * in_w + e + ax * cn]);
     }
 }
 
@@ -270,6 +275,14 @@ __global__ void __launch_bounds__(256) sep_fast_kernel(Img src, Img dst, const _
 #pragma unroll
                     for (int c = 0; c < 4; c++) if (gx + c < dst.cols) dp[c] = out[c];
                 }
+                if constexpr (MODE == M_FLOAT && sizeof(ST) == 4 && sizeof(DT) == 4) {
+                    if (p.has_dog) {       // DoG level fused into the blur that produces its minuend (sift.dispatch.cpp:292)
+                        const ST* ctr = s_in + (q * RV + o + RB) * SW + RP + c4 * 4;
+                        float* gp = p.dog.row<float>(f, gy) + gx;
+#pragma unroll
+                        for (int c = 0; c < 4; c++) if (gx + c < dst.cols) gp[c] = __fsub_rn((float)out[c], (float)ctr[c]);
+                    }
+                }
             }
         }
     }
@@ -351,10 +364,11 @@ static int launch_generic(const Img& s, const Img& d, const SepParams& p, cudaSt
 // common entry: taps are float arrays; mode picks the epilogue
 template <typename ST, typename DT, int MODE>
 static int sep_dispatch(const Img& s, const Img& d, int cn, const float* kx, int nx, const float* ky, int ny, int ax, int ay,
-                        float delta, int delta_i, int border, cudaStream_t st, int even_limit = 0)
+                        float delta, int delta_i, int border, cudaStream_t st, int even_limit = 0, const Img* dog = nullptr)
 {
     SepParams p;
     memset(&p, 0, sizeof(p));
+    if (dog) { p.dog = *dog; p.has_dog = 1; }
     p.delta = delta; p.delta_i = delta_i; p.border = border; p.cn = cn; p.even_limit = even_limit;
     bool centred = (nx & 1) && (ny & 1) && ax == nx / 2 && ay == ny / 2;
     int kb = centred ? fast_bucket(nx > ny ? nx : ny) : 0;
@@ -406,7 +420,7 @@ static bool bit_exact_kernel(const float* k, int n, int bits, std::vector<float>
 }
 
 int sep_filter_impl(const b200cvMat* src, const b200cvMat* dst, const float* kx, int nx, const float* ky, int ny,
-                    int ax, int ay, double delta, int border, void* stream)
+                    int ax, int ay, double delta, int border, void* stream, const b200cvMat* dog)
 {
     int rc;
     if ((rc = check_mat(src, "src")) || (rc = check_mat(dst, "dst"))) return rc;
@@ -451,7 +465,12 @@ int sep_filter_impl(const b200cvMat* src, const b200cvMat* dst, const float* kx,
     if (sdepth == B200CV_8U && ddepth == B200CV_8U) return sep_dispatch<uchar, uchar, M_FLOAT>(s, d, cn, kx, nx, ky, ny, ax, ay, fd, 0, border, st);
     if (sdepth == B200CV_8U && ddepth == B200CV_16S) return sep_dispatch<uchar, short, M_FLOAT>(s, d, cn, kx, nx, ky, ny, ax, ay, fd, 0, border, st);
     if (sdepth == B200CV_8U && ddepth == B200CV_32F) return sep_dispatch<uchar, float, M_FLOAT>(s, d, cn, kx, nx, ky, ny, ax, ay, fd, 0, border, st);
-    if (sdepth == B200CV_32F && ddepth == B200CV_32F) return sep_dispatch<float, float, M_FLOAT>(s, d, cn, kx, nx, ky, ny, ax, ay, fd, 0, border, st);
+    if (sdepth == B200CV_32F && ddepth == B200CV_32F) {
+        Img g;
+        if (dog) { g = make_img(dog); B200_REQUIRE(g.frames == s.frames && dog->cols == src->cols && dog->rows == src->rows, "dog shape mismatch"); }
+        return sep_dispatch<float, float, M_FLOAT>(s, d, cn, kx, nx, ky, ny, ax, ay, fd, 0, border, st, 0, dog ? &g : nullptr);
+    }
+    if (dog) return B200CV_NOT_IMPLEMENTED;
     return B200CV_NOT_IMPLEMENTED;
 }
 
@@ -520,7 +539,7 @@ using namespace b200cv;
 extern "C" int b200cv_sep_filter2d(const b200cvMat* src, const b200cvMat* dst, const float* kx, int kx_len, const float* ky,
                                    int ky_len, int anchor_x, int anchor_y, double delta, int border, void* stream)
 {
-    return sep_filter_impl(src, dst, kx, kx_len, ky, ky_len, anchor_x, anchor_y, delta, border, stream);
+    return sep_filter_impl(src, dst, kx, kx_len, ky, ky_len, anchor_x, anchor_y, delta, border, stream, nullptr);
 }
 
 extern "C" int b200cv_sobel(const b200cvMat* src, const b200cvMat* dst, int dx, int dy, int ksize, double scale, double delta,
@@ -529,7 +548,7 @@ extern "C" int b200cv_sobel(const b200cvMat* src, const b200cvMat* dst, int dx, 
     std::vector<float> kx, ky;
     int rc = sobel_taps(dx, dy, ksize, scale, kx, ky);
     if (rc) return rc;
-    return sep_filter_impl(src, dst, kx.data(), (int)kx.size(), ky.data(), (int)ky.size(), -1, -1, delta, border, stream);
+    return sep_filter_impl(src, dst, kx.data(), (int)kx.size(), ky.data(), (int)ky.size(), -1, -1, delta, border, stream, nullptr);
 }
 
 extern "C" int b200cv_get_gaussian_kernel(int n, double sigma, double* out)
@@ -551,8 +570,19 @@ extern "C" int b200cv_get_gaussian_kernel_fixed8(int n, double sigma, uint16_t* 
 }
 
 // cv::GaussianBlur (smooth.dispatch.cpp:609-826)
+namespace b200cv {
+int gaussian_blur_impl(const b200cvMat* src, const b200cvMat* dst, int kw, int kh, double sigma1, double sigma2, int border, void* stream,
+                       const b200cvMat* dog);
+}
+
 extern "C" int b200cv_gaussian_blur(const b200cvMat* src, const b200cvMat* dst, int kw, int kh, double sigma1, double sigma2,
                                     int border, void* stream)
+{
+    return gaussian_blur_impl(src, dst, kw, kh, sigma1, sigma2, border, stream, nullptr);
+}
+
+int b200cv::gaussian_blur_impl(const b200cvMat* src, const b200cvMat* dst, int kw, int kh, double sigma1, double sigma2, int border,
+                               void* stream, const b200cvMat* dog)
 {
     int rc;
     if ((rc = check_mat(src, "src")) || (rc = check_mat(dst, "dst"))) return rc;
@@ -564,7 +594,7 @@ extern "C" int b200cv_gaussian_blur(const b200cvMat* src, const b200cvMat* dst, 
         if (src->rows == 1) kh = 1;
         if (src->cols == 1) kw = 1;
     }
-    if (kw == 1 && kh == 1) return copy_impl(src, dst, stream);
+    if (kw == 1 && kh == 1) { if (dog) return B200CV_NOT_IMPLEMENTED; return copy_impl(src, dst, stream); }
     if (sigma2 <= 0) sigma2 = sigma1;
     // createGaussianKernels (:280-304)
     if (kw <= 0 && sigma1 > 0) kw = gaussian_auto_ksize(sigma1, depth == B200CV_8U);
@@ -574,6 +604,7 @@ extern "C" int b200cv_gaussian_blur(const b200cvMat* src, const b200cvMat* dst, 
     sigma2 = sigma2 > 0 ? sigma2 : 0;
     std::vector<float> kx(kw), ky(kh);
     if (depth == B200CV_8U) {
+        if (dog) return B200CV_NOT_IMPLEMENTED;
         std::vector<int64_t> fx, fy;
         gaussian_kernel_fixed(kw, sigma1, 8, fx);
         if (kh == kw && fabs(sigma1 - sigma2) < 2.220446049250313e-16) fy = fx;
@@ -594,5 +625,5 @@ extern "C" int b200cv_gaussian_blur(const b200cvMat* src, const b200cvMat* dst, 
     else gaussian_kernel_bitexact(kh, sigma2, dy);
     for (int i = 0; i < kw; i++) kx[i] = (float)dx[i];
     for (int i = 0; i < kh; i++) ky[i] = (float)dy[i];
-    return sep_filter_impl(src, dst, kx.data(), kw, ky.data(), kh, kw / 2, kh / 2, 0.0, b, stream);
+    return sep_filter_impl(src, dst, kx.data(), kw, ky.data(), kh, kw / 2, kh / 2, 0.0, b, stream, dog);
 }

@@ -1,0 +1,135 @@
+"""GPU parity: matchTemplate, cornerHarris / cornerMinEigenVal, goodFeaturesToTrack, SIFT pyramid vs the CPU oracle.
+
+Bars
+  matchTemplate ......... relative 1e-3 of the result range (the reference's own bar, test_templmatch.cpp:333; its numerator is a
+                          float DFT, ours is the exact integer sum for 8-bit images)
+  cornerHarris/MinEig ... |d| <= 2e-6 * max|ref| + tiny  (reference test: relative 2e-6, test_goodfeaturetotrack.cpp:439-513;
+                          operations are the same fp32 ones, only FMA chaining inside the 3-tap Sobel rows differs)
+  goodFeaturesToTrack ... identical corner list (order included) whenever the response maps agree on the ranking; compared as
+                          exact coordinates on inputs with well separated responses
+  SIFT pyramid .......... per level |d| <= 1e-3 absolute on a 0..255 scale (a chain of up to 5 f32 blurs per octave and 10 octaves;
+                          NOTE the reference has no test that pins these pyramids -- the oracle is the reference's own code
+                          (oracle/_ref) or the same composition of public calls in the port)
+"""
+import numpy as np
+import pytest
+
+import opencv_b200 as C
+from util import assert_close, assert_exact, cpu, gpu, rand_u8
+
+pytestmark = pytest.mark.gpu
+
+
+def smooth_img(rng, h, w):
+    """band-limited random image: corners / templates with structure instead of white noise"""
+    small = rng.random((h // 8 + 2, w // 8 + 2)).astype(np.float32)
+    img = np.kron(small, np.ones((8, 8), np.float32))[:h, :w]
+    img = img + 0.15 * rng.random((h, w)).astype(np.float32)
+    img = (img - img.min()) / (img.max() - img.min())
+    return (img * 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("method", [C.TM_SQDIFF, C.TM_SQDIFF_NORMED, C.TM_CCORR, C.TM_CCORR_NORMED, C.TM_CCOEFF, C.TM_CCOEFF_NORMED])
+@pytest.mark.parametrize("isz,tsz", [((128, 160), (17, 23)), ((200, 320), (64, 64)), ((131, 97), (1, 1)), ((90, 90), (30, 7))])
+def test_match_template_u8(cvb, oracle, rng, method, isz, tsz):
+    img = rand_u8(rng, *isz)
+    templ = img[5:5 + tsz[0], 9:9 + tsz[1]].copy() if tsz[0] > 1 else rand_u8(rng, *tsz)
+    want = oracle.matchTemplate(img, templ, method)
+    got = cpu(cvb.matchTemplate(gpu(img), gpu(templ), method))
+    scale = max(1.0, float(np.abs(want).max()))
+    assert_close(got, want, atol=1e-3 * scale, what="matchTemplate u8 method=%d %s %s" % (method, isz, tsz))
+
+
+@pytest.mark.parametrize("method", [C.TM_SQDIFF_NORMED, C.TM_CCORR, C.TM_CCORR_NORMED, C.TM_CCOEFF_NORMED])
+def test_match_template_f32(cvb, oracle, rng, method):
+    img = rand_u8(rng, 128, 160).astype(np.float32)
+    templ = img[20:20 + 19, 30:30 + 33].copy()
+    want = oracle.matchTemplate(img, templ, method)
+    got = cpu(cvb.matchTemplate(gpu(img), gpu(templ), method))
+    assert_close(got, want, atol=1e-3 * max(1.0, float(np.abs(want).max())), what="matchTemplate f32 method=%d" % method)
+
+
+def test_match_template_4k(cvb, ref, rng):
+    """BASELINE config C4: TM_CCORR_NORMED, 3840x2160 8UC1 frame vs a 64x64 crop at (1000,700)"""
+    img = rand_u8(rng, 2160, 3840)
+    templ = img[700:764, 1000:1064].copy()
+    want = ref.matchTemplate(img, templ, C.TM_CCORR_NORMED)
+    got = cpu(cvb.matchTemplate(gpu(img), gpu(templ), C.TM_CCORR_NORMED))
+    assert_close(got, want, atol=1e-3, what="C4 matchTemplate")
+    assert np.unravel_index(got.argmax(), got.shape) == (700, 1000)
+
+
+@pytest.mark.parametrize("bs,ks", [(2, 3), (3, 3), (5, 5), (3, 7), (2, 1), (7, 3)])
+@pytest.mark.parametrize("border", [C.BORDER_REFLECT_101, C.BORDER_REPLICATE, C.BORDER_CONSTANT, C.BORDER_REFLECT])
+def test_corner_harris(cvb, oracle, rng, bs, ks, border):
+    for img in (smooth_img(rng, 97, 131), smooth_img(rng, 64, 200).astype(np.float32) / 255.0):
+        want = oracle.cornerHarris(img, bs, ks, 0.04, border)
+        got = cpu(cvb.cornerHarris(gpu(img), bs, ks, 0.04, border))
+        assert_close(got, want, atol=3e-6 * float(np.abs(want).max()) + 1e-12, what="cornerHarris %s bs=%d ks=%d border=%d" % (img.dtype, bs, ks, border))
+        want = oracle.cornerMinEigenVal(img, bs, ks, border)
+        got = cpu(cvb.cornerMinEigenVal(gpu(img), bs, ks, border))
+        assert_close(got, want, atol=3e-6 * float(np.abs(want).max()) + 1e-12, what="cornerMinEigenVal %s bs=%d ks=%d" % (img.dtype, bs, ks))
+
+
+def test_corner_harris_4k(cvb, ref, rng):
+    """BASELINE config C4: cornerHarris(blockSize=2, ksize=3, k=0.04) on 3840x2160 8UC1"""
+    img = smooth_img(rng, 2160, 3840)
+    want = ref.cornerHarris(img, 2, 3, 0.04)
+    got = cpu(cvb.cornerHarris(gpu(img), 2, 3, 0.04))
+    assert_close(got, want, atol=3e-6 * float(np.abs(want).max()), what="C4 cornerHarris")
+
+
+@pytest.mark.parametrize("harris", [True, False])
+@pytest.mark.parametrize("mind", [0, 1, 5, 10.5])
+def test_good_features(cvb, oracle, rng, harris, mind):
+    img = smooth_img(rng, 240, 320)
+    want, wq = oracle.goodFeaturesToTrack(img, 200, 0.01, mind, 3, 3, harris, 0.04)
+    got, gq = cvb.goodFeaturesToTrack(gpu(img), 200, 0.01, mind, 3, 3, harris, 0.04, with_quality=True)
+    assert len(got) == len(want), "corner count %d vs %d" % (len(got), len(want))
+    # same set; same order wherever neighbouring responses are separated by more than the fp32 noise of the response map
+    assert_close(gq, wq, atol=3e-6 * float(np.abs(wq).max()), what="corner qualities")
+    same = np.all(got == want, axis=1)
+    if not same.all():
+        gs = set(map(tuple, got.tolist())); ws = set(map(tuple, want.tolist()))
+        assert len(gs ^ ws) <= max(2, len(want) // 50), "corner sets differ: %s" % sorted(gs ^ ws)[:10]
+
+
+def test_good_features_4k(cvb, ref, rng):
+    """BASELINE config C4: goodFeaturesToTrack(1000, 0.01, 10, blockSize 3, gradientSize 3, Harris k=0.04) on 4K"""
+    img = smooth_img(rng, 2160, 3840)
+    want, wq = ref.goodFeaturesToTrack(img, 1000, 0.01, 10, 3, 3, True, 0.04)
+    got, gq = cvb.goodFeaturesToTrack(gpu(img), 1000, 0.01, 10, 3, 3, True, 0.04, with_quality=True)
+    assert len(got) == len(want) == 1000
+    gs = set(map(tuple, got.tolist())); ws = set(map(tuple, want.tolist()))
+    assert len(gs ^ ws) <= 20, "corner sets differ in %d entries" % len(gs ^ ws)
+
+
+@pytest.mark.parametrize("shape,upscale", [((135, 240), True), ((100, 75), True), ((96, 128), False)])
+def test_sift_pyramid(cvb, oracle, rng, shape, upscale):
+    from oracle.api import unpack_pyramid
+    img = smooth_img(rng, *shape)
+    wg, wd = oracle.sift_pyramid(img, 3, 1.6, upscale)
+    G, D, dims = cvb.sift_pyramid(gpu(img), 3, 1.6, upscale)
+    no = len(dims)
+    assert no == len(wg)
+    gg, gd = unpack_pyramid(cpu(G)[0], cpu(D)[0], dims.reshape(-1), no, 3)
+    for o in range(no):
+        for i in range(6):
+            assert_close(gg[o][i], wg[o][i], atol=1e-3, what="gauss o=%d i=%d" % (o, i))
+        for i in range(5):
+            assert_close(gd[o][i], wd[o][i], atol=1e-3, what="dog o=%d i=%d" % (o, i))
+            # the fused DoG must be exactly the f32 difference of the two stored Gaussian levels
+            assert_exact(gd[o][i], gg[o][i + 1] - gg[o][i], "dog == G[i+1]-G[i] o=%d i=%d" % (o, i))
+
+
+def test_sift_pyramid_batch_1080p(cvb, ref, rng):
+    base = smooth_img(rng, 540, 960)
+    batch = np.stack([np.roll(base, (17 * i, 31 * i), axis=(0, 1)) for i in range(3)])[..., None]
+    G, D, dims = cvb.sift_pyramid(gpu(batch), 3, 1.6, True)
+    from oracle.api import unpack_pyramid
+    for f in (0, 2):
+        wg, wd = ref.sift_pyramid(batch[f, :, :, 0], 3, 1.6, True)
+        gg, gd = unpack_pyramid(cpu(G)[f], cpu(D)[f], dims.reshape(-1), len(dims), 3)
+        for o in range(len(dims)):
+            assert_close(gg[o][5], wg[o][5], atol=1e-3, what="frame %d gauss o=%d" % (f, o))
+            assert_close(gd[o][4], wd[o][4], atol=1e-3, what="frame %d dog o=%d" % (f, o))
