@@ -1,0 +1,281 @@
+// hal_api.cu -- host-pointer entry points: the cv_hal_* replacement functions and the batched host pipeline.
+// No arithmetic here: upload, call the device API of b200cv.h, download.
+#include <functional>
+#include <vector>
+#include "common.cuh"
+#include "../../include/b200cv_hal.h"
+
+namespace b200cv {
+
+constexpr int NPIPE = 3;
+
+struct HostCtx {                      // one per host thread: OpenCV calls HAL functions concurrently from many threads
+    cudaStream_t st[NPIPE] = {nullptr, nullptr, nullptr};
+    void* dbuf[NPIPE][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+    size_t cap[NPIPE][2] = {{0, 0}, {0, 0}, {0, 0}};
+    void* daux = nullptr; size_t caux = 0;
+    ~HostCtx()
+    {
+        for (int i = 0; i < NPIPE; i++) {
+            for (int j = 0; j < 2; j++) if (dbuf[i][j]) cudaFree(dbuf[i][j]);
+            if (st[i]) cudaStreamDestroy(st[i]);
+        }
+        if (daux) cudaFree(daux);
+    }
+};
+static thread_local HostCtx g_ctx;
+
+static int ensure(void** p, size_t* cap, size_t bytes)
+{
+    if (*cap >= bytes) return B200CV_OK;
+    if (*p) { B200_CUDA(cudaFree(*p)); *p = nullptr; *cap = 0; }
+    size_t want = bytes + bytes / 4;
+    B200_CUDA(cudaMalloc(p, want));
+    *cap = want;
+    return B200CV_OK;
+}
+
+static inline size_t pitch_of(const b200cvMat* m) { return ((size_t)m->cols * elem_size(m->type) + 255) & ~(size_t)255; }
+
+typedef std::function<int(const b200cvMat*, const b200cvMat*, void*)> DevOp;
+
+// Generic pipeline: src/dst are HOST descriptors (batches allowed); frames flow in chunks through NPIPE streams.
+static int host_pipeline(const b200cvMat* hsrc, const b200cvMat* hdst, const DevOp& op)
+{
+    int rc;
+    if ((rc = check_mat(hsrc, "src")) || (rc = check_mat(hdst, "dst"))) return rc;
+    const int frames = hsrc->frames > 1 ? hsrc->frames : 1;
+    B200_REQUIRE((hdst->frames > 1 ? hdst->frames : 1) == frames, "src/dst batch mismatch");
+    const size_t sp = pitch_of(hsrc), dp = pitch_of(hdst);
+    const size_t sfb = sp * hsrc->rows, dfb = dp * hdst->rows;
+    // chunk so that a chunk is ~>= 32 MB of traffic but at least 1 frame; single frames use one stream
+    int chunk = (int)std::max<size_t>(1, (32u << 20) / std::max<size_t>(1, sfb + dfb));
+    if (chunk > frames) chunk = frames;
+    HostCtx& c = g_ctx;
+    const int nchunks = (frames + chunk - 1) / chunk;
+    const int npipe = nchunks < NPIPE ? nchunks : NPIPE;
+    for (int i = 0; i < npipe; i++) {
+        if (!c.st[i]) B200_CUDA(cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking));
+        if ((rc = ensure(&c.dbuf[i][0], &c.cap[i][0], sfb * chunk)) || (rc = ensure(&c.dbuf[i][1], &c.cap[i][1], dfb * chunk))) return rc;
+    }
+    const size_t swb = (size_t)hsrc->cols * elem_size(hsrc->type), dwb = (size_t)hdst->cols * elem_size(hdst->type);
+    for (int ci = 0; ci < nchunks; ci++) {
+        const int i = ci % NPIPE, f0 = ci * chunk, n = std::min(chunk, frames - f0);
+        cudaStream_t st = c.st[i];
+        const char* hs = (const char*)hsrc->data + (size_t)f0 * hsrc->frame_step;
+        char* hd = (char*)hdst->data + (size_t)f0 * hdst->frame_step;
+        const bool packed_s = hsrc->frame_step == hsrc->step * (size_t)hsrc->rows || n == 1;
+        const bool packed_d = hdst->frame_step == hdst->step * (size_t)hdst->rows || n == 1;
+        if (packed_s) B200_CUDA(cudaMemcpy2DAsync(c.dbuf[i][0], sp, hs, hsrc->step, swb, (size_t)hsrc->rows * n, cudaMemcpyHostToDevice, st));
+        else for (int f = 0; f < n; f++)
+            B200_CUDA(cudaMemcpy2DAsync((char*)c.dbuf[i][0] + f * sfb, sp, hs + (size_t)f * hsrc->frame_step, hsrc->step, swb, hsrc->rows, cudaMemcpyHostToDevice, st));
+        b200cvMat ds = {c.dbuf[i][0], sp, hsrc->cols, hsrc->rows, hsrc->type, n, sfb};
+        b200cvMat dd = {c.dbuf[i][1], dp, hdst->cols, hdst->rows, hdst->type, n, dfb};
+        if ((rc = op(&ds, &dd, (void*)st))) { for (int k = 0; k < npipe; k++) cudaStreamSynchronize(c.st[k]); return rc; }
+        if (packed_d) B200_CUDA(cudaMemcpy2DAsync(hd, hdst->step, c.dbuf[i][1], dp, dwb, (size_t)hdst->rows * n, cudaMemcpyDeviceToHost, st));
+        else for (int f = 0; f < n; f++)
+            B200_CUDA(cudaMemcpy2DAsync(hd + (size_t)f * hdst->frame_step, hdst->step, (char*)c.dbuf[i][1] + f * dfb, dp, dwb, hdst->rows, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < npipe; i++) B200_CUDA(cudaStreamSynchronize(c.st[i]));
+    return B200CV_OK;
+}
+
+static inline b200cvMat hmat(const void* p, size_t step, int w, int h, int type)
+{
+    b200cvMat m = {const_cast<void*>(p), step, w, h, type, 1, 0};
+    return m;
+}
+
+struct FilterCtxImpl {
+    int separable;
+    std::vector<float> kx, ky, k2d;
+    int kw, kh, ax, ay, src_type, dst_type, border;
+    double delta;
+};
+
+static bool taps_to_float(const uchar* data, size_t step, int type, int w, int h, std::vector<float>& out)
+{
+    out.resize((size_t)w * h);
+    const int depth = B200CV_DEPTH(type);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uchar* p = data + (size_t)y * step;
+            if (depth == B200CV_32F) out[(size_t)y * w + x] = ((const float*)p)[x];
+            else if (depth == 6) out[(size_t)y * w + x] = (float)((const double*)p)[x];
+            else if (depth == 4) out[(size_t)y * w + x] = (float)((const int*)p)[x];
+            else return false;
+        }
+    return true;
+}
+
+}  // namespace b200cv
+
+using namespace b200cv;
+
+// ---- batched host API -----------------------------------------------------------------------------------------------------
+extern "C" int b200cv_host_gaussian_blur(const b200cvMat* s, const b200cvMat* d, int kw, int kh, double sx, double sy, int border)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_gaussian_blur(a, b, kw, kh, sx, sy, border, st); }); }
+extern "C" int b200cv_host_sep_filter2d(const b200cvMat* s, const b200cvMat* d, const float* kx, int nx, const float* ky, int ny, int ax, int ay, double delta, int border)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_sep_filter2d(a, b, kx, nx, ky, ny, ax, ay, delta, border, st); }); }
+extern "C" int b200cv_host_filter2d(const b200cvMat* s, const b200cvMat* d, const float* k, int kw, int kh, int ax, int ay, double delta, int border)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_filter2d(a, b, k, kw, kh, ax, ay, delta, border, st); }); }
+extern "C" int b200cv_host_sobel(const b200cvMat* s, const b200cvMat* d, int dx, int dy, int ksize, double scale, double delta, int border)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_sobel(a, b, dx, dy, ksize, scale, delta, border, st); }); }
+extern "C" int b200cv_host_resize(const b200cvMat* s, const b200cvMat* d, int interp)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_resize(a, b, interp, st); }); }
+extern "C" int b200cv_host_warp_affine(const b200cvMat* s, const b200cvMat* d, const double* M, int flags, int border, const double* bv)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_warp_affine(a, b, M, flags, border, bv, st); }); }
+extern "C" int b200cv_host_warp_perspective(const b200cvMat* s, const b200cvMat* d, const double* M, int flags, int border, const double* bv)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_warp_perspective(a, b, M, flags, border, bv, st); }); }
+extern "C" int b200cv_host_cvt_color(const b200cvMat* s, const b200cvMat* d, int code)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_cvt_color(a, b, code, st); }); }
+extern "C" int b200cv_host_corner_harris(const b200cvMat* s, const b200cvMat* d, int bs, int ks, double k, int border)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_corner_harris(a, b, bs, ks, k, border, st); }); }
+extern "C" int b200cv_host_corner_min_eigen_val(const b200cvMat* s, const b200cvMat* d, int bs, int ks, int border)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_corner_min_eigen_val(a, b, bs, ks, border, st); }); }
+
+extern "C" int b200cv_host_match_template(const b200cvMat* image, const b200cvMat* templ, const b200cvMat* result, int method)
+{
+    int rc;
+    if ((rc = check_mat(templ, "templ"))) return rc;
+    HostCtx& c = g_ctx;
+    const size_t tp = pitch_of(templ);
+    if ((rc = ensure(&c.daux, &c.caux, tp * templ->rows))) return rc;
+    B200_CUDA(cudaMemcpy2D(c.daux, tp, templ->data, templ->step, (size_t)templ->cols * elem_size(templ->type), templ->rows, cudaMemcpyHostToDevice));
+    b200cvMat dt = {c.daux, tp, templ->cols, templ->rows, templ->type, 1, 0};
+    return host_pipeline(image, result, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_match_template(a, &dt, b, method, st); });
+}
+
+// ---- cv_hal_* replacements ----------------------------------------------------------------------------------------------
+#define NO_MARGINS(l, t, r, b, border) \
+    if (((l) | (t) | (r) | (b)) != 0 && !((border) & B200CV_BORDER_ISOLATED)) return B200CV_NOT_IMPLEMENTED   /* ROI of a larger Mat: let OpenCV handle it */
+
+extern "C" int b200cv_hal_gaussianBlur(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int cn,
+                                       size_t ml, size_t mt, size_t mr, size_t mb, size_t kw, size_t kh, double sx, double sy, int border)
+{
+    NO_MARGINS(ml, mt, mr, mb, border);
+    if (src == dst) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(depth, cn)), d = hmat(dst, dstep, w, h, B200CV_MAKETYPE(depth, cn));
+    return b200cv_host_gaussian_blur(&s, &d, (int)kw, (int)kh, sx, sy, border);
+}
+
+extern "C" int b200cv_hal_gaussianBlurBinomial(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int cn,
+                                               size_t ml, size_t mt, size_t mr, size_t mb, size_t ksize, int border)
+{
+    NO_MARGINS(ml, mt, mr, mb, border);
+    if (src == dst) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(depth, cn)), d = hmat(dst, dstep, w, h, B200CV_MAKETYPE(depth, cn));
+    return b200cv_host_gaussian_blur(&s, &d, (int)ksize, (int)ksize, 0, 0, border);
+}
+
+extern "C" int b200cv_hal_sepFilterInit(b200cvFilterCtx** context, int src_type, int dst_type, int kernel_type, uchar* kx, int nx, uchar* ky, int ny,
+                                        int ax, int ay, double delta, int border)
+{
+    if (!context) return B200CV_ERR_BAD_ARG;
+    FilterCtxImpl* c = new FilterCtxImpl();
+    c->separable = 1;
+    if (!taps_to_float(kx, 0, kernel_type, nx, 1, c->kx) || !taps_to_float(ky, 0, kernel_type, ny, 1, c->ky)) { delete c; return B200CV_NOT_IMPLEMENTED; }
+    c->ax = ax; c->ay = ay; c->delta = delta; c->border = border; c->src_type = src_type; c->dst_type = dst_type;
+    *context = (b200cvFilterCtx*)c;
+    return B200CV_OK;
+}
+
+extern "C" int b200cv_hal_sepFilter(b200cvFilterCtx* context, uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int fw, int fh, int ox, int oy)
+{
+    FilterCtxImpl* c = (FilterCtxImpl*)context;
+    if (!c) return B200CV_ERR_BAD_ARG;
+    if ((fw != w || fh != h || ox || oy) && !(c->border & B200CV_BORDER_ISOLATED)) return B200CV_NOT_IMPLEMENTED;
+    if (src == dst) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, w, h, c->src_type), d = hmat(dst, dstep, w, h, c->dst_type);
+    return b200cv_host_sep_filter2d(&s, &d, c->kx.data(), (int)c->kx.size(), c->ky.data(), (int)c->ky.size(), c->ax, c->ay, c->delta, c->border);
+}
+
+extern "C" int b200cv_hal_sepFilterFree(b200cvFilterCtx* context) { delete (FilterCtxImpl*)context; return B200CV_OK; }
+
+extern "C" int b200cv_hal_filterInit(b200cvFilterCtx** context, uchar* kdata, size_t kstep, int ktype, int kw, int kh, int, int, int src_type, int dst_type,
+                                     int border, double delta, int ax, int ay, bool, bool)
+{
+    if (!context) return B200CV_ERR_BAD_ARG;
+    FilterCtxImpl* c = new FilterCtxImpl();
+    c->separable = 0;
+    if (B200CV_CN(ktype) != 1 || !taps_to_float(kdata, kstep, ktype, kw, kh, c->k2d)) { delete c; return B200CV_NOT_IMPLEMENTED; }
+    c->kw = kw; c->kh = kh; c->ax = ax; c->ay = ay; c->delta = delta; c->border = border; c->src_type = src_type; c->dst_type = dst_type;
+    *context = (b200cvFilterCtx*)c;
+    return B200CV_OK;
+}
+
+extern "C" int b200cv_hal_filter(b200cvFilterCtx* context, uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int fw, int fh, int ox, int oy)
+{
+    FilterCtxImpl* c = (FilterCtxImpl*)context;
+    if (!c) return B200CV_ERR_BAD_ARG;
+    if ((fw != w || fh != h || ox || oy) && !(c->border & B200CV_BORDER_ISOLATED)) return B200CV_NOT_IMPLEMENTED;
+    if (src == dst) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, w, h, c->src_type), d = hmat(dst, dstep, w, h, c->dst_type);
+    return b200cv_host_filter2d(&s, &d, c->k2d.data(), c->kw, c->kh, c->ax, c->ay, c->delta, c->border);
+}
+
+extern "C" int b200cv_hal_filterFree(b200cvFilterCtx* context) { delete (FilterCtxImpl*)context; return B200CV_OK; }
+
+extern "C" int b200cv_hal_sobel(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int sdepth, int ddepth, int cn,
+                                int ml, int mt, int mr, int mb, int dx, int dy, int ksize, double scale, double delta, int border)
+{
+    NO_MARGINS(ml, mt, mr, mb, border);
+    if (src == dst) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(sdepth, cn)), d = hmat(dst, dstep, w, h, B200CV_MAKETYPE(ddepth, cn));
+    return b200cv_host_sobel(&s, &d, dx, dy, ksize, scale, delta, border);
+}
+
+extern "C" int b200cv_hal_resize(int type, const uchar* src, size_t sstep, int sw, int sh, uchar* dst, size_t dstep, int dw, int dh,
+                                 double inv_x, double inv_y, int interp)
+{
+    // the device path derives the scale from the sizes (the fx = fy = 0 form of cv::resize); decline explicit, different factors
+    if (inv_x > 0 && inv_y > 0 && (inv_x != (double)dw / sw || inv_y != (double)dh / sh)) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, sw, sh, type), d = hmat(dst, dstep, dw, dh, type);
+    return b200cv_host_resize(&s, &d, interp);
+}
+
+extern "C" int b200cv_hal_warpAffine(int type, const uchar* src, size_t sstep, int sw, int sh, uchar* dst, size_t dstep, int dw, int dh,
+                                     const double M[6], int interp, int border, const double bv[4])
+{
+    b200cvMat s = hmat(src, sstep, sw, sh, type), d = hmat(dst, dstep, dw, dh, type);
+    return b200cv_host_warp_affine(&s, &d, M, interp | B200CV_WARP_INVERSE_MAP, border, bv);
+}
+
+extern "C" int b200cv_hal_warpPerspective(int type, const uchar* src, size_t sstep, int sw, int sh, uchar* dst, size_t dstep, int dw, int dh,
+                                          const double M[9], int interp, int border, const double bv[4])
+{
+    b200cvMat s = hmat(src, sstep, sw, sh, type), d = hmat(dst, dstep, dw, dh, type);
+    return b200cv_host_warp_perspective(&s, &d, M, interp | B200CV_WARP_INVERSE_MAP, border, bv);
+}
+
+static int cvt(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, int dcn, int code)
+{
+    if (depth != B200CV_8U) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(depth, scn)), d = hmat(dst, dstep, w, h, B200CV_MAKETYPE(depth, dcn));
+    return b200cv_host_cvt_color(&s, &d, code);
+}
+
+extern "C" int b200cv_hal_cvtBGRtoBGR(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, int dcn, bool swapBlue)
+{
+    int code = scn == 3 ? (dcn == 4 ? (swapBlue ? 2 : 0) : (swapBlue ? 4 : -1)) : (dcn == 3 ? (swapBlue ? 3 : 1) : (swapBlue ? 5 : -1));
+    if (code < 0) return B200CV_NOT_IMPLEMENTED;
+    return cvt(src, sstep, dst, dstep, w, h, depth, scn, dcn, code);
+}
+extern "C" int b200cv_hal_cvtBGRtoGray(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, bool swapBlue)
+{ return cvt(src, sstep, dst, dstep, w, h, depth, scn, 1, scn == 3 ? (swapBlue ? 7 : 6) : (swapBlue ? 11 : 10)); }
+extern "C" int b200cv_hal_cvtGraytoBGR(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int dcn)
+{ return cvt(src, sstep, dst, dstep, w, h, depth, 1, dcn, dcn == 3 ? 8 : 9); }
+extern "C" int b200cv_hal_cvtBGRtoYUV(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, bool swapBlue, bool isCbCr)
+{ return cvt(src, sstep, dst, dstep, w, h, depth, scn, 3, isCbCr ? (swapBlue ? 37 : 36) : (swapBlue ? 83 : 82)); }
+extern "C" int b200cv_hal_cvtYUVtoBGR(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int dcn, bool swapBlue, bool isCbCr)
+{ return cvt(src, sstep, dst, dstep, w, h, depth, 3, dcn, isCbCr ? (swapBlue ? 39 : 38) : (swapBlue ? 85 : 84)); }
+extern "C" int b200cv_hal_cvtBGRtoHSV(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, bool swapBlue, bool full, bool isHSV)
+{
+    if (!isHSV) return B200CV_NOT_IMPLEMENTED;   // HLS: not on the device path
+    return cvt(src, sstep, dst, dstep, w, h, depth, scn, 3, full ? (swapBlue ? 67 : 66) : (swapBlue ? 41 : 40));
+}
+extern "C" int b200cv_hal_cvtHSVtoBGR(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int dcn, bool swapBlue, bool full, bool isHSV)
+{
+    if (!isHSV) return B200CV_NOT_IMPLEMENTED;
+    return cvt(src, sstep, dst, dstep, w, h, depth, 3, dcn, full ? (swapBlue ? 71 : 70) : (swapBlue ? 55 : 54));
+}

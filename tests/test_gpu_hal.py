@@ -1,0 +1,65 @@
+"""GPU: the host-pointer C ABI (cv_hal_* shaped and batched b200cv_host_*) gives the same bytes as the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import opencv_b200 as C
+from util import assert_close, assert_exact, rand_u8
+
+pytestmark = pytest.mark.gpu
+u8p = ctypes.POINTER(ctypes.c_ubyte)
+
+
+def p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_hal_signatures(cvb, oracle, rng):
+    L = cvb.lib()
+    img = rand_u8(rng, 120, 161, 3)
+    dst = np.empty_like(img)
+    sz = ctypes.c_size_t
+    rc = L.b200cv_hal_gaussianBlur(p(img), sz(img.strides[0]), p(dst), sz(dst.strides[0]), 161, 120, 0, 3, sz(0), sz(0), sz(0), sz(0), sz(5), sz(5),
+                                   ctypes.c_double(0), ctypes.c_double(0), 4)
+    assert rc == 0
+    assert_exact(dst, oracle.GaussianBlur(img, (5, 5), 0), "hal gaussianBlur")
+    # a ROI (non-zero margins) must be declined so OpenCV falls back to its own code
+    rc = L.b200cv_hal_gaussianBlur(p(img), sz(img.strides[0]), p(dst), sz(dst.strides[0]), 161, 120, 0, 3, sz(1), sz(0), sz(0), sz(0), sz(5), sz(5),
+                                   ctypes.c_double(0), ctypes.c_double(0), 4)
+    assert rc == 1
+    gray = np.empty((120, 161), np.uint8)
+    assert L.b200cv_hal_cvtBGRtoGray(p(img), sz(img.strides[0]), p(gray), sz(gray.strides[0]), 161, 120, 0, 3, ctypes.c_bool(False)) == 0
+    assert_exact(gray, oracle.cvtColor(img, C.COLOR_BGR2GRAY, 1), "hal cvtBGRtoGray")
+    hsv = np.empty_like(img)
+    assert L.b200cv_hal_cvtBGRtoHSV(p(img), sz(img.strides[0]), p(hsv), sz(hsv.strides[0]), 161, 120, 0, 3, ctypes.c_bool(True), ctypes.c_bool(False),
+                                    ctypes.c_bool(True)) == 0
+    assert_exact(hsv, oracle.cvtColor(img, C.COLOR_RGB2HSV, 3), "hal cvtBGRtoHSV swapBlue")
+    half = np.empty((60, 80, 3), np.uint8)
+    assert L.b200cv_hal_resize(16, p(img[:, :160]), sz(img.strides[0]), 160, 120, p(half), sz(half.strides[0]), 80, 60, ctypes.c_double(0.5),
+                               ctypes.c_double(0.5), 1) == 0
+    assert_exact(half, oracle.resize(np.ascontiguousarray(img[:, :160]), (80, 60), 1), "hal resize")
+    # filter context life cycle
+    ctx = ctypes.c_void_p()
+    ker = (rng.random((5, 5)).astype(np.float32)); ker /= ker.sum()
+    assert L.b200cv_hal_filterInit(ctypes.byref(ctx), p(ker), sz(ker.strides[0]), 5, 5, 5, 161, 120, 16, 16, 4, ctypes.c_double(0), 2, 2,
+                                   ctypes.c_bool(False), ctypes.c_bool(False)) == 0
+    assert L.b200cv_hal_filter(ctx, p(img), sz(img.strides[0]), p(dst), sz(dst.strides[0]), 161, 120, 161, 120, 0, 0) == 0
+    assert L.b200cv_hal_filterFree(ctx) == 0
+    assert_close(dst, oracle.filter2D(img, -1, ker), atol=1, what="hal filter")
+
+
+def test_host_batch_pipeline(cvb, oracle, rng):
+    from opencv_b200 import hal
+    batch = np.stack([rand_u8(rng, 480, 640, 3) for _ in range(40)])     # > one chunk: exercises all three pipeline streams
+    src = hal.pinned_empty(batch.shape, np.uint8); src[...] = batch
+    out = hal.GaussianBlur(src, (7, 7), 1.5)
+    gray = hal.cvtColor(src, C.COLOR_BGR2GRAY)
+    for i in (0, 13, 39):
+        assert_exact(out[i], oracle.GaussianBlur(batch[i], (7, 7), 1.5), "batched host blur frame %d" % i)
+        assert_exact(gray[i, :, :, 0], oracle.cvtColor(batch[i], C.COLOR_BGR2GRAY, 1), "batched host gray frame %d" % i)
+    M = np.array([[0.9, 0.1, 5], [-0.1, 0.9, 7]])
+    w = hal.warpAffine(batch[:3], M, (640, 480))
+    assert_exact(w[1], oracle.warpAffine(batch[1], M, (640, 480)), "host warpAffine")
+    r = hal.matchTemplate(batch[0, :, :, 0].copy(), batch[0, 100:132, 200:232, 0].copy(), C.TM_CCORR_NORMED)
+    assert np.unravel_index(r.argmax(), r.shape) == (100, 200)
