@@ -1,0 +1,238 @@
+// gauss_u8.cu -- the 8-bit single-channel GaussianBlur fast path: TMA tile loads + packed-integer (IDP4A) arithmetic.
+//
+// Same result as the reference's fixedSmoothInvoker (modules/imgproc/src/smooth.simd.hpp:1925-2197; evaluator
+// modules/imgproc/test/test_smooth_bitexact.cpp:40-53):  dst = ((sum_j ky[j] * (sum_i kx[i] * src)) + 2^15) >> 16  with 8.8 taps
+// (every tap <= 255 for ksize >= 3), bit for bit.
+//
+// Per CTA: one 192 x TH output tile (TH = 64-(K-1) rounded down to a multiple of 4).
+//   1. ONE thread issues a 3-D TMA box load (cp.async.bulk.tensor) of the 256 x (TH+K-1) byte tile + apron into shared
+//      memory; everybody waits on the mbarrier.  TMA zero-fills outside the image = BORDER_CONSTANT; for REPLICATE /
+//      REFLECT / REFLECT_101 only CTAs on the image boundary patch their apron cells from the mirrored in-tile cells.
+//   2. Row pass: each thread takes 4 columns x 4 rows.  4 taps per IDP4A (u8 x u8 -> u32); the three unaligned windows
+//      of a group come from PRMT of two aligned shared words.  The 16-bit row sums of the 4 rows are split into low / high
+//      bytes and transposed in registers (PRMT) into "4 vertically adjacent bytes per word" and stored to shared memory.
+//   3. Column pass: sum_j ky[j]*mid = 256 * sum_j ky[j]*hi_j + sum_j ky[j]*lo_j -- again 4 taps per IDP4A, with the tap
+//      words pre-shifted on the host for each of the 4 row phases (zero padded) so no data realignment is needed.
+//      Epilogue: v = hi*256 + lo + 2^15; the result byte is bits 16..23 of v (never saturates: sum k = 256), picked by PRMT;
+//      4 pixels per 32-bit store.
+// Instruction budget (K=5): ~2.1 + 4 IDP4A and ~7 other instructions per pixel, against ~46 for the generic float kernel.
+#include <vector>
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace b200cv {
+
+constexpr int GU_TW = 192;      // output tile width
+constexpr int GU_IW = 256;      // staged tile width (bytes) = TMA box width
+constexpr int GU_RG = 16;       // row groups of 4 rows staged / processed per tile (64 rows)
+
+struct GU8Params {
+    uint32_t kxw[8];            // row taps, 4 per word
+    uint32_t kyw[4][9];         // column taps for output row phase o (0..3) and row group g: byte i = ky[4g + i - o] or 0
+    int W, H, TH, border;
+};
+
+__host__ __device__ constexpr bool gu_nz(int KB, int o, int g) { return 4 * g - o < KB; }
+
+template <int KB>
+__global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const CUtensorMap* __restrict__ tmap, Img dst, const __grid_constant__ GU8Params p)
+{
+    constexpr int RB = KB / 2;
+    constexpr int RA = 16;                           // left apron staged: TMA needs the box to start on a 16-byte boundary
+    constexpr int OFF = RA - RB;                     // tile column of (output column 0, tap 0)
+    constexpr int GH = (KB + 3) / 4;                 // tap groups per row
+    constexpr int GV = (KB + 3 + 3) / 4;             // row groups touched by one 4-row output group
+    __shared__ __align__(128) unsigned char s_in[GU_IW * GU_RG * 4];          // 256 x 64 bytes
+    __shared__ __align__(16) uint32_t s_mid[GU_RG * GU_TW * 2];               // [row group][column][lo, hi]
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int TH = p.TH, IH = TH + KB - 1;
+    const int f = blockIdx.z, x0 = blockIdx.x * GU_TW, y0 = blockIdx.y * TH;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_barrier_init();
+        mbar_arrive_expect_tx(&s_bar, (uint32_t)(GU_IW * IH));
+        tma_load_3d(s_in, tmap, x0 - RA, y0 - RB, f, &s_bar);
+    }
+    __syncthreads();
+    mbar_wait(&s_bar, 0);
+
+    // ---- border patch (only CTAs whose tile crosses the image boundary; BORDER_CONSTANT needs nothing) ----
+    const int tx0 = x0 - RA;                            // image column of tile column 0
+    const bool edge = (tx0 < 0) || (y0 - RB < 0) || (tx0 + GU_IW > p.W) || (y0 - RB + IH > p.H);
+    if (edge && p.border != B200CV_BORDER_CONSTANT) {
+        // rows first (whole rows from the mirrored source row), then columns
+        for (int idx = tid; idx < IH * (GU_IW / 4); idx += 256) {
+            int r = idx / (GU_IW / 4), c4 = idx - r * (GU_IW / 4);
+            int gy = y0 - RB + r;
+            if ((unsigned)gy < (unsigned)p.H) continue;
+            int sr = border_interpolate(gy, p.H, p.border) - (y0 - RB);
+            if ((unsigned)sr < (unsigned)IH)      // rows further than the apron below the image feed no valid output: leave them
+                ((uint32_t*)s_in)[r * (GU_IW / 4) + c4] = ((const uint32_t*)s_in)[sr * (GU_IW / 4) + c4];
+        }
+        __syncthreads();
+        {   // columns left of the image (tile columns [0, RA) of the first tile column) and right of it (from c_first on)
+            const int c_first = p.W - tx0;
+            const int nright = c_first < GU_IW ? min(GU_IW - c_first, RB + 4) : 0;
+            const int nleft = tx0 < 0 ? RA : 0;
+            const int ncol = nleft + nright;
+            for (int idx = tid; idx < IH * ncol; idx += 256) {
+                int r = idx / ncol, k = idx - r * ncol;
+                int c = k < nleft ? k : c_first + (k - nleft);
+                int sc = border_interpolate(tx0 + c, p.W, p.border) - tx0;
+                if ((unsigned)sc < (unsigned)GU_IW) s_in[r * GU_IW + c] = s_in[r * GU_IW + sc];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- row pass: item = 4 columns x 4 rows ----
+#pragma unroll 1
+    for (int it = tid; it < (GU_TW / 4) * GU_RG; it += 256) {
+        const int rg = it / (GU_TW / 4), cg = it - rg * (GU_TW / 4);
+        uint32_t res[4][4];                                          // [row][col] 16-bit sums
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t* wp = (const uint32_t*)(s_in + (rg * 4 + r) * GU_IW + cg * 4);
+            constexpr int W0 = OFF / 4, W1 = (OFF + 3 + 4 * (GH - 1) + 3) / 4;
+            uint32_t w[W1 - W0 + 1];
+#pragma unroll
+            for (int j = W0; j <= W1; j++) w[j - W0] = wp[j];
+            uint32_t a[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int g = 0; g < GH; g++) {
+                const uint32_t t = p.kxw[g];
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int tot = OFF + b + 4 * g, wi = tot / 4 - W0, sh = tot % 4;     // compile-time after unrolling
+                    const uint32_t win = sh == 0 ? w[wi] : __byte_perm(w[wi], w[wi + 1], sh == 1 ? 0x4321 : sh == 2 ? 0x5432 : 0x6543);
+                    a[b] = __dp4a(win, t, a[b]);
+                }
+            }
+            const uint32_t a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
+            res[r][0] = a0; res[r][1] = a1; res[r][2] = a2; res[r][3] = a3;
+        }
+        // transpose: per column, (lo0,lo1,lo2,lo3) and (hi0,hi1,hi2,hi3) of the 4 rows
+        uint32_t out[8];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t t01 = __byte_perm(res[0][c], res[1][c], 0x5140);   // lo0, lo1, hi0, hi1
+            uint32_t t23 = __byte_perm(res[2][c], res[3][c], 0x5140);
+            out[2 * c] = __byte_perm(t01, t23, 0x5410);                 // lo0..lo3
+            out[2 * c + 1] = __byte_perm(t01, t23, 0x7632);             // hi0..hi3
+        }
+        uint4* mp = (uint4*)(s_mid + (rg * GU_TW + cg * 4) * 2);
+        mp[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        mp[1] = make_uint4(out[4], out[5], out[6], out[7]);
+    }
+    __syncthreads();
+
+    // ---- column pass: item = 4 columns x 4 output rows ----
+    const bool vec_store = (((uintptr_t)dst.data | dst.step | dst.fstep) & 3) == 0;
+    const int nq = TH / 4;
+#pragma unroll 1
+    for (int it = tid; it < (GU_TW / 4) * nq; it += 256) {
+        const int q = it / (GU_TW / 4), cg = it - q * (GU_TW / 4);
+        uint32_t lo[4][4], hi[4][4];                                  // [output row][column]
+#pragma unroll
+        for (int o = 0; o < 4; o++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) { lo[o][c] = 32768u; hi[o][c] = 0u; }
+#pragma unroll
+        for (int g = 0; g < GV; g++) {
+            const uint4* mp = (const uint4*)(s_mid + ((q + g) * GU_TW + cg * 4) * 2);
+            uint4 m0 = mp[0], m1 = mp[1];
+            const uint32_t l[4] = {m0.x, m0.z, m1.x, m1.z}, h[4] = {m0.y, m0.w, m1.y, m1.w};
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                if (gu_nz(KB, o, g)) {
+                    const uint32_t t = p.kyw[o][g];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) { lo[o][c] = __dp4a(l[c], t, lo[o][c]); hi[o][c] = __dp4a(h[c], t, hi[o][c]); }
+                }
+            }
+        }
+        const int gx = x0 + cg * 4;
+        if (gx >= p.W) continue;
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            const int gy = y0 + q * 4 + o;
+            if (gy >= p.H) break;
+            uint32_t v[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) v[c] = hi[o][c] * 256u + lo[o][c];
+            uint32_t packed = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
+            uchar* dp = dst.row<uchar>(f, gy) + gx;
+            if (vec_store && gx + 4 <= p.W) *(uint32_t*)dp = packed;
+            else {
+#pragma unroll
+                for (int c = 0; c < 4; c++) if (gx + c < p.W) dp[c] = (uchar)(packed >> (8 * c));
+            }
+        }
+    }
+}
+
+template <int KB>
+static int launch_gu8(const CUtensorMap& tm, const Img& d, const GU8Params& p, int frames, cudaStream_t st)
+{
+    CUtensorMap* dtm = nullptr;
+    int rc = upload_tensor_map(tm, &dtm, st);
+    if (rc) return rc;
+    dim3 grid(div_up((unsigned)p.W, GU_TW), div_up((unsigned)p.H, (unsigned)p.TH), (unsigned)frames);
+    gauss_u8_dp4a_kernel<KB><<<grid, 256, 0, st>>>(dtm, d, p);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(dtm, st);
+    count_launch();
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
+    return B200CV_OK;
+}
+
+// returns B200CV_NOT_IMPLEMENTED when the fast path does not apply (caller falls back to the generic kernel)
+int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st)
+{
+    if (!(kw & 1) || !(kh & 1) || kw < 3 || kh < 3 || kw > 31 || kh > 31) return B200CV_NOT_IMPLEMENTED;
+    if (border == B200CV_BORDER_WRAP) return B200CV_NOT_IMPLEMENTED;
+    if (!tma_compatible(s) || s.rows >= 65536 * 4 || s.frames >= 65536) return B200CV_NOT_IMPLEMENTED;
+    static const int buckets[] = {3, 5, 7, 9, 11, 13, 15, 17, 21, 25, 27, 31};
+    int kmax = kw > kh ? kw : kh, KB = 0;
+    for (int b : buckets) if (kmax <= b) { KB = b; break; }
+    if (!KB || s.cols < KB || s.rows < KB) return B200CV_NOT_IMPLEMENTED;
+    for (int i = 0; i < kw; i++) if (fx[i] < 0 || fx[i] > 255) return B200CV_NOT_IMPLEMENTED;
+    for (int i = 0; i < kh; i++) if (fy[i] < 0 || fy[i] > 255) return B200CV_NOT_IMPLEMENTED;
+    GU8Params p;
+    memset(&p, 0, sizeof(p));
+    unsigned char tx[36] = {0}, ty[36] = {0};
+    for (int i = 0; i < kw; i++) tx[(KB - kw) / 2 + i] = (unsigned char)fx[i];
+    for (int i = 0; i < kh; i++) ty[(KB - kh) / 2 + i] = (unsigned char)fy[i];
+    for (int g = 0; g < 8; g++) p.kxw[g] = tx[4 * g] | (tx[4 * g + 1] << 8) | (tx[4 * g + 2] << 16) | ((uint32_t)tx[4 * g + 3] << 24);
+    for (int o = 0; o < 4; o++)
+        for (int g = 0; g < 9; g++) {
+            uint32_t w = 0;
+            for (int i = 0; i < 4; i++) { int j = 4 * g + i - o; if (j >= 0 && j < KB) w |= (uint32_t)ty[j] << (8 * i); }
+            p.kyw[o][g] = w;
+        }
+    p.W = s.cols; p.H = s.rows; p.border = border;
+    p.TH = ((64 - (KB - 1)) / 4) * 4;
+    CUtensorMap tm;
+    int rc = make_tensor_map_3d(&tm, s.data, 1, s.cols, s.rows, s.frames, s.step, s.fstep, GU_IW, p.TH + KB - 1);   // box start x0-16: 16-byte aligned
+    if (rc) return rc;
+    switch (KB) {
+    case 3: return launch_gu8<3>(tm, d, p, s.frames, st);
+    case 5: return launch_gu8<5>(tm, d, p, s.frames, st);
+    case 7: return launch_gu8<7>(tm, d, p, s.frames, st);
+    case 9: return launch_gu8<9>(tm, d, p, s.frames, st);
+    case 11: return launch_gu8<11>(tm, d, p, s.frames, st);
+    case 13: return launch_gu8<13>(tm, d, p, s.frames, st);
+    case 15: return launch_gu8<15>(tm, d, p, s.frames, st);
+    case 17: return launch_gu8<17>(tm, d, p, s.frames, st);
+    case 21: return launch_gu8<21>(tm, d, p, s.frames, st);
+    case 25: return launch_gu8<25>(tm, d, p, s.frames, st);
+    case 27: return launch_gu8<27>(tm, d, p, s.frames, st);
+    case 31: return launch_gu8<31>(tm, d, p, s.frames, st);
+    }
+    return B200CV_NOT_IMPLEMENTED;
+}
+
+}  // namespace b200cv

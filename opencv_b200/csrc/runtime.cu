@@ -215,3 +215,47 @@ int b200cv_event_elapsed_ms(void* start, void* end, float* ms)
 }
 
 }  // extern "C"
+
+// ---- TMA tensor maps ---------------------------------------------------------------------------------------------------
+#include "tma.cuh"
+namespace b200cv {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int make_tensor_map_3d(CUtensorMap* map, const void* base, int elem_bytes, int cols, int rows, int frames, size_t step, size_t fstep,
+                       int box_w, int box_h)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return B200CV_ERR_CUDA; }
+    CUtensorMapDataType dt = elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(frames > 0 ? frames : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)step, (cuuint64_t)(frames > 1 ? fstep : step * (size_t)rows)};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(map, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return B200CV_ERR_CUDA; }
+    return B200CV_OK;
+}
+
+int upload_tensor_map(const CUtensorMap& tm, CUtensorMap** dptr, cudaStream_t st)
+{
+    void* p = nullptr;
+    B200_CUDA(cudaMallocAsync(&p, sizeof(CUtensorMap), st));
+    cudaError_t e = cudaMemcpyAsync(p, &tm, sizeof(CUtensorMap), cudaMemcpyHostToDevice, st);   // pageable source: staged before return
+    if (e != cudaSuccess) { cudaFreeAsync(p, st); return cuda_fail(e, "tensor map upload", __FILE__, __LINE__); }
+    *dptr = (CUtensorMap*)p;
+    return B200CV_OK;
+}
+}  // namespace b200cv

@@ -26,6 +26,9 @@
 
 namespace b200cv {
 
+int sep_f32_fast(const Img& s, const Img& d, const float* kx, int nx, const float* ky, int ny, float delta, int border, const Img* dog, cudaStream_t st);
+int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st);
+
 enum { M_FLOAT = 0, M_FIXED16 = 1, M_INT = 2 };
 
 struct SepParams {
@@ -468,6 +471,10 @@ int sep_filter_impl(const b200cvMat* src, const b200cvMat* dst, const float* kx,
     if (sdepth == B200CV_32F && ddepth == B200CV_32F) {
         Img g;
         if (dog) { g = make_img(dog); B200_REQUIRE(g.frames == s.frames && dog->cols == src->cols && dog->rows == src->rows, "dog shape mismatch"); }
+        if (cn == 1 && ax == nx / 2 && ay == ny / 2) {     // TMA fast path (sep_f32.cu); declines what it cannot do
+            int frc = sep_f32_fast(s, d, kx, nx, ky, ny, fd, border, dog ? &g : nullptr, st);
+            if (frc != B200CV_NOT_IMPLEMENTED) return frc;
+        }
         return sep_dispatch<float, float, M_FLOAT>(s, d, cn, kx, nx, ky, ny, ax, ay, fd, 0, border, st, 0, dog ? &g : nullptr);
     }
     if (dog) return B200CV_NOT_IMPLEMENTED;
@@ -616,6 +623,10 @@ int b200cv::gaussian_blur_impl(const b200cvMat* src, const b200cvMat* dst, int k
         B200_REQUIRE(src->data != dst->data, "in-place filtering is not supported: pass distinct buffers");
         B200_REQUIRE(src->cols == dst->cols && src->rows == dst->rows, "src/dst size mismatch");
         if (b < 0 || b > B200CV_BORDER_REFLECT_101) return B200CV_NOT_IMPLEMENTED;
+        if (B200CV_CN(src->type) == 1) {      // TMA + IDP4A fast path (gauss_u8.cu); declines what it cannot do
+            int frc = gauss_u8_fast(s, d, fx.data(), kw, fy.data(), kh, b, as_stream(stream));
+            if (frc != B200CV_NOT_IMPLEMENTED) return frc;
+        }
         return sep_dispatch<uchar, uchar, M_FIXED16>(s, d, B200CV_CN(src->type), kx.data(), kw, ky.data(), kh, kw / 2, kh / 2,
                                                      0.f, 0, b, as_stream(stream));
     }
