@@ -88,88 +88,111 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const CUtensorMap
         __syncthreads();
     }
 
-    // ---- row pass: item = 4 columns x 4 rows ----
-#pragma unroll 1
-    for (int it = tid; it < (GU_TW / 4) * GU_RG; it += 256) {
-        const int rg = it / (GU_TW / 4), cg = it - rg * (GU_TW / 4);
-        uint32_t res[4][4];                                          // [row][col] 16-bit sums
+    // ---- row pass: item = 4 columns x 4 rows; 768 items = exactly 3 per thread; (rg, cg) advance without divisions ----
+    {
+        constexpr int NCG = GU_TW / 4;                               // 48 column groups
+        int rg = tid / NCG, cg = tid - rg * NCG;
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const uint32_t* wp = (const uint32_t*)(s_in + (rg * 4 + r) * GU_IW + cg * 4);
-            constexpr int W0 = OFF / 4, W1 = (OFF + 3 + 4 * (GH - 1) + 3) / 4;
-            uint32_t w[W1 - W0 + 1];
+        for (int rep = 0; rep < (NCG * GU_RG) / 256; rep++) {
+            uint32_t res[4][4];                                      // [row][col] 16-bit sums
+            const uint32_t* wp0 = (const uint32_t*)(s_in + (rg * 4) * GU_IW + cg * 4);
 #pragma unroll
-            for (int j = W0; j <= W1; j++) w[j - W0] = wp[j];
-            uint32_t a[4] = {0, 0, 0, 0};
+            for (int r = 0; r < 4; r++) {
+                const uint32_t* wp = wp0 + r * (GU_IW / 4);
+                constexpr int W0 = OFF / 4, W1 = (OFF + 3 + 4 * (GH - 1) + 3) / 4;
+                uint32_t w[W1 - W0 + 1];
 #pragma unroll
-            for (int g = 0; g < GH; g++) {
-                const uint32_t t = p.kxw[g];
+                for (int j = W0; j <= W1; j++) w[j - W0] = wp[j];
+                uint32_t a[4] = {0, 0, 0, 0};
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int tot = OFF + b + 4 * g, wi = tot / 4 - W0, sh = tot % 4;     // compile-time after unrolling
-                    const uint32_t win = sh == 0 ? w[wi] : __byte_perm(w[wi], w[wi + 1], sh == 1 ? 0x4321 : sh == 2 ? 0x5432 : 0x6543);
-                    a[b] = __dp4a(win, t, a[b]);
+                for (int g = 0; g < GH; g++) {
+                    const uint32_t t = p.kxw[g];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int tot = OFF + b + 4 * g, wi = tot / 4 - W0, sh = tot % 4;     // compile-time after unrolling
+                        const uint32_t win = sh == 0 ? w[wi] : __byte_perm(w[wi], w[wi + 1], sh == 1 ? 0x4321 : sh == 2 ? 0x5432 : 0x6543);
+                        a[b] = __dp4a(win, t, a[b]);
+                    }
                 }
+                res[r][0] = a[0]; res[r][1] = a[1]; res[r][2] = a[2]; res[r][3] = a[3];
             }
-            const uint32_t a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3];
-            res[r][0] = a0; res[r][1] = a1; res[r][2] = a2; res[r][3] = a3;
-        }
-        // transpose: per column, (lo0,lo1,lo2,lo3) and (hi0,hi1,hi2,hi3) of the 4 rows
-        uint32_t out[8];
+            // transpose: per column, (lo0,lo1,lo2,lo3) and (hi0,hi1,hi2,hi3) of the 4 rows
+            uint32_t out[8];
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            uint32_t t01 = __byte_perm(res[0][c], res[1][c], 0x5140);   // lo0, lo1, hi0, hi1
-            uint32_t t23 = __byte_perm(res[2][c], res[3][c], 0x5140);
-            out[2 * c] = __byte_perm(t01, t23, 0x5410);                 // lo0..lo3
-            out[2 * c + 1] = __byte_perm(t01, t23, 0x7632);             // hi0..hi3
+            for (int c = 0; c < 4; c++) {
+                uint32_t t01 = __byte_perm(res[0][c], res[1][c], 0x5140);   // lo0, lo1, hi0, hi1
+                uint32_t t23 = __byte_perm(res[2][c], res[3][c], 0x5140);
+                out[2 * c] = __byte_perm(t01, t23, 0x5410);                 // lo0..lo3
+                out[2 * c + 1] = __byte_perm(t01, t23, 0x7632);             // hi0..hi3
+            }
+            uint4* mp = (uint4*)(s_mid + (rg * GU_TW + cg * 4) * 2);
+            mp[0] = make_uint4(out[0], out[1], out[2], out[3]);
+            mp[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            cg += 256 % NCG; rg += 256 / NCG;
+            if (cg >= NCG) { cg -= NCG; rg += 1; }
         }
-        uint4* mp = (uint4*)(s_mid + (rg * GU_TW + cg * 4) * 2);
-        mp[0] = make_uint4(out[0], out[1], out[2], out[3]);
-        mp[1] = make_uint4(out[4], out[5], out[6], out[7]);
     }
     __syncthreads();
 
     // ---- column pass: item = 4 columns x 4 output rows ----
-    const bool vec_store = (((uintptr_t)dst.data | dst.step | dst.fstep) & 3) == 0;
-    const int nq = TH / 4;
+    {
+        constexpr int NCG = GU_TW / 4;
+        const bool vec_store = (((uintptr_t)dst.data | dst.step | dst.fstep) & 3) == 0;
+        const bool full = vec_store && x0 + GU_TW <= p.W && y0 + TH <= p.H;      // interior tile: no bounds checks at all
+        const int nq = TH / 4;
+        int q = tid / NCG, cg = tid - q * NCG;
+        uchar* dbase = dst.row<uchar>(f, y0) + x0;
+        const size_t dstep = dst.step;
 #pragma unroll 1
-    for (int it = tid; it < (GU_TW / 4) * nq; it += 256) {
-        const int q = it / (GU_TW / 4), cg = it - q * (GU_TW / 4);
-        uint32_t lo[4][4], hi[4][4];                                  // [output row][column]
+        for (; q < nq; ) {
+            uint32_t lo[4][4], hi[4][4];                                  // [output row][column]
 #pragma unroll
-        for (int o = 0; o < 4; o++)
+            for (int o = 0; o < 4; o++)
 #pragma unroll
-            for (int c = 0; c < 4; c++) { lo[o][c] = 32768u; hi[o][c] = 0u; }
+                for (int c = 0; c < 4; c++) { lo[o][c] = 32768u; hi[o][c] = 0u; }
+            const uint4* mp0 = (const uint4*)(s_mid + (q * GU_TW + cg * 4) * 2);
 #pragma unroll
-        for (int g = 0; g < GV; g++) {
-            const uint4* mp = (const uint4*)(s_mid + ((q + g) * GU_TW + cg * 4) * 2);
-            uint4 m0 = mp[0], m1 = mp[1];
-            const uint32_t l[4] = {m0.x, m0.z, m1.x, m1.z}, h[4] = {m0.y, m0.w, m1.y, m1.w};
+            for (int g = 0; g < GV; g++) {
+                const uint4* mp = mp0 + g * (GU_TW * 2 / 4);
+                uint4 m0 = mp[0], m1 = mp[1];
+                const uint32_t l[4] = {m0.x, m0.z, m1.x, m1.z}, h[4] = {m0.y, m0.w, m1.y, m1.w};
 #pragma unroll
-            for (int o = 0; o < 4; o++) {
-                if (gu_nz(KB, o, g)) {
-                    const uint32_t t = p.kyw[o][g];
+                for (int o = 0; o < 4; o++) {
+                    if (gu_nz(KB, o, g)) {
+                        const uint32_t t = p.kyw[o][g];
 #pragma unroll
-                    for (int c = 0; c < 4; c++) { lo[o][c] = __dp4a(l[c], t, lo[o][c]); hi[o][c] = __dp4a(h[c], t, hi[o][c]); }
+                        for (int c = 0; c < 4; c++) { lo[o][c] = __dp4a(l[c], t, lo[o][c]); hi[o][c] = __dp4a(h[c], t, hi[o][c]); }
+                    }
                 }
             }
-        }
-        const int gx = x0 + cg * 4;
-        if (gx >= p.W) continue;
+            uint32_t packed[4];
 #pragma unroll
-        for (int o = 0; o < 4; o++) {
-            const int gy = y0 + q * 4 + o;
-            if (gy >= p.H) break;
-            uint32_t v[4];
+            for (int o = 0; o < 4; o++) {
+                uint32_t v[4];
 #pragma unroll
-            for (int c = 0; c < 4; c++) v[c] = hi[o][c] * 256u + lo[o][c];
-            uint32_t packed = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
-            uchar* dp = dst.row<uchar>(f, gy) + gx;
-            if (vec_store && gx + 4 <= p.W) *(uint32_t*)dp = packed;
-            else {
-#pragma unroll
-                for (int c = 0; c < 4; c++) if (gx + c < p.W) dp[c] = (uchar)(packed >> (8 * c));
+                for (int c = 0; c < 4; c++) v[c] = (hi[o][c] << 8) + lo[o][c];
+                packed[o] = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
             }
+            uchar* dp = dbase + (size_t)(q * 4) * dstep + cg * 4;
+            if (full) {
+#pragma unroll
+                for (int o = 0; o < 4; o++) *(uint32_t*)(dp + o * dstep) = packed[o];
+            } else {
+                const int gx = x0 + cg * 4;
+#pragma unroll
+                for (int o = 0; o < 4; o++) {
+                    const int gy = y0 + q * 4 + o;
+                    if (gy < p.H && gx < p.W) {
+                        if (vec_store && gx + 4 <= p.W) *(uint32_t*)(dp + o * dstep) = packed[o];
+                        else {
+#pragma unroll
+                            for (int c = 0; c < 4; c++) if (gx + c < p.W) dp[o * dstep + c] = (uchar)(packed[o] >> (8 * c));
+                        }
+                    }
+                }
+            }
+            cg += 256 % NCG; q += 256 / NCG;
+            if (cg >= NCG) { cg -= NCG; q += 1; }
         }
     }
 }

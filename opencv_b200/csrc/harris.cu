@@ -31,17 +31,21 @@ struct HarrisParams {
     int op;                     // 0 = Harris, 1 = min eigen value
 };
 
-constexpr int H_TW = 64, H_TH = 16;
+constexpr int H_TW = 128, H_TH = 16;
 
-template <typename ST>
+// KS = Sobel taps per direction (3 / 5 / 7), BS = box size when small (2 / 3 / 5), 0 = run-time box size
+template <typename ST, int KS, int BS>
 __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __grid_constant__ HarrisParams p)
 {
     extern __shared__ __align__(16) float smem[];
-    const int rs = p.ks / 2;
-    const int cw = H_TW + p.bs - 1, ch = H_TH + p.bs - 1;         // product (cov) region
+    constexpr int rs = KS / 2;
+    const int bs = BS ? BS : p.bs;
+    const int cw = H_TW + bs - 1, ch = H_TH + bs - 1;             // product (cov) region
     const int sw_ = cw + 2 * rs, sh_ = ch + 2 * rs;               // source region
     float* s_src = smem;                                          // sh_ x sw_
-    float* s_a = s_src + sw_ * sh_;                               // ch x cw : dx*dx
+    float* s_rx = s_src + sw_ * sh_;                              // sh_ x cw : row pass with the Dx row taps
+    float* s_ry = s_rx + sh_ * cw;                                // sh_ x cw : row pass with the Dy row taps
+    float* s_a = s_ry + sh_ * cw;                                 // ch x cw : dx*dx
     float* s_b = s_a + cw * ch;                                   //           dx*dy
     float* s_c = s_b + cw * ch;                                   //           dy*dy
     const int f = blockIdx.z, x0 = blockIdx.x * H_TW, y0 = blockIdx.y * H_TH;
@@ -55,44 +59,66 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
         s_src[idx] = (sy < 0 || sx < 0) ? 0.f : (float)src.row<ST>(f, sy)[sx];
     }
     __syncthreads();
-    // derivatives + products at the in-image positions of the cov region
+    // row pass (both derivative filters share the staged source row)
+    for (int idx = threadIdx.x; idx < sh_ * cw; idx += 256) {
+        int r = idx / cw, c = idx - r * cw;
+        const float* row = s_src + r * sw_ + c;
+        float rx = 0.f, ry = 0.f;
+#pragma unroll
+        for (int i = 0; i < KS; i++) { rx = fmaf(row[i], p.dxk_x[i], rx); ry = fmaf(row[i], p.dyk_x[i], ry); }
+        s_rx[idx] = rx; s_ry[idx] = ry;
+    }
+    __syncthreads();
+    // column pass + products at the in-image positions of the cov region
     for (int idx = threadIdx.x; idx < cw * ch; idx += 256) {
         int r = idx / cw, c = idx - r * cw;
         int gx = cx0 + c, gy = cy0 + r;
         if ((unsigned)gx >= (unsigned)W || (unsigned)gy >= (unsigned)H) continue;
         float dx = 0.f, dy = 0.f;
-        for (int j = 0; j < p.ks; j++) {
-            const float* row = s_src + (r + j) * sw_ + c;
-            float rx = 0.f, ry = 0.f;
-            for (int i = 0; i < p.ks; i++) { rx = fmaf(row[i], p.dxk_x[i], rx); ry = fmaf(row[i], p.dyk_x[i], ry); }
-            dx = fmaf(rx, p.dxk_y[j], dx);
-            dy = fmaf(ry, p.dyk_y[j], dy);
+#pragma unroll
+        for (int j = 0; j < KS; j++) {
+            dx = fmaf(s_rx[(r + j) * cw + c], p.dxk_y[j], dx);
+            dy = fmaf(s_ry[(r + j) * cw + c], p.dyk_y[j], dy);
         }
         s_a[idx] = __fmul_rn(dx, dx); s_b[idx] = __fmul_rn(dx, dy); s_c[idx] = __fmul_rn(dy, dy);
     }
     __syncthreads();
-    // the box filter's border: out-of-image positions take the products of the border-interpolated position (or 0)
-    for (int idx = threadIdx.x; idx < cw * ch; idx += 256) {
-        int r = idx / cw, c = idx - r * cw;
-        int gx = cx0 + c, gy = cy0 + r;
-        if ((unsigned)gx < (unsigned)W && (unsigned)gy < (unsigned)H) continue;
-        int qx = border_interpolate(gx, W, p.border), qy = border_interpolate(gy, H, p.border);
-        int qc = qx - cx0, qr = qy - cy0;
-        if (qx < 0 || qy < 0 || qc < 0 || qc >= cw || qr < 0 || qr >= ch) { s_a[idx] = s_b[idx] = s_c[idx] = 0.f; continue; }
-        int q = qr * cw + qc;
-        s_a[idx] = s_a[q]; s_b[idx] = s_b[q]; s_c[idx] = s_c[q];
+    // the box filter's border: out-of-image positions take the products of the border-interpolated position (or 0);
+    // only CTAs on the image boundary have any
+    if (cx0 < 0 || cy0 < 0 || cx0 + cw > W || cy0 + ch > H) {
+        for (int idx = threadIdx.x; idx < cw * ch; idx += 256) {
+            int r = idx / cw, c = idx - r * cw;
+            int gx = cx0 + c, gy = cy0 + r;
+            if ((unsigned)gx < (unsigned)W && (unsigned)gy < (unsigned)H) continue;
+            int qx = border_interpolate(gx, W, p.border), qy = border_interpolate(gy, H, p.border);
+            int qc = qx - cx0, qr = qy - cy0;
+            if (qx < 0 || qy < 0 || qc < 0 || qc >= cw || qr < 0 || qr >= ch) { s_a[idx] = s_b[idx] = s_c[idx] = 0.f; continue; }
+            int q = qr * cw + qc;
+            s_a[idx] = s_a[q]; s_b[idx] = s_b[q]; s_c[idx] = s_c[q];
+        }
+        __syncthreads();
     }
-    __syncthreads();
     for (int idx = threadIdx.x; idx < H_TW * H_TH; idx += 256) {
         int r = idx / H_TW, c = idx - r * H_TW;
         int gx = x0 + c, gy = y0 + r;
         if (gx >= W || gy >= H) continue;
         double a = 0, b = 0, cc = 0;
-        for (int j = 0; j < p.bs; j++) {
-            int o = (r + j) * cw + c;
-            double ra = 0, rb = 0, rc = 0;
-            for (int i = 0; i < p.bs; i++) { ra += (double)s_a[o + i]; rb += (double)s_b[o + i]; rc += (double)s_c[o + i]; }
-            a += ra; b += rb; cc += rc;
+        if constexpr (BS != 0) {
+#pragma unroll
+            for (int j = 0; j < BS; j++) {
+                int o = (r + j) * cw + c;
+                double ra = 0, rb = 0, rc = 0;
+#pragma unroll
+                for (int i = 0; i < BS; i++) { ra += (double)s_a[o + i]; rb += (double)s_b[o + i]; rc += (double)s_c[o + i]; }
+                a += ra; b += rb; cc += rc;
+            }
+        } else {
+            for (int j = 0; j < bs; j++) {
+                int o = (r + j) * cw + c;
+                double ra = 0, rb = 0, rc = 0;
+                for (int i = 0; i < bs; i++) { ra += (double)s_a[o + i]; rb += (double)s_b[o + i]; rc += (double)s_c[o + i]; }
+                a += ra; b += rb; cc += rc;
+            }
         }
         float fa = (float)a, fb = (float)b, fc = (float)cc, out;
         if (p.op == 0) {
@@ -107,6 +133,43 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
         }
         dst.row<float>(f, gy)[gx] = out;
     }
+}
+
+template <typename ST, int KS, int BS>
+static int launch_harris(const Img& s, const Img& d, const HarrisParams& p, cudaStream_t st)
+{
+    const int rs = KS / 2, cw = H_TW + p.bs - 1, ch = H_TH + p.bs - 1, sw_ = cw + 2 * rs, sh_ = ch + 2 * rs;
+    size_t smem = ((size_t)sw_ * sh_ + 2 * (size_t)sh_ * cw + 3 * (size_t)cw * ch) * sizeof(float);
+    auto kern = harris_kernel<ST, KS, BS>;
+    static bool a = false;
+    if (!a) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a = true; }
+    if (smem > 200 * 1024) return B200CV_NOT_IMPLEMENTED;
+    dim3 grid(div_up((unsigned)s.cols, H_TW), div_up((unsigned)s.rows, H_TH), (unsigned)s.frames);
+    kern<<<grid, 256, smem, st>>>(s, d, p);
+    B200_LAUNCH_CHECK();
+    return B200CV_OK;
+}
+
+template <typename ST, int KS>
+static int launch_harris_bs(const Img& s, const Img& d, const HarrisParams& p, cudaStream_t st)
+{
+    switch (p.bs) {
+    case 2: return launch_harris<ST, KS, 2>(s, d, p, st);
+    case 3: return launch_harris<ST, KS, 3>(s, d, p, st);
+    case 5: return launch_harris<ST, KS, 5>(s, d, p, st);
+    default: return launch_harris<ST, KS, 0>(s, d, p, st);
+    }
+}
+
+template <typename ST>
+static int launch_harris_ks(const Img& s, const Img& d, const HarrisParams& p, cudaStream_t st)
+{
+    switch (p.ks) {
+    case 3: return launch_harris_bs<ST, 3>(s, d, p, st);
+    case 5: return launch_harris_bs<ST, 5>(s, d, p, st);
+    case 7: return launch_harris_bs<ST, 7>(s, d, p, st);
+    }
+    return B200CV_NOT_IMPLEMENTED;
 }
 
 int corner_response(const b200cvMat* src, const b200cvMat* dst, int block_size, int ksize, double k, int border, int op, void* stream)
@@ -136,21 +199,8 @@ int corner_response(const b200cvMat* src, const b200cvMat* dst, int block_size, 
     p.ks = ks; p.bs = block_size; p.ba = block_size / 2; p.border = border; p.k = (float)k; p.op = op;
     Img s = make_img(src), d = make_img(dst);
     B200_REQUIRE(s.frames == d.frames, "src/dst batch mismatch");
-    const int rs = ks / 2, cw = H_TW + p.bs - 1, ch = H_TH + p.bs - 1;
-    size_t smem = ((size_t)(cw + 2 * rs) * (ch + 2 * rs) + 3 * (size_t)cw * ch) * sizeof(float);
-    dim3 grid(div_up((unsigned)s.cols, H_TW), div_up((unsigned)s.rows, H_TH), (unsigned)s.frames);
     cudaStream_t st = as_stream(stream);
-    if (u8) {
-        static bool a = false;
-        if (!a) { B200_CUDA(cudaFuncSetAttribute(harris_kernel<uchar>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); a = true; }
-        harris_kernel<uchar><<<grid, 256, smem, st>>>(s, d, p);
-    } else {
-        static bool a = false;
-        if (!a) { B200_CUDA(cudaFuncSetAttribute(harris_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); a = true; }
-        harris_kernel<float><<<grid, 256, smem, st>>>(s, d, p);
-    }
-    B200_LAUNCH_CHECK();
-    return B200CV_OK;
+    return u8 ? launch_harris_ks<uchar>(s, d, p, st) : launch_harris_ks<float>(s, d, p, st);
 }
 
 // ---- goodFeaturesToTrack device side --------------------------------------------------------------------------------
@@ -235,13 +285,13 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
     // workspace: response map + per-frame max + candidate list
     float* d_eig = nullptr; unsigned* d_max = nullptr; int* d_cnt = nullptr; Cand* d_cand = nullptr;
     size_t pitch = ((size_t)W * 4 + 255) & ~(size_t)255;
-    int cap = std::min<long long>((long long)W * H, 1 << 22);
-    auto cleanup = [&]() { cudaFree(d_eig); cudaFree(d_max); cudaFree(d_cnt); cudaFree(d_cand); };
+    int cap = (int)std::min<long long>((long long)W * H, 1 << 20);
+    auto cleanup = [&]() { cudaFreeAsync(d_eig, st); cudaFreeAsync(d_max, st); cudaFreeAsync(d_cnt, st); cudaFreeAsync(d_cand, st); };
 #define TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
-    TRY(cudaMalloc(&d_eig, pitch * H * frames));
-    TRY(cudaMalloc(&d_max, sizeof(unsigned) * frames));
-    TRY(cudaMalloc(&d_cnt, sizeof(int) * frames));
-    TRY(cudaMalloc(&d_cand, sizeof(Cand) * (size_t)cap * frames));
+    TRY(cudaMallocAsync(&d_eig, pitch * H * frames, st));
+    TRY(cudaMallocAsync(&d_max, sizeof(unsigned) * frames, st));
+    TRY(cudaMallocAsync(&d_cnt, sizeof(int) * frames, st));
+    TRY(cudaMallocAsync(&d_cand, sizeof(Cand) * (size_t)cap * frames, st));
     TRY(cudaMemsetAsync(d_max, 0, sizeof(unsigned) * frames, st));
     TRY(cudaMemsetAsync(d_cnt, 0, sizeof(int) * frames, st));
     b200cvMat eig = {d_eig, pitch, W, H, B200CV_MAKETYPE(B200CV_32F, 1), frames, pitch * H};

@@ -26,24 +26,42 @@ struct ResizeParams {
 __device__ __forceinline__ int clip_i(int x, int a, int b) { return x >= a ? (x < b ? x : b - 1) : a; }
 
 // ---- NEAREST ------------------------------------------------------------------------------------------------------
+// Each thread produces 4 consecutive destination pixels: the 4 gathers are independent (memory-level parallelism) and the
+// 4*PIX output bytes leave as 32-bit stores when the destination row allows it.
 template <int PIX>   // pixel size in bytes
-__global__ void __launch_bounds__(256) resize_nn_kernel(Img src, Img dst, ResizeParams p)
+__global__ void __launch_bounds__(256) resize_nn_kernel(Img src, Img dst, ResizeParams p, int vec_ok)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     const int y = blockIdx.y;
     const int f = blockIdx.z;
-    if (x >= p.dw) return;
-    int sx = min((int)floor(__dmul_rn((double)x, p.ifx)), p.sw - 1);
-    int sy = min((int)floor(__dmul_rn((double)y, p.ify)), p.sh - 1);
-    const uchar* s = src.row<uchar>(f, sy) + (size_t)sx * PIX;
-    uchar* d = dst.row<uchar>(f, y) + (size_t)x * PIX;
-    if constexpr (PIX == 4) *(uint32_t*)d = *(const uint32_t*)s;
-    else if constexpr (PIX == 8) *(uint2*)d = *(const uint2*)s;
-    else if constexpr (PIX == 16) *(uint4*)d = *(const uint4*)s;
-    else if constexpr (PIX == 12) { const uint32_t* s4 = (const uint32_t*)s; uint32_t* d4 = (uint32_t*)d; d4[0] = s4[0]; d4[1] = s4[1]; d4[2] = s4[2]; }
-    else {
+    if (x0 >= p.dw) return;
+    const int sy = min((int)floor(__dmul_rn((double)y, p.ify)), p.sh - 1);
+    const uchar* srow = src.row<uchar>(f, sy);
+    uchar* d = dst.row<uchar>(f, y) + (size_t)x0 * PIX;
+    const int n = min(4, p.dw - x0);
+    if (vec_ok && n == 4) {
+        uint32_t out[PIX];                       // 4 pixels = 4*PIX bytes = PIX words
+        uchar* ob = (uchar*)out;
 #pragma unroll
-        for (int i = 0; i < PIX; i++) d[i] = s[i];
+        for (int k = 0; k < 4; k++) {
+            const int sx = min((int)floor(__dmul_rn((double)(x0 + k), p.ifx)), p.sw - 1);
+            const uchar* sp = srow + (size_t)sx * PIX;
+            if constexpr (PIX % 4 == 0) {
+#pragma unroll
+                for (int i = 0; i < PIX / 4; i++) out[k * (PIX / 4) + i] = ((const uint32_t*)sp)[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < PIX; i++) ob[k * PIX + i] = sp[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PIX; i++) ((uint32_t*)d)[i] = out[i];
+    } else {
+        for (int k = 0; k < n; k++) {
+            const int sx = min((int)floor(__dmul_rn((double)(x0 + k), p.ifx)), p.sw - 1);
+            const uchar* sp = srow + (size_t)sx * PIX;
+            for (int i = 0; i < PIX; i++) d[k * PIX + i] = sp[i];
+        }
     }
 }
 
@@ -74,38 +92,74 @@ __device__ __forceinline__ void cubic_coeffs(float x, float* c)
 
 __device__ __forceinline__ short coef_s16(float c) { return sat_s16(__float2int_rn(__fmul_rn(c, 2048.f))); }
 
+// ---- coefficient tables ----------------------------------------------------------------------------------------------
+// The reference tabulates per destination column / row the source index and the taps once per call on the host
+// (resize.cpp:4097-4190).  Same here, on the device: one tiny kernel fills the tables (identical arithmetic to the helpers
+// above), the main kernels only read them -- no fp64 in the per-pixel loop.
+struct ResTab {            // 32 bytes
+    int s;                 // source index (unclamped for rows / cubic columns, clamped for linear columns)
+    int last;              // linear columns: taps collapse to S[s]*ONE (dx >= xmax)
+    int pad[2];
+    union { int ic[4]; float fc[4]; };
+};
+
+template <bool CUBIC, bool FIXPT>
+__global__ void resize_tab_kernel(ResTab* xt, ResTab* yt, ResizeParams p)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool is_y = i >= p.dw;
+    const int d = is_y ? i - p.dw : i;
+    if (is_y && d >= p.dh) return;
+    int s; float fr;
+    linear_coef(d, is_y ? p.scale_y : p.scale_x, is_y ? p.sh : p.sw, s, fr, !CUBIC && !is_y);
+    ResTab t;
+    t.s = s; t.last = (!CUBIC && !is_y && s >= p.sw - 1); t.pad[0] = t.pad[1] = 0;
+    float c[4];
+    if (CUBIC) cubic_coeffs(fr, c);
+    else { c[0] = __fsub_rn(1.f, fr); c[1] = fr; c[2] = c[3] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (FIXPT) t.ic[k] = coef_s16(c[k]); else t.fc[k] = c[k]; }
+    (is_y ? yt : xt)[d] = t;
+}
+
+constexpr int RS_ROWS = 8;   // destination rows per thread
+
 // ---- LINEAR ----------------------------------------------------------------------------------------------------------
 template <typename T, int CN>
-__global__ void __launch_bounds__(256) resize_linear_kernel(Img src, Img dst, ResizeParams p)
+__global__ void __launch_bounds__(256) resize_linear_kernel(Img src, Img dst, ResizeParams p, const ResTab* __restrict__ xt, const ResTab* __restrict__ yt)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
+    const int yb = blockIdx.y * RS_ROWS;
     const int f = blockIdx.z;
     if (x >= p.dw) return;
-    int sx, sy; float fx, fy;
-    linear_coef(x, p.scale_x, p.sw, sx, fx, true);
-    linear_coef(y, p.scale_y, p.sh, sy, fy, false);      // rows are clipped when fetched, the taps keep fy (:4160-4170, :2211)
-    const int sy0 = clip_i(sy, 0, p.sh), sy1 = clip_i(sy + 1, 0, p.sh);
-    const bool last_col = sx >= p.sw - 1;                  // dx >= xmax: D = S[sx] * ONE
-    const T* r0 = src.row<T>(f, sy0) + (size_t)sx * CN;
-    const T* r1 = src.row<T>(f, sy1) + (size_t)sx * CN;
-    T* d = dst.row<T>(f, y) + (size_t)x * CN;
-    if constexpr (sizeof(T) == 1) {
-        const int a0 = coef_s16(__fsub_rn(1.f, fx)), a1 = coef_s16(fx);
-        const int b0 = coef_s16(__fsub_rn(1.f, fy)), b1 = coef_s16(fy);
+    const ResTab tx = xt[x];
+    const bool last_col = tx.last != 0;                    // dx >= xmax: D = S[sx] * ONE
+    const size_t xo = (size_t)tx.s * CN;
+#pragma unroll 2
+    for (int r = 0; r < RS_ROWS; r++) {
+        const int y = yb + r;
+        if (y >= p.dh) break;
+        const ResTab ty = yt[y];                            // uniform across the CTA: one broadcast load
+        const int sy0 = clip_i(ty.s, 0, p.sh), sy1 = clip_i(ty.s + 1, 0, p.sh);   // rows are clipped when fetched, the taps keep fy (:2211)
+        const T* r0 = src.row<T>(f, sy0) + xo;
+        const T* r1 = src.row<T>(f, sy1) + xo;
+        T* d = dst.row<T>(f, y) + (size_t)x * CN;
+        if constexpr (sizeof(T) == 1) {
+            const int a0 = tx.ic[0], a1 = tx.ic[1], b0 = ty.ic[0], b1 = ty.ic[1];
 #pragma unroll
-        for (int c = 0; c < CN; c++) {
-            int t0 = last_col ? r0[c] * 2048 : r0[c] * a0 + r0[c + CN] * a1;
-            int t1 = last_col ? r1[c] * 2048 : r1[c] * a0 + r1[c + CN] * a1;
-            d[c] = (uchar)((((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2);
-        }
-    } else {
-        const float a0 = __fsub_rn(1.f, fx), a1 = fx, b0 = __fsub_rn(1.f, fy), b1 = fy;
+            for (int c = 0; c < CN; c++) {
+                int t0 = last_col ? r0[c] * 2048 : r0[c] * a0 + r0[c + CN] * a1;
+                int t1 = last_col ? r1[c] * 2048 : r1[c] * a0 + r1[c + CN] * a1;
+                d[c] = (uchar)((((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2);
+            }
+        } else {
+            const float a0 = tx.fc[0], a1 = tx.fc[1], b0 = ty.fc[0], b1 = ty.fc[1];
 #pragma unroll
-        for (int c = 0; c < CN; c++) {
-            float t0 = last_col ? r0[c] : __fadd_rn(__fmul_rn(r0[c], a0), __fmul_rn(r0[c + CN], a1));
-            float t1 = last_col ? r1[c] : __fadd_rn(__fmul_rn(r1[c], a0), __fmul_rn(r1[c + CN], a1));
-            d[c] = __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, b1));
+            for (int c = 0; c < CN; c++) {
+                float t0 = last_col ? r0[c] : __fadd_rn(__fmul_rn(r0[c], a0), __fmul_rn(r0[c + CN], a1));
+                float t1 = last_col ? r1[c] : __fadd_rn(__fmul_rn(r1[c], a0), __fmul_rn(r1[c + CN], a1));
+                d[c] = __fadd_rn(__fmul_rn(t0, b0), __fmul_rn(t1, b1));
+            }
         }
     }
 }
@@ -162,76 +216,74 @@ __global__ void __launch_bounds__(256) resize_area2_f32_kernel(Img src, Img dst,
 
 // ---- CUBIC ---------------------------------------------------------------------------------------------------------------
 template <typename T, int CN>
-__global__ void __launch_bounds__(256) resize_cubic_kernel(Img src, Img dst, ResizeParams p)
+__global__ void __launch_bounds__(256) resize_cubic_kernel(Img src, Img dst, ResizeParams p, const ResTab* __restrict__ xt, const ResTab* __restrict__ yt)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
+    const int yb = blockIdx.y * RS_ROWS;
     const int f = blockIdx.z;
     if (x >= p.dw) return;
-    int sx, sy; float fx, fy;
-    linear_coef(x, p.scale_x, p.sw, sx, fx, false);
-    linear_coef(y, p.scale_y, p.sh, sy, fy, false);
-    float cx[4], cy[4];
-    cubic_coeffs(fx, cx);
-    cubic_coeffs(fy, cy);
+    const ResTab tx = xt[x];
     int xi[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) xi[j] = min(max(sx - 1 + j, 0), p.sw - 1);    // per-tap clamping == the while-loops of HResizeCubic
-    const T* rows[4];
+    for (int j = 0; j < 4; j++) xi[j] = min(max(tx.s - 1 + j, 0), p.sw - 1) * CN;    // per-tap clamping == the while-loops of HResizeCubic
+#pragma unroll 1
+    for (int r = 0; r < RS_ROWS; r++) {
+        const int y = yb + r;
+        if (y >= p.dh) break;
+        const ResTab ty = yt[y];
+        const T* rows[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) rows[k] = src.row<T>(f, clip_i(sy - 1 + k, 0, p.sh));
-    T* d = dst.row<T>(f, y) + (size_t)x * CN;
-    if constexpr (sizeof(T) == 1) {
-        int ia[4], ib[4];
+        for (int k = 0; k < 4; k++) rows[k] = src.row<T>(f, clip_i(ty.s - 1 + k, 0, p.sh));
+        T* d = dst.row<T>(f, y) + (size_t)x * CN;
+        if constexpr (sizeof(T) == 1) {
+            const int vec_limit = ((p.dw * CN) / 8) * 8;
+            const float sc = 1.f / (2048.f * 2048.f);
 #pragma unroll
-        for (int j = 0; j < 4; j++) { ia[j] = coef_s16(cx[j]); ib[j] = coef_s16(cy[j]); }
-        const int vec_limit = ((p.dw * CN) / 8) * 8;
-        const float sc = 1.f / (2048.f * 2048.f);
+            for (int c = 0; c < CN; c++) {
+                int t[4];
 #pragma unroll
-        for (int c = 0; c < CN; c++) {
-            int t[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uchar* r = rows[k];
-                t[k] = r[xi[0] * CN + c] * ia[0] + r[xi[1] * CN + c] * ia[1] + r[xi[2] * CN + c] * ia[2] + r[xi[3] * CN + c] * ia[3];
+                for (int k = 0; k < 4; k++) {
+                    const uchar* rr = rows[k] + c;
+                    t[k] = rr[xi[0]] * tx.ic[0] + rr[xi[1]] * tx.ic[1] + rr[xi[2]] * tx.ic[2] + rr[xi[3]] * tx.ic[3];
+                }
+                if (x * CN + c < vec_limit) {
+                    float v = __fmul_rn((float)t[3], __fmul_rn((float)ty.ic[3], sc));
+                    v = __fadd_rn(__fmul_rn((float)t[2], __fmul_rn((float)ty.ic[2], sc)), v);
+                    v = __fadd_rn(__fmul_rn((float)t[1], __fmul_rn((float)ty.ic[1], sc)), v);
+                    v = __fadd_rn(__fmul_rn((float)t[0], __fmul_rn((float)ty.ic[0], sc)), v);
+                    d[c] = sat_u8(__float2int_rn(v));
+                } else {
+                    d[c] = sat_u8((t[0] * ty.ic[0] + t[1] * ty.ic[1] + t[2] * ty.ic[2] + t[3] * ty.ic[3] + (1 << 21)) >> 22);
+                }
             }
-            if (x * CN + c < vec_limit) {
-                float v = __fmul_rn((float)t[3], __fmul_rn((float)ib[3], sc));
-                v = __fadd_rn(__fmul_rn((float)t[2], __fmul_rn((float)ib[2], sc)), v);
-                v = __fadd_rn(__fmul_rn((float)t[1], __fmul_rn((float)ib[1], sc)), v);
-                v = __fadd_rn(__fmul_rn((float)t[0], __fmul_rn((float)ib[0], sc)), v);
-                d[c] = sat_u8(__float2int_rn(v));
-            } else {
-                d[c] = sat_u8((t[0] * ib[0] + t[1] * ib[1] + t[2] * ib[2] + t[3] * ib[3] + (1 << 21)) >> 22);
-            }
-        }
-    } else {
-        const int vec_limit = ((p.dw * CN) / 4) * 4;
+        } else {
+            const int vec_limit = ((p.dw * CN) / 4) * 4;
 #pragma unroll
-        for (int c = 0; c < CN; c++) {
-            float t[4];
+            for (int c = 0; c < CN; c++) {
+                float t[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float* r = rows[k];
-                float v = __fmul_rn(r[xi[0] * CN + c], cx[0]);
-                v = __fadd_rn(v, __fmul_rn(r[xi[1] * CN + c], cx[1]));
-                v = __fadd_rn(v, __fmul_rn(r[xi[2] * CN + c], cx[2]));
-                v = __fadd_rn(v, __fmul_rn(r[xi[3] * CN + c], cx[3]));
-                t[k] = v;
+                for (int k = 0; k < 4; k++) {
+                    const float* rr = rows[k] + c;
+                    float v = __fmul_rn(rr[xi[0]], tx.fc[0]);
+                    v = __fadd_rn(v, __fmul_rn(rr[xi[1]], tx.fc[1]));
+                    v = __fadd_rn(v, __fmul_rn(rr[xi[2]], tx.fc[2]));
+                    v = __fadd_rn(v, __fmul_rn(rr[xi[3]], tx.fc[3]));
+                    t[k] = v;
+                }
+                float o;
+                if (x * CN + c < vec_limit) {
+                    o = __fmul_rn(t[3], ty.fc[3]);
+                    o = __fadd_rn(__fmul_rn(t[2], ty.fc[2]), o);
+                    o = __fadd_rn(__fmul_rn(t[1], ty.fc[1]), o);
+                    o = __fadd_rn(__fmul_rn(t[0], ty.fc[0]), o);
+                } else {
+                    o = __fmul_rn(t[0], ty.fc[0]);
+                    o = __fadd_rn(o, __fmul_rn(t[1], ty.fc[1]));
+                    o = __fadd_rn(o, __fmul_rn(t[2], ty.fc[2]));
+                    o = __fadd_rn(o, __fmul_rn(t[3], ty.fc[3]));
+                }
+                d[c] = o;
             }
-            float o;
-            if (x * CN + c < vec_limit) {
-                o = __fmul_rn(t[3], cy[3]);
-                o = __fadd_rn(__fmul_rn(t[2], cy[2]), o);
-                o = __fadd_rn(__fmul_rn(t[1], cy[1]), o);
-                o = __fadd_rn(__fmul_rn(t[0], cy[0]), o);
-            } else {
-                o = __fmul_rn(t[0], cy[0]);
-                o = __fadd_rn(o, __fmul_rn(t[1], cy[1]));
-                o = __fadd_rn(o, __fmul_rn(t[2], cy[2]));
-                o = __fadd_rn(o, __fmul_rn(t[3], cy[3]));
-            }
-            d[c] = o;
         }
     }
 }
@@ -239,15 +291,26 @@ __global__ void __launch_bounds__(256) resize_cubic_kernel(Img src, Img dst, Res
 template <typename T>
 static int launch_by_cn(int cn, int interp, const Img& s, const Img& d, const ResizeParams& p, cudaStream_t st)
 {
-    dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
-#define L(K, CN) K<T, CN><<<grid, 256, 0, st>>>(s, d, p)
+    ResTab* tab = nullptr;
+    B200_CUDA(cudaMallocAsync(&tab, sizeof(ResTab) * (size_t)(p.dw + p.dh), st));
+    ResTab *xt = tab, *yt = tab + p.dw;
+    const unsigned nt = div_up((unsigned)(p.dw + p.dh), 256);
+    constexpr bool FIX = sizeof(T) == 1;
+    if (interp == B200CV_INTER_LINEAR) resize_tab_kernel<false, FIX><<<nt, 256, 0, st>>>(xt, yt, p);
+    else resize_tab_kernel<true, FIX><<<nt, 256, 0, st>>>(xt, yt, p);
+    count_launch();
+    dim3 grid(div_up((unsigned)p.dw, 256), div_up((unsigned)p.dh, RS_ROWS), (unsigned)s.frames);
+#define L(K, CN) K<T, CN><<<grid, 256, 0, st>>>(s, d, p, xt, yt)
     if (interp == B200CV_INTER_LINEAR) {
         if (cn == 1) L(resize_linear_kernel, 1); else if (cn == 3) L(resize_linear_kernel, 3); else L(resize_linear_kernel, 4);
     } else {
         if (cn == 1) L(resize_cubic_kernel, 1); else if (cn == 3) L(resize_cubic_kernel, 3); else L(resize_cubic_kernel, 4);
     }
 #undef L
-    B200_LAUNCH_CHECK();
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(tab, st);
+    count_launch();
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
     return B200CV_OK;
 }
 
@@ -280,12 +343,14 @@ extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int int
     dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
 
     if (interpolation == B200CV_INTER_NEAREST) {
+        dim3 g4(div_up(div_up((unsigned)p.dw, 4), 128), (unsigned)p.dh, (unsigned)s.frames);
+        int vec_ok = (((uintptr_t)d.data | d.step | d.fstep) & 3) == 0 && (pix % 4 != 0 || (((uintptr_t)s.data | s.step | s.fstep) & 3) == 0);
         switch (pix) {
-        case 1: resize_nn_kernel<1><<<grid, 256, 0, st>>>(s, d, p); break;
-        case 3: resize_nn_kernel<3><<<grid, 256, 0, st>>>(s, d, p); break;
-        case 4: resize_nn_kernel<4><<<grid, 256, 0, st>>>(s, d, p); break;
-        case 12: resize_nn_kernel<12><<<grid, 256, 0, st>>>(s, d, p); break;
-        case 16: resize_nn_kernel<16><<<grid, 256, 0, st>>>(s, d, p); break;
+        case 1: resize_nn_kernel<1><<<g4, 128, 0, st>>>(s, d, p, vec_ok); break;
+        case 3: resize_nn_kernel<3><<<g4, 128, 0, st>>>(s, d, p, vec_ok); break;
+        case 4: resize_nn_kernel<4><<<g4, 128, 0, st>>>(s, d, p, vec_ok); break;
+        case 12: resize_nn_kernel<12><<<g4, 128, 0, st>>>(s, d, p, vec_ok); break;
+        case 16: resize_nn_kernel<16><<<g4, 128, 0, st>>>(s, d, p, vec_ok); break;
         default: return B200CV_NOT_IMPLEMENTED;
         }
         B200_LAUNCH_CHECK();
