@@ -1,0 +1,270 @@
+/* oracle/port/port_geometry.c -- cv::resize / cv::warpAffine / cv::warpPerspective restated in scalar C.
+ * TEST INFRASTRUCTURE ONLY (see port_common.h).
+ *   hal::resize               modules/imgproc/src/resize.cpp:3826-4194 (tables :4097-4190)
+ *   resizeNN                  :1121-1172 ; HResizeLinear :1877-1928 ; VResizeLinear<uchar> :1963-1989
+ *   HResizeCubic              :1993-2041 ; VResizeCubic + VResizeCubicVec_32s8u (SSE body) :1408-1444, :2044-2062
+ *   resizeAreaFast (2x2)      :2919-3068
+ *   cv::warpAffine            modules/imgproc/src/imgwarp.cpp:2788-2902, hal::warpAffine :2673-2700, blocklines :2702-2782
+ *   cv::warpPerspective       :3370-3466, WarpPerspectiveInvoker :3160-3226, blocklines :3299-3365, cv::invert 3x3 core/src/lapack.cpp:944-970
+ *   remapNearest/Bilinear/Bicubic :329-430, :675-904, :907-1010 ; initInterTab2D :213-287
+ */
+#include "port_common.h"
+
+static int clipi(int x, int a, int b) { return x >= a ? (x < b ? x : b - 1) : a; }
+
+static void cubic_c(float x, float* c)
+{
+    const float A = -0.75f;
+    c[0] = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A;
+    c[1] = ((A + 2) * x - (A + 3)) * x * x + 1;
+    c[2] = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1;
+    c[3] = 1.f - c[0] - c[1] - c[2];
+}
+
+static short s16(float v) { return port_sat_s16i((int)lrintf(v)); }
+
+#define SRC(y, x, c) (depth == P_8U ? (float)((const uchar*)src + (size_t)(y) * sstep)[(x) * cn + (c)] : ((const float*)((const char*)src + (size_t)(y) * sstep))[(x) * cn + (c)])
+
+PORT_API int port_resize(const void* src, size_t sstep, int sw, int sh, void* dst, size_t dstep, int dw, int dh, int type, int interp)
+{
+    int depth = P_DEPTH(type), cn = P_CN(type), es = (int)port_esz(depth) * cn;
+    double inv_x = (double)dw / sw, inv_y = (double)dh / sh, scale_x = 1. / inv_x, scale_y = 1. / inv_y;
+    if (depth != P_8U && depth != P_32F) return 1;
+    if (dw == sw && dh == sh) {
+        for (int y = 0; y < sh; y++) memcpy((char*)dst + (size_t)y * dstep, (const char*)src + (size_t)y * sstep, (size_t)sw * es);
+        return 0;
+    }
+    if (interp == 0) {
+        double ifx = 1. / inv_x, ify = 1. / inv_y;
+        for (int y = 0; y < dh; y++) {
+            int sy = (int)floor(y * ify); if (sy > sh - 1) sy = sh - 1;
+            for (int x = 0; x < dw; x++) {
+                int sx = (int)floor(x * ifx); if (sx > sw - 1) sx = sw - 1;
+                memcpy((char*)dst + (size_t)y * dstep + (size_t)x * es, (const char*)src + (size_t)sy * sstep + (size_t)sx * es, es);
+            }
+        }
+        return 0;
+    }
+    int isx = port_round(scale_x), isy = port_round(scale_y);
+    int area_fast = fabs(scale_x - isx) < 2.220446049250313e-16 && fabs(scale_y - isy) < 2.220446049250313e-16;
+    if ((interp == 1 || interp == 3) && area_fast && isx == 2 && isy == 2) {
+        for (int y = 0; y < dh; y++)
+            for (int x = 0; x < dw; x++)
+                for (int c = 0; c < cn; c++) {
+                    if (depth == P_8U) {
+                        const uchar* s0 = (const uchar*)src + (size_t)(2 * y) * sstep + 2 * x * cn + c; const uchar* s1 = s0 + sstep;
+                        ((uchar*)dst + (size_t)y * dstep)[x * cn + c] = (uchar)((s0[0] + s0[cn] + s1[0] + s1[cn] + 2) >> 2);
+                    } else {
+                        const float* s0 = (const float*)((const char*)src + (size_t)(2 * y) * sstep) + 2 * x * cn + c;
+                        const float* s1 = (const float*)((const char*)s0 + sstep);
+                        float sum = (cn == 1 || cn == 4) ? (s0[0] + s0[cn]) + (s1[0] + s1[cn]) : ((s0[0] + s0[cn]) + s1[0]) + s1[cn];
+                        ((float*)((char*)dst + (size_t)y * dstep))[x * cn + c] = sum * 0.25f;
+                    }
+                }
+        return 0;
+    }
+    if (interp != 1 && interp != 2) return 1;
+    int cubic = interp == 2;
+    /* tables */
+    int* xs = (int*)malloc(sizeof(int) * (dw + dh)); int* ys = xs + dw;
+    float* xa = (float*)malloc(sizeof(float) * 4 * (dw + dh)); float* ya = xa + 4 * dw;
+    for (int pass = 0; pass < 2; pass++) {
+        int dn = pass ? dh : dw, sn = pass ? sh : sw; double sc = pass ? scale_y : scale_x;
+        for (int d = 0; d < dn; d++) {
+            float f = (float)((d + 0.5) * sc - 0.5);
+            int s = (int)floorf(f); f -= s;
+            if (!cubic && !pass) { if (s < 0) { f = 0; s = 0; } if (s >= sn - 1) { f = 0; s = sn - 1; } }
+            float* c = (pass ? ya : xa) + 4 * d;
+            if (cubic) cubic_c(f, c); else { c[0] = 1.f - f; c[1] = f; c[2] = c[3] = 0; }
+            (pass ? ys : xs)[d] = s;
+        }
+    }
+    int vec8 = ((dw * cn) / 8) * 8, vec4 = ((dw * cn) / 4) * 4;
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++)
+            for (int c = 0; c < cn; c++) {
+                int e = x * cn + c;
+                if (!cubic) {
+                    int sy0 = clipi(ys[y], 0, sh), sy1 = clipi(ys[y] + 1, 0, sh), sx = xs[x], last = sx >= sw - 1;
+                    if (depth == P_8U) {
+                        int a0 = s16(xa[4 * x] * 2048.f), a1 = s16(xa[4 * x + 1] * 2048.f), b0 = s16(ya[4 * y] * 2048.f), b1 = s16(ya[4 * y + 1] * 2048.f);
+                        const uchar* r0 = (const uchar*)src + (size_t)sy0 * sstep + sx * cn + c; const uchar* r1 = (const uchar*)src + (size_t)sy1 * sstep + sx * cn + c;
+                        int t0 = last ? r0[0] * 2048 : r0[0] * a0 + r0[cn] * a1, t1 = last ? r1[0] * 2048 : r1[0] * a0 + r1[cn] * a1;
+                        ((uchar*)dst + (size_t)y * dstep)[e] = (uchar)((((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2);
+                    } else {
+                        float a0 = xa[4 * x], a1 = xa[4 * x + 1], b0 = ya[4 * y], b1 = ya[4 * y + 1];
+                        const float* r0 = (const float*)((const char*)src + (size_t)sy0 * sstep) + sx * cn + c; const float* r1 = (const float*)((const char*)src + (size_t)sy1 * sstep) + sx * cn + c;
+                        float t0 = last ? r0[0] : r0[0] * a0 + r0[cn] * a1, t1 = last ? r1[0] : r1[0] * a0 + r1[cn] * a1;
+                        ((float*)((char*)dst + (size_t)y * dstep))[e] = t0 * b0 + t1 * b1;
+                    }
+                } else {
+                    int xi[4], yi[4];
+                    for (int j = 0; j < 4; j++) { xi[j] = clipi(xs[x] - 1 + j, 0, sw); yi[j] = clipi(ys[y] - 1 + j, 0, sh); }
+                    if (depth == P_8U) {
+                        int ia[4], ib[4], t[4];
+                        for (int j = 0; j < 4; j++) { ia[j] = s16(xa[4 * x + j] * 2048.f); ib[j] = s16(ya[4 * y + j] * 2048.f); }
+                        for (int k = 0; k < 4; k++) { const uchar* r = (const uchar*)src + (size_t)yi[k] * sstep; t[k] = 0; for (int j = 0; j < 4; j++) t[k] += r[xi[j] * cn + c] * ia[j]; }
+                        uchar o;
+                        if (e < vec8) {      /* SSE body: float, S0*b0 + (S1*b1 + (S2*b2 + S3*b3)), b = beta/2^22, round-half-even */
+                            const float sc = 1.f / (2048.f * 2048.f);
+                            float v = (float)t[3] * (ib[3] * sc);
+                            v = (float)t[2] * (ib[2] * sc) + v; v = (float)t[1] * (ib[1] * sc) + v; v = (float)t[0] * (ib[0] * sc) + v;
+                            o = port_sat_u8i((int)lrintf(v));
+                        } else o = port_sat_u8i((t[0] * ib[0] + t[1] * ib[1] + t[2] * ib[2] + t[3] * ib[3] + (1 << 21)) >> 22);
+                        ((uchar*)dst + (size_t)y * dstep)[e] = o;
+                    } else {
+                        float t[4];
+                        for (int k = 0; k < 4; k++) {
+                            const float* r = (const float*)((const char*)src + (size_t)yi[k] * sstep);
+                            float v = r[xi[0] * cn + c] * xa[4 * x]; v += r[xi[1] * cn + c] * xa[4 * x + 1]; v += r[xi[2] * cn + c] * xa[4 * x + 2]; v += r[xi[3] * cn + c] * xa[4 * x + 3];
+                            t[k] = v;
+                        }
+                        const float* b = ya + 4 * y; float o;
+                        if (e < vec4) { o = t[3] * b[3]; o = t[2] * b[2] + o; o = t[1] * b[1] + o; o = t[0] * b[0] + o; }
+                        else { o = t[0] * b[0]; o += t[1] * b[1]; o += t[2] * b[2]; o += t[3] * b[3]; }
+                        ((float*)((char*)dst + (size_t)y * dstep))[e] = o;
+                    }
+                }
+            }
+    free(xs); free(xa);
+    return 0;
+}
+
+/* ---- remap tables ---- */
+static float g_lin_f[1024 * 4], g_cub_f[1024 * 16];
+static short g_lin_i[1024 * 4], g_cub_i[1024 * 16];
+static void build_tabs(void)
+{
+    static int done = 0;
+    if (done) return;
+    for (int ks = 2; ks <= 4; ks += 2) {
+        float t1[32 * 4]; float* ft = ks == 2 ? g_lin_f : g_cub_f; short* it = ks == 2 ? g_lin_i : g_cub_i;
+        for (int i = 0; i < 32; i++) { float x = i * (1.f / 32); if (ks == 2) { t1[i * 2] = 1.f - x; t1[i * 2 + 1] = x; } else cubic_c(x, t1 + i * 4); }
+        for (int iy = 0; iy < 32; iy++)
+            for (int ix = 0; ix < 32; ix++) {
+                float* f = ft + (iy * 32 + ix) * ks * ks; short* q = it + (iy * 32 + ix) * ks * ks; int total = 0;
+                for (int a = 0; a < ks; a++) for (int b = 0; b < ks; b++) { float v = t1[iy * ks + a] * t1[ix * ks + b]; f[a * ks + b] = v; q[a * ks + b] = s16(v * 32768.f); total += q[a * ks + b]; }
+                int res = total - 32768;
+                if (res && ks == 2) q[3] = (short)(q[3] - res);
+                else if (res) {
+                    int lo = 10, hi = 10; const int idx[4] = {10, 11, 14, 15};
+                    for (int k = 0; k < 4; k++) { if (q[idx[k]] < q[lo]) lo = idx[k]; else if (q[idx[k]] > q[hi]) hi = idx[k]; }
+                    int tg = res < 0 ? hi : lo; q[tg] = (short)(q[tg] - res);
+                }
+            }
+    }
+    done = 1;
+}
+
+static int warp_impl(const void* src, size_t sstep, int sw, int sh, void* dst, size_t dstep, int dw, int dh, int type, const double* M, int persp,
+                     int interp, int border, const double* bv)
+{
+    int depth = P_DEPTH(type), cn = P_CN(type);
+    if (depth != P_8U && depth != P_32F) return 1;
+    if (interp == 3) interp = 1;
+    if (interp > 2) return 1;
+    build_tabs();
+    border &= ~16;
+    float cvf[4]; int cvi[4];
+    for (int c = 0; c < 4; c++) { cvf[c] = (float)bv[c]; cvi[c] = port_sat_u8i((int)lrint(bv[c])); }
+    int bh0 = dh < 16 ? dh : 16, bw0 = 1024 / bh0; if (bw0 > dw) bw0 = dw;
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++) {
+            int sx, sy, a = 0;
+            if (!persp) {
+                int rd = interp == 0 ? 512 : 16;
+                int ad = port_round(M[0] * x * 1024), bd = port_round(M[3] * x * 1024);
+                int X0 = port_round((M[1] * y + M[2]) * 1024) + rd, Y0 = port_round((M[4] * y + M[5]) * 1024) + rd;
+                if (interp == 0) { sx = port_sat_s16i((X0 + ad) >> 10); sy = port_sat_s16i((Y0 + bd) >> 10); }
+                else { int X = (X0 + ad) >> 5, Y = (Y0 + bd) >> 5; sx = port_sat_s16i(X >> 5); sy = port_sat_s16i(Y >> 5); a = (Y & 31) * 32 + (X & 31); }
+            } else {
+                int xb = (x / bw0) * bw0, x1 = x - xb;
+                double X0 = M[0] * xb + M[1] * y + M[2], Y0 = M[3] * xb + M[4] * y + M[5], W0 = M[6] * xb + M[7] * y + M[8];
+                double W = W0 + M[6] * x1; W = W ? (interp == 0 ? 1. : 32.) / W : 0;
+                double fX = fmax(-2147483648.0, fmin(2147483647.0, (X0 + M[0] * x1) * W)), fY = fmax(-2147483648.0, fmin(2147483647.0, (Y0 + M[3] * x1) * W));
+                int X = port_round(fX), Y = port_round(fY);
+                if (interp == 0) { sx = port_sat_s16i(X); sy = port_sat_s16i(Y); } else { sx = port_sat_s16i(X >> 5); sy = port_sat_s16i(Y >> 5); a = (Y & 31) * 32 + (X & 31); }
+            }
+            for (int c = 0; c < cn; c++) {
+                float outf = 0; int outi = 0;
+#define PIX(yy, xx) (((yy) < 0 || (xx) < 0) ? (depth == P_8U ? (float)cvi[c] : cvf[c]) : SRC(yy, xx, c))
+                if (interp == 0) {
+                    int qx, qy;
+                    if ((unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh) { qx = sx; qy = sy; }
+                    else if (border == PB_REPLICATE) { qx = clipi(sx, 0, sw); qy = clipi(sy, 0, sh); }
+                    else if (border == PB_CONSTANT) { qx = qy = -1; }
+                    else { qx = port_border(sx, sw, border); qy = port_border(sy, sh, border); }
+                    outf = PIX(qy, qx); outi = (int)outf;
+                } else if (interp == 1) {
+                    if (border == PB_CONSTANT && (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0)) { outf = cvf[c]; outi = cvi[c]; }
+                    else {
+                        int x0, x1, y0, y1;
+                        if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) { x0 = sx; x1 = sx + 1; y0 = sy; y1 = sy + 1; }
+                        else if (border == PB_REPLICATE) { x0 = clipi(sx, 0, sw); x1 = clipi(sx + 1, 0, sw); y0 = clipi(sy, 0, sh); y1 = clipi(sy + 1, 0, sh); }
+                        else { x0 = port_border(sx, sw, border); x1 = port_border(sx + 1, sw, border); y0 = port_border(sy, sh, border); y1 = port_border(sy + 1, sh, border); }
+                        float v0 = PIX(y0, x0), v1 = PIX(y0, x1), v2 = PIX(y1, x0), v3 = PIX(y1, x1);
+                        if (depth == P_8U) { const short* w = g_lin_i + a * 4; outi = port_sat_u8i(((int)v0 * w[0] + (int)v1 * w[1] + (int)v2 * w[2] + (int)v3 * w[3] + (1 << 14)) >> 15); }
+                        else { const float* w = g_lin_f + a * 4; outf = v0 * w[0] + v1 * w[1] + v2 * w[2] + v3 * w[3]; }
+                    }
+                } else {
+                    int bx = sx - 1, by = sy - 1;
+                    int inl = (unsigned)bx < (unsigned)(sw - 3 > 0 ? sw - 3 : 0) && (unsigned)by < (unsigned)(sh - 3 > 0 ? sh - 3 : 0);
+                    if (!inl && border == PB_CONSTANT && (bx >= sw || bx + 4 <= 0 || by >= sh || by + 4 <= 0)) { outf = cvf[c]; outi = cvi[c]; }
+                    else {
+                        int xs4[4], ys4[4];
+                        for (int i = 0; i < 4; i++) { xs4[i] = inl ? bx + i : port_border(bx + i, sw, border); ys4[i] = inl ? by + i : port_border(by + i, sh, border); }
+                        if (depth == P_8U) {
+                            const short* w = g_cub_i + a * 16; int sum = 0;
+                            for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) sum += (int)PIX(ys4[i], xs4[j]) * w[i * 4 + j];
+                            outi = port_sat_u8i((sum + (1 << 14)) >> 15);
+                        } else {
+                            const float* w = g_cub_f + a * 16;
+                            if (inl) {
+                                float sum = 0;
+                                for (int i = 0; i < 4; i++) { float rs = SRC(ys4[i], xs4[0], c) * w[i * 4] + SRC(ys4[i], xs4[1], c) * w[i * 4 + 1] + SRC(ys4[i], xs4[2], c) * w[i * 4 + 2] + SRC(ys4[i], xs4[3], c) * w[i * 4 + 3]; sum = i ? sum + rs : rs; }
+                                outf = sum;
+                            } else {
+                                float cv = cvf[c], sum = cv;
+                                for (int i = 0; i < 4; i++) { if (ys4[i] < 0) continue; for (int j = 0; j < 4; j++) if (xs4[j] >= 0) sum += (SRC(ys4[i], xs4[j], c) - cv) * w[i * 4 + j]; }
+                                outf = sum;
+                            }
+                        }
+                    }
+                }
+                if (depth == P_8U) ((uchar*)dst + (size_t)y * dstep)[x * cn + c] = (uchar)outi;
+                else ((float*)((char*)dst + (size_t)y * dstep))[x * cn + c] = outf;
+            }
+        }
+    return 0;
+}
+
+PORT_API int port_warp_affine(const void* src, size_t sstep, int sw, int sh, void* dst, size_t dstep, int dw, int dh, int type, const double* M0,
+                              int flags, int border, const double* bv)
+{
+    double M[9] = {M0[0], M0[1], M0[2], M0[3], M0[4], M0[5], 0, 0, 1};
+    if (!(flags & 16)) {
+        double D = M[0] * M[4] - M[1] * M[3]; D = D != 0 ? 1. / D : 0;
+        double A11 = M[4] * D, A22 = M[0] * D;
+        M[0] = A11; M[1] *= -D; M[3] *= -D; M[4] = A22;
+        double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
+        M[2] = b1; M[5] = b2;
+    }
+    return warp_impl(src, sstep, sw, sh, dst, dstep, dw, dh, type, M, 0, flags & 7, border, bv);
+}
+
+PORT_API int port_warp_perspective(const void* src, size_t sstep, int sw, int sh, void* dst, size_t dstep, int dw, int dh, int type, const double* m,
+                                   int flags, int border, const double* bv)
+{
+    double M[9];
+    memcpy(M, m, sizeof(M));
+    if (!(flags & 16)) {
+        double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+        if (det != 0.) {
+            double d = 1. / det;
+            M[0] = (m[4] * m[8] - m[5] * m[7]) * d; M[1] = (m[2] * m[7] - m[1] * m[8]) * d; M[2] = (m[1] * m[5] - m[2] * m[4]) * d;
+            M[3] = (m[5] * m[6] - m[3] * m[8]) * d; M[4] = (m[0] * m[8] - m[2] * m[6]) * d; M[5] = (m[2] * m[3] - m[0] * m[5]) * d;
+            M[6] = (m[3] * m[7] - m[4] * m[6]) * d; M[7] = (m[1] * m[6] - m[0] * m[7]) * d; M[8] = (m[0] * m[4] - m[1] * m[3]) * d;
+        } else memset(M, 0, sizeof(M));
+    }
+    return warp_impl(src, sstep, sw, sh, dst, dstep, dw, dh, type, M, 1, flags & 7, border, bv);
+}
