@@ -11,10 +11,14 @@
 //       f32: same blocking with FFMA.
 //   * window sums  sum I, sum I^2 over each w x h window in f64 (exact for u8): separable sliding sums.
 //   * normalisation: the formulas and clamps of common_matchTemplate :975-1026, in f64, per output.
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "common.cuh"
 
 namespace b200cv {
+
+int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, cudaStream_t st);
 
 constexpr int MT_T = 64;     // outputs per CTA side
 constexpr int MT_R = 4;      // outputs per thread side
@@ -281,7 +285,17 @@ extern "C" int b200cv_match_template(const b200cvMat* image, const b200cvMat* te
     const int frames = im.frames;
     dim3 grid(div_up((unsigned)ow, MT_T), div_up((unsigned)oh, MT_T), (unsigned)frames);
 
-    if (u8) {
+    bool done = false;
+    if (u8 && (long long)w * h <= 33025) {      // tensor-core path (matchtemplate_tc.cu): s32 accumulators stay exact (65025*w*h < 2^31)
+        const char* force = getenv("B200CV_MATCHTEMPLATE_PATH");
+        if (!(force && !strcmp(force, "dp4a"))) {
+            rc = ccorr_u8_tensor(im, tp, rs, w, h, st);
+            if (rc == B200CV_OK) done = true;
+            else if (rc != B200CV_NOT_IMPLEMENTED) return rc;
+        }
+    }
+    if (done) {
+    } else if (u8) {
         if ((long long)w * h > 66051) return B200CV_NOT_IMPLEMENTED;   // u32 accumulators stay exact
         int wpad = (w + 3) & ~3;
         size_t smem = (((size_t)h * wpad + 15) & ~(size_t)15) + (size_t)(MT_T + h - 1) * (MT_T + wpad + 4) + 16;
@@ -296,7 +310,7 @@ extern "C" int b200cv_match_template(const b200cvMat* image, const b200cvMat* te
         if (!a) { B200_CUDA(cudaFuncSetAttribute(ccorr_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a = true; }
         ccorr_f32_kernel<<<grid, 256, smem, st>>>(im, tp, rs, w, h);
     }
-    B200_LAUNCH_CHECK();
+    if (!done) B200_LAUNCH_CHECK();
     if (method == B200CV_TM_CCORR) return B200CV_OK;
 
     // workspace (stream-ordered): row sums, window sums, template statistics

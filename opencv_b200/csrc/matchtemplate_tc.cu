@@ -1,0 +1,197 @@
+// matchtemplate_tc.cu -- the matchTemplate correlation numerator on 5th-generation tensor cores (tcgen05, kind::i8).
+//
+//   R(y, x) = sum_{v<h} sum_{u<w} T(v,u) * I(y+v, x+u)          8-bit image and template, exact 32-bit integer result
+//
+// is a dense contraction with N = 1 per window.  To give the MMA a useful N the template row is expanded into a banded
+// (Toeplitz) operand: for an x-tile of 64 outputs and one template row v
+//   D[m][j] += sum_{k<128} A_v[m][k] * B_v[k][j],   A_v[m][k] = I(y0+m+v, x0+k),   B_v[k][j] = T(v, k-j) (0 outside [0,w))
+// A_v is a plain 128-byte-wide box of image rows -- NO im2col is materialised: the CTA stages rows y0 .. y0+M+h-2 once
+// (TMA, 16-byte-column boxes = the canonical K-major no-swizzle core-matrix layout) and the A descriptor of step v simply
+// starts v rows (v*16 bytes) further down.  B_v (8 KB) is pre-expanded once per call into global memory in the same layout
+// and streamed through a 4-stage cp.async.bulk ring.  One elected thread issues tcgen05.mma (M=128, N=64, K=32, u8 x u8 ->
+// s32, accumulators in TMEM, two M-tiles per CTA share every B_v), tcgen05.commit frees ring slots and publishes the
+// accumulator; all four warps read it back with tcgen05.ld and store float(R).  Half of B is zeros (2.1x redundant MACs),
+// the price of a well-shaped MMA; the result is exact because products <= 65025 and sums < 2^31.
+//
+// Reference: crossCorr, modules/imgproc/src/templmatch.cpp:566-760 (block DFT in float on one thread).
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace b200cv {
+
+constexpr int TC_N = 64;          // outputs per x-tile (MMA N)
+constexpr int TC_K = 128;         // K per template row: w + N - 1 <= 128
+constexpr int TC_MT = 2;          // M-tiles (of 128 rows) per CTA
+constexpr int TC_NS = 4;          // B ring stages
+constexpr int TC_BBYTES = TC_N * TC_K;   // 8192
+
+// B_v in smem/global: [k-chunk c (8)][column j (64)][16 bytes]: byte b = T(v, 16c + b - j)
+__global__ void toeplitz_kernel(Img templ, int w, int h, unsigned char* out)
+{
+    const int v = blockIdx.x;
+    for (int idx = threadIdx.x; idx < TC_BBYTES; idx += blockDim.x) {
+        int c = idx >> 10, j = (idx >> 4) & 63, b = idx & 15;
+        int u = 16 * c + b - j;
+        out[(size_t)v * TC_BBYTES + idx] = (u >= 0 && u < w) ? templ.row<uchar>(0, v)[u] : (uchar)0;
+    }
+}
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    // K-major, no swizzle: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=0 [61,64)
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+          "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+          "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+struct TCParams {
+    int h, ra_alloc, box_h, nbox;       // template rows; staged image rows (allocated), rows per TMA box, boxes per column chunk
+    int ow, oh;
+};
+
+__global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const CUtensorMap* __restrict__ tmap, const unsigned char* __restrict__ bglob, Img res, TCParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sA = smem;                                          // 8 chunks x ra_alloc rows x 16 B
+    unsigned char* sB = smem + (size_t)8 * p.ra_alloc * 16;            // TC_NS x 8 KB
+    __shared__ __align__(8) uint64_t full[TC_NS], empty[TC_NS], a_full, acc_full;
+    __shared__ uint32_t s_tmem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.z, x0 = blockIdx.x * TC_N, y0 = blockIdx.y * (128 * TC_MT);
+    const uint32_t lbo_a = (uint32_t)p.ra_alloc * 16u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&a_full, 1); mbar_init(&acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {   // TMEM: TC_MT x 64 columns of 32-bit accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TC_MT * TC_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (warp == 0 && lane == 0) {
+        // ---- producer: image rows once, then the Toeplitz operand of every template row through the ring ----
+        mbar_arrive_expect_tx(&a_full, (uint32_t)p.ra_alloc * 128u);
+        for (int c = 0; c < 8; c++)
+            for (int b = 0; b < p.nbox; b++)
+                tma_load_3d(sA + (size_t)c * lbo_a + (size_t)b * p.box_h * 16, tmap, x0 + 16 * c, y0 + b * p.box_h, f, &a_full);
+        for (int v = 0; v < p.h; v++) {
+            const int s = v % TC_NS;
+            mbar_wait(&empty[s], ((v / TC_NS) & 1) ^ 1);
+            mbar_arrive_expect_tx(&full[s], TC_BBYTES);
+            bulk_load(sB + (size_t)s * TC_BBYTES, bglob + (size_t)v * TC_BBYTES, TC_BBYTES, &full[s]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer ----
+        // instruction descriptor: D = S32 (2<<4), A = B = unsigned 8 bit (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        mbar_wait(&a_full, 0);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        for (int v = 0; v < p.h; v++) {
+            const int s = v % TC_NS;
+            mbar_wait(&full[s], (v / TC_NS) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int mt = 0; mt < TC_MT; mt++)
+#pragma unroll
+                for (int ks = 0; ks < TC_K / 32; ks++) {
+                    uint64_t ad = umma_desc(a_base + (uint32_t)(2 * ks) * lbo_a + (uint32_t)(mt * 128 + v) * 16u, lbo_a, 128u);
+                    uint64_t bd = umma_desc(b_base + (uint32_t)s * TC_BBYTES + (uint32_t)(2 * ks) * (TC_N * 16), TC_N * 16, 128u);
+                    umma_i8(tmem + mt * TC_N, ad, bd, idesc, (v | ks) != 0);
+                }
+            umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full);
+    }
+    // ---- epilogue: all four warps; warp w owns TMEM lanes (= accumulator rows) 32w .. 32w+31 ----
+    __syncwarp();
+    mbar_wait(&acc_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int mt = 0; mt < TC_MT; mt++) {
+        const int gy = y0 + mt * 128 + warp * 32 + lane;
+        float* rp = gy < p.oh ? res.row<float>(f, gy) + x0 : nullptr;
+#pragma unroll 1
+        for (int half = 0; half < 2; half++) {
+            uint32_t r[32];
+            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * TC_N + half * 32, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (rp) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    int gx = x0 + half * 32 + j;
+                    if (gx < p.ow) rp[half * 32 + j] = (float)(int)r[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_MT * TC_N) : "memory");
+}
+
+// returns B200CV_NOT_IMPLEMENTED when the tensor-core path does not apply (caller uses the IDP4A kernel)
+int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, cudaStream_t st)
+{
+    if (w > TC_K - TC_N + 1 || h > 512 || !tma_compatible(im) || im.frames >= 65536) return B200CV_NOT_IMPLEMENTED;
+    const int ow = im.cols - w + 1, oh = im.rows - h + 1;
+    TCParams p;
+    p.h = h; p.ow = ow; p.oh = oh;
+    int ra = 128 * TC_MT + h - 1;
+    p.nbox = (ra + 255) / 256;
+    p.box_h = (((ra + p.nbox - 1) / p.nbox) + 7) & ~7;
+    p.ra_alloc = p.nbox * p.box_h;
+    size_t smem = (size_t)8 * p.ra_alloc * 16 + (size_t)TC_NS * TC_BBYTES;
+    if (smem > 200 * 1024) return B200CV_NOT_IMPLEMENTED;
+    static bool attr = false;
+    if (!attr) { B200_CUDA(cudaFuncSetAttribute(ccorr_u8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    unsigned char* bglob = nullptr;
+    B200_CUDA(cudaMallocAsync(&bglob, (size_t)h * TC_BBYTES, st));
+    toeplitz_kernel<<<h, 256, 0, st>>>(tp, w, h, bglob);
+    count_launch();
+    CUtensorMap tm;
+    int rc = make_tensor_map_3d(&tm, im.data, 1, im.cols, im.rows, im.frames, im.step, im.fstep, 16, p.box_h);
+    CUtensorMap* dtm = nullptr;
+    if (!rc) rc = upload_tensor_map(tm, &dtm, st);
+    if (rc) { cudaFreeAsync(bglob, st); return rc; }
+    dim3 grid(div_up((unsigned)ow, TC_N), div_up((unsigned)oh, 128 * TC_MT), (unsigned)im.frames);
+    ccorr_u8_tc_kernel<<<grid, 128, smem, st>>>(dtm, bglob, rs, p);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(dtm, st);
+    cudaFreeAsync(bglob, st);
+    count_launch();
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
+    return B200CV_OK;
+}
+
+}  // namespace b200cv
