@@ -13,6 +13,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_LIB = os.path.join(HERE, "_ref", "libocvref.so")
+REF_HAL_LIB = os.path.join(HERE, "_ref", "libocvref_hal.so")   # the reference with hal/b200cv_hal_replacement.hpp registered (integration proof)
 PORT_LIB = os.path.join(HERE, "_build", "liboracle_port.so")
 
 CV_8U, CV_16S, CV_32F = 0, 3, 5
@@ -31,18 +32,22 @@ def _p(a):
     return a.ctypes.data_as(vp)
 
 
+def _path(kind):
+    return {"ref": REF_LIB, "ref_hal": REF_HAL_LIB}.get(kind, PORT_LIB)
+
+
 def available(kind):
-    return os.path.exists(REF_LIB if kind == "ref" else PORT_LIB)
+    return os.path.exists(_path(kind))
 
 
 class Oracle:
     def __init__(self, kind="ref"):
         self.kind = kind
-        path = REF_LIB if kind == "ref" else PORT_LIB
+        path = _path(kind)
         if not os.path.exists(path):
             raise FileNotFoundError("%s oracle not built: %s" % (kind, path))
         self.lib = ctypes.CDLL(path)
-        self.pfx = "ref_" if kind == "ref" else "port_"
+        self.pfx = "ref_" if kind in ("ref", "ref_hal") else "port_"
 
     def has(self, name):
         return hasattr(self.lib, self.pfx + name)

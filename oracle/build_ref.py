@@ -140,6 +140,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
     ap.add_argument("-j", type=int, default=os.cpu_count() or 4)
+    ap.add_argument("--hal", action="store_true",
+                    help="also build libocvref_hal.so: the same reference with hal/b200cv_hal_replacement.hpp registered as its imgproc HAL "
+                         "(what -DOpenCV_HAL_DIR=<repo>/hal does in a CMake build) and linked against libb200cv.so -- integration proof")
     args = ap.parse_args()
     ref = args.reference
     if not os.path.isdir(os.path.join(ref, "modules", "imgproc", "src")):
@@ -192,7 +195,29 @@ def main():
         objs.append(obj)
     lib = os.path.join(OUT, "libocvref.so")
     ninja.append("build %s: link %s\n" % (lib, " ".join(objs)))
-    ninja.append("default %s\n" % lib)
+    defaults = [lib]
+    if args.hal:
+        repo = os.path.dirname(HERE)
+        w(os.path.join(GEN, "hal_on", "custom_hal.hpp"),
+          '#ifndef _CUSTOM_HAL_INCLUDED_\n#define _CUSTOM_HAL_INCLUDED_\n#include "b200cv_hal_replacement.hpp"\n#endif\n')
+        hal_objs = []
+        for src, obj, mod in units:
+            if mod != "imgproc":
+                hal_objs.append(obj)
+                continue
+            hobj = obj[:-2] + ".hal.o"
+            flags = CXXFLAGS + ["-I" + os.path.join(GEN, "hal_on"), "-I" + os.path.join(repo, "hal"), "-I" + os.path.join(repo, "include")] + incs(mod)
+            sfx = os.path.basename(src).split(".")
+            if len(sfx) == 3 and sfx[1].upper() in MODE_NAMES:
+                flags = flags + mode_flags(sfx[1].upper())
+            ninja.append("build %s: cxx %s\n  flags = %s\n" % (hobj, src, " ".join(flags)))
+            hal_objs.append(hobj)
+        hlib = os.path.join(OUT, "libocvref_hal.so")
+        b200 = os.path.join(repo, "opencv_b200", "lib")
+        ninja.insert(2, "rule linkhal\n  command = g++ -shared -o $out $in -pthread -ldl -lm -Wl,--gc-sections -L%s -lb200cv -Wl,-rpath,%s -Wl,-rpath,$$ORIGIN/../../opencv_b200/lib\n  description = LINK $out\n" % (b200, b200))
+        ninja.append("build %s: linkhal %s\n" % (hlib, " ".join(hal_objs)))
+        defaults.append(hlib)
+    ninja.append("default %s\n" % " ".join(defaults))
     os.makedirs(os.path.join(OUT, "obj"), exist_ok=True)
     w(os.path.join(OUT, "build.ninja"), "\n".join(ninja))
     r = subprocess.call(["ninja", "-C", OUT, "-j", str(args.j)])

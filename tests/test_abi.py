@@ -45,3 +45,18 @@ def test_host_tables_are_pure_host_code():
     k = cvb.getGaussianKernelFixed8(5, 0)
     assert list(k) == [16, 64, 96, 64, 16]
     assert abs(cvb.getGaussianKernel(7, 1.5).sum() - 1) < 1e-12
+
+
+def test_cpp_host_mirror_compiles_against_the_c_abi():
+    """the C++ mirror (cv:: signatures, Stream/Event/GpuMat/Filter) builds with plain g++ against include/*.h + the shared library"""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "cpp", "test_host_api.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "test_host_api")
+    lib = os.path.join(ROOT, "opencv_b200", "lib")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, src, "-L" + lib, "-lb200cv", "-Wl,-rpath,$ORIGIN/../../opencv_b200/lib"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode == 1 and "no CPU fallback" in run.stderr      # loud failure without a device
