@@ -251,6 +251,10 @@ def make_extra(ops, rng, need_device):
 
 
 def main():
+    # keep stdout clean for the ONE JSON line: libraries (e.g. the NCCL version banner) write to fd 1 -> send that to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -326,22 +330,40 @@ def main():
     if args.workload == "c4":
         extra["templ"] = ops[0]["_src"][0, 700:764, 1000:1064, 0].contiguous()
 
+    # The one collective of the path: rank 0's filter taps / kernels / template, NCCL broadcast once per step (= per batch).
+    # It runs on a side stream one step ahead and lands in page-locked host memory (the C ABI takes these small operands as
+    # host pointers), so the frame pipeline never drains for it.
+    side = torch.cuda.Stream(device=dev)
+    pin_taps = torch.empty((len(K_SWEEP), 31), dtype=torch.float32).pin_memory()
+    pin_kern = torch.empty((len(K_SWEEP), 31 * 31), dtype=torch.float32).pin_memory()
+    d_taps = torch.empty((len(K_SWEEP), 31), dtype=torch.float32, device=dev)
+    d_kern = torch.empty((len(K_SWEEP), 31 * 31), dtype=torch.float32, device=dev)
+    ev_ops = torch.cuda.Event()
+    if rank == 0:
+        tp0 = np.zeros((len(K_SWEEP), 31), np.float32); kn0 = np.zeros((len(K_SWEEP), 961), np.float32)
+        for i, k in enumerate(K_SWEEP):
+            tp0[i, :k] = gauss_taps(k); kn0[i, :k * k] = extra["kernels"][k].reshape(-1)
+        h_taps0 = torch.from_numpy(tp0).pin_memory(); h_kern0 = torch.from_numpy(kn0).pin_memory()
+
+    def prefetch_operands():
+        with torch.cuda.stream(side):
+            if rank == 0:
+                d_taps.copy_(h_taps0, non_blocking=True); d_kern.copy_(h_kern0, non_blocking=True)
+            if world > 1:
+                dist.broadcast(d_taps, 0); dist.broadcast(d_kern, 0)
+                if "templ" in extra:
+                    dist.broadcast(extra["templ"], 0)
+            pin_taps.copy_(d_taps, non_blocking=True); pin_kern.copy_(d_kern, non_blocking=True)
+            ev_ops.record(side)
+
     def shared_operands():
-        """the one collective of the path: rank 0's filter taps / kernels / template, NCCL broadcast per step"""
-        taps = torch.empty((len(K_SWEEP), 31), dtype=torch.float32, device=dev)
-        kern = torch.empty((len(K_SWEEP), 31 * 31), dtype=torch.float32, device=dev)
-        if rank == 0:
-            tp = np.zeros((len(K_SWEEP), 31), np.float32); kn = np.zeros((len(K_SWEEP), 961), np.float32)
-            for i, k in enumerate(K_SWEEP):
-                tp[i, :k] = gauss_taps(k); kn[i, :k * k] = extra["kernels"][k].reshape(-1)
-            taps.copy_(torch.from_numpy(tp)); kern.copy_(torch.from_numpy(kn))
-        if world > 1:
-            dist.broadcast(taps, 0); dist.broadcast(kern, 0)
-            if "templ" in extra:
-                dist.broadcast(extra["templ"], 0)
-        tp = taps.cpu().numpy(); kn = kern.cpu().numpy()
+        ev_ops.synchronize()                      # waits for the side stream only
+        tp = pin_taps.numpy(); kn = pin_kern.numpy()
         for i, k in enumerate(K_SWEEP):
             extra["taps"][k] = tp[i, :k].copy(); extra["kernels"][k] = kn[i, :k * k].reshape(k, k).copy()
+        prefetch_operands()                       # next step's broadcast overlaps this step's kernels
+
+    prefetch_operands()
 
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops]
 

@@ -14,6 +14,8 @@
 
 namespace b200cv {
 
+int filter2d_u8_tensor(const Img& s, const Img& d, int dd, const float* k, int kw, int kh, int ax, int ay, float delta, int border, cudaStream_t st);
+
 struct F2DParams {
     float k[33 * 33];    // row-major, row stride = kstride
     int kw, kh, ax, ay, kstride;
@@ -190,6 +192,14 @@ extern "C" int b200cv_filter2d(const b200cvMat* src, const b200cvMat* dst, const
     B200_REQUIRE(s.frames == d.frames, "src/dst batch mismatch");
     cudaStream_t st = as_stream(stream);
     float fd = (float)delta;
+    if (sd == B200CV_8U && cn == 1 && kw * kh >= (dd == B200CV_32F ? 50 : 121)) {
+        // the sizes where the reference leaves the direct sum for a DFT (filter.dispatch.cpp:1288): tensor-core correlation
+        const char* path = getenv("B200CV_FILTER2D_PATH");
+        if (!(path && !strcmp(path, "direct"))) {
+            rc = filter2d_u8_tensor(s, d, dd, kernel, kw, kh, ax, ay, fd, border, st);
+            if (rc != B200CV_NOT_IMPLEMENTED) return rc;
+        }
+    }
     if (sd == B200CV_8U && dd == B200CV_8U) return f2d_dispatch<uchar, uchar>(s, d, cn, kernel, kw, kh, ax, ay, fd, border, st);
     if (sd == B200CV_8U && dd == B200CV_16S) return f2d_dispatch<uchar, short>(s, d, cn, kernel, kw, kh, ax, ay, fd, border, st);
     if (sd == B200CV_8U && dd == B200CV_32F) return f2d_dispatch<uchar, float>(s, d, cn, kernel, kw, kh, ax, ay, fd, border, st);

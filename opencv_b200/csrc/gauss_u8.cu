@@ -8,14 +8,14 @@
 //   1. ONE thread issues a 3-D TMA box load (cp.async.bulk.tensor) of the 256 x (TH+K-1) byte tile + apron into shared
 //      memory; everybody waits on the mbarrier.  TMA zero-fills outside the image = BORDER_CONSTANT; for REPLICATE /
 //      REFLECT / REFLECT_101 only CTAs on the image boundary patch their apron cells from the mirrored in-tile cells.
-//   2. Row pass: each thread takes 4 columns x 4 rows.  4 taps per IDP4A (u8 x u8 -> u32); the three unaligned windows
-//      of a group come from PRMT of two aligned shared words.  The 16-bit row sums of the 4 rows are split into low / high
-//      bytes and transposed in registers (PRMT) into "4 vertically adjacent bytes per word" and stored to shared memory.
-//   3. Column pass: sum_j ky[j]*mid = 256 * sum_j ky[j]*hi_j + sum_j ky[j]*lo_j -- again 4 taps per IDP4A, with the tap
-//      words pre-shifted on the host for each of the 4 row phases (zero padded) so no data realignment is needed.
-//      Epilogue: v = hi*256 + lo + 2^15; the result byte is bits 16..23 of v (never saturates: sum k = 256), picked by PRMT;
-//      4 pixels per 32-bit store.
-// Instruction budget (K=5): ~2.1 + 4 IDP4A and ~7 other instructions per pixel, against ~46 for the generic float kernel.
+//   2. Row pass: each thread takes 4 columns x 4 rows.  4 taps per IDP4A (u8 x u8 -> u32); the unaligned windows of a
+//      group come from PRMT of two aligned shared words.  The 16-bit row sums of vertically adjacent rows (2p, 2p+1) are
+//      packed into one word per column (PRMT) and stored to shared memory.
+//   3. Column pass: 2 taps per IDP2A (u16 x u8 -> u32) on those vertical pairs, with the tap words pre-shifted on the host
+//      for each of the 4 row phases (zero padded) so no data realignment is needed; accumulators start at 2^15.
+//      Epilogue: the result byte is bits 16..23 of the sum (never saturates: sum k = 256), picked by PRMT; 4 pixels per
+//      32-bit store.
+// Instruction budget (K=3): ~1 IDP4A + 2 IDP2A and ~6 other instructions per pixel, against ~46 for the generic float kernel.
 #include <vector>
 #include "common.cuh"
 #include "tma.cuh"
@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const CUtensorMap
     constexpr int GH = (KB + 3) / 4;                 // tap groups per row
     constexpr int GV = (KB + 3 + 3) / 4;             // row groups touched by one 4-row output group
     __shared__ __align__(128) unsigned char s_in[GU_IW * GU_RG * 4];          // 256 x 64 bytes
-    __shared__ __align__(16) uint32_t s_mid[GU_RG * GU_TW * 2];               // [row group][column][lo, hi]
+    __shared__ __align__(16) uint32_t s_mid[GU_RG * 2 * GU_TW];               // [row pair][column]: (sum of row 2p, sum of row 2p+1) as 2 x u16
     __shared__ __align__(8) uint64_t s_bar;
 
     const int TH = p.TH, IH = TH + KB - 1;
@@ -116,18 +116,12 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const CUtensorMap
                 }
                 res[r][0] = a[0]; res[r][1] = a[1]; res[r][2] = a[2]; res[r][3] = a[3];
             }
-            // transpose: per column, (lo0,lo1,lo2,lo3) and (hi0,hi1,hi2,hi3) of the 4 rows
-            uint32_t out[8];
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                uint32_t t01 = __byte_perm(res[0][c], res[1][c], 0x5140);   // lo0, lo1, hi0, hi1
-                uint32_t t23 = __byte_perm(res[2][c], res[3][c], 0x5140);
-                out[2 * c] = __byte_perm(t01, t23, 0x5410);                 // lo0..lo3
-                out[2 * c + 1] = __byte_perm(t01, t23, 0x7632);             // hi0..hi3
-            }
-            uint4* mp = (uint4*)(s_mid + (rg * GU_TW + cg * 4) * 2);
-            mp[0] = make_uint4(out[0], out[1], out[2], out[3]);
-            mp[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            // vertical pairs: word = (row 2p, row 2p+1) of one column
+            uint32_t* mp = s_mid + (rg * 2) * GU_TW + cg * 4;
+            *(uint4*)mp = make_uint4(__byte_perm(res[0][0], res[1][0], 0x5410), __byte_perm(res[0][1], res[1][1], 0x5410),
+                                     __byte_perm(res[0][2], res[1][2], 0x5410), __byte_perm(res[0][3], res[1][3], 0x5410));
+            *(uint4*)(mp + GU_TW) = make_uint4(__byte_perm(res[2][0], res[3][0], 0x5410), __byte_perm(res[2][1], res[3][1], 0x5410),
+                                               __byte_perm(res[2][2], res[3][2], 0x5410), __byte_perm(res[2][3], res[3][3], 0x5410));
             cg += 256 % NCG; rg += 256 / NCG;
             if (cg >= NCG) { cg -= NCG; rg += 1; }
         }
@@ -145,34 +139,37 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const CUtensorMap
         const size_t dstep = dst.step;
 #pragma unroll 1
         for (; q < nq; ) {
-            uint32_t lo[4][4], hi[4][4];                                  // [output row][column]
+            uint32_t acc[4][4];                                           // [output row][column], start at the rounding constant
 #pragma unroll
             for (int o = 0; o < 4; o++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) { lo[o][c] = 32768u; hi[o][c] = 0u; }
-            const uint4* mp0 = (const uint4*)(s_mid + (q * GU_TW + cg * 4) * 2);
+                for (int c = 0; c < 4; c++) acc[o][c] = 32768u;
+            const uint32_t* mp0 = s_mid + (q * 2) * GU_TW + cg * 4;
 #pragma unroll
             for (int g = 0; g < GV; g++) {
-                const uint4* mp = mp0 + g * (GU_TW * 2 / 4);
-                uint4 m0 = mp[0], m1 = mp[1];
-                const uint32_t l[4] = {m0.x, m0.z, m1.x, m1.z}, h[4] = {m0.y, m0.w, m1.y, m1.w};
+                // rows 4g, 4g+1 (pair 2g) and 4g+2, 4g+3 (pair 2g+1) of this item; tap word bytes 0..3 = taps of rows 4g..4g+3 for phase o
+                const bool need_lo = 4 * g - 3 < KB, need_hi = 4 * g + 2 - 3 < KB;       // any phase o in 0..3 touches them
+                uint4 m0 = make_uint4(0, 0, 0, 0), m1 = make_uint4(0, 0, 0, 0);
+                if (need_lo) m0 = *(const uint4*)(mp0 + (2 * g) * GU_TW);
+                if (need_hi) m1 = *(const uint4*)(mp0 + (2 * g + 1) * GU_TW);
+                const uint32_t a0[4] = {m0.x, m0.y, m0.z, m0.w}, a1[4] = {m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
                 for (int o = 0; o < 4; o++) {
-                    if (gu_nz(KB, o, g)) {
-                        const uint32_t t = p.kyw[o][g];
+                    const uint32_t t = p.kyw[o][g];
+                    if (4 * g + 1 - o >= 0 && 4 * g - o < KB) {
 #pragma unroll
-                        for (int c = 0; c < 4; c++) { lo[o][c] = __dp4a(l[c], t, lo[o][c]); hi[o][c] = __dp4a(h[c], t, hi[o][c]); }
+                        for (int c = 0; c < 4; c++) acc[o][c] = __dp2a_lo(a0[c], t, acc[o][c]);
+                    }
+                    if (4 * g + 3 - o >= 0 && 4 * g + 2 - o < KB) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) acc[o][c] = __dp2a_hi(a1[c], t, acc[o][c]);
                     }
                 }
             }
             uint32_t packed[4];
 #pragma unroll
-            for (int o = 0; o < 4; o++) {
-                uint32_t v[4];
-#pragma unroll
-                for (int c = 0; c < 4; c++) v[c] = (hi[o][c] << 8) + lo[o][c];
-                packed[o] = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
-            }
+            for (int o = 0; o < 4; o++)
+                packed[o] = __byte_perm(__byte_perm(acc[o][0], acc[o][1], 0x0062), __byte_perm(acc[o][2], acc[o][3], 0x0062), 0x5410);
             uchar* dp = dbase + (size_t)(q * 4) * dstep + cg * 4;
             if (full) {
 #pragma unroll

@@ -13,9 +13,18 @@
 // accumulator; all four warps read it back with tcgen05.ld and store float(R).  Half of B is zeros (2.1x redundant MACs),
 // the price of a well-shaped MMA; the result is exact because products <= 65025 and sums < 2^31.
 //
+//
+// The same engine evaluates filter2D on 8-bit images for kernels of >= 11x11 taps -- the sizes at which the reference itself
+// leaves the direct sum for a DFT (filter.dispatch.cpp:1288-1310).  The float taps are quantised to 24-bit fixed point against
+// max|k| and split into three signed base-256 digits; the three digit planes ride in ONE MMA as N = 3 x 64 (u8 x s8 -> s32,
+// exact), and the epilogue recombines S0 + 256 S1 + 65536 S2 in 64-bit, scales by the power of two and adds delta.  The
+// only error left is the tap quantisation (<= 2^-24 max|k| per tap), the same order as a float accumulation.
+//
 // Reference: crossCorr, modules/imgproc/src/templmatch.cpp:566-760 (block DFT in float on one thread).
 #include "common.cuh"
 #include "tma.cuh"
+#include <cmath>
+#include <vector>
 
 namespace b200cv {
 
@@ -24,6 +33,8 @@ constexpr int TC_K = 128;         // K per template row: w + N - 1 <= 128
 constexpr int TC_MT = 2;          // M-tiles (of 128 rows) per CTA
 constexpr int TC_NS = 4;          // B ring stages
 constexpr int TC_BBYTES = TC_N * TC_K;   // 8192
+
+enum { EPI_CCORR = 0, EPI_U8 = 1, EPI_F32 = 2, EPI_S16 = 3 };
 
 // B_v in smem/global: [k-chunk c (8)][column j (64)][16 bytes]: byte b = T(v, 16c + b - j)
 __global__ void toeplitz_kernel(Img templ, int w, int h, unsigned char* out)
@@ -34,6 +45,42 @@ __global__ void toeplitz_kernel(Img templ, int w, int h, unsigned char* out)
         int u = 16 * c + b - j;
         out[(size_t)v * TC_BBYTES + idx] = (u >= 0 && u < w) ? templ.row<uchar>(0, v)[u] : (uchar)0;
     }
+}
+
+// filter2D operand: [kernel row v][k-chunk c (2*kch)][column j (192) = digit d * 64 + jj][16 bytes]: byte b = digit_d(Kq(v, 16c + b - jj))
+__global__ void toeplitz_digits_kernel(const int* __restrict__ kq, int w, int h, int kch, signed char* out)
+{
+    const int v = blockIdx.x;
+    const int slab = 2 * kch * 192 * 16;
+    for (int idx = threadIdx.x; idx < slab; idx += blockDim.x) {
+        int b = idx & 15, j = (idx >> 4) % 192, c = (idx >> 4) / 192;
+        int d = j >> 6, jj = j & 63;
+        int u = 16 * c + b - jj;
+        int q = (u >= 0 && u < w) ? kq[v * w + u] : 0;
+        // balanced base-256 digits, each in [-128, 127]
+        int d0 = ((q + 128) & 255) - 128; q = (q - d0) >> 8;
+        int d1 = ((q + 128) & 255) - 128; q = (q - d1) >> 8;
+        out[(size_t)v * slab + idx] = (signed char)(d == 0 ? d0 : d == 1 ? d1 : q);
+    }
+}
+
+// border-extended copy of an 8-bit single-channel image: P(y, x) = src(y - ay, x - ax) under `border`
+__global__ void pad_u8_kernel(Img src, Img dst, int ax, int ay, int border)
+{
+    const int f = blockIdx.z, y = blockIdx.y;
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x4 >= dst.cols) return;
+    const int sy = border_interpolate(y - ay, src.rows, border);
+    uint32_t w = 0;
+    if (sy >= 0) {
+        const uchar* sp = src.row<uchar>(f, sy);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int sx = border_interpolate(x4 + i - ax, src.cols, border);
+            w |= (uint32_t)(sx >= 0 ? sp[sx] : (uchar)0) << (8 * i);
+        }
+    }
+    *(uint32_t*)(dst.row<uchar>(f, y) + x4) = w;
 }
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
@@ -71,13 +118,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r)
 struct TCParams {
     int h, ra_alloc, box_h, nbox;       // template rows; staged image rows (allocated), rows per TMA box, boxes per column chunk
     int ow, oh;
+    int kch;                            // K per template row = 32 * kch (w + N - 1 <= 32 * kch)
+    float scale, delta;                 // filter2D epilogue: value = sum * scale + delta
 };
 
+template <int NB, int EPI>     // NB = digit planes of the B operand (MMA N = 64 NB)
 __global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const CUtensorMap* __restrict__ tmap, const unsigned char* __restrict__ bglob, Img res, TCParams p)
 {
+    constexpr int NN = TC_N * NB;                                      // MMA N
+    constexpr int TCOLS = TC_MT * NN <= 128 ? 128 : TC_MT * NN <= 256 ? 256 : 512;   // TMEM columns (power of two)
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* sA = smem;                                          // 8 chunks x ra_alloc rows x 16 B
-    unsigned char* sB = smem + (size_t)8 * p.ra_alloc * 16;            // TC_NS x 8 KB
+    const int nchunk = 2 * p.kch;                                      // 16-byte K chunks per row
+    const uint32_t bbytes = (uint32_t)nchunk * NN * 16;                // one B slab
+    unsigned char* sA = smem;                                          // nchunk x ra_alloc rows x 16 B
+    unsigned char* sB = smem + (size_t)nchunk * p.ra_alloc * 16;       // TC_NS slabs
     __shared__ __align__(8) uint64_t full[TC_NS], empty[TC_NS], a_full, acc_full;
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,8 +143,8 @@ __global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const CUtensorMap* __r
         mbar_init(&a_full, 1); mbar_init(&acc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 0) {   // TMEM: TC_MT x 64 columns of 32-bit accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TC_MT * TC_N) : "memory");
+    if (warp == 0) {   // TMEM: TC_MT x NN columns of 32-bit accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TCOLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -100,20 +154,21 @@ __global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const CUtensorMap* __r
 
     if (warp == 0 && lane == 0) {
         // ---- producer: image rows once, then the Toeplitz operand of every template row through the ring ----
-        mbar_arrive_expect_tx(&a_full, (uint32_t)p.ra_alloc * 128u);
-        for (int c = 0; c < 8; c++)
+        mbar_arrive_expect_tx(&a_full, (uint32_t)p.ra_alloc * 16u * nchunk);
+        for (int c = 0; c < nchunk; c++)
             for (int b = 0; b < p.nbox; b++)
                 tma_load_3d(sA + (size_t)c * lbo_a + (size_t)b * p.box_h * 16, tmap, x0 + 16 * c, y0 + b * p.box_h, f, &a_full);
         for (int v = 0; v < p.h; v++) {
             const int s = v % TC_NS;
             mbar_wait(&empty[s], ((v / TC_NS) & 1) ^ 1);
-            mbar_arrive_expect_tx(&full[s], TC_BBYTES);
-            bulk_load(sB + (size_t)s * TC_BBYTES, bglob + (size_t)v * TC_BBYTES, TC_BBYTES, &full[s]);
+            mbar_arrive_expect_tx(&full[s], bbytes);
+            bulk_load(sB + (size_t)s * bbytes, bglob + (size_t)v * bbytes, bbytes, &full[s]);
         }
     } else if (warp == 1 && lane == 0) {
         // ---- MMA issuer ----
-        // instruction descriptor: D = S32 (2<<4), A = B = unsigned 8 bit (0), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-        const uint32_t idesc = (2u << 4) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // instruction descriptor: D = S32 (2<<4), A = unsigned 8 bit (0 at [7,10)), B = unsigned (0) or signed (1) 8 bit at [10,13),
+        // K-major both, N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (2u << 4) | ((EPI == EPI_CCORR ? 0u : 1u) << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         mbar_wait(&a_full, 0);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
@@ -125,9 +180,11 @@ __global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const CUtensorMap* __r
             for (int mt = 0; mt < TC_MT; mt++)
 #pragma unroll
                 for (int ks = 0; ks < TC_K / 32; ks++) {
-                    uint64_t ad = umma_desc(a_base + (uint32_t)(2 * ks) * lbo_a + (uint32_t)(mt * 128 + v) * 16u, lbo_a, 128u);
-                    uint64_t bd = umma_desc(b_base + (uint32_t)s * TC_BBYTES + (uint32_t)(2 * ks) * (TC_N * 16), TC_N * 16, 128u);
-                    umma_i8(tmem + mt * TC_N, ad, bd, idesc, (v | ks) != 0);
+                    if (ks < p.kch) {
+                        uint64_t ad = umma_desc(a_base + (uint32_t)(2 * ks) * lbo_a + (uint32_t)(mt * 128 + v) * 16u, lbo_a, 128u);
+                        uint64_t bd = umma_desc(b_base + (uint32_t)s * bbytes + (uint32_t)(2 * ks) * (NN * 16), NN * 16, 128u);
+                        umma_i8(tmem + mt * NN, ad, bd, idesc, (v | ks) != 0);
+                    }
                 }
             umma_commit(&empty[s]);
         }
@@ -140,24 +197,64 @@ __global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const CUtensorMap* __r
 #pragma unroll 1
     for (int mt = 0; mt < TC_MT; mt++) {
         const int gy = y0 + mt * 128 + warp * 32 + lane;
-        float* rp = gy < p.oh ? res.row<float>(f, gy) + x0 : nullptr;
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16) + mt * NN;
 #pragma unroll 1
         for (int half = 0; half < 2; half++) {
             uint32_t r[32];
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mt * TC_N + half * 32, r);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (rp) {
+            tmem_ld32(trow + half * 32, r);
+            if constexpr (EPI == EPI_CCORR) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float* rp = gy < p.oh ? res.row<float>(f, gy) + x0 : nullptr;
+                if (rp) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        int gx = x0 + half * 32 + j;
+                        if (gx < p.ow) rp[half * 32 + j] = (float)(int)r[j];
+                    }
+                }
+            } else {
+                uint32_t r1[32], r2[32];
+                tmem_ld32(trow + TC_N + half * 32, r1);
+                tmem_ld32(trow + 2 * TC_N + half * 32, r2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    int gx = x0 + half * 32 + j;
-                    if (gx < p.ow) rp[half * 32 + j] = (float)(int)r[j];
+                    long long sum = (long long)(int)r[j] + ((long long)(int)r1[j] << 8) + ((long long)(int)r2[j] << 16);
+                    v[j] = __fadd_rn(__fmul_rn(__ll2float_rn(sum), p.scale), p.delta);
+                }
+                if (gy < p.oh) {
+                    const int gx0 = x0 + half * 32;
+                    if constexpr (EPI == EPI_U8) {
+                        uchar* dp = res.row<uchar>(f, gy) + gx0;
+                        if (gx0 + 32 <= p.ow && ((uintptr_t)dp & 15) == 0) {
+                            uint32_t w[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                                w[j] = (uint32_t)sat_u8(v[4 * j]) | ((uint32_t)sat_u8(v[4 * j + 1]) << 8) | ((uint32_t)sat_u8(v[4 * j + 2]) << 16) |
+                                       ((uint32_t)sat_u8(v[4 * j + 3]) << 24);
+                            ((uint4*)dp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            ((uint4*)dp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) if (gx0 + j < p.ow) dp[j] = sat_u8(v[j]);
+                        }
+                    } else if constexpr (EPI == EPI_S16) {
+                        short* dp = res.row<short>(f, gy) + gx0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (gx0 + j < p.ow) dp[j] = sat_s16(v[j]);
+                    } else {
+                        float* dp = res.row<float>(f, gy) + gx0;
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if (gx0 + j < p.ow) dp[j] = v[j];
+                    }
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TC_MT * TC_N) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS) : "memory");
 }
 
 // returns B200CV_NOT_IMPLEMENTED when the tensor-core path does not apply (caller uses the IDP4A kernel)
@@ -166,7 +263,7 @@ int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, c
     if (w > TC_K - TC_N + 1 || h > 512 || !tma_compatible(im) || im.frames >= 65536) return B200CV_NOT_IMPLEMENTED;
     const int ow = im.cols - w + 1, oh = im.rows - h + 1;
     TCParams p;
-    p.h = h; p.ow = ow; p.oh = oh;
+    p.h = h; p.ow = ow; p.oh = oh; p.kch = TC_K / 32; p.scale = 1.f; p.delta = 0.f;
     int ra = 128 * TC_MT + h - 1;
     p.nbox = (ra + 255) / 256;
     p.box_h = (((ra + p.nbox - 1) / p.nbox) + 7) & ~7;
@@ -174,7 +271,7 @@ int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, c
     size_t smem = (size_t)8 * p.ra_alloc * 16 + (size_t)TC_NS * TC_BBYTES;
     if (smem > 200 * 1024) return B200CV_NOT_IMPLEMENTED;
     static bool attr = false;
-    if (!attr) { B200_CUDA(cudaFuncSetAttribute(ccorr_u8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    if (!attr) { B200_CUDA(cudaFuncSetAttribute(ccorr_u8_tc_kernel<1, EPI_CCORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
     unsigned char* bglob = nullptr;
     B200_CUDA(cudaMallocAsync(&bglob, (size_t)h * TC_BBYTES, st));
     toeplitz_kernel<<<h, 256, 0, st>>>(tp, w, h, bglob);
@@ -185,13 +282,89 @@ int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, c
     if (!rc) rc = upload_tensor_map(tm, &dtm, st);
     if (rc) { cudaFreeAsync(bglob, st); return rc; }
     dim3 grid(div_up((unsigned)ow, TC_N), div_up((unsigned)oh, 128 * TC_MT), (unsigned)im.frames);
-    ccorr_u8_tc_kernel<<<grid, 128, smem, st>>>(dtm, bglob, rs, p);
+    ccorr_u8_tc_kernel<1, EPI_CCORR><<<grid, 128, smem, st>>>(dtm, bglob, rs, p);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(dtm, st);
     cudaFreeAsync(bglob, st);
     count_launch();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
     return B200CV_OK;
+}
+
+template <int EPI>
+static int launch_filter_tc(const CUtensorMap* dtm, const unsigned char* bglob, const Img& d, const TCParams& p, size_t smem, cudaStream_t st)
+{
+    auto kern = ccorr_u8_tc_kernel<3, EPI>;
+    static bool attr = false;
+    if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    dim3 grid(div_up((unsigned)p.ow, TC_N), div_up((unsigned)p.oh, 128 * TC_MT), (unsigned)d.frames);
+    kern<<<grid, 128, smem, st>>>(dtm, bglob, d, p);
+    cudaError_t e = cudaGetLastError();
+    count_launch();
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
+    return B200CV_OK;
+}
+
+// filter2D, 8-bit single-channel source, kernels the reference would hand to its DFT path.  dd = destination depth.
+// returns B200CV_NOT_IMPLEMENTED when the tensor-core path does not apply (caller uses the direct-sum kernel)
+int filter2d_u8_tensor(const Img& s, const Img& d, int dd, const float* k, int kw, int kh, int ax, int ay, float delta, int border, cudaStream_t st)
+{
+    if (kw + TC_N - 1 > TC_K || kh > 64 || s.frames >= 65536) return B200CV_NOT_IMPLEMENTED;
+    if (dd != B200CV_8U && dd != B200CV_32F && dd != B200CV_16S) return B200CV_NOT_IMPLEMENTED;
+    float mx = 0.f;
+    for (int i = 0; i < kw * kh; i++) {
+        if (!std::isfinite(k[i])) return B200CV_NOT_IMPLEMENTED;
+        mx = std::max(mx, std::fabs(k[i]));
+    }
+    if (!(mx > 0.f) || mx > 1e30f || mx < 1e-30f) return B200CV_NOT_IMPLEMENTED;
+    // |Kq| <= 2^23 - 2^15 keeps the three balanced digits inside [-128, 127]
+    int e;
+    std::frexp((double)mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
+    const int sh = 22 - e;                            // |k| * 2^sh < 2^22
+    std::vector<int> kq((size_t)kw * kh);
+    for (int i = 0; i < kw * kh; i++) kq[i] = (int)std::lrint(std::ldexp((double)k[i], sh));
+
+    TCParams p;
+    p.h = kh; p.ow = s.cols; p.oh = s.rows; p.kch = (kw + TC_N - 1 + 31) / 32; p.scale = (float)std::ldexp(1.0, -sh); p.delta = delta;
+    int ra = 128 * TC_MT + kh - 1;
+    p.nbox = (ra + 255) / 256;
+    p.box_h = (((ra + p.nbox - 1) / p.nbox) + 7) & ~7;
+    p.ra_alloc = p.nbox * p.box_h;
+    const int nchunk = 2 * p.kch;
+    const size_t bbytes = (size_t)nchunk * 192 * 16;
+    size_t smem = (size_t)nchunk * p.ra_alloc * 16 + (size_t)TC_NS * bbytes;
+    if (smem > 200 * 1024) return B200CV_NOT_IMPLEMENTED;
+
+    // border-extended source, rows padded to a multiple of 16 bytes (TMA)
+    Img pad = s;
+    pad.cols = (s.cols + kw - 1 + 15) & ~15;
+    pad.rows = s.rows + kh - 1;
+    pad.step = (size_t)pad.cols;
+    pad.fstep = pad.step * pad.rows;
+    unsigned char* pbuf = nullptr; unsigned char* bglob = nullptr; int* dkq = nullptr;
+    B200_CUDA(cudaMallocAsync(&pbuf, pad.fstep * (size_t)s.frames, st));
+    B200_CUDA(cudaMallocAsync(&bglob, (size_t)kh * bbytes, st));
+    B200_CUDA(cudaMallocAsync(&dkq, kq.size() * sizeof(int), st));
+    pad.data = pbuf;
+    B200_CUDA(cudaMemcpyAsync(dkq, kq.data(), kq.size() * sizeof(int), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+    toeplitz_digits_kernel<<<kh, 256, 0, st>>>(dkq, kw, kh, p.kch, (signed char*)bglob);
+    count_launch();
+    pad_u8_kernel<<<dim3(div_up((unsigned)pad.cols / 4, 128), (unsigned)pad.rows, (unsigned)s.frames), 128, 0, st>>>(s, pad, ax, ay, border);
+    count_launch();
+    CUtensorMap tm;
+    int rc = make_tensor_map_3d(&tm, pad.data, 1, pad.cols, pad.rows, pad.frames, pad.step, pad.fstep, 16, p.box_h);
+    CUtensorMap* dtm = nullptr;
+    if (!rc) rc = upload_tensor_map(tm, &dtm, st);
+    if (!rc) {
+        rc = dd == B200CV_8U ? launch_filter_tc<EPI_U8>(dtm, bglob, d, p, smem, st)
+           : dd == B200CV_16S ? launch_filter_tc<EPI_S16>(dtm, bglob, d, p, smem, st)
+                              : launch_filter_tc<EPI_F32>(dtm, bglob, d, p, smem, st);
+    }
+    if (dtm) cudaFreeAsync(dtm, st);
+    cudaFreeAsync(dkq, st);
+    cudaFreeAsync(bglob, st);
+    cudaFreeAsync(pbuf, st);
+    return rc;
 }
 
 }  // namespace b200cv

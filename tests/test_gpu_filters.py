@@ -109,6 +109,31 @@ def test_filter2d(cvb, oracle, rng, k):
                      what="filter2D f32 k=%d b=%d" % (k, b))
 
 
+def test_filter2d_tensor_core(cvb, oracle, rng, monkeypatch):
+    """8-bit filter2D with >= 11x11 taps runs on the tcgen05 correlation engine (three base-256 digit planes of the fixed-point
+    taps, exact integer MMA).  Checked against the CPU (DFT path) and against our own direct-sum kernel; ragged sizes, several
+    M/N tiles and frames, signed taps, off-centre anchor, delta, every destination depth."""
+    import os
+    img = rng.integers(0, 256, (3, 301, 263, 1), dtype=np.uint8)       # batch of 3 frames, > 1 M-tile pair and > 4 N-tiles
+    for (kh, kw), anchor, delta in (((11, 11), (-1, -1), 0.0), ((13, 17), (2, 9), 3.5), ((31, 31), (-1, -1), 0.0), ((5, 33), (30, 1), -2.0)):
+        ker = (rng.random((kh, kw)).astype(np.float32) - 0.25); ker /= np.abs(ker).sum() * 0.5
+        for b in (0, 1, 2, 4):
+            got = cpu(cvb.filter2D(gpu(img), -1, ker, anchor=anchor, delta=delta, borderType=b))
+            monkeypatch.setenv("B200CV_FILTER2D_PATH", "direct")
+            direct = cpu(cvb.filter2D(gpu(img), -1, ker, anchor=anchor, delta=delta, borderType=b))
+            monkeypatch.delenv("B200CV_FILTER2D_PATH")
+            assert_close(got, direct, atol=1, what="filter2D tc vs direct %dx%d b=%d" % (kh, kw, b))
+            assert (got != direct).mean() < 1e-3          # only exact .5 ties may differ
+            for i in range(img.shape[0]):
+                assert_close(got[i, :, :, 0], oracle.filter2D(img[i, :, :, 0], -1, ker, anchor=anchor, delta=delta, borderType=b), atol=1,
+                             what="filter2D tc vs cpu %dx%d b=%d" % (kh, kw, b))
+        im0 = np.ascontiguousarray(img[0, :, :, 0])
+        ref = oracle.filter2D(im0, 5, ker, anchor=anchor, delta=delta)
+        assert_close(cpu(cvb.filter2D(gpu(im0), 5, ker, anchor=anchor, delta=delta)), ref, atol=2e-3, rtol=1e-5, what="filter2D tc u8->f32")
+        assert_close(cpu(cvb.filter2D(gpu(im0), 3, ker * 64, anchor=anchor, delta=delta)), oracle.filter2D(im0, 3, ker * 64, anchor=anchor, delta=delta),
+                     atol=1, what="filter2D tc u8->s16")
+
+
 def test_filter2d_generic(cvb, oracle, rng):
     img3 = rand_u8(rng, 61, 77, 3)
     ker = rng.random((4, 6)).astype(np.float32) - 0.3
