@@ -108,41 +108,52 @@ struct OpBGR2HSV {    // 3|4 -> 3
     }
 };
 
+constexpr int PPT = 16;  // pixels per thread
+
 template <int bidx>
 struct OpHSV2BGR {    // 3 -> 3|4 ; float arithmetic mirroring the reference's vector body
     float hscale;
     int trunc_cols;     // pixels x < trunc_cols are truncated after scaling (vector body), the rest rounded (scalar tail)
+    // Conversions are the scarce resource here (I2F/F2I/FRND issue at a quarter of the FP32 rate): bytes become floats by
+    // OR-ing them into the mantissa of 2^23, floats become bytes by adding 2^23 (round-to-nearest-even = cvRound, or
+    // round-toward-zero = the vector body's truncation) and taking the low mantissa byte.  All values are in [0, 255].
     __device__ __forceinline__ void px_at(const uchar* s, uchar* d, int x) const
     {
-        float h = (float)s[0], sv = __fmul_rn((float)s[1], 1.0f / 255.0f), v = __fmul_rn((float)s[2], 1.0f / 255.0f);
-        float b, g, r;
+        const float two23 = 8388608.0f;
+        float h = __fsub_rn(__uint_as_float(0x4B000000u | s[0]), two23);
+        float sv = __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | s[1]), two23), 1.0f / 255.0f);
+        float v = __fmul_rn(__fsub_rn(__uint_as_float(0x4B000000u | s[2]), two23), 1.0f / 255.0f);
         h = __fmul_rn(h, hscale);
-        float pre = truncf(h);
+        const float hm = __fadd_rz(h, two23);                  // 2^23 + trunc(h), exact
+        const float pre = __fsub_rn(hm, two23);
+        const int ipre = (int)(__float_as_uint(hm) & 0xffu);   // h * hscale <= 8.5
         h = __fsub_rn(h, pre);
         float tab0 = v;
         float tab1 = __fmul_rn(v, __fsub_rn(1.0f, sv));
         // the reference's AVX2 unit is compiled with -mfma and GCC contracts 1 - s*h into a single fnmadd
         float tab2 = __fmul_rn(v, __fmaf_rn(-sv, h, 1.0f));
         float tab3 = __fmul_rn(v, __fmaf_rn(-sv, __fsub_rn(1.0f, h), 1.0f));
-        float sec = truncf(__fmul_rn(pre, 1.0f / 6.0f));
-        int sector = (int)__fsub_rn(pre, __fmul_rn(sec, 6.0f));
+        // sector = pre - 6 * trunc(pre * (1/6.f)); pre is an integer in [0, 8]
+        const int sector = ipre >= 6 ? ipre - 6 : ipre;
         // sector_data rows {b,g,r} = {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}
-        b = sector <= 1 ? tab1 : sector == 2 ? tab3 : sector <= 4 ? tab0 : tab2;
-        g = sector == 0 ? tab3 : sector <= 2 ? tab0 : sector == 3 ? tab2 : tab1;
-        r = sector == 0 ? tab0 : sector == 1 ? tab2 : sector <= 3 ? tab1 : sector == 4 ? tab3 : tab0;
+        // as a two-level multiplexer on (sector & 1, sector >> 1) with two shared first-level selections
+        const bool odd = sector & 1, mid = (sector >> 1) == 1, hi = (sector >> 1) == 2;
+        const float X = odd ? tab0 : tab3, Y = odd ? tab2 : tab0;
+        float b = hi ? Y : (mid ? X : tab1);
+        float g = hi ? tab1 : (mid ? Y : X);
+        float r = hi ? X : (mid ? tab1 : Y);
         b = __fmul_rn(b, 255.0f); g = __fmul_rn(g, 255.0f); r = __fmul_rn(r, 255.0f);
-        uchar ub, ug, ur;
-        if (x < trunc_cols) {
-            ub = sat_u8((int)b); ug = sat_u8((int)g); ur = sat_u8((int)r);     // v_trunc + saturating pack
-        } else {
-            ub = sat_u8(b); ug = sat_u8(g); ur = sat_u8(r);                    // saturate_cast<uchar>(float)
+        uint32_t ub, ug, ur;
+        if (x < trunc_cols) {      // v_trunc + saturating pack
+            ub = __float_as_uint(__fadd_rz(b, two23)); ug = __float_as_uint(__fadd_rz(g, two23)); ur = __float_as_uint(__fadd_rz(r, two23));
+        } else {                   // saturate_cast<uchar>(float)
+            ub = __float_as_uint(__fadd_rn(b, two23)); ug = __float_as_uint(__fadd_rn(g, two23)); ur = __float_as_uint(__fadd_rn(r, two23));
         }
-        d[bidx] = ub; d[1] = ug; d[bidx ^ 2] = ur; d[3] = 255;
+        d[bidx] = (uchar)ub; d[1] = (uchar)ug; d[bidx ^ 2] = (uchar)ur; d[3] = 255;
     }
 };
 
 // ---- generic streaming kernel -----------------------------------------------------------------------------------
-constexpr int PPT = 16;  // pixels per thread
 
 template <int N> struct Bytes {
     uint32_t w[(N + 3) / 4];
@@ -183,6 +194,10 @@ __global__ void __launch_bounds__(256) cvt_kernel(Img src, Img dst, Op op, int n
     const int n = min(PPT, src.cols - x0);
 
     if (vec_ok && n == PPT) {
+        if constexpr (POS) {
+            // position-dependent ops switch behaviour at a multiple of 32 pixels: uniform over this thread's 16 pixels
+            if (x0 < op.trunc_cols) op.trunc_cols = 0x7fffffff; else op.trunc_cols = 0;
+        }
         uint4 in[SCN];
 #pragma unroll
         for (int i = 0; i < SCN; i++) in[i] = ldg_stream((const uint4*)sp + i);

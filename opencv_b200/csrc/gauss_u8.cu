@@ -30,6 +30,7 @@ struct GU8Params {
     uint32_t kxw[8];            // row taps, 4 per word
     uint32_t kyw[4][9];         // column taps for output row phase o (0..3) and row group g: byte i = ky[4g + i - o] or 0
     int W, H, TH, border;
+    int sep_mode, even_limit;   // sepFilter2D's 8.8 fixed-point mode: columns < even_limit round half-to-even, the rest half-up (filter.simd.hpp:1011-1100)
 };
 
 __host__ __device__ constexpr bool gu_nz(int KB, int o, int g) { return 4 * g - o < KB; }
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const CUtensorMap
 #pragma unroll
             for (int o = 0; o < 4; o++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) acc[o][c] = 32768u;
+                for (int c = 0; c < 4; c++) acc[o][c] = p.sep_mode ? 32767u : 32768u;
             const uint32_t* mp0 = s_mid + (q * 2) * GU_TW + cg * 4;
 #pragma unroll
             for (int g = 0; g < GV; g++) {
@@ -165,6 +166,13 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const CUtensorMap
                         for (int c = 0; c < 4; c++) acc[o][c] = __dp2a_hi(a1[c], t, acc[o][c]);
                     }
                 }
+            }
+            if (p.sep_mode) {
+                const bool half_even = x0 + cg * 4 < p.even_limit;      // uniform over the 4 columns: even_limit is a multiple of 16
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[o][c] += half_even ? (((acc[o][c] - 32767u) >> 16) & 1u) : 1u;
             }
             uint32_t packed[4];
 #pragma unroll
@@ -210,7 +218,7 @@ static int launch_gu8(const CUtensorMap& tm, const Img& d, const GU8Params& p, i
 }
 
 // returns B200CV_NOT_IMPLEMENTED when the fast path does not apply (caller falls back to the generic kernel)
-int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st)
+int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st, int sep_mode, int even_limit)
 {
     if (!(kw & 1) || !(kh & 1) || kw < 3 || kh < 3 || kw > 31 || kh > 31) return B200CV_NOT_IMPLEMENTED;
     if (border == B200CV_BORDER_WRAP) return B200CV_NOT_IMPLEMENTED;
@@ -221,6 +229,10 @@ int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const i
     if (!KB || s.cols < KB || s.rows < KB) return B200CV_NOT_IMPLEMENTED;
     for (int i = 0; i < kw; i++) if (fx[i] < 0 || fx[i] > 255) return B200CV_NOT_IMPLEMENTED;
     for (int i = 0; i < kh; i++) if (fy[i] < 0 || fy[i] > 255) return B200CV_NOT_IMPLEMENTED;
+    int64_t sx = 0, sy = 0;
+    for (int i = 0; i < kw; i++) sx += fx[i];
+    for (int i = 0; i < kh; i++) sy += fy[i];
+    if (sx > 256 || sy > 256) return B200CV_NOT_IMPLEMENTED;      // 16-bit row sums and an unsaturated result byte
     GU8Params p;
     memset(&p, 0, sizeof(p));
     unsigned char tx[36] = {0}, ty[36] = {0};
@@ -233,7 +245,7 @@ int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const i
             for (int i = 0; i < 4; i++) { int j = 4 * g + i - o; if (j >= 0 && j < KB) w |= (uint32_t)ty[j] << (8 * i); }
             p.kyw[o][g] = w;
         }
-    p.W = s.cols; p.H = s.rows; p.border = border;
+    p.W = s.cols; p.H = s.rows; p.border = border; p.sep_mode = sep_mode; p.even_limit = even_limit;
     p.TH = ((64 - (KB - 1)) / 4) * 4;
     CUtensorMap tm;
     int rc = make_tensor_map_3d(&tm, s.data, 1, s.cols, s.rows, s.frames, s.step, s.fstep, GU_IW, p.TH + KB - 1);   // box start x0-16: 16-byte aligned

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <vector>
+#include <cub/device/device_radix_sort.cuh>
 #include "common.cuh"
 
 namespace b200cv {
@@ -229,9 +230,11 @@ __global__ void __launch_bounds__(256) frame_max_kernel(Img eig, unsigned* maxor
     if ((threadIdx.x & 31) == 0) atomicMax(maxord + f, best);
 }
 
-struct Cand { float val; int pos; };
+// candidate key: order-preserving bits of the response in the high word, row-major position in the low word.  Sorting keys
+// descending = strongest first, equal responses: larger address first (featureselect.cpp:55-60).
+typedef unsigned long long CandKey;
 
-__global__ void __launch_bounds__(256) gftt_candidates_kernel(Img eig, const unsigned* maxord, double quality, Cand* out, int cap, int* counts)
+__global__ void __launch_bounds__(256) gftt_candidates_kernel(Img eig, const unsigned* maxord, double quality, CandKey* out, int cap, int* counts)
 {
     const int f = blockIdx.z;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(256) gftt_candidates_kernel(Img eig, const uns
     }
     if (!ismax) return;
     int slot = atomicAdd(counts + f, 1);
-    if (slot < cap) { out[(size_t)f * cap + slot].val = v; out[(size_t)f * cap + slot].pos = y * W + x; }
+    if (slot < cap) out[(size_t)f * cap + slot] = ((CandKey)f2ord(v) << 32) | (unsigned)(y * W + x);
 }
 
 }  // namespace b200cv
@@ -283,15 +286,19 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
     const int W = src->cols, H = src->rows, frames = src->frames > 1 ? src->frames : 1;
     cudaStream_t st = as_stream(stream);
     // workspace: response map + per-frame max + candidate list
-    float* d_eig = nullptr; unsigned* d_max = nullptr; int* d_cnt = nullptr; Cand* d_cand = nullptr;
+    float* d_eig = nullptr; unsigned* d_max = nullptr; int* d_cnt = nullptr; CandKey* d_cand = nullptr; CandKey* d_sorted = nullptr; void* d_tmp = nullptr;
     size_t pitch = ((size_t)W * 4 + 255) & ~(size_t)255;
     int cap = (int)std::min<long long>((long long)W * H, 1 << 20);
-    auto cleanup = [&]() { cudaFreeAsync(d_eig, st); cudaFreeAsync(d_max, st); cudaFreeAsync(d_cnt, st); cudaFreeAsync(d_cand, st); };
+    auto cleanup = [&]() {
+        cudaFreeAsync(d_eig, st); cudaFreeAsync(d_max, st); cudaFreeAsync(d_cnt, st); cudaFreeAsync(d_cand, st);
+        if (d_sorted) cudaFreeAsync(d_sorted, st);
+        if (d_tmp) cudaFreeAsync(d_tmp, st);
+    };
 #define TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
     TRY(cudaMallocAsync(&d_eig, pitch * H * frames, st));
     TRY(cudaMallocAsync(&d_max, sizeof(unsigned) * frames, st));
     TRY(cudaMallocAsync(&d_cnt, sizeof(int) * frames, st));
-    TRY(cudaMallocAsync(&d_cand, sizeof(Cand) * (size_t)cap * frames, st));
+    TRY(cudaMallocAsync(&d_cand, sizeof(CandKey) * (size_t)cap * frames, st));
     TRY(cudaMemsetAsync(d_max, 0, sizeof(unsigned) * frames, st));
     TRY(cudaMemsetAsync(d_cnt, 0, sizeof(int) * frames, st));
     b200cvMat eig = {d_eig, pitch, W, H, B200CV_MAKETYPE(B200CV_32F, 1), frames, pitch * H};
@@ -306,13 +313,36 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
     std::vector<int> hcnt(frames);
     TRY(cudaMemcpyAsync(hcnt.data(), d_cnt, sizeof(int) * frames, cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
-    std::vector<Cand> cand;
+    // order the candidates on the device (library radix sort: not per-pixel work), then walk them on the host in chunks --
+    // the greedy minimum-distance selection is sequential and normally stops after a short prefix
+    int nmax = 0;
+    for (int f = 0; f < frames; f++) { hcnt[f] = std::min(hcnt[f], cap); nmax = std::max(nmax, hcnt[f]); }
+    size_t tmp_bytes = 0;
+    if (nmax) {
+        TRY(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, d_cand, d_sorted, nmax, 0, 64, st));
+        TRY(cudaMallocAsync(&d_tmp, tmp_bytes, st));
+        TRY(cudaMallocAsync(&d_sorted, sizeof(CandKey) * (size_t)cap * frames, st));
+        for (int f = 0; f < frames; f++)
+            if (hcnt[f]) {
+                TRY(cub::DeviceRadixSort::SortKeysDescending(d_tmp, tmp_bytes, d_cand + (size_t)f * cap, d_sorted + (size_t)f * cap, hcnt[f], 0, 64, st));
+                count_launch();
+            }
+    }
+    const int CHUNK = 1 << 15;
+    std::vector<CandKey> chunk;
     for (int f = 0; f < frames; f++) {
-        int n = std::min(hcnt[f], cap);
-        cand.resize(n);
-        if (n) TRY(cudaMemcpy(cand.data(), d_cand + (size_t)f * cap, sizeof(Cand) * n, cudaMemcpyDeviceToHost));
-        // strongest first; equal responses: larger address (= larger row-major position) first  (featureselect.cpp:55-60)
-        std::sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) { return a.val > b.val || (a.val == b.val && a.pos > b.pos); });
+        const int n = hcnt[f];
+        int fetched = 0;
+        // next(): the i-th strongest candidate; fetches another chunk when the walk gets there
+        auto fetch = [&](int i) -> cudaError_t {
+            if (i < fetched) return cudaSuccess;
+            int m = std::min(CHUNK, n - fetched);
+            chunk.resize(m);
+            cudaError_t ce = cudaMemcpyAsync(chunk.data(), d_sorted + (size_t)f * cap + fetched, sizeof(CandKey) * m, cudaMemcpyDeviceToHost, st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+            fetched += m;
+            return ce;
+        };
         float* outp = corners + (size_t)f * max_out * 2;
         float* outq = quality ? quality + (size_t)f * max_out : nullptr;
         int accepted = 0;
@@ -325,8 +355,11 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
             const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
             std::vector<std::vector<std::pair<float, float>>> grid((size_t)gw * gh);
             const double md2 = min_distance * min_distance;
-            for (const Cand& c : cand) {
-                int y = c.pos / W, x = c.pos - y * W;
+            for (int i = 0; i < n; i++) {
+                TRY(fetch(i));
+                const CandKey key = chunk[i - (fetched - (int)chunk.size())];
+                const int pos = (int)(unsigned)key;
+                int y = pos / W, x = pos - y * W;
                 int cx = x / cell, cy = y / cell;
                 bool keep = true;
                 for (int yy = std::max(0, cy - 1); keep && yy <= std::min(gh - 1, cy + 1); yy++)
@@ -337,13 +370,16 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
                         }
                 if (!keep) continue;
                 grid[(size_t)cy * gw + cx].emplace_back((float)x, (float)y);
-                emit(x, y, c.val);
+                emit(x, y, ord2f((unsigned)(key >> 32)));
                 if (max_corners > 0 && accepted == max_corners) break;
             }
         } else {
-            for (const Cand& c : cand) {
-                int y = c.pos / W, x = c.pos - y * W;
-                emit(x, y, c.val);
+            for (int i = 0; i < n; i++) {
+                TRY(fetch(i));
+                const CandKey key = chunk[i - (fetched - (int)chunk.size())];
+                const int pos = (int)(unsigned)key;
+                int y = pos / W, x = pos - y * W;
+                emit(x, y, ord2f((unsigned)(key >> 32)));
                 if (max_corners > 0 && accepted == max_corners) break;
             }
         }

@@ -27,7 +27,7 @@
 namespace b200cv {
 
 int sep_f32_fast(const Img& s, const Img& d, const float* kx, int nx, const float* ky, int ny, float delta, int border, const Img* dog, cudaStream_t st);
-int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st);
+int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st, int sep_mode = 0, int even_limit = 0);
 
 enum { M_FLOAT = 0, M_FIXED16 = 1, M_INT = 2 };
 
@@ -456,9 +456,19 @@ int sep_filter_impl(const b200cvMat* src, const b200cvMat* dst, const float* kx,
                     long long di = llrint(delta * (double)(1 << (2 * bits)));
                     if (di > INT32_MAX) di = INT32_MAX;
                     if (di < INT32_MIN) di = INT32_MIN;
+                    const int even_limit = ny > 1 ? ((s.cols * cn) / 16) * 16 : 0;
+                    if (ddepth == B200CV_8U && cn == 1 && di == 0 && ax == nx / 2 && ay == ny / 2 && ny > 1) {   // TMA + IDP fast path (gauss_u8.cu)
+                        int64_t qx[32], qy[32];
+                        if (nx <= 31 && ny <= 31) {
+                            for (int i = 0; i < nx; i++) qx[i] = (int64_t)ikx[i];
+                            for (int i = 0; i < ny; i++) qy[i] = (int64_t)iky[i];
+                            int frc = gauss_u8_fast(s, d, qx, nx, qy, ny, border, st, 1, even_limit);
+                            if (frc != B200CV_NOT_IMPLEMENTED) return frc;
+                        }
+                    }
                     if (ddepth == B200CV_8U)
                         return sep_dispatch<uchar, uchar, M_FIXED16>(s, d, cn, ikx.data(), nx, iky.data(), ny, ax, ay, 0.f, (int)di, border, st,
-                                                                     ny > 1 ? ((s.cols * cn) / 16) * 16 : 0);
+                                                                     even_limit);
                     return sep_dispatch<uchar, short, M_INT>(s, d, cn, ikx.data(), nx, iky.data(), ny, ax, ay, 0.f, (int)di, border, st);
                 }
             }

@@ -88,6 +88,28 @@ def test_sepfilter_variants(cvb, oracle, rng):
                  atol=2e-3, rtol=1e-5, what="sep anchor")
 
 
+@pytest.mark.parametrize("k", [3, 5, 9, 15, 31])
+def test_sepfilter_u8_fixed_fast_path(cvb, oracle, rng, k):
+    """8-bit sepFilter2D with smooth symmetric taps = the reference's 8.8 fixed-point mode (filter.dispatch.cpp:1087-1110); on rows
+    that TMA can address it runs on the IDP4A/IDP2A kernel.  The width is not a multiple of 16, so both rounding regimes of the
+    reference (vector body half-to-even, scalar tail half-up) are inside the image.  Bit-exact."""
+    import torch
+    H, W = 203, 344 + 7
+    buf = torch.from_numpy(rng.integers(0, 256, (H, 352), dtype=np.uint8)).cuda()
+    view = buf[:, :W]                                     # row stride 352: 16-byte aligned rows, ragged width
+    img = view.cpu().numpy().copy()
+    g = np.exp(-0.5 * ((np.arange(k) - k // 2) / (0.3 * ((k - 1) * 0.5 - 1) + 0.8)) ** 2); g = (g / g.sum()).astype(np.float32)
+    tri = (1 + k // 2 - np.abs(np.arange(k) - k // 2)).astype(np.float32); tri /= tri.sum()
+    for b in (0, 1, 2, 4):
+        assert_exact(cpu(cvb.sepFilter2D(view, -1, g, tri, borderType=b)), oracle.sepFilter2D(img, -1, g, tri, borderType=b), "sep u8 fixed k=%d b=%d" % (k, b))
+    # ties are rare on random data: a constant-row image whose exact value is x.5 in every pixel exercises both regimes
+    tie = np.zeros((64, 352), np.uint8); tie[:, :] = (np.arange(352) % 2 * 1 + 2)[None, :]
+    tbuf = torch.from_numpy(tie).cuda()[:, :W]
+    timg = tbuf.cpu().numpy().copy()
+    half = np.array([.25, .5, .25], np.float32)
+    assert_exact(cpu(cvb.sepFilter2D(tbuf, -1, half, half)), oracle.sepFilter2D(timg, -1, half, half), "sep u8 fixed ties")
+
+
 @pytest.mark.parametrize("ksize", [1, 3, 5, 7])
 def test_sobel(cvb, oracle, rng, ksize):
     img = rand_u8(rng, 97, 131)
