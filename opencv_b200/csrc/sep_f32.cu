@@ -1,9 +1,13 @@
-// sep_f32.cu -- single-channel float separable filter fast path (GaussianBlur f32, sepFilter2D f32, the SIFT pyramid blurs):
+// sep_f32.cu -- single-channel separable filter in float arithmetic, fast path (GaussianBlur f32, sepFilter2D f32, the SIFT
+// pyramid blurs; sepFilter2D on 8-bit data with taps that are not 8-bit exact, where the reference also computes in float):
 // TMA tile load + FFMA row/column passes, optional fused difference-of-Gaussians output.
 //
-// Same arithmetic as sep_fast_kernel<float,float,M_FLOAT,KB> in sepfilter.cu (row pass s = fma(src, kx[i], s) in tap order,
-// column pass starting from delta; reference: RowVec_32f / SymmColumnFilter, modules/imgproc/src/filter.simd.hpp:1634-1648,
-// 2652-2757) -- only the data movement differs: ONE thread issues a 3-D cp.async.bulk.tensor box load of the
+// Arithmetic = the operation order of the reference's AVX2 objects, so the results are bit-identical to the CPU's:
+//   rows     s = fma(x[i], kx[i], s) in tap order from 0 (RowVec_32f, filter.simd.hpp:1632-1650); a float source with 3 or 5
+//            (anti)symmetric taps goes centre-out: fma(x0, k0, (x-1 + x1) k1), then fma(x-2 + x2, k2, .) (SymmRowSmallVec_32f :1768-1844)
+//   columns  mirrored rows first: s = fma(ky[c], S[c], delta); s = fma(ky[c+k], S[c+k] +/- S[c-k], s)  (SymmColumnVec_32f :1878-1949,
+//            SymmColumnVec_32f8u :1158-1202).  Kernels that are not (anti)symmetric are left to the generic kernel.
+// Same arithmetic as sep_fast_kernel<.,.,M_FLOAT,KB> in sepfilter.cu -- only the data movement differs: ONE thread issues a 3-D cp.async.bulk.tensor box load of the
 // (192+2r) x (32+2r) float tile into shared memory and the CTA waits on an mbarrier, so the loads of one CTA overlap the
 // arithmetic of the other CTAs resident on the SM instead of stalling every thread on its own LDG (the generic kernel was
 // long-scoreboard bound: ncu profiles/r01_prof1_summary.txt).  TMA zero-fills outside the image (= BORDER_CONSTANT); for
@@ -22,25 +26,27 @@ struct SF32Params {
     int W, H, border;
     Img dog;
     int has_dog;
+    int row_small;             // float source, 3/5 (anti)symmetric taps: 1 symmetric, 2 antisymmetric (centre-out order), 0 tap order
+    unsigned col_sign;         // 0: symmetric column kernel, 0x80000000: antisymmetric (S[c+k] - S[c-k])
 };
 
-template <int KB>
+template <int KB, typename ST, typename DT>
 __global__ void __launch_bounds__(256, 2) sep_f32_tma_kernel(const CUtensorMap* __restrict__ tmap, Img dst, const __grid_constant__ SF32Params p)
 {
     constexpr int RB = KB / 2;
-    constexpr int RA = ((RB + 3) / 4) * 4;               // left apron staged: TMA needs the box to start on a 16-byte boundary
+    constexpr int RA = sizeof(ST) == 1 ? 16 : ((RB + 3) / 4) * 4;   // left apron staged: TMA needs the box to start on a 16-byte boundary
     constexpr int OFF = RA - RB;
     constexpr int IH = SF_TH + KB - 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float* s_in = (float*)smem_raw;                       // IH x SF_IW
-    float* s_mid = s_in + IH * SF_IW;                     // IH x SF_TW
+    ST* s_in = (ST*)smem_raw;                             // IH x SF_IW
+    float* s_mid = (float*)(smem_raw + (((size_t)IH * SF_IW * sizeof(ST) + 127) & ~(size_t)127));    // IH x SF_TW
     __shared__ __align__(8) uint64_t s_bar;
     const int f = blockIdx.z, x0 = blockIdx.x * SF_TW, y0 = blockIdx.y * SF_TH;
     const int tid = threadIdx.x;
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         fence_barrier_init();
-        mbar_arrive_expect_tx(&s_bar, (uint32_t)(SF_IW * IH * sizeof(float)));
+        mbar_arrive_expect_tx(&s_bar, (uint32_t)(SF_IW * IH * sizeof(ST)));
         tma_load_3d(s_in, tmap, x0 - RA, y0 - RB, f, &s_bar);
     }
     __syncthreads();
@@ -78,24 +84,43 @@ __global__ void __launch_bounds__(256, 2) sep_f32_tma_kernel(const CUtensorMap* 
 #pragma unroll 1
         for (int it = tid; it < IH * GPR; it += 256) {
             const int r = it / GPR, g = it - r * GPR;
-            const float4* vp = (const float4*)(s_in + r * SF_IW + g * 8);
-            float acc[8];
-#pragma unroll
-            for (int o = 0; o < 8; o++) acc[o] = 0.f;
+            float win[NV * 4];                            // the item's window (+ alignment slack), all indices compile-time
 #pragma unroll
             for (int w = 0; w < NV; w++) {
-                float4 q = vp[w];
-                const float vals[4] = {q.x, q.y, q.z, q.w};
+                if constexpr (sizeof(ST) == 1) {
+                    // bytes -> floats through the mantissa of 2^23 (PRMT + FADD instead of the quarter-rate I2F)
+                    const uint32_t q = ((const uint32_t*)(s_in + r * SF_IW + g * 8))[w];
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int e = w * 4 + b - OFF;
-                    if (e >= 0 && e < NEED) {
+                    for (int b = 0; b < 4; b++) win[w * 4 + b] = __fsub_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7650 + b)), 8388608.0f);
+                } else {
+                    const float4 q = ((const float4*)(s_in + r * SF_IW + g * 8))[w];
+                    win[w * 4] = q.x; win[w * 4 + 1] = q.y; win[w * 4 + 2] = q.z; win[w * 4 + 3] = q.w;
+                }
+            }
+            float acc[8];
+            bool done = false;
+            if constexpr (KB <= 5 && sizeof(ST) == 4) {
+                if (p.row_small) {
+                    const unsigned sg = p.row_small == 2 ? 0x80000000u : 0u;
 #pragma unroll
-                        for (int o = 0; o < 8; o++) {
-                            const int i = e - o;
-                            if (i >= 0 && i < KB) acc[o] = fmaf(vals[b], p.kx[i], acc[o]);
-                        }
+                    for (int o = 0; o < 8; o++) {
+                        const float* x = win + OFF + o + RB;      // centre tap
+                        // symmetric: fma(x0, k0, (x-1 + x1) k1); antisymmetric: (x1 - x-1) k1  (k0 = 0: fma(x0, 0, t) = t)
+                        float t = __fmul_rn(__fadd_rn(x[1], __uint_as_float(__float_as_uint(x[-1]) ^ sg)), p.kx[RB + 1]);
+                        t = fmaf(x[0], p.kx[RB], t);
+                        if constexpr (KB == 5) t = fmaf(__fadd_rn(x[2], __uint_as_float(__float_as_uint(x[-2]) ^ sg)), p.kx[RB + 2], t);
+                        acc[o] = t;
                     }
+                    done = true;
+                }
+            }
+            if (!done) {
+#pragma unroll
+                for (int o = 0; o < 8; o++) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int i = 0; i < KB; i++) t = fmaf(win[OFF + o + i], p.kx[i], t);
+                    acc[o] = t;
                 }
             }
             float4* mp = (float4*)(s_mid + r * SF_TW + g * 8);
@@ -105,52 +130,75 @@ __global__ void __launch_bounds__(256, 2) sep_f32_tma_kernel(const CUtensorMap* 
     }
     __syncthreads();
 
-    // ---- column pass: item = 4 columns x 8 rows ----
+    // ---- column pass: item = CW columns x R rows; the R + KB - 1 mid rows it needs are held in registers ----
     {
-        const bool dvec = (((uintptr_t)dst.data | dst.step | dst.fstep) & 15) == 0;
-        const bool gvec = p.has_dog && (((uintptr_t)p.dog.data | p.dog.step | p.dog.fstep) & 15) == 0;
+        constexpr int CW = KB <= 15 ? 4 : 2, R = KB <= 15 ? 2 : 4;
+        constexpr int IPR = SF_TW / CW;                   // items per row group
+        const bool dvec = (((uintptr_t)dst.data | dst.step | dst.fstep) & (CW * sizeof(DT) - 1)) == 0;
+        const bool gvec = p.has_dog && (((uintptr_t)p.dog.data | p.dog.step | p.dog.fstep) & (CW * 4 - 1)) == 0;
 #pragma unroll 1
-        for (int it = tid; it < (SF_TW / 4) * (SF_TH / 8); it += 256) {
-            const int q = it / (SF_TW / 4), c4 = it - q * (SF_TW / 4);
-            const float* mbase = s_mid + (q * 8) * SF_TW + c4 * 4;
-            float acc[8][4];
+        for (int it = tid; it < IPR * (SF_TH / R); it += 256) {
+            const int q = it / IPR, cg = it - q * IPR;
+            const float* mbase = s_mid + (q * R) * SF_TW + cg * CW;
+            float win[R + KB - 1][CW];
 #pragma unroll
-            for (int o = 0; o < 8; o++)
-#pragma unroll
-                for (int c = 0; c < 4; c++) acc[o][c] = p.delta;
-#pragma unroll
-            for (int m = 0; m < 8 + KB - 1; m++) {
-                const float4 v = *(const float4*)(mbase + m * SF_TW);
-#pragma unroll
-                for (int o = 0; o < 8; o++) {
-                    const int j = m - o;
-                    if (j >= 0 && j < KB) {
-                        const float t = p.ky[j];
-                        acc[o][0] = fmaf(v.x, t, acc[o][0]); acc[o][1] = fmaf(v.y, t, acc[o][1]);
-                        acc[o][2] = fmaf(v.z, t, acc[o][2]); acc[o][3] = fmaf(v.w, t, acc[o][3]);
-                    }
+            for (int m = 0; m < R + KB - 1; m++) {
+                if constexpr (CW == 4) {
+                    const float4 v = *(const float4*)(mbase + m * SF_TW);
+                    win[m][0] = v.x; win[m][1] = v.y; win[m][2] = v.z; win[m][3] = v.w;
+                } else {
+                    const float2 v = *(const float2*)(mbase + m * SF_TW);
+                    win[m][0] = v.x; win[m][1] = v.y;
                 }
             }
-            const int gx = x0 + c4 * 4;
+            const int gx = x0 + cg * CW;
             if (gx >= p.W) continue;
 #pragma unroll
-            for (int o = 0; o < 8; o++) {
-                const int gy = y0 + q * 8 + o;
+            for (int o = 0; o < R; o++) {
+                const int gy = y0 + q * R + o;
                 if (gy >= p.H) break;
-                float* dp = dst.row<float>(f, gy) + gx;
-                if (dvec && gx + 4 <= p.W) *(float4*)dp = make_float4(acc[o][0], acc[o][1], acc[o][2], acc[o][3]);
-                else {
+                float acc[CW];
 #pragma unroll
-                    for (int c = 0; c < 4; c++) if (gx + c < p.W) dp[c] = acc[o][c];
+                for (int c = 0; c < CW; c++) {
+                    float t = fmaf(p.ky[RB], win[o + RB][c], p.delta);
+#pragma unroll
+                    for (int k = 1; k <= RB; k++)
+                        t = fmaf(p.ky[RB + k], __fadd_rn(win[o + RB + k][c], __uint_as_float(__float_as_uint(win[o + RB - k][c]) ^ p.col_sign)), t);
+                    acc[c] = t;
                 }
-                if (p.has_dog) {
-                    const float* ctr = s_in + (q * 8 + o + RB) * SF_IW + RA + c4 * 4;
-                    float* gp = p.dog.row<float>(f, gy) + gx;
-                    if (gvec && gx + 4 <= p.W)
-                        *(float4*)gp = make_float4(__fsub_rn(acc[o][0], ctr[0]), __fsub_rn(acc[o][1], ctr[1]), __fsub_rn(acc[o][2], ctr[2]), __fsub_rn(acc[o][3], ctr[3]));
-                    else {
+                if constexpr (sizeof(DT) == 1) {
+                    uchar* dp = dst.row<uchar>(f, gy) + gx;
+                    uint32_t pk = 0;
 #pragma unroll
-                        for (int c = 0; c < 4; c++) if (gx + c < p.W) gp[c] = __fsub_rn(acc[o][c], ctr[c]);
+                    for (int c = 0; c < CW; c++) pk |= (uint32_t)sat_u8(acc[c]) << (8 * c);
+                    if (dvec && gx + CW <= p.W) {
+                        if constexpr (CW == 4) *(uint32_t*)dp = pk; else *(unsigned short*)dp = (unsigned short)pk;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CW; c++) if (gx + c < p.W) dp[c] = (uchar)(pk >> (8 * c));
+                    }
+                } else {
+                    float* dp = dst.row<float>(f, gy) + gx;
+                    if (dvec && gx + CW <= p.W) {
+                        if constexpr (CW == 4) *(float4*)dp = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        else *(float2*)dp = make_float2(acc[0], acc[1]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CW; c++) if (gx + c < p.W) dp[c] = acc[c];
+                    }
+                    if constexpr (sizeof(ST) == 4) {
+                        if (p.has_dog) {
+                            const float* ctr = (const float*)s_in + (q * R + o + RB) * SF_IW + RA + cg * CW;
+                            float* gp = p.dog.row<float>(f, gy) + gx;
+                            if (gvec && gx + CW <= p.W) {
+                                if constexpr (CW == 4)
+                                    *(float4*)gp = make_float4(__fsub_rn(acc[0], ctr[0]), __fsub_rn(acc[1], ctr[1]), __fsub_rn(acc[2], ctr[2]), __fsub_rn(acc[3], ctr[3]));
+                                else *(float2*)gp = make_float2(__fsub_rn(acc[0], ctr[0]), __fsub_rn(acc[1], ctr[1]));
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < CW; c++) if (gx + c < p.W) gp[c] = __fsub_rn(acc[c], ctr[c]);
+                            }
+                        }
                     }
                 }
             }
@@ -158,12 +206,12 @@ __global__ void __launch_bounds__(256, 2) sep_f32_tma_kernel(const CUtensorMap* 
     }
 }
 
-template <int KB>
+template <int KB, typename ST, typename DT>
 static int launch_sf32(const CUtensorMap& tm, const Img& d, const SF32Params& p, int frames, cudaStream_t st)
 {
     constexpr int IH = SF_TH + KB - 1;
-    const size_t smem = (size_t)IH * (SF_IW + SF_TW) * sizeof(float);
-    auto kern = sep_f32_tma_kernel<KB>;
+    const size_t smem = (((size_t)IH * SF_IW * sizeof(ST) + 127) & ~(size_t)127) + (size_t)IH * SF_TW * sizeof(float);
+    auto kern = sep_f32_tma_kernel<KB, ST, DT>;
     static bool attr = false;
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     CUtensorMap* dtm = nullptr;
@@ -178,10 +226,22 @@ static int launch_sf32(const CUtensorMap& tm, const Img& d, const SF32Params& p,
     return B200CV_OK;
 }
 
-// returns B200CV_NOT_IMPLEMENTED when the fast path does not apply
-int sep_f32_fast(const Img& s, const Img& d, const float* kx, int nx, const float* ky, int ny, float delta, int border, const Img* dog, cudaStream_t st)
+// 1: k[i] == k[n-1-i] for all i, 2: k[i] == -k[n-1-i], 0: neither (reference: getKernelType, filter.dispatch.cpp:225-259)
+static int symmetry_of(const float* k, int n)
+{
+    bool sy = true, as = true;
+    for (int i = 0; i < n; i++) { if (k[i] != k[n - 1 - i]) sy = false; if (k[i] != -k[n - 1 - i]) as = false; }
+    return sy ? 1 : as ? 2 : 0;
+}
+
+template <typename ST, typename DT>
+static int sep_float_fast(const Img& s, const Img& d, const float* kx, int nx, const float* ky, int ny, float delta, int border, const Img* dog, cudaStream_t st)
 {
     if (!(nx & 1) || !(ny & 1) || nx > 31 || ny > 31) return B200CV_NOT_IMPLEMENTED;
+    const int csym = symmetry_of(ky, ny);
+    if (!csym) return B200CV_NOT_IMPLEMENTED;                       // scalar ColumnFilter order: generic kernel
+    const int rsym = (sizeof(ST) == 4 && nx <= 5 && nx >= 3) ? symmetry_of(kx, nx) : 0;
+    if (rsym && (nx > ny ? nx : ny) > 5) return B200CV_NOT_IMPLEMENTED;   // small-row order inside a wide bucket: generic kernel
     if (border == B200CV_BORDER_WRAP || !tma_compatible(s) || s.frames >= 65536) return B200CV_NOT_IMPLEMENTED;
     static const int buckets[] = {3, 5, 7, 9, 11, 13, 15, 17, 21, 25, 27, 31};
     int kmax = nx > ny ? nx : ny, KB = 0;
@@ -192,25 +252,37 @@ int sep_f32_fast(const Img& s, const Img& d, const float* kx, int nx, const floa
     for (int i = 0; i < nx; i++) p.kx[(KB - nx) / 2 + i] = kx[i];
     for (int i = 0; i < ny; i++) p.ky[(KB - ny) / 2 + i] = ky[i];
     p.delta = delta; p.W = s.cols; p.H = s.rows; p.border = border;
+    p.row_small = rsym; p.col_sign = csym == 2 ? 0x80000000u : 0u;
     if (dog) { p.dog = *dog; p.has_dog = 1; }
     CUtensorMap tm;
-    int rc = make_tensor_map_3d(&tm, s.data, 4, s.cols, s.rows, s.frames, s.step, s.fstep, SF_IW, SF_TH + KB - 1);
+    int rc = make_tensor_map_3d(&tm, s.data, (int)sizeof(ST), s.cols, s.rows, s.frames, s.step, s.fstep, SF_IW, SF_TH + KB - 1);
     if (rc) return rc;
     switch (KB) {
-    case 3: return launch_sf32<3>(tm, d, p, s.frames, st);
-    case 5: return launch_sf32<5>(tm, d, p, s.frames, st);
-    case 7: return launch_sf32<7>(tm, d, p, s.frames, st);
-    case 9: return launch_sf32<9>(tm, d, p, s.frames, st);
-    case 11: return launch_sf32<11>(tm, d, p, s.frames, st);
-    case 13: return launch_sf32<13>(tm, d, p, s.frames, st);
-    case 15: return launch_sf32<15>(tm, d, p, s.frames, st);
-    case 17: return launch_sf32<17>(tm, d, p, s.frames, st);
-    case 21: return launch_sf32<21>(tm, d, p, s.frames, st);
-    case 25: return launch_sf32<25>(tm, d, p, s.frames, st);
-    case 27: return launch_sf32<27>(tm, d, p, s.frames, st);
-    case 31: return launch_sf32<31>(tm, d, p, s.frames, st);
+    case 3: return launch_sf32<3, ST, DT>(tm, d, p, s.frames, st);
+    case 5: return launch_sf32<5, ST, DT>(tm, d, p, s.frames, st);
+    case 7: return launch_sf32<7, ST, DT>(tm, d, p, s.frames, st);
+    case 9: return launch_sf32<9, ST, DT>(tm, d, p, s.frames, st);
+    case 11: return launch_sf32<11, ST, DT>(tm, d, p, s.frames, st);
+    case 13: return launch_sf32<13, ST, DT>(tm, d, p, s.frames, st);
+    case 15: return launch_sf32<15, ST, DT>(tm, d, p, s.frames, st);
+    case 17: return launch_sf32<17, ST, DT>(tm, d, p, s.frames, st);
+    case 21: return launch_sf32<21, ST, DT>(tm, d, p, s.frames, st);
+    case 25: return launch_sf32<25, ST, DT>(tm, d, p, s.frames, st);
+    case 27: return launch_sf32<27, ST, DT>(tm, d, p, s.frames, st);
+    case 31: return launch_sf32<31, ST, DT>(tm, d, p, s.frames, st);
     }
     return B200CV_NOT_IMPLEMENTED;
+}
+
+// return B200CV_NOT_IMPLEMENTED when the fast path does not apply
+int sep_f32_fast(const Img& s, const Img& d, const float* kx, int nx, const float* ky, int ny, float delta, int border, const Img* dog, cudaStream_t st)
+{
+    return sep_float_fast<float, float>(s, d, kx, nx, ky, ny, delta, border, dog, st);
+}
+
+int sep_u8_float_fast(const Img& s, const Img& d, const float* kx, int nx, const float* ky, int ny, float delta, int border, cudaStream_t st)
+{
+    return sep_float_fast<uchar, uchar>(s, d, kx, nx, ky, ny, delta, border, nullptr, st);
 }
 
 }  // namespace b200cv

@@ -26,6 +26,7 @@
 
 namespace b200cv {
 
+int sep_u8_float_fast(const Img& s, const Img& d, const float* kx, int nx, const float* ky, int ny, float delta, int border, cudaStream_t st);
 int sep_f32_fast(const Img& s, const Img& d, const float* kx, int nx, const float* ky, int ny, float delta, int border, const Img* dog, cudaStream_t st);
 int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st, int sep_mode = 0, int even_limit = 0);
 
@@ -40,6 +41,8 @@ struct SepParams {
     Img dog;          // optional second output (f32 only): dog = dst - src, the SIFT difference-of-Gaussians level
     int has_dog;
     int even_limit;   // M_FIXED16: row elements < even_limit round half-to-even (sepFilter2D's vector body), the rest half-up
+    int row_small;    // M_FLOAT, float source, 3/5 (anti)symmetric taps: 1|2 = centre-out order of SymmRowSmallVec_32f, 0 = tap order
+    int col_mode;     // M_FLOAT: 1|2 = (anti)symmetric column kernel, mirrored rows added first; 0 = scalar ColumnFilter order (no FMA)
 };
 
 template <typename T> __device__ __forceinline__ float to_f(T v) { return (float)v; }
@@ -100,7 +103,15 @@ __global__ void __launch_bounds__(256) sep_generic_kernel(Img src, Img dst, SepP
         int r = idx / mid_w, e = idx - r * mid_w;
         const float* s = s_in + r * in_w + e;
         float acc = 0.f;
-        for (int i = 0; i < nx; i++) acc = fmaf(s[i * cn], p.t.kx[i], acc);
+        if (MODE == M_FLOAT && p.row_small) {             // filter.simd.hpp:1768-1844 (see sep_f32.cu)
+            const int m = nx / 2;
+            const float sg = p.row_small == 2 ? -1.f : 1.f;
+            acc = __fmul_rn(__fadd_rn(s[(m + 1) * cn], sg * s[(m - 1) * cn]), p.t.kx[m + 1]);
+            acc = fmaf(s[m * cn], p.t.kx[m], acc);
+            if (nx == 5) acc = fmaf(__fadd_rn(s[(m + 2) * cn], sg * s[(m - 2) * cn]), p.t.kx[m + 2], acc);
+        } else {
+            for (int i = 0; i < nx; i++) acc = fmaf(s[i * cn], p.t.kx[i], acc);
+        }
         s_mid[idx] = acc;
     }
     __syncthreads();
@@ -110,8 +121,20 @@ __global__ void __launch_bounds__(256) sep_generic_kernel(Img src, Img dst, SepP
         int y = y0 + r, xe = x0 * cn + e;
         if (y >= dst.rows || xe >= dst.cols * cn) continue;
         const float* s = s_mid + r * mid_w + e;
-        float acc = MODE == M_FLOAT ? p.delta : 0.f;
-        for (int j = 0; j < ny; j++) acc = fmaf(s[j * mid_w], p.t.ky[j], acc);
+        float acc = 0.f;
+        if constexpr (MODE == M_FLOAT) {
+            if (p.col_mode) {                             // SymmColumnVec_32f / _32f8u: filter.simd.hpp:1878-1949, :1158-1202
+                const int c = ny / 2;
+                const float sg = p.col_mode == 2 ? -1.f : 1.f;
+                acc = fmaf(p.t.ky[c], s[c * mid_w], p.delta);
+                for (int k = 1; k <= c; k++) acc = fmaf(p.t.ky[c + k], __fadd_rn(s[(c + k) * mid_w], sg * s[(c - k) * mid_w]), acc);
+            } else {                                      // scalar ColumnFilter, not contracted: :2590-2640
+                acc = __fadd_rn(__fmul_rn(s[0], p.t.ky[0]), p.delta);
+                for (int j = 1; j < ny; j++) acc = __fadd_rn(acc, __fmul_rn(s[j * mid_w], p.t.ky[j]));
+            }
+        } else {
+            for (int j = 0; j < ny; j++) acc = fmaf(s[j * mid_w], p.t.ky[j], acc);
+        }
         DT outv = finish<DT, MODE>(acc, p.delta_i, xe, p.even_limit);
         dst.row<DT>(f, y)[xe] = outv;
         if constexpr (MODE == M_FLOAT && sizeof(ST) == 4 && sizeof(DT) == 4)
@@ -205,6 +228,16 @@ __global__ void __launch_bounds__(256) sep_fast_kernel(Img src, Img dst, const _
                         }
                     }
                 }
+            } else if (MODE == M_FLOAT && KB <= 5 && p.row_small) {
+                const float sg = p.row_small == 2 ? -1.f : 1.f;
+                const ST* x = base + LO + RB;              // centre tap of output 0
+#pragma unroll
+                for (int o = 0; o < F_R; o++) {
+                    float t = __fmul_rn(__fadd_rn((float)x[o + 1], sg * (float)x[o - 1]), p.t.kx[RB + 1]);
+                    t = fmaf((float)x[o], p.t.kx[RB], t);
+                    if (KB == 5) t = fmaf(__fadd_rn((float)x[o + 2], sg * (float)x[o - 2]), p.t.kx[RB + 2], t);
+                    acc[o] = t;
+                }
             } else {
                 constexpr int V0 = LO / 4, V1 = (LO + NEED - 1) / 4;
                 const float4* vp = (const float4*)base;
@@ -244,7 +277,26 @@ __global__ void __launch_bounds__(256) sep_fast_kernel(Img src, Img dst, const _
 #pragma unroll
             for (int o = 0; o < RV; o++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) acc[o][c] = MODE == M_FLOAT ? p.delta : 0.f;
+                for (int c = 0; c < 4; c++) acc[o][c] = 0.f;
+            if constexpr (MODE == M_FLOAT) {
+                // (anti)symmetric column kernel, mirrored rows added first (the only float kernels routed here)
+                const float sg = p.col_mode == 2 ? -1.f : 1.f;
+#pragma unroll 1
+                for (int o = 0; o < RV; o++) {
+                    const float* ctr = mbase + (o + RB) * F_TW;
+                    const float4 v0 = *(const float4*)ctr;
+                    const float t0 = p.t.ky[RB];
+                    float a0 = fmaf(t0, v0.x, p.delta), a1 = fmaf(t0, v0.y, p.delta), a2 = fmaf(t0, v0.z, p.delta), a3 = fmaf(t0, v0.w, p.delta);
+#pragma unroll
+                    for (int k = 1; k <= RB; k++) {
+                        const float4 va = *(const float4*)(ctr + k * F_TW), vb = *(const float4*)(ctr - k * F_TW);
+                        const float t = p.t.ky[RB + k];
+                        a0 = fmaf(t, __fadd_rn(va.x, sg * vb.x), a0); a1 = fmaf(t, __fadd_rn(va.y, sg * vb.y), a1);
+                        a2 = fmaf(t, __fadd_rn(va.z, sg * vb.z), a2); a3 = fmaf(t, __fadd_rn(va.w, sg * vb.w), a3);
+                    }
+                    acc[o][0] = a0; acc[o][1] = a1; acc[o][2] = a2; acc[o][3] = a3;
+                }
+            } else
 #pragma unroll
             for (int m = 0; m < RV + KB - 1; m++) {
                 float4 v = *(const float4*)(mbase + m * F_TW);
@@ -371,11 +423,23 @@ static int sep_dispatch(const Img& s, const Img& d, int cn, const float* kx, int
 {
     SepParams p;
     memset(&p, 0, sizeof(p));
+    bool fast_ok = true;
+    if (MODE == M_FLOAT) {
+        auto symmetry = [](const float* k, int n) {
+            bool sy = true, as = true;
+            for (int i = 0; i < n; i++) { if (k[i] != k[n - 1 - i]) sy = false; if (k[i] != -k[n - 1 - i]) as = false; }
+            return sy ? 1 : as ? 2 : 0;
+        };
+        if ((ny & 1) && ay == ny / 2) p.col_mode = symmetry(ky, ny);
+        if (sizeof(ST) == 4 && (nx == 3 || nx == 5) && ax == nx / 2) p.row_small = symmetry(kx, nx);
+        // the fast kernel implements the (anti)symmetric column order only, and the small-row order only in the 3/5 buckets
+        fast_ok = p.col_mode != 0 && (!p.row_small || (nx <= 5 && ny <= 5));
+    }
     if (dog) { p.dog = *dog; p.has_dog = 1; }
     p.delta = delta; p.delta_i = delta_i; p.border = border; p.cn = cn; p.even_limit = even_limit;
     bool centred = (nx & 1) && (ny & 1) && ax == nx / 2 && ay == ny / 2;
     int kb = centred ? fast_bucket(nx > ny ? nx : ny) : 0;
-    if (cn == 1 && kb) {
+    if (cn == 1 && kb && fast_ok) {
         int ox = (kb - nx) / 2, oy = (kb - ny) / 2;
         for (int i = 0; i < nx; i++) p.t.kx[ox + i] = kx[i];
         for (int i = 0; i < ny; i++) p.t.ky[oy + i] = ky[i];
@@ -475,6 +539,10 @@ int sep_filter_impl(const b200cvMat* src, const b200cvMat* dst, const float* kx,
         }
     }
     float fd = (float)delta;
+    if (sdepth == B200CV_8U && ddepth == B200CV_8U && cn == 1 && ax == nx / 2 && ay == ny / 2) {     // TMA fast path (sep_f32.cu); declines what it cannot do
+        int frc = sep_u8_float_fast(s, d, kx, nx, ky, ny, fd, border, st);
+        if (frc != B200CV_NOT_IMPLEMENTED) return frc;
+    }
     if (sdepth == B200CV_8U && ddepth == B200CV_8U) return sep_dispatch<uchar, uchar, M_FLOAT>(s, d, cn, kx, nx, ky, ny, ax, ay, fd, 0, border, st);
     if (sdepth == B200CV_8U && ddepth == B200CV_16S) return sep_dispatch<uchar, short, M_FLOAT>(s, d, cn, kx, nx, ky, ny, ax, ay, fd, 0, border, st);
     if (sdepth == B200CV_8U && ddepth == B200CV_32F) return sep_dispatch<uchar, float, M_FLOAT>(s, d, cn, kx, nx, ky, ny, ax, ay, fd, 0, border, st);

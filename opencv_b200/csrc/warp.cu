@@ -12,6 +12,10 @@
 // Sampling follows remapNearest / remapBilinear / remapBicubic (:329-430, :675-904, :907-1010): 5-bit sub-pixel index into
 // the 32x32 tap tables (initInterTab2D :213-287; built on the host with the same float code and uploaded once),
 // u8: sat_u8((sum + 2^14) >> 15); f32: float sums in the reference's order; borders CONSTANT/REPLICATE/REFLECT/REFLECT_101/WRAP.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "common.cuh"
 #include "host_tables.h"
@@ -73,15 +77,10 @@ __device__ __forceinline__ void warp_coords(const WarpParams& p, int x, int y, i
     }
 }
 
+// one destination pixel gathered straight from global memory, all border modes
 template <typename T, int CN, int INTERP>
-__global__ void __launch_bounds__(256) warp_kernel(Img src, Img dst, const __grid_constant__ WarpParams p)
+__device__ __forceinline__ void sample_direct(const Img& src, int f, const WarpParams& p, int sx, int sy, int a, T* d)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, f = blockIdx.z;
-    if (x >= p.dw) return;
-    int sx, sy, a;
-    warp_coords<INTERP>(p, x, y, sx, sy, a);
-    T* d = dst.row<T>(f, y) + (size_t)x * CN;
     const int sw = p.sw, sh = p.sh, border = p.border;
     T cval[4];
 #pragma unroll
@@ -179,6 +178,159 @@ __global__ void __launch_bounds__(256) warp_kernel(Img src, Img dst, const __gri
     }
 }
 
+template <typename T, int CN, int INTERP>
+__global__ void __launch_bounds__(256) warp_kernel(Img src, Img dst, const __grid_constant__ WarpParams p)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, f = blockIdx.z;
+    if (x >= p.dw) return;
+    int sx, sy, a;
+    warp_coords<INTERP>(p, x, y, sx, sy, a);
+    sample_direct<T, CN, INTERP>(src, f, p, sx, sy, a, dst.row<T>(f, y) + (size_t)x * CN);
+}
+
+// ---- tiled kernel: the source footprint of a 64x16 destination tile is staged in shared memory ---------------------------
+// The footprint is the bounding box of the tile's four corner coordinates (exact for the affine fixed-point map, which is
+// monotone in x and in y; for a projective map every pixel re-checks containment and falls back to the direct gather).
+// Staging is coalesced 16-byte traffic and applies the border rule once per staged element, so the gather itself is
+// branch-free shared-memory reads: the global-memory gather costs one L1 wavefront per touched line per tap, this costs one
+// per warp per tap.
+constexpr int WT_W = 64, WT_H = 16;
+constexpr int WT_SMEM_MAX = 96 * 1024;
+
+template <typename T, int CN, int INTERP>
+__global__ void __launch_bounds__(256) warp_tile_kernel(Img src, Img dst, const __grid_constant__ WarpParams p, int smem_cap)
+{
+    extern __shared__ __align__(16) unsigned char s_src[];
+    __shared__ int s_box[4];
+    constexpr int ES = CN * (int)sizeof(T);                  // bytes per pixel
+    constexpr int K0 = INTERP == W_CUB ? -1 : 0, K1 = INTERP == W_NN ? 0 : INTERP == W_LIN ? 1 : 2;
+    const int f = blockIdx.z, x0 = blockIdx.x * WT_W, y0 = blockIdx.y * WT_H;
+    const int tid = threadIdx.x;
+    if (tid < 32) {
+        const int cx = (tid & 1) ? min(x0 + WT_W, p.dw) - 1 : x0, cy = (tid & 2) ? min(y0 + WT_H, p.dh) - 1 : y0;
+        int sx, sy, a;
+        warp_coords<INTERP>(p, cx, cy, sx, sy, a);
+        int mnx = sx, mxx = sx, mny = sy, mxy = sy;
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        }
+        if (tid == 0) { s_box[0] = (mnx + K0) & ~15; s_box[1] = mny + K0; s_box[2] = mxx + K1; s_box[3] = mxy + K1; }
+    }
+    __syncthreads();
+    const int bx0 = s_box[0], by0 = s_box[1];
+    const int bw = (s_box[2] - bx0 + 16) & ~15, bh = s_box[3] - by0 + 1;        // staged pixels per row (multiple of 16), rows
+    int nvec = bw * ES / 16;                                                    // 16-byte vectors per staged row
+    const int pitch = (nvec | 1) * 16;                                          // odd number of vectors: rows start on different banks
+    const bool staged = (long long)pitch * bh <= smem_cap;
+    const int sw = p.sw, sh = p.sh, border = p.border;
+
+    if (staged) {
+        const bool aligned = (((uintptr_t)src.data | src.step | src.fstep) & 15) == 0;
+        const int total = nvec * bh;
+        for (int v = tid; v < total; v += 256) {
+            const int r = v / nvec, j = v - r * nvec;
+            int sy = by0 + r;
+            if ((unsigned)sy >= (unsigned)sh) sy = border == B200CV_BORDER_REPLICATE ? clipi(sy, 0, sh) : border_interpolate(sy, sh, border);
+            const long long gb = (long long)bx0 * ES + (long long)j * 16;      // first byte of this vector within the source row
+            uint4 val;
+            if (sy >= 0 && aligned && gb >= 0 && gb + 16 <= (long long)sw * ES) {
+                val = *(const uint4*)((const unsigned char*)src.row<T>(f, sy) + gb);
+            } else {
+                T e[16 / sizeof(T)];
+#pragma unroll
+                for (int i = 0; i < (int)(16 / sizeof(T)); i++) {
+                    const long long ge = gb / (long long)sizeof(T) + i;         // element index in the row (may be negative)
+                    long long px = ge >= 0 ? ge / CN : -((-ge + CN - 1) / CN);
+                    const int c = (int)(ge - px * CN);
+                    int sx = (int)px;
+                    if ((unsigned)sx >= (unsigned)sw) sx = border == B200CV_BORDER_REPLICATE ? clipi(sx, 0, sw) : border_interpolate(sx, sw, border);
+                    if (sy >= 0 && sx >= 0) e[i] = src.row<T>(f, sy)[sx * CN + c];
+                    else { if constexpr (sizeof(T) == 1) e[i] = (T)p.cval_i[c]; else e[i] = p.cval_f[c]; }
+                }
+                val = *(const uint4*)e;
+            }
+            *(uint4*)(s_src + (size_t)r * pitch + (size_t)j * 16) = val;
+        }
+    }
+    __syncthreads();
+
+    const int x = x0 + (tid & (WT_W - 1));
+    if (x >= p.dw) return;
+#pragma unroll 1
+    for (int yy = tid / WT_W; yy < WT_H; yy += 256 / WT_W) {
+        const int y = y0 + yy;
+        if (y >= p.dh) break;
+        int sx, sy, a;
+        warp_coords<INTERP>(p, x, y, sx, sy, a);
+        T* d = dst.row<T>(f, y) + (size_t)x * CN;
+        const int lx = sx + K0 - bx0, ly = sy + K0 - by0;            // first tap, staged coordinates
+        if (!staged || lx < 0 || ly < 0 || lx + (K1 - K0) >= bw || ly + (K1 - K0) >= bh) {
+            sample_direct<T, CN, INTERP>(src, f, p, sx, sy, a, d);
+            continue;
+        }
+        const T* s = (const T*)(s_src + (size_t)ly * pitch) + lx * CN;
+        const int rp = pitch / (int)sizeof(T);                       // row pitch in elements
+        if constexpr (INTERP == W_NN) {
+#pragma unroll
+            for (int c = 0; c < CN; c++) d[c] = s[c];
+        } else if constexpr (INTERP == W_LIN) {
+            if constexpr (sizeof(T) == 1) {
+                const short4 w = *(const short4*)(g_bilin_i + a * 4);
+#pragma unroll
+                for (int c = 0; c < CN; c++)
+                    d[c] = sat_u8((s[c] * w.x + s[CN + c] * w.y + s[rp + c] * w.z + s[rp + CN + c] * w.w + (1 << 14)) >> 15);
+            } else {
+                const float4 w = *(const float4*)(g_bilin_f + a * 4);
+#pragma unroll
+                for (int c = 0; c < CN; c++)
+                    d[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s[c], w.x), __fmul_rn(s[CN + c], w.y)), __fmul_rn(s[rp + c], w.z)),
+                                     __fmul_rn(s[rp + CN + c], w.w));
+            }
+        } else {
+            if constexpr (sizeof(T) == 1) {
+                short w[16];
+                *(uint4*)w = *(const uint4*)(g_bicub_i + a * 16);
+                *(uint4*)(w + 8) = *(const uint4*)(g_bicub_i + a * 16 + 8);
+#pragma unroll
+                for (int c = 0; c < CN; c++) {
+                    int sum = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) sum += s[i * rp + j * CN + c] * w[i * 4 + j];
+                    d[c] = sat_u8((sum + (1 << 14)) >> 15);
+                }
+            } else {
+                float w[16];
+#pragma unroll
+                for (int i = 0; i < 4; i++) *(float4*)(w + 4 * i) = *(const float4*)(g_bicub_f + a * 16 + 4 * i);
+                // the reference uses two different summation orders (remapBicubic, imgwarp.cpp:944-1003)
+                const bool inlier = (unsigned)(sx - 1) < (unsigned)max(sw - 3, 0) && (unsigned)(sy - 1) < (unsigned)max(sh - 3, 0);
+#pragma unroll
+                for (int c = 0; c < CN; c++) {
+                    if (inlier) {
+                        float sum = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const float* r = s + i * rp + c;
+                            float rs = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[0], w[i * 4]), __fmul_rn(r[CN], w[i * 4 + 1])),
+                                                           __fmul_rn(r[2 * CN], w[i * 4 + 2])), __fmul_rn(r[3 * CN], w[i * 4 + 3]));
+                            sum = i == 0 ? rs : __fadd_rn(sum, rs);
+                        }
+                        d[c] = sum;
+                    } else {
+                        sample_direct<T, CN, INTERP>(src, f, p, sx, sy, a, d);   // border pixels: the skip-outside-taps formula
+                        break;
+                    }
+                }
+            }
+        }
+    }
+}
+
 static int ensure_warp_tables()
 {
     static bool done = false;
@@ -194,15 +346,61 @@ static int ensure_warp_tables()
     return B200CV_OK;
 }
 
+// host estimate of the staged footprint (bytes) of one 64x16 tile whose first pixel is (x0, y0); < 0: do not stage
+static long long tile_footprint(const WarpParams& p, int x0, int y0, int es, int taps)
+{
+    double mnx = 1e300, mxx = -1e300, mny = 1e300, mxy = -1e300;
+    for (int k = 0; k < 4; k++) {
+        double x = (k & 1) ? std::min(x0 + WT_W, p.dw) - 1 : x0, y = (k & 2) ? std::min(y0 + WT_H, p.dh) - 1 : y0;
+        double X = p.M[0] * x + p.M[1] * y + p.M[2], Y = p.M[3] * x + p.M[4] * y + p.M[5], W = p.persp ? p.M[6] * x + p.M[7] * y + p.M[8] : 1.0;
+        if (!(fabs(W) > 1e-12)) return -1;
+        X /= W; Y /= W;
+        if (!(fabs(X) < 1e6 && fabs(Y) < 1e6)) return -1;
+        mnx = std::min(mnx, X); mxx = std::max(mxx, X); mny = std::min(mny, Y); mxy = std::max(mxy, Y);
+    }
+    long long bw = ((long long)(mxx - mnx) + taps + 3 + 15 + 15) & ~15LL, bh = (long long)(mxy - mny) + taps + 3;
+    long long nvec = bw * es / 16;
+    return (nvec | 1) * 16 * bh;
+}
+
+template <typename T, int CN, int INTERP>
+static int launch_warp_i(const Img& s, const Img& d, const WarpParams& p, cudaStream_t st)
+{
+    const int es = CN * (int)sizeof(T), taps = INTERP == W_NN ? 1 : INTERP == W_LIN ? 2 : 4;
+    // shared memory to request: the largest footprint over a coarse sample of tiles (an affine map has the same footprint everywhere)
+    long long need = 0;
+    const int tx = (int)div_up((unsigned)p.dw, WT_W), ty = (int)div_up((unsigned)p.dh, WT_H);
+    const int nsx = p.persp ? std::min(tx, 9) : 1, nsy = p.persp ? std::min(ty, 9) : 1;
+    for (int j = 0; j < nsy && need >= 0; j++)
+        for (int i = 0; i < nsx; i++) {
+            int bx = nsx > 1 ? (int)((long long)i * (tx - 1) / (nsx - 1)) : 0, by = nsy > 1 ? (int)((long long)j * (ty - 1) / (nsy - 1)) : 0;
+            long long fp = tile_footprint(p, bx * WT_W, by * WT_H, es, taps);
+            if (fp < 0) { need = -1; break; }
+            need = std::max(need, fp);
+        }
+    const char* path = getenv("B200CV_WARP_PATH");
+    if (need < 0 || need > WT_SMEM_MAX || (path && !strcmp(path, "direct"))) {          // heavy minification / degenerate map: direct gather
+        dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
+        warp_kernel<T, CN, INTERP><<<grid, 256, 0, st>>>(s, d, p);
+        B200_LAUNCH_CHECK();
+        return B200CV_OK;
+    }
+    int smem = (int)std::min<long long>(WT_SMEM_MAX, std::max<long long>(need + need / 8, 8 * 1024));
+    auto kern = warp_tile_kernel<T, CN, INTERP>;
+    static bool attr = false;
+    if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_MAX)); attr = true; }
+    dim3 grid((unsigned)tx, (unsigned)ty, (unsigned)s.frames);
+    kern<<<grid, 256, smem, st>>>(s, d, p, smem);
+    B200_LAUNCH_CHECK();
+    return B200CV_OK;
+}
+
 template <typename T, int CN>
 static int launch_warp(int interp, const Img& s, const Img& d, const WarpParams& p, cudaStream_t st)
 {
-    dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
-    if (interp == W_NN) warp_kernel<T, CN, W_NN><<<grid, 256, 0, st>>>(s, d, p);
-    else if (interp == W_LIN) warp_kernel<T, CN, W_LIN><<<grid, 256, 0, st>>>(s, d, p);
-    else warp_kernel<T, CN, W_CUB><<<grid, 256, 0, st>>>(s, d, p);
-    B200_LAUNCH_CHECK();
-    return B200CV_OK;
+    if (interp == W_NN) return launch_warp_i<T, CN, W_NN>(s, d, p, st);
+    if (interp == W_LIN) return launch_warp_i<T, CN, W_LIN>(s, d, p, st);
+    return launch_warp_i<T, CN, W_CUB>(s, d, p, st);
 }
 
 static int warp_common(const b200cvMat* src, const b200cvMat* dst, const double* Minv, int persp, int flags, int border,

@@ -83,9 +83,22 @@ static void sep_int(const uchar* src, size_t sstep, void* dst, size_t dstep, int
             }
 }
 
-/* float separable pass: rows first (s = 0; s = fma(src, kx[i], s)), then columns starting from delta */
+static float mul_rn(float a, float b) { volatile float p = a * b; return p; }   /* a product rounded to float on its own */
+
+/* float separable pass, in the operation order of the reference's AVX2 objects (the ones its dispatcher picks on any AVX2 host):
+   rows     tap order, s = fma(x[i], kx[i], s) from 0            RowVec_32f, filter.simd.hpp:1632-1650
+            row_mode 1|2: float source, 3 or 5 (anti)symmetric taps, centre-out
+              k=3: fma(x0, k0, (x-1 + x1)*k1)   k=5: fma(x-2 + x2, k2, <k=3 expression>)   (differences and no centre for mode 2)
+                                                                 SymmRowSmallVec_32f, :1768-1844
+   columns  col_mode 1|2: (anti)symmetric odd kernel, mirrored rows are added first:
+              s = fma(ky[c], S[c], delta); s = fma(ky[c+k], S[c+k] +/- S[c-k], s)
+                                                                 SymmColumnVec_32f / _32f8u, :1878-1949, :1158-1202
+            col_mode 0: any other kernel runs the scalar ColumnFilter, which is not contracted:
+              s = ky[0]*S[0] + delta; s += ky[j]*S[j]            :2590-2640
+   The last (w*cn mod 8) elements of a float->float row come from the reference's scalar remainder loops, whose rounding depends on
+   how its compiler contracted each of them; this port uses the formulas above there too (differences <= 1 ulp, tests/ mask them). */
 static void sep_float(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int cn, int sdepth, int ddepth,
-                      const float* kx, int nx, const float* ky, int ny, int ax, int ay, float delta, int border)
+                      const float* kx, int nx, const float* ky, int ny, int ax, int ay, float delta, int border, int col_mode, int row_mode)
 {
     int we = w * cn;
     float* mid = (float*)malloc(sizeof(float) * (size_t)we * h);
@@ -94,6 +107,21 @@ static void sep_float(const void* src, size_t sstep, void* dst, size_t dstep, in
         for (int x = 0; x < w; x++)
             for (int c = 0; c < cn; c++) {
                 float s = 0.f;
+                if (row_mode) {
+                    float v[5];
+                    for (int i = 0; i < nx; i++) {
+                        int sx = port_border(x + i - ax, w, border);
+                        v[i] = sx < 0 ? 0.f : load_f(row, sdepth, sx * cn + c);
+                    }
+                    int m = nx / 2;
+                    if (row_mode == 1) {
+                        s = fmaf(v[m], kx[m], mul_rn(v[m - 1] + v[m + 1], kx[m + 1]));
+                        if (nx == 5) s = fmaf(v[m - 2] + v[m + 2], kx[m + 2], s);
+                    } else {
+                        s = mul_rn(v[m + 1] - v[m - 1], kx[m + 1]);
+                        if (nx == 5) s = fmaf(v[m + 2] - v[m - 2], kx[m + 2], s);
+                    }
+                } else
                 for (int i = 0; i < nx; i++) {
                     int sx = port_border(x + i - ax, w, border);
                     float v = sx < 0 ? 0.f : load_f(row, sdepth, sx * cn + c);
@@ -106,10 +134,23 @@ static void sep_float(const void* src, size_t sstep, void* dst, size_t dstep, in
         void* drow = (char*)dst + (size_t)y * dstep;
         for (int e = 0; e < we; e++) {
             float s = delta;
-            for (int j = 0; j < ny; j++) {
-                int sy = port_border(y + j - ay, h, border);
-                float v = sy < 0 ? 0.f : mid[(size_t)sy * we + e];
-                s = fmaf(v, ky[j], s);
+            if (col_mode) {
+                int c = ny / 2;
+                if (col_mode == 1) {
+                    int sy = port_border(y, h, border);
+                    s = fmaf(ky[c], sy < 0 ? 0.f : mid[(size_t)sy * we + e], delta);
+                }
+                for (int k = 1; k <= c; k++) {
+                    int s0 = port_border(y + k, h, border), s1 = port_border(y - k, h, border);
+                    float a = s0 < 0 ? 0.f : mid[(size_t)s0 * we + e], b = s1 < 0 ? 0.f : mid[(size_t)s1 * we + e];
+                    s = fmaf(ky[c + k], col_mode == 1 ? a + b : a - b, s);
+                }
+            } else {
+                for (int j = 0; j < ny; j++) {
+                    int sy = port_border(y + j - ay, h, border);
+                    float v = sy < 0 ? 0.f : mid[(size_t)sy * we + e];
+                    s = j == 0 ? mul_rn(v, ky[0]) + delta : s + mul_rn(v, ky[j]);
+                }
             }
             store_f(drow, ddepth, e, s);
         }
@@ -147,7 +188,16 @@ int port_sep_filter_core(const void* src, size_t sstep, void* dst, size_t dstep,
             }
         }
     }
-    sep_float(src, sstep, dst, dstep, w, h, cn, sdepth, ddepth, kx, nx, ky, ny, ax, ay, (float)delta, border);
+    int col_mode = 0, row_mode = 0;
+    if ((ny & 1) && ay == ny / 2) {
+        int ct = ktype_of(ky, ny, ay);
+        col_mode = (ct & KT_SYMM) ? 1 : (ct & KT_ASYMM) ? 2 : 0;
+    }
+    if (sdepth == P_32F && (nx == 3 || nx == 5) && ax == nx / 2) {
+        int rt = ktype_of(kx, nx, ax);
+        row_mode = (rt & KT_SYMM) ? 1 : (rt & KT_ASYMM) ? 2 : 0;
+    }
+    sep_float(src, sstep, dst, dstep, w, h, cn, sdepth, ddepth, kx, nx, ky, ny, ax, ay, (float)delta, border, col_mode, row_mode);
     return 0;
 }
 

@@ -2,13 +2,16 @@
 
 Tolerances
   u8 GaussianBlur, u8 sepFilter2D (8-bit-exact symmetric taps), u8->s16 integer kernels: BIT-EXACT
-  f32 paths: |d| <= 1e-5 * max(1, |ref|) * taps-scale  (reference's own bar: test_filter.cpp:826-830 uses 1e-5 relative for GaussianBlur f32)
+  f32 GaussianBlur / sepFilter2D, and 8-bit sepFilter2D through float: BIT-EXACT wherever the reference runs a full SIMD vector
+    (same operation order: centre-out small rows, mirrored-pair columns, FMA); the last W*cn mod 8 (float source) / mod 16 (8-bit
+    source) elements of each row are the reference's scalar remainder loops: |d| <= 1e-4 + 1e-5 |ref| there (the reference's own
+    bar for the whole image: test_filter.cpp:826-830 uses 1e-5 relative)
   filter2D u8: <= 1 LSB (the CPU uses a DFT for >= 130 taps; its own test allows 2, test_filter.cpp:420-425)
 """
 import numpy as np
 import pytest
 
-from util import assert_close, assert_exact, cpu, gpu, rand_u8
+from util import assert_close, assert_exact, assert_exact_body, cpu, gpu, rand_u8
 
 pytestmark = pytest.mark.gpu
 
@@ -57,31 +60,44 @@ def test_gaussian_f32(cvb, oracle, rng, shape, ks):
     for b in (0, 1, 2, 4):
         want = oracle.GaussianBlur(img, (k, k), s, s, b)
         got = cpu(cvb.GaussianBlur(gpu(img), (k, k), s, s, b))
-        assert_close(got, want, atol=1e-4, rtol=1e-5, what="GaussianBlur f32 %s k=%d border=%d" % (shape, k, b))
+        assert_exact_body(got, want, 8, atol=1e-4, rtol=1e-5, what="GaussianBlur f32 %s k=%d border=%d" % (shape, k, b))
 
 
 @pytest.mark.parametrize("k", [3, 9, 31])
 def test_gaussian_f32_4k(cvb, ref, rng, k):
     img = rand_u8(rng, 2160, 3840).astype(np.float32)
-    assert_close(cpu(cvb.GaussianBlur(gpu(img), (k, k), 0)), ref.GaussianBlur(img, (k, k), 0), atol=1e-4, rtol=1e-5, what="4K f32 k=%d" % k)
+    assert_exact(cpu(cvb.GaussianBlur(gpu(img), (k, k), 0)), ref.GaussianBlur(img, (k, k), 0), "4K f32 k=%d" % k)      # 3840 % 8 == 0: no remainder columns
+    assert_exact(cpu(cvb.GaussianBlur(gpu(img), (k, k), 0.3 * k + 0.45)), ref.GaussianBlur(img, (k, k), 0.3 * k + 0.45), "4K f32 k=%d sigma" % k)
 
 
 def test_sepfilter_variants(cvb, oracle, rng):
     img1 = rand_u8(rng, 97, 131); img3 = rand_u8(rng, 61, 77, 3); f1 = img1.astype(np.float32)
     kx = rng.random(5).astype(np.float32); ky = rng.random(7).astype(np.float32)
     CV_8U, CV_16S, CV_32F = 0, 3, 5
-    assert_close(cpu(cvb.sepFilter2D(gpu(f1), -1, kx, ky)), oracle.sepFilter2D(f1, -1, kx, ky), atol=2e-3, rtol=1e-5, what="sep f32")
-    # u8 -> u8 float path (non-symmetric taps): saturate_cast rounding, allow 1 LSB at exact .5 ties of differently-rounded sums
+    assert_exact_body(cpu(cvb.sepFilter2D(gpu(f1), -1, kx, ky)), oracle.sepFilter2D(f1, -1, kx, ky), 8, atol=2e-3, rtol=1e-5, what="sep f32 (no symmetry)")
+    # u8 -> u8 through float (taps that are not 8-bit exact): same operation order as the reference, bit-exact
     a = cpu(cvb.sepFilter2D(gpu(img1), -1, kx / kx.sum(), ky / ky.sum())); b = oracle.sepFilter2D(img1, -1, kx / kx.sum(), ky / ky.sum())
-    assert_close(a, b, atol=1, what="sep u8 float path")
+    assert_exact_body(a, b, 16, atol=1, what="sep u8 float path (no symmetry)")
+    g7 = np.exp(-0.5 * ((np.arange(7) - 3) / 1.37) ** 2).astype(np.float32); g7 /= g7.sum()
+    d5 = np.array([-0.11, -0.37, 0, 0.37, 0.11], np.float32)
+    for img in (img1, img3):
+        assert_exact_body(cpu(cvb.sepFilter2D(gpu(img), -1, g7, g7)), oracle.sepFilter2D(img, -1, g7, g7), 16, atol=1, what="sep u8 float path (symmetric)")
+        assert_exact_body(cpu(cvb.sepFilter2D(gpu(img), -1, g7, d5, delta=128)), oracle.sepFilter2D(img, -1, g7, d5, delta=128), 16, atol=1,
+                          what="sep u8 float path (antisymmetric columns)")
+        f = img.astype(np.float32)
+        assert_exact_body(cpu(cvb.sepFilter2D(gpu(f), -1, d5, g7, delta=0.25)), oracle.sepFilter2D(f, -1, d5, g7, delta=0.25), 8, atol=1e-3, rtol=1e-5,
+                          what="sep f32 antisymmetric small rows")
+        assert_exact_body(cpu(cvb.sepFilter2D(gpu(f), -1, g7, d5)), oracle.sepFilter2D(f, -1, g7, d5), 8, atol=1e-3, rtol=1e-5, what="sep f32 antisymmetric columns")
     # u8 -> u8 bit-exact mode (symmetric, 8-bit exact) incl. delta and the half-even/half-up split of the reference
     for img in (img1, img3):
         for delta in (0, 3, -2.5):
             a = cpu(cvb.sepFilter2D(gpu(img), -1, [.25, .5, .25], [.125, .75, .125], delta=delta))
             b = oracle.sepFilter2D(img, -1, [.25, .5, .25], [.125, .75, .125], delta=delta)
             assert_exact(a, b, "sep u8 bit-exact mode delta=%g %s" % (delta, img.shape))
-    assert_close(cpu(cvb.sepFilter2D(gpu(img1), CV_32F, kx, ky, delta=1.5, borderType=1)),
-                 oracle.sepFilter2D(img1, CV_32F, kx, ky, delta=1.5, borderType=1), atol=2e-3, rtol=1e-5, what="sep u8->f32")
+    assert_exact_body(cpu(cvb.sepFilter2D(gpu(img1), CV_32F, kx, ky, delta=1.5, borderType=1)),
+                      oracle.sepFilter2D(img1, CV_32F, kx, ky, delta=1.5, borderType=1), 16, atol=2e-3, rtol=1e-5, what="sep u8->f32")
+    assert_exact_body(cpu(cvb.sepFilter2D(gpu(img1), CV_32F, g7, g7, delta=1.5)), oracle.sepFilter2D(img1, CV_32F, g7, g7, delta=1.5), 16, atol=2e-3, rtol=1e-5,
+                      what="sep u8->f32 symmetric")
     # anchors / even sizes go to the generic kernel
     kx4 = rng.random(4).astype(np.float32)
     assert_close(cpu(cvb.sepFilter2D(gpu(f1), -1, kx4, ky, anchor=(1, 5))), oracle.sepFilter2D(f1, -1, kx4, ky, anchor=(1, 5)),
@@ -98,10 +114,16 @@ def test_sepfilter_u8_fixed_fast_path(cvb, oracle, rng, k):
     buf = torch.from_numpy(rng.integers(0, 256, (H, 352), dtype=np.uint8)).cuda()
     view = buf[:, :W]                                     # row stride 352: 16-byte aligned rows, ragged width
     img = view.cpu().numpy().copy()
-    g = np.exp(-0.5 * ((np.arange(k) - k // 2) / (0.3 * ((k - 1) * 0.5 - 1) + 0.8)) ** 2); g = (g / g.sum()).astype(np.float32)
+    g = np.exp(-0.5 * ((np.arange(k) - k // 2) / (0.3 * ((k - 1) * 0.5 - 1) + 0.8)) ** 2); g = np.rint(g / g.sum() * 256)
+    g[k // 2] += 256 - g.sum(); g = (g / 256).astype(np.float32)          # exact 8-bit taps summing to 1: the reference's bit-exact mode
     tri = (1 + k // 2 - np.abs(np.arange(k) - k // 2)).astype(np.float32); tri /= tri.sum()
     for b in (0, 1, 2, 4):
         assert_exact(cpu(cvb.sepFilter2D(view, -1, g, tri, borderType=b)), oracle.sepFilter2D(img, -1, g, tri, borderType=b), "sep u8 fixed k=%d b=%d" % (k, b))
+    # taps that are NOT 8-bit exact: the reference computes in float; TMA float kernel, bit-exact outside the remainder columns
+    gs = np.exp(-0.5 * ((np.arange(k) - k // 2) / (0.3 * ((k - 1) * 0.5 - 1) + 0.87)) ** 2).astype(np.float32); gs /= gs.sum()
+    for b in (0, 1, 4):
+        assert_exact_body(cpu(cvb.sepFilter2D(view, -1, gs, gs, borderType=b)), oracle.sepFilter2D(img, -1, gs, gs, borderType=b), 16, atol=1,
+                          what="sep u8 float path, TMA kernel k=%d b=%d" % (k, b))
     # ties are rare on random data: a constant-row image whose exact value is x.5 in every pixel exercises both regimes
     tie = np.zeros((64, 352), np.uint8); tie[:, :] = (np.arange(352) % 2 * 1 + 2)[None, :]
     tbuf = torch.from_numpy(tie).cuda()[:, :W]

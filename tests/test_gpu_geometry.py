@@ -121,3 +121,31 @@ def test_warp_8k(cvb, ref, rng, interp):
     H = np.array([[0.95, 0.02, 50], [-0.015, 0.97, 30], [1e-6, 2e-6, 1]])
     assert_exact(cpu(cvb.warpPerspective(gpu(img), H, (7680, 4320), interp, C.BORDER_CONSTANT)), ref.warpPerspective(img, H, (7680, 4320), interp, C.BORDER_CONSTANT),
                  "8K perspective %d" % interp)
+
+
+@pytest.mark.parametrize("interp", [C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC])
+def test_warp_tile_and_direct_paths(cvb, oracle, rng, interp, monkeypatch):
+    """The tiled kernel stages each 64x16 tile's source footprint in shared memory; maps whose footprint does not fit (strong
+    minification, a horizon inside the image) use the direct gather, per launch or per tile/pixel.  Both must equal the CPU."""
+    img = rand_u8(rng, 331, 517, 3)
+    f32 = rand_u8(rng, 207, 333).astype(np.float32)
+    maps = [
+        np.array([[0.8, 0.6, -40.0], [-0.6, 0.8, 120.0]]),        # 37 degree rotation
+        np.array([[6.5, 0.3, -100.0], [0.2, 7.0, -50.0]]),        # 7x minification: footprint too large -> direct kernel
+        np.array([[-1.0, 0.0, 500.0], [0.0, -1.0, 300.0]]),       # 180 degree flip: decreasing coordinates
+    ]
+    for M in maps:
+        for border in (C.BORDER_CONSTANT, C.BORDER_REFLECT_101):
+            flags = interp | C.WARP_INVERSE_MAP
+            assert_exact(cpu(cvb.warpAffine(gpu(img), M, (401, 283), flags, border, (9, 8, 7, 6))), oracle.warpAffine(img, M, (401, 283), flags, border, (9, 8, 7, 6)),
+                         "warpAffine tile path %s" % M[0])
+            assert_close(cpu(cvb.warpAffine(gpu(f32), M, (401, 283), flags, border, 3.0)), oracle.warpAffine(f32, M, (401, 283), flags, border, 3.0),
+                         atol=2e-4, what="warpAffine f32 tile path")
+    Hs = [np.array([[0.9, 0.1, 5.0], [-0.08, 1.1, 3.0], [4e-4, 3e-4, 1.0]]),
+          np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, -8e-3, 1.0]])]       # W crosses zero inside the destination
+    for Hm in Hs:
+        got = cpu(cvb.warpPerspective(gpu(img), Hm, (401, 283), interp | C.WARP_INVERSE_MAP, C.BORDER_REPLICATE))
+        assert_exact(got, oracle.warpPerspective(img, Hm, (401, 283), interp | C.WARP_INVERSE_MAP, C.BORDER_REPLICATE), "warpPerspective tile path")
+        monkeypatch.setenv("B200CV_WARP_PATH", "direct")
+        assert_exact(got, cpu(cvb.warpPerspective(gpu(img), Hm, (401, 283), interp | C.WARP_INVERSE_MAP, C.BORDER_REPLICATE)), "tile vs direct")
+        monkeypatch.delenv("B200CV_WARP_PATH")
