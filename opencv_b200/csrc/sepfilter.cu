@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(256) sep_generic_kernel(Img src, Img dst, SepP
                 const float sg = p.col_mode == 2 ? -1.f : 1.f;
                 acc = fmaf(p.t.ky[c], s[c * mid_w], p.delta);
                 for (int k = 1; k <= c; k++) acc = fmaf(p.t.ky[c + k], __fadd_rn(s[(c + k) * mid_w], sg * s[(c - k) * mid_w]), acc);
-            } else {                                      // scalar ColumnFilter, not contracted: :2590-2640
-                acc = __fadd_rn(__fmul_rn(s[0], p.t.ky[0]), p.delta);
+            } else {                                      // scalar ColumnFilter: products rounded before they are added, :2590-2640
+                acc = fmaf(s[0], p.t.ky[0], p.delta);      // only the delta term is contracted in the reference object
                 for (int j = 1; j < ny; j++) acc = __fadd_rn(acc, __fmul_rn(s[j * mid_w], p.t.ky[j]));
             }
         } else {

@@ -379,7 +379,8 @@ static int launch_warp_i(const Img& s, const Img& d, const WarpParams& p, cudaSt
             need = std::max(need, fp);
         }
     const char* path = getenv("B200CV_WARP_PATH");
-    if (need < 0 || need > WT_SMEM_MAX || (path && !strcmp(path, "direct"))) {          // heavy minification / degenerate map: direct gather
+    // one tap per pixel (NEAREST) does not repay the staging pass
+    if (INTERP == W_NN || need < 0 || need > WT_SMEM_MAX || (path && !strcmp(path, "direct"))) {          // heavy minification / degenerate map: direct gather
         dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
         warp_kernel<T, CN, INTERP><<<grid, 256, 0, st>>>(s, d, p);
         B200_LAUNCH_CHECK();

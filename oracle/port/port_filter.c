@@ -94,7 +94,7 @@ static float mul_rn(float a, float b) { volatile float p = a * b; return p; }   
               s = fma(ky[c], S[c], delta); s = fma(ky[c+k], S[c+k] +/- S[c-k], s)
                                                                  SymmColumnVec_32f / _32f8u, :1878-1949, :1158-1202
             col_mode 0: any other kernel runs the scalar ColumnFilter, which is not contracted:
-              s = ky[0]*S[0] + delta; s += ky[j]*S[j]            :2590-2640
+              s = fma(ky[0], S[0], delta); s += round(ky[j]*S[j])   :2590-2640 (as compiled: only the delta term is fused)
    The last (w*cn mod 8) elements of a float->float row come from the reference's scalar remainder loops, whose rounding depends on
    how its compiler contracted each of them; this port uses the formulas above there too (differences <= 1 ulp, tests/ mask them). */
 static void sep_float(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int cn, int sdepth, int ddepth,
@@ -108,7 +108,7 @@ static void sep_float(const void* src, size_t sstep, void* dst, size_t dstep, in
             for (int c = 0; c < cn; c++) {
                 float s = 0.f;
                 if (row_mode) {
-                    float v[5];
+                    float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
                     for (int i = 0; i < nx; i++) {
                         int sx = port_border(x + i - ax, w, border);
                         v[i] = sx < 0 ? 0.f : load_f(row, sdepth, sx * cn + c);
@@ -149,7 +149,7 @@ static void sep_float(const void* src, size_t sstep, void* dst, size_t dstep, in
                 for (int j = 0; j < ny; j++) {
                     int sy = port_border(y + j - ay, h, border);
                     float v = sy < 0 ? 0.f : mid[(size_t)sy * we + e];
-                    s = j == 0 ? mul_rn(v, ky[0]) + delta : s + mul_rn(v, ky[j]);
+                    s = j == 0 ? fmaf(v, ky[0], delta) : s + mul_rn(v, ky[j]);
                 }
             }
             store_f(drow, ddepth, e, s);

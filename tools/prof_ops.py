@@ -21,6 +21,8 @@ half = torch.empty((2, 2160, 3840, 3), dtype=torch.uint8, device=dev)
 k5 = torch.empty((2, 2880, 5120, 3), dtype=torch.uint8, device=dev)
 M = np.array([[0.8911, 0.1094, 182.0], [-0.1094, 0.8911, 655.0]])
 templ = u8[0, 700:764, 1000:1064, 0].contiguous()
+g11 = cvb.getGaussianKernel(11, 0).astype(np.float32).ravel()
+g31 = cvb.getGaussianKernel(31, 0).astype(np.float32).ravel()
 ops = {
     "gauss_u8_k3": lambda: cvb.GaussianBlur(u8, (3, 3), 0, dst=o8),
     "gauss_u8_k5": lambda: cvb.GaussianBlur(u8, (5, 5), 0, dst=o8),
@@ -35,6 +37,15 @@ ops = {
     "hsv2bgr": lambda: cvb.cvtColor(bgr, 54, dst=obgr),
     "bgr2yuv": lambda: cvb.cvtColor(bgr, 82, dst=obgr),
     "match": lambda: cvb.matchTemplate(u8[:2], templ, 2),
+    "gauss_f32_k11": lambda: cvb.GaussianBlur(f32, (11, 11), 0, dst=o32),
+    "gauss_f32_k3": lambda: cvb.GaussianBlur(f32, (3, 3), 0, dst=o32),
+    "sep_u8_k11": lambda: cvb.sepFilter2D(u8, -1, g11, g11, dst=o8),
+    "sep_u8_k31": lambda: cvb.sepFilter2D(u8, -1, g31, g31, dst=o8),
+    "filter2d_u8_k31": lambda: cvb.filter2D(u8, -1, np.outer(g31, g31), dst=o8),
+    "filter2d_u8_k11": lambda: cvb.filter2D(u8, -1, np.outer(g11, g11), dst=o8),
+    "warp_cub": lambda: cvb.warpAffine(bgr, M, (7680, 4320), 2, dst=obgr),
+    "resize_cub5k": lambda: cvb.resize(bgr, (5120, 2880), interpolation=2, dst=k5),
+    "resize_lin_up": lambda: cvb.resize(half, (7680, 4320), interpolation=1, dst=obgr),
 }
 for name, fn in ops.items():
     if which and name not in which:
