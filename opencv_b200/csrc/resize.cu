@@ -13,6 +13,9 @@
 //             u8 V pass: the reference's SSE body evaluates S0*b0+(S1*b1+(S2*b2+S3*b3)) in float with b=beta/2^22 and
 //             rounds half-even for the first floor8(width*cn) elements of a row, and uses (sum+2^21)>>22 for the tail
 //             (VResizeCubicVec_32s8u :1408-1444, FixedPtCast :2059-2060) -- both are reproduced, so u8 CUBIC is bit-exact.
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
 #include "common.cuh"
 
 namespace b200cv {
@@ -288,6 +291,190 @@ __global__ void __launch_bounds__(256) resize_cubic_kernel(Img src, Img dst, Res
     }
 }
 
+
+// ---- LINEAR / CUBIC, tiled ------------------------------------------------------------------------------------------------
+// The per-pixel kernels above gather every tap from global memory (2*CN or 4*CN byte loads per source row and pixel, each a
+// separate L1 wavefront) and redo the horizontal pass for every destination row.  The tiled kernel follows the reference's own
+// structure (resizeGeneric_: a horizontal pass per SOURCE row into a ring of intermediate rows, then the vertical pass,
+// resize.cpp:2192-2258): the source footprint of a 128 x 16 destination tile is staged in shared memory with coalesced 16-byte
+// loads, each staged row is filtered horizontally once into a 32-bit intermediate row, and the vertical pass combines
+// intermediate rows 4 elements per thread and stores 4 bytes (u8) or 16 bytes (f32) at a time.  Same integer / float
+// operations per element as the per-pixel kernels (bit-exact with the CPU).
+constexpr int RT_W = 128, RT_H = 16;
+
+template <int TAPS> struct RTab {     // per destination column of the tile
+    int off[TAPS];                    // byte offsets of the taps inside a staged row (clamped like the reference's xofs loops)
+    union { int ic[TAPS]; float fc[TAPS]; };
+};
+
+template <typename T, int CN, bool CUBIC>
+__global__ void __launch_bounds__(256) resize_tile_kernel(Img src, Img dst, ResizeParams p, const ResTab* __restrict__ xt, const ResTab* __restrict__ yt)
+{
+    constexpr int TAPS = CUBIC ? 4 : 2;
+    constexpr int ES = CN * (int)sizeof(T);
+    constexpr int EW = RT_W * CN;                    // intermediate elements per row
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_geo[6];
+    const int f = blockIdx.z, x0 = blockIdx.x * RT_W, y0 = blockIdx.y * RT_H;
+    const int tid = threadIdx.x;
+    const int x1 = min(x0 + RT_W, p.dw) - 1, y1 = min(y0 + RT_H, p.dh) - 1;
+    if (tid == 0) {
+        const int sxl = CUBIC ? clip_i(xt[x0].s - 1, 0, p.sw) : xt[x0].s;
+        const int sxh = CUBIC ? clip_i(xt[x1].s + 2, 0, p.sw) : min(xt[x1].s + 1, p.sw - 1);
+        const int syl = clip_i(yt[y0].s - (CUBIC ? 1 : 0), 0, p.sh), syh = clip_i(yt[y1].s + (CUBIC ? 2 : 1), 0, p.sh);
+        const int bx0 = sxl & ~15;                                    // staged rows start on a 16-pixel (hence 16-byte) boundary
+        const int nvec = ((sxh - bx0 + 1) * ES + 15) / 16;
+        s_geo[0] = bx0; s_geo[1] = nvec; s_geo[2] = syl; s_geo[3] = syh - syl + 1;
+    }
+    __syncthreads();
+    const int bx0 = s_geo[0], nvec = s_geo[1], sy_lo = s_geo[2], nrows = s_geo[3];
+    const int pitch = nvec * 16;
+    unsigned char* s_src = smem;                                                      // nrows x pitch
+    typedef typename std::conditional<sizeof(T) == 1, int, float>::type MT;
+    MT* s_mid = (MT*)(smem + (size_t)nrows * pitch);                                  // nrows x EW
+    RTab<TAPS>* s_tab = (RTab<TAPS>*)(s_mid + (size_t)nrows * EW);                    // RT_W
+
+    // ---- stage the footprint + the column table ----
+    {
+        const bool aligned = (((uintptr_t)src.data | src.step | src.fstep) & 15) == 0;
+        const long long rowbytes = (long long)p.sw * ES;
+        for (int v = tid; v < nvec * nrows; v += 256) {
+            const int r = v / nvec, j = v - r * nvec;
+            const unsigned char* srow = (const unsigned char*)src.row<T>(f, sy_lo + r);
+            const long long gb = (long long)bx0 * ES + (long long)j * 16;
+            uint4 val;
+            if (aligned && gb + 16 <= rowbytes) val = *(const uint4*)(srow + gb);
+            else {
+                unsigned char b[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) b[i] = gb + i < rowbytes ? srow[gb + i] : (unsigned char)0;
+                val = *(const uint4*)b;
+            }
+            *(uint4*)(s_src + (size_t)r * pitch + (size_t)j * 16) = val;
+        }
+        if (tid < RT_W) {
+            const int x = min(x0 + tid, p.dw - 1);
+            const ResTab t = xt[x];
+            RTab<TAPS> o;
+#pragma unroll
+            for (int j = 0; j < TAPS; j++) {
+                int sx;
+                if (CUBIC) sx = min(max(t.s - 1 + j, 0), p.sw - 1);                 // per-tap clamping == the while-loops of HResizeCubic
+                else sx = (j == 1 && !t.last) ? t.s + 1 : t.s;                       // dx >= xmax: D = S[sx] * ONE (taps are (ONE, 0) there)
+                o.off[j] = (sx - bx0) * ES;
+                o.ic[j] = t.ic[j];
+            }
+            if (!CUBIC && t.last) { if (sizeof(T) == 1) { o.ic[0] = 2048; o.ic[1] = 0; } else { o.fc[0] = 1.f; o.fc[1] = 0.f; } }
+            s_tab[tid] = o;
+        }
+    }
+    __syncthreads();
+
+    // ---- horizontal pass: item = 4 consecutive intermediate elements of one staged row ----
+    for (int it = tid; it < nrows * (EW / 4); it += 256) {
+        const int r = it / (EW / 4), e0 = (it - r * (EW / 4)) * 4;
+        const unsigned char* srow = s_src + (size_t)r * pitch;
+        MT out[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int e = e0 + i, xl = e / CN, c = e - xl * CN;
+            const RTab<TAPS>& t = s_tab[xl];
+            if constexpr (sizeof(T) == 1) {
+                int acc = 0;
+#pragma unroll
+                for (int j = 0; j < TAPS; j++) acc += srow[t.off[j] + c] * t.ic[j];
+                out[i] = acc;
+            } else {
+                const float* fr = (const float*)srow;
+                float acc = __fmul_rn(fr[(t.off[0] >> 2) + c], t.fc[0]);
+#pragma unroll
+                for (int j = 1; j < TAPS; j++) acc = __fadd_rn(acc, __fmul_rn(fr[(t.off[j] >> 2) + c], t.fc[j]));
+                out[i] = acc;
+            }
+        }
+        *(uint4*)(s_mid + (size_t)r * EW + e0) = *(const uint4*)out;
+    }
+    __syncthreads();
+
+    // ---- vertical pass: item = 4 consecutive elements of one destination row ----
+    const int row_elems = p.dw * CN;
+    const int vec_limit = sizeof(T) == 1 ? (row_elems / 8) * 8 : (row_elems / 4) * 4;      // reference SIMD body / scalar tail split (cubic)
+    const bool dvec = (((uintptr_t)dst.data | dst.step | dst.fstep) & (4 * sizeof(T) - 1)) == 0;
+    for (int it = tid; it < RT_H * (EW / 4); it += 256) {
+        const int yy = it / (EW / 4), e0 = (it - yy * (EW / 4)) * 4;
+        const int y = y0 + yy;
+        const int E0 = x0 * CN + e0;                  // element index in the destination row
+        if (y > y1 || E0 >= row_elems) continue;
+        const ResTab ty = yt[y];
+        MT m[TAPS][4];
+#pragma unroll
+        for (int k = 0; k < TAPS; k++) {
+            const int rr = clip_i(ty.s + k - (CUBIC ? 1 : 0), 0, p.sh) - sy_lo;       // rows are clipped when fetched, the taps keep fy (:2211)
+            *(uint4*)m[k] = *(const uint4*)(s_mid + (size_t)rr * EW + e0);
+        }
+        T out[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if constexpr (sizeof(T) == 1) {
+                if constexpr (!CUBIC) {
+                    out[i] = (uchar)((((ty.ic[0] * (m[0][i] >> 4)) >> 16) + ((ty.ic[1] * (m[1][i] >> 4)) >> 16) + 2) >> 2);
+                } else if (E0 + i < vec_limit) {
+                    const float sc = 1.f / (2048.f * 2048.f);
+                    float v = __fmul_rn((float)m[3][i], __fmul_rn((float)ty.ic[3], sc));
+                    v = __fadd_rn(__fmul_rn((float)m[2][i], __fmul_rn((float)ty.ic[2], sc)), v);
+                    v = __fadd_rn(__fmul_rn((float)m[1][i], __fmul_rn((float)ty.ic[1], sc)), v);
+                    v = __fadd_rn(__fmul_rn((float)m[0][i], __fmul_rn((float)ty.ic[0], sc)), v);
+                    out[i] = sat_u8(__float2int_rn(v));
+                } else {
+                    out[i] = sat_u8((m[0][i] * ty.ic[0] + m[1][i] * ty.ic[1] + m[2][i] * ty.ic[2] + m[3][i] * ty.ic[3] + (1 << 21)) >> 22);
+                }
+            } else {
+                if constexpr (!CUBIC) {
+                    out[i] = __fadd_rn(__fmul_rn(m[0][i], ty.fc[0]), __fmul_rn(m[1][i], ty.fc[1]));
+                } else if (E0 + i < vec_limit) {
+                    float o = __fmul_rn(m[3][i], ty.fc[3]);
+                    o = __fadd_rn(__fmul_rn(m[2][i], ty.fc[2]), o);
+                    o = __fadd_rn(__fmul_rn(m[1][i], ty.fc[1]), o);
+                    out[i] = __fadd_rn(__fmul_rn(m[0][i], ty.fc[0]), o);
+                } else {
+                    float o = __fmul_rn(m[0][i], ty.fc[0]);
+                    o = __fadd_rn(o, __fmul_rn(m[1][i], ty.fc[1]));
+                    o = __fadd_rn(o, __fmul_rn(m[2][i], ty.fc[2]));
+                    out[i] = __fadd_rn(o, __fmul_rn(m[3][i], ty.fc[3]));
+                }
+            }
+        }
+        T* dp = dst.row<T>(f, y) + E0;
+        if (dvec && E0 + 4 <= row_elems) {
+            if constexpr (sizeof(T) == 1) *(uint32_t*)dp = *(const uint32_t*)out;
+            else *(float4*)dp = *(const float4*)out;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) if (E0 + i < row_elems) dp[i] = out[i];
+        }
+    }
+}
+
+// shared memory a tile can need (rigorous: s(x) = floor((x + 0.5) scale - 0.5) grows by at most ceil(n scale) + 1 over n columns)
+static size_t resize_tile_smem(const ResizeParams& p, int es, int cn, int taps)
+{
+    const long long wpx = (long long)ceil((RT_W - 1) * p.scale_x) + 1 + taps + 15 + 1;
+    const long long rows = (long long)ceil((RT_H - 1) * p.scale_y) + 1 + taps + 1;
+    const long long pitch = ((wpx * es + 15) / 16 + 1) * 16;
+    return (size_t)(rows * (pitch + (long long)RT_W * cn * 4) + (long long)RT_W * taps * 8 + 64);
+}
+
+template <typename T, int CN, bool CUBIC>
+static int launch_resize_tile(const Img& s, const Img& d, const ResizeParams& p, const ResTab* xt, const ResTab* yt, size_t smem, cudaStream_t st)
+{
+    auto kern = resize_tile_kernel<T, CN, CUBIC>;
+    static bool attr = false;
+    if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+    dim3 grid(div_up((unsigned)p.dw, RT_W), div_up((unsigned)p.dh, RT_H), (unsigned)s.frames);
+    kern<<<grid, 256, smem, st>>>(s, d, p, xt, yt);
+    return B200CV_OK;
+}
+
 template <typename T>
 static int launch_by_cn(int cn, int interp, const Img& s, const Img& d, const ResizeParams& p, cudaStream_t st)
 {
@@ -299,6 +486,20 @@ static int launch_by_cn(int cn, int interp, const Img& s, const Img& d, const Re
     if (interp == B200CV_INTER_LINEAR) resize_tab_kernel<false, FIX><<<nt, 256, 0, st>>>(xt, yt, p);
     else resize_tab_kernel<true, FIX><<<nt, 256, 0, st>>>(xt, yt, p);
     count_launch();
+    const bool cubic = interp != B200CV_INTER_LINEAR;
+    const size_t tsmem = resize_tile_smem(p, cn * (int)sizeof(T), cn, cubic ? 4 : 2);
+    const char* path = getenv("B200CV_RESIZE_PATH");
+    if (tsmem <= 160 * 1024 && !(path && !strcmp(path, "pixel"))) {         // strong minification does not fit: per-pixel kernels below
+#define LT(CN) (cubic ? launch_resize_tile<T, CN, true>(s, d, p, xt, yt, tsmem, st) : launch_resize_tile<T, CN, false>(s, d, p, xt, yt, tsmem, st))
+        int rc = cn == 1 ? LT(1) : cn == 3 ? LT(3) : LT(4);
+#undef LT
+        cudaError_t e = cudaGetLastError();
+        cudaFreeAsync(tab, st);
+        count_launch();
+        if (rc) return rc;
+        if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
+        return B200CV_OK;
+    }
     dim3 grid(div_up((unsigned)p.dw, 256), div_up((unsigned)p.dh, RS_ROWS), (unsigned)s.frames);
 #define L(K, CN) K<T, CN><<<grid, 256, 0, st>>>(s, d, p, xt, yt)
     if (interp == B200CV_INTER_LINEAR) {

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256, 2) sep_f32_tma_kernel(const CUtensorMap* 
 
     // ---- column pass: item = CW columns x R rows; the R + KB - 1 mid rows it needs are held in registers ----
     {
-        constexpr int CW = KB <= 15 ? 4 : 2, R = KB <= 15 ? 2 : 4;
+        constexpr int CW = KB <= 15 ? 4 : 2, R = 8;        // window: (R + KB - 1) x CW registers (<= 88)
         constexpr int IPR = SF_TW / CW;                   // items per row group
         const bool dvec = (((uintptr_t)dst.data | dst.step | dst.fstep) & (CW * sizeof(DT) - 1)) == 0;
         const bool gvec = p.has_dog && (((uintptr_t)p.dog.data | p.dog.step | p.dog.fstep) & (CW * 4 - 1)) == 0;
