@@ -14,6 +14,7 @@
 
 namespace b200cv {
 
+int filter2d_tma(const Img& s, const Img& d, int sd, int dd, int cn, const float* k, int kw, int kh, int ax, int ay, float delta, int border, cudaStream_t st);
 int filter2d_u8_tensor(const Img& s, const Img& d, int dd, const float* k, int kw, int kh, int ax, int ay, float delta, int border, cudaStream_t st);
 
 struct F2DParams {
@@ -197,6 +198,13 @@ extern "C" int b200cv_filter2d(const b200cvMat* src, const b200cvMat* dst, const
         const char* path = getenv("B200CV_FILTER2D_PATH");
         if (!(path && !strcmp(path, "direct"))) {
             rc = filter2d_u8_tensor(s, d, dd, kernel, kw, kh, ax, ay, fd, border, st);
+            if (rc != B200CV_NOT_IMPLEMENTED) return rc;
+        }
+    }
+    {
+        const char* path = getenv("B200CV_FILTER2D_PATH");
+        if (!(path && !strcmp(path, "v1"))) {
+            rc = filter2d_tma(s, d, sd, dd, cn, kernel, kw, kh, ax, ay, fd, border, st);
             if (rc != B200CV_NOT_IMPLEMENTED) return rc;
         }
     }

@@ -178,6 +178,35 @@ def test_filter2d_tensor_core(cvb, oracle, rng, monkeypatch):
                      atol=1, what="filter2D tc u8->s16")
 
 
+@pytest.mark.parametrize("ksz", [(3, 3), (5, 5), (9, 9), (7, 3), (3, 13), (21, 21)])
+def test_filter2d_tma_path(cvb, oracle, rng, ksz, monkeypatch):
+    """single-channel filter2D on TMA-addressable rows (16-byte aligned pitch) runs the TMA tile kernel; identical arithmetic to the
+    generic kernels (must agree bit for bit with them) and within the reference's own tolerance of the CPU."""
+    import torch
+    kw, kh = ksz
+    H, W = 131, 421
+    buf = torch.from_numpy(rng.integers(0, 256, (2, H, 432, 1), dtype=np.uint8)).cuda()
+    view = buf[:, :, :W]
+    img = view.cpu().numpy().copy()
+    fbuf = torch.from_numpy((rng.random((H, 432)) * 255).astype(np.float32)).cuda()
+    fview = fbuf[:, :W]
+    fimg = fview.cpu().numpy().copy()
+    ker = (rng.random((kh, kw)).astype(np.float32) - 0.2); ker /= np.abs(ker).sum()
+    for b in (0, 1, 2, 4):
+        got = cpu(cvb.filter2D(view, -1, ker, delta=1.25, borderType=b))
+        gotf = cpu(cvb.filter2D(fview, -1, ker, delta=1.25, borderType=b))
+        got32 = cpu(cvb.filter2D(view, 5, ker, borderType=b))
+        monkeypatch.setenv("B200CV_FILTER2D_PATH", "v1")
+        if kw * kh < 121:       # larger 8-bit kernels take the tensor-core path unless told otherwise
+            assert_exact(got, cpu(cvb.filter2D(view, -1, ker, delta=1.25, borderType=b)), "filter2D tma vs v1 u8 %s b=%d" % (ksz, b))
+            assert_exact(got32, cpu(cvb.filter2D(view, 5, ker, borderType=b)), "filter2D tma vs v1 u8->f32 %s b=%d" % (ksz, b))
+        assert_exact(gotf, cpu(cvb.filter2D(fview, -1, ker, delta=1.25, borderType=b)), "filter2D tma vs v1 f32 %s b=%d" % (ksz, b))
+        monkeypatch.delenv("B200CV_FILTER2D_PATH")
+        for i in range(2):
+            assert_close(got[i, :, :, 0], oracle.filter2D(img[i, :, :, 0], -1, ker, delta=1.25, borderType=b), atol=1, what="filter2D tma u8 %s b=%d" % (ksz, b))
+        assert_close(gotf, oracle.filter2D(fimg, -1, ker, delta=1.25, borderType=b), atol=5e-4, rtol=1e-5, what="filter2D tma f32 %s b=%d" % (ksz, b))
+
+
 def test_filter2d_generic(cvb, oracle, rng):
     img3 = rand_u8(rng, 61, 77, 3)
     ker = rng.random((4, 6)).astype(np.float32) - 0.3

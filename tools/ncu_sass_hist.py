@@ -1,5 +1,5 @@
-"""per-kernel SASS opcode histogram (thread-level instructions executed) from an .ncu-rep captured with --import-source on:
-python tools/ncu_sass_hist.py report.ncu-rep [out.txt]"""
+"""per-kernel SASS opcode histogram (thread-level instructions executed + stall samples) from an .ncu-rep captured with
+--import-source on:  python tools/ncu_sass_hist.py report.ncu-rep [out.txt] [kernel-name-substring]"""
 import collections
 import csv
 import io
@@ -8,56 +8,44 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
+only = sys.argv[3] if len(sys.argv) > 3 else "b200cv"
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 out = []
-kernel = None
-hist = None
-hdr = None
+seen = set()
+kernel, hist, samp, hdr = None, None, None, None
 
 
 def flush():
     if kernel and hist:
-        tot = sum(hist.values())
-        out.append("== %s   thread-instructions %d" % (kernel[:140], tot))
-        for op, n in hist.most_common(24):
-            out.append("   %-14s %14d  %5.1f%%" % (op, n, 100.0 * n / max(tot, 1)))
+        tot, st = sum(hist.values()), sum(samp.values())
+        out.append("== %s\n   thread-instructions %d   stall samples %d" % (kernel[:150], tot, st))
+        for op, n in hist.most_common(22):
+            out.append("   %-12s %14d  %5.1f%%   samples %5.1f%%" % (op, n, 100.0 * n / max(tot, 1), 100.0 * samp[op] / max(st, 1)))
 
 
-seen = set()
-for line in raw.splitlines():
-    if line.startswith('"Kernel Name"') or line.startswith("Kernel Name"):
+for row in csv.reader(io.StringIO(raw)):
+    if not row:
         continue
-    m = re.match(r'^\s*(\S.*\))\s*\(\d+, \d+, \d+\)x\(\d+, \d+, \d+\)', line)
-    if m and not line.startswith('"'):
+    if row[0] == "Kernel Name":
         flush()
-        kernel = m.group(1)
-        if kernel in seen:
-            kernel = None
-        else:
-            seen.add(kernel)
-        hist = collections.Counter()
-        hdr = None
+        name = row[1] if len(row) > 1 else ""
+        kernel = name if (only in name and name not in seen) else None
+        seen.add(name)
+        hist, samp, hdr = collections.Counter(), collections.Counter(), None
         continue
     if kernel is None:
         continue
-    try:
-        row = next(csv.reader(io.StringIO(line)))
-    except Exception:
+    if row[0] == "Address":
+        hdr = {c: i for i, c in enumerate(row)}
         continue
     if hdr is None:
-        if any("Source" == c for c in row):
-            hdr = {c: i for i, c in enumerate(row)}
         continue
-    ci = hdr.get("Source")
-    ti = hdr.get("# Thread Instructions Executed", hdr.get("Thread Instructions Executed"))
-    if ci is None or ti is None or len(row) <= max(ci, ti):
-        continue
-    sass = row[ci].strip()
-    sass = re.sub(r"^@!?U?P\d+\s+", "", sass)
-    op = sass.split(" ")[0].split(".")[0]
     try:
-        hist[op] += int(row[ti])
-    except ValueError:
+        sass = re.sub(r"^@!?U?P\w+\s+", "", row[hdr["Source"]].strip())
+        op = sass.split(" ")[0].split(".")[0]
+        hist[op] += int(row[hdr["Thread Instructions Executed"]])
+        samp[op] += int(row[hdr["# Samples"]])
+    except (KeyError, ValueError, IndexError):
         pass
 flush()
 txt = "\n".join(out)
