@@ -64,23 +64,36 @@ __global__ void toeplitz_digits_kernel(const int* __restrict__ kq, int w, int h,
     }
 }
 
-// border-extended copy of an 8-bit single-channel image: P(y, x) = src(y - ay, x - ax) under `border`
-__global__ void pad_u8_kernel(Img src, Img dst, int ax, int ay, int border)
+// border-extended copy of an 8-bit single-channel image: P(y, x) = src(y - ay, x - ax) under `border`.
+// 16 output bytes per thread; away from the borders the (generally unaligned) source run is read as 5 aligned words and realigned
+// with funnel shifts.
+__global__ void __launch_bounds__(128) pad_u8_kernel(Img src, Img dst, int ax, int ay, int border, int words_ok)
 {
     const int f = blockIdx.z, y = blockIdx.y;
-    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (x4 >= dst.cols) return;
+    const int x16 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x16 >= dst.cols) return;
     const int sy = border_interpolate(y - ay, src.rows, border);
-    uint32_t w = 0;
+    uint32_t o[4] = {0, 0, 0, 0};
     if (sy >= 0) {
         const uchar* sp = src.row<uchar>(f, sy);
+        const int sx0 = x16 - ax;
+        if (words_ok && sx0 >= 0 && sx0 + 20 <= src.cols) {
+            const int a = sx0 & 3;
+            const uint32_t* wp = (const uint32_t*)(sp + (sx0 - a));
+            uint32_t w[5];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            int sx = border_interpolate(x4 + i - ax, src.cols, border);
-            w |= (uint32_t)(sx >= 0 ? sp[sx] : (uchar)0) << (8 * i);
+            for (int i = 0; i < 5; i++) w[i] = wp[i];
+#pragma unroll
+            for (int i = 0; i < 4; i++) o[i] = __funnelshift_r(w[i], w[i + 1], 8 * a);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                int sx = border_interpolate(sx0 + i, src.cols, border);
+                o[i >> 2] |= (uint32_t)(sx >= 0 ? sp[sx] : (uchar)0) << (8 * (i & 3));
+            }
         }
     }
-    *(uint32_t*)(dst.row<uchar>(f, y) + x4) = w;
+    *(uint4*)(dst.row<uchar>(f, y) + x16) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
@@ -349,7 +362,8 @@ int filter2d_u8_tensor(const Img& s, const Img& d, int dd, const float* k, int k
     B200_CUDA(cudaMemcpyAsync(dkq, kq.data(), kq.size() * sizeof(int), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
     toeplitz_digits_kernel<<<kh, 256, 0, st>>>(dkq, kw, kh, p.kch, (signed char*)bglob);
     count_launch();
-    pad_u8_kernel<<<dim3(div_up((unsigned)pad.cols / 4, 128), (unsigned)pad.rows, (unsigned)s.frames), 128, 0, st>>>(s, pad, ax, ay, border);
+    pad_u8_kernel<<<dim3(div_up((unsigned)pad.cols / 16, 128), (unsigned)pad.rows, (unsigned)s.frames), 128, 0, st>>>(
+        s, pad, ax, ay, border, (((uintptr_t)s.data | s.step | s.fstep) & 3) == 0);
     count_launch();
     CUtensorMap tm;
     int rc = make_tensor_map_3d(&tm, pad.data, 1, pad.cols, pad.rows, pad.frames, pad.step, pad.fstep, 16, p.box_h);

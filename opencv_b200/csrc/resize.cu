@@ -370,87 +370,105 @@ __global__ void __launch_bounds__(256) resize_tile_kernel(Img src, Img dst, Resi
     }
     __syncthreads();
 
-    // ---- horizontal pass: item = 4 consecutive intermediate elements of one staged row ----
-    for (int it = tid; it < nrows * (EW / 4); it += 256) {
-        const int r = it / (EW / 4), e0 = (it - r * (EW / 4)) * 4;
-        const unsigned char* srow = s_src + (size_t)r * pitch;
-        MT out[4];
+    // Both passes give every thread a FIXED group of 4 consecutive intermediate elements (its tap offsets and coefficients stay in
+    // registers) and walk the rows: no per-element index arithmetic in the loops.
+    constexpr int NG = EW / 4;                       // column groups
+    constexpr int RS = 256 / NG;                     // row phases that fit the CTA (C3: 2 -> 192 active threads)
+    const int cg = tid % NG, rp = tid / NG;
+    const int e0 = cg * 4;
+    const int row_elems = p.dw * CN;
+    const int E0 = x0 * CN + e0;                     // element index in the destination row
+    const bool active = rp < RS && E0 < row_elems;
+
+    // ---- horizontal pass ----
+    if (active) {
+        int off[4][TAPS];
+        MT cf[4][TAPS];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int e = e0 + i, xl = e / CN, c = e - xl * CN;
-            const RTab<TAPS>& t = s_tab[xl];
-            if constexpr (sizeof(T) == 1) {
-                int acc = 0;
+            const RTab<TAPS> t = s_tab[xl];
 #pragma unroll
-                for (int j = 0; j < TAPS; j++) acc += srow[t.off[j] + c] * t.ic[j];
-                out[i] = acc;
-            } else {
-                const float* fr = (const float*)srow;
-                float acc = __fmul_rn(fr[(t.off[0] >> 2) + c], t.fc[0]);
-#pragma unroll
-                for (int j = 1; j < TAPS; j++) acc = __fadd_rn(acc, __fmul_rn(fr[(t.off[j] >> 2) + c], t.fc[j]));
-                out[i] = acc;
+            for (int j = 0; j < TAPS; j++) {
+                off[i][j] = t.off[j] + c * (int)sizeof(T);
+                if constexpr (sizeof(T) == 1) cf[i][j] = t.ic[j]; else cf[i][j] = t.fc[j];
             }
         }
-        *(uint4*)(s_mid + (size_t)r * EW + e0) = *(const uint4*)out;
+        for (int r = rp; r < nrows; r += RS) {
+            const unsigned char* srow = s_src + (size_t)r * pitch;
+            MT out[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if constexpr (sizeof(T) == 1) {
+                    int acc = 0;
+#pragma unroll
+                    for (int j = 0; j < TAPS; j++) acc += srow[off[i][j]] * cf[i][j];
+                    out[i] = acc;
+                } else {
+                    float acc = __fmul_rn(*(const float*)(srow + off[i][0]), cf[i][0]);
+#pragma unroll
+                    for (int j = 1; j < TAPS; j++) acc = __fadd_rn(acc, __fmul_rn(*(const float*)(srow + off[i][j]), cf[i][j]));
+                    out[i] = acc;
+                }
+            }
+            *(uint4*)(s_mid + (size_t)r * EW + e0) = *(const uint4*)out;
+        }
     }
     __syncthreads();
 
-    // ---- vertical pass: item = 4 consecutive elements of one destination row ----
-    const int row_elems = p.dw * CN;
-    const int vec_limit = sizeof(T) == 1 ? (row_elems / 8) * 8 : (row_elems / 4) * 4;      // reference SIMD body / scalar tail split (cubic)
-    const bool dvec = (((uintptr_t)dst.data | dst.step | dst.fstep) & (4 * sizeof(T) - 1)) == 0;
-    for (int it = tid; it < RT_H * (EW / 4); it += 256) {
-        const int yy = it / (EW / 4), e0 = (it - yy * (EW / 4)) * 4;
-        const int y = y0 + yy;
-        const int E0 = x0 * CN + e0;                  // element index in the destination row
-        if (y > y1 || E0 >= row_elems) continue;
-        const ResTab ty = yt[y];
-        MT m[TAPS][4];
+    // ---- vertical pass ----
+    if (active) {
+        const int vec_limit = sizeof(T) == 1 ? (row_elems / 8) * 8 : (row_elems / 4) * 4;      // reference SIMD body / scalar tail split (cubic)
+        const bool dvec = (((uintptr_t)dst.data | dst.step | dst.fstep) & (4 * sizeof(T) - 1)) == 0;
+        const bool full4 = dvec && E0 + 4 <= row_elems;
+        for (int y = y0 + rp; y <= y1; y += RS) {
+            const ResTab ty = yt[y];                  // one 32-byte broadcast load per row
+            MT m[TAPS][4];
 #pragma unroll
-        for (int k = 0; k < TAPS; k++) {
-            const int rr = clip_i(ty.s + k - (CUBIC ? 1 : 0), 0, p.sh) - sy_lo;       // rows are clipped when fetched, the taps keep fy (:2211)
-            *(uint4*)m[k] = *(const uint4*)(s_mid + (size_t)rr * EW + e0);
-        }
-        T out[4];
+            for (int k = 0; k < TAPS; k++) {
+                const int rr = clip_i(ty.s + k - (CUBIC ? 1 : 0), 0, p.sh) - sy_lo;       // rows are clipped when fetched, the taps keep fy (:2211)
+                *(uint4*)m[k] = *(const uint4*)(s_mid + (size_t)rr * EW + e0);
+            }
+            T out[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if constexpr (sizeof(T) == 1) {
-                if constexpr (!CUBIC) {
-                    out[i] = (uchar)((((ty.ic[0] * (m[0][i] >> 4)) >> 16) + ((ty.ic[1] * (m[1][i] >> 4)) >> 16) + 2) >> 2);
-                } else if (E0 + i < vec_limit) {
-                    const float sc = 1.f / (2048.f * 2048.f);
-                    float v = __fmul_rn((float)m[3][i], __fmul_rn((float)ty.ic[3], sc));
-                    v = __fadd_rn(__fmul_rn((float)m[2][i], __fmul_rn((float)ty.ic[2], sc)), v);
-                    v = __fadd_rn(__fmul_rn((float)m[1][i], __fmul_rn((float)ty.ic[1], sc)), v);
-                    v = __fadd_rn(__fmul_rn((float)m[0][i], __fmul_rn((float)ty.ic[0], sc)), v);
-                    out[i] = sat_u8(__float2int_rn(v));
+            for (int i = 0; i < 4; i++) {
+                if constexpr (sizeof(T) == 1) {
+                    if constexpr (!CUBIC) {
+                        out[i] = (uchar)((((ty.ic[0] * (m[0][i] >> 4)) >> 16) + ((ty.ic[1] * (m[1][i] >> 4)) >> 16) + 2) >> 2);
+                    } else if (E0 + i < vec_limit) {
+                        const float sc = 1.f / (2048.f * 2048.f);
+                        float v = __fmul_rn((float)m[3][i], __fmul_rn((float)ty.ic[3], sc));
+                        v = __fadd_rn(__fmul_rn((float)m[2][i], __fmul_rn((float)ty.ic[2], sc)), v);
+                        v = __fadd_rn(__fmul_rn((float)m[1][i], __fmul_rn((float)ty.ic[1], sc)), v);
+                        v = __fadd_rn(__fmul_rn((float)m[0][i], __fmul_rn((float)ty.ic[0], sc)), v);
+                        out[i] = sat_u8(__float2int_rn(v));
+                    } else {
+                        out[i] = sat_u8((m[0][i] * ty.ic[0] + m[1][i] * ty.ic[1] + m[2][i] * ty.ic[2] + m[3][i] * ty.ic[3] + (1 << 21)) >> 22);
+                    }
                 } else {
-                    out[i] = sat_u8((m[0][i] * ty.ic[0] + m[1][i] * ty.ic[1] + m[2][i] * ty.ic[2] + m[3][i] * ty.ic[3] + (1 << 21)) >> 22);
-                }
-            } else {
-                if constexpr (!CUBIC) {
-                    out[i] = __fadd_rn(__fmul_rn(m[0][i], ty.fc[0]), __fmul_rn(m[1][i], ty.fc[1]));
-                } else if (E0 + i < vec_limit) {
-                    float o = __fmul_rn(m[3][i], ty.fc[3]);
-                    o = __fadd_rn(__fmul_rn(m[2][i], ty.fc[2]), o);
-                    o = __fadd_rn(__fmul_rn(m[1][i], ty.fc[1]), o);
-                    out[i] = __fadd_rn(__fmul_rn(m[0][i], ty.fc[0]), o);
-                } else {
-                    float o = __fmul_rn(m[0][i], ty.fc[0]);
-                    o = __fadd_rn(o, __fmul_rn(m[1][i], ty.fc[1]));
-                    o = __fadd_rn(o, __fmul_rn(m[2][i], ty.fc[2]));
-                    out[i] = __fadd_rn(o, __fmul_rn(m[3][i], ty.fc[3]));
+                    if constexpr (!CUBIC) {
+                        out[i] = __fadd_rn(__fmul_rn(m[0][i], ty.fc[0]), __fmul_rn(m[1][i], ty.fc[1]));
+                    } else if (E0 + i < vec_limit) {
+                        float o = __fmul_rn(m[3][i], ty.fc[3]);
+                        o = __fadd_rn(__fmul_rn(m[2][i], ty.fc[2]), o);
+                        o = __fadd_rn(__fmul_rn(m[1][i], ty.fc[1]), o);
+                        out[i] = __fadd_rn(__fmul_rn(m[0][i], ty.fc[0]), o);
+                    } else {
+                        float o = __fmul_rn(m[0][i], ty.fc[0]);
+                        o = __fadd_rn(o, __fmul_rn(m[1][i], ty.fc[1]));
+                        o = __fadd_rn(o, __fmul_rn(m[2][i], ty.fc[2]));
+                        out[i] = __fadd_rn(o, __fmul_rn(m[3][i], ty.fc[3]));
+                    }
                 }
             }
-        }
-        T* dp = dst.row<T>(f, y) + E0;
-        if (dvec && E0 + 4 <= row_elems) {
-            if constexpr (sizeof(T) == 1) *(uint32_t*)dp = *(const uint32_t*)out;
-            else *(float4*)dp = *(const float4*)out;
-        } else {
+            T* dp = dst.row<T>(f, y) + E0;
+            if (full4) {
+                if constexpr (sizeof(T) == 1) *(uint32_t*)dp = *(const uint32_t*)out;
+                else *(float4*)dp = *(const float4*)out;
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) if (E0 + i < row_elems) dp[i] = out[i];
+                for (int i = 0; i < 4; i++) if (E0 + i < row_elems) dp[i] = out[i];
+            }
         }
     }
 }

@@ -31,7 +31,7 @@ struct SF32Params {
 };
 
 template <int KB, typename ST, typename DT>
-__global__ void __launch_bounds__(256, 2) sep_f32_tma_kernel(const CUtensorMap* __restrict__ tmap, Img dst, const __grid_constant__ SF32Params p)
+__global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(const CUtensorMap* __restrict__ tmap, Img dst, const __grid_constant__ SF32Params p)
 {
     constexpr int RB = KB / 2;
     constexpr int RA = sizeof(ST) == 1 ? 16 : ((RB + 3) / 4) * 4;   // left apron staged: TMA needs the box to start on a 16-byte boundary
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256, 2) sep_f32_tma_kernel(const CUtensorMap* 
 
     // ---- column pass: item = CW columns x R rows; the R + KB - 1 mid rows it needs are held in registers ----
     {
-        constexpr int CW = KB <= 15 ? 4 : 2, R = 8;        // window: (R + KB - 1) x CW registers (<= 88)
+        constexpr int CW = KB <= 15 ? 4 : 2, R = KB == 11 ? 4 : 8;   // window: (R + KB - 1) x CW registers, sized for 3 (KB <= 11) or 2 CTAs per SM
         constexpr int IPR = SF_TW / CW;                   // items per row group
         const bool dvec = (((uintptr_t)dst.data | dst.step | dst.fstep) & (CW * sizeof(DT) - 1)) == 0;
         const bool gvec = p.has_dog && (((uintptr_t)p.dog.data | p.dog.step | p.dog.fstep) & (CW * 4 - 1)) == 0;

@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(Img src, Img dst, const 
 {
     extern __shared__ __align__(16) unsigned char s_src[];
     __shared__ int s_box[4];
+    __shared__ int s_ad[WT_W], s_bd[WT_W], s_X0[WT_H], s_Y0[WT_H];     // affine: the reference's adelta/bdelta and per-row X0/Y0 tables
     constexpr int ES = CN * (int)sizeof(T);                  // bytes per pixel
     constexpr int K0 = INTERP == W_CUB ? -1 : 0, K1 = INTERP == W_NN ? 0 : INTERP == W_LIN ? 1 : 2;
     const int f = blockIdx.z, x0 = blockIdx.x * WT_W, y0 = blockIdx.y * WT_H;
@@ -218,6 +219,19 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(Img src, Img dst, const 
             mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
         }
         if (tid == 0) { s_box[0] = (mnx + K0) & ~15; s_box[1] = mny + K0; s_box[2] = mxx + K1; s_box[3] = mxy + K1; }
+    } else if (!p.persp) {
+        // fp64 once per tile column / row instead of once per pixel (hal::warpAffine builds the same tables on the host, imgwarp.cpp:2673-2700)
+        const int t = tid - 32;
+        if (t < WT_W) {
+            const double x = (double)(x0 + t);
+            s_ad[t] = __double2int_rn(__dmul_rn(__dmul_rn(p.M[0], x), 1024.0));
+            s_bd[t] = __double2int_rn(__dmul_rn(__dmul_rn(p.M[3], x), 1024.0));
+        } else if (t < WT_W + WT_H) {
+            const double y = (double)(y0 + t - WT_W);
+            const int rd = INTERP == W_NN ? 512 : 16;
+            s_X0[t - WT_W] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(p.M[1], y), p.M[2]), 1024.0)) + rd;
+            s_Y0[t - WT_W] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(p.M[4], y), p.M[5]), 1024.0)) + rd;
+        }
     }
     __syncthreads();
     const int bx0 = s_box[0], by0 = s_box[1];
@@ -228,31 +242,36 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(Img src, Img dst, const 
     const int sw = p.sw, sh = p.sh, border = p.border;
 
     if (staged) {
+        // one warp per staged row (row-uniform work hoisted), lanes over its 16-byte vectors
         const bool aligned = (((uintptr_t)src.data | src.step | src.fstep) & 15) == 0;
-        const int total = nvec * bh;
-        for (int v = tid; v < total; v += 256) {
-            const int r = v / nvec, j = v - r * nvec;
+        const int gb0 = bx0 * ES;                                               // byte offset of the staged row start inside a source row
+        const int row_bytes = sw * ES;
+        for (int r = tid >> 5; r < bh; r += 8) {
             int sy = by0 + r;
             if ((unsigned)sy >= (unsigned)sh) sy = border == B200CV_BORDER_REPLICATE ? clipi(sy, 0, sh) : border_interpolate(sy, sh, border);
-            const long long gb = (long long)bx0 * ES + (long long)j * 16;      // first byte of this vector within the source row
-            uint4 val;
-            if (sy >= 0 && aligned && gb >= 0 && gb + 16 <= (long long)sw * ES) {
-                val = *(const uint4*)((const unsigned char*)src.row<T>(f, sy) + gb);
-            } else {
-                T e[16 / sizeof(T)];
+            const unsigned char* srow = sy >= 0 ? (const unsigned char*)src.row<T>(f, sy) : nullptr;
+            unsigned char* drow = s_src + r * pitch;
+            for (int j = tid & 31; j < nvec; j += 32) {
+                const int gb = gb0 + j * 16;                                    // first byte of this vector within the source row
+                uint4 val;
+                if (srow && aligned && gb >= 0 && gb + 16 <= row_bytes) {
+                    val = *(const uint4*)(srow + gb);
+                } else {
+                    T e[16 / sizeof(T)];
 #pragma unroll
-                for (int i = 0; i < (int)(16 / sizeof(T)); i++) {
-                    const long long ge = gb / (long long)sizeof(T) + i;         // element index in the row (may be negative)
-                    long long px = ge >= 0 ? ge / CN : -((-ge + CN - 1) / CN);
-                    const int c = (int)(ge - px * CN);
-                    int sx = (int)px;
-                    if ((unsigned)sx >= (unsigned)sw) sx = border == B200CV_BORDER_REPLICATE ? clipi(sx, 0, sw) : border_interpolate(sx, sw, border);
-                    if (sy >= 0 && sx >= 0) e[i] = src.row<T>(f, sy)[sx * CN + c];
-                    else { if constexpr (sizeof(T) == 1) e[i] = (T)p.cval_i[c]; else e[i] = p.cval_f[c]; }
+                    for (int i = 0; i < (int)(16 / sizeof(T)); i++) {
+                        const int ge = gb / (int)sizeof(T) + i;                 // element index in the row (may be negative; gb is a multiple of 16)
+                        const int px = ge >= 0 ? ge / CN : -((-ge + CN - 1) / CN);
+                        const int c = ge - px * CN;
+                        int sx = px;
+                        if ((unsigned)sx >= (unsigned)sw) sx = border == B200CV_BORDER_REPLICATE ? clipi(sx, 0, sw) : border_interpolate(sx, sw, border);
+                        if (srow && sx >= 0) e[i] = ((const T*)srow)[sx * CN + c];
+                        else { if constexpr (sizeof(T) == 1) e[i] = (T)p.cval_i[c]; else e[i] = p.cval_f[c]; }
+                    }
+                    val = *(const uint4*)e;
                 }
-                val = *(const uint4*)e;
+                *(uint4*)(drow + j * 16) = val;
             }
-            *(uint4*)(s_src + (size_t)r * pitch + (size_t)j * 16) = val;
         }
     }
     __syncthreads();
@@ -264,14 +283,19 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(Img src, Img dst, const 
         const int y = y0 + yy;
         if (y >= p.dh) break;
         int sx, sy, a;
-        warp_coords<INTERP>(p, x, y, sx, sy, a);
+        if (p.persp) warp_coords<INTERP>(p, x, y, sx, sy, a);
+        else {
+            const int XX = s_X0[yy] + s_ad[tid & (WT_W - 1)], YY = s_Y0[yy] + s_bd[tid & (WT_W - 1)];
+            if (INTERP == W_NN) { sx = sat_s16(XX >> 10); sy = sat_s16(YY >> 10); a = 0; }
+            else { sx = sat_s16(XX >> 10); sy = sat_s16(YY >> 10); a = ((YY >> 5) & 31) * 32 + ((XX >> 5) & 31); }
+        }
         T* d = dst.row<T>(f, y) + (size_t)x * CN;
         const int lx = sx + K0 - bx0, ly = sy + K0 - by0;            // first tap, staged coordinates
         if (!staged || lx < 0 || ly < 0 || lx + (K1 - K0) >= bw || ly + (K1 - K0) >= bh) {
             sample_direct<T, CN, INTERP>(src, f, p, sx, sy, a, d);
             continue;
         }
-        const T* s = (const T*)(s_src + (size_t)ly * pitch) + lx * CN;
+        const T* s = (const T*)(s_src + ly * pitch) + lx * CN;
         const int rp = pitch / (int)sizeof(T);                       // row pitch in elements
         if constexpr (INTERP == W_NN) {
 #pragma unroll
