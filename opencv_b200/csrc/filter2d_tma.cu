@@ -49,7 +49,7 @@ template <> __device__ __forceinline__ void ft_store8<float>(float* dp, const fl
 }
 
 template <int KB, typename ST, typename DT>
-__global__ void __launch_bounds__(256, 2) filter2d_tma_kernel(const CUtensorMap* __restrict__ tmap, Img dst, const __grid_constant__ FTParams p)
+__global__ void __launch_bounds__(256, 2) filter2d_tma_kernel(const __grid_constant__ CUtensorMap tmap, Img dst, const __grid_constant__ FTParams p)
 {
     constexpr int RB = KB / 2;
     constexpr int RA = sizeof(ST) == 1 ? 16 : ((RB + 3) / 4) * 4;   // left apron staged: the TMA box must start on a 16-byte boundary
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256, 2) filter2d_tma_kernel(const CUtensorMap*
         mbar_init(&s_bar, 1);
         fence_barrier_init();
         mbar_arrive_expect_tx(&s_bar, (uint32_t)(FT_IW * IH * sizeof(ST)));
-        tma_load_3d(s_in, tmap, x0 - RA, y0 - RB, f, &s_bar);
+        tma_load_3d(s_in, &tmap, x0 - RA, y0 - RB, f, &s_bar);
     }
     __syncthreads();
     mbar_wait(&s_bar, 0);
@@ -146,13 +146,9 @@ static int launch_ft(const CUtensorMap& tm, const Img& d, const FTParams& p, int
     auto kern = filter2d_tma_kernel<KB, ST, DT>;
     static bool attr = false;
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    CUtensorMap* dtm = nullptr;
-    int rc = upload_tensor_map(tm, &dtm, st);
-    if (rc) return rc;
     dim3 grid(div_up((unsigned)p.W, FT_TW), div_up((unsigned)p.H, FT_TH), (unsigned)frames);
-    kern<<<grid, 256, smem, st>>>(dtm, d, p);
+    kern<<<grid, 256, smem, st>>>(tm, d, p);
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(dtm, st);
     count_launch();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
     return B200CV_OK;

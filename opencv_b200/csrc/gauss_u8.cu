@@ -36,7 +36,7 @@ struct GU8Params {
 __host__ __device__ constexpr bool gu_nz(int KB, int o, int g) { return 4 * g - o < KB; }
 
 template <int KB>
-__global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const CUtensorMap* __restrict__ tmap, Img dst, const __grid_constant__ GU8Params p)
+__global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const __grid_constant__ CUtensorMap tmap, Img dst, const __grid_constant__ GU8Params p)
 {
     constexpr int RB = KB / 2;
     constexpr int RA = 16;                           // left apron staged: TMA needs the box to start on a 16-byte boundary
@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const CUtensorMap
         mbar_init(&s_bar, 1);
         fence_barrier_init();
         mbar_arrive_expect_tx(&s_bar, (uint32_t)(GU_IW * IH));
-        tma_load_3d(s_in, tmap, x0 - RA, y0 - RB, f, &s_bar);
+        tma_load_3d(s_in, &tmap, x0 - RA, y0 - RB, f, &s_bar);
     }
     __syncthreads();
     mbar_wait(&s_bar, 0);
@@ -205,13 +205,9 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const CUtensorMap
 template <int KB>
 static int launch_gu8(const CUtensorMap& tm, const Img& d, const GU8Params& p, int frames, cudaStream_t st)
 {
-    CUtensorMap* dtm = nullptr;
-    int rc = upload_tensor_map(tm, &dtm, st);
-    if (rc) return rc;
     dim3 grid(div_up((unsigned)p.W, GU_TW), div_up((unsigned)p.H, (unsigned)p.TH), (unsigned)frames);
-    gauss_u8_dp4a_kernel<KB><<<grid, 256, 0, st>>>(dtm, d, p);
+    gauss_u8_dp4a_kernel<KB><<<grid, 256, 0, st>>>(tm, d, p);
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(dtm, st);
     count_launch();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
     return B200CV_OK;

@@ -48,8 +48,11 @@ __global__ void toeplitz_kernel(Img templ, int w, int h, unsigned char* out)
 }
 
 // filter2D operand: [kernel row v][k-chunk c (2*kch)][column j (192) = digit d * 64 + jj][16 bytes]: byte b = digit_d(Kq(v, 16c + b - jj))
-__global__ void toeplitz_digits_kernel(const int* __restrict__ kq, int w, int h, int kch, signed char* out)
+struct KqParams { int q[33 * 33]; };     // quantised taps travel as a kernel parameter: no H2D copy that would queue behind bulk transfers
+
+__global__ void toeplitz_digits_kernel(const __grid_constant__ KqParams kp, int w, int h, int kch, signed char* out)
 {
+    const int* kq = kp.q;
     const int v = blockIdx.x;
     const int slab = 2 * kch * 192 * 16;
     for (int idx = threadIdx.x; idx < slab; idx += blockDim.x) {
@@ -136,7 +139,7 @@ struct TCParams {
 };
 
 template <int NB, int EPI>     // NB = digit planes of the B operand (MMA N = 64 NB)
-__global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const CUtensorMap* __restrict__ tmap, const unsigned char* __restrict__ bglob, Img res, TCParams p)
+__global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ bglob, Img res, TCParams p)
 {
     constexpr int NN = TC_N * NB;                                      // MMA N
     constexpr int TCOLS = TC_MT * NN <= 128 ? 128 : TC_MT * NN <= 256 ? 256 : 512;   // TMEM columns (power of two)
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const CUtensorMap* __r
         mbar_arrive_expect_tx(&a_full, (uint32_t)p.ra_alloc * 16u * nchunk);
         for (int c = 0; c < nchunk; c++)
             for (int b = 0; b < p.nbox; b++)
-                tma_load_3d(sA + (size_t)c * lbo_a + (size_t)b * p.box_h * 16, tmap, x0 + 16 * c, y0 + b * p.box_h, f, &a_full);
+                tma_load_3d(sA + (size_t)c * lbo_a + (size_t)b * p.box_h * 16, &tmap, x0 + 16 * c, y0 + b * p.box_h, f, &a_full);
         for (int v = 0; v < p.h; v++) {
             const int s = v % TC_NS;
             mbar_wait(&empty[s], ((v / TC_NS) & 1) ^ 1);
@@ -291,13 +294,10 @@ int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, c
     count_launch();
     CUtensorMap tm;
     int rc = make_tensor_map_3d(&tm, im.data, 1, im.cols, im.rows, im.frames, im.step, im.fstep, 16, p.box_h);
-    CUtensorMap* dtm = nullptr;
-    if (!rc) rc = upload_tensor_map(tm, &dtm, st);
     if (rc) { cudaFreeAsync(bglob, st); return rc; }
     dim3 grid(div_up((unsigned)ow, TC_N), div_up((unsigned)oh, 128 * TC_MT), (unsigned)im.frames);
-    ccorr_u8_tc_kernel<1, EPI_CCORR><<<grid, 128, smem, st>>>(dtm, bglob, rs, p);
+    ccorr_u8_tc_kernel<1, EPI_CCORR><<<grid, 128, smem, st>>>(tm, bglob, rs, p);
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(dtm, st);
     cudaFreeAsync(bglob, st);
     count_launch();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
@@ -305,13 +305,13 @@ int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, c
 }
 
 template <int EPI>
-static int launch_filter_tc(const CUtensorMap* dtm, const unsigned char* bglob, const Img& d, const TCParams& p, size_t smem, cudaStream_t st)
+static int launch_filter_tc(const CUtensorMap& tm, const unsigned char* bglob, const Img& d, const TCParams& p, size_t smem, cudaStream_t st)
 {
     auto kern = ccorr_u8_tc_kernel<3, EPI>;
     static bool attr = false;
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
     dim3 grid(div_up((unsigned)p.ow, TC_N), div_up((unsigned)p.oh, 128 * TC_MT), (unsigned)d.frames);
-    kern<<<grid, 128, smem, st>>>(dtm, bglob, d, p);
+    kern<<<grid, 128, smem, st>>>(tm, bglob, d, p);
     cudaError_t e = cudaGetLastError();
     count_launch();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
@@ -334,8 +334,9 @@ int filter2d_u8_tensor(const Img& s, const Img& d, int dd, const float* k, int k
     int e;
     std::frexp((double)mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
     const int sh = 22 - e;                            // |k| * 2^sh < 2^22
-    std::vector<int> kq((size_t)kw * kh);
-    for (int i = 0; i < kw * kh; i++) kq[i] = (int)std::lrint(std::ldexp((double)k[i], sh));
+    if (kw * kh > 33 * 33) return B200CV_NOT_IMPLEMENTED;
+    static thread_local KqParams kq;
+    for (int i = 0; i < kw * kh; i++) kq.q[i] = (int)std::lrint(std::ldexp((double)k[i], sh));
 
     TCParams p;
     p.h = kh; p.ow = s.cols; p.oh = s.rows; p.kch = (kw + TC_N - 1 + 31) / 32; p.scale = (float)std::ldexp(1.0, -sh); p.delta = delta;
@@ -354,28 +355,22 @@ int filter2d_u8_tensor(const Img& s, const Img& d, int dd, const float* k, int k
     pad.rows = s.rows + kh - 1;
     pad.step = (size_t)pad.cols;
     pad.fstep = pad.step * pad.rows;
-    unsigned char* pbuf = nullptr; unsigned char* bglob = nullptr; int* dkq = nullptr;
+    unsigned char* pbuf = nullptr; unsigned char* bglob = nullptr;
     B200_CUDA(cudaMallocAsync(&pbuf, pad.fstep * (size_t)s.frames, st));
     B200_CUDA(cudaMallocAsync(&bglob, (size_t)kh * bbytes, st));
-    B200_CUDA(cudaMallocAsync(&dkq, kq.size() * sizeof(int), st));
     pad.data = pbuf;
-    B200_CUDA(cudaMemcpyAsync(dkq, kq.data(), kq.size() * sizeof(int), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
-    toeplitz_digits_kernel<<<kh, 256, 0, st>>>(dkq, kw, kh, p.kch, (signed char*)bglob);
+    toeplitz_digits_kernel<<<kh, 256, 0, st>>>(kq, kw, kh, p.kch, (signed char*)bglob);
     count_launch();
     pad_u8_kernel<<<dim3(div_up((unsigned)pad.cols / 16, 128), (unsigned)pad.rows, (unsigned)s.frames), 128, 0, st>>>(
         s, pad, ax, ay, border, (((uintptr_t)s.data | s.step | s.fstep) & 3) == 0);
     count_launch();
     CUtensorMap tm;
     int rc = make_tensor_map_3d(&tm, pad.data, 1, pad.cols, pad.rows, pad.frames, pad.step, pad.fstep, 16, p.box_h);
-    CUtensorMap* dtm = nullptr;
-    if (!rc) rc = upload_tensor_map(tm, &dtm, st);
     if (!rc) {
-        rc = dd == B200CV_8U ? launch_filter_tc<EPI_U8>(dtm, bglob, d, p, smem, st)
-           : dd == B200CV_16S ? launch_filter_tc<EPI_S16>(dtm, bglob, d, p, smem, st)
-                              : launch_filter_tc<EPI_F32>(dtm, bglob, d, p, smem, st);
+        rc = dd == B200CV_8U ? launch_filter_tc<EPI_U8>(tm, bglob, d, p, smem, st)
+           : dd == B200CV_16S ? launch_filter_tc<EPI_S16>(tm, bglob, d, p, smem, st)
+                              : launch_filter_tc<EPI_F32>(tm, bglob, d, p, smem, st);
     }
-    if (dtm) cudaFreeAsync(dtm, st);
-    cudaFreeAsync(dkq, st);
     cudaFreeAsync(bglob, st);
     cudaFreeAsync(pbuf, st);
     return rc;

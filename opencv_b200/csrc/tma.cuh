@@ -13,9 +13,10 @@ namespace b200cv {
 // box dims <= 256.  Out-of-bounds box elements are filled with ZEROS.
 int make_tensor_map_3d(CUtensorMap* map, const void* base, int elem_bytes, int cols, int rows, int frames, size_t step, size_t fstep,
                        int box_w, int box_h);
-// The descriptor is handed to kernels through GLOBAL memory (stream-ordered 128-byte allocation + H2D copy): on this driver a
-// __grid_constant__ CUtensorMap parameter makes UTMALDG fault with "illegal instruction" (tools/tma_test.cu reproduces it), a
-// descriptor in global memory works.  The caller frees it with cudaFreeAsync on the same stream after the launch.
+// Kernels take the descriptor as a `const __grid_constant__ CUtensorMap` parameter (no allocation, and above all no small H2D copy
+// per launch: on the host path such a copy queues behind the bulk frame uploads on the copy engine and stalls the kernel that
+// needs it -- measured as a 2-4x loss of end-to-end throughput).  upload_tensor_map (descriptor in global memory) is kept for
+// tools/tma_test.cu.
 int upload_tensor_map(const CUtensorMap& tm, CUtensorMap** dptr, cudaStream_t st);
 static inline bool tma_compatible(const Img& m) { return (((uintptr_t)m.data | m.step | m.fstep) & 15) == 0; }
 

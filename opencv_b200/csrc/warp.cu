@@ -189,6 +189,24 @@ __global__ void __launch_bounds__(256) warp_kernel(Img src, Img dst, const __gri
     sample_direct<T, CN, INTERP>(src, f, p, sx, sy, a, dst.row<T>(f, y) + (size_t)x * CN);
 }
 
+
+// ---- 8-bit sampling from the staged footprint with word loads -----------------------------------------------------------------
+// A tap row is TAPS*CN consecutive bytes at an arbitrary byte address: read the aligned words that cover it, realign with funnel
+// shifts, gather the TAPS bytes of one channel into a word with PRMT (all selectors are compile-time) and let IDP2A multiply them by
+// the 16-bit table weights: dp2a.lo(a = two s16 weights, b = bytes 0,1).  Exact 32-bit integer sums, as remapBilinear /
+// remapBicubic compute them (imgwarp.cpp:675-904, :907-1010).
+__device__ __forceinline__ int dp2a_lo_su(int a, unsigned b, int c)
+{
+    int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+// (tap j0, tap j0+1) of channel c as bytes 0,1 of a word: bytes c + j0*CN and c + (j0+1)*CN of the 16-byte string in w[0..3].
+// One PRMT: its two source words are the ones holding the two bytes (positions are compile-time after unrolling).
+template <int CN> __device__ __forceinline__ unsigned tap_pair(const unsigned* w, int c, int j0)
+{
+    const int p0 = c + j0 * CN, p1 = p0 + CN;
+    return __byte_perm(w[p0 >> 2], w[p1 >> 2], (unsigned)((p0 & 3) | ((4 + (p1 & 3)) << 4)));
+}
+
 // ---- tiled kernel: the source footprint of a 64x16 destination tile is staged in shared memory ---------------------------
 // The footprint is the bounding box of the tile's four corner coordinates (exact for the affine fixed-point map, which is
 // monotone in x and in y; for a projective map every pixel re-checks containment and falls back to the direct gather).
@@ -302,10 +320,20 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(Img src, Img dst, const 
             for (int c = 0; c < CN; c++) d[c] = s[c];
         } else if constexpr (INTERP == W_LIN) {
             if constexpr (sizeof(T) == 1) {
-                const short4 w = *(const short4*)(g_bilin_i + a * 4);
+                const int2 w = *(const int2*)(g_bilin_i + a * 4);              // (w0, w1), (w2, w3) as s16 pairs
+                const unsigned A = (unsigned)(ly * pitch + lx * CN), sh8 = 8 * (A & 3);
+                constexpr int NW = (2 * CN + 3) / 4;                           // words that hold one realigned tap row
+                unsigned r0[4], r1[4];
+                const unsigned* q0 = (const unsigned*)(s_src + (A & ~3u));
+                const unsigned* q1 = (const unsigned*)(s_src + (A & ~3u) + pitch);
 #pragma unroll
-                for (int c = 0; c < CN; c++)
-                    d[c] = sat_u8((s[c] * w.x + s[CN + c] * w.y + s[rp + c] * w.z + s[rp + CN + c] * w.w + (1 << 14)) >> 15);
+                for (int i = 0; i < NW; i++) { r0[i] = __funnelshift_r(q0[i], q0[i + 1], sh8); r1[i] = __funnelshift_r(q1[i], q1[i + 1], sh8); }
+#pragma unroll
+                for (int c = 0; c < CN; c++) {
+                    int sum = dp2a_lo_su(w.x, tap_pair<CN>(r0, c, 0), 1 << 14);
+                    sum = dp2a_lo_su(w.y, tap_pair<CN>(r1, c, 0), sum);
+                    d[c] = sat_u8(sum >> 15);
+                }
             } else {
                 const float4 w = *(const float4*)(g_bilin_f + a * 4);
 #pragma unroll
@@ -315,18 +343,27 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(Img src, Img dst, const 
             }
         } else {
             if constexpr (sizeof(T) == 1) {
-                short w[16];
+                int w[8];                                                        // 16 s16 weights: row i = (w[2i], w[2i+1])
                 *(uint4*)w = *(const uint4*)(g_bicub_i + a * 16);
-                *(uint4*)(w + 8) = *(const uint4*)(g_bicub_i + a * 16 + 8);
+                *(uint4*)(w + 4) = *(const uint4*)(g_bicub_i + a * 16 + 8);
+                const unsigned A = (unsigned)(ly * pitch + lx * CN), sh8 = 8 * (A & 3);
+                constexpr int NW = (4 * CN + 3) / 4;
+                int sum[CN];
 #pragma unroll
-                for (int c = 0; c < CN; c++) {
-                    int sum = 0;
+                for (int c = 0; c < CN; c++) sum[c] = 1 << 14;
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
+                for (int i = 0; i < 4; i++) {
+                    const unsigned* q = (const unsigned*)(s_src + (A & ~3u) + i * pitch);
+                    unsigned r[4];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) sum += s[i * rp + j * CN + c] * w[i * 4 + j];
-                    d[c] = sat_u8((sum + (1 << 14)) >> 15);
+                    for (int k = 0; k < NW; k++) r[k] = __funnelshift_r(q[k], q[k + 1], sh8);
+#pragma unroll
+                    for (int c = 0; c < CN; c++) {
+                        sum[c] = dp2a_lo_su(w[2 * i + 1], tap_pair<CN>(r, c, 2), dp2a_lo_su(w[2 * i], tap_pair<CN>(r, c, 0), sum[c]));
+                    }
                 }
+#pragma unroll
+                for (int c = 0; c < CN; c++) d[c] = sat_u8(sum[c] >> 15);
             } else {
                 float w[16];
 #pragma unroll

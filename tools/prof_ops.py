@@ -21,6 +21,8 @@ half = torch.empty((2, 2160, 3840, 3), dtype=torch.uint8, device=dev)
 k5 = torch.empty((2, 2880, 5120, 3), dtype=torch.uint8, device=dev)
 M = np.array([[0.8911, 0.1094, 182.0], [-0.1094, 0.8911, 655.0]])
 templ = u8[0, 700:764, 1000:1064, 0].contiguous()
+g3 = np.array([0.2, 0.55, 0.25], np.float32)
+g5 = np.array([0.1, 0.2, 0.35, 0.25, 0.1], np.float32)
 g11 = cvb.getGaussianKernel(11, 0).astype(np.float32).ravel()
 g31 = cvb.getGaussianKernel(31, 0).astype(np.float32).ravel()
 ops = {
@@ -43,6 +45,8 @@ ops = {
     "sep_u8_k31": lambda: cvb.sepFilter2D(u8, -1, g31, g31, dst=o8),
     "filter2d_u8_k31": lambda: cvb.filter2D(u8, -1, np.outer(g31, g31), dst=o8),
     "filter2d_u8_k11": lambda: cvb.filter2D(u8, -1, np.outer(g11, g11), dst=o8),
+    "filter2d_u8_k3": lambda: cvb.filter2D(u8, -1, np.outer(g3, g3), dst=o8),
+    "filter2d_f32_k5": lambda: cvb.filter2D(f32, -1, np.outer(g5, g5), dst=o32),
     "warp_cub": lambda: cvb.warpAffine(bgr, M, (7680, 4320), 2, dst=obgr),
     "resize_cub5k": lambda: cvb.resize(bgr, (5120, 2880), interpolation=2, dst=k5),
     "resize_lin_up": lambda: cvb.resize(half, (7680, 4320), interpolation=1, dst=obgr),
