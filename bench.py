@@ -262,6 +262,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every launch from the host each step instead of replaying a captured CUDA graph")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -367,8 +368,7 @@ def main():
 
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops]
 
-    def step(record):
-        shared_operands()
+    def run_ops(record):
         for i, op in enumerate(ops):
             if record:
                 ev[i][0].record()
@@ -382,28 +382,65 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(W):
-        step(False)
+        shared_operands()
+        run_ops(False)
+    barrier()
+
+    # The step's launches are captured ONCE into a CUDA graph and replayed: the step is ~50-190 short kernels and its wall time must
+    # not depend on how fast this host thread can issue them (Python + driver contention with the NVML clock sampler doubled the
+    # step time on some boxes).  Stream-ordered allocations inside the ops become graph memory nodes.  Ops that synchronise
+    # (goodFeaturesToTrack returns host data) cannot be captured: those workloads run eagerly.
+    graph, graph_note = None, "eager launches"
+    n_before = cvb.launch_count()
+    if not args.no_graph and not any(op["kind"] in ("gftt",) for op in ops):
+        try:
+            shared_operands()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run_ops(False)
+            graph, graph_note = g, "one CUDA graph per step (captured once, replayed)"
+        except Exception as exc:                      # noqa: BLE001 -- any capture failure falls back to eager launches
+            print("graph capture failed, running eagerly: %r" % (exc,), file=sys.stderr)
+            torch.cuda.synchronize()
+            graph = None
+    if graph is None:
+        shared_operands()
+        run_ops(False)
+    launches_per_step = cvb.launch_count() - n_before          # the library counts launches as it issues (or captures) them
+    barrier()
+
+    def step():
+        shared_operands()
+        if graph is not None:
+            graph.replay()
+        else:
+            run_ops(False)
+
+    for _ in range(2):
+        step()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     per_op_ms = np.zeros(len(ops))
-    n0 = cvb.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host0 = time.perf_counter()
     for s in range(args.steps):
-        step(True)
-        # per-op times are read after the step's own sync; the step timing below is one uninterrupted region only when steps == 1
-        if s == args.steps - 1:
-            e1.record()
+        step()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
+    e1.record()
     barrier()
     total_ms = e0.elapsed_time(e1)
-    # separate per-op pass (events inside a step do not serialise work, but read them from the last step)
-    for i in range(len(ops)):
-        per_op_ms[i] = ev[i][0].elapsed_time(ev[i][1])
-    launches = cvb.launch_count() - n0
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    # per-op times: one more eager step with an event pair around every op (outside the timed region)
+    shared_operands()
+    run_ops(True)
+    barrier()
+    for i in range(len(ops)):
+        per_op_ms[i] = ev[i][0].elapsed_time(ev[i][1])
+    launches = launches_per_step * args.steps
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -483,7 +520,8 @@ def main():
         out = {"metric": "Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": W,
                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32",
                "data": "synthetic", "config": {"workload": desc, "l2": "every op streams a batch whose input+output exceed the 126 MB L2",
-                                                "parallelism": "frames sharded across %d rank(s); NCCL broadcast of taps/kernels per step" % world},
+                                                "parallelism": "frames sharded across %d rank(s); NCCL broadcast of taps/kernels per step" % world,
+                                                "launch": graph_note, "host_enqueue_ms_per_step": round(host_enqueue_ms, 3)},
                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "per_op": per_op}
         if e2e:
             out["e2e"] = e2e

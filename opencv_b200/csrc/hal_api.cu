@@ -1,5 +1,6 @@
 // hal_api.cu -- host-pointer entry points: the cv_hal_* replacement functions and the batched host pipeline.
 // No arithmetic here: upload, call the device API of b200cv.h, download.
+#include <cstdlib>
 #include <functional>
 #include <vector>
 #include "common.cuh"
@@ -7,12 +8,12 @@
 
 namespace b200cv {
 
-constexpr int NPIPE = 3;
+constexpr int NPIPE = 4;          // pipeline streams (B200CV_HOST_PIPE=1..4 overrides; default 3)
 
 struct HostCtx {                      // one per host thread: OpenCV calls HAL functions concurrently from many threads
-    cudaStream_t st[NPIPE] = {nullptr, nullptr, nullptr};
-    void* dbuf[NPIPE][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
-    size_t cap[NPIPE][2] = {{0, 0}, {0, 0}, {0, 0}};
+    cudaStream_t st[NPIPE] = {};
+    void* dbuf[NPIPE][2] = {};
+    size_t cap[NPIPE][2] = {};
     void* daux = nullptr; size_t caux = 0;
     ~HostCtx()
     {
@@ -49,18 +50,20 @@ static int host_pipeline(const b200cvMat* hsrc, const b200cvMat* hdst, const Dev
     const size_t sp = pitch_of(hsrc), dp = pitch_of(hdst);
     const size_t sfb = sp * hsrc->rows, dfb = dp * hdst->rows;
     // chunk so that a chunk is ~>= 32 MB of traffic but at least 1 frame; single frames use one stream
-    int chunk = (int)std::max<size_t>(1, (32u << 20) / std::max<size_t>(1, sfb + dfb));
+    static const int env_pipe = [] { const char* e = getenv("B200CV_HOST_PIPE"); int v = e ? atoi(e) : 3; return v < 1 ? 1 : v > NPIPE ? NPIPE : v; }();
+    static const size_t env_chunk = [] { const char* e = getenv("B200CV_HOST_CHUNK_MB"); int v = e ? atoi(e) : 32; return (size_t)(v < 1 ? 1 : v) << 20; }();
+    int chunk = (int)std::max<size_t>(1, env_chunk / std::max<size_t>(1, sfb + dfb));
     if (chunk > frames) chunk = frames;
     HostCtx& c = g_ctx;
     const int nchunks = (frames + chunk - 1) / chunk;
-    const int npipe = nchunks < NPIPE ? nchunks : NPIPE;
+    const int npipe = nchunks < env_pipe ? nchunks : env_pipe;
     for (int i = 0; i < npipe; i++) {
         if (!c.st[i]) B200_CUDA(cudaStreamCreateWithFlags(&c.st[i], cudaStreamNonBlocking));
         if ((rc = ensure(&c.dbuf[i][0], &c.cap[i][0], sfb * chunk)) || (rc = ensure(&c.dbuf[i][1], &c.cap[i][1], dfb * chunk))) return rc;
     }
     const size_t swb = (size_t)hsrc->cols * elem_size(hsrc->type), dwb = (size_t)hdst->cols * elem_size(hdst->type);
     for (int ci = 0; ci < nchunks; ci++) {
-        const int i = ci % NPIPE, f0 = ci * chunk, n = std::min(chunk, frames - f0);
+        const int i = ci % npipe, f0 = ci * chunk, n = std::min(chunk, frames - f0);
         cudaStream_t st = c.st[i];
         const char* hs = (const char*)hsrc->data + (size_t)f0 * hsrc->frame_step;
         char* hd = (char*)hdst->data + (size_t)f0 * hdst->frame_step;
