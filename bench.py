@@ -434,7 +434,11 @@ def main():
     total_ms = e0.elapsed_time(e1)
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    # per-op times: one more eager step with an event pair around every op (outside the timed region)
+    # per-op times: eager steps with an event pair around every op (outside the timed region; the first pass re-warms the
+    # stream-ordered allocator after the graph replays)
+    shared_operands()
+    run_ops(False)
+    barrier()
     shared_operands()
     run_ops(True)
     barrier()

@@ -126,6 +126,9 @@ __global__ void resize_tab_kernel(ResTab* xt, ResTab* yt, ResizeParams p)
 }
 
 constexpr int RS_ROWS = 8;   // destination rows per thread
+// (Two shared-memory tiled variants were measured and dropped: staging the footprint and filtering every source row once, with
+//  the intermediate rows in shared memory or in a per-thread register ring, ran at 12-24 resident warps per SM and were latency
+//  bound -- 0.52-1.9 ms against 0.30-1.3 ms for the kernels below on the 8K->5K and 4K->8K cases, profiles/r01_notes.md.)
 
 // ---- LINEAR ----------------------------------------------------------------------------------------------------------
 template <typename T, int CN>
@@ -292,236 +295,6 @@ __global__ void __launch_bounds__(256) resize_cubic_kernel(Img src, Img dst, Res
 }
 
 
-// ---- LINEAR / CUBIC, tiled ------------------------------------------------------------------------------------------------
-// The per-pixel kernels above gather every tap from global memory (2*CN or 4*CN byte loads per source row and pixel, each a
-// separate L1 wavefront) and redo the horizontal pass for every destination row.  The tiled kernel follows the reference's own
-// structure (resizeGeneric_: a horizontal pass per SOURCE row into a ring of intermediate rows, then the vertical pass,
-// resize.cpp:2192-2258): the source footprint of a destination tile is staged in shared memory with coalesced 16-byte loads; every
-// thread owns 4 consecutive intermediate elements of a strip of 8 destination rows and keeps the ring of horizontally filtered
-// rows IN REGISTERS -- a source row is filtered once when the strip first needs it (the row index is uniform across the warp, so
-// the branch does not diverge) and reused by the following destination rows.  4 bytes (u8) or 16 bytes (f32) per store.
-// Same integer / float operations per element as the per-pixel kernels (bit-exact with the CPU).
-constexpr int RT_W = 128;       // destination columns per tile
-constexpr int RT_SH = 8;        // destination rows per strip (one thread walks one strip)
-
-template <int TAPS> struct RTab {     // per destination column of the tile
-    int off[TAPS];                    // byte offsets of the taps inside a staged row (clamped like the reference's xofs loops)
-    union { int ic[TAPS]; float fc[TAPS]; };
-};
-
-template <int CN> struct RTile {
-    static constexpr int EW = RT_W * CN;             // intermediate elements per row
-    static constexpr int NG = EW / 4;                // column groups (4 elements each)
-    static constexpr int STRIPS = 256 / NG;          // strips that fit the CTA (C1: 8, C3: 2, C4: 2)
-    static constexpr int TH = RT_SH * STRIPS;        // destination rows per tile
-};
-
-template <typename T, int CN, bool CUBIC>
-__global__ void __launch_bounds__(256) resize_tile_kernel(Img src, Img dst, ResizeParams p, const ResTab* __restrict__ xt, const ResTab* __restrict__ yt)
-{
-    constexpr int TAPS = CUBIC ? 4 : 2;
-    constexpr int ES = CN * (int)sizeof(T);
-    constexpr int NG = RTile<CN>::NG, TH = RTile<CN>::TH;
-    typedef typename std::conditional<sizeof(T) == 1, int, float>::type MT;
-    extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_geo[4];
-    __shared__ RTab<TAPS> s_tab[RT_W];
-    const int f = blockIdx.z, x0 = blockIdx.x * RT_W, y0 = blockIdx.y * TH;
-    const int tid = threadIdx.x;
-    const int x1 = min(x0 + RT_W, p.dw) - 1, y1 = min(y0 + TH, p.dh) - 1;
-    if (tid == 0) {
-        const int sxl = CUBIC ? clip_i(xt[x0].s - 1, 0, p.sw) : xt[x0].s;
-        const int sxh = CUBIC ? clip_i(xt[x1].s + 2, 0, p.sw) : min(xt[x1].s + 1, p.sw - 1);
-        const int syl = clip_i(yt[y0].s - (CUBIC ? 1 : 0), 0, p.sh), syh = clip_i(yt[y1].s + (CUBIC ? 2 : 1), 0, p.sh);
-        const int bx0 = sxl & ~15;                                    // staged rows start on a 16-pixel (hence 16-byte) boundary
-        s_geo[0] = bx0; s_geo[1] = ((sxh - bx0 + 1) * ES + 15) / 16; s_geo[2] = syl; s_geo[3] = syh - syl + 1;
-    }
-    __syncthreads();
-    const int bx0 = s_geo[0], nvec = s_geo[1], sy_lo = s_geo[2], nrows = s_geo[3];
-    const int pitch = (nvec | 1) * 16;                                // odd number of 16-byte vectors: rows start on different banks
-    unsigned char* s_src = smem;                                      // nrows x pitch
-
-    // ---- stage the footprint (one warp per row) + the column table ----
-    {
-        const bool aligned = (((uintptr_t)src.data | src.step | src.fstep) & 15) == 0;
-        const int rowbytes = p.sw * ES, gb0 = bx0 * ES;
-        for (int r = tid >> 5; r < nrows; r += 8) {
-            const unsigned char* srow = (const unsigned char*)src.row<T>(f, sy_lo + r);
-            unsigned char* drow = s_src + r * pitch;
-            for (int j = tid & 31; j < nvec; j += 32) {
-                const int gb = gb0 + j * 16;
-                uint4 val;
-                if (aligned && gb + 16 <= rowbytes) val = *(const uint4*)(srow + gb);
-                else {
-                    unsigned char b[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) b[i] = gb + i < rowbytes ? srow[gb + i] : (unsigned char)0;
-                    val = *(const uint4*)b;
-                }
-                *(uint4*)(drow + j * 16) = val;
-            }
-        }
-        if (tid < RT_W) {
-            const int x = min(x0 + tid, p.dw - 1);
-            const ResTab t = xt[x];
-            RTab<TAPS> o;
-#pragma unroll
-            for (int j = 0; j < TAPS; j++) {
-                int sx;
-                if (CUBIC) sx = min(max(t.s - 1 + j, 0), p.sw - 1);                 // per-tap clamping == the while-loops of HResizeCubic
-                else sx = (j == 1 && !t.last) ? t.s + 1 : t.s;                       // dx >= xmax: D = S[sx] * ONE (taps are (ONE, 0) there)
-                o.off[j] = (sx - bx0) * ES;
-                o.ic[j] = t.ic[j];
-            }
-            if (!CUBIC && t.last) { if (sizeof(T) == 1) { o.ic[0] = 2048; o.ic[1] = 0; } else { o.fc[0] = 1.f; o.fc[1] = 0.f; } }
-            s_tab[tid] = o;
-        }
-    }
-    __syncthreads();
-
-    const int cg = tid % NG, strip = tid / NG;
-    const int e0 = cg * 4;
-    const int row_elems = p.dw * CN;
-    const int E0 = x0 * CN + e0;                     // element index in the destination row
-    if (strip >= RTile<CN>::STRIPS || E0 >= row_elems) return;
-
-    int off[4][TAPS];
-    MT cf[4][TAPS];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int e = e0 + i, xl = e / CN, c = e - xl * CN;
-        const RTab<TAPS> t = s_tab[xl];
-#pragma unroll
-        for (int j = 0; j < TAPS; j++) {
-            off[i][j] = t.off[j] + c * (int)sizeof(T);
-            if constexpr (sizeof(T) == 1) cf[i][j] = t.ic[j]; else cf[i][j] = t.fc[j];
-        }
-    }
-    const int vec_limit = sizeof(T) == 1 ? (row_elems / 8) * 8 : (row_elems / 4) * 4;      // reference SIMD body / scalar tail split (cubic)
-    const bool full4 = (((uintptr_t)dst.data | dst.step | dst.fstep) & (4 * sizeof(T) - 1)) == 0 && E0 + 4 <= row_elems;
-
-    MT ring[TAPS][4];                 // horizontally filtered rows, ring[k] belongs to source row ring_id[k]
-    int ring_id[TAPS];
-#pragma unroll
-    for (int k = 0; k < TAPS; k++) ring_id[k] = -1;
-
-    const int ys = y0 + strip * RT_SH, ye = min(ys + RT_SH - 1, y1);
-    for (int y = ys; y <= ye; y++) {
-        const ResTab ty = yt[y];                      // one 32-byte broadcast load per row
-        MT m[TAPS][4];
-        int mid[TAPS];
-#pragma unroll
-        for (int k = 0; k < TAPS; k++) {
-            const int sr = clip_i(ty.s + k - (CUBIC ? 1 : 0), 0, p.sh);       // rows are clipped when fetched, the taps keep fy (:2211)
-            mid[k] = sr;
-            bool hit = false;
-#pragma unroll
-            for (int q = 0; q < TAPS; q++) {
-                if (!hit && ring_id[q] == sr) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) m[k][i] = ring[q][i];
-                    hit = true;
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < k; q++) {             // clipped rows repeat at the image border
-                if (!hit && mid[q] == sr) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) m[k][i] = m[q][i];
-                    hit = true;
-                }
-            }
-            if (!hit) {                               // uniform across the warp: every lane of a warp works on the same destination row
-                const unsigned char* srow = s_src + (sr - sy_lo) * pitch;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if constexpr (sizeof(T) == 1) {
-                        int acc = 0;
-#pragma unroll
-                        for (int j = 0; j < TAPS; j++) acc += srow[off[i][j]] * cf[i][j];
-                        m[k][i] = acc;
-                    } else {
-                        float acc = __fmul_rn(*(const float*)(srow + off[i][0]), cf[i][0]);
-#pragma unroll
-                        for (int j = 1; j < TAPS; j++) acc = __fadd_rn(acc, __fmul_rn(*(const float*)(srow + off[i][j]), cf[i][j]));
-                        m[k][i] = acc;
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < TAPS; k++) {
-            ring_id[k] = mid[k];
-#pragma unroll
-            for (int i = 0; i < 4; i++) ring[k][i] = m[k][i];
-        }
-        T out[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if constexpr (sizeof(T) == 1) {
-                if constexpr (!CUBIC) {
-                    out[i] = (uchar)((((ty.ic[0] * (m[0][i] >> 4)) >> 16) + ((ty.ic[1] * (m[1][i] >> 4)) >> 16) + 2) >> 2);
-                } else if (E0 + i < vec_limit) {
-                    const float sc = 1.f / (2048.f * 2048.f);
-                    float v = __fmul_rn((float)m[3][i], __fmul_rn((float)ty.ic[3], sc));
-                    v = __fadd_rn(__fmul_rn((float)m[2][i], __fmul_rn((float)ty.ic[2], sc)), v);
-                    v = __fadd_rn(__fmul_rn((float)m[1][i], __fmul_rn((float)ty.ic[1], sc)), v);
-                    v = __fadd_rn(__fmul_rn((float)m[0][i], __fmul_rn((float)ty.ic[0], sc)), v);
-                    out[i] = sat_u8(__float2int_rn(v));
-                } else {
-                    out[i] = sat_u8((m[0][i] * ty.ic[0] + m[1][i] * ty.ic[1] + m[2][i] * ty.ic[2] + m[3][i] * ty.ic[3] + (1 << 21)) >> 22);
-                }
-            } else {
-                if constexpr (!CUBIC) {
-                    out[i] = __fadd_rn(__fmul_rn(m[0][i], ty.fc[0]), __fmul_rn(m[1][i], ty.fc[1]));
-                } else if (E0 + i < vec_limit) {
-                    float o = __fmul_rn(m[3][i], ty.fc[3]);
-                    o = __fadd_rn(__fmul_rn(m[2][i], ty.fc[2]), o);
-                    o = __fadd_rn(__fmul_rn(m[1][i], ty.fc[1]), o);
-                    out[i] = __fadd_rn(__fmul_rn(m[0][i], ty.fc[0]), o);
-                } else {
-                    float o = __fmul_rn(m[0][i], ty.fc[0]);
-                    o = __fadd_rn(o, __fmul_rn(m[1][i], ty.fc[1]));
-                    o = __fadd_rn(o, __fmul_rn(m[2][i], ty.fc[2]));
-                    out[i] = __fadd_rn(o, __fmul_rn(m[3][i], ty.fc[3]));
-                }
-            }
-        }
-        T* dp = dst.row<T>(f, y) + E0;
-        if (full4) {
-            if constexpr (sizeof(T) == 1) *(uint32_t*)dp = *(const uint32_t*)out;
-            else *(float4*)dp = *(const float4*)out;
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; i++) if (E0 + i < row_elems) dp[i] = out[i];
-        }
-    }
-}
-
-// shared memory a tile can need (rigorous: s(x) = floor((x + 0.5) scale - 0.5) grows by at most ceil(n scale) + 1 over n columns)
-static size_t resize_tile_smem(const ResizeParams& p, int es, int th, int taps)
-{
-    const long long wpx = (long long)ceil((RT_W - 1) * p.scale_x) + 1 + taps + 15 + 1;
-    const long long rows = (long long)ceil((th - 1) * p.scale_y) + 1 + taps + 1;
-    const long long pitch = ((wpx * es + 15) / 16 + 2) * 16;
-    return (size_t)(rows * pitch + 64);
-}
-
-template <typename T, int CN, bool CUBIC>
-static int launch_resize_tile(const Img& s, const Img& d, const ResizeParams& p, const ResTab* xt, const ResTab* yt, cudaStream_t st, bool* done)
-{
-    const size_t smem = resize_tile_smem(p, CN * (int)sizeof(T), RTile<CN>::TH, CUBIC ? 4 : 2);
-    *done = false;
-    if (smem > 96 * 1024) return B200CV_OK;          // strong minification does not fit: per-pixel kernels
-    auto kern = resize_tile_kernel<T, CN, CUBIC>;
-    static bool attr = false;
-    if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
-    dim3 grid(div_up((unsigned)p.dw, RT_W), div_up((unsigned)p.dh, RTile<CN>::TH), (unsigned)s.frames);
-    kern<<<grid, 256, smem, st>>>(s, d, p, xt, yt);
-    *done = true;
-    return B200CV_OK;
-}
-
 template <typename T>
 static int launch_by_cn(int cn, int interp, const Img& s, const Img& d, const ResizeParams& p, cudaStream_t st)
 {
@@ -533,22 +306,6 @@ static int launch_by_cn(int cn, int interp, const Img& s, const Img& d, const Re
     if (interp == B200CV_INTER_LINEAR) resize_tab_kernel<false, FIX><<<nt, 256, 0, st>>>(xt, yt, p);
     else resize_tab_kernel<true, FIX><<<nt, 256, 0, st>>>(xt, yt, p);
     count_launch();
-    const bool cubic = interp != B200CV_INTER_LINEAR;
-    const char* path = getenv("B200CV_RESIZE_PATH");
-    if (!(path && !strcmp(path, "pixel"))) {
-        bool done = false;
-#define LT(CN) (cubic ? launch_resize_tile<T, CN, true>(s, d, p, xt, yt, st, &done) : launch_resize_tile<T, CN, false>(s, d, p, xt, yt, st, &done))
-        int rc = cn == 1 ? LT(1) : cn == 3 ? LT(3) : LT(4);
-#undef LT
-        if (rc) { cudaFreeAsync(tab, st); return rc; }
-        if (done) {
-            cudaError_t e = cudaGetLastError();
-            cudaFreeAsync(tab, st);
-            count_launch();
-            if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
-            return B200CV_OK;
-        }
-    }
     dim3 grid(div_up((unsigned)p.dw, 256), div_up((unsigned)p.dh, RS_ROWS), (unsigned)s.frames);
 #define L(K, CN) K<T, CN><<<grid, 256, 0, st>>>(s, d, p, xt, yt)
     if (interp == B200CV_INTER_LINEAR) {

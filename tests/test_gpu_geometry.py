@@ -149,22 +149,3 @@ def test_warp_tile_and_direct_paths(cvb, oracle, rng, interp, monkeypatch):
         monkeypatch.setenv("B200CV_WARP_PATH", "direct")
         assert_exact(got, cpu(cvb.warpPerspective(gpu(img), Hm, (401, 283), interp | C.WARP_INVERSE_MAP, C.BORDER_REPLICATE)), "tile vs direct")
         monkeypatch.delenv("B200CV_WARP_PATH")
-
-
-@pytest.mark.parametrize("interp", [C.INTER_LINEAR, C.INTER_CUBIC])
-def test_resize_tile_and_pixel_paths(cvb, oracle, rng, interp, monkeypatch):
-    """LINEAR/CUBIC run on the tiled kernel (footprint staged in shared memory, one horizontal pass per source row); the per-pixel
-    kernel remains for strong minification.  Both must equal the CPU bit for bit (u8) / to float rounding (f32 is bit-exact too:
-    same operations in the same order)."""
-    for shape, dsz in (((301, 517, 3), (333, 201)), ((301, 517, 3), (1100, 640)), ((257, 263, 1), (64, 48)), ((97, 1031, 4), (771, 97)),
-                       ((64, 80, 1), (7, 5)), ((400, 900, 3), (31, 23))):          # the last two minify too strongly for the tile
-        img = rand_u8(rng, *shape)
-        got = cpu(cvb.resize(gpu(img), dsz, interpolation=interp))
-        assert_exact(got, oracle.resize(img, dsz, interp), "resize u8 %s -> %s interp %d" % (shape, dsz, interp))
-        f = img.astype(np.float32) * 0.37
-        gotf = cpu(cvb.resize(gpu(f), dsz, interpolation=interp))
-        assert_close(gotf, oracle.resize(f, dsz, interp), atol=1e-4, rtol=1e-6, what="resize f32 %s -> %s interp %d" % (shape, dsz, interp))
-        monkeypatch.setenv("B200CV_RESIZE_PATH", "pixel")
-        assert_exact(got, cpu(cvb.resize(gpu(img), dsz, interpolation=interp)), "tile vs pixel u8")
-        assert_exact(gotf, cpu(cvb.resize(gpu(f), dsz, interpolation=interp)), "tile vs pixel f32")
-        monkeypatch.delenv("B200CV_RESIZE_PATH")
