@@ -369,6 +369,9 @@ def main():
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in ops]
 
     def run_ops(record):
+        if record:      # keep the GPU busy while the host enqueues, so the first op's event pair does not include launch latency
+            big = ops[int(np.argmax([o["px"] * o["frames"] for o in ops]))]
+            run_op(cvb, big, big["_src"], big["_dst"], extra)
         for i, op in enumerate(ops):
             if record:
                 ev[i][0].record()
