@@ -47,26 +47,6 @@ __global__ void toeplitz_kernel(Img templ, int w, int h, unsigned char* out)
     }
 }
 
-// filter2D operand: [kernel row v][k-chunk c (2*kch)][column j (192) = digit d * 64 + jj][16 bytes]: byte b = digit_d(Kq(v, 16c + b - jj))
-struct KqParams { int q[33 * 33]; };     // quantised taps travel as a kernel parameter: no H2D copy that would queue behind bulk transfers
-
-__global__ void toeplitz_digits_kernel(const __grid_constant__ KqParams kp, int w, int h, int kch, signed char* out)
-{
-    const int* kq = kp.q;
-    const int v = blockIdx.x;
-    const int slab = 2 * kch * 192 * 16;
-    for (int idx = threadIdx.x; idx < slab; idx += blockDim.x) {
-        int b = idx & 15, j = (idx >> 4) % 192, c = (idx >> 4) / 192;
-        int d = j >> 6, jj = j & 63;
-        int u = 16 * c + b - jj;
-        int q = (u >= 0 && u < w) ? kq[v * w + u] : 0;
-        // balanced base-256 digits, each in [-128, 127]
-        int d0 = ((q + 128) & 255) - 128; q = (q - d0) >> 8;
-        int d1 = ((q + 128) & 255) - 128; q = (q - d1) >> 8;
-        out[(size_t)v * slab + idx] = (signed char)(d == 0 ? d0 : d == 1 ? d1 : q);
-    }
-}
-
 // border-extended copy of an 8-bit single-channel image: P(y, x) = src(y - ay, x - ax) under `border`.
 // 16 output bytes per thread; away from the borders the (generally unaligned) source run is read as 5 aligned words and realigned
 // with funnel shifts.
@@ -304,76 +284,11 @@ int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, c
     return B200CV_OK;
 }
 
-template <int EPI>
-static int launch_filter_tc(const CUtensorMap& tm, const unsigned char* bglob, const Img& d, const TCParams& p, size_t smem, cudaStream_t st)
+void launch_pad_u8(const Img& src, const Img& dst, int ax, int ay, int border, cudaStream_t st)
 {
-    auto kern = ccorr_u8_tc_kernel<3, EPI>;
-    static bool attr = false;
-    if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-    dim3 grid(div_up((unsigned)p.ow, TC_N), div_up((unsigned)p.oh, 128 * TC_MT), (unsigned)d.frames);
-    kern<<<grid, 128, smem, st>>>(tm, bglob, d, p);
-    cudaError_t e = cudaGetLastError();
+    pad_u8_kernel<<<dim3(div_up((unsigned)dst.cols / 16, 128), (unsigned)dst.rows, (unsigned)src.frames), 128, 0, st>>>(
+        src, dst, ax, ay, border, (((uintptr_t)src.data | src.step | src.fstep) & 3) == 0);
     count_launch();
-    if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
-    return B200CV_OK;
-}
-
-// filter2D, 8-bit single-channel source, kernels the reference would hand to its DFT path.  dd = destination depth.
-// returns B200CV_NOT_IMPLEMENTED when the tensor-core path does not apply (caller uses the direct-sum kernel)
-int filter2d_u8_tensor(const Img& s, const Img& d, int dd, const float* k, int kw, int kh, int ax, int ay, float delta, int border, cudaStream_t st)
-{
-    if (kw + TC_N - 1 > TC_K || kh > 64 || s.frames >= 65536) return B200CV_NOT_IMPLEMENTED;
-    if (dd != B200CV_8U && dd != B200CV_32F && dd != B200CV_16S) return B200CV_NOT_IMPLEMENTED;
-    float mx = 0.f;
-    for (int i = 0; i < kw * kh; i++) {
-        if (!std::isfinite(k[i])) return B200CV_NOT_IMPLEMENTED;
-        mx = std::max(mx, std::fabs(k[i]));
-    }
-    if (!(mx > 0.f) || mx > 1e30f || mx < 1e-30f) return B200CV_NOT_IMPLEMENTED;
-    // |Kq| <= 2^23 - 2^15 keeps the three balanced digits inside [-128, 127]
-    int e;
-    std::frexp((double)mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
-    const int sh = 22 - e;                            // |k| * 2^sh < 2^22
-    if (kw * kh > 33 * 33) return B200CV_NOT_IMPLEMENTED;
-    static thread_local KqParams kq;
-    for (int i = 0; i < kw * kh; i++) kq.q[i] = (int)std::lrint(std::ldexp((double)k[i], sh));
-
-    TCParams p;
-    p.h = kh; p.ow = s.cols; p.oh = s.rows; p.kch = (kw + TC_N - 1 + 31) / 32; p.scale = (float)std::ldexp(1.0, -sh); p.delta = delta;
-    int ra = 128 * TC_MT + kh - 1;
-    p.nbox = (ra + 255) / 256;
-    p.box_h = (((ra + p.nbox - 1) / p.nbox) + 7) & ~7;
-    p.ra_alloc = p.nbox * p.box_h;
-    const int nchunk = 2 * p.kch;
-    const size_t bbytes = (size_t)nchunk * 192 * 16;
-    size_t smem = (size_t)nchunk * p.ra_alloc * 16 + (size_t)TC_NS * bbytes;
-    if (smem > 200 * 1024) return B200CV_NOT_IMPLEMENTED;
-
-    // border-extended source, rows padded to a multiple of 16 bytes (TMA)
-    Img pad = s;
-    pad.cols = (s.cols + kw - 1 + 15) & ~15;
-    pad.rows = s.rows + kh - 1;
-    pad.step = (size_t)pad.cols;
-    pad.fstep = pad.step * pad.rows;
-    unsigned char* pbuf = nullptr; unsigned char* bglob = nullptr;
-    B200_CUDA(cudaMallocAsync(&pbuf, pad.fstep * (size_t)s.frames, st));
-    B200_CUDA(cudaMallocAsync(&bglob, (size_t)kh * bbytes, st));
-    pad.data = pbuf;
-    toeplitz_digits_kernel<<<kh, 256, 0, st>>>(kq, kw, kh, p.kch, (signed char*)bglob);
-    count_launch();
-    pad_u8_kernel<<<dim3(div_up((unsigned)pad.cols / 16, 128), (unsigned)pad.rows, (unsigned)s.frames), 128, 0, st>>>(
-        s, pad, ax, ay, border, (((uintptr_t)s.data | s.step | s.fstep) & 3) == 0);
-    count_launch();
-    CUtensorMap tm;
-    int rc = make_tensor_map_3d(&tm, pad.data, 1, pad.cols, pad.rows, pad.frames, pad.step, pad.fstep, 16, p.box_h);
-    if (!rc) {
-        rc = dd == B200CV_8U ? launch_filter_tc<EPI_U8>(tm, bglob, d, p, smem, st)
-           : dd == B200CV_16S ? launch_filter_tc<EPI_S16>(tm, bglob, d, p, smem, st)
-                              : launch_filter_tc<EPI_F32>(tm, bglob, d, p, smem, st);
-    }
-    cudaFreeAsync(bglob, st);
-    cudaFreeAsync(pbuf, st);
-    return rc;
 }
 
 }  // namespace b200cv
