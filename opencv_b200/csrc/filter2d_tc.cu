@@ -33,6 +33,7 @@ constexpr int FC_K = 64;                      // K per kernel row
 constexpr int FC_MT = 2;                      // M-tiles (128 rows) per tile
 constexpr int FC_BROW = (FC_K / 16) * FC_N * 16;   // bytes of B per kernel row = 6144
 constexpr int FC_THREADS = 192;
+constexpr int FC_SMEM_MAX = 227 * 1024 - 512;   // opt-in limit per CTA (232448 B) minus this kernel's static shared memory (barriers)
 
 struct FCKq { int q[33 * 33]; };
 
@@ -238,7 +239,7 @@ static int launch_fc(const CUtensorMap& tm, const unsigned char* bglob, const Im
 {
     auto kern = filter2d_tc_kernel<EPI>;
     static bool attr = false;
-    if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+    if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_MAX)); attr = true; }
     kern<<<grid, FC_THREADS, smem, st>>>(tm, bglob, d, p);
     cudaError_t e = cudaGetLastError();
     count_launch();
@@ -276,7 +277,7 @@ int filter2d_u8_tensor(const Img& s, const Img& d, int dd, const float* k, int k
     p.box_h = (((ra + p.nbox - 1) / p.nbox) + 7) & ~7;
     p.ra_alloc = p.nbox * p.box_h;
     const size_t smem = (size_t)kh * FC_BROW + 2 * (size_t)(FC_K / 16) * p.ra_alloc * 16;
-    if (smem > 227 * 1024) return B200CV_NOT_IMPLEMENTED;
+    if (smem > (size_t)FC_SMEM_MAX) return B200CV_NOT_IMPLEMENTED;
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; B200_CUDA(cudaGetDevice(&dev)); B200_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
     const int grid = (int)std::min<long long>(nt, n_sm);
