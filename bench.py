@@ -461,15 +461,39 @@ def main():
         per_op[op["name"]] = {"ms": round(float(ms), 4), "mpix_s": round(op["px"] * op["frames"] / (ms * 1e-3) / 1e6, 1), "gbs": round(gbs, 1), "frac_hbm": round(gbs / peak, 4)}
     dom = int(np.argmax(per_op_ms))
     dgbs = ops[dom]["abytes"] * ops[dom]["frames"] / (per_op_ms[dom] * 1e-3) / 1e9
-    roofline = {"kernel": ops[dom]["name"], "bound": "hbm", "achieved": round(dgbs, 1), "peak": peak, "unit": "GB/s", "frac": round(dgbs / peak, 4), "traffic": None,
+    # dram bytes per launch of the op's main kernel from `ncu --set full` (profiles/ncu_traffic.json, written from the committed captures)
+    traffic = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as fh:
+            traffic = json.load(fh).get(ops[dom]["name"])
+    except (OSError, ValueError):
+        traffic = None
+    roofline = {"kernel": ops[dom]["name"], "bound": "hbm", "achieved": round(dgbs, 1), "peak": peak, "unit": "GB/s", "frac": round(dgbs / peak, 4), "traffic": traffic,
                 "peak_source": peak_src, "share_of_step": round(float(per_op_ms[dom] / per_op_ms.sum()), 3),
                 "note": "dominant = largest share of step time; per_op lists achieved GB/s and HBM fraction of every op (algorithmic bytes, SURVEY 8d)"}
+    if ops[dom]["kind"] == "f2d":
+        # a k x k direct sum is k*k FMA per pixel: the FP32 pipe, not HBM, bounds it -- report that too
+        k = ops[dom]["k"]
+        tfl = 2.0 * k * k * ops[dom]["px"] * ops[dom]["frames"] / (per_op_ms[dom] * 1e-3) / 1e12
+        fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        roofline["fp32"] = {"achieved": round(tfl, 1), "peak": round(fp32_peak, 1), "unit": "TFLOP/s", "frac": round(tfl / fp32_peak, 3),
+                            "note": "148 SM x 128 FMA lanes x 2 x 1.965 GHz; this op is FMA-issue bound (k*k MAC per pixel), its HBM fraction is not the limiter"}
 
     # ---------------- e2e: the same ops through the host C ABI (pinned host memory, H2D+D2H in the timed region) --------------
     e2e = None
     if not args.no_e2e:
         hops = [op for op in ops if op["kind"] not in ("gftt", "sift")]
         hb = {}
+        # page-locked buffers are placed on the NUMA node of the allocating thread: run this section on the CPUs next to the GPU
+        # (what `numactl --cpunodebind` does for a production host process), and put the mask back afterwards
+        old_aff = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            old_aff = os.sched_getaffinity(0)
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        except Exception:                          # noqa: BLE001 -- affinity is an optimisation, never a requirement
+            old_aff = None
 
         def hbuf(spec, fill):
             key = (spec[0], np.dtype(spec[1]).str, fill)
@@ -500,6 +524,11 @@ def main():
             t = torch.tensor([dt], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        if old_aff is not None:
+            try:
+                os.sched_setaffinity(0, old_aff)
+            except OSError:
+                pass
         hpx = sum(op["px"] * op["frames"] for op in hops)
         e2e = {"value": hpx * world * hsteps / dt / 1e6, "unit": "Mpix/s",
                "h2d_bytes_per_step": int(sum(op["_hsrc"].nbytes for op in hops)), "d2h_bytes_per_step": int(sum(op["_hdst"].nbytes for op in hops)),

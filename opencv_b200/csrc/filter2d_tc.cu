@@ -15,7 +15,8 @@
 // 256 rows x 32 columns:
 //   warp 0  producer  -- per tile one TMA load of the 64-byte-wide A strip (256 + kh - 1 rows, 18 KB), double buffered
 //   warp 1  issuer    -- kh x 2 M-tiles x 2 K-steps tcgen05.mma per tile into one of two TMEM accumulator stages (2 x 192 columns)
-//   warps 2-5 epilogue -- tcgen05.ld of the previous tile's stage, recombination, 32-byte row stores, overlapping the next tile's MMAs
+//   warps 2-9 epilogue -- tcgen05.ld of the previous tile's stage (two warps per TMEM lane quarter, 16 columns each), recombination,
+//                        16-byte row stores, overlapping the next tile's MMAs
 // mbarriers: b_full, a_full/a_empty[2], acc_full/acc_empty[2]; tcgen05.commit releases A buffers and publishes accumulators.
 #include <algorithm>
 #include <cmath>
@@ -32,7 +33,7 @@ constexpr int FC_N = 3 * FC_NT;               // MMA N (three digit planes)
 constexpr int FC_K = 64;                      // K per kernel row
 constexpr int FC_MT = 2;                      // M-tiles (128 rows) per tile
 constexpr int FC_BROW = (FC_K / 16) * FC_N * 16;   // bytes of B per kernel row = 6144
-constexpr int FC_THREADS = 192;
+constexpr int FC_THREADS = 320;                // producer warp, issuer warp, 8 epilogue warps
 constexpr int FC_SMEM_MAX = 227 * 1024 - 512;   // opt-in limit per CTA (232448 B) minus this kernel's static shared memory (barriers)
 
 struct FCKq { int q[33 * 33]; };
@@ -93,6 +94,15 @@ __device__ __forceinline__ void fc_tmem_ld32(uint32_t taddr, uint32_t* r)
         : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void fc_tmem_ld16(uint32_t taddr, uint32_t* r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+          "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+
 enum { FC_U8 = 0, FC_F32 = 1, FC_S16 = 2 };
 
 template <int EPI>
@@ -110,7 +120,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) filter2d_tc_kernel(const __grid
 
     if (threadIdx.x == 0) {
         mbar_init(&b_full, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < 2; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
         fence_barrier_init();
     }
     if (warp == 1) {   // TMEM: 2 stages x FC_MT x 96 columns of 32-bit accumulators = 384 -> 512 allocated
@@ -169,64 +179,64 @@ __global__ void __launch_bounds__(FC_THREADS, 1) filter2d_tc_kernel(const __grid
             }
         }
     } else {
-        // ---- epilogue: warps 2..5; warp w may touch TMEM lanes 32 (w % 4) .. +31 = accumulator rows ----
-        const int quarter = warp & 3;
+        // ---- epilogue: warps 2..9; warp w may touch TMEM lanes 32 (w % 4) .. +31 = accumulator rows; the two warps of a quarter
+        //      split the 32 output columns ----
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         int i = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
             const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, f = t / (p.tiles_x * p.tiles_y);
             const int buf = i & 1;
             mbar_wait(&acc_full[buf], (i >> 1) & 1);
             fc_fence_after();
-            const int gx0 = tx * FC_NT;
+            const int gx0 = tx * FC_NT + half * 16;
 #pragma unroll 1
             for (int mt = 0; mt < FC_MT; mt++) {
                 const int gy = ty * (128 * FC_MT) + mt * 128 + quarter * 32 + lane;
-                const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * (FC_MT * FC_N) + mt * FC_N;
-                uint32_t r0[32], r1[32], r2[32];
-                fc_tmem_ld32(trow, r0);
-                fc_tmem_ld32(trow + FC_NT, r1);
-                fc_tmem_ld32(trow + 2 * FC_NT, r2);
+                const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)buf * (FC_MT * FC_N) + mt * FC_N + half * 16;
+                uint32_t r0[16], r1[16], r2[16];
+                fc_tmem_ld16(trow, r0);
+                fc_tmem_ld16(trow + FC_NT, r1);
+                fc_tmem_ld16(trow + 2 * FC_NT, r2);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float v[32];
+                float v[16];
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
+                for (int j = 0; j < 16; j++) {
                     const long long sum = (long long)(int)r0[j] + ((long long)(int)r1[j] << 8) + ((long long)(int)r2[j] << 16);
                     v[j] = __fadd_rn(__fmul_rn(__ll2float_rn(sum), p.scale), p.delta);
                 }
-                if (gy < p.oh) {
+                if (gy < p.oh && gx0 < p.ow) {
                     if constexpr (EPI == FC_U8) {
                         uchar* dp = dst.row<uchar>(f, gy) + gx0;
-                        if (gx0 + 32 <= p.ow && ((uintptr_t)dp & 15) == 0) {
-                            uint32_t w[8];
+                        if (gx0 + 16 <= p.ow && ((uintptr_t)dp & 15) == 0) {
+                            uint32_t w[4];
 #pragma unroll
-                            for (int j = 0; j < 8; j++)
+                            for (int j = 0; j < 4; j++)
                                 w[j] = (uint32_t)sat_u8(v[4 * j]) | ((uint32_t)sat_u8(v[4 * j + 1]) << 8) | ((uint32_t)sat_u8(v[4 * j + 2]) << 16) |
                                        ((uint32_t)sat_u8(v[4 * j + 3]) << 24);
-                            ((uint4*)dp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                            ((uint4*)dp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                            *(uint4*)dp = make_uint4(w[0], w[1], w[2], w[3]);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; j++) if (gx0 + j < p.ow) dp[j] = sat_u8(v[j]);
+                            for (int j = 0; j < 16; j++) if (gx0 + j < p.ow) dp[j] = sat_u8(v[j]);
                         }
                     } else if constexpr (EPI == FC_S16) {
                         short* dp = dst.row<short>(f, gy) + gx0;
 #pragma unroll
-                        for (int j = 0; j < 32; j++) if (gx0 + j < p.ow) dp[j] = sat_s16(v[j]);
+                        for (int j = 0; j < 16; j++) if (gx0 + j < p.ow) dp[j] = sat_s16(v[j]);
                     } else {
                         float* dp = dst.row<float>(f, gy) + gx0;
-                        if (gx0 + 32 <= p.ow && ((uintptr_t)dp & 15) == 0) {
+                        if (gx0 + 16 <= p.ow && ((uintptr_t)dp & 15) == 0) {
 #pragma unroll
-                            for (int j = 0; j < 8; j++) ((float4*)dp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            for (int j = 0; j < 4; j++) ((float4*)dp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 32; j++) if (gx0 + j < p.ow) dp[j] = v[j];
+                            for (int j = 0; j < 16; j++) if (gx0 + j < p.ow) dp[j] = v[j];
                         }
                     }
                 }
             }
             fc_fence_before();
             __syncwarp();
-            if (lane == 0) fc_mbar_arrive(&acc_empty[buf]);      // 4 arrivals (one per epilogue warp) free the stage
+            if (lane == 0) fc_mbar_arrive(&acc_empty[buf]);      // 8 arrivals (one per epilogue warp) free the stage
         }
     }
     fc_fence_before();

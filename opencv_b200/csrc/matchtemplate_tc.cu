@@ -14,11 +14,7 @@
 // the price of a well-shaped MMA; the result is exact because products <= 65025 and sums < 2^31.
 //
 //
-// The same engine evaluates filter2D on 8-bit images for kernels of >= 11x11 taps -- the sizes at which the reference itself
-// leaves the direct sum for a DFT (filter.dispatch.cpp:1288-1310).  The float taps are quantised to 24-bit fixed point against
-// max|k| and split into three signed base-256 digits; the three digit planes ride in ONE MMA as N = 3 x 64 (u8 x s8 -> s32,
-// exact), and the epilogue recombines S0 + 256 S1 + 65536 S2 in 64-bit, scales by the power of two and adds delta.  The
-// only error left is the tap quantisation (<= 2^-24 max|k| per tap), the same order as a float accumulation.
+// (8-bit filter2D with >= 11x11 taps uses the same Toeplitz formulation in a persistent kernel: filter2d_tc.cu.)
 //
 // Reference: crossCorr, modules/imgproc/src/templmatch.cpp:566-760 (block DFT in float on one thread).
 #include "common.cuh"

@@ -45,6 +45,7 @@ ops = {
     "sep_u8_k31": lambda: cvb.sepFilter2D(u8, -1, g31, g31, dst=o8),
     "filter2d_u8_k31": lambda: cvb.filter2D(u8, -1, np.outer(g31, g31), dst=o8),
     "filter2d_u8_k11": lambda: cvb.filter2D(u8, -1, np.outer(g11, g11), dst=o8),
+    "filter2d_f32_k31": lambda: cvb.filter2D(f32, -1, np.outer(g31, g31), dst=o32),
     "filter2d_u8_k3": lambda: cvb.filter2D(u8, -1, np.outer(g3, g3), dst=o8),
     "filter2d_f32_k5": lambda: cvb.filter2D(f32, -1, np.outer(g5, g5), dst=o32),
     "warp_cub": lambda: cvb.warpAffine(bgr, M, (7680, 4320), 2, dst=obgr),
