@@ -13,7 +13,7 @@
 // Data movement.  K = 64 per kernel row covers kw <= 33 (kw + 31 <= 64): a kernel row's operand B_v is 4 x 96 x 16 B = 6 KB, so
 // ALL of B (31 rows = 186 KB) stays RESIDENT in shared memory for the life of the CTA.  One CTA per SM walks destination tiles of
 // 256 rows x 32 columns:
-//   warp 0  producer  -- per tile one TMA load of the 64-byte-wide A strip (256 + kh - 1 rows, 18 KB), double buffered
+//   warp 0  producer  -- per tile one TMA load of the 64-byte-wide A strip (256 + kh - 1 rows, 18 KB) into a ring of 2-4 buffers
 //   warp 1  issuer    -- kh x 2 M-tiles x 2 K-steps tcgen05.mma per tile into one of two TMEM accumulator stages (2 x 192 columns)
 //   warps 2-9 epilogue -- tcgen05.ld of the previous tile's stage (two warps per TMEM lane quarter, 16 columns each), recombination,
 //                        16-byte row stores, overlapping the next tile's MMAs
@@ -41,6 +41,7 @@ struct FCKq { int q[33 * 33]; };
 struct FCParams {
     int kh, ra_alloc, box_h, nbox;
     int ow, oh, frames, tiles_x, tiles_y, ntiles;
+    int na;                                   // A strip buffers (2..4): as many as fit next to the resident B
     float scale, delta;
 };
 
@@ -112,15 +113,16 @@ __global__ void __launch_bounds__(FC_THREADS, 1) filter2d_tc_kernel(const __grid
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t abytes = (uint32_t)(FC_K / 16) * p.ra_alloc * 16;        // one A buffer
     unsigned char* sB = smem;                                               // kh x 6 KB, resident
-    unsigned char* sA = smem + (size_t)p.kh * FC_BROW;                      // 2 buffers
-    __shared__ __align__(8) uint64_t b_full, a_full[2], a_empty[2], acc_full[2], acc_empty[2];
+    unsigned char* sA = smem + (size_t)p.kh * FC_BROW;                      // p.na buffers
+    __shared__ __align__(8) uint64_t b_full, a_full[4], a_empty[4], acc_full[2], acc_empty[2];
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lbo_a = (uint32_t)p.ra_alloc * 16u;
 
     if (threadIdx.x == 0) {
         mbar_init(&b_full, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
+        for (int s = 0; s < 4; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
         fence_barrier_init();
     }
     if (warp == 1) {   // TMEM: 2 stages x FC_MT x 96 columns of 32-bit accumulators = 384 -> 512 allocated
@@ -140,8 +142,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) filter2d_tc_kernel(const __grid
             int i = 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
                 const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, f = t / (p.tiles_x * p.tiles_y);
-                const int buf = i & 1;
-                mbar_wait(&a_empty[buf], ((i >> 1) & 1) ^ 1);
+                const int buf = i % p.na;
+                mbar_wait(&a_empty[buf], ((i / p.na) & 1) ^ 1);
                 mbar_arrive_expect_tx(&a_full[buf], abytes);
                 unsigned char* dstA = sA + (size_t)buf * abytes;
                 for (int c = 0; c < FC_K / 16; c++)
@@ -158,12 +160,12 @@ __global__ void __launch_bounds__(FC_THREADS, 1) filter2d_tc_kernel(const __grid
             const uint32_t b_base = smem_u32(sB);
             int i = 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
-                const int buf = i & 1;
-                mbar_wait(&a_full[buf], (i >> 1) & 1);
-                mbar_wait(&acc_empty[buf], ((i >> 1) & 1) ^ 1);
+                const int buf = i % p.na, acc = i & 1;
+                mbar_wait(&a_full[buf], (i / p.na) & 1);
+                mbar_wait(&acc_empty[acc], ((i >> 1) & 1) ^ 1);
                 fc_fence_after();
                 const uint32_t a_base = smem_u32(sA + (size_t)buf * abytes);
-                const uint32_t d_base = tmem + (uint32_t)buf * (FC_MT * FC_N);
+                const uint32_t d_base = tmem + (uint32_t)acc * (FC_MT * FC_N);
                 for (int v = 0; v < p.kh; v++) {
 #pragma unroll
                     for (int mt = 0; mt < FC_MT; mt++)
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) filter2d_tc_kernel(const __grid
                         }
                 }
                 fc_commit(&a_empty[buf]);        // the A strip may be overwritten once these MMAs have read it
-                fc_commit(&acc_full[buf]);       // ... and the accumulator stage is complete
+                fc_commit(&acc_full[acc]);       // ... and the accumulator stage is complete
             }
         }
     } else {
@@ -286,8 +288,10 @@ int filter2d_u8_tensor(const Img& s, const Img& d, int dd, const float* k, int k
     p.nbox = (ra + 255) / 256;
     p.box_h = (((ra + p.nbox - 1) / p.nbox) + 7) & ~7;
     p.ra_alloc = p.nbox * p.box_h;
-    const size_t smem = (size_t)kh * FC_BROW + 2 * (size_t)(FC_K / 16) * p.ra_alloc * 16;
-    if (smem > (size_t)FC_SMEM_MAX) return B200CV_NOT_IMPLEMENTED;
+    const size_t abytes = (size_t)(FC_K / 16) * p.ra_alloc * 16;
+    if ((size_t)kh * FC_BROW + 2 * abytes > (size_t)FC_SMEM_MAX) return B200CV_NOT_IMPLEMENTED;
+    p.na = (int)std::min<size_t>(4, ((size_t)FC_SMEM_MAX - (size_t)kh * FC_BROW) / abytes);
+    const size_t smem = (size_t)kh * FC_BROW + p.na * abytes;
     static int n_sm = 0;
     if (!n_sm) { int dev = 0; B200_CUDA(cudaGetDevice(&dev)); B200_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
     const int grid = (int)std::min<long long>(nt, n_sm);

@@ -56,9 +56,10 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const __grid_cons
         fence_barrier_init();
         mbar_arrive_expect_tx(&s_bar, (uint32_t)(GU_IW * IH));
         tma_load_3d(s_in, &tmap, x0 - RA, y0 - RB, f, &s_bar);
+        // only this thread polls the barrier; the others sleep in bar.sync instead of spending issue slots on a spin loop
+        mbar_wait(&s_bar, 0);
     }
     __syncthreads();
-    mbar_wait(&s_bar, 0);
 
     // ---- border patch (only CTAs whose tile crosses the image boundary; BORDER_CONSTANT needs nothing) ----
     const int tx0 = x0 - RA;                            // image column of tile column 0

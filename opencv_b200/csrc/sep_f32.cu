@@ -48,9 +48,10 @@ __global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(co
         fence_barrier_init();
         mbar_arrive_expect_tx(&s_bar, (uint32_t)(SF_IW * IH * sizeof(ST)));
         tma_load_3d(s_in, &tmap, x0 - RA, y0 - RB, f, &s_bar);
+        // only this thread polls the barrier; the others sleep in bar.sync instead of spending issue slots on a spin loop
+        mbar_wait(&s_bar, 0);
     }
     __syncthreads();
-    mbar_wait(&s_bar, 0);
 
     const int tx0 = x0 - RA;
     const bool edge = (tx0 < 0) || (y0 - RB < 0) || (tx0 + SF_IW > p.W) || (y0 - RB + IH > p.H);
