@@ -125,6 +125,32 @@ __global__ void resize_tab_kernel(ResTab* xt, ResTab* yt, ResizeParams p)
     (is_y ? yt : xt)[d] = t;
 }
 
+
+// ---- 8-bit taps with word loads ---------------------------------------------------------------------------------------
+// The TAPS*CN bytes of one source row that a destination pixel needs are contiguous (away from the clamped image edges): read the
+// aligned 32-bit words covering them (one L1 wavefront each instead of one per byte), realign with funnel shifts, gather the two
+// bytes of a tap pair with one PRMT and multiply by the s16 coefficient pair with IDP2A (exact: |coef| <= 2^15, bytes <= 255).
+template <int NW>      // loads NW + 1 words starting at the word that holds byte A, returns the NW words starting AT byte A
+__device__ __forceinline__ void load_realigned(const uchar* row, unsigned A, unsigned* w)
+{
+    const unsigned* q = (const unsigned*)(row + (A & ~3u));
+    const unsigned sh8 = 8 * (A & 3u);
+    unsigned t[NW + 1];
+#pragma unroll
+    for (int i = 0; i <= NW; i++) t[i] = q[i];
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = __funnelshift_r(t[i], t[i + 1], sh8);
+}
+template <int CN> __device__ __forceinline__ unsigned rs_tap_pair(const unsigned* w, int c, int j0)
+{
+    const int p0 = c + j0 * CN, p1 = p0 + CN;
+    return __byte_perm(w[p0 >> 2], w[p1 >> 2], (unsigned)((p0 & 3) | ((4 + (p1 & 3)) << 4)));
+}
+__device__ __forceinline__ int rs_dp2a(int a, unsigned b, int c)
+{
+    int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
 constexpr int RS_ROWS = 8;   // destination rows per thread
 // (Two shared-memory tiled variants were measured and dropped: staging the footprint and filtering every source row once, with
 //  the intermediate rows in shared memory or in a per-thread register ring, ran at 12-24 resident warps per SM and were latency
@@ -141,6 +167,8 @@ __global__ void __launch_bounds__(256) resize_linear_kernel(Img src, Img dst, Re
     const ResTab tx = xt[x];
     const bool last_col = tx.last != 0;                    // dx >= xmax: D = S[sx] * ONE
     const size_t xo = (size_t)tx.s * CN;
+    const bool words_ok = sizeof(T) == 1 && (((uintptr_t)src.data | src.step | src.fstep) & 3) == 0;
+    const int row_bytes = p.sw * CN * (int)sizeof(T);
 #pragma unroll 2
     for (int r = 0; r < RS_ROWS; r++) {
         const int y = yb + r;
@@ -152,11 +180,24 @@ __global__ void __launch_bounds__(256) resize_linear_kernel(Img src, Img dst, Re
         T* d = dst.row<T>(f, y) + (size_t)x * CN;
         if constexpr (sizeof(T) == 1) {
             const int a0 = tx.ic[0], a1 = tx.ic[1], b0 = ty.ic[0], b1 = ty.ic[1];
+            constexpr int NW = (2 * CN + 3) / 4;
+            if (words_ok && !last_col && (int)xo + 2 * CN + 7 <= row_bytes) {          // the NW+1 words stay inside the row
+                const int a01 = (a0 & 0xffff) | (a1 << 16);
+                unsigned w0[NW], w1[NW];
+                load_realigned<NW>(src.row<uchar>(f, sy0), (unsigned)xo, w0);
+                load_realigned<NW>(src.row<uchar>(f, sy1), (unsigned)xo, w1);
 #pragma unroll
-            for (int c = 0; c < CN; c++) {
-                int t0 = last_col ? r0[c] * 2048 : r0[c] * a0 + r0[c + CN] * a1;
-                int t1 = last_col ? r1[c] * 2048 : r1[c] * a0 + r1[c + CN] * a1;
-                d[c] = (uchar)((((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2);
+                for (int c = 0; c < CN; c++) {
+                    const int t0 = rs_dp2a(a01, rs_tap_pair<CN>(w0, c, 0), 0), t1 = rs_dp2a(a01, rs_tap_pair<CN>(w1, c, 0), 0);
+                    d[c] = (uchar)((((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CN; c++) {
+                    int t0 = last_col ? r0[c] * 2048 : r0[c] * a0 + r0[c + CN] * a1;
+                    int t1 = last_col ? r1[c] * 2048 : r1[c] * a0 + r1[c + CN] * a1;
+                    d[c] = (uchar)((((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2);
+                }
             }
         } else {
             const float a0 = tx.fc[0], a1 = tx.fc[1], b0 = ty.fc[0], b1 = ty.fc[1];
@@ -229,6 +270,7 @@ __global__ void __launch_bounds__(256) resize_cubic_kernel(Img src, Img dst, Res
     const int f = blockIdx.z;
     if (x >= p.dw) return;
     const ResTab tx = xt[x];
+    const bool words_ok = sizeof(T) == 1 && (((uintptr_t)src.data | src.step | src.fstep) & 3) == 0;
     int xi[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) xi[j] = min(max(tx.s - 1 + j, 0), p.sw - 1) * CN;    // per-tap clamping == the while-loops of HResizeCubic
@@ -244,11 +286,26 @@ __global__ void __launch_bounds__(256) resize_cubic_kernel(Img src, Img dst, Res
         if constexpr (sizeof(T) == 1) {
             const int vec_limit = ((p.dw * CN) / 8) * 8;
             const float sc = 1.f / (2048.f * 2048.f);
+            constexpr int NW = (4 * CN + 3) / 4;
+            int tt[CN][4];
+            // taps contiguous (no edge clamping) and the NW+1 words inside the row: word loads + IDP2A
+            const bool fastx = words_ok && tx.s >= 1 && tx.s + 2 <= p.sw - 1 && (tx.s - 1) * CN + 4 * CN + 7 <= p.sw * CN;
+            if (fastx) {
+                const int c01 = (tx.ic[0] & 0xffff) | (tx.ic[1] << 16), c23 = (tx.ic[2] & 0xffff) | (tx.ic[3] << 16);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    unsigned w[NW];
+                    load_realigned<NW>(rows[k], (unsigned)((tx.s - 1) * CN), w);
+#pragma unroll
+                    for (int c = 0; c < CN; c++) tt[c][k] = rs_dp2a(c23, rs_tap_pair<CN>(w, c, 2), rs_dp2a(c01, rs_tap_pair<CN>(w, c, 0), 0));
+                }
+            }
 #pragma unroll
             for (int c = 0; c < CN; c++) {
                 int t[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
+                    if (fastx) { t[k] = tt[c][k]; continue; }
                     const uchar* rr = rows[k] + c;
                     t[k] = rr[xi[0]] * tx.ic[0] + rr[xi[1]] * tx.ic[1] + rr[xi[2]] * tx.ic[2] + rr[xi[3]] * tx.ic[3];
                 }
