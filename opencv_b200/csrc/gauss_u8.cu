@@ -35,14 +35,21 @@ struct GU8Params {
 
 __host__ __device__ constexpr bool gu_nz(int KB, int o, int g) { return 4 * g - o < KB; }
 
-template <int KB>
+// Interleaved channels: a row of W pixels x CN channels is a row of W*CN byte ELEMENTS whose horizontal taps are CN elements apart;
+// the column pass does not see channels at all.  Tile width in elements so that apron + tile + apron fits one 256-byte TMA box row.
+template <int CN> struct GUTile { static constexpr int TW = CN == 1 ? 192 : CN == 3 ? 160 : 128; };
+
+template <int KB, int CN>
 __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const __grid_constant__ CUtensorMap tmap, Img dst, const __grid_constant__ GU8Params p)
 {
+    constexpr int GU_TW = GUTile<CN>::TW;            // (shadows the single-channel constant)
     constexpr int RB = KB / 2;
-    constexpr int RA = 16;                           // left apron staged: TMA needs the box to start on a 16-byte boundary
-    constexpr int OFF = RA - RB;                     // tile column of (output column 0, tap 0)
+    constexpr int RBE = RB * CN;                     // horizontal apron in elements
+    constexpr int RA = ((RBE + 15) / 16) * 16;       // left apron staged: TMA needs the box to start on a 16-byte boundary
+    constexpr int OFF = RA - RBE;                    // tile column of (output column 0, tap 0)
     constexpr int GH = (KB + 3) / 4;                 // tap groups per row
     constexpr int GV = (KB + 3 + 3) / 4;             // row groups touched by one 4-row output group
+    static_assert(RA + GU_TW + RBE <= GU_IW, "apron + tile must fit the TMA box");
     __shared__ __align__(128) unsigned char s_in[GU_IW * GU_RG * 4];          // 256 x 64 bytes
     __shared__ __align__(16) uint32_t s_mid[GU_RG * 2 * GU_TW];               // [row pair][column]: (sum of row 2p, sum of row 2p+1) as 2 x u16
     __shared__ __align__(8) uint64_t s_bar;
@@ -77,31 +84,37 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const __grid_cons
         __syncthreads();
         {   // columns left of the image (tile columns [0, RA) of the first tile column) and right of it (from c_first on)
             const int c_first = p.W - tx0;
-            const int nright = c_first < GU_IW ? min(GU_IW - c_first, RB + 4) : 0;
+            const int nright = c_first < GU_IW ? min(GU_IW - c_first, RBE + 4) : 0;
             const int nleft = tx0 < 0 ? RA : 0;
             const int ncol = nleft + nright;
             for (int idx = tid; idx < IH * ncol; idx += 256) {
                 int r = idx / ncol, k = idx - r * ncol;
                 int c = k < nleft ? k : c_first + (k - nleft);
-                int sc = border_interpolate(tx0 + c, p.W, p.border) - tx0;
+                int sc;
+                if (CN == 1) sc = border_interpolate(tx0 + c, p.W, p.border) - tx0;
+                else {      // element -> (pixel, channel); the border rule acts on pixels
+                    const int e = tx0 + c, px = e >= 0 ? e / CN : -((-e + CN - 1) / CN), ch = e - px * CN;
+                    sc = border_interpolate(px, p.W / CN, p.border) * CN + ch - tx0;
+                }
                 if ((unsigned)sc < (unsigned)GU_IW) s_in[r * GU_IW + c] = s_in[r * GU_IW + sc];
             }
         }
         __syncthreads();
     }
 
-    // ---- row pass: item = 4 columns x 4 rows; 768 items = exactly 3 per thread; (rg, cg) advance without divisions ----
+    // ---- row pass: item = 4 columns x 4 rows; (rg, cg) advance without divisions ----
     {
-        constexpr int NCG = GU_TW / 4;                               // 48 column groups
+        constexpr int NCG = GU_TW / 4;                               // column groups (48 / 40 / 32)
         int rg = tid / NCG, cg = tid - rg * NCG;
-#pragma unroll
-        for (int rep = 0; rep < (NCG * GU_RG) / 256; rep++) {
+#pragma unroll 1
+        for (; rg < GU_RG; ) {
             uint32_t res[4][4];                                      // [row][col] 16-bit sums
             const uint32_t* wp0 = (const uint32_t*)(s_in + (rg * 4) * GU_IW + cg * 4);
 #pragma unroll
             for (int r = 0; r < 4; r++) {
                 const uint32_t* wp = wp0 + r * (GU_IW / 4);
-                constexpr int W0 = OFF / 4, W1 = (OFF + 3 + 4 * (GH - 1) + 3) / 4;
+                // last byte any (column b, tap) of this item touches: OFF + 3 + CN * (KB - 1)
+                constexpr int W0 = OFF / 4, W1 = (OFF + 3 + CN * (KB - 1)) / 4 + (CN == 1 ? 1 : 0);
                 uint32_t w[W1 - W0 + 1];
 #pragma unroll
                 for (int j = W0; j <= W1; j++) w[j - W0] = wp[j];
@@ -111,8 +124,19 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const __grid_cons
                     const uint32_t t = p.kxw[g];
 #pragma unroll
                     for (int b = 0; b < 4; b++) {
-                        const int tot = OFF + b + 4 * g, wi = tot / 4 - W0, sh = tot % 4;     // compile-time after unrolling
-                        const uint32_t win = sh == 0 ? w[wi] : __byte_perm(w[wi], w[wi + 1], sh == 1 ? 0x4321 : sh == 2 ? 0x5432 : 0x6543);
+                        uint32_t win;
+                        if constexpr (CN == 1) {
+                            const int tot = OFF + b + 4 * g, wi = tot / 4 - W0, sh = tot % 4;     // compile-time after unrolling
+                            win = sh == 0 ? w[wi] : __byte_perm(w[wi], w[wi + 1], sh == 1 ? 0x4321 : sh == 2 ? 0x5432 : 0x6543);
+                        } else {
+                            // taps 4g .. 4g+3 of output column b are CN bytes apart; taps beyond KB-1 carry zero weights: reuse the last real one
+                            int pos[4];
+#pragma unroll
+                            for (int q = 0; q < 4; q++) pos[q] = OFF + b + CN * (4 * g + q < KB ? 4 * g + q : KB - 1);
+                            const uint32_t lo = __byte_perm(w[pos[0] / 4 - W0], w[pos[1] / 4 - W0], (unsigned)((pos[0] & 3) | ((4 + (pos[1] & 3)) << 4)));
+                            const uint32_t hi = __byte_perm(w[pos[2] / 4 - W0], w[pos[3] / 4 - W0], (unsigned)((pos[2] & 3) | ((4 + (pos[3] & 3)) << 4)));
+                            win = __byte_perm(lo, hi, 0x5410);
+                        }
                         a[b] = __dp4a(win, t, a[b]);
                     }
                 }
@@ -203,20 +227,29 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const __grid_cons
     }
 }
 
-template <int KB>
-static int launch_gu8(const CUtensorMap& tm, const Img& d, const GU8Params& p, int frames, cudaStream_t st)
+template <int KB, int CN>
+static int launch_gu8_cn(const CUtensorMap& tm, const Img& d, const GU8Params& p, int frames, cudaStream_t st)
 {
-    dim3 grid(div_up((unsigned)p.W, GU_TW), div_up((unsigned)p.H, (unsigned)p.TH), (unsigned)frames);
-    gauss_u8_dp4a_kernel<KB><<<grid, 256, 0, st>>>(tm, d, p);
+    dim3 grid(div_up((unsigned)p.W, GUTile<CN>::TW), div_up((unsigned)p.H, (unsigned)p.TH), (unsigned)frames);
+    gauss_u8_dp4a_kernel<KB, CN><<<grid, 256, 0, st>>>(tm, d, p);
     cudaError_t e = cudaGetLastError();
     count_launch();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
     return B200CV_OK;
 }
 
-// returns B200CV_NOT_IMPLEMENTED when the fast path does not apply (caller falls back to the generic kernel)
-int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st, int sep_mode, int even_limit)
+template <int KB>
+static int launch_gu8(const CUtensorMap& tm, const Img& d, const GU8Params& p, int frames, int cn, cudaStream_t st)
 {
+    if (cn == 1) return launch_gu8_cn<KB, 1>(tm, d, p, frames, st);
+    if (cn == 3) return launch_gu8_cn<KB, 3>(tm, d, p, frames, st);
+    return launch_gu8_cn<KB, 4>(tm, d, p, frames, st);
+}
+
+// returns B200CV_NOT_IMPLEMENTED when the fast path does not apply (caller falls back to the generic kernel)
+int gauss_u8_fast(const Img& s, const Img& d, int cn, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st, int sep_mode, int even_limit)
+{
+    if (cn != 1 && cn != 3 && cn != 4) return B200CV_NOT_IMPLEMENTED;
     if (!(kw & 1) || !(kh & 1) || kw < 3 || kh < 3 || kw > 31 || kh > 31) return B200CV_NOT_IMPLEMENTED;
     if (border == B200CV_BORDER_WRAP) return B200CV_NOT_IMPLEMENTED;
     if (!tma_compatible(s) || s.rows >= 65536 * 4 || s.frames >= 65536) return B200CV_NOT_IMPLEMENTED;
@@ -242,24 +275,24 @@ int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const i
             for (int i = 0; i < 4; i++) { int j = 4 * g + i - o; if (j >= 0 && j < KB) w |= (uint32_t)ty[j] << (8 * i); }
             p.kyw[o][g] = w;
         }
-    p.W = s.cols; p.H = s.rows; p.border = border; p.sep_mode = sep_mode; p.even_limit = even_limit;
+    p.W = s.cols * cn; p.H = s.rows; p.border = border; p.sep_mode = sep_mode; p.even_limit = even_limit;      // W in byte elements
     p.TH = ((64 - (KB - 1)) / 4) * 4;
     CUtensorMap tm;
-    int rc = make_tensor_map_3d(&tm, s.data, 1, s.cols, s.rows, s.frames, s.step, s.fstep, GU_IW, p.TH + KB - 1);   // box start x0-16: 16-byte aligned
+    int rc = make_tensor_map_3d(&tm, s.data, 1, s.cols * cn, s.rows, s.frames, s.step, s.fstep, GU_IW, p.TH + KB - 1);   // box start x0-RA: 16-byte aligned
     if (rc) return rc;
     switch (KB) {
-    case 3: return launch_gu8<3>(tm, d, p, s.frames, st);
-    case 5: return launch_gu8<5>(tm, d, p, s.frames, st);
-    case 7: return launch_gu8<7>(tm, d, p, s.frames, st);
-    case 9: return launch_gu8<9>(tm, d, p, s.frames, st);
-    case 11: return launch_gu8<11>(tm, d, p, s.frames, st);
-    case 13: return launch_gu8<13>(tm, d, p, s.frames, st);
-    case 15: return launch_gu8<15>(tm, d, p, s.frames, st);
-    case 17: return launch_gu8<17>(tm, d, p, s.frames, st);
-    case 21: return launch_gu8<21>(tm, d, p, s.frames, st);
-    case 25: return launch_gu8<25>(tm, d, p, s.frames, st);
-    case 27: return launch_gu8<27>(tm, d, p, s.frames, st);
-    case 31: return launch_gu8<31>(tm, d, p, s.frames, st);
+    case 3: return launch_gu8<3>(tm, d, p, s.frames, cn, st);
+    case 5: return launch_gu8<5>(tm, d, p, s.frames, cn, st);
+    case 7: return launch_gu8<7>(tm, d, p, s.frames, cn, st);
+    case 9: return launch_gu8<9>(tm, d, p, s.frames, cn, st);
+    case 11: return launch_gu8<11>(tm, d, p, s.frames, cn, st);
+    case 13: return launch_gu8<13>(tm, d, p, s.frames, cn, st);
+    case 15: return launch_gu8<15>(tm, d, p, s.frames, cn, st);
+    case 17: return launch_gu8<17>(tm, d, p, s.frames, cn, st);
+    case 21: return launch_gu8<21>(tm, d, p, s.frames, cn, st);
+    case 25: return launch_gu8<25>(tm, d, p, s.frames, cn, st);
+    case 27: return launch_gu8<27>(tm, d, p, s.frames, cn, st);
+    case 31: return launch_gu8<31>(tm, d, p, s.frames, cn, st);
     }
     return B200CV_NOT_IMPLEMENTED;
 }

@@ -28,7 +28,7 @@ namespace b200cv {
 
 int sep_u8_float_fast(const Img& s, const Img& d, const float* kx, int nx, const float* ky, int ny, float delta, int border, cudaStream_t st);
 int sep_f32_fast(const Img& s, const Img& d, const float* kx, int nx, const float* ky, int ny, float delta, int border, const Img* dog, cudaStream_t st);
-int gauss_u8_fast(const Img& s, const Img& d, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st, int sep_mode = 0, int even_limit = 0);
+int gauss_u8_fast(const Img& s, const Img& d, int cn, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st, int sep_mode = 0, int even_limit = 0);
 
 enum { M_FLOAT = 0, M_FIXED16 = 1, M_INT = 2 };
 
@@ -521,12 +521,12 @@ int sep_filter_impl(const b200cvMat* src, const b200cvMat* dst, const float* kx,
                     if (di > INT32_MAX) di = INT32_MAX;
                     if (di < INT32_MIN) di = INT32_MIN;
                     const int even_limit = ny > 1 ? ((s.cols * cn) / 16) * 16 : 0;
-                    if (ddepth == B200CV_8U && cn == 1 && di == 0 && ax == nx / 2 && ay == ny / 2 && ny > 1) {   // TMA + IDP fast path (gauss_u8.cu)
+                    if (ddepth == B200CV_8U && di == 0 && ax == nx / 2 && ay == ny / 2 && ny > 1) {   // TMA + IDP fast path (gauss_u8.cu)
                         int64_t qx[32], qy[32];
                         if (nx <= 31 && ny <= 31) {
                             for (int i = 0; i < nx; i++) qx[i] = (int64_t)ikx[i];
                             for (int i = 0; i < ny; i++) qy[i] = (int64_t)iky[i];
-                            int frc = gauss_u8_fast(s, d, qx, nx, qy, ny, border, st, 1, even_limit);
+                            int frc = gauss_u8_fast(s, d, cn, qx, nx, qy, ny, border, st, 1, even_limit);
                             if (frc != B200CV_NOT_IMPLEMENTED) return frc;
                         }
                     }
@@ -701,8 +701,8 @@ int b200cv::gaussian_blur_impl(const b200cvMat* src, const b200cvMat* dst, int k
         B200_REQUIRE(src->data != dst->data, "in-place filtering is not supported: pass distinct buffers");
         B200_REQUIRE(src->cols == dst->cols && src->rows == dst->rows, "src/dst size mismatch");
         if (b < 0 || b > B200CV_BORDER_REFLECT_101) return B200CV_NOT_IMPLEMENTED;
-        if (B200CV_CN(src->type) == 1) {      // TMA + IDP4A fast path (gauss_u8.cu); declines what it cannot do
-            int frc = gauss_u8_fast(s, d, fx.data(), kw, fy.data(), kh, b, as_stream(stream));
+        {      // TMA + IDP fast path (gauss_u8.cu); declines what it cannot do
+            int frc = gauss_u8_fast(s, d, B200CV_CN(src->type), fx.data(), kw, fy.data(), kh, b, as_stream(stream));
             if (frc != B200CV_NOT_IMPLEMENTED) return frc;
         }
         return sep_dispatch<uchar, uchar, M_FIXED16>(s, d, B200CV_CN(src->type), kx.data(), kw, ky.data(), kh, kw / 2, kh / 2,

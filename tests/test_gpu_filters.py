@@ -30,6 +30,24 @@ def test_gaussian_u8_bitexact(cvb, oracle, rng, shape, ks):
         assert_exact(got, want, "GaussianBlur u8 %s k=%d s=%g border=%d" % (shape, k, s, b))
 
 
+@pytest.mark.parametrize("shape", [(70, 400, 3), (131, 1072, 3), (33, 112, 4), (90, 516, 4)])
+@pytest.mark.parametrize("ks", [(3, 0), (5, 0), (7, 1.4), (13, 0), (21, 3.3), (31, 5.0)])
+def test_gaussian_u8_multichannel_tma_path(cvb, oracle, rng, shape, ks):
+    """8UC3 / 8UC4 rows whose pitch is a multiple of 16 bytes run the IDP kernel on byte elements (taps CN elements apart); several
+    tiles per row, every border mode, plus the 8.8 fixed-point sepFilter2D mode.  Bit-exact."""
+    h, w, cn = shape
+    img = rand_u8(rng, h, w, cn)
+    k, s = ks
+    for b in BORDERS:
+        if b == 3:
+            continue                              # BORDER_WRAP stays on the generic kernel
+        assert_exact(cpu(cvb.GaussianBlur(gpu(img), (k, k), s, s, b)), oracle.GaussianBlur(img, (k, k), s, s, b),
+                     "GaussianBlur u8 %s k=%d s=%g border=%d" % (shape, k, s, b))
+    tri = (1 + k // 2 - np.abs(np.arange(k) - k // 2)).astype(np.float32); tri /= tri.sum()
+    if np.all(tri * 256 == np.rint(tri * 256)):
+        assert_exact(cpu(cvb.sepFilter2D(gpu(img), -1, tri, tri)), oracle.sepFilter2D(img, -1, tri, tri), "sepFilter2D fixed mode %s k=%d" % (shape, k))
+
+
 def test_gaussian_u8_rect_kernel_and_batch(cvb, oracle, rng):
     imgs = np.stack([rand_u8(rng, 120, 333) for _ in range(3)])[..., None]
     got = cpu(cvb.GaussianBlur(gpu(imgs), (7, 3), 1.2, 0.7, 4))
