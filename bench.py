@@ -50,7 +50,12 @@ def gauss_taps(k):
 def build_ops(workload, rng):
     """returns (ops, description).  Each op: name, kind, args, src spec (shape, dtype), dst spec, px, algo_bytes per frame"""
     ops = []
-    if workload == "c2":
+    if workload == "c1":
+        nb = 64
+        ops.append(dict(name="GaussianBlur_8UC3_1080p_k5", kind="gauss", k=5, src=((nb, 1080, 1920, 3), np.uint8), dst=((nb, 1080, 1920, 3), np.uint8),
+                        px=1920 * 1080, abytes=1920 * 1080 * 6, frames=nb))
+        desc = "C1: GaussianBlur 5x5 on 1920x1080 8UC3 (the reference's own CPU-runnable case), 64 frames per launch"
+    elif workload == "c2":
         for depth, nb, es in (("u8", 16, 1), ("f32", 8, 4)):
             dt = np.uint8 if depth == "u8" else np.float32
             for k in K_SWEEP:
@@ -260,7 +265,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from the host each step instead of replaying a captured CUDA graph")
     ap.add_argument("--no-cpu", action="store_true")
