@@ -38,12 +38,15 @@ static int ensure(void** p, size_t* cap, size_t bytes)
 
 static inline size_t pitch_of(const b200cvMat* m) { return ((size_t)m->cols * elem_size(m->type) + 255) & ~(size_t)255; }
 
+void configure_mem_pool();     // runtime.cu
+
 typedef std::function<int(const b200cvMat*, const b200cvMat*, void*)> DevOp;
 
 // Generic pipeline: src/dst are HOST descriptors (batches allowed); frames flow in chunks through NPIPE streams.
 static int host_pipeline(const b200cvMat* hsrc, const b200cvMat* hdst, const DevOp& op)
 {
     int rc;
+    configure_mem_pool();
     if ((rc = check_mat(hsrc, "src")) || (rc = check_mat(hdst, "dst"))) return rc;
     const int frames = hsrc->frames > 1 ? hsrc->frames : 1;
     B200_REQUIRE((hdst->frames > 1 ? hdst->frames : 1) == frames, "src/dst batch mismatch");
