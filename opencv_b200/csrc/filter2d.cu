@@ -193,7 +193,9 @@ extern "C" int b200cv_filter2d(const b200cvMat* src, const b200cvMat* dst, const
     B200_REQUIRE(s.frames == d.frames, "src/dst batch mismatch");
     cudaStream_t st = as_stream(stream);
     float fd = (float)delta;
-    if (sd == B200CV_8U && cn == 1 && kw * kh >= (dd == B200CV_32F ? 50 : 121)) {
+    const char* tc_env = getenv("B200CV_FILTER2D_TC_MIN_TAPS");          // test hook: lower / raise the tensor-core threshold
+    const int tc_min_taps = tc_env ? atoi(tc_env) : 0;
+    if (sd == B200CV_8U && cn == 1 && kw * kh >= (tc_min_taps ? tc_min_taps : dd == B200CV_32F ? 50 : 121)) {
         // the sizes where the reference leaves the direct sum for a DFT (filter.dispatch.cpp:1288): tensor-core correlation
         const char* path = getenv("B200CV_FILTER2D_PATH");
         if (!(path && !strcmp(path, "direct"))) {
