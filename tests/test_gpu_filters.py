@@ -6,7 +6,8 @@ Tolerances
     (same operation order: centre-out small rows, mirrored-pair columns, FMA); the last W*cn mod 8 (float source) / mod 16 (8-bit
     source) elements of each row are the reference's scalar remainder loops: |d| <= 1e-4 + 1e-5 |ref| there (the reference's own
     bar for the whole image: test_filter.cpp:826-830 uses 1e-5 relative)
-  filter2D u8: <= 1 LSB (the CPU uses a DFT for >= 130 taps; its own test allows 2, test_filter.cpp:420-425)
+  filter2D u8: BIT-EXACT below 130 taps (the CPU's direct float sum, reproduced in operation order); <= 1 LSB from 130 taps on, where
+    the CPU uses a DFT (its own test allows 2, test_filter.cpp:420-425) and the GPU an exact fixed-point tensor-core correlation
 """
 import numpy as np
 import pytest
@@ -166,7 +167,11 @@ def test_filter2d(cvb, oracle, rng, k):
     img = rand_u8(rng, 97, 131); f = img.astype(np.float32)
     ker = rng.random((k, k)).astype(np.float32); ker /= ker.sum()
     for b in (0, 1, 2, 4):
-        assert_close(cpu(cvb.filter2D(gpu(img), -1, ker, borderType=b)), oracle.filter2D(img, -1, ker, borderType=b), atol=1, what="filter2D u8 k=%d b=%d" % (k, b))
+        got = cpu(cvb.filter2D(gpu(img), -1, ker, borderType=b)); want = oracle.filter2D(img, -1, ker, borderType=b)
+        if k * k < 130:     # the reference evaluates the direct float sum: same operation order here, bit-exact
+            assert_exact(got, want, "filter2D u8 k=%d b=%d" % (k, b))
+        else:               # the reference switches to a float DFT (filter.dispatch.cpp:1288): +-1 LSB at ties
+            assert_close(got, want, atol=1, what="filter2D u8 k=%d b=%d" % (k, b))
         assert_close(cpu(cvb.filter2D(gpu(f), -1, ker, borderType=b)), oracle.filter2D(f, -1, ker, borderType=b), atol=5e-4, rtol=1e-5,
                      what="filter2D f32 k=%d b=%d" % (k, b))
 
@@ -177,7 +182,7 @@ def test_filter2d_tensor_core(cvb, oracle, rng, monkeypatch):
     M/N tiles and frames, signed taps, off-centre anchor, delta, every destination depth."""
     import os
     img = rng.integers(0, 256, (3, 301, 263, 1), dtype=np.uint8)       # batch of 3 frames, > 1 M-tile pair and > 4 N-tiles
-    for (kh, kw), anchor, delta in (((11, 11), (-1, -1), 0.0), ((13, 17), (2, 9), 3.5), ((31, 31), (-1, -1), 0.0), ((5, 33), (30, 1), -2.0)):
+    for (kh, kw), anchor, delta in (((11, 13), (-1, -1), 0.0), ((13, 17), (2, 9), 3.5), ((31, 31), (-1, -1), 0.0), ((5, 33), (30, 1), -2.0)):
         ker = (rng.random((kh, kw)).astype(np.float32) - 0.25); ker /= np.abs(ker).sum() * 0.5
         for b in (0, 1, 2, 4):
             got = cpu(cvb.filter2D(gpu(img), -1, ker, anchor=anchor, delta=delta, borderType=b))
@@ -215,13 +220,17 @@ def test_filter2d_tma_path(cvb, oracle, rng, ksz, monkeypatch):
         gotf = cpu(cvb.filter2D(fview, -1, ker, delta=1.25, borderType=b))
         got32 = cpu(cvb.filter2D(view, 5, ker, borderType=b))
         monkeypatch.setenv("B200CV_FILTER2D_PATH", "v1")
-        if kw * kh < 121:       # larger 8-bit kernels take the tensor-core path unless told otherwise
+        if kw * kh < 130:       # larger 8-bit kernels take the tensor-core path unless told otherwise
             assert_exact(got, cpu(cvb.filter2D(view, -1, ker, delta=1.25, borderType=b)), "filter2D tma vs v1 u8 %s b=%d" % (ksz, b))
             assert_exact(got32, cpu(cvb.filter2D(view, 5, ker, borderType=b)), "filter2D tma vs v1 u8->f32 %s b=%d" % (ksz, b))
         assert_exact(gotf, cpu(cvb.filter2D(fview, -1, ker, delta=1.25, borderType=b)), "filter2D tma vs v1 f32 %s b=%d" % (ksz, b))
         monkeypatch.delenv("B200CV_FILTER2D_PATH")
         for i in range(2):
-            assert_close(got[i, :, :, 0], oracle.filter2D(img[i, :, :, 0], -1, ker, delta=1.25, borderType=b), atol=1, what="filter2D tma u8 %s b=%d" % (ksz, b))
+            want = oracle.filter2D(img[i, :, :, 0], -1, ker, delta=1.25, borderType=b)
+            if kw * kh < 130:
+                assert_exact(got[i, :, :, 0], want, "filter2D tma u8 %s b=%d" % (ksz, b))
+            else:
+                assert_close(got[i, :, :, 0], want, atol=1, what="filter2D tma u8 %s b=%d" % (ksz, b))
         assert_close(gotf, oracle.filter2D(fimg, -1, ker, delta=1.25, borderType=b), atol=5e-4, rtol=1e-5, what="filter2D tma f32 %s b=%d" % (ksz, b))
 
 
