@@ -1,7 +1,8 @@
 // filter2d.cu -- cv::filter2D: correlation with an arbitrary kh x kw float kernel.
 //
 // Reference arithmetic (Filter2D<ST,CastOp,VecOp>, modules/imgproc/src/filter.simd.hpp:3103-3175): per output
-//   s = (float)delta; for every non-zero tap in row-major order: s = fma(k, src, s); dst = saturate_cast<DT>(s).
+//   s = (float)delta; for every non-zero tap in row-major order: s = fma(k, src, s); dst = saturate_cast<DT>(s)
+//   (8-bit source with a float destination: the scalar FilterNoVec object, s += round(k * src), no FMA).
 // (The CPU switches to a DFT for >= 130 taps, filter.dispatch.cpp:1288; the GPU evaluates the direct sum for every
 //  size, which is the more accurate of the two -- parity tolerance per modules/imgproc/test/test_filter.cpp:420-425.)
 //
@@ -64,7 +65,10 @@ __global__ void __launch_bounds__(256) filter2d_fast_kernel(Img src, Img dst, co
 #pragma unroll
                     for (int o = 0; o < F2_R; o++) {
                         const int i = e - o;
-                        if (i >= 0 && i < KB) acc[o] = fmaf(kr[i], vals[b], acc[o]);
+                        if (i >= 0 && i < KB) {
+                            if constexpr (sizeof(ST) == 1 && sizeof(DT) == 4) acc[o] = __fadd_rn(acc[o], __fmul_rn(kr[i], vals[b]));   // scalar FilterNoVec: no FMA
+                            else acc[o] = fmaf(kr[i], vals[b], acc[o]);
+                        }
                     }
                 }
             }
@@ -108,7 +112,10 @@ __global__ void __launch_bounds__(256) filter2d_generic_kernel(Img src, Img dst,
         for (int ky = 0; ky < p.kh; ky++) {
             const float* s = s_in + (r + ky) * in_w + e;
             const float* kr = p.k + ky * p.kstride;
-            for (int kx = 0; kx < p.kw; kx++) acc = fmaf(kr[kx], s[kx * cn], acc);
+            for (int kx = 0; kx < p.kw; kx++) {
+                if constexpr (sizeof(ST) == 1 && sizeof(DT) == 4) acc = __fadd_rn(acc, __fmul_rn(kr[kx], s[kx * cn]));   // scalar FilterNoVec: no FMA
+                else acc = fmaf(kr[kx], s[kx * cn], acc);
+            }
         }
         dst.row<DT>(f, gy)[xe] = OutCast<DT>::from(acc);
     }

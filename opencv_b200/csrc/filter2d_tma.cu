@@ -132,7 +132,11 @@ __global__ void __launch_bounds__(256, 2) filter2d_tma_kernel(const __grid_const
             for (int i = 0; i < KB; i++) {
                 const float t = kr[i];
 #pragma unroll
-                for (int o = 0; o < 8; o++) acc[o] = fmaf(t, win[OFF + o + i], acc[o]);
+                for (int o = 0; o < 8; o++) {
+                    // 8-bit source with a float destination is the reference's scalar FilterNoVec: products rounded before the add
+                    if constexpr (sizeof(ST) == 1 && sizeof(DT) == 4) acc[o] = __fadd_rn(acc[o], __fmul_rn(t, win[OFF + o + i]));
+                    else acc[o] = fmaf(t, win[OFF + o + i], acc[o]);
+                }
             }
         }
         ft_store8<DT>(dst.row<DT>(f, gy) + gx, acc, dvec, min(8, p.W - gx));

@@ -259,7 +259,9 @@ PORT_API int port_filter2d(const void* src, size_t sstep, void* dst, size_t dste
                         if (kv == 0) continue;
                         int sx = port_border(x + i - ax, w, border);
                         float v = (row && sx >= 0) ? load_f(row, sdepth, sx * cn + c) : 0.f;
-                        s = fmaf(kv, v, s);
+                        /* 8-bit source, float destination: the reference runs the scalar Filter2D<uchar, Cast<float,float>, FilterNoVec>, whose
+                           products are rounded before they are added (filter.simd.hpp:3160-3172); every other pair has a vector body with FMA */
+                        s = (sdepth == P_8U && ddepth == P_32F) ? s + mul_rn(kv, v) : fmaf(kv, v, s);
                     }
                 }
                 store_f(drow, ddepth, x * cn + c, s);
