@@ -95,7 +95,7 @@ static float mul_rn(float a, float b) { volatile float p = a * b; return p; }   
                                                                  SymmColumnVec_32f / _32f8u, :1878-1949, :1158-1202
             col_mode 0: any other kernel runs the scalar ColumnFilter, which is not contracted:
               s = fma(ky[0], S[0], delta); s += round(ky[j]*S[j])   :2590-2640 (as compiled: only the delta term is fused)
-   The last (w*cn mod 8) elements of a float->float row come from the reference's scalar remainder loops, whose rounding depends on
+   The last (w*cn mod 8) elements of a float-source row (mod 32 for an 8-bit source feeding a float intermediate) come from the reference's scalar remainder loops, whose rounding depends on
    how its compiler contracted each of them; this port uses the formulas above there too (differences <= 1 ulp, tests/ mask them). */
 static void sep_float(const void* src, size_t sstep, void* dst, size_t dstep, int w, int h, int cn, int sdepth, int ddepth,
                       const float* kx, int nx, const float* ky, int ny, int ax, int ay, float delta, int border, int col_mode, int row_mode)

@@ -34,7 +34,10 @@ def test_resize_f32(cvb, oracle, rng, ssz, dsz, cn, interp):
     img = rand_u8(rng, ssz[0], ssz[1], cn).astype(np.float32)
     want = oracle.resize(img, (dsz[1], dsz[0]), interp)
     got = cpu(cvb.resize(gpu(img), (dsz[1], dsz[0]), interpolation=interp))
-    assert_close(got, want, atol=1e-4, rtol=1e-6, what="resize f32 %s->%s cn=%d interp=%d" % (ssz, dsz, cn, interp))
+    assert_exact(got, want, "resize f32 %s->%s cn=%d interp=%d" % (ssz, dsz, cn, interp))      # same float operations in the same order
+    frac = (rand_u8(rng, ssz[0], ssz[1], cn).astype(np.float32) + 0.37) * 0.731                # non-integer data: rounding shows
+    assert_exact(cpu(cvb.resize(gpu(frac), (dsz[1], dsz[0]), interpolation=interp)), oracle.resize(frac, (dsz[1], dsz[0]), interp),
+                 "resize f32 (fractional data) %s->%s cn=%d interp=%d" % (ssz, dsz, cn, interp))
 
 
 @pytest.mark.parametrize("interp", [C.INTER_LINEAR, C.INTER_AREA])
@@ -94,12 +97,13 @@ def test_warp_perspective_u8(cvb, oracle, rng, cn, interp, border):
 @pytest.mark.parametrize("interp", [C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC])
 @pytest.mark.parametrize("border", [C.BORDER_CONSTANT, C.BORDER_REPLICATE, C.BORDER_REFLECT])
 def test_warp_f32(cvb, oracle, rng, interp, border):
-    img = rand_u8(rng, 131, 157, 1).astype(np.float32)
+    img = (rand_u8(rng, 131, 157, 1).astype(np.float32) + 0.37) * 0.731
     M = _rot(oracle, 157, 131)
-    assert_close(cpu(cvb.warpAffine(gpu(img), M, (170, 140), interp, border, 7.5)), oracle.warpAffine(img, M, (170, 140), interp, border, 7.5),
-                 atol=2e-4, what="warpAffine f32 interp=%d border=%d" % (interp, border))
-    assert_close(cpu(cvb.warpPerspective(gpu(img), H0, (170, 140), interp, border, 7.5)), oracle.warpPerspective(img, H0, (170, 140), interp, border, 7.5),
-                 atol=2e-4, what="warpPerspective f32 interp=%d border=%d" % (interp, border))
+    # float sums in the reference's order (remapBilinear / remapBicubic incl. its two cubic formulas): bit-exact
+    assert_exact(cpu(cvb.warpAffine(gpu(img), M, (170, 140), interp, border, 7.5)), oracle.warpAffine(img, M, (170, 140), interp, border, 7.5),
+                 "warpAffine f32 interp=%d border=%d" % (interp, border))
+    assert_exact(cpu(cvb.warpPerspective(gpu(img), H0, (170, 140), interp, border, 7.5)), oracle.warpPerspective(img, H0, (170, 140), interp, border, 7.5),
+                 "warpPerspective f32 interp=%d border=%d" % (interp, border))
 
 
 def test_sift_upsample_warp(cvb, oracle, rng):

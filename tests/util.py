@@ -40,7 +40,7 @@ def assert_exact_body(got, want, lanes, atol=0.0, rtol=0.0, what=""):
     """Float separable filters reproduce the operation order of the reference's SIMD loops, so every row element the reference
     computes in a full vector is bit-identical.  The last (W*cn mod lanes) elements of a row come from the reference's scalar
     remainder loops, whose rounding depends on how its compiler contracted them: those are held to the tolerance instead.
-    lanes = 8 for float sources, 16 for 8-bit sources (filter.simd.hpp row/column loops)."""
+    lanes = 8 for float sources, 32 for 8-bit sources (measured against the reference build: filter.simd.hpp row/column loops)."""
     got = np.asarray(got); want = np.asarray(want)
     assert got.shape == want.shape, "%s: shape %s vs %s" % (what, got.shape, want.shape)
     g2 = got.reshape(got.shape[0], -1) if got.ndim <= 3 else got.reshape(got.shape[0] * got.shape[1], -1)
