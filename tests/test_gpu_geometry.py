@@ -4,7 +4,7 @@ Bars (the reference's own strict test allows |d| <= 1 for LINEAR/CUBIC, test_img
   resize NEAREST, LINEAR u8, AREA 2x2 u8, CUBIC u8 ......... BIT-EXACT (the SSE vector-body / scalar-tail split of the
                                                              reference's u8 CUBIC column pass is reproduced)
   warp* u8 (NEAREST/LINEAR/CUBIC) .......................... BIT-EXACT (fixed-point coordinates + 2^15 tap tables)
-  f32 ...................................................... |d| <= 1e-4 (values 0..255): same operation order, fp32
+  f32 (resize and warps, every interpolation and border) ... BIT-EXACT: same float operations in the same order
 """
 import numpy as np
 import pytest
