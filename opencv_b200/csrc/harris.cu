@@ -65,8 +65,20 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
         int r = idx / cw, c = idx - r * cw;
         const float* row = s_src + r * sw_ + c;
         float rx = 0.f, ry = 0.f;
+        // Same operation order as the reference's Sobel = sepFilter2D (filter.simd.hpp, see sep_f32.cu): 8-bit rows and 7-tap float
+        // rows in tap order with FMA; 3/5-tap float rows centre-out (Dx row kernel antisymmetric, Dy row kernel symmetric)
+        if constexpr (sizeof(ST) == 4 && KS <= 5) {
+            constexpr int m = KS / 2;
+            rx = __fmul_rn(__fsub_rn(row[m + 1], row[m - 1]), p.dxk_x[m + 1]);
+            ry = fmaf(row[m], p.dyk_x[m], __fmul_rn(__fadd_rn(row[m - 1], row[m + 1]), p.dyk_x[m + 1]));
+            if constexpr (KS == 5) {
+                rx = fmaf(__fsub_rn(row[m + 2], row[m - 2]), p.dxk_x[m + 2], rx);
+                ry = fmaf(__fadd_rn(row[m - 2], row[m + 2]), p.dyk_x[m + 2], ry);
+            }
+        } else {
 #pragma unroll
-        for (int i = 0; i < KS; i++) { rx = fmaf(row[i], p.dxk_x[i], rx); ry = fmaf(row[i], p.dyk_x[i], ry); }
+            for (int i = 0; i < KS; i++) { rx = fmaf(row[i], p.dxk_x[i], rx); ry = fmaf(row[i], p.dyk_x[i], ry); }
+        }
         s_rx[idx] = rx; s_ry[idx] = ry;
     }
     __syncthreads();
@@ -75,11 +87,13 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
         int r = idx / cw, c = idx - r * cw;
         int gx = cx0 + c, gy = cy0 + r;
         if ((unsigned)gx >= (unsigned)W || (unsigned)gy >= (unsigned)H) continue;
-        float dx = 0.f, dy = 0.f;
+        // columns: mirrored rows first (Dx column kernel symmetric, Dy column kernel antisymmetric; delta = 0)
+        constexpr int m = KS / 2;
+        float dx = fmaf(p.dxk_y[m], s_rx[(r + m) * cw + c], 0.f), dy = 0.f;
 #pragma unroll
-        for (int j = 0; j < KS; j++) {
-            dx = fmaf(s_rx[(r + j) * cw + c], p.dxk_y[j], dx);
-            dy = fmaf(s_ry[(r + j) * cw + c], p.dyk_y[j], dy);
+        for (int j = 1; j <= m; j++) {
+            dx = fmaf(p.dxk_y[m + j], __fadd_rn(s_rx[(r + m + j) * cw + c], s_rx[(r + m - j) * cw + c]), dx);
+            dy = fmaf(p.dyk_y[m + j], __fsub_rn(s_ry[(r + m + j) * cw + c], s_ry[(r + m - j) * cw + c]), dy);
         }
         s_a[idx] = __fmul_rn(dx, dx); s_b[idx] = __fmul_rn(dx, dy); s_c[idx] = __fmul_rn(dy, dy);
     }
@@ -125,7 +139,7 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
         if (p.op == 0) {
             float acbb = __fsub_rn(__fmul_rn(fa, fc), __fmul_rn(fb, fb));
             float ac = __fadd_rn(fa, fc);
-            out = __fsub_rn(acbb, __fmul_rn(__fmul_rn(p.k, ac), ac));
+            out = __fsub_rn(acbb, __fmul_rn(p.k, __fmul_rn(ac, ac)));     // calcHarrisLine_AVX: k * ((a+c)*(a+c)), no FMA (corner.avx.cpp:145-160)
         } else {
             float ha = __fmul_rn(fa, 0.5f), hc = __fmul_rn(fc, 0.5f);
             float t = __fsub_rn(ha, hc);

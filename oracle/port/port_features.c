@@ -93,7 +93,8 @@ static int corner_impl(const void* src, size_t sstep, int w, int h, int type, fl
                 sa += ra; sb += rb; sc += rc;
             }
             float fa = (float)sa, fb = (float)sb, fc = (float)sc, out;
-            if (op == 0) { float acbb = fa * fc - fb * fb, ac = fa + fc; out = acbb - ((float)k * ac) * ac; }
+            /* calcHarrisLine_AVX (corner.avx.cpp:145-160, plain AVX object: no FMA): (a*c - b*b) - k*((a+c)*(a+c)) */
+            if (op == 0) { float acbb = fa * fc - fb * fb, ac = fa + fc; out = acbb - (float)k * (ac * ac); }
             else { float ha = fa * 0.5f, hc = fc * 0.5f, t = ha - hc; t = fb * fb + t * t; out = (ha + hc) - sqrtf(t); }
             ((float*)((char*)dst + (size_t)y * dstep))[x] = out;
         }
