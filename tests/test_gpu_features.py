@@ -87,7 +87,7 @@ def test_good_features(cvb, oracle, rng, harris, mind):
     got, gq = cvb.goodFeaturesToTrack(gpu(img), 200, 0.01, mind, 3, 3, harris, 0.04, with_quality=True)
     assert len(got) == len(want), "corner count %d vs %d" % (len(got), len(want))
     # same set; same order wherever neighbouring responses are separated by more than the fp32 noise of the response map
-    assert_close(gq, wq, atol=3e-6 * float(np.abs(wq).max()), what="corner qualities")
+    assert_close(gq, wq, atol=5e-7 * float(np.abs(wq).max()), what="corner qualities")
     same = np.all(got == want, axis=1)
     if not same.all():
         gs = set(map(tuple, got.tolist())); ws = set(map(tuple, want.tolist()))
@@ -113,11 +113,19 @@ def test_sift_pyramid(cvb, oracle, rng, shape, upscale):
     no = len(dims)
     assert no == len(wg)
     gg, gd = unpack_pyramid(cpu(G)[0], cpu(D)[0], dims.reshape(-1), no, 3)
+    exact = True     # octaves are bit-exact as long as no level so far had remainder columns (width % 8) in the reference's SIMD loops
     for o in range(no):
+        exact = exact and wg[o][0].shape[1] % 8 == 0
         for i in range(6):
-            assert_close(gg[o][i], wg[o][i], atol=1e-3, what="gauss o=%d i=%d" % (o, i))
+            if exact:
+                assert_exact(gg[o][i], wg[o][i], "gauss o=%d i=%d" % (o, i))
+            else:
+                assert_close(gg[o][i], wg[o][i], atol=1e-4, what="gauss o=%d i=%d" % (o, i))
         for i in range(5):
-            assert_close(gd[o][i], wd[o][i], atol=1e-3, what="dog o=%d i=%d" % (o, i))
+            if exact:
+                assert_exact(gd[o][i], wd[o][i], "dog o=%d i=%d" % (o, i))
+            else:
+                assert_close(gd[o][i], wd[o][i], atol=1e-4, what="dog o=%d i=%d" % (o, i))
             # the fused DoG must be exactly the f32 difference of the two stored Gaussian levels
             assert_exact(gd[o][i], gg[o][i + 1] - gg[o][i], "dog == G[i+1]-G[i] o=%d i=%d" % (o, i))
 
@@ -130,6 +138,12 @@ def test_sift_pyramid_batch_1080p(cvb, ref, rng):
     for f in (0, 2):
         wg, wd = ref.sift_pyramid(batch[f, :, :, 0], 3, 1.6, True)
         gg, gd = unpack_pyramid(cpu(G)[f], cpu(D)[f], dims.reshape(-1), len(dims), 3)
+        exact = True
         for o in range(len(dims)):
-            assert_close(gg[o][5], wg[o][5], atol=1e-3, what="frame %d gauss o=%d" % (f, o))
-            assert_close(gd[o][4], wd[o][4], atol=1e-3, what="frame %d dog o=%d" % (f, o))
+            exact = exact and wg[o][0].shape[1] % 8 == 0
+            if exact:      # 1920, 960, 480, 240, 120 wide: the whole level equals the reference bit for bit
+                assert_exact(gg[o][5], wg[o][5], "frame %d gauss o=%d" % (f, o))
+                assert_exact(gd[o][4], wd[o][4], "frame %d dog o=%d" % (f, o))
+            else:
+                assert_close(gg[o][5], wg[o][5], atol=1e-4, what="frame %d gauss o=%d" % (f, o))
+                assert_close(gd[o][4], wd[o][4], atol=1e-4, what="frame %d dog o=%d" % (f, o))
