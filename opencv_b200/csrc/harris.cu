@@ -53,16 +53,23 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
     const int cx0 = x0 - p.ba, cy0 = y0 - p.ba;                   // image coordinates of cov region origin
     const int W = src.cols, H = src.rows;
 
-    for (int idx = threadIdx.x; idx < sw_ * sh_; idx += 256) {
-        int r = idx / sw_, c = idx - r * sw_;
-        int sy = border_interpolate(cy0 - rs + r, H, p.border);
-        int sx = border_interpolate(cx0 - rs + c, W, p.border);
-        s_src[idx] = (sy < 0 || sx < 0) ? 0.f : (float)src.row<ST>(f, sy)[sx];
+    // one warp per staged row, lanes over columns (no per-element division); interior tiles skip the border arithmetic
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool interior = cx0 - rs >= 0 && cy0 - rs >= 0 && cx0 - rs + sw_ <= W && cy0 - rs + sh_ <= H;
+    for (int r = warp; r < sh_; r += 8) {
+        const int sy = interior ? cy0 - rs + r : border_interpolate(cy0 - rs + r, H, p.border);
+        const ST* srow = sy >= 0 ? src.row<ST>(f, sy) : nullptr;
+        float* drow = s_src + r * sw_;
+        for (int c = lane; c < sw_; c += 32) {
+            const int sx = interior ? cx0 - rs + c : border_interpolate(cx0 - rs + c, W, p.border);
+            drow[c] = (srow && sx >= 0) ? (float)srow[sx] : 0.f;
+        }
     }
     __syncthreads();
     // row pass (both derivative filters share the staged source row)
-    for (int idx = threadIdx.x; idx < sh_ * cw; idx += 256) {
-        int r = idx / cw, c = idx - r * cw;
+    for (int r = warp; r < sh_; r += 8)
+    for (int c = lane; c < cw; c += 32) {
+        const int idx = r * cw + c;
         const float* row = s_src + r * sw_ + c;
         float rx = 0.f, ry = 0.f;
         // Same operation order as the reference's Sobel = sepFilter2D (filter.simd.hpp, see sep_f32.cu): 8-bit rows and 7-tap float
@@ -83,8 +90,9 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
     }
     __syncthreads();
     // column pass + products at the in-image positions of the cov region
-    for (int idx = threadIdx.x; idx < cw * ch; idx += 256) {
-        int r = idx / cw, c = idx - r * cw;
+    for (int r = warp; r < ch; r += 8)
+    for (int c = lane; c < cw; c += 32) {
+        const int idx = r * cw + c;
         int gx = cx0 + c, gy = cy0 + r;
         if ((unsigned)gx >= (unsigned)W || (unsigned)gy >= (unsigned)H) continue;
         // columns: mirrored rows first (Dx column kernel symmetric, Dy column kernel antisymmetric; delta = 0)
