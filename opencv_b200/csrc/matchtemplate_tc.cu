@@ -30,7 +30,6 @@ constexpr int TC_MT = 2;          // M-tiles (of 128 rows) per CTA
 constexpr int TC_NS = 4;          // B ring stages
 constexpr int TC_BBYTES = TC_N * TC_K;   // 8192
 
-enum { EPI_CCORR = 0, EPI_U8 = 1, EPI_F32 = 2, EPI_S16 = 3 };
 
 // B_v in smem/global: [k-chunk c (8)][column j (64)][16 bytes]: byte b = T(v, 16c + b - j)
 __global__ void toeplitz_kernel(Img templ, int w, int h, unsigned char* out)
@@ -111,13 +110,11 @@ struct TCParams {
     int h, ra_alloc, box_h, nbox;       // template rows; staged image rows (allocated), rows per TMA box, boxes per column chunk
     int ow, oh;
     int kch;                            // K per template row = 32 * kch (w + N - 1 <= 32 * kch)
-    float scale, delta;                 // filter2D epilogue: value = sum * scale + delta
 };
 
-template <int NB, int EPI>     // NB = digit planes of the B operand (MMA N = 64 NB)
 __global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ bglob, Img res, TCParams p)
 {
-    constexpr int NN = TC_N * NB;                                      // MMA N
+    constexpr int NN = TC_N;                                           // MMA N
     constexpr int TCOLS = TC_MT * NN <= 128 ? 128 : TC_MT * NN <= 256 ? 256 : 512;   // TMEM columns (power of two)
     extern __shared__ __align__(128) unsigned char smem[];
     const int nchunk = 2 * p.kch;                                      // 16-byte K chunks per row
@@ -158,9 +155,9 @@ __global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const __grid_constant_
         }
     } else if (warp == 1 && lane == 0) {
         // ---- MMA issuer ----
-        // instruction descriptor: D = S32 (2<<4), A = unsigned 8 bit (0 at [7,10)), B = unsigned (0) or signed (1) 8 bit at [10,13),
+        // instruction descriptor: D = S32 (2<<4), A = B = unsigned 8 bit (0 at [7,10) and [10,13)),
         // K-major both, N>>3 at [17,23), M>>4 at [24,29)
-        const uint32_t idesc = (2u << 4) | ((EPI == EPI_CCORR ? 0u : 1u) << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc = (2u << 4) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         mbar_wait(&a_full, 0);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
@@ -194,52 +191,13 @@ __global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const __grid_constant_
         for (int half = 0; half < 2; half++) {
             uint32_t r[32];
             tmem_ld32(trow + half * 32, r);
-            if constexpr (EPI == EPI_CCORR) {
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float* rp = gy < p.oh ? res.row<float>(f, gy) + x0 : nullptr;
-                if (rp) {
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        int gx = x0 + half * 32 + j;
-                        if (gx < p.ow) rp[half * 32 + j] = (float)(int)r[j];
-                    }
-                }
-            } else {
-                uint32_t r1[32], r2[32];
-                tmem_ld32(trow + TC_N + half * 32, r1);
-                tmem_ld32(trow + 2 * TC_N + half * 32, r2);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float v[32];
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float* rp = gy < p.oh ? res.row<float>(f, gy) + x0 : nullptr;
+            if (rp) {
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    long long sum = (long long)(int)r[j] + ((long long)(int)r1[j] << 8) + ((long long)(int)r2[j] << 16);
-                    v[j] = __fadd_rn(__fmul_rn(__ll2float_rn(sum), p.scale), p.delta);
-                }
-                if (gy < p.oh) {
-                    const int gx0 = x0 + half * 32;
-                    if constexpr (EPI == EPI_U8) {
-                        uchar* dp = res.row<uchar>(f, gy) + gx0;
-                        if (gx0 + 32 <= p.ow && ((uintptr_t)dp & 15) == 0) {
-                            uint32_t w[8];
-#pragma unroll
-                            for (int j = 0; j < 8; j++)
-                                w[j] = (uint32_t)sat_u8(v[4 * j]) | ((uint32_t)sat_u8(v[4 * j + 1]) << 8) | ((uint32_t)sat_u8(v[4 * j + 2]) << 16) |
-                                       ((uint32_t)sat_u8(v[4 * j + 3]) << 24);
-                            ((uint4*)dp)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                            ((uint4*)dp)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; j++) if (gx0 + j < p.ow) dp[j] = sat_u8(v[j]);
-                        }
-                    } else if constexpr (EPI == EPI_S16) {
-                        short* dp = res.row<short>(f, gy) + gx0;
-#pragma unroll
-                        for (int j = 0; j < 32; j++) if (gx0 + j < p.ow) dp[j] = sat_s16(v[j]);
-                    } else {
-                        float* dp = res.row<float>(f, gy) + gx0;
-#pragma unroll
-                        for (int j = 0; j < 32; j++) if (gx0 + j < p.ow) dp[j] = v[j];
-                    }
+                    int gx = x0 + half * 32 + j;
+                    if (gx < p.ow) rp[half * 32 + j] = (float)(int)r[j];
                 }
             }
         }
@@ -255,7 +213,7 @@ int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, c
     if (w > TC_K - TC_N + 1 || h > 512 || !tma_compatible(im) || im.frames >= 65536) return B200CV_NOT_IMPLEMENTED;
     const int ow = im.cols - w + 1, oh = im.rows - h + 1;
     TCParams p;
-    p.h = h; p.ow = ow; p.oh = oh; p.kch = TC_K / 32; p.scale = 1.f; p.delta = 0.f;
+    p.h = h; p.ow = ow; p.oh = oh; p.kch = TC_K / 32;
     int ra = 128 * TC_MT + h - 1;
     p.nbox = (ra + 255) / 256;
     p.box_h = (((ra + p.nbox - 1) / p.nbox) + 7) & ~7;
@@ -263,7 +221,7 @@ int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, c
     size_t smem = (size_t)8 * p.ra_alloc * 16 + (size_t)TC_NS * TC_BBYTES;
     if (smem > 200 * 1024) return B200CV_NOT_IMPLEMENTED;
     static bool attr = false;
-    if (!attr) { B200_CUDA(cudaFuncSetAttribute(ccorr_u8_tc_kernel<1, EPI_CCORR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+    if (!attr) { B200_CUDA(cudaFuncSetAttribute(ccorr_u8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
     unsigned char* bglob = nullptr;
     B200_CUDA(cudaMallocAsync(&bglob, (size_t)h * TC_BBYTES, st));
     toeplitz_kernel<<<h, 256, 0, st>>>(tp, w, h, bglob);
@@ -272,7 +230,7 @@ int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, c
     int rc = make_tensor_map_3d(&tm, im.data, 1, im.cols, im.rows, im.frames, im.step, im.fstep, 16, p.box_h);
     if (rc) { cudaFreeAsync(bglob, st); return rc; }
     dim3 grid(div_up((unsigned)ow, TC_N), div_up((unsigned)oh, 128 * TC_MT), (unsigned)im.frames);
-    ccorr_u8_tc_kernel<1, EPI_CCORR><<<grid, 128, smem, st>>>(tm, bglob, rs, p);
+    ccorr_u8_tc_kernel<<<grid, 128, smem, st>>>(tm, bglob, rs, p);
     cudaError_t e = cudaGetLastError();
     cudaFreeAsync(bglob, st);
     count_launch();
