@@ -103,7 +103,10 @@ __global__ void __launch_bounds__(256, 2) filter2d_tma_kernel(const __grid_const
             v.y = __fsub_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7651)), 8388608.0f);
             v.z = __fsub_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7652)), 8388608.0f);
             v.w = __fsub_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7653)), 8388608.0f);
-            ((float4*)s_f)[idx] = v;
+            // 16-byte chunks of a float row are stored XOR-swizzled (chunk c -> c ^ ((c >> 3) & 1)): a thread's window starts 32 bytes after
+            // its neighbour's, so un-swizzled 128-bit loads of 8 adjacent lanes would hit every bank twice (ncu: 93 M conflicts at 7x7)
+            const int row = idx / (FT_IW / 4), c = idx - row * (FT_IW / 4);
+            ((float4*)s_f)[row * (FT_IW / 4) + (c ^ ((c >> 3) & 1))] = v;
         }
         __syncthreads();
     }
@@ -123,11 +126,16 @@ __global__ void __launch_bounds__(256, 2) filter2d_tma_kernel(const __grid_const
         for (int o = 0; o < 8; o++) acc[o] = p.delta;
 #pragma unroll 1
         for (int ky = p.ky0; ky < p.ky1; ky++) {
-            const float4* vp = (const float4*)(s_f + (r + ky) * FT_IW + g * 8);
+            const float4* vp = (const float4*)(s_f + (r + ky) * FT_IW);
             const float* kr = p.k + ky * KB;
             float win[NV * 4];
 #pragma unroll
-            for (int w = 0; w < NV; w++) { const float4 q = vp[w]; win[4 * w] = q.x; win[4 * w + 1] = q.y; win[4 * w + 2] = q.z; win[4 * w + 3] = q.w; }
+            for (int w = 0; w < NV; w++) {
+                int c = g * 2 + w;
+                if constexpr (sizeof(ST) == 1) c ^= (c >> 3) & 1;              // swizzled by the widening pass (8-bit sources only)
+                const float4 q = vp[c];
+                win[4 * w] = q.x; win[4 * w + 1] = q.y; win[4 * w + 2] = q.z; win[4 * w + 3] = q.w;
+            }
 #pragma unroll
             for (int i = 0; i < KB; i++) {
                 const float t = kr[i];

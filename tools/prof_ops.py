@@ -23,6 +23,7 @@ M = np.array([[0.8911, 0.1094, 182.0], [-0.1094, 0.8911, 655.0]])
 templ = u8[0, 700:764, 1000:1064, 0].contiguous()
 g3 = np.array([0.2, 0.55, 0.25], np.float32)
 g5 = np.array([0.1, 0.2, 0.35, 0.25, 0.1], np.float32)
+g7 = cvb.getGaussianKernel(7, 1.3).astype(np.float32).ravel()
 g11 = cvb.getGaussianKernel(11, 0).astype(np.float32).ravel()
 g31 = cvb.getGaussianKernel(31, 0).astype(np.float32).ravel()
 ops = {
@@ -46,6 +47,8 @@ ops = {
     "filter2d_u8_k31": lambda: cvb.filter2D(u8, -1, np.outer(g31, g31), dst=o8),
     "filter2d_u8_k11": lambda: cvb.filter2D(u8, -1, np.outer(g11, g11), dst=o8),
     "filter2d_f32_k31": lambda: cvb.filter2D(f32, -1, np.outer(g31, g31), dst=o32),
+    "filter2d_u8_k7": lambda: cvb.filter2D(u8, -1, np.outer(g7, g7), dst=o8),
+    "filter2d_u8_k11d": lambda: cvb.filter2D(u8, -1, np.outer(g11, g11) + 1e-4, dst=o8),
     "filter2d_u8_k3": lambda: cvb.filter2D(u8, -1, np.outer(g3, g3), dst=o8),
     "filter2d_f32_k5": lambda: cvb.filter2D(f32, -1, np.outer(g5, g5), dst=o32),
     "warp_cub": lambda: cvb.warpAffine(bgr, M, (7680, 4320), 2, dst=obgr),
