@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256, 2) filter2d_tma_kernel(const __grid_const
     constexpr int IH = FT_TH + KB - 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_f = (float*)smem_raw;                                   // IH x FT_IW floats
-    ST* s_in = sizeof(ST) == 4 ? (ST*)smem_raw : (ST*)(smem_raw + (size_t)IH * FT_IW * 4);    // 8-bit: raw tile behind the float tile
+    ST* s_in = (ST*)(smem_raw + (size_t)IH * FT_IW * 4);            // raw TMA tile behind the (swizzled) float tile
     __shared__ __align__(8) uint64_t s_bar;
     const int f = blockIdx.z, x0 = blockIdx.x * FT_TW, y0 = blockIdx.y * FT_TH;
     const int tid = threadIdx.x;
@@ -94,22 +94,23 @@ __global__ void __launch_bounds__(256, 2) filter2d_tma_kernel(const __grid_const
         }
         __syncthreads();
     }
-    if constexpr (sizeof(ST) == 1) {
-        // widen once: 4 bytes -> 4 floats per step
-        for (int idx = tid; idx < IH * (FT_IW / 4); idx += 256) {
+    // Build the float tile.  Its 16-byte chunks are stored XOR-swizzled (chunk c -> c ^ ((c >> 3) & 1)): a thread's window starts 32 bytes
+    // after its neighbour's, so un-swizzled 128-bit loads of 8 adjacent lanes would hit every bank twice (ncu: 93 M conflicts at 7x7).
+    for (int idx = tid; idx < IH * (FT_IW / 4); idx += 256) {
+        float4 v;
+        if constexpr (sizeof(ST) == 1) {      // widen: 4 bytes -> 4 floats (PRMT into the mantissa of 2^23, no I2F)
             const uint32_t q = ((const uint32_t*)s_in)[idx];
-            float4 v;
             v.x = __fsub_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7650)), 8388608.0f);
             v.y = __fsub_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7651)), 8388608.0f);
             v.z = __fsub_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7652)), 8388608.0f);
             v.w = __fsub_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7653)), 8388608.0f);
-            // 16-byte chunks of a float row are stored XOR-swizzled (chunk c -> c ^ ((c >> 3) & 1)): a thread's window starts 32 bytes after
-            // its neighbour's, so un-swizzled 128-bit loads of 8 adjacent lanes would hit every bank twice (ncu: 93 M conflicts at 7x7)
-            const int row = idx / (FT_IW / 4), c = idx - row * (FT_IW / 4);
-            ((float4*)s_f)[row * (FT_IW / 4) + (c ^ ((c >> 3) & 1))] = v;
+        } else {
+            v = ((const float4*)s_in)[idx];
         }
-        __syncthreads();
+        const int row = idx / (FT_IW / 4), c = idx - row * (FT_IW / 4);
+        ((float4*)s_f)[row * (FT_IW / 4) + (c ^ ((c >> 3) & 1))] = v;
     }
+    __syncthreads();
 
     // ---- item = 8 consecutive outputs of one row; the kernel rows stream through a register window ----
     constexpr int GPR = FT_TW / 8;
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256, 2) filter2d_tma_kernel(const __grid_const
 #pragma unroll
             for (int w = 0; w < NV; w++) {
                 int c = g * 2 + w;
-                if constexpr (sizeof(ST) == 1) c ^= (c >> 3) & 1;              // swizzled by the widening pass (8-bit sources only)
+                c ^= (c >> 3) & 1;
                 const float4 q = vp[c];
                 win[4 * w] = q.x; win[4 * w + 1] = q.y; win[4 * w + 2] = q.z; win[4 * w + 3] = q.w;
             }
@@ -155,7 +156,7 @@ template <int KB, typename ST, typename DT>
 static int launch_ft(const CUtensorMap& tm, const Img& d, const FTParams& p, int frames, cudaStream_t st)
 {
     constexpr int IH = FT_TH + KB - 1;
-    const size_t smem = (size_t)IH * FT_IW * 4 + (sizeof(ST) == 1 ? (size_t)IH * FT_IW : 0);
+    const size_t smem = (size_t)IH * FT_IW * 4 + (size_t)IH * FT_IW * sizeof(ST);
     auto kern = filter2d_tma_kernel<KB, ST, DT>;
     static bool attr = false;
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }

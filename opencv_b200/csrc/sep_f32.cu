@@ -77,10 +77,12 @@ __global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(co
         __syncthreads();
     }
 
-    // ---- row pass: item = 8 consecutive outputs of one staged row ----
+    // ---- row pass: item = NO consecutive outputs of one staged row.  Float rows: NO = 4, so that neighbouring lanes read neighbouring
+    //      16-byte chunks (8 outputs = 32-byte lane stride made every 128-bit shared load a 2-way bank conflict); byte rows: NO = 8 ----
     {
-        constexpr int GPR = SF_TW / 8;                    // 24 items per row
-        constexpr int NEED = 8 + KB - 1;
+        constexpr int NO = sizeof(ST) == 4 ? 4 : 8;
+        constexpr int GPR = SF_TW / NO;                   // items per row
+        constexpr int NEED = NO + KB - 1;
         constexpr int NV = (OFF + NEED + 3) / 4;
 #pragma unroll 1
         for (int it = tid; it < IH * GPR; it += 256) {
@@ -90,21 +92,21 @@ __global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(co
             for (int w = 0; w < NV; w++) {
                 if constexpr (sizeof(ST) == 1) {
                     // bytes -> floats through the mantissa of 2^23 (PRMT + FADD instead of the quarter-rate I2F)
-                    const uint32_t q = ((const uint32_t*)(s_in + r * SF_IW + g * 8))[w];
+                    const uint32_t q = ((const uint32_t*)(s_in + r * SF_IW + g * NO))[w];
 #pragma unroll
                     for (int b = 0; b < 4; b++) win[w * 4 + b] = __fsub_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7650 + b)), 8388608.0f);
                 } else {
-                    const float4 q = ((const float4*)(s_in + r * SF_IW + g * 8))[w];
+                    const float4 q = ((const float4*)(s_in + r * SF_IW + g * NO))[w];
                     win[w * 4] = q.x; win[w * 4 + 1] = q.y; win[w * 4 + 2] = q.z; win[w * 4 + 3] = q.w;
                 }
             }
-            float acc[8];
+            float acc[NO];
             bool done = false;
             if constexpr (KB <= 5 && sizeof(ST) == 4) {
                 if (p.row_small) {
                     const unsigned sg = p.row_small == 2 ? 0x80000000u : 0u;
 #pragma unroll
-                    for (int o = 0; o < 8; o++) {
+                    for (int o = 0; o < NO; o++) {
                         const float* x = win + OFF + o + RB;      // centre tap
                         // symmetric: fma(x0, k0, (x-1 + x1) k1); antisymmetric: (x1 - x-1) k1  (k0 = 0: fma(x0, 0, t) = t)
                         float t = __fmul_rn(__fadd_rn(x[1], __uint_as_float(__float_as_uint(x[-1]) ^ sg)), p.kx[RB + 1]);
@@ -117,16 +119,16 @@ __global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(co
             }
             if (!done) {
 #pragma unroll
-                for (int o = 0; o < 8; o++) {
+                for (int o = 0; o < NO; o++) {
                     float t = 0.f;
 #pragma unroll
                     for (int i = 0; i < KB; i++) t = fmaf(win[OFF + o + i], p.kx[i], t);
                     acc[o] = t;
                 }
             }
-            float4* mp = (float4*)(s_mid + r * SF_TW + g * 8);
+            float4* mp = (float4*)(s_mid + r * SF_TW + g * NO);
             mp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            mp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            if constexpr (NO == 8) mp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
     }
     __syncthreads();
