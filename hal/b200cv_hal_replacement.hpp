@@ -33,6 +33,8 @@
 #define cv_hal_warpAffine b200cv_hal_warpAffine
 #undef cv_hal_warpPerspective
 #define cv_hal_warpPerspective b200cv_hal_warpPerspective
+#undef cv_hal_remap32f
+#define cv_hal_remap32f b200cv_hal_remap32f
 #undef cv_hal_cvtBGRtoBGR
 #define cv_hal_cvtBGRtoBGR b200cv_hal_cvtBGRtoBGR
 #undef cv_hal_cvtBGRtoGray

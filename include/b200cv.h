@@ -58,6 +58,7 @@ extern "C" {
 
 /* depth / type codes (== CV_8U ...) */
 #define B200CV_8U 0
+#define B200CV_16U 2
 #define B200CV_16S 3
 #define B200CV_32F 5
 #define B200CV_MAKETYPE(depth, cn) (((depth) & 7) + (((cn) - 1) << 3))
@@ -77,6 +78,7 @@ extern "C" {
 #define B200CV_INTER_CUBIC 2
 #define B200CV_INTER_AREA 3
 #define B200CV_WARP_INVERSE_MAP 16
+#define B200CV_WARP_RELATIVE_MAP 32
 
 #define B200CV_TM_SQDIFF 0
 #define B200CV_TM_SQDIFF_NORMED 1
@@ -160,6 +162,12 @@ B200CV_API int b200cv_warp_affine(const b200cvMat* src, const b200cvMat* dst, co
 /* replaces cv::warpPerspective (imgproc.hpp:2482; imgwarp.cpp:3370-3466). M: 3x3 doubles. */
 B200CV_API int b200cv_warp_perspective(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags,
                                        int border, const double* border_value, void* stream);
+/* replaces cv::remap (imgproc.hpp:2531; imgwarp.cpp:1762-1900, RemapInvoker :1096-1330) -- SURVEY 8(f) "next": the caller of the
+ * sampling code the warps already use.  dst has the size of the maps and the type of src.  Maps (one set for the whole batch):
+ *   map1 CV_32FC1 + map2 CV_32FC1 (x and y planes), map1 CV_32FC2 (map2 NULL), or the fixed-point pair of cv::convertMaps
+ *   map1 CV_16SC2 + map2 CV_16UC1 (map2 may be NULL for INTER_NEAREST).  WARP_RELATIVE_MAP is not implemented. */
+B200CV_API int b200cv_remap(const b200cvMat* src, const b200cvMat* dst, const b200cvMat* map1, const b200cvMat* map2, int interpolation,
+                            int border, const double* border_value, void* stream);
 /* replaces cv::cvtColor (imgproc.hpp:3736; color.cpp:192-400) for BGR/RGB(A) <-> GRAY / YUV / YCrCb / HSV(_FULL) / BGR(A) */
 B200CV_API int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int code, void* stream);
 /* replaces cv::matchTemplate (imgproc.hpp:3916; templmatch.cpp:1158-1194), 1-channel u8/f32, all six methods.

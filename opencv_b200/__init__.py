@@ -292,6 +292,21 @@ def warpPerspective(src, M, dsize, flags=INTER_LINEAR, borderMode=BORDER_CONSTAN
     return _warp(lib().b200cv_warp_perspective, "warpPerspective", src, M, dsize, flags, borderMode, borderValue, dst, stream, 9)
 
 
+def remap(src, map1, map2, interpolation, borderMode=BORDER_CONSTANT, borderValue=0, dst=None, stream=None):
+    """cv::remap (imgproc.hpp:2531).  map1/map2: float32 (H,W) planes, map1 float32 (H,W,2) with map2=None, or the fixed-point pair of
+    cv::convertMaps: map1 int16 (H,W,2) + map2 int16/None (H,W).  dst takes the size of the maps."""
+    m1 = describe(map1)
+    dst = dst if dst is not None else _new(src, size=(m1.cols, m1.rows))
+    ms, md = _pair(src, dst)
+    m2 = describe(map2) if map2 is not None else None
+    bv = np.zeros(4, np.float64)
+    b = np.atleast_1d(np.asarray(borderValue, np.float64))
+    bv[:len(b)] = b
+    _check(lib().b200cv_remap(ctypes.byref(ms), ctypes.byref(md), ctypes.byref(m1), ctypes.byref(m2) if m2 is not None else None, int(interpolation),
+                              int(borderMode), bv.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), _stream_ptr(stream)), "remap")
+    return dst
+
+
 def matchTemplate(image, templ, method, result=None, stream=None):
     """cv::matchTemplate (imgproc.hpp:3916): image (H,W) / (N,H,W,1), templ (h,w); result float32 (H-h+1, W-w+1)"""
     import torch

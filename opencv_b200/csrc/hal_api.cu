@@ -257,6 +257,33 @@ extern "C" int b200cv_hal_warpPerspective(int type, const uchar* src, size_t sst
     return b200cv_host_warp_perspective(&s, &d, M, interp | B200CV_WARP_INVERSE_MAP, border, bv);
 }
 
+extern "C" int b200cv_host_remap(const b200cvMat* src, const b200cvMat* dst, const b200cvMat* map1, const b200cvMat* map2, int interp, int border, const double* bv)
+{
+    int rc;
+    if ((rc = check_mat(map1, "map1"))) return rc;
+    const bool has2 = map2 && map2->data;
+    if (has2 && (rc = check_mat(map2, "map2"))) return rc;
+    // the maps are uploaded once (aux buffer), the frames flow through the pipeline
+    HostCtx& c = g_ctx;
+    const size_t p1 = pitch_of(map1), p2 = has2 ? pitch_of(map2) : 0;
+    const size_t b1 = p1 * map1->rows, b2 = has2 ? p2 * map2->rows : 0;
+    if ((rc = ensure(&c.daux, &c.caux, b1 + b2))) return rc;
+    B200_CUDA(cudaMemcpy2D(c.daux, p1, map1->data, map1->step, (size_t)map1->cols * elem_size(map1->type), map1->rows, cudaMemcpyHostToDevice));
+    if (has2) B200_CUDA(cudaMemcpy2D((char*)c.daux + b1, p2, map2->data, map2->step, (size_t)map2->cols * elem_size(map2->type), map2->rows, cudaMemcpyHostToDevice));
+    b200cvMat d1 = {c.daux, p1, map1->cols, map1->rows, map1->type, 1, 0};
+    b200cvMat d2 = {has2 ? (void*)((char*)c.daux + b1) : nullptr, p2, has2 ? map2->cols : 0, has2 ? map2->rows : 0, has2 ? map2->type : 0, 1, 0};
+    return host_pipeline(src, dst, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_remap(a, b, &d1, has2 ? &d2 : nullptr, interp, border, bv, st); });
+}
+
+extern "C" int b200cv_hal_remap32f(int type, const uchar* src, size_t sstep, int sw, int sh, uchar* dst, size_t dstep, int dw, int dh,
+                                   float* mapx, size_t mapx_step, float* mapy, size_t mapy_step, int interp, int border, const double bv[4])
+{
+    if (src == dst) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, sw, sh, type), d = hmat(dst, dstep, dw, dh, type);
+    b200cvMat mx = hmat(mapx, mapx_step, dw, dh, B200CV_MAKETYPE(B200CV_32F, 1)), my = hmat(mapy, mapy_step, dw, dh, B200CV_MAKETYPE(B200CV_32F, 1));
+    return b200cv_host_remap(&s, &d, &mx, &my, interp, border, bv);
+}
+
 static int cvt(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, int dcn, int code)
 {
     if (depth != B200CV_8U) return B200CV_NOT_IMPLEMENTED;

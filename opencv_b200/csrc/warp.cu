@@ -465,6 +465,51 @@ static int launch_warp(int interp, const Img& s, const Img& d, const WarpParams&
     return launch_warp_i<T, CN, W_CUB>(s, d, p, st);
 }
 
+
+// ---- cv::remap: coordinates come from maps instead of a matrix; sampling is the warps' (RemapInvoker, imgwarp.cpp:1096-1330) -----------
+enum { MAP_PLANAR_F32 = 0, MAP_PACKED_F32 = 1, MAP_FIXED = 2 };
+
+// cvRound / v_round on x86: round-to-nearest-even, the "integer indefinite" 0x80000000 for NaN and values outside int32
+__device__ __forceinline__ int x86_round(float v) { return fabsf(v) < 2147483648.f ? __float2int_rn(v) : (int)0x80000000; }
+
+template <typename T, int CN, int INTERP>
+__global__ void __launch_bounds__(256) remap_kernel(Img src, Img dst, Img m1, Img m2, const __grid_constant__ WarpParams p, int kind)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, f = blockIdx.z;
+    if (x >= p.dw) return;
+    int sx, sy, a = 0;
+    if (kind == MAP_FIXED) {
+        const short* xy = m1.row<short>(0, y) + 2 * x;
+        const int fr = m2.data ? (m2.row<unsigned short>(0, y)[x] & 1023) : 0;
+        if (INTERP == W_NN) {       // NNDeltaTab_i as the reference fills it: +1 where the 5-bit fraction is BELOW 1/2 (:237-238, :1176-1181)
+            sx = (short)(xy[0] + ((fr & 31) < 16)); sy = (short)(xy[1] + ((fr >> 5) < 16));
+        } else { sx = xy[0]; sy = xy[1]; a = fr; }
+    } else {
+        float mx, my;
+        if (kind == MAP_PLANAR_F32) { mx = m1.row<float>(0, y)[x]; my = m2.row<float>(0, y)[x]; }
+        else { const float2 q = ((const float2*)m1.row<float>(0, y))[x]; mx = q.x; my = q.y; }
+        if (INTERP == W_NN) { sx = sat_s16(x86_round(mx)); sy = sat_s16(x86_round(my)); }       // saturate_cast<short>(float), :1195-1216
+        else {                                                                                   // :1253-1283
+            const int ix = x86_round(__fmul_rn(mx, 32.f)), iy = x86_round(__fmul_rn(my, 32.f));
+            sx = sat_s16(ix >> 5); sy = sat_s16(iy >> 5);
+            a = (iy & 31) * 32 + (ix & 31);
+        }
+    }
+    sample_direct<T, CN, INTERP>(src, f, p, sx, sy, a, dst.row<T>(f, y) + (size_t)x * CN);
+}
+
+template <typename T, int CN>
+static int launch_remap(int interp, const Img& s, const Img& d, const Img& m1, const Img& m2, const WarpParams& p, int kind, cudaStream_t st)
+{
+    dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
+    if (interp == W_NN) remap_kernel<T, CN, W_NN><<<grid, 256, 0, st>>>(s, d, m1, m2, p, kind);
+    else if (interp == W_LIN) remap_kernel<T, CN, W_LIN><<<grid, 256, 0, st>>>(s, d, m1, m2, p, kind);
+    else remap_kernel<T, CN, W_CUB><<<grid, 256, 0, st>>>(s, d, m1, m2, p, kind);
+    B200_LAUNCH_CHECK();
+    return B200CV_OK;
+}
+
 static int warp_common(const b200cvMat* src, const b200cvMat* dst, const double* Minv, int persp, int flags, int border,
                        const double* bv, void* stream)
 {
@@ -549,4 +594,56 @@ extern "C" int b200cv_warp_perspective(const b200cvMat* src, const b200cvMat* ds
         }
     }
     return warp_common(src, dst, M, 1, flags, border, border_value, stream);
+}
+
+extern "C" int b200cv_remap(const b200cvMat* src, const b200cvMat* dst, const b200cvMat* map1, const b200cvMat* map2, int interpolation,
+                            int border, const double* bv, void* stream)
+{
+    int rc;
+    if ((rc = check_mat(src, "src")) || (rc = check_mat(dst, "dst")) || (rc = check_mat(map1, "map1"))) return rc;
+    if (map2 && map2->data && (rc = check_mat(map2, "map2"))) return rc;
+    B200_REQUIRE(src->type == dst->type, "remap: dst type must equal src type");
+    B200_REQUIRE(src->data != dst->data, "remap: in-place is not supported");
+    B200_REQUIRE(dst->cols == map1->cols && dst->rows == map1->rows, "remap: dst must have the size of the maps");
+    if (interpolation & B200CV_WARP_RELATIVE_MAP) return B200CV_NOT_IMPLEMENTED;
+    const bool has2 = map2 && map2->data;
+    if (has2) B200_REQUIRE(map2->cols == map1->cols && map2->rows == map1->rows, "remap: map sizes differ");
+    int kind;
+    const int t1 = map1->type, t2 = has2 ? map2->type : -1;
+    if (t1 == B200CV_MAKETYPE(B200CV_32F, 1) && t2 == B200CV_MAKETYPE(B200CV_32F, 1)) kind = MAP_PLANAR_F32;
+    else if (t1 == B200CV_MAKETYPE(B200CV_32F, 2) && !has2) kind = MAP_PACKED_F32;
+    else if (t1 == B200CV_MAKETYPE(B200CV_16S, 2) && (t2 == B200CV_MAKETYPE(B200CV_16U, 1) || t2 == B200CV_MAKETYPE(B200CV_16S, 1) || !has2)) kind = MAP_FIXED;
+    else return B200CV_NOT_IMPLEMENTED;
+    const int depth = B200CV_DEPTH(src->type), cn = B200CV_CN(src->type);
+    if ((depth != B200CV_8U && depth != B200CV_32F) || (cn != 1 && cn != 3 && cn != 4)) return B200CV_NOT_IMPLEMENTED;
+    int interp = interpolation & 7;
+    if (interp == B200CV_INTER_AREA) interp = B200CV_INTER_LINEAR;            // imgwarp.cpp:1826
+    if (interp > B200CV_INTER_CUBIC) return B200CV_NOT_IMPLEMENTED;
+    if (kind == MAP_FIXED && !has2 && interp != B200CV_INTER_NEAREST) return B200CV_ERR_BAD_ARG;
+    border &= ~B200CV_BORDER_ISOLATED;
+    if (border < 0 || border > B200CV_BORDER_REFLECT_101) return B200CV_NOT_IMPLEMENTED;
+    if (src->cols >= 32767 || src->rows >= 32767 || dst->cols >= 32767 || dst->rows >= 32767) return B200CV_NOT_IMPLEMENTED;   // CV_Assert(... < SHRT_MAX), :1810
+    if ((rc = ensure_warp_tables())) return rc;
+    Img s = make_img(src), d = make_img(dst), m1 = make_img(map1), m2;
+    memset(&m2, 0, sizeof(m2));
+    if (has2) m2 = make_img(map2);
+    B200_REQUIRE(s.frames == d.frames, "src/dst batch mismatch");
+    WarpParams p;
+    memset(&p, 0, sizeof(p));
+    for (int c = 0; c < 4; c++) {
+        double v = bv ? bv[c] : 0.0;
+        long r = lrint(v);
+        p.cval_i[c] = (int)(r < 0 ? 0 : r > 255 ? 255 : r);
+        p.cval_f[c] = (float)v;
+    }
+    p.sw = src->cols; p.sh = src->rows; p.dw = dst->cols; p.dh = dst->rows; p.border = border; p.bw0 = 1;
+    cudaStream_t st = as_stream(stream);
+    if (depth == B200CV_8U) {
+        if (cn == 1) return launch_remap<uchar, 1>(interp, s, d, m1, m2, p, kind, st);
+        if (cn == 3) return launch_remap<uchar, 3>(interp, s, d, m1, m2, p, kind, st);
+        return launch_remap<uchar, 4>(interp, s, d, m1, m2, p, kind, st);
+    }
+    if (cn == 1) return launch_remap<float, 1>(interp, s, d, m1, m2, p, kind, st);
+    if (cn == 3) return launch_remap<float, 3>(interp, s, d, m1, m2, p, kind, st);
+    return launch_remap<float, 4>(interp, s, d, m1, m2, p, kind, st);
 }

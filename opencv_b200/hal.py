@@ -11,7 +11,7 @@ import numpy as np
 
 from . import (BORDER_CONSTANT, BORDER_DEFAULT, INTER_LINEAR, CV_8U, CV_16S, CV_32F, Mat, _check, lib, make_type, _CVT_DCN)
 
-_DEPTH = {np.dtype(np.uint8): CV_8U, np.dtype(np.int16): CV_16S, np.dtype(np.float32): CV_32F}
+_DEPTH = {np.dtype(np.uint8): CV_8U, np.dtype(np.uint16): 2, np.dtype(np.int16): CV_16S, np.dtype(np.float32): CV_32F}
 _NP = {CV_8U: np.uint8, CV_16S: np.int16, CV_32F: np.float32}
 
 
@@ -129,6 +129,19 @@ def warpAffine(src, M, dsize, flags=INTER_LINEAR, borderMode=BORDER_CONSTANT, bo
 
 def warpPerspective(src, M, dsize, flags=INTER_LINEAR, borderMode=BORDER_CONSTANT, borderValue=0, dst=None):
     return _warp(lib().b200cv_host_warp_perspective, "warpPerspective", src, M, dsize, flags, borderMode, borderValue, dst)
+
+
+def remap(src, map1, map2, interpolation, borderMode=BORDER_CONSTANT, borderValue=0, dst=None):
+    m1 = describe(map1)
+    dst = dst if dst is not None else _new(src, size=(m1.cols, m1.rows))
+    ms, md = describe(src), describe(dst)
+    m2 = describe(map2) if map2 is not None else None
+    bv = np.zeros(4, np.float64)
+    b = np.atleast_1d(np.asarray(borderValue, np.float64))
+    bv[:len(b)] = b
+    _check(lib().b200cv_host_remap(ctypes.byref(ms), ctypes.byref(md), ctypes.byref(m1), ctypes.byref(m2) if m2 is not None else None, int(interpolation),
+                                   int(borderMode), bv.ctypes.data_as(ctypes.POINTER(ctypes.c_double))), "remap")
+    return dst
 
 
 def cornerHarris(src, blockSize, ksize, k, borderType=BORDER_DEFAULT, dst=None):

@@ -85,7 +85,7 @@ public:
     {
         if (data && r == rows && c == cols && t == type_ && nframes == frames) return;
         release();
-        size_t es = (size_t)B200CV_CN(t) * (B200CV_DEPTH(t) == 0 ? 1 : B200CV_DEPTH(t) == 3 ? 2 : 4);
+        size_t es = (size_t)B200CV_CN(t) * (B200CV_DEPTH(t) <= 1 ? 1 : B200CV_DEPTH(t) <= 3 ? 2 : 4);
         void* p = nullptr;
         check(b200cv_malloc_pitch(&p, &step, (size_t)c * es, (size_t)r * nframes), "GpuMat::create");
         own_.reset((unsigned char*)p, [](unsigned char* q) { b200cv_free(q); });
@@ -98,7 +98,7 @@ public:
     { check(b200cv_download(data, step, host, host_step, rowBytes(), (size_t)rows * frames, s.cudaPtr()), "download"); if (!s.cudaPtr()) b200cv_stream_synchronize(nullptr); }
     b200cvMat desc() const { b200cvMat m = {data, step, cols, rows, type_, frames, frame_step}; return m; }
 private:
-    size_t rowBytes() const { return (size_t)cols * B200CV_CN(type_) * (B200CV_DEPTH(type_) == 0 ? 1 : B200CV_DEPTH(type_) == 3 ? 2 : 4); }
+    size_t rowBytes() const { return (size_t)cols * B200CV_CN(type_) * (B200CV_DEPTH(type_) <= 1 ? 1 : B200CV_DEPTH(type_) <= 3 ? 2 : 4); }
     int type_ = 0; std::shared_ptr<unsigned char> own_;
 };
 
@@ -136,6 +136,14 @@ inline void warpAffine(const GpuMat& src, GpuMat& dst, const double M[6], Size d
 inline void warpPerspective(const GpuMat& src, GpuMat& dst, const double M[9], Size dsize, int flags = INTER_LINEAR, int borderMode = BORDER_CONSTANT, Scalar bv = Scalar(),
                             Stream& s = Stream::Null())
 { dst.create(dsize.height, dsize.width, src.type(), src.frames); b200cvMat a = src.desc(), b = dst.desc(); check(b200cv_warp_perspective(&a, &b, M, flags, borderMode, bv.val, s.cudaPtr()), "warpPerspective"); }
+// cv::remap (imgproc.hpp:2531): map1/map2 as cv::remap takes them (CV_32FC1 pair, CV_32FC2, or CV_16SC2 + CV_16UC1); one set of maps per batch
+inline void remap(const GpuMat& src, GpuMat& dst, const GpuMat& map1, const GpuMat& map2, int interpolation, int borderMode = BORDER_CONSTANT, Scalar bv = Scalar(),
+                  Stream& s = Stream::Null())
+{
+    dst.create(map1.rows, map1.cols, src.type(), src.frames);
+    b200cvMat a = src.desc(), b = dst.desc(), m1 = map1.desc(), m2 = map2.desc();
+    check(b200cv_remap(&a, &b, &m1, map2.data ? &m2 : nullptr, interpolation, borderMode, bv.val, s.cudaPtr()), "remap");
+}
 inline void cvtColor(const GpuMat& src, GpuMat& dst, int code, int dcn, Stream& s = Stream::Null())
 { B200CV_DST(dst, src, makeType(B200CV_DEPTH(src.type()), dcn)); b200cvMat a = src.desc(), b = dst.desc(); check(b200cv_cvt_color(&a, &b, code, s.cudaPtr()), "cvtColor"); }
 inline void matchTemplate(const GpuMat& image, const GpuMat& templ, GpuMat& result, int method, Stream& s = Stream::Null())

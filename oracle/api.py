@@ -17,7 +17,7 @@ REF_HAL_LIB = os.path.join(HERE, "_ref", "libocvref_hal.so")   # the reference w
 PORT_LIB = os.path.join(HERE, "_build", "liboracle_port.so")
 
 CV_8U, CV_16S, CV_32F = 0, 3, 5
-_DEPTH = {np.dtype(np.uint8): CV_8U, np.dtype(np.int16): CV_16S, np.dtype(np.float32): CV_32F}
+_DEPTH = {np.dtype(np.uint8): CV_8U, np.dtype(np.uint16): 2, np.dtype(np.int16): CV_16S, np.dtype(np.float32): CV_32F}
 _NP = {CV_8U: np.uint8, CV_16S: np.int16, CV_32F: np.float32}
 
 vp, sz, dbl = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_double
@@ -151,6 +151,27 @@ class Oracle:
 
     def warpPerspective(self, src, M, dsize, flags=1, borderMode=0, borderValue=0):
         return self._warp("warp_perspective", src, M, dsize, flags, borderMode, borderValue)
+
+    def remap(self, src, map1, map2, interpolation, borderMode=0, borderValue=0):
+        src = np.ascontiguousarray(src); map1 = np.ascontiguousarray(map1)
+        map2 = np.ascontiguousarray(map2) if map2 is not None else None
+        dh, dw = map1.shape[:2]
+        dst = np.zeros((dh, dw) + src.shape[2:], src.dtype)
+        sh, sw = src.shape[:2]
+        bv = np.zeros(4, np.float64)
+        bv[:len(np.atleast_1d(borderValue))] = np.atleast_1d(borderValue)
+        self._ok(self.fn("remap")(_p(src), sz(src.strides[0]), sw, sh, cvtype(src), _p(dst), sz(dst.strides[0]), dw, dh,
+                                  _p(map1), sz(map1.strides[0]), cvtype(map1), _p(map2) if map2 is not None else None,
+                                  sz(map2.strides[0]) if map2 is not None else sz(0), cvtype(map2) if map2 is not None else 0,
+                                  int(interpolation), int(borderMode), _p(bv)), "remap")
+        return dst
+
+    def convertMaps(self, mapx, mapy, nninterpolation=False):
+        mapx = np.ascontiguousarray(mapx, np.float32); mapy = np.ascontiguousarray(mapy, np.float32)
+        h, w = mapx.shape
+        xy = np.zeros((h, w, 2), np.int16); fr = np.zeros((h, w), np.uint16)
+        self._ok(self.fn("convert_maps")(_p(mapx), _p(mapy), w, h, _p(xy), _p(fr), int(bool(nninterpolation))), "convertMaps")
+        return xy, fr
 
     def cvtColor(self, src, code, dcn):
         src = np.ascontiguousarray(src)

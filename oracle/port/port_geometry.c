@@ -156,8 +156,37 @@ static void build_tabs(void)
     done = 1;
 }
 
+/* cvRound / v_round on x86: nearest-even, 0x80000000 for NaN and values outside int32 */
+static int x86_round(float v) { return fabsf(v) < 2147483648.f ? (int)lrintf(v) : (int)0x80000000; }
+
+typedef struct { const void* m1; size_t s1; int t1; const void* m2; size_t s2; int t2; } PortMaps;
+
+/* cv::remap coordinates (RemapInvoker, imgwarp.cpp:1164-1283): float maps are rounded (NEAREST) or scaled by 32 and rounded into a
+   5-bit-fraction fixed point; fixed-point maps are used as they are (NEAREST rounds the fractions through NNDeltaTab_i) */
+static void map_coords(const PortMaps* mp, int x, int y, int interp, int* sx, int* sy, int* a)
+{
+    *a = 0;
+    if (P_DEPTH(mp->t1) == P_16S) {
+        const short* xy = (const short*)((const char*)mp->m1 + (size_t)y * mp->s1) + 2 * x;
+        int fr = mp->m2 ? (((const unsigned short*)((const char*)mp->m2 + (size_t)y * mp->s2))[x] & 1023) : 0;
+        /* NNDeltaTab_i is filled as (fraction < 1/2) (imgwarp.cpp:237-238) -- and only once a bilinear table has been built in the process;
+           before that it is all zeros.  The table as built is what is reproduced here. */
+        if (interp == 0) { *sx = (short)(xy[0] + ((fr & 31) < 16)); *sy = (short)(xy[1] + ((fr >> 5) < 16)); }
+        else { *sx = xy[0]; *sy = xy[1]; *a = fr; }
+        return;
+    }
+    float mx, my;
+    if (mp->m2) { mx = ((const float*)((const char*)mp->m1 + (size_t)y * mp->s1))[x]; my = ((const float*)((const char*)mp->m2 + (size_t)y * mp->s2))[x]; }
+    else { const float* q = (const float*)((const char*)mp->m1 + (size_t)y * mp->s1) + 2 * x; mx = q[0]; my = q[1]; }
+    if (interp == 0) { *sx = port_sat_s16i(x86_round(mx)); *sy = port_sat_s16i(x86_round(my)); }
+    else {
+        int ix = x86_round(mx * 32.f), iy = x86_round(my * 32.f);
+        *sx = port_sat_s16i(ix >> 5); *sy = port_sat_s16i(iy >> 5); *a = (iy & 31) * 32 + (ix & 31);
+    }
+}
+
 static int warp_impl(const void* src, size_t sstep, int sw, int sh, void* dst, size_t dstep, int dw, int dh, int type, const double* M, int persp,
-                     int interp, int border, const double* bv)
+                     int interp, int border, const double* bv, const PortMaps* maps)
 {
     int depth = P_DEPTH(type), cn = P_CN(type);
     if (depth != P_8U && depth != P_32F) return 1;
@@ -171,7 +200,8 @@ static int warp_impl(const void* src, size_t sstep, int sw, int sh, void* dst, s
     for (int y = 0; y < dh; y++)
         for (int x = 0; x < dw; x++) {
             int sx, sy, a = 0;
-            if (!persp) {
+            if (maps) map_coords(maps, x, y, interp, &sx, &sy, &a);
+            else if (!persp) {
                 int rd = interp == 0 ? 512 : 16;
                 int ad = port_round(M[0] * x * 1024), bd = port_round(M[3] * x * 1024);
                 int X0 = port_round((M[1] * y + M[2]) * 1024) + rd, Y0 = port_round((M[4] * y + M[5]) * 1024) + rd;
@@ -249,7 +279,7 @@ PORT_API int port_warp_affine(const void* src, size_t sstep, int sw, int sh, voi
         double b1 = -M[0] * M[2] - M[1] * M[5], b2 = -M[3] * M[2] - M[4] * M[5];
         M[2] = b1; M[5] = b2;
     }
-    return warp_impl(src, sstep, sw, sh, dst, dstep, dw, dh, type, M, 0, flags & 7, border, bv);
+    return warp_impl(src, sstep, sw, sh, dst, dstep, dw, dh, type, M, 0, flags & 7, border, bv, NULL);
 }
 
 PORT_API int port_warp_perspective(const void* src, size_t sstep, int sw, int sh, void* dst, size_t dstep, int dw, int dh, int type, const double* m,
@@ -266,5 +296,15 @@ PORT_API int port_warp_perspective(const void* src, size_t sstep, int sw, int sh
             M[6] = (m[3] * m[7] - m[4] * m[6]) * d; M[7] = (m[1] * m[6] - m[0] * m[7]) * d; M[8] = (m[0] * m[4] - m[1] * m[3]) * d;
         } else memset(M, 0, sizeof(M));
     }
-    return warp_impl(src, sstep, sw, sh, dst, dstep, dw, dh, type, M, 1, flags & 7, border, bv);
+    return warp_impl(src, sstep, sw, sh, dst, dstep, dw, dh, type, M, 1, flags & 7, border, bv, NULL);
+}
+
+/* cv::remap (imgwarp.cpp:1762-1900) */
+PORT_API int port_remap(const void* src, size_t sstep, int sw, int sh, int type, void* dst, size_t dstep, int dw, int dh,
+                        const void* m1, size_t m1step, int m1type, const void* m2, size_t m2step, int m2type, int interp, int border, const double* bv)
+{
+    PortMaps mp = {m1, m1step, m1type, m2, m2step, m2type};
+    static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (interp & 32) return 1;
+    return warp_impl(src, sstep, sw, sh, dst, dstep, dw, dh, type, I, 0, interp & 7, border, bv, &mp);
 }

@@ -139,6 +139,27 @@ API int ref_warp_perspective(const void* src, size_t sstep, int sw, int sh, void
     GUARD_END
 }
 
+API int ref_remap(const void* src, size_t sstep, int sw, int sh, int type, void* dst, size_t dstep, int dw, int dh,
+                  const void* m1, size_t m1step, int m1type, const void* m2, size_t m2step, int m2type, int interp, int border, const double* bv)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, sw, sh, type), d = hdr(dst, dstep, dw, dh, type);
+    Mat a = hdr(m1, m1step, dw, dh, m1type), b;
+    if (m2) b = hdr(m2, m2step, dw, dh, m2type);
+    remap(s, d, a, b, interp, border, Scalar(bv[0], bv[1], bv[2], bv[3]));
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+API int ref_convert_maps(const float* mx, const float* my, int w, int h, short* xy, unsigned short* frac, int nn)
+{
+    GUARD_BEGIN
+    Mat a(h, w, CV_32FC1, (void*)mx), b(h, w, CV_32FC1, (void*)my), o1(h, w, CV_16SC2, xy), o2(h, w, CV_16UC1, frac);
+    convertMaps(a, b, o1, o2, CV_16SC2, nn != 0);
+    CV_Assert(o1.data == (uchar*)xy);
+    GUARD_END
+}
+
 API int ref_invert_affine(const double* M, double* iM)
 {
     GUARD_BEGIN

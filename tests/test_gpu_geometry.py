@@ -153,3 +153,44 @@ def test_warp_tile_and_direct_paths(cvb, oracle, rng, interp, monkeypatch):
         monkeypatch.setenv("B200CV_WARP_PATH", "direct")
         assert_exact(got, cpu(cvb.warpPerspective(gpu(img), Hm, (401, 283), interp | C.WARP_INVERSE_MAP, C.BORDER_REPLICATE)), "tile vs direct")
         monkeypatch.delenv("B200CV_WARP_PATH")
+
+
+def _test_maps(rng, h, w, sw, sh, kind):
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    if kind == 0:       # barrel-like distortion reaching outside the source
+        cx, cy = w / 2, h / 2
+        r2 = ((xx - cx) ** 2 + (yy - cy) ** 2) / (cx * cx)
+        mx = (cx + (xx - cx) * (1 + 0.35 * r2)) * sw / w; my = (cy + (yy - cy) * (1 + 0.35 * r2)) * sh / h
+    elif kind == 1:     # random scatter
+        mx = rng.random((h, w)) * (sw + 40) - 20; my = rng.random((h, w)) * (sh + 40) - 20
+    else:               # ties, NaN, values outside short / int
+        mx = xx * 1.3 - 7.25; my = yy * 0.7 + 3.5
+        mx[0, 0] = np.nan; mx[0, 1] = 1e20; my[0, 2] = -1e20; mx[1, 0] = 40000.4; my[1, 1] = -40000.6; mx[2, :5] = [0.5, 1.5, 2.5, -0.5, -1.5]
+    return mx.astype(np.float32), my.astype(np.float32)
+
+
+@pytest.mark.parametrize("cn", [1, 3, 4])
+@pytest.mark.parametrize("interp", [C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC])
+def test_remap(cvb, oracle, rng, cn, interp):
+    """cv::remap (SURVEY 8f): float x/y planes, packed CV_32FC2 maps and the fixed-point pair of cv::convertMaps; u8 and f32; every border;
+    NaN / out-of-range map values follow x86 cvRound (0x80000000).  Bit-exact."""
+    for dt in (np.uint8, np.float32):
+        src = (rng.random((97, 131, cn) if cn > 1 else (97, 131)) * 255).astype(dt)
+        for kind in (0, 1, 2):
+            mx, my = _test_maps(rng, 80, 111, 131, 97, kind)
+            for border in (C.BORDER_CONSTANT, C.BORDER_REPLICATE, C.BORDER_REFLECT, C.BORDER_REFLECT_101, C.BORDER_WRAP):
+                want = oracle.remap(src, mx, my, interp, border, (9, 8, 7, 6))
+                assert_exact(cpu(cvb.remap(gpu(src), gpu(mx), gpu(my), interp, border, (9, 8, 7, 6))), want, "remap planar %s cn=%d kind=%d b=%d" % (dt.__name__, cn, kind, border))
+            m12 = np.stack([mx, my], -1)
+            assert_exact(cpu(cvb.remap(gpu(src), gpu(m12), None, interp, C.BORDER_REFLECT_101)), oracle.remap(src, m12, None, interp, C.BORDER_REFLECT_101), "remap packed")
+            if kind < 2 and oracle.has("convert_maps"):
+                oracle.remap(src, mx, my, C.INTER_LINEAR, C.BORDER_REPLICATE)      # the reference fills NNDeltaTab_i with its bilinear table
+                xy, fr = oracle.convertMaps(mx, my)
+                got = cpu(cvb.remap(gpu(src), gpu(xy), gpu(fr.view(np.int16)), interp, C.BORDER_REPLICATE))
+                assert_exact(got, oracle.remap(src, xy, fr, interp, C.BORDER_REPLICATE), "remap fixed-point maps")
+    # a batch shares one set of maps
+    batch = rng.integers(0, 256, (3, 60, 90, cn), dtype=np.uint8)
+    mx, my = _test_maps(rng, 70, 50, 90, 60, 0)
+    got = cpu(cvb.remap(gpu(batch), gpu(mx), gpu(my), interp, C.BORDER_REPLICATE))
+    for i in range(3):
+        assert_exact(got[i] if cn > 1 else got[i, :, :, 0], oracle.remap(batch[i] if cn > 1 else batch[i, :, :, 0], mx, my, interp, C.BORDER_REPLICATE), "remap batch frame %d" % i)

@@ -59,6 +59,10 @@ def test_host_batch_pipeline(cvb, oracle, rng):
         assert_exact(out[i], oracle.GaussianBlur(batch[i], (7, 7), 1.5), "batched host blur frame %d" % i)
         assert_exact(gray[i, :, :, 0], oracle.cvtColor(batch[i], C.COLOR_BGR2GRAY, 1), "batched host gray frame %d" % i)
     M = np.array([[0.9, 0.1, 5], [-0.1, 0.9, 7]])
+    yy, xx = np.mgrid[0:200, 0:300].astype(np.float32)
+    mx = (xx * 2.1 + 3).astype(np.float32); my = (yy * 2.3 + 5 * np.sin(xx / 17)).astype(np.float32)
+    rm = hal.remap(batch[:3], mx, my, 2, 4)
+    assert_exact(rm[2], oracle.remap(batch[2], mx, my, 2, 4), "host remap")
     w = hal.warpAffine(batch[:3], M, (640, 480))
     assert_exact(w[1], oracle.warpAffine(batch[1], M, (640, 480)), "host warpAffine")
     r = hal.matchTemplate(batch[0, :, :, 0].copy(), batch[0, 100:132, 200:232, 0].copy(), C.TM_CCORR_NORMED)
@@ -83,6 +87,12 @@ def test_opencv_built_with_b200_hal(cvb, ref, rng):
     assert_exact(hal.resize(img, (427, 321), 2), ref.resize(img, (427, 321), 2), "cv::resize CUBIC via HAL")
     M = np.array([[0.9, 0.1, 5], [-0.1, 0.9, 7]])
     assert_exact(hal.warpAffine(img, M, (640, 480), 1, 1), ref.warpAffine(img, M, (640, 480), 1, 1), "cv::warpAffine via HAL")
+    if hal.has("remap"):
+        yy, xx = np.mgrid[0:300, 0:400].astype(np.float32)
+        mx = (xx * 1.5 + 10 * np.sin(yy / 20)).astype(np.float32); my = (yy * 1.55 - 8 + 5 * np.cos(xx / 30)).astype(np.float32)
+        nb = cvb.launch_count()
+        assert_exact(hal.remap(img, mx, my, 1, 1), ref.remap(img, mx, my, 1, 1), "cv::remap via HAL (hal_ni_remap32f)")
+        assert cvb.launch_count() > nb, "cv::remap did not reach the B200 HAL"
     assert_exact(hal.GaussianBlur(img, (5, 5), 0), ref.GaussianBlur(img, (5, 5), 0), "cv::GaussianBlur (binomial HAL hook)")
     f = g.astype(np.float32)
     assert_close(hal.GaussianBlur(f, (7, 7), 1.5), ref.GaussianBlur(f, (7, 7), 1.5), atol=1e-4, what="cv::GaussianBlur f32 via HAL")
