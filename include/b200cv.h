@@ -168,6 +168,10 @@ B200CV_API int b200cv_warp_perspective(const b200cvMat* src, const b200cvMat* ds
  *   map1 CV_16SC2 + map2 CV_16UC1 (map2 may be NULL for INTER_NEAREST).  WARP_RELATIVE_MAP is not implemented. */
 B200CV_API int b200cv_remap(const b200cvMat* src, const b200cvMat* dst, const b200cvMat* map1, const b200cvMat* map2, int interpolation,
                             int border, const double* border_value, void* stream);
+/* replace cv::pyrDown / cv::pyrUp (imgproc.hpp:3325, :3351; pyramids.cpp:1348-1400, :1459-1505) for the default destination sizes
+ * ((W+1)/2 x (H+1)/2 and 2W x 2H), 8-bit and float, 1/3/4 channels -- SURVEY 8(f) */
+B200CV_API int b200cv_pyr_down(const b200cvMat* src, const b200cvMat* dst, int border, void* stream);
+B200CV_API int b200cv_pyr_up(const b200cvMat* src, const b200cvMat* dst, int border, void* stream);
 /* replaces cv::cvtColor (imgproc.hpp:3736; color.cpp:192-400) for BGR/RGB(A) <-> GRAY / YUV / YCrCb / HSV(_FULL) / BGR(A) */
 B200CV_API int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int code, void* stream);
 /* replaces cv::matchTemplate (imgproc.hpp:3916; templmatch.cpp:1158-1194), 1-channel u8/f32, all six methods.

@@ -66,6 +66,9 @@ B200CV_API int b200cv_hal_warpPerspective(int src_type, const b200cv_uchar* src_
 B200CV_API int b200cv_hal_remap32f(int src_type, const b200cv_uchar* src_data, size_t src_step, int src_width, int src_height, b200cv_uchar* dst_data,
                                    size_t dst_step, int dst_width, int dst_height, float* mapx, size_t mapx_step, float* mapy, size_t mapy_step,
                                    int interpolation, int border_type, const double border_value[4]);
+/* hal_ni_pyrdown, hal_replacement.hpp:1244 (cv::pyrDown on a whole Mat, pyramids.cpp:1377) */
+B200CV_API int b200cv_hal_pyrdown(const b200cv_uchar* src_data, size_t src_step, int src_width, int src_height, b200cv_uchar* dst_data, size_t dst_step,
+                                  int dst_width, int dst_height, int depth, int cn, int border_type);
 /* colour: hal_ni_cvtBGRtoBGR :395, cvtBGRtoGray :442, cvtGraytoBGR :456, cvtBGRtoYUV :500, cvtYUVtoBGR :533, cvtBGRtoHSV :596, cvtHSVtoBGR :613 */
 B200CV_API int b200cv_hal_cvtBGRtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                       int depth, int scn, int dcn, bool swapBlue);
@@ -92,6 +95,8 @@ B200CV_API int b200cv_host_sobel(const b200cvMat* src, const b200cvMat* dst, int
 B200CV_API int b200cv_host_resize(const b200cvMat* src, const b200cvMat* dst, int interpolation);
 B200CV_API int b200cv_host_warp_affine(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags, int border, const double* border_value);
 B200CV_API int b200cv_host_warp_perspective(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags, int border, const double* border_value);
+B200CV_API int b200cv_host_pyr_down(const b200cvMat* src, const b200cvMat* dst, int border);
+B200CV_API int b200cv_host_pyr_up(const b200cvMat* src, const b200cvMat* dst, int border);
 /* maps are host arrays too (one set for the whole batch); they are uploaded once per call */
 B200CV_API int b200cv_host_remap(const b200cvMat* src, const b200cvMat* dst, const b200cvMat* map1, const b200cvMat* map2, int interpolation, int border,
                                  const double* border_value);

@@ -307,6 +307,24 @@ def remap(src, map1, map2, interpolation, borderMode=BORDER_CONSTANT, borderValu
     return dst
 
 
+def pyrDown(src, dst=None, borderType=BORDER_DEFAULT, stream=None):
+    """cv::pyrDown (imgproc.hpp:3325), default destination size ((W+1)/2, (H+1)/2)"""
+    m = describe(src)
+    dst = dst if dst is not None else _new(src, size=((m.cols + 1) // 2, (m.rows + 1) // 2))
+    ms, md = _pair(src, dst)
+    _check(lib().b200cv_pyr_down(ctypes.byref(ms), ctypes.byref(md), int(borderType), _stream_ptr(stream)), "pyrDown")
+    return dst
+
+
+def pyrUp(src, dst=None, stream=None):
+    """cv::pyrUp (imgproc.hpp:3351), destination 2W x 2H"""
+    m = describe(src)
+    dst = dst if dst is not None else _new(src, size=(m.cols * 2, m.rows * 2))
+    ms, md = _pair(src, dst)
+    _check(lib().b200cv_pyr_up(ctypes.byref(ms), ctypes.byref(md), int(BORDER_DEFAULT), _stream_ptr(stream)), "pyrUp")
+    return dst
+
+
 def matchTemplate(image, templ, method, result=None, stream=None):
     """cv::matchTemplate (imgproc.hpp:3916): image (H,W) / (N,H,W,1), templ (h,w); result float32 (H-h+1, W-w+1)"""
     import torch

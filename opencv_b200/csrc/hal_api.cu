@@ -257,6 +257,18 @@ extern "C" int b200cv_hal_warpPerspective(int type, const uchar* src, size_t sst
     return b200cv_host_warp_perspective(&s, &d, M, interp | B200CV_WARP_INVERSE_MAP, border, bv);
 }
 
+extern "C" int b200cv_host_pyr_down(const b200cvMat* s, const b200cvMat* d, int border)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_pyr_down(a, b, border, st); }); }
+extern "C" int b200cv_host_pyr_up(const b200cvMat* s, const b200cvMat* d, int border)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_pyr_up(a, b, border, st); }); }
+
+extern "C" int b200cv_hal_pyrdown(const uchar* src, size_t sstep, int sw, int sh, uchar* dst, size_t dstep, int dw, int dh, int depth, int cn, int border)
+{
+    if (src == dst) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, sw, sh, B200CV_MAKETYPE(depth, cn)), d = hmat(dst, dstep, dw, dh, B200CV_MAKETYPE(depth, cn));
+    return b200cv_host_pyr_down(&s, &d, border);
+}
+
 extern "C" int b200cv_host_remap(const b200cvMat* src, const b200cvMat* dst, const b200cvMat* map1, const b200cvMat* map2, int interp, int border, const double* bv)
 {
     int rc;

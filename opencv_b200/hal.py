@@ -131,6 +131,22 @@ def warpPerspective(src, M, dsize, flags=INTER_LINEAR, borderMode=BORDER_CONSTAN
     return _warp(lib().b200cv_host_warp_perspective, "warpPerspective", src, M, dsize, flags, borderMode, borderValue, dst)
 
 
+def pyrDown(src, dst=None, borderType=BORDER_DEFAULT):
+    m = describe(src)
+    dst = dst if dst is not None else _new(src, size=((m.cols + 1) // 2, (m.rows + 1) // 2))
+    ms, md = describe(src), describe(dst)
+    _check(lib().b200cv_host_pyr_down(ctypes.byref(ms), ctypes.byref(md), int(borderType)), "pyrDown")
+    return dst
+
+
+def pyrUp(src, dst=None):
+    m = describe(src)
+    dst = dst if dst is not None else _new(src, size=(m.cols * 2, m.rows * 2))
+    ms, md = describe(src), describe(dst)
+    _check(lib().b200cv_host_pyr_up(ctypes.byref(ms), ctypes.byref(md), int(BORDER_DEFAULT)), "pyrUp")
+    return dst
+
+
 def remap(src, map1, map2, interpolation, borderMode=BORDER_CONSTANT, borderValue=0, dst=None):
     m1 = describe(map1)
     dst = dst if dst is not None else _new(src, size=(m1.cols, m1.rows))

@@ -136,6 +136,11 @@ inline void warpAffine(const GpuMat& src, GpuMat& dst, const double M[6], Size d
 inline void warpPerspective(const GpuMat& src, GpuMat& dst, const double M[9], Size dsize, int flags = INTER_LINEAR, int borderMode = BORDER_CONSTANT, Scalar bv = Scalar(),
                             Stream& s = Stream::Null())
 { dst.create(dsize.height, dsize.width, src.type(), src.frames); b200cvMat a = src.desc(), b = dst.desc(); check(b200cv_warp_perspective(&a, &b, M, flags, borderMode, bv.val, s.cudaPtr()), "warpPerspective"); }
+// cv::pyrDown / cv::pyrUp (imgproc.hpp:3325, :3351), default destination sizes
+inline void pyrDown(const GpuMat& src, GpuMat& dst, int borderType = BORDER_DEFAULT, Stream& s = Stream::Null())
+{ dst.create((src.rows + 1) / 2, (src.cols + 1) / 2, src.type(), src.frames); b200cvMat a = src.desc(), b = dst.desc(); check(b200cv_pyr_down(&a, &b, borderType, s.cudaPtr()), "pyrDown"); }
+inline void pyrUp(const GpuMat& src, GpuMat& dst, Stream& s = Stream::Null())
+{ dst.create(src.rows * 2, src.cols * 2, src.type(), src.frames); b200cvMat a = src.desc(), b = dst.desc(); check(b200cv_pyr_up(&a, &b, BORDER_DEFAULT, s.cudaPtr()), "pyrUp"); }
 // cv::remap (imgproc.hpp:2531): map1/map2 as cv::remap takes them (CV_32FC1 pair, CV_32FC2, or CV_16SC2 + CV_16UC1); one set of maps per batch
 inline void remap(const GpuMat& src, GpuMat& dst, const GpuMat& map1, const GpuMat& map2, int interpolation, int borderMode = BORDER_CONSTANT, Scalar bv = Scalar(),
                   Stream& s = Stream::Null())

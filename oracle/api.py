@@ -173,6 +173,20 @@ class Oracle:
         self._ok(self.fn("convert_maps")(_p(mapx), _p(mapy), w, h, _p(xy), _p(fr), int(bool(nninterpolation))), "convertMaps")
         return xy, fr
 
+    def pyrDown(self, src, borderType=4):
+        src = np.ascontiguousarray(src)
+        h, w = src.shape[:2]
+        dst = np.zeros(((h + 1) // 2, (w + 1) // 2) + src.shape[2:], src.dtype)
+        self._ok(self.fn("pyr_down")(_p(src), sz(src.strides[0]), w, h, cvtype(src), _p(dst), sz(dst.strides[0]), int(borderType)), "pyrDown")
+        return dst
+
+    def pyrUp(self, src):
+        src = np.ascontiguousarray(src)
+        h, w = src.shape[:2]
+        dst = np.zeros((h * 2, w * 2) + src.shape[2:], src.dtype)
+        self._ok(self.fn("pyr_up")(_p(src), sz(src.strides[0]), w, h, cvtype(src), _p(dst), sz(dst.strides[0])), "pyrUp")
+        return dst
+
     def cvtColor(self, src, code, dcn):
         src = np.ascontiguousarray(src)
         h, w = src.shape[:2]

@@ -308,3 +308,80 @@ PORT_API int port_remap(const void* src, size_t sstep, int sw, int sh, int type,
     if (interp & 32) return 1;
     return warp_impl(src, sstep, sw, sh, dst, dstep, dw, dh, type, I, 0, interp & 7, border, bv, &mp);
 }
+
+/* cv::pyrDown (pyramids.cpp:884-1039), default destination size.  8-bit exact; float in the order of the reference's SSE bodies
+   (:324-341 rows, :497-516 columns; its edge columns and vector remainders use the scalar order: <= 1 ulp there) */
+PORT_API int port_pyr_down(const void* src, size_t sstep, int sw, int sh, int type, void* dst, size_t dstep, int border)
+{
+    int depth = P_DEPTH(type), cn = P_CN(type), dw = (sw + 1) / 2, dh = (sh + 1) / 2;
+    if (depth != P_8U && depth != P_32F) return 1;
+    border &= ~16;
+    for (int y = 0; y < dh; y++)
+        for (int x = 0; x < dw; x++)
+            for (int c = 0; c < cn; c++) {
+                int sx[5];
+                for (int k = 0; k < 5; k++) sx[k] = port_border(2 * x + k - 2, sw, border) * cn + c;
+                if (depth == P_8U) {
+                    int r[5];
+                    for (int j = 0; j < 5; j++) {
+                        const uchar* s = (const uchar*)src + (size_t)port_border(2 * y + j - 2, sh, border) * sstep;
+                        r[j] = s[sx[2]] * 6 + (s[sx[1]] + s[sx[3]]) * 4 + s[sx[0]] + s[sx[4]];
+                    }
+                    ((uchar*)dst + (size_t)y * dstep)[x * cn + c] = (uchar)((r[2] * 6 + (r[1] + r[3]) * 4 + r[0] + r[4] + 128) >> 8);
+                } else {
+                    volatile float r[5], t, u;
+                    for (int j = 0; j < 5; j++) {
+                        const float* s = (const float*)((const char*)src + (size_t)port_border(2 * y + j - 2, sh, border) * sstep);
+                        t = s[sx[1]] + s[sx[3]]; t = t * 4.f; u = s[sx[0]] + s[sx[4]]; t = t + u; u = s[sx[2]] * 6.f; r[j] = u + t;
+                    }
+                    t = r[1] + r[3]; t = t + r[2]; t = t * 4.f; u = r[0] + r[4]; { volatile float d2 = r[2] + r[2]; u = u + d2; } t = t + u;
+                    ((float*)((char*)dst + (size_t)y * dstep))[x * cn + c] = t * (1.f / 256);
+                }
+            }
+    return 0;
+}
+
+static float pyr_up_hf(const float* s, int dx, int c, int cn, int sw)
+{
+    int x = dx >> 1, odd = dx & 1;
+    volatile float a, b;
+    if (sw == 1) return s[c] * 8.f;
+    if (x == 0) { if (odd) { a = s[c] + s[cn + c]; return a * 4.f; } a = s[c] * 6.f; b = s[cn + c] * 2.f; return a + b; }
+    if (x == sw - 1) { if (odd) return s[x * cn + c] * 8.f; a = s[x * cn + c] * 7.f; return s[(x - 1) * cn + c] + a; }
+    if (odd) { a = s[x * cn + c] + s[(x + 1) * cn + c]; return a * 4.f; }
+    a = s[x * cn + c] * 6.f; b = s[(x - 1) * cn + c] + a; return b + s[(x + 1) * cn + c];
+}
+static int pyr_up_hi(const uchar* s, int dx, int c, int cn, int sw)
+{
+    int x = dx >> 1, odd = dx & 1;
+    if (sw == 1) return s[c] * 8;
+    if (x == 0) return odd ? (s[c] + s[cn + c]) * 4 : s[c] * 6 + s[cn + c] * 2;
+    if (x == sw - 1) return odd ? s[x * cn + c] * 8 : s[(x - 1) * cn + c] + s[x * cn + c] * 7;
+    return odd ? (s[x * cn + c] + s[(x + 1) * cn + c]) * 4 : s[(x - 1) * cn + c] + s[x * cn + c] * 6 + s[(x + 1) * cn + c];
+}
+
+/* cv::pyrUp (pyramids.cpp:1041-1155), 2W x 2H.  Rows of the ring: y-1 -> 1 at the top (REFLECT_101 on the doubled grid), y+1 -> H-1 at the bottom */
+PORT_API int port_pyr_up(const void* src, size_t sstep, int sw, int sh, int type, void* dst, size_t dstep)
+{
+    int depth = P_DEPTH(type), cn = P_CN(type), dw = sw * 2, dh = sh * 2;
+    if (depth != P_8U && depth != P_32F) return 1;
+    for (int dy = 0; dy < dh; dy++) {
+        int y = dy >> 1, y0 = y - 1 < 0 ? (sh > 1 ? 1 : 0) : y - 1, y2 = y + 1 >= sh ? sh - 1 : y + 1;
+        for (int dx = 0; dx < dw; dx++)
+            for (int c = 0; c < cn; c++) {
+                if (depth == P_8U) {
+                    const uchar* b = (const uchar*)src;
+                    int r0 = pyr_up_hi(b + (size_t)y0 * sstep, dx, c, cn, sw), r1 = pyr_up_hi(b + (size_t)y * sstep, dx, c, cn, sw), r2 = pyr_up_hi(b + (size_t)y2 * sstep, dx, c, cn, sw);
+                    ((uchar*)dst + (size_t)dy * dstep)[dx * cn + c] = (uchar)((dy & 1) ? ((r1 + r2) * 4 + 32) >> 6 : (r0 + r1 * 6 + r2 + 32) >> 6);
+                } else {
+                    const char* b = (const char*)src;
+                    volatile float r0 = pyr_up_hf((const float*)(b + (size_t)y0 * sstep), dx, c, cn, sw), r1 = pyr_up_hf((const float*)(b + (size_t)y * sstep), dx, c, cn, sw),
+                                   r2 = pyr_up_hf((const float*)(b + (size_t)y2 * sstep), dx, c, cn, sw), t;
+                    if (dy & 1) { t = r1 + r2; t = (1.f / 16) * t; }
+                    else { t = 6.f * r1; t = t + r0; t = t + r2; t = (1.f / 64) * t; }
+                    ((float*)((char*)dst + (size_t)dy * dstep))[dx * cn + c] = t;
+                }
+            }
+    }
+    return 0;
+}

@@ -160,6 +160,24 @@ API int ref_convert_maps(const float* mx, const float* my, int w, int h, short* 
     GUARD_END
 }
 
+API int ref_pyr_down(const void* src, size_t sstep, int sw, int sh, int type, void* dst, size_t dstep, int border)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, sw, sh, type), d = hdr(dst, dstep, (sw + 1) / 2, (sh + 1) / 2, type);
+    pyrDown(s, d, Size(), border);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
+API int ref_pyr_up(const void* src, size_t sstep, int sw, int sh, int type, void* dst, size_t dstep)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, sw, sh, type), d = hdr(dst, dstep, sw * 2, sh * 2, type);
+    pyrUp(s, d);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
 API int ref_invert_affine(const double* M, double* iM)
 {
     GUARD_BEGIN

@@ -194,3 +194,25 @@ def test_remap(cvb, oracle, rng, cn, interp):
     got = cpu(cvb.remap(gpu(batch), gpu(mx), gpu(my), interp, C.BORDER_REPLICATE))
     for i in range(3):
         assert_exact(got[i] if cn > 1 else got[i, :, :, 0], oracle.remap(batch[i] if cn > 1 else batch[i, :, :, 0], mx, my, interp, C.BORDER_REPLICATE), "remap batch frame %d" % i)
+
+
+@pytest.mark.parametrize("shape", [(97, 131), (64, 80), (5, 7), (2, 2), (1, 9), (33, 1), (40, 51, 3), (20, 22, 4), (270, 481, 3)])
+def test_pyramids(cvb, oracle, rng, shape):
+    """cv::pyrDown / cv::pyrUp (SURVEY 8f).  8-bit: bit-exact, every border mode the reference accepts.  Float: bit-exact for pyrUp; for
+    pyrDown the reference's first / last columns and vector remainders use its scalar operation order (1 ulp): exact inside, 1e-4 there."""
+    for dt in (np.uint8, np.float32):
+        src = (rng.random(shape) * 255).astype(dt)
+        for b in (C.BORDER_REPLICATE, C.BORDER_REFLECT, C.BORDER_REFLECT_101, C.BORDER_WRAP):
+            got = cpu(cvb.pyrDown(gpu(src), borderType=b)); want = oracle.pyrDown(src, b)
+            if dt is np.uint8:
+                assert_exact(got, want, "pyrDown u8 %s b=%d" % (shape, b))
+            else:
+                assert_close(got, want, atol=1e-4, rtol=1e-6, what="pyrDown f32 %s b=%d" % (shape, b))
+                if want.shape[1] > 12:
+                    assert_exact(got[:, 1:want.shape[1] - 8], want[:, 1:want.shape[1] - 8], "pyrDown f32 interior %s b=%d" % (shape, b))
+        assert_exact(cpu(cvb.pyrUp(gpu(src))), oracle.pyrUp(src), "pyrUp %s %s" % (dt.__name__, shape))
+    batch = rng.integers(0, 256, (3,) + shape + ((1,) if len(shape) == 2 else ()), dtype=np.uint8)
+    got = cpu(cvb.pyrDown(gpu(batch)))
+    for i in range(3):
+        a = batch[i, :, :, 0] if len(shape) == 2 else batch[i]
+        assert_exact(got[i, :, :, 0] if len(shape) == 2 else got[i], oracle.pyrDown(a), "pyrDown batch")

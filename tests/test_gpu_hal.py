@@ -87,6 +87,10 @@ def test_opencv_built_with_b200_hal(cvb, ref, rng):
     assert_exact(hal.resize(img, (427, 321), 2), ref.resize(img, (427, 321), 2), "cv::resize CUBIC via HAL")
     M = np.array([[0.9, 0.1, 5], [-0.1, 0.9, 7]])
     assert_exact(hal.warpAffine(img, M, (640, 480), 1, 1), ref.warpAffine(img, M, (640, 480), 1, 1), "cv::warpAffine via HAL")
+    if hal.has("pyr_down"):
+        nb = cvb.launch_count()
+        assert_exact(hal.pyrDown(img), ref.pyrDown(img), "cv::pyrDown via HAL (hal_ni_pyrdown)")
+        assert cvb.launch_count() > nb, "cv::pyrDown did not reach the B200 HAL"
     if hal.has("remap"):
         yy, xx = np.mgrid[0:300, 0:400].astype(np.float32)
         mx = (xx * 1.5 + 10 * np.sin(yy / 20)).astype(np.float32); my = (yy * 1.55 - 8 + 5 * np.cos(xx / 30)).astype(np.float32)
