@@ -37,6 +37,8 @@
 #define cv_hal_remap32f b200cv_hal_remap32f
 #undef cv_hal_pyrdown
 #define cv_hal_pyrdown b200cv_hal_pyrdown
+#undef cv_hal_scharr
+#define cv_hal_scharr b200cv_hal_scharr
 #undef cv_hal_cvtBGRtoBGR
 #define cv_hal_cvtBGRtoBGR b200cv_hal_cvtBGRtoBGR
 #undef cv_hal_cvtBGRtoGray

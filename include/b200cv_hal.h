@@ -52,6 +52,10 @@ B200CV_API int b200cv_hal_filterFree(struct b200cvFilterCtx* context);
 B200CV_API int b200cv_hal_sobel(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                 int src_depth, int dst_depth, int cn, int margin_left, int margin_top, int margin_right, int margin_bottom,
                                 int dx, int dy, int ksize, double scale, double delta, int border_type);
+/* hal_ni_scharr, hal_replacement.hpp:1224 */
+B200CV_API int b200cv_hal_scharr(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
+                                 int src_depth, int dst_depth, int cn, int margin_left, int margin_top, int margin_right, int margin_bottom,
+                                 int dx, int dy, double scale, double delta, int border_type);
 /* hal_ni_resize, hal_replacement.hpp:257 */
 B200CV_API int b200cv_hal_resize(int src_type, const b200cv_uchar* src_data, size_t src_step, int src_width, int src_height, b200cv_uchar* dst_data,
                                  size_t dst_step, int dst_width, int dst_height, double inv_scale_x, double inv_scale_y, int interpolation);

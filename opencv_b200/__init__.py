@@ -224,6 +224,11 @@ def Sobel(src, ddepth, dx, dy, ksize=3, scale=1.0, delta=0.0, borderType=BORDER_
     return dst
 
 
+def Scharr(src, ddepth, dx, dy, scale=1.0, delta=0.0, borderType=BORDER_DEFAULT, dst=None, stream=None):
+    """cv::Scharr (imgproc.hpp:1928) = cv::Sobel with ksize = FILTER_SCHARR (deriv.cpp:468-510)"""
+    return Sobel(src, ddepth, dx, dy, -1, scale, delta, borderType, dst, stream)
+
+
 _CVT_DCN = {COLOR_BGR2BGRA: 4, COLOR_BGRA2BGR: 3, COLOR_BGR2RGBA: 4, COLOR_RGBA2BGR: 3, COLOR_BGR2RGB: 3, COLOR_BGRA2RGBA: 4,
             COLOR_BGR2GRAY: 1, COLOR_RGB2GRAY: 1, COLOR_BGRA2GRAY: 1, COLOR_RGBA2GRAY: 1, COLOR_GRAY2BGR: 3, COLOR_GRAY2BGRA: 4}
 

@@ -234,6 +234,12 @@ extern "C" int b200cv_hal_sobel(const uchar* src, size_t sstep, uchar* dst, size
     return b200cv_host_sobel(&s, &d, dx, dy, ksize, scale, delta, border);
 }
 
+extern "C" int b200cv_hal_scharr(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int sdepth, int ddepth, int cn,
+                                 int ml, int mt, int mr, int mb, int dx, int dy, double scale, double delta, int border)
+{
+    return b200cv_hal_sobel(src, sstep, dst, dstep, w, h, sdepth, ddepth, cn, ml, mt, mr, mb, dx, dy, -1, scale, delta, border);
+}
+
 extern "C" int b200cv_hal_resize(int type, const uchar* src, size_t sstep, int sw, int sh, uchar* dst, size_t dstep, int dw, int dh,
                                  double inv_x, double inv_y, int interp)
 {

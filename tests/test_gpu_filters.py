@@ -165,6 +165,18 @@ def test_sobel(cvb, oracle, rng, ksize):
                           atol=2e-2, rtol=1e-4, what="Sobel f32 k%d %d%d" % (ksize, dx, dy))
 
 
+def test_scharr(cvb, oracle, rng):
+    """cv::Scharr = cv::Sobel(ksize = FILTER_SCHARR): 3/10/3 smoothing, -1/0/1 derivative (deriv.cpp:468-510)"""
+    img = rand_u8(rng, 97, 131); img3 = rand_u8(rng, 61, 77, 3)
+    for dx, dy in ((1, 0), (0, 1)):
+        for im in (img, img3):
+            assert_exact(cpu(cvb.Scharr(gpu(im), 3, dx, dy)), oracle.Sobel(im, 3, dx, dy, -1), "Scharr s16 %d%d" % (dx, dy))
+        assert_exact_body(cpu(cvb.Scharr(gpu(img), 5, dx, dy, scale=1 / 4080., delta=0.5)), oracle.Sobel(img, 5, dx, dy, -1, scale=1 / 4080., delta=0.5), 32,
+                          atol=1e-4, rtol=2e-5, what="Scharr u8->f32 %d%d" % (dx, dy))
+        ff = (img.astype(np.float32) + 0.37) * 0.731
+        assert_exact_body(cpu(cvb.Scharr(gpu(ff), 5, dx, dy, scale=0.11)), oracle.Sobel(ff, 5, dx, dy, -1, scale=0.11), 8, atol=1e-2, rtol=1e-4, what="Scharr f32 %d%d" % (dx, dy))
+
+
 @pytest.mark.parametrize("k", [3, 5, 7, 9, 11, 13, 15, 21, 31])
 def test_filter2d(cvb, oracle, rng, k):
     img = rand_u8(rng, 97, 131); f = img.astype(np.float32)
