@@ -39,6 +39,8 @@
 #define cv_hal_pyrdown b200cv_hal_pyrdown
 #undef cv_hal_scharr
 #define cv_hal_scharr b200cv_hal_scharr
+#undef cv_hal_boxFilter
+#define cv_hal_boxFilter b200cv_hal_boxFilter
 #undef cv_hal_cvtBGRtoBGR
 #define cv_hal_cvtBGRtoBGR b200cv_hal_cvtBGRtoBGR
 #undef cv_hal_cvtBGRtoGray

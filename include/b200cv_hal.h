@@ -56,6 +56,10 @@ B200CV_API int b200cv_hal_sobel(const b200cv_uchar* src_data, size_t src_step, b
 B200CV_API int b200cv_hal_scharr(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                  int src_depth, int dst_depth, int cn, int margin_left, int margin_top, int margin_right, int margin_bottom,
                                  int dx, int dy, double scale, double delta, int border_type);
+/* hal_ni_boxFilter, hal_replacement.hpp:1105 (cv::boxFilter / cv::blur, box_filter.dispatch.cpp:474) */
+B200CV_API int b200cv_hal_boxFilter(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
+                                    int src_depth, int dst_depth, int cn, int margin_left, int margin_top, int margin_right, int margin_bottom,
+                                    size_t ksize_width, size_t ksize_height, int anchor_x, int anchor_y, bool normalize, int border_type);
 /* hal_ni_resize, hal_replacement.hpp:257 */
 B200CV_API int b200cv_hal_resize(int src_type, const b200cv_uchar* src_data, size_t src_step, int src_width, int src_height, b200cv_uchar* dst_data,
                                  size_t dst_step, int dst_width, int dst_height, double inv_scale_x, double inv_scale_y, int interpolation);
@@ -96,6 +100,7 @@ B200CV_API int b200cv_host_sep_filter2d(const b200cvMat* src, const b200cvMat* d
 B200CV_API int b200cv_host_filter2d(const b200cvMat* src, const b200cvMat* dst, const float* kernel, int kw, int kh, int anchor_x, int anchor_y,
                                     double delta, int border);
 B200CV_API int b200cv_host_sobel(const b200cvMat* src, const b200cvMat* dst, int dx, int dy, int ksize, double scale, double delta, int border);
+B200CV_API int b200cv_host_box_filter(const b200cvMat* src, const b200cvMat* dst, int ksize_w, int ksize_h, int anchor_x, int anchor_y, int normalize, int border);
 B200CV_API int b200cv_host_resize(const b200cvMat* src, const b200cvMat* dst, int interpolation);
 B200CV_API int b200cv_host_warp_affine(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags, int border, const double* border_value);
 B200CV_API int b200cv_host_warp_perspective(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags, int border, const double* border_value);

@@ -224,6 +224,23 @@ def Sobel(src, ddepth, dx, dy, ksize=3, scale=1.0, delta=0.0, borderType=BORDER_
     return dst
 
 
+def boxFilter(src, ddepth, ksize, anchor=(-1, -1), normalize=True, borderType=BORDER_DEFAULT, dst=None, stream=None):
+    """cv::boxFilter (imgproc.hpp:1603)"""
+    if not _is_torch(src):
+        from . import hal
+        return hal.boxFilter(src, ddepth, ksize, anchor, normalize, borderType, dst)
+    dst = dst if dst is not None else _new(src, dtype=_ddepth_dtype(src, ddepth))
+    ms, md = _pair(src, dst)
+    _check(lib().b200cv_box_filter(ctypes.byref(ms), ctypes.byref(md), int(ksize[0]), int(ksize[1]), int(anchor[0]), int(anchor[1]),
+                                   int(bool(normalize)), int(borderType), _stream_ptr(stream)), "boxFilter")
+    return dst
+
+
+def blur(src, ksize, anchor=(-1, -1), borderType=BORDER_DEFAULT, dst=None, stream=None):
+    """cv::blur (imgproc.hpp:1659) = boxFilter(src, -1, ksize, anchor, true, borderType)"""
+    return boxFilter(src, -1, ksize, anchor, True, borderType, dst, stream)
+
+
 def Scharr(src, ddepth, dx, dy, scale=1.0, delta=0.0, borderType=BORDER_DEFAULT, dst=None, stream=None):
     """cv::Scharr (imgproc.hpp:1928) = cv::Sobel with ksize = FILTER_SCHARR (deriv.cpp:468-510)"""
     return Sobel(src, ddepth, dx, dy, -1, scale, delta, borderType, dst, stream)

@@ -130,6 +130,8 @@ extern "C" int b200cv_host_filter2d(const b200cvMat* s, const b200cvMat* d, cons
 { return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_filter2d(a, b, k, kw, kh, ax, ay, delta, border, st); }); }
 extern "C" int b200cv_host_sobel(const b200cvMat* s, const b200cvMat* d, int dx, int dy, int ksize, double scale, double delta, int border)
 { return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_sobel(a, b, dx, dy, ksize, scale, delta, border, st); }); }
+extern "C" int b200cv_host_box_filter(const b200cvMat* s, const b200cvMat* d, int kw, int kh, int ax, int ay, int normalize, int border)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_box_filter(a, b, kw, kh, ax, ay, normalize, border, st); }); }
 extern "C" int b200cv_host_resize(const b200cvMat* s, const b200cvMat* d, int interp)
 { return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_resize(a, b, interp, st); }); }
 extern "C" int b200cv_host_warp_affine(const b200cvMat* s, const b200cvMat* d, const double* M, int flags, int border, const double* bv)
@@ -238,6 +240,15 @@ extern "C" int b200cv_hal_scharr(const uchar* src, size_t sstep, uchar* dst, siz
                                  int ml, int mt, int mr, int mb, int dx, int dy, double scale, double delta, int border)
 {
     return b200cv_hal_sobel(src, sstep, dst, dstep, w, h, sdepth, ddepth, cn, ml, mt, mr, mb, dx, dy, -1, scale, delta, border);
+}
+
+extern "C" int b200cv_hal_boxFilter(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int sdepth, int ddepth, int cn,
+                                    int ml, int mt, int mr, int mb, size_t kw, size_t kh, int ax, int ay, bool normalize, int border)
+{
+    NO_MARGINS(ml, mt, mr, mb, border);
+    if (src == dst || kw > 128 || kh > 128) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(sdepth, cn)), d = hmat(dst, dstep, w, h, B200CV_MAKETYPE(ddepth, cn));
+    return b200cv_host_box_filter(&s, &d, (int)kw, (int)kh, ax, ay, normalize ? 1 : 0, border);
 }
 
 extern "C" int b200cv_hal_resize(int type, const uchar* src, size_t sstep, int sw, int sh, uchar* dst, size_t dstep, int dw, int dh,

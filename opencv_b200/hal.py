@@ -131,6 +131,19 @@ def warpPerspective(src, M, dsize, flags=INTER_LINEAR, borderMode=BORDER_CONSTAN
     return _warp(lib().b200cv_host_warp_perspective, "warpPerspective", src, M, dsize, flags, borderMode, borderValue, dst)
 
 
+def boxFilter(src, ddepth, ksize, anchor=(-1, -1), normalize=True, borderType=BORDER_DEFAULT, dst=None):
+    dd = src.dtype if ddepth is None or ddepth < 0 else {0: np.uint8, 5: np.float32}[int(ddepth)]
+    dst = dst if dst is not None else _new(src, dtype=dd)
+    ms, md = describe(src), describe(dst)
+    _check(lib().b200cv_host_box_filter(ctypes.byref(ms), ctypes.byref(md), int(ksize[0]), int(ksize[1]), int(anchor[0]), int(anchor[1]),
+                                        int(bool(normalize)), int(borderType)), "boxFilter")
+    return dst
+
+
+def blur(src, ksize, anchor=(-1, -1), borderType=BORDER_DEFAULT, dst=None):
+    return boxFilter(src, -1, ksize, anchor, True, borderType, dst)
+
+
 def pyrDown(src, dst=None, borderType=BORDER_DEFAULT):
     m = describe(src)
     dst = dst if dst is not None else _new(src, size=((m.cols + 1) // 2, (m.rows + 1) // 2))

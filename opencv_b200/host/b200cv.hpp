@@ -127,6 +127,13 @@ inline void Sobel(const GpuMat& src, GpuMat& dst, int ddepth, int dx, int dy, in
                   Stream& s = Stream::Null())
 { B200CV_DST(dst, src, makeType(ddepth < 0 ? B200CV_DEPTH(src.type()) : ddepth, src.channels())); b200cvMat a = src.desc(), b = dst.desc();
   check(b200cv_sobel(&a, &b, dx, dy, ksize, scale, delta, borderType, s.cudaPtr()), "Sobel"); }
+// cv::boxFilter / cv::blur (imgproc.hpp:1603, :1659)
+inline void boxFilter(const GpuMat& src, GpuMat& dst, int ddepth, Size ksize, Point anchor = Point(-1, -1), bool normalize = true, int borderType = BORDER_DEFAULT,
+                      Stream& s = Stream::Null())
+{ B200CV_DST(dst, src, makeType(ddepth < 0 ? B200CV_DEPTH(src.type()) : ddepth, src.channels())); b200cvMat a = src.desc(), b = dst.desc();
+  check(b200cv_box_filter(&a, &b, ksize.width, ksize.height, anchor.x, anchor.y, normalize ? 1 : 0, borderType, s.cudaPtr()), "boxFilter"); }
+inline void blur(const GpuMat& src, GpuMat& dst, Size ksize, Point anchor = Point(-1, -1), int borderType = BORDER_DEFAULT, Stream& s = Stream::Null())
+{ boxFilter(src, dst, -1, ksize, anchor, true, borderType, s); }
 inline void resize(const GpuMat& src, GpuMat& dst, Size dsize, double fx = 0, double fy = 0, int interpolation = INTER_LINEAR, Stream& s = Stream::Null())
 { if (dsize.width <= 0) dsize = Size((int)(src.cols * fx + 0.5), (int)(src.rows * fy + 0.5));
   dst.create(dsize.height, dsize.width, src.type(), src.frames); b200cvMat a = src.desc(), b = dst.desc(); check(b200cv_resize(&a, &b, interpolation, s.cudaPtr()), "resize"); }

@@ -187,6 +187,18 @@ class Oracle:
         self._ok(self.fn("pyr_up")(_p(src), sz(src.strides[0]), w, h, cvtype(src), _p(dst), sz(dst.strides[0])), "pyrUp")
         return dst
 
+    def boxFilter(self, src, ddepth, ksize, anchor=(-1, -1), normalize=True, borderType=4):
+        src = np.ascontiguousarray(src)
+        h, w = src.shape[:2]
+        dd = {-1: src.dtype, 0: np.uint8, 5: np.float32}[int(ddepth)]
+        dst = np.zeros(src.shape, dd)
+        self._ok(self.fn("box_filter")(_p(src), sz(src.strides[0]), w, h, cvtype(src), _p(dst), sz(dst.strides[0]), int(ddepth),
+                                       int(ksize[0]), int(ksize[1]), int(anchor[0]), int(anchor[1]), int(bool(normalize)), int(borderType)), "boxFilter")
+        return dst
+
+    def blur(self, src, ksize, anchor=(-1, -1), borderType=4):
+        return self.boxFilter(src, -1, ksize, anchor, True, borderType)
+
     def cvtColor(self, src, code, dcn):
         src = np.ascontiguousarray(src)
         h, w = src.shape[:2]

@@ -306,3 +306,113 @@ PORT_API int port_sobel(const void* src, size_t sstep, void* dst, size_t dstep, 
     }
     return port_sep_filter_core(src, sstep, dst, dstep, w, h, stype, ddepth, kx, nx, ky, ny, -1, -1, delta, border);
 }
+
+/* ---- cv::boxFilter / cv::blur (box_filter.dispatch.cpp:440-498; box_filter.simd.hpp) ------------------------------------------------
+ * Sum type as createBoxFilter picks it (simd.hpp:1250-1272): 8U->8U with kw*kh <= 256 -> 16-bit sums and the integer divide of
+ * ColumnSum<ushort,uchar> (simd.hpp:430-600: d = cvRound(1/scale), (s + divDelta) * divScale >> 23); other 8U sources -> int sums,
+ * scaled as float(s) * float(scale) in the SIMD body and as double s * scale in the scalar remainder (ColumnSum<int,uchar> :275-428,
+ * <int,float> :1039-1158; remainder = last (w*cn) mod 8 resp. mod 4 elements); 32F -> double sums, RowSum direct for 3 / 5 taps and
+ * sliding otherwise (:64-172), ColumnSum sliding down the whole image (:175-272), result (float)(s * scale).
+ * Borders through cv::borderInterpolate; BORDER_CONSTANT pads with zeros (no borderValue on this path). */
+PORT_API int port_box_filter(const void* src, size_t sstep, int w, int h, int stype, void* dst, size_t dstep, int ddepth,
+                             int kw, int kh, int ax, int ay, int normalize, int border)
+{
+    int sdepth = P_DEPTH(stype), cn = P_CN(stype), b = border & ~16;
+    if (ddepth < 0) ddepth = sdepth;
+    if (ax < 0) ax = kw / 2;
+    if (ay < 0) ay = kh / 2;
+    if (kw <= 0 || kh <= 0 || ax >= kw || ay >= kh || b == PB_WRAP) return -1;
+    if (!((sdepth == P_8U && (ddepth == P_8U || ddepth == P_32F)) || (sdepth == P_32F && ddepth == P_32F))) return -1;
+    const int wn = w * cn;
+    const double scale = normalize ? 1. / ((double)kw * kh) : 1.;
+    const int have_scale = scale != 1;
+    const int u16path = sdepth == P_8U && ddepth == P_8U && kw * kh <= 256;
+    int div_scale = 1, div_delta = 0;
+    if (u16path && have_scale) {
+        int d = port_round(1. / scale);
+        double sf = (double)(1 << 23) / d;
+        div_scale = (int)floor(sf);
+        sf -= div_scale;
+        div_delta = d / 2;
+        if (sf < 0.5) div_delta++; else div_scale++;
+    }
+    /* padded source row indices */
+    int* xtab = (int*)malloc(sizeof(int) * (size_t)(w + kw));
+    for (int j = 0; j < w + kw - 1; j++) xtab[j] = port_border(j - ax, w, b);
+    const int isf = sdepth == P_32F;
+    /* row sums of every source row (int or double), then the sliding column sum in image order */
+    double* rsd = isf ? (double*)malloc(sizeof(double) * (size_t)wn * h) : NULL;
+    int* rsi = isf ? NULL : (int*)malloc(sizeof(int) * (size_t)wn * h);
+    double* padd = isf ? (double*)malloc(sizeof(double) * (size_t)(w + kw) * cn) : NULL;
+    for (int y = 0; y < h; y++) {
+        const uchar* su = (const uchar*)src + (size_t)y * sstep;
+        const float* sf = (const float*)su;
+        if (!isf) {
+            for (int e = 0; e < wn; e++) {
+                int x = e / cn, c = e - x * cn, s = 0;
+                for (int k = 0; k < kw; k++) { int sx = xtab[x + k]; s += sx < 0 ? 0 : su[sx * cn + c]; }
+                rsi[(size_t)y * wn + e] = s;
+            }
+        } else {
+            for (int j = 0; j < w + kw - 1; j++)
+                for (int c = 0; c < cn; c++) padd[j * cn + c] = xtab[j] < 0 ? 0. : (double)sf[xtab[j] * cn + c];
+            double* D = rsd + (size_t)y * wn;
+            if (kw == 3) for (int e = 0; e < wn; e++) D[e] = padd[e] + padd[e + cn] + padd[e + 2 * cn];
+            else if (kw == 5) for (int e = 0; e < wn; e++) D[e] = padd[e] + padd[e + cn] + padd[e + 2 * cn] + padd[e + 3 * cn] + padd[e + 4 * cn];
+            else
+                for (int c = 0; c < cn; c++) {
+                    double s = 0;
+                    for (int k = 0; k < kw; k++) s += padd[k * cn + c];
+                    D[c] = s;
+                    for (int x = 0; x < w - 1; x++) { s += padd[(x + kw) * cn + c] - padd[x * cn + c]; D[(x + 1) * cn + c] = s; }
+                }
+        }
+    }
+    const float scale_f = (float)scale;
+    const int tail8 = wn - wn % 8, tail4 = wn - wn % 4;
+    if (!isf) {
+        int* SUM = (int*)calloc((size_t)wn, sizeof(int));
+        for (int r = 0; r < kh - 1; r++) {
+            int sy = port_border(r - ay, h, b);
+            if (sy >= 0) for (int e = 0; e < wn; e++) SUM[e] += rsi[(size_t)sy * wn + e];
+        }
+        for (int y = 0; y < h; y++) {
+            int sp = port_border(y - ay + kh - 1, h, b), sm = port_border(y - ay, h, b);
+            uchar* du = (uchar*)dst + (size_t)y * dstep;
+            float* df = (float*)du;
+            for (int e = 0; e < wn; e++) {
+                int s0 = SUM[e] + (sp < 0 ? 0 : rsi[(size_t)sp * wn + e]);
+                if (ddepth == P_8U) {
+                    if (u16path) du[e] = have_scale ? (uchar)(((unsigned)(s0 + div_delta) * (unsigned)div_scale) >> 23) : port_sat_u8i(s0);
+                    else if (!have_scale) du[e] = port_sat_u8i(s0);
+                    else if (e < tail8) du[e] = port_sat_u8i((int)lrintf(mul_rn((float)s0, scale_f)));
+                    else du[e] = port_sat_u8i(port_round(s0 * scale));
+                } else {
+                    if (!have_scale) df[e] = (float)s0;
+                    else if (e < tail4) df[e] = mul_rn((float)s0, scale_f);
+                    else df[e] = (float)(s0 * scale);
+                }
+                SUM[e] = s0 - (sm < 0 ? 0 : rsi[(size_t)sm * wn + e]);
+            }
+        }
+        free(SUM);
+    } else {
+        double* SUM = (double*)calloc((size_t)wn, sizeof(double));
+        for (int r = 0; r < kh - 1; r++) {
+            int sy = port_border(r - ay, h, b);
+            for (int e = 0; e < wn; e++) SUM[e] += sy < 0 ? 0. : rsd[(size_t)sy * wn + e];
+        }
+        for (int y = 0; y < h; y++) {
+            int sp = port_border(y - ay + kh - 1, h, b), sm = port_border(y - ay, h, b);
+            float* df = (float*)((uchar*)dst + (size_t)y * dstep);
+            for (int e = 0; e < wn; e++) {
+                double s0 = SUM[e] + (sp < 0 ? 0. : rsd[(size_t)sp * wn + e]);
+                df[e] = have_scale ? (float)(s0 * scale) : (float)s0;
+                SUM[e] = s0 - (sm < 0 ? 0. : rsd[(size_t)sm * wn + e]);
+            }
+        }
+        free(SUM);
+    }
+    free(xtab); free(rsd); free(rsi); free(padd);
+    return 0;
+}

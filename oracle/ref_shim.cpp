@@ -178,6 +178,17 @@ API int ref_pyr_up(const void* src, size_t sstep, int sw, int sh, int type, void
     GUARD_END
 }
 
+API int ref_box_filter(const void* src, size_t sstep, int w, int h, int stype, void* dst, size_t dstep, int ddepth,
+                       int kw, int kh, int ax, int ay, int normalize, int border)
+{
+    GUARD_BEGIN
+    int dd = ddepth < 0 ? CV_MAT_DEPTH(stype) : ddepth;
+    Mat s = hdr(src, sstep, w, h, stype), d = hdr(dst, dstep, w, h, CV_MAKETYPE(dd, CV_MAT_CN(stype)));
+    boxFilter(s, d, dd, Size(kw, kh), Point(ax, ay), normalize != 0, border);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
 API int ref_invert_affine(const double* M, double* iM)
 {
     GUARD_BEGIN

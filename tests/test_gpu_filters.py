@@ -165,6 +165,36 @@ def test_sobel(cvb, oracle, rng, ksize):
                           atol=2e-2, rtol=1e-4, what="Sobel f32 k%d %d%d" % (ksize, dx, dy))
 
 
+@pytest.mark.parametrize("cn", [1, 3, 4])
+@pytest.mark.parametrize("border", [4, 1, 0, 2])
+def test_box_filter(cvb, oracle, rng, cn, border):
+    """cv::boxFilter / cv::blur (box_filter.simd.hpp): 8U->8U with 16-bit sums + integer divide (area <= 256), 8U->8U with int sums
+    (float scale in the SIMD body, double in the last w*cn % 8 elements), 8U->32F (w*cn % 4), 32F->32F with double sums: all bit-exact"""
+    for (h, w) in ((97, 131), (64, 200), (33, 37)):
+        u8 = rand_u8(rng, h, w, cn)
+        f32 = (rng.random(u8.shape, dtype=np.float32) * 255).astype(np.float32)
+        for ks in ((3, 3), (5, 5), (7, 3), (2, 4), (16, 16), (17, 17), (20, 20), (1, 1), (31, 9)):
+            for norm in (True, False):
+                anchor = (-1, -1) if ks != (7, 3) else (6, 0)
+                what = "boxFilter %%s cn=%d %s ks=%s norm=%d border=%d" % (cn, (h, w), ks, norm, border)
+                assert_exact(cpu(cvb.boxFilter(gpu(u8), -1, ks, anchor, norm, border)), oracle.boxFilter(u8, -1, ks, anchor, norm, border), what % "8U")
+                assert_exact(cpu(cvb.boxFilter(gpu(u8), 5, ks, anchor, norm, border)), oracle.boxFilter(u8, 5, ks, anchor, norm, border), what % "8U->32F")
+                assert_exact(cpu(cvb.boxFilter(gpu(f32), -1, ks, anchor, norm, border)), oracle.boxFilter(f32, -1, ks, anchor, norm, border), what % "32F")
+    assert_exact(cpu(cvb.blur(gpu(u8), (9, 9))), oracle.blur(u8, (9, 9)), "blur")
+
+
+def test_box_filter_batch_4k(cvb, ref, rng):
+    """4 frames of 3840x2160 8UC1 in one launch, 5x5 and 21x21 (both sum types), unaligned destination pitch handled by the byte-store path"""
+    base = rand_u8(rng, 2160, 3840)
+    batch = np.stack([np.roll(base, 7 * i, axis=1) for i in range(4)])[..., None]
+    for ks in ((5, 5), (21, 21)):
+        out = cpu(cvb.blur(gpu(batch), ks))
+        for f in (0, 3):
+            assert_exact(out[f, :, :, 0], ref.blur(batch[f, :, :, 0], ks), "blur 4K frame %d %s" % (f, ks))
+    odd = rand_u8(rng, 301, 1001)
+    assert_exact(cpu(cvb.blur(gpu(odd), (3, 3))), ref.blur(odd, (3, 3)), "blur 1001-wide")
+
+
 def test_scharr(cvb, oracle, rng):
     """cv::Scharr = cv::Sobel(ksize = FILTER_SCHARR): 3/10/3 smoothing, -1/0/1 derivative (deriv.cpp:468-510)"""
     img = rand_u8(rng, 97, 131); img3 = rand_u8(rng, 61, 77, 3)

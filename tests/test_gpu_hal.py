@@ -63,6 +63,8 @@ def test_host_batch_pipeline(cvb, oracle, rng):
     mx = (xx * 2.1 + 3).astype(np.float32); my = (yy * 2.3 + 5 * np.sin(xx / 17)).astype(np.float32)
     rm = hal.remap(batch[:3], mx, my, 2, 4)
     assert_exact(rm[2], oracle.remap(batch[2], mx, my, 2, 4), "host remap")
+    bl = hal.blur(batch[:5], (11, 11))
+    assert_exact(bl[4], oracle.blur(batch[4], (11, 11)), "host blur")
     w = hal.warpAffine(batch[:3], M, (640, 480))
     assert_exact(w[1], oracle.warpAffine(batch[1], M, (640, 480)), "host warpAffine")
     r = hal.matchTemplate(batch[0, :, :, 0].copy(), batch[0, 100:132, 200:232, 0].copy(), C.TM_CCORR_NORMED)
@@ -91,6 +93,11 @@ def test_opencv_built_with_b200_hal(cvb, ref, rng):
         nb = cvb.launch_count()
         assert_exact(hal.pyrDown(img), ref.pyrDown(img), "cv::pyrDown via HAL (hal_ni_pyrdown)")
         assert cvb.launch_count() > nb, "cv::pyrDown did not reach the B200 HAL"
+    if hal.has("box_filter"):
+        nb = cvb.launch_count()
+        assert_exact(hal.blur(img, (5, 5)), ref.blur(img, (5, 5)), "cv::blur via HAL (hal_ni_boxFilter)")
+        assert_exact(hal.boxFilter(g, 5, (19, 19), (-1, -1), True, 1), ref.boxFilter(g, 5, (19, 19), (-1, -1), True, 1), "cv::boxFilter 8U->32F via HAL")
+        assert cvb.launch_count() - nb >= 2, "cv::boxFilter did not reach the B200 HAL"
     if hal.has("remap"):
         yy, xx = np.mgrid[0:300, 0:400].astype(np.float32)
         mx = (xx * 1.5 + 10 * np.sin(yy / 20)).astype(np.float32); my = (yy * 1.55 - 8 + 5 * np.cos(xx / 30)).astype(np.float32)
