@@ -9,8 +9,12 @@
 //   32F -> 32F ............... double sums, float(s * scale).  The reference slides its sums along the row and down the whole
 //                              image; here every window is summed on its own.  Both are exact (and equal) unless a double
 //                              addition rounds, i.e. the window spans > 2^29 in magnitude.
-// One CTA = 128 destination elements x 32 rows: horizontal sums of the 32 + kh - 1 source rows of the tile go to shared memory
+// 8U -> 8U with odd sizes <= 31 around the centre runs on the TMA + IDP4A/IDP2A kernel of GaussianBlur (gauss_u8.cu) with all taps 1
+// and the epilogues above; everything else on the kernel of this file:
+// one CTA = 128 destination elements x 32 rows: horizontal sums of the 32 + kh - 1 source rows of the tile go to shared memory
 // (taps through a per-CTA border table), then each thread slides one column down 16 rows.
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace b200cv {
@@ -154,17 +158,27 @@ extern "C" int b200cv_box_filter(const b200cvMat* src, const b200cvMat* dst, int
     p.tail_from = wn - wn % (u8u8 ? 8 : 4);
     p.pack4 = ddepth == B200CV_8U && ((size_t)dst->data % 4 == 0) && dst->step % 4 == 0 && (d.frames == 1 || dst->frame_step % 4 == 0);
     cudaStream_t st = as_stream(stream);
-    if (u8u8 && ksize_w * ksize_h <= 256) {
-        if (p.have_scale) {            // ColumnSum<ushort,uchar> constructor, box_filter.simd.hpp:435-455
-            const int dv = (int)nearbyint(1. / p.scale);
-            double sf = (double)(1 << 23) / dv;
-            p.div_scale = (int)floor(sf);
-            sf -= p.div_scale;
-            p.div_delta = dv / 2;
-            if (sf < 0.5) p.div_delta++; else p.div_scale++;
-        }
-        return box_launch<uchar, int, uchar, BX_U16>(s, d, p, st);
+    const bool u16sums = u8u8 && ksize_w * ksize_h <= 256;
+    if (u16sums && p.have_scale) {            // ColumnSum<ushort,uchar> constructor, box_filter.simd.hpp:435-455
+        const int dv = (int)nearbyint(1. / p.scale);
+        double sf = (double)(1 << 23) / dv;
+        p.div_scale = (int)floor(sf);
+        sf -= p.div_scale;
+        p.div_delta = dv / 2;
+        if (sf < 0.5) p.div_delta++; else p.div_scale++;
     }
+    // 8U -> 8U, odd sizes up to 31 around the centre: the TMA + IDP4A/IDP2A kernel of GaussianBlur with all taps 1 and a box epilogue
+    const char* path = getenv("B200CV_BOX_PATH");                       // test hook: "generic" keeps every call on the kernel of this file
+    if (u8u8 && (ksize_w & 1) && (ksize_h & 1) && anchor_x == ksize_w / 2 && anchor_y == ksize_h / 2 && !(path && !strcmp(path, "generic"))) {
+        int64_t ones[32];
+        for (int i = 0; i < 32; i++) ones[i] = 1;
+        GU8Box b;
+        b.have_scale = p.have_scale; b.tail_from = p.tail_from; b.div_scale = (unsigned)p.div_scale; b.div_delta = (unsigned)p.div_delta;
+        b.scale_f = p.scale_f; b.scale = p.scale;
+        rc = gauss_u8_fast(s, d, cn, ones, ksize_w, ones, ksize_h, border, st, u16sums ? 2 : 3, 0, &b);
+        if (rc != B200CV_NOT_IMPLEMENTED) return rc;
+    }
+    if (u16sums) return box_launch<uchar, int, uchar, BX_U16>(s, d, p, st);
     if (u8u8) return box_launch<uchar, int, uchar, BX_INT_U8>(s, d, p, st);
     if (u8f) return box_launch<uchar, int, float, BX_INT_F32>(s, d, p, st);
     return box_launch<float, double, float, BX_F64_F32>(s, d, p, st);

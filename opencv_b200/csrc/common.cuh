@@ -115,4 +115,16 @@ struct SepTaps {           // up to 33 taps per direction, by value in kernel pa
     int nx, ny, ax, ay;
 };
 
+// epilogue of cv::boxFilter on the 8-bit TMA kernel (gauss_u8.cu; box_filter.simd.hpp): sep_mode 2 = ColumnSum<ushort,uchar>,
+// (s + div_delta) * div_scale >> 23; sep_mode 3 = ColumnSum<int,uchar>, cvRound(float(s) * scale_f) for elements < tail_from and
+// cvRound(double(s) * scale) after them; !have_scale: saturate
+struct GU8Box {
+    int have_scale, tail_from;
+    unsigned div_scale, div_delta;
+    float scale_f;
+    double scale;
+};
+int gauss_u8_fast(const Img& s, const Img& d, int cn, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st, int sep_mode = 0, int even_limit = 0,
+                  const GU8Box* box = nullptr);
+
 }  // namespace b200cv

@@ -31,6 +31,7 @@ struct GU8Params {
     uint32_t kyw[4][9];         // column taps for output row phase o (0..3) and row group g: byte i = ky[4g + i - o] or 0
     int W, H, TH, border;
     int sep_mode, even_limit;   // sepFilter2D's 8.8 fixed-point mode: columns < even_limit round half-to-even, the rest half-up (filter.simd.hpp:1011-1100)
+    GU8Box box;                 // sep_mode 2 / 3: cv::boxFilter epilogues on the plain window sum (all taps 1)
 };
 
 __host__ __device__ constexpr bool gu_nz(int KB, int o, int g) { return 4 * g - o < KB; }
@@ -39,7 +40,7 @@ __host__ __device__ constexpr bool gu_nz(int KB, int o, int g) { return 4 * g - 
 // the column pass does not see channels at all.  Tile width in elements so that apron + tile + apron fits one 256-byte TMA box row.
 template <int CN> struct GUTile { static constexpr int TW = CN == 1 ? 192 : CN == 3 ? 160 : 128; };
 
-template <int KB, int CN>
+template <int KB, int CN, bool BOX>
 __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const __grid_constant__ CUtensorMap tmap, Img dst, const __grid_constant__ GU8Params p)
 {
     constexpr int GU_TW = GUTile<CN>::TW;            // (shadows the single-channel constant)
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const __grid_cons
 #pragma unroll
             for (int o = 0; o < 4; o++)
 #pragma unroll
-                for (int c = 0; c < 4; c++) acc[o][c] = p.sep_mode ? 32767u : 32768u;
+                for (int c = 0; c < 4; c++) acc[o][c] = BOX ? 0u : p.sep_mode ? 32767u : 32768u;
             const uint32_t* mp0 = s_mid + (q * 2) * GU_TW + cg * 4;
 #pragma unroll
             for (int g = 0; g < GV; g++) {
@@ -192,7 +193,20 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const __grid_cons
                     }
                 }
             }
-            if (p.sep_mode) {
+            if constexpr (BOX) {                                         // box filter: result byte goes to bits 16..23 for the pack below
+                const bool body = x0 + cg * 4 < p.box.tail_from;         // uniform over the 4 columns: tail_from is a multiple of 8
+#pragma unroll
+                for (int o = 0; o < 4; o++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint32_t s = acc[o][c];
+                        uint32_t r;
+                        if (!p.box.have_scale) r = min(s, 255u) << 16;
+                        else if (p.sep_mode == 2) r = ((s + p.box.div_delta) * p.box.div_scale) >> 7;
+                        else r = (uint32_t)min(body ? __float2int_rn(__fmul_rn(__uint2float_rn(s), p.box.scale_f)) : __double2int_rn(__dmul_rn((double)s, p.box.scale)), 255) << 16;
+                        acc[o][c] = r;
+                    }
+            } else if (p.sep_mode) {
                 const bool half_even = x0 + cg * 4 < p.even_limit;      // uniform over the 4 columns: even_limit is a multiple of 16
 #pragma unroll
                 for (int o = 0; o < 4; o++)
@@ -230,8 +244,9 @@ __global__ void __launch_bounds__(256, 4) gauss_u8_dp4a_kernel(const __grid_cons
 template <int KB, int CN>
 static int launch_gu8_cn(const CUtensorMap& tm, const Img& d, const GU8Params& p, int frames, cudaStream_t st)
 {
+    auto kern = p.sep_mode >= 2 ? gauss_u8_dp4a_kernel<KB, CN, true> : gauss_u8_dp4a_kernel<KB, CN, false>;
     dim3 grid(div_up((unsigned)p.W, GUTile<CN>::TW), div_up((unsigned)p.H, (unsigned)p.TH), (unsigned)frames);
-    gauss_u8_dp4a_kernel<KB, CN><<<grid, 256, 0, st>>>(tm, d, p);
+    kern<<<grid, 256, 0, st>>>(tm, d, p);
     cudaError_t e = cudaGetLastError();
     count_launch();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
@@ -247,7 +262,8 @@ static int launch_gu8(const CUtensorMap& tm, const Img& d, const GU8Params& p, i
 }
 
 // returns B200CV_NOT_IMPLEMENTED when the fast path does not apply (caller falls back to the generic kernel)
-int gauss_u8_fast(const Img& s, const Img& d, int cn, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st, int sep_mode, int even_limit)
+int gauss_u8_fast(const Img& s, const Img& d, int cn, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st, int sep_mode, int even_limit,
+                  const GU8Box* box)
 {
     if (cn != 1 && cn != 3 && cn != 4) return B200CV_NOT_IMPLEMENTED;
     if (!(kw & 1) || !(kh & 1) || kw < 3 || kh < 3 || kw > 31 || kh > 31) return B200CV_NOT_IMPLEMENTED;
@@ -276,6 +292,7 @@ int gauss_u8_fast(const Img& s, const Img& d, int cn, const int64_t* fx, int kw,
             p.kyw[o][g] = w;
         }
     p.W = s.cols * cn; p.H = s.rows; p.border = border; p.sep_mode = sep_mode; p.even_limit = even_limit;      // W in byte elements
+    if (box) p.box = *box;
     p.TH = ((64 - (KB - 1)) / 4) * 4;
     CUtensorMap tm;
     int rc = make_tensor_map_3d(&tm, s.data, 1, s.cols * cn, s.rows, s.frames, s.step, s.fstep, GU_IW, p.TH + KB - 1);   // box start x0-RA: 16-byte aligned

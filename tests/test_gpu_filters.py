@@ -183,6 +183,21 @@ def test_box_filter(cvb, oracle, rng, cn, border):
     assert_exact(cpu(cvb.blur(gpu(u8), (9, 9))), oracle.blur(u8, (9, 9)), "blur")
 
 
+def test_box_filter_both_u8_kernels(cvb, oracle, rng, monkeypatch):
+    """odd, centred 8U->8U boxes run on the TMA + IDP4A/IDP2A kernel (epilogue modes 2 / 3); B200CV_BOX_PATH=generic keeps them on the
+    shared-memory kernel of boxfilter.cu: both must return the reference's bytes, 16-bit-sum and int-sum cases, every channel count"""
+    for cn in (1, 3, 4):
+        img = rand_u8(rng, 203, 331, cn)                       # 331 * cn % 8 != 0: the double-scaled remainder columns exist
+        for ks in ((3, 3), (5, 5), (15, 15), (9, 3), (17, 17), (31, 31), (21, 13)):
+            for norm in (True, False):
+                for border in (4, 0, 1):
+                    want = oracle.boxFilter(img, -1, ks, (-1, -1), norm, border)
+                    for path in ("", "generic"):
+                        monkeypatch.setenv("B200CV_BOX_PATH", path)
+                        assert_exact(cpu(cvb.boxFilter(gpu(img), -1, ks, (-1, -1), norm, border)), want,
+                                     "boxFilter path=%r cn=%d ks=%s norm=%d border=%d" % (path, cn, ks, norm, border))
+
+
 def test_box_filter_batch_4k(cvb, ref, rng):
     """4 frames of 3840x2160 8UC1 in one launch, 5x5 and 21x21 (both sum types), unaligned destination pitch handled by the byte-store path"""
     base = rand_u8(rng, 2160, 3840)
