@@ -40,6 +40,21 @@ def available(kind):
     return os.path.exists(_path(kind))
 
 
+def yuv_dst_shape(sw, sh, code):
+    """(width, height, channels) of cv::cvtColor's destination for the subsampled-YUV codes (color.cpp:323-372)"""
+    if 90 <= code <= 105:
+        return sw, sh * 2 // 3, (4 if code in (94, 95, 96, 97, 102, 103, 104, 105) else 3)
+    if code == 106:
+        return sw, sh * 2 // 3, 1
+    if 107 <= code <= 122:
+        return sw, sh, (4 if code in (111, 112, 119, 120, 121, 122) else 3)
+    if code in (123, 124):
+        return sw, sh, 1
+    if 127 <= code <= 134:
+        return sw, sh * 3 // 2, 1
+    raise ValueError("not a subsampled-YUV code: %d" % code)
+
+
 class Oracle:
     def __init__(self, kind="ref"):
         self.kind = kind
@@ -205,6 +220,16 @@ class Oracle:
         dst = np.empty((h, w) if dcn == 1 else (h, w, dcn), src.dtype)
         self._ok(self.fn("cvt_color")(_p(src), sz(src.strides[0]), _p(dst), sz(dst.strides[0]), w, h, cvtype(src), cvtype(dst),
                                       int(code)), "cvtColor")
+        return dst
+
+    def cvtColorYUV(self, src, code):
+        """subsampled YUV wire formats (codes 90-134): destination shape follows from the code"""
+        src = np.ascontiguousarray(src)
+        sh, sw = src.shape[:2]
+        scn = 1 if src.ndim == 2 else src.shape[2]
+        dw, dh, dcn = yuv_dst_shape(sw, sh, code)
+        dst = np.zeros((dh, dw) if dcn == 1 else (dh, dw, dcn), np.uint8)
+        self._ok(self.fn("cvt_color_yuv")(_p(src), sz(src.strides[0]), sw, sh, scn, _p(dst), sz(dst.strides[0]), dw, dh, dcn, int(code)), "cvtColor(YUV)")
         return dst
 
     def matchTemplate(self, image, templ, method):

@@ -111,3 +111,95 @@ PORT_API int port_cvt_color(const void* src_, size_t sstep, void* dst_, size_t d
     }
     return 0;
 }
+
+/* ---- subsampled YUV wire formats (color_yuv.simd.hpp:1018-2202; BT.601 limited range, 20-bit fixed point) -----------------------------
+ * 4:2:0 two-plane NV12 / NV21 (codes 90-97), three-plane YV12 / IYUV (98-105), Y extraction (106), 4:2:2 UYVY / YUY2 / YVYU (107-124),
+ * BGR(A) / RGB(A) -> IYUV / YV12 (127-134).  A 4:2:0 image of W x H pixels is one 8-bit plane of H*3/2 rows: Y rows, then the chroma:
+ * interleaved (NV) rows of W bytes, or planar half rows of W/2 bytes, two to a row, all U (V for YV12) rows before the others.
+ *   ruv = 2^19 + 1673527 (v-128);  guv = 2^19 - 852492 (v-128) - 409993 (u-128);  buv = 2^19 + 2116026 (u-128)      (:1043-1052)
+ *   y' = max(0, y-16) * 1220542;   c = saturate((y' + cuv) >> 20)                                                     (:1090-1099)
+ *   Y = (269484 r + 528482 g + 102760 b + 2^19 + (16 << 20)) >> 20;  U, V likewise from the EVEN row, EVEN column pixel (:1473-1523) */
+static void yuv_px(int y, int u, int v, int bidx, int dcn, uchar* d)
+{
+    int uu = u - 128, vv = v - 128;
+    int ruv = (1 << 19) + 1673527 * vv, guv = (1 << 19) - 852492 * vv - 409993 * uu, buv = (1 << 19) + 2116026 * uu;
+    int yy = (y - 16 > 0 ? y - 16 : 0) * 1220542;
+    d[2 - bidx] = port_sat_u8i((yy + ruv) >> 20);
+    d[1] = port_sat_u8i((yy + guv) >> 20);
+    d[bidx] = port_sat_u8i((yy + buv) >> 20);
+    if (dcn == 4) d[3] = 255;
+}
+
+PORT_API int port_cvt_color_yuv(const void* src_, size_t sstep, int sw, int sh, int scn, void* dst_, size_t dstep, int dw, int dh, int dcn, int code)
+{
+    const uchar* src = (const uchar*)src_;
+    uchar* dst = (uchar*)dst_;
+    if (code >= 90 && code <= 105) {                         /* 4:2:0 -> BGR family */
+        if (scn != 1 || sw != dw || sh != dh * 3 / 2 || (dw & 1) || (dh & 1) || (dcn != 3 && dcn != 4)) return -1;
+        const int planar = code >= 98;
+        int rgb, uidx;                                       /* uidx 1: V comes first */
+        if (!planar) { int c = code - 90; rgb = !(c & 1); uidx = (c >> 1) & 1; }
+        else { int c = (code - 98) & 3; rgb = !(c & 1); uidx = c < 2; }
+        const int bidx = rgb ? 2 : 0;
+        for (int y = 0; y < dh; y++)
+            for (int x = 0; x < dw; x++) {
+                int u, v;
+                if (!planar) {
+                    const uchar* uv = src + (size_t)(dh + y / 2) * sstep + (x & ~1);
+                    u = uv[uidx]; v = uv[1 - uidx];
+                } else {
+                    int k0 = y / 2, k1 = dh / 2 + y / 2;      /* half-row index of the first / second chroma plane */
+                    int a = src[(size_t)(dh + k0 / 2) * sstep + (k0 & 1) * (dw / 2) + x / 2];
+                    int b = src[(size_t)(dh + k1 / 2) * sstep + (k1 & 1) * (dw / 2) + x / 2];
+                    u = uidx ? b : a; v = uidx ? a : b;
+                }
+                yuv_px(src[(size_t)y * sstep + x], u, v, bidx, dcn, dst + (size_t)y * dstep + x * dcn);
+            }
+        return 0;
+    }
+    if (code == 106) {                                       /* Y plane of a 4:2:0 image */
+        if (scn != 1 || dcn != 1 || sw != dw || sh != dh * 3 / 2) return -1;
+        for (int y = 0; y < dh; y++) memcpy(dst + (size_t)y * dstep, src + (size_t)y * sstep, (size_t)dw);
+        return 0;
+    }
+    if ((code >= 107 && code <= 124) && code != 109 && code != 110 && code != 113 && code != 114) {   /* 4:2:2 interleaved, 2 bytes / pixel */
+        if (scn != 2 || sw != dw || sh != dh || (dw & 1)) return -1;
+        if (code >= 123) {
+            if (dcn != 1) return -1;
+            for (int y = 0; y < dh; y++)
+                for (int x = 0; x < dw; x++) dst[(size_t)y * dstep + x] = src[(size_t)y * sstep + 2 * x + (code == 123 ? 1 : 0)];
+            return 0;
+        }
+        if (dcn != 3 && dcn != 4) return -1;
+        const int ycn = (code == 107 || code == 108 || code == 111 || code == 112) ? 1 : 0;      /* UYVY: luma in the odd bytes */
+        const int yvyu = code == 117 || code == 118 || code == 121 || code == 122;
+        const int rgb = code == 107 || code == 111 || code == 115 || code == 117 || code == 119 || code == 121;
+        const int uoff = 1 - ycn + yvyu * 2, voff = (2 + uoff) % 4, bidx = rgb ? 2 : 0;
+        for (int y = 0; y < dh; y++)
+            for (int x = 0; x < dw; x++) {
+                const uchar* q = src + (size_t)y * sstep + (x >> 1) * 4;
+                yuv_px(q[ycn + (x & 1) * 2], q[uoff], q[voff], bidx, dcn, dst + (size_t)y * dstep + x * dcn);
+            }
+        return 0;
+    }
+    if (code >= 127 && code <= 134) {                        /* BGR family -> IYUV / YV12 */
+        if (dcn != 1 || sw != dw || dh != sh * 3 / 2 || (sw & 1) || (sh & 1) || (scn != 3 && scn != 4)) return -1;
+        const int c = (code - 127) & 3, rgb = !(c & 1), yv12 = code >= 131;   /* the channel count is the source's, whatever the code says (the reference's own KAT feeds 3 channels to the RGBA codes) */
+        const int bidx = rgb ? 2 : 0, w = sw, h = sh;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                const uchar* p = src + (size_t)y * sstep + x * scn;
+                int b = p[bidx], g = p[1], r = p[2 - bidx];
+                dst[(size_t)y * dstep + x] = port_sat_u8i((269484 * r + 528482 * g + 102760 * b + (1 << 19) + (16 << 20)) >> 20);
+                if (!(y & 1) && !(x & 1)) {
+                    int uu = (-155188 * r - 305135 * g + 460324 * b + (1 << 19) + (128 << 20)) >> 20;
+                    int vv = (460324 * r - 385875 * g - 74448 * b + (1 << 19) + (128 << 20)) >> 20;
+                    int ku = y / 2 + (yv12 ? h / 2 : 0), kv = y / 2 + (yv12 ? 0 : h / 2);
+                    dst[(size_t)(h + ku / 2) * dstep + (ku & 1) * (w / 2) + x / 2] = port_sat_u8i(uu);
+                    dst[(size_t)(h + kv / 2) * dstep + (kv & 1) * (w / 2) + x / 2] = port_sat_u8i(vv);
+                }
+            }
+        return 0;
+    }
+    return -1;
+}

@@ -223,6 +223,15 @@ API int ref_cvt_color(const void* src, size_t sstep, void* dst, size_t dstep, in
     GUARD_END
 }
 
+API int ref_cvt_color_yuv(const void* src, size_t sstep, int sw, int sh, int scn, void* dst, size_t dstep, int dw, int dh, int dcn, int code)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, sw, sh, CV_MAKETYPE(CV_8U, scn)), d = hdr(dst, dstep, dw, dh, CV_MAKETYPE(CV_8U, dcn));
+    cvtColor(s, d, code, dcn);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
 API int ref_match_template(const void* img, size_t istep, int iw, int ih, const void* templ, size_t tstep, int tw, int th,
                            int type, float* result, size_t rstep, int method)
 {

@@ -4,6 +4,7 @@
   * the product's host-side coefficient tables against both.
 """
 import os
+import sys
 import zlib
 
 import numpy as np
@@ -84,10 +85,48 @@ def test_port_cvtcolor_known_answer_hashes(port, code):
     assert zlib.adler32(np.ascontiguousarray(port.cvtColor(img, code, dcn)).tobytes()) == KAT[code]
 
 
+# modules/imgproc/test/test_color.cpp:2857-2900 (Imgproc_cvtColor_BE, "packed input"): code -> (adler32, input fixture)
+KAT_YUV = {90: 0x46a1bb76, 91: 0x3843bb76, 92: 0xf3fdf2ea, 93: 0x6e84f2ea, 94: 0xb6a16bd3, 95: 0xa8436bd3, 96: 0x1c7fa347, 97: 0x96f7a347,
+           98: 0xc5da1651, 99: 0x12161651, 100: 0xb4e62ea5, 101: 0xfa632ea5, 102: 0x0db4c69f, 103: 0x59e1c69f, 104: 0xfe09def3, 105: 0x4395def3,
+           106: 0xf672b440,
+           107: 0x69bea2c1, 108: 0xdc51a2c1, 111: 0x851eab45, 112: 0xf7b1ab45, 115: 0x607e8889, 116: 0xfb148889, 117: 0x239b13d4, 118: 0x402b13d4,
+           119: 0xf6af910d, 120: 0x9154910d, 121: 0x14481c58, 122: 0x30d81c58, 123: 0x228e669c, 124: 0x125c62fd,
+           127: 0x44bb076a, 128: 0xf908ff52, 129: 0x44bb076a, 130: 0xf908ff52, 131: 0x1b0d076a, 132: 0xda8aff52, 133: 0x1b0d076a, 134: 0xda8aff52}
+
+
+def kat_yuv_input(code):
+    name = "cvtcolor_kat_yuv420_input.npy" if code <= 106 else "cvtcolor_kat_yuv422_input.npy" if code <= 124 else "cvtcolor_kat_bgr_262x254_input.npy"
+    return np.load(os.path.join(GOLD, name))
+
+
+@pytest.mark.parametrize("code", sorted(KAT_YUV))
+def test_port_yuv_wire_formats_known_answer_hashes(port, code):
+    """NV12 / NV21 / YV12 / IYUV / UYVY / YUY2 / YVYU -> BGR family, Y extraction, BGR family -> I420 / YV12: the port reproduces the
+    reference's own known-answer hashes (the RGBA codes are fed the 3-channel image, as the reference's test does)"""
+    assert zlib.adler32(np.ascontiguousarray(port.cvtColorYUV(kat_yuv_input(code), code)).tobytes()) == KAT_YUV[code]
+
+
+def test_port_vs_reference_yuv_wire_formats(ref, port, rng):
+    for (h, w) in [(4, 6), (18, 34), (36, 66), (250, 320), (480, 642)]:        # h % 4 == 2: the V plane starts in the middle of a row
+        yuv = rng.integers(0, 256, (h * 3 // 2, w), dtype=np.uint8)
+        for code in range(90, 107):
+            assert np.array_equal(ref.cvtColorYUV(yuv, code), port.cvtColorYUV(yuv, code)), "4:2:0 code %d %dx%d" % (code, w, h)
+        y2 = rng.integers(0, 256, (h, w, 2), dtype=np.uint8)
+        for code in (107, 108, 111, 112, 115, 116, 117, 118, 119, 120, 121, 122, 123, 124):
+            assert np.array_equal(ref.cvtColorYUV(y2, code), port.cvtColorYUV(y2, code)), "4:2:2 code %d %dx%d" % (code, w, h)
+        for code in range(127, 135):
+            img = rng.integers(0, 256, (h, w, 4 if (code - 127) & 2 else 3), dtype=np.uint8)
+            assert np.array_equal(ref.cvtColorYUV(img, code), port.cvtColorYUV(img, code)), "to 4:2:0 code %d %dx%d" % (code, w, h)
+
+
 def test_kat_input_is_the_reference_rng_stream(ref):
     """tests/golden/cvtcolor_kat_input.npy was generated by cv::RNG(0).fill(263x255 8UC3, UNIFORM, 0, 255) -- regenerate and compare"""
     img = np.load(os.path.join(GOLD, "cvtcolor_kat_input.npy"))
     assert_exact(ref.rng_fill((255, 263, 3), np.uint8, 0, 0, 255), img, "KAT input")
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLD), "..", "tools"))
+    import make_golden
+    for name, shape in make_golden.FIXTURES.items():
+        assert_exact(ref.rng_fill(shape, np.uint8, 0, 0, 255), np.load(os.path.join(GOLD, name)), name)
 
 
 def test_product_and_port_gaussian_kernels_match_reference(ref, port):
