@@ -39,6 +39,14 @@
 #define cv_hal_pyrdown b200cv_hal_pyrdown
 #undef cv_hal_scharr
 #define cv_hal_scharr b200cv_hal_scharr
+#undef cv_hal_cvtTwoPlaneYUVtoBGR
+#define cv_hal_cvtTwoPlaneYUVtoBGR b200cv_hal_cvtTwoPlaneYUVtoBGR
+#undef cv_hal_cvtThreePlaneYUVtoBGR
+#define cv_hal_cvtThreePlaneYUVtoBGR b200cv_hal_cvtThreePlaneYUVtoBGR
+#undef cv_hal_cvtBGRtoThreePlaneYUV
+#define cv_hal_cvtBGRtoThreePlaneYUV b200cv_hal_cvtBGRtoThreePlaneYUV
+#undef cv_hal_cvtOnePlaneYUVtoBGR
+#define cv_hal_cvtOnePlaneYUVtoBGR b200cv_hal_cvtOnePlaneYUVtoBGR
 #undef cv_hal_boxFilter
 #define cv_hal_boxFilter b200cv_hal_boxFilter
 #undef cv_hal_cvtBGRtoBGR

@@ -92,6 +92,17 @@ B200CV_API int b200cv_hal_cvtBGRtoHSV(const b200cv_uchar* src_data, size_t src_s
                                       int depth, int scn, bool swapBlue, bool isFullRange, bool isHSV);
 B200CV_API int b200cv_hal_cvtHSVtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                       int depth, int dcn, bool swapBlue, bool isFullRange, bool isHSV);
+/* subsampled YUV wire formats: hal_ni_cvtTwoPlaneYUVtoBGR :664 (NV12 uIdx 0 / NV21 uIdx 1, one buffer), cvtThreePlaneYUVtoBGR :763
+ * (IYUV uIdx 0 / YV12 uIdx 1), cvtBGRtoThreePlaneYUV :797 (IYUV uIdx 1 / YV12 uIdx 2: color.hpp:162-176), cvtOnePlaneYUVtoBGR :833
+ * (YUY2 uIdx 0 ycn 0, YVYU uIdx 1 ycn 0, UYVY uIdx 0 ycn 1) */
+B200CV_API int b200cv_hal_cvtTwoPlaneYUVtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int dst_width, int dst_height,
+                                              int dcn, bool swapBlue, int uIdx);
+B200CV_API int b200cv_hal_cvtThreePlaneYUVtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int dst_width, int dst_height,
+                                                int dcn, bool swapBlue, int uIdx);
+B200CV_API int b200cv_hal_cvtBGRtoThreePlaneYUV(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
+                                                int scn, bool swapBlue, int uIdx);
+B200CV_API int b200cv_hal_cvtOnePlaneYUVtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
+                                              int dcn, bool swapBlue, int uIdx, int ycn);
 
 /* ---- batched host API (what cv::-signature wrappers over cv::Mat call; pipelined over 3 streams) ----------------------- */
 B200CV_API int b200cv_host_gaussian_blur(const b200cvMat* src, const b200cvMat* dst, int ksize_w, int ksize_h, double sigma_x, double sigma_y, int border);

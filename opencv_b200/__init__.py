@@ -38,6 +38,20 @@ COLOR_BGR2YCrCb, COLOR_RGB2YCrCb, COLOR_YCrCb2BGR, COLOR_YCrCb2RGB = 36, 37, 38,
 COLOR_BGR2HSV, COLOR_RGB2HSV, COLOR_HSV2BGR, COLOR_HSV2RGB = 40, 41, 54, 55
 COLOR_BGR2HSV_FULL, COLOR_RGB2HSV_FULL, COLOR_HSV2BGR_FULL, COLOR_HSV2RGB_FULL = 66, 67, 70, 71
 COLOR_BGR2YUV, COLOR_RGB2YUV, COLOR_YUV2BGR, COLOR_YUV2RGB = 82, 83, 84, 85
+# subsampled-YUV wire formats (imgproc.hpp: ColorConversionCodes 90-134)
+COLOR_YUV2RGB_NV12, COLOR_YUV2BGR_NV12, COLOR_YUV2RGB_NV21, COLOR_YUV2BGR_NV21 = 90, 91, 92, 93
+COLOR_YUV2RGBA_NV12, COLOR_YUV2BGRA_NV12, COLOR_YUV2RGBA_NV21, COLOR_YUV2BGRA_NV21 = 94, 95, 96, 97
+COLOR_YUV2RGB_YV12, COLOR_YUV2BGR_YV12, COLOR_YUV2RGB_IYUV, COLOR_YUV2BGR_IYUV = 98, 99, 100, 101
+COLOR_YUV2RGBA_YV12, COLOR_YUV2BGRA_YV12, COLOR_YUV2RGBA_IYUV, COLOR_YUV2BGRA_IYUV = 102, 103, 104, 105
+COLOR_YUV2RGB_I420, COLOR_YUV2BGR_I420, COLOR_YUV2RGBA_I420, COLOR_YUV2BGRA_I420 = 100, 101, 104, 105
+COLOR_YUV2GRAY_420 = COLOR_YUV2GRAY_NV12 = COLOR_YUV2GRAY_NV21 = COLOR_YUV2GRAY_I420 = COLOR_YUV2GRAY_YV12 = 106
+COLOR_YUV2RGB_UYVY, COLOR_YUV2BGR_UYVY, COLOR_YUV2RGBA_UYVY, COLOR_YUV2BGRA_UYVY = 107, 108, 111, 112
+COLOR_YUV2RGB_YUY2, COLOR_YUV2BGR_YUY2, COLOR_YUV2RGB_YVYU, COLOR_YUV2BGR_YVYU = 115, 116, 117, 118
+COLOR_YUV2RGBA_YUY2, COLOR_YUV2BGRA_YUY2, COLOR_YUV2RGBA_YVYU, COLOR_YUV2BGRA_YVYU = 119, 120, 121, 122
+COLOR_YUV2GRAY_UYVY, COLOR_YUV2GRAY_YUY2 = 123, 124
+COLOR_RGB2YUV_I420, COLOR_BGR2YUV_I420, COLOR_RGBA2YUV_I420, COLOR_BGRA2YUV_I420 = 127, 128, 129, 130
+COLOR_RGB2YUV_IYUV, COLOR_BGR2YUV_IYUV, COLOR_RGBA2YUV_IYUV, COLOR_BGRA2YUV_IYUV = 127, 128, 129, 130
+COLOR_RGB2YUV_YV12, COLOR_BGR2YUV_YV12, COLOR_RGBA2YUV_YV12, COLOR_BGRA2YUV_YV12 = 131, 132, 133, 134
 
 OK, NOT_IMPLEMENTED = 0, 1
 
@@ -250,13 +264,29 @@ _CVT_DCN = {COLOR_BGR2BGRA: 4, COLOR_BGRA2BGR: 3, COLOR_BGR2RGBA: 4, COLOR_RGBA2
             COLOR_BGR2GRAY: 1, COLOR_RGB2GRAY: 1, COLOR_BGRA2GRAY: 1, COLOR_RGBA2GRAY: 1, COLOR_GRAY2BGR: 3, COLOR_GRAY2BGRA: 4}
 
 
+def _cvt_dst_geometry(code, cols, rows, dstCn=0):
+    """(width, height, channels) of cv::cvtColor's destination (color.cpp:323-372 for the subsampled-YUV codes)"""
+    if 90 <= code <= 105:
+        return cols, rows * 2 // 3, (4 if code in (94, 95, 96, 97, 102, 103, 104, 105) else 3)
+    if code == 106:
+        return cols, rows * 2 // 3, 1
+    if 107 <= code <= 122:
+        return cols, rows, (4 if code in (111, 112, 119, 120, 121, 122) else 3)
+    if code in (123, 124):
+        return cols, rows, 1
+    if 127 <= code <= 134:
+        return cols, rows * 3 // 2, 1
+    return cols, rows, (dstCn if dstCn > 0 else _CVT_DCN.get(code, 3))
+
+
 def cvtColor(src, code, dstCn=0, dst=None, stream=None):
     """cv::cvtColor (imgproc.hpp:3736)"""
     if not _is_torch(src):
         from . import hal
         return hal.cvtColor(src, code, dstCn)
-    dcn = dstCn if dstCn > 0 else _CVT_DCN.get(code, 3)
-    dst = dst if dst is not None else _new(src, channels=dcn)
+    m = describe(src)
+    w, h, dcn = _cvt_dst_geometry(int(code), m.cols, m.rows, dstCn)
+    dst = dst if dst is not None else _new(src, channels=dcn, size=(w, h))
     ms, md = _pair(src, dst)
     _check(lib().b200cv_cvt_color(ctypes.byref(ms), ctypes.byref(md), int(code), _stream_ptr(stream)), "cvtColor")
     return dst

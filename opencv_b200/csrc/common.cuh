@@ -1,6 +1,10 @@
 // common.cuh -- shared device/host helpers for the b200cv kernels (sm_100a only).
 #pragma once
+#ifdef B200CV_HOST_EMULATION      // tests/emu/cuda_emu.h: simple kernels compiled for the host by tests/test_kernel_emulation.py
+#include "cuda_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/b200cv.h"
@@ -93,6 +97,7 @@ template <> struct OutCast<uchar> { __device__ __forceinline__ static uchar from
 template <> struct OutCast<short> { __device__ __forceinline__ static short from(float v) { return sat_s16(v); } };
 template <> struct OutCast<float> { __device__ __forceinline__ static float from(float v) { return v; } };
 
+#ifndef B200CV_HOST_EMULATION
 // streaming (evict-first) 128-bit global accesses: every pixel is touched once per launch
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p)
 {
@@ -104,6 +109,7 @@ __device__ __forceinline__ void stg_stream(uint4* p, const uint4& v)
 {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+#endif
 
 static inline unsigned div_up(unsigned a, unsigned b) { return (a + b - 1) / b; }
 static inline size_t div_up_sz(size_t a, size_t b) { return (a + b - 1) / b; }
@@ -124,6 +130,7 @@ struct GU8Box {
     float scale_f;
     double scale;
 };
+int cvt_color_yuv(const b200cvMat* src, const b200cvMat* dst, int code, cudaStream_t st);      // cvtcolor_yuv.cu
 int gauss_u8_fast(const Img& s, const Img& d, int cn, const int64_t* fx, int kw, const int64_t* fy, int kh, int border, cudaStream_t st, int sep_mode = 0, int even_limit = 0,
                   const GU8Box* box = nullptr);
 

@@ -320,6 +320,36 @@ static int cvt(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, 
     return b200cv_host_cvt_color(&s, &d, code);
 }
 
+// subsampled YUV wire formats (cvtcolor_yuv.cu); source and destination differ in size
+static int cvt_yuv(const uchar* src, size_t sstep, int sw, int sh, int scn, uchar* dst, size_t dstep, int dw, int dh, int dcn, int code)
+{
+    if ((dw & 1) || (sw & 1) || src == dst) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, sw, sh, B200CV_MAKETYPE(B200CV_8U, scn)), d = hmat(dst, dstep, dw, dh, B200CV_MAKETYPE(B200CV_8U, dcn));
+    return b200cv_host_cvt_color(&s, &d, code);
+}
+extern "C" int b200cv_hal_cvtTwoPlaneYUVtoBGR(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int dw, int dh, int dcn, bool swapBlue, int uIdx)
+{
+    if ((dcn != 3 && dcn != 4) || (uIdx != 0 && uIdx != 1) || (dh & 1)) return B200CV_NOT_IMPLEMENTED;
+    return cvt_yuv(src, sstep, dw, dh * 3 / 2, 1, dst, dstep, dw, dh, dcn, 90 + (swapBlue ? 0 : 1) + 2 * uIdx + (dcn == 4 ? 4 : 0));
+}
+extern "C" int b200cv_hal_cvtThreePlaneYUVtoBGR(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int dw, int dh, int dcn, bool swapBlue, int uIdx)
+{
+    if ((dcn != 3 && dcn != 4) || (uIdx != 0 && uIdx != 1) || (dh & 1)) return B200CV_NOT_IMPLEMENTED;
+    return cvt_yuv(src, sstep, dw, dh * 3 / 2, 1, dst, dstep, dw, dh, dcn, 98 + (swapBlue ? 0 : 1) + (uIdx == 1 ? 0 : 2) + (dcn == 4 ? 4 : 0));
+}
+extern "C" int b200cv_hal_cvtBGRtoThreePlaneYUV(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int scn, bool swapBlue, int uIdx)
+{
+    if ((scn != 3 && scn != 4) || (uIdx != 1 && uIdx != 2) || (h & 1)) return B200CV_NOT_IMPLEMENTED;
+    return cvt_yuv(src, sstep, w, h, scn, dst, dstep, w, h * 3 / 2, 1, (uIdx == 2 ? 131 : 127) + (swapBlue ? 0 : 1) + (scn == 4 ? 2 : 0));
+}
+extern "C" int b200cv_hal_cvtOnePlaneYUVtoBGR(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int dcn, bool swapBlue, int uIdx, int ycn)
+{
+    if ((dcn != 3 && dcn != 4) || (uIdx != 0 && uIdx != 1) || (ycn != 0 && ycn != 1) || (ycn == 1 && uIdx == 1)) return B200CV_NOT_IMPLEMENTED;
+    // UYVY: 107 RGB 108 BGR 111 RGBA 112 BGRA; YUY2: 115 116 119 120; YVYU: 117 118 121 122
+    const int base = ycn == 1 ? (dcn == 3 ? 107 : 111) : (dcn == 3 ? 115 : 119) + (uIdx == 1 ? 2 : 0);
+    return cvt_yuv(src, sstep, w, h, 2, dst, dstep, w, h, dcn, base + (swapBlue ? 0 : 1));
+}
+
 extern "C" int b200cv_hal_cvtBGRtoBGR(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, int dcn, bool swapBlue)
 {
     int code = scn == 3 ? (dcn == 4 ? (swapBlue ? 2 : 0) : (swapBlue ? 4 : -1)) : (dcn == 3 ? (swapBlue ? 3 : 1) : (swapBlue ? 5 : -1));

@@ -9,7 +9,7 @@ import ctypes
 
 import numpy as np
 
-from . import (BORDER_CONSTANT, BORDER_DEFAULT, INTER_LINEAR, CV_8U, CV_16S, CV_32F, Mat, _check, lib, make_type, _CVT_DCN)
+from . import (BORDER_CONSTANT, BORDER_DEFAULT, INTER_LINEAR, CV_8U, CV_16S, CV_32F, Mat, _check, lib, make_type, _CVT_DCN, _cvt_dst_geometry)
 
 _DEPTH = {np.dtype(np.uint8): CV_8U, np.dtype(np.uint16): 2, np.dtype(np.int16): CV_16S, np.dtype(np.float32): CV_32F}
 _NP = {CV_8U: np.uint8, CV_16S: np.int16, CV_32F: np.float32}
@@ -95,8 +95,9 @@ def filter2D(src, ddepth, kernel, anchor=(-1, -1), delta=0.0, borderType=BORDER_
 
 
 def cvtColor(src, code, dstCn=0, dst=None):
-    dcn = dstCn if dstCn > 0 else _CVT_DCN.get(code, 3)
-    dst = dst if dst is not None else _new(src, channels=dcn)
+    m = describe(src)
+    w, h, dcn = _cvt_dst_geometry(int(code), m.cols, m.rows, dstCn)
+    dst = dst if dst is not None else _new(src, channels=dcn, size=(w, h))
     ms, md = describe(src), describe(dst)
     _check(lib().b200cv_host_cvt_color(ctypes.byref(ms), ctypes.byref(md), int(code)), "cvtColor")
     return dst

@@ -1,0 +1,53 @@
+// cuda_emu.h -- just enough of the CUDA programming model to run SIMPLE kernels (no shared memory, no warp intrinsics, no barriers) on
+// the host, one thread at a time.  TEST INFRASTRUCTURE: tests/test_kernel_emulation.py compiles a kernel source with g++ against this
+// header (B200CV_HOST_EMULATION), replaces its <<<grid, block, 0, st>>> launches by EMU_LAUNCH and compares the result with the oracle.
+// It checks index arithmetic, plane layouts, tails and the aligned / unaligned access paths on machines without a GPU; it says nothing
+// about performance and is no substitute for the -m gpu parity tests.
+#pragma once
+#include <math.h>
+#include <stdarg.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __restrict__
+
+struct uint2 { unsigned x, y; };
+struct uint4 { unsigned x, y, z, w; };
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+static dim3 blockIdx, threadIdx, blockDim, gridDim;
+
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+
+template <typename T> static inline T min(T a, T b) { return b < a ? b : a; }
+template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }
+static inline int __float2int_rn(float v) { return (int)lrintf(v); }
+
+template <typename F>
+static inline void emu_launch(dim3 grid, dim3 block, F thread_body)
+{
+    gridDim = grid; blockDim = block;
+    for (unsigned bz = 0; bz < grid.z; bz++)
+        for (unsigned by = 0; by < grid.y; by++)
+            for (unsigned bx = 0; bx < grid.x; bx++)
+                for (unsigned tz = 0; tz < block.z; tz++)
+                    for (unsigned ty = 0; ty < block.y; ty++)
+                        for (unsigned tx = 0; tx < block.x; tx++) {
+                            blockIdx = dim3(bx, by, bz); threadIdx = dim3(tx, ty, tz);
+                            thread_body();
+                        }
+}
+#define EMU_LAUNCH(grid, block, ...) emu_launch(grid, block, [&] { __VA_ARGS__; })

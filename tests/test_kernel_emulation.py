@@ -1,0 +1,130 @@
+"""CPU check of kernel LOGIC: simple kernels (no shared memory / warp intrinsics / barriers) are compiled for the host against
+tests/emu/cuda_emu.h, their <<<grid, block, 0, st>>> launches run as plain loops over every thread, and the result is compared with the
+oracle.  This exercises index arithmetic, plane layouts, tails and the aligned / unaligned access branches without a GPU.  It is not a
+parity claim for the CUDA build -- that is what the -m gpu tests are for -- but it catches logic errors before GPU time is spent."""
+import ctypes
+import os
+import re
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "opencv_b200", "csrc")
+OUT = os.path.join(ROOT, "tests", "emu", "_build")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+LAUNCH = re.compile(r"(\b[\w:]+(?:<[^<>;]*>)?)<<<\s*grid\s*,\s*block\s*,\s*0\s*,\s*st\s*>>>\(([^;]*)\);")
+
+STUBS = r"""
+namespace b200cv {
+void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); }
+int cuda_fail(cudaError_t, const char*, const char*, int) { return -1; }
+void count_launch(int) {}
+}
+"""
+
+
+def build_emulation(cu_name, entry_decl, entry_body):
+    os.makedirs(OUT, exist_ok=True)
+    src = open(os.path.join(CSRC, cu_name)).read()
+    translated, n = LAUNCH.subn(r"EMU_LAUNCH(grid, block, \1(\2));", src)
+    assert n > 0 and "<<<" not in translated, "untranslated kernel launch left in %s" % cu_name
+    cpp = os.path.join(OUT, cu_name.replace(".cu", "_emu.cpp"))
+    so = os.path.join(OUT, cu_name.replace(".cu", "_emu.so"))
+    with open(cpp, "w") as f:
+        f.write("#define B200CV_HOST_EMULATION 1\n" + translated + STUBS + 'extern "C" ' + entry_decl + "\n{\n" + entry_body + "\n}\n")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", CSRC, "-I", os.path.join(ROOT, "tests", "emu"), cpp, "-o", so])
+    return ctypes.CDLL(so)
+
+
+class Mat(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("step", ctypes.c_size_t), ("cols", ctypes.c_int), ("rows", ctypes.c_int), ("type", ctypes.c_int),
+                ("frames", ctypes.c_int), ("frame_step", ctypes.c_size_t)]
+
+
+def mat_of(a):
+    """(H,W) / (H,W,C) / (N,H,W,C) uint8 array (rows may be strided) -> b200cvMat"""
+    if a.ndim == 4:
+        n, h, w, c = a.shape
+        return Mat(a.ctypes.data, a.strides[1], w, h, (c - 1) << 3, n, a.strides[0])
+    h, w = a.shape[:2]
+    c = 1 if a.ndim == 2 else a.shape[2]
+    return Mat(a.ctypes.data, a.strides[0], w, h, (c - 1) << 3, 1, 0)
+
+
+@pytest.fixture(scope="module")
+def yuv_emu():
+    lib = build_emulation("cvtcolor_yuv.cu", "int emu_cvt_color_yuv(const b200cvMat* s, const b200cvMat* d, int code)",
+                          "    return b200cv::cvt_color_yuv(s, d, code, nullptr);")
+    lib.emu_cvt_color_yuv.argtypes = [ctypes.POINTER(Mat), ctypes.POINTER(Mat), ctypes.c_int]
+
+    def run(src, code, dst=None):
+        from oracle.api import yuv_dst_shape
+        if src.ndim == 4:
+            n, sh, sw = src.shape[:3]
+            dw, dh, dcn = yuv_dst_shape(sw, sh, code)
+            dst = np.full((n, dh, dw, dcn), 0xCD, np.uint8) if dst is None else dst
+        else:
+            sh, sw = src.shape[:2]
+            dw, dh, dcn = yuv_dst_shape(sw, sh, code)
+            dst = np.full((dh, dw) if dcn == 1 else (dh, dw, dcn), 0xCD, np.uint8) if dst is None else dst
+        ms, md = mat_of(src), mat_of(dst)
+        rc = lib.emu_cvt_color_yuv(ctypes.byref(ms), ctypes.byref(md), int(code))
+        assert rc == 0, "emulated cvt_color_yuv(code %d) returned %d" % (code, rc)
+        return dst
+    return run
+
+
+KAT_YUV = {90: 0x46a1bb76, 91: 0x3843bb76, 92: 0xf3fdf2ea, 93: 0x6e84f2ea, 94: 0xb6a16bd3, 95: 0xa8436bd3, 96: 0x1c7fa347, 97: 0x96f7a347,
+           98: 0xc5da1651, 99: 0x12161651, 100: 0xb4e62ea5, 101: 0xfa632ea5, 102: 0x0db4c69f, 103: 0x59e1c69f, 104: 0xfe09def3, 105: 0x4395def3,
+           106: 0xf672b440,
+           107: 0x69bea2c1, 108: 0xdc51a2c1, 111: 0x851eab45, 112: 0xf7b1ab45, 115: 0x607e8889, 116: 0xfb148889, 117: 0x239b13d4, 118: 0x402b13d4,
+           119: 0xf6af910d, 120: 0x9154910d, 121: 0x14481c58, 122: 0x30d81c58, 123: 0x228e669c, 124: 0x125c62fd,
+           127: 0x44bb076a, 128: 0xf908ff52, 129: 0x44bb076a, 130: 0xf908ff52, 131: 0x1b0d076a, 132: 0xda8aff52, 133: 0x1b0d076a, 134: 0xda8aff52}
+
+
+@pytest.mark.parametrize("code", sorted(KAT_YUV))
+def test_emulated_yuv_kernels_reproduce_the_reference_hashes(yuv_emu, code):
+    name = "cvtcolor_kat_yuv420_input.npy" if code <= 106 else "cvtcolor_kat_yuv422_input.npy" if code <= 124 else "cvtcolor_kat_bgr_262x254_input.npy"
+    out = yuv_emu(np.load(os.path.join(GOLD, name)), code)
+    assert zlib.adler32(np.ascontiguousarray(out).tobytes()) == KAT_YUV[code]
+
+
+def test_emulated_yuv_kernels_vs_port(yuv_emu, port, rng):
+    for (h, w) in [(2, 2), (4, 6), (18, 34), (36, 66), (66, 130), (250, 322)]:
+        yuv = rng.integers(0, 256, (h * 3 // 2, w), dtype=np.uint8)
+        for code in range(90, 107):
+            assert np.array_equal(yuv_emu(yuv, code), port.cvtColorYUV(yuv, code)), "4:2:0 code %d %dx%d" % (code, w, h)
+        y2 = rng.integers(0, 256, (h, w, 2), dtype=np.uint8)
+        for code in (107, 108, 111, 112, 115, 116, 117, 118, 119, 120, 121, 122, 123, 124):
+            assert np.array_equal(yuv_emu(y2, code), port.cvtColorYUV(y2, code)), "4:2:2 code %d %dx%d" % (code, w, h)
+        for code in range(127, 135):
+            img = rng.integers(0, 256, (h, w, 4 if (code - 127) & 2 else 3), dtype=np.uint8)
+            assert np.array_equal(yuv_emu(img, code), port.cvtColorYUV(img, code)), "to 4:2:0 code %d %dx%d" % (code, w, h)
+
+
+def test_emulated_yuv_kernels_unaligned_pitches_and_batches(yuv_emu, port, rng):
+    """odd base offsets / pitches force the byte paths; padded destinations must keep their padding; batches walk frame_step"""
+    h, w = 34, 90
+    wide = rng.integers(0, 256, (h * 3 // 2, w + 7), dtype=np.uint8)
+    for off in (0, 1, 3, 4):
+        src = wide[:, off:off + w]
+        for code in (91, 96, 99, 104, 106):
+            from oracle.api import yuv_dst_shape
+            dw, dh, dcn = yuv_dst_shape(w, h * 3 // 2, code)
+            big = np.full((dh, dw * dcn + 13), 0xEE, np.uint8)
+            view = big[:, 5:5 + dw * dcn].reshape(dh, dw, dcn) if dcn > 1 else big[:, 5:5 + dw]
+            yuv_emu(src, code, dst=view)
+            assert np.array_equal(view, port.cvtColorYUV(np.ascontiguousarray(src), code)), "offset %d code %d" % (off, code)
+            assert (big[:, :5] == 0xEE).all() and (big[:, 5 + dw * dcn:] == 0xEE).all(), "destination padding overwritten (offset %d code %d)" % (off, code)
+    batch = rng.integers(0, 256, (3, 36, 40, 1), dtype=np.uint8)
+    out = yuv_emu(batch, 91)
+    for f in range(3):
+        assert np.array_equal(out[f], port.cvtColorYUV(batch[f, :, :, 0], 91)), "batch frame %d" % f
+    bgr = rng.integers(0, 256, (2, 26, 38, 3), dtype=np.uint8)
+    out = yuv_emu(bgr, 132)
+    for f in range(2):
+        assert np.array_equal(out[f, :, :, 0], port.cvtColorYUV(bgr[f], 132)), "YV12 batch frame %d" % f
