@@ -438,6 +438,8 @@ extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int int
         B200_LAUNCH_CHECK();
         return B200CV_OK;
     }
+    // true area mode (both factors >= 1): resize_area.cu.  INTER_AREA enlargements are a bilinear variant in the reference: not built yet
+    if (interpolation == B200CV_INTER_AREA && p.scale_x >= 1 && p.scale_y >= 1) return resize_area_impl(s, d, depth, cn, st);
     if (interpolation != B200CV_INTER_LINEAR && interpolation != B200CV_INTER_CUBIC) return B200CV_NOT_IMPLEMENTED;
     return depth == B200CV_8U ? launch_by_cn<uchar>(cn, interpolation, s, d, p, st) : launch_by_cn<float>(cn, interpolation, s, d, p, st);
 }

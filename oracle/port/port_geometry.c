@@ -63,6 +63,81 @@ PORT_API int port_resize(const void* src, size_t sstep, int sw, int sh, void* ds
                 }
         return 0;
     }
+    if (interp == 3) {
+        /* INTER_AREA, true area mode only (both scales >= 1; resize.cpp:4016-4064).  Integer scales: plain window sum times float(1/area)
+         * (resizeAreaFast_Invoker :2969-3060; float sums in groups of four, CV_ENABLE_UNROLLED); otherwise the DecimateAlpha tables of
+         * computeResizeAreaTab (:3334-3373) and ResizeArea_Invoker (:3183-3297): per source row buf = sum_k S*alpha_k, per destination
+         * row sum = beta_0*buf_0, then sum += beta_j*buf_j; all in float, no fused operations; cvRound at the end for 8-bit data. */
+        if (scale_x < 1 || scale_y < 1) return 1;
+        if (area_fast) {
+            const int area = isx * isy;
+            const float scale = 1.f / area;
+            for (int y = 0; y < dh; y++)
+                for (int x = 0; x < dw; x++)
+                    for (int c = 0; c < cn; c++) {
+                        if (depth == P_8U) {
+                            int sum = 0;
+                            for (int j = 0; j < isy; j++)
+                                for (int i = 0; i < isx; i++) sum += ((const uchar*)src + (size_t)(y * isy + j) * sstep)[(x * isx + i) * cn + c];
+                            ((uchar*)dst + (size_t)y * dstep)[x * cn + c] = port_sat_u8f((float)sum * scale);
+                        } else {
+                            float v[4], sum = 0; int k = 0, n = 0;
+                            for (int j = 0; j < isy; j++)
+                                for (int i = 0; i < isx; i++) {
+                                    float s = ((const float*)((const char*)src + (size_t)(y * isy + j) * sstep))[(x * isx + i) * cn + c];
+                                    if (k <= area - 4 || n) { v[n++] = s; if (n == 4) { sum += ((v[0] + v[1]) + v[2]) + v[3]; n = 0; k += 4; } }
+                                    else { sum += s; k++; }
+                                }
+                            ((float*)((char*)dst + (size_t)y * dstep))[x * cn + c] = sum * scale;
+                        }
+                    }
+            return 0;
+        }
+        typedef struct { int si, di; float alpha; } DecAlpha;
+        DecAlpha* tabs[2]; int tn[2];
+        for (int pass = 0; pass < 2; pass++) {
+            int ssize = pass ? sh : sw, dsize = pass ? dh : dw; double scale = pass ? scale_y : scale_x;
+            DecAlpha* tab = (DecAlpha*)malloc(sizeof(DecAlpha) * (size_t)ssize * 2 + 64);
+            int k = 0;
+            for (int dx = 0; dx < dsize; dx++) {
+                double fsx1 = dx * scale, fsx2 = fsx1 + scale, cell = scale < ssize - fsx1 ? scale : ssize - fsx1;
+                int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+                if (sx2 > ssize - 1) sx2 = ssize - 1;
+                if (sx1 > sx2) sx1 = sx2;
+                if (sx1 - fsx1 > 1e-3) { tab[k].di = dx; tab[k].si = sx1 - 1; tab[k++].alpha = (float)((sx1 - fsx1) / cell); }
+                for (int sx = sx1; sx < sx2; sx++) { tab[k].di = dx; tab[k].si = sx; tab[k++].alpha = (float)(1.0 / cell); }
+                if (fsx2 - sx2 > 1e-3) {
+                    double m = fsx2 - sx2 < 1. ? fsx2 - sx2 : 1.; if (cell < m) m = cell;
+                    tab[k].di = dx; tab[k].si = sx2; tab[k++].alpha = (float)(m / cell);
+                }
+            }
+            tabs[pass] = tab; tn[pass] = k;
+        }
+        float* buf = (float*)malloc(sizeof(float) * (size_t)dw * cn * 2); float* sum = buf + (size_t)dw * cn;
+        int prev_dy = tabs[1][0].di;
+        for (int e = 0; e < dw * cn; e++) sum[e] = 0;
+        for (int j = 0; j <= tn[1]; j++) {
+            if (j == tn[1] || tabs[1][j].di != prev_dy) {
+                for (int e = 0; e < dw * cn; e++) {
+                    if (depth == P_8U) ((uchar*)dst + (size_t)prev_dy * dstep)[e] = port_sat_u8f(sum[e]);
+                    else ((float*)((char*)dst + (size_t)prev_dy * dstep))[e] = sum[e];
+                }
+                if (j == tn[1]) break;
+            }
+            const float beta = tabs[1][j].alpha; const int sy = tabs[1][j].si, dy = tabs[1][j].di;
+            for (int e = 0; e < dw * cn; e++) buf[e] = 0;
+            for (int k = 0; k < tn[0]; k++)
+                for (int c = 0; c < cn; c++) {
+                    float sv = depth == P_8U ? (float)((const uchar*)src + (size_t)sy * sstep)[tabs[0][k].si * cn + c]
+                                             : ((const float*)((const char*)src + (size_t)sy * sstep))[tabs[0][k].si * cn + c];
+                    buf[tabs[0][k].di * cn + c] += sv * tabs[0][k].alpha;
+                }
+            if (dy != prev_dy) { for (int e = 0; e < dw * cn; e++) sum[e] = beta * buf[e]; prev_dy = dy; }
+            else for (int e = 0; e < dw * cn; e++) sum[e] += beta * buf[e];
+        }
+        free(buf); free(tabs[0]); free(tabs[1]);
+        return 0;
+    }
     if (interp != 1 && interp != 2) return 1;
     int cubic = interp == 2;
     /* tables */

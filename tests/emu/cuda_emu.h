@@ -35,6 +35,15 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 template <typename T> static inline T min(T a, T b) { return b < a ? b : a; }
 template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }
 static inline int __float2int_rn(float v) { return (int)lrintf(v); }
+// single operations rounded on their own (volatile: the host compiler must not contract or re-associate them either)
+static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
+static inline float __int2float_rn(int a) { return (float)a; }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+static inline float __double2float_rn(double a) { return (float)a; }
 
 template <typename F>
 static inline void emu_launch(dim3 grid, dim3 block, F thread_body)

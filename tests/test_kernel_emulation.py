@@ -128,3 +128,39 @@ def test_emulated_yuv_kernels_unaligned_pitches_and_batches(yuv_emu, port, rng):
     out = yuv_emu(bgr, 132)
     for f in range(2):
         assert np.array_equal(out[f, :, :, 0], port.cvtColorYUV(bgr[f], 132)), "YV12 batch frame %d" % f
+
+
+# ---- INTER_AREA (resize_area.cu) ------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def area_emu():
+    lib = build_emulation("resize_area.cu", "int emu_resize_area(const b200cvMat* s, const b200cvMat* d)",
+                          "    return b200cv::resize_area_impl(b200cv::make_img(s), b200cv::make_img(d), B200CV_DEPTH(s->type), B200CV_CN(s->type), nullptr);")
+    lib.emu_resize_area.argtypes = [ctypes.POINTER(Mat), ctypes.POINTER(Mat)]
+
+    def run(src, dsize):
+        dw, dh = dsize
+        dst = np.zeros((dh, dw) + src.shape[2:], src.dtype)
+        ms, md = mat_of(src), mat_of(dst)
+        if src.dtype == np.float32:
+            ms.type |= 5; md.type |= 5
+        rc = lib.emu_resize_area(ctypes.byref(ms), ctypes.byref(md))
+        assert rc == 0, "emulated resize_area_impl returned %d" % rc
+        return dst
+    return run
+
+
+def test_emulated_area_resize_vs_port(area_emu, port, rng):
+    """integer factors (window sums) and fractional factors (DecimateAlpha weights derived per thread in double): bit-exact against the
+    port, which tests/test_oracle.py pins to the reference"""
+    cases = [((120, 180), (40, 60)), ((120, 180), (30, 90)), ((121, 183), (40, 61)), ((100, 150), (37, 41)), ((97, 131), (96, 130)),
+             ((64, 64), (16, 16)), ((90, 120), (30, 24)), ((50, 70), (49, 23)), ((33, 47), (1, 1)), ((300, 400), (7, 399)), ((240, 320), (150, 200))]
+    for (sh, sw), (dh, dw) in cases:
+        for cn in (1, 3, 4):
+            shape = (sh, sw) if cn == 1 else (sh, sw, cn)
+            u8 = rng.integers(0, 256, shape, dtype=np.uint8)
+            f32 = (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)
+            for img in (u8, f32):
+                if sh == 2 * dh and sw == 2 * dw:
+                    continue                                   # 2 x 2: resize.cu's own path
+                got, want = area_emu(img, (dw, dh)), port.resize(img, (dw, dh), 3)
+                assert np.array_equal(got, want), "INTER_AREA %s %s -> %s cn=%d" % (img.dtype, (sh, sw), (dh, dw), cn)

@@ -216,6 +216,17 @@ def _smooth(rng, h, w):
     return (img * 255).astype(np.uint8)
 
 
+def test_port_vs_reference_area_resize(ref, port, rng):
+    """INTER_AREA, true area mode: integer factors (window sums; float sums in groups of four) and fractional factors (DecimateAlpha)"""
+    cases = [((120, 180), (40, 60)), ((120, 180), (30, 90)), ((121, 183), (40, 61)), ((100, 150), (37, 41)), ((480, 640), (300, 400)),
+             ((97, 131), (96, 130)), ((64, 64), (16, 16)), ((90, 120), (30, 24)), ((50, 70), (49, 23)), ((33, 47), (1, 1)), ((300, 400), (7, 399))]
+    for (sh, sw), (dh, dw) in cases:
+        for cn in (1, 3, 4):
+            shape = (sh, sw) if cn == 1 else (sh, sw, cn)
+            for img in (rng.integers(0, 256, shape, dtype=np.uint8), (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)):
+                assert np.array_equal(ref.resize(img, (dw, dh), 3), port.resize(img, (dw, dh), 3)), "INTER_AREA %s %s -> %s cn=%d" % (img.dtype, (sh, sw), (dh, dw), cn)
+
+
 def test_port_vs_reference_remap(ref, port, rng):
     """cv::remap restated in the port: float planes, packed float pairs, fixed-point maps (incl. the NNDeltaTab_i quirk), NaN and
     out-of-range coordinates -- bit-exact against the reference for u8 and f32."""
