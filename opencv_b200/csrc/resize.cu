@@ -256,7 +256,10 @@ __global__ void __launch_bounds__(256) resize_area2_f32_kernel(Img src, Img dst,
 #pragma unroll
     for (int c = 0; c < CN; c++) {
         float a = s0[c], b = s0[c + CN], e = s1[c], g = s1[c + CN];
-        float sum = (CN == 1 || CN == 4) ? __fadd_rn(__fadd_rn(a, b), __fadd_rn(e, g)) : __fadd_rn(__fadd_rn(__fadd_rn(a, b), e), g);
+        // 1 / 4 channels: the 4-lane SIMD body adds row sums, (a+b)+(e+g); 3 channels and the single-channel remainder columns
+        // (dw % 4, resize.cpp:3012-3024) run the scalar loop, ((a+b)+e)+g
+        const bool seq = CN == 3 || (CN == 1 && x >= (dw & ~3));
+        float sum = seq ? __fadd_rn(__fadd_rn(__fadd_rn(a, b), e), g) : __fadd_rn(__fadd_rn(a, b), __fadd_rn(e, g));
         d[c] = __fmul_rn(sum, 0.25f);
     }
 }
@@ -406,6 +409,8 @@ extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int int
     const int pix = (int)elem_size(src->type);
     dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
 
+    if (interpolation == B200CV_INTER_NEAREST_EXACT) return resize_exact_impl(s, d, depth, cn, interpolation, st);
+    if (interpolation == B200CV_INTER_LINEAR_EXACT && depth == B200CV_32F) interpolation = B200CV_INTER_LINEAR;      // cv::resize, resize.cpp:4223
     if (interpolation == B200CV_INTER_NEAREST) {
         dim3 g4(div_up(div_up((unsigned)p.dw, 4), 128), (unsigned)p.dh, (unsigned)s.frames);
         int vec_ok = (((uintptr_t)d.data | d.step | d.fstep) & 3) == 0 && (pix % 4 != 0 || (((uintptr_t)s.data | s.step | s.fstep) & 3) == 0);
@@ -423,7 +428,7 @@ extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int int
     // exact 2x2 decimation: INTER_AREA, and INTER_LINEAR which the reference rewrites to it (resize.cpp:4009-4012)
     const int isx = (int)lrint(p.scale_x), isy = (int)lrint(p.scale_y);
     const bool area_fast = fabs(p.scale_x - isx) < 2.220446049250313e-16 && fabs(p.scale_y - isy) < 2.220446049250313e-16;
-    if ((interpolation == B200CV_INTER_LINEAR || interpolation == B200CV_INTER_AREA) && area_fast && isx == 2 && isy == 2) {
+    if ((interpolation == B200CV_INTER_LINEAR || interpolation == B200CV_INTER_AREA || interpolation == B200CV_INTER_LINEAR_EXACT) && area_fast && isx == 2 && isy == 2) {   // LINEAR_EXACT: resize.cpp:3976-3981
         if (depth == B200CV_8U) {
             int vec_ok = (((uintptr_t)s.data | s.step | s.fstep | (uintptr_t)d.data | d.step | d.fstep) & 3) == 0;
             dim3 g4(div_up((unsigned)div_up((unsigned)p.dw, 4), 256), (unsigned)p.dh, (unsigned)s.frames);
@@ -438,6 +443,7 @@ extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int int
         B200_LAUNCH_CHECK();
         return B200CV_OK;
     }
+    if (interpolation == B200CV_INTER_LINEAR_EXACT) return resize_exact_impl(s, d, depth, cn, interpolation, st);
     // true area mode (both factors >= 1): resize_area.cu.  INTER_AREA enlargements are a bilinear variant in the reference: not built yet
     if (interpolation == B200CV_INTER_AREA && p.scale_x >= 1 && p.scale_y >= 1) return resize_area_impl(s, d, depth, cn, st);
     if (interpolation != B200CV_INTER_LINEAR && interpolation != B200CV_INTER_CUBIC) return B200CV_NOT_IMPLEMENTED;

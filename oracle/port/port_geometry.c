@@ -47,7 +47,8 @@ PORT_API int port_resize(const void* src, size_t sstep, int sw, int sh, void* ds
     }
     int isx = port_round(scale_x), isy = port_round(scale_y);
     int area_fast = fabs(scale_x - isx) < 2.220446049250313e-16 && fabs(scale_y - isy) < 2.220446049250313e-16;
-    if ((interp == 1 || interp == 3) && area_fast && isx == 2 && isy == 2) {
+    if (interp == 5 && depth == P_32F) interp = 1;       /* cv::resize, resize.cpp:4223: float data has no exact mode */
+    if ((interp == 1 || interp == 3 || interp == 5) && area_fast && isx == 2 && isy == 2) {   /* LINEAR_EXACT 2 x 2: resize.cpp:3976-3981 */
         for (int y = 0; y < dh; y++)
             for (int x = 0; x < dw; x++)
                 for (int c = 0; c < cn; c++) {
@@ -57,10 +58,72 @@ PORT_API int port_resize(const void* src, size_t sstep, int sw, int sh, void* ds
                     } else {
                         const float* s0 = (const float*)((const char*)src + (size_t)(2 * y) * sstep) + 2 * x * cn + c;
                         const float* s1 = (const float*)((const char*)s0 + sstep);
-                        float sum = (cn == 1 || cn == 4) ? (s0[0] + s0[cn]) + (s1[0] + s1[cn]) : ((s0[0] + s0[cn]) + s1[0]) + s1[cn];
+                        /* 4-lane SIMD body: (a+b)+(c+d); 3 channels and the single-channel remainder columns (dw % 4): scalar loop, ((a+b)+c)+d */
+                        int seq = cn == 3 || (cn == 1 && x >= (dw & ~3));
+                        float sum = seq ? ((s0[0] + s0[cn]) + s1[0]) + s1[cn] : (s0[0] + s0[cn]) + (s1[0] + s1[cn]);
                         ((float*)((char*)dst + (size_t)y * dstep))[x * cn + c] = sum * 0.25f;
                     }
                 }
+        return 0;
+    }
+    if (interp == 6) {
+        /* INTER_NEAREST_EXACT (resizeNN_bitexact, resize.cpp:1267-1288): 16.16 fixed-point source coordinate of the pixel centre */
+        if (sw >= 32768 || sh >= 32768) return 1;
+        int ifx = ((sw << 16) + dw / 2) / dw, ifx0 = ifx / 2 - sw % 2, ify = ((sh << 16) + dh / 2) / dh, ify0 = ify / 2 - sh % 2;
+        for (int y = 0; y < dh; y++) {
+            int sy = (ify * y + ify0) >> 16; if (sy > sh - 1) sy = sh - 1;
+            for (int x = 0; x < dw; x++) {
+                int sx = (ifx * x + ifx0) >> 16; if (sx > sw - 1) sx = sw - 1;
+                memcpy((char*)dst + (size_t)y * dstep + (size_t)x * es, (const char*)src + (size_t)sy * sstep + (size_t)sx * es, es);
+            }
+        }
+        return 0;
+    }
+    if (interp == 5) {
+        /* INTER_LINEAR_EXACT for 8-bit data (resize_bitExact<uint8_t, interpolationLinear>, resize.cpp:776-960; fixedpoint.inl.hpp:326-374):
+         * 8.8 fixed-point weights c1 = cvRound((f - floor f) * 256), c0 = 256 - c1 from f = (1/inv_scale) * (d + 0.5) - 0.5 in double;
+         * positions left of the first / right of the last source sample copy it; rows: H = c0*p0 + c1*p1 (16-bit), columns:
+         * (H0*b0 + H1*b1 + 2^15) >> 16, or (H + 128) >> 8 for the copied rows. */
+        int* ofs[2]; unsigned short* co[2]; int mn[2], mx[2];
+        for (int pass = 0; pass < 2; pass++) {
+            int dn = pass ? dh : dw, sn = pass ? sh : sw; double scale = 1.0 / (pass ? inv_y : inv_x);
+            ofs[pass] = (int*)calloc((size_t)dn, sizeof(int)); co[pass] = (unsigned short*)calloc((size_t)dn * 2, sizeof(unsigned short));
+            int minofst = 0, maxofst = dn;
+            for (int d = 0; d < dn; d++) {
+                volatile double t = scale * (d + 0.5); double fval = t - 0.5;
+                int ival = (int)floor(fval);
+                if (ival >= 0 && sn > 1) {
+                    if (ival < sn - 1) {
+                        ofs[pass][d] = ival;
+                        volatile double fr = fval - ival; double q = fr * 256.0;
+                        co[pass][2 * d + 1] = (unsigned short)port_round(q);
+                        co[pass][2 * d] = (unsigned short)(256 - co[pass][2 * d + 1]);
+                    } else { ofs[pass][d] = sn - 1; if (d < maxofst) maxofst = d; }
+                } else if (d + 1 > minofst) minofst = d + 1;
+            }
+            mn[pass] = minofst; mx[pass] = maxofst;
+        }
+        for (int y = 0; y < dh; y++)
+            for (int x = 0; x < dw; x++)
+                for (int c = 0; c < cn; c++) {
+                    unsigned H[2]; int rows[2], nr;
+                    if (y < mn[1]) { rows[0] = 0; nr = 1; } else if (y >= mx[1]) { rows[0] = sh - 1; nr = 1; } else { rows[0] = ofs[1][y]; rows[1] = rows[0] + 1; nr = 2; }
+                    for (int r = 0; r < nr; r++) {
+                        const uchar* sp = (const uchar*)src + (size_t)rows[r] * sstep;
+                        if (x < mn[0]) H[r] = (unsigned)sp[c] << 8;
+                        else if (x >= mx[0]) H[r] = (unsigned)sp[(sw - 1) * cn + c] << 8;
+                        else {
+                            unsigned a = co[0][2 * x] * sp[ofs[0][x] * cn + c], b = co[0][2 * x + 1] ? co[0][2 * x + 1] * sp[(ofs[0][x] + 1) * cn + c] : 0;
+                            if (a > 65535) a = 65535; if (b > 65535) b = 65535;
+                            H[r] = a + b > 65535 ? 65535 : a + b;
+                        }
+                    }
+                    unsigned v;
+                    if (nr == 1) v = ((H[0] + 128) & 0xFFFF) >> 8;
+                    else v = (H[0] * co[1][2 * y] + H[1] * co[1][2 * y + 1] + 32768u) >> 16;
+                    ((uchar*)dst + (size_t)y * dstep)[x * cn + c] = (uchar)(v > 255 ? 255 : v);
+                }
+        free(ofs[0]); free(ofs[1]); free(co[0]); free(co[1]);
         return 0;
     }
     if (interp == 3) {

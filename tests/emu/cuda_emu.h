@@ -44,6 +44,7 @@ static inline double __dadd_rn(double a, double b) { volatile double r = a + b; 
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline float __double2float_rn(double a) { return (float)a; }
+static inline int __double2int_rn(double a) { return (int)lrint(a); }
 
 template <typename F>
 static inline void emu_launch(dim3 grid, dim3 block, F thread_body)

@@ -164,3 +164,37 @@ def test_emulated_area_resize_vs_port(area_emu, port, rng):
                     continue                                   # 2 x 2: resize.cu's own path
                 got, want = area_emu(img, (dw, dh)), port.resize(img, (dw, dh), 3)
                 assert np.array_equal(got, want), "INTER_AREA %s %s -> %s cn=%d" % (img.dtype, (sh, sw), (dh, dw), cn)
+
+
+# ---- INTER_NEAREST_EXACT / INTER_LINEAR_EXACT (resize_exact.cu) -------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def exact_emu():
+    lib = build_emulation("resize_exact.cu", "int emu_resize_exact(const b200cvMat* s, const b200cvMat* d, int interp)",
+                          "    return b200cv::resize_exact_impl(b200cv::make_img(s), b200cv::make_img(d), B200CV_DEPTH(s->type), B200CV_CN(s->type), interp, nullptr);")
+    lib.emu_resize_exact.argtypes = [ctypes.POINTER(Mat), ctypes.POINTER(Mat), ctypes.c_int]
+
+    def run(src, dsize, interp):
+        dw, dh = dsize
+        dst = np.zeros((dh, dw) + src.shape[2:], src.dtype)
+        ms, md = mat_of(src), mat_of(dst)
+        if src.dtype == np.float32:
+            ms.type |= 5; md.type |= 5
+        rc = lib.emu_resize_exact(ctypes.byref(ms), ctypes.byref(md), interp)
+        assert rc == 0, "emulated resize_exact_impl returned %d" % rc
+        return dst
+    return run
+
+
+EXACT_CASES = [((120, 180), (40, 60)), ((121, 183), (40, 61)), ((100, 150), (237, 341)), ((97, 131), (96, 130)), ((64, 64), (160, 160)),
+               ((1, 47), (5, 90)), ((50, 1), (49, 23)), ((33, 47), (1, 1)), ((300, 400), (7, 399)), ((2, 2), (9, 9)), ((3, 5), (30, 50))]
+
+
+def test_emulated_exact_resizers_vs_port(exact_emu, port, rng):
+    for (sh, sw), (dh, dw) in EXACT_CASES:
+        for cn in (1, 3, 4):
+            shape = (sh, sw) if cn == 1 else (sh, sw, cn)
+            u8 = rng.integers(0, 256, shape, dtype=np.uint8)
+            f32 = (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)
+            assert np.array_equal(exact_emu(u8, (dw, dh), 5), port.resize(u8, (dw, dh), 5)), "LINEAR_EXACT %s -> %s cn=%d" % ((sh, sw), (dh, dw), cn)
+            for img in (u8, f32):
+                assert np.array_equal(exact_emu(img, (dw, dh), 6), port.resize(img, (dw, dh), 6)), "NEAREST_EXACT %s %s -> %s cn=%d" % (img.dtype, (sh, sw), (dh, dw), cn)

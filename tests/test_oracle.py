@@ -227,6 +227,21 @@ def test_port_vs_reference_area_resize(ref, port, rng):
                 assert np.array_equal(ref.resize(img, (dw, dh), 3), port.resize(img, (dw, dh), 3)), "INTER_AREA %s %s -> %s cn=%d" % (img.dtype, (sh, sw), (dh, dw), cn)
 
 
+def test_port_vs_reference_exact_resizers(ref, port, rng):
+    """INTER_LINEAR_EXACT (8.8 fixed point; float data falls back to INTER_LINEAR, 2 x 2 decimation to the INTER_AREA fast path) and
+    INTER_NEAREST_EXACT (16.16 pixel-centre coordinates)"""
+    cases = [((120, 180), (40, 60)), ((120, 180), (60, 90)), ((121, 183), (40, 61)), ((100, 150), (237, 341)), ((480, 640), (300, 400)),
+             ((97, 131), (96, 130)), ((64, 64), (160, 160)), ((1, 47), (5, 90)), ((50, 1), (49, 23)), ((33, 47), (1, 1)), ((300, 400), (7, 399)),
+             ((2, 2), (9, 9)), ((3, 5), (30, 50)), ((120, 178), (60, 89)), ((120, 182), (60, 91))]
+    for (sh, sw), (dh, dw) in cases:
+        for cn in (1, 3, 4):
+            shape = (sh, sw) if cn == 1 else (sh, sw, cn)
+            for img in (rng.integers(0, 256, shape, dtype=np.uint8), (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)):
+                for interp in (5, 6):
+                    assert np.array_equal(ref.resize(img, (dw, dh), interp), port.resize(img, (dw, dh), interp)), \
+                        "interp %d %s %s -> %s cn=%d" % (interp, img.dtype, (sh, sw), (dh, dw), cn)
+
+
 def test_port_vs_reference_remap(ref, port, rng):
     """cv::remap restated in the port: float planes, packed float pairs, fixed-point maps (incl. the NNDeltaTab_i quirk), NaN and
     out-of-range coordinates -- bit-exact against the reference for u8 and f32."""
