@@ -23,7 +23,9 @@ namespace b200cv {
 struct ResizeParams {
     double ifx, ify;        // NEAREST: 1/fx, 1/fy
     double scale_x, scale_y;  // LINEAR/CUBIC: 1/inv_scale
+    double inv_x, inv_y;      // INTER_AREA on an enlarging axis: weights from (d + 1) - (s + 1) * inv_scale
     int sw, sh, dw, dh;
+    int area_mode;
 };
 
 __device__ __forceinline__ int clip_i(int x, int a, int b) { return x >= a ? (x < b ? x : b - 1) : a; }
@@ -70,11 +72,20 @@ __global__ void __launch_bounds__(256) resize_nn_kernel(Img src, Img dst, Resize
 
 // ---- coefficient helpers -------------------------------------------------------------------------------------------
 // linear: returns source index and fractional weight with the reference's edge clamps (ksize2 == 1)
-__device__ __forceinline__ void linear_coef(int d, double scale, int ssize, int& s, float& fr, bool clamp_edges)
+// area_mode (INTER_AREA when an axis is enlarged, resize.cpp:4104-4109): s = floor(d * scale), f = (d+1) - (s+1) * inv_scale, <= 0 -> 0, else its fraction
+__device__ __forceinline__ void linear_coef(int d, double scale, int ssize, int& s, float& fr, bool clamp_edges, bool area_mode = false, double inv_scale = 0.)
 {
-    float fx = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
-    int sx = (int)floorf(fx);
-    fx = __fsub_rn(fx, (float)sx);
+    float fx;
+    int sx;
+    if (!area_mode) {
+        fx = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5);
+        sx = (int)floorf(fx);
+        fx = __fsub_rn(fx, (float)sx);
+    } else {
+        sx = (int)floor(__dmul_rn((double)d, scale));
+        fx = (float)__dsub_rn((double)(d + 1), __dmul_rn((double)(sx + 1), inv_scale));
+        fx = fx <= 0.f ? 0.f : __fsub_rn(fx, floorf(fx));
+    }
     if (clamp_edges) {
         if (sx < 0) { fx = 0.f; sx = 0; }
         if (sx >= ssize - 1) { fx = 0.f; sx = ssize - 1; }
@@ -114,7 +125,7 @@ __global__ void resize_tab_kernel(ResTab* xt, ResTab* yt, ResizeParams p)
     const int d = is_y ? i - p.dw : i;
     if (is_y && d >= p.dh) return;
     int s; float fr;
-    linear_coef(d, is_y ? p.scale_y : p.scale_x, is_y ? p.sh : p.sw, s, fr, !CUBIC && !is_y);
+    linear_coef(d, is_y ? p.scale_y : p.scale_x, is_y ? p.sh : p.sw, s, fr, !CUBIC && !is_y, !CUBIC && p.area_mode, is_y ? p.inv_y : p.inv_x);
     ResTab t;
     t.s = s; t.last = (!CUBIC && !is_y && s >= p.sw - 1); t.pad[0] = t.pad[1] = 0;
     float c[4];
@@ -406,6 +417,7 @@ extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int int
     const double inv_x = (double)p.dw / p.sw, inv_y = (double)p.dh / p.sh;   // hal::resize, resize.cpp:3835-3839
     p.ifx = 1. / inv_x; p.ify = 1. / inv_y;
     p.scale_x = 1. / inv_x; p.scale_y = 1. / inv_y;
+    p.inv_x = inv_x; p.inv_y = inv_y; p.area_mode = 0;
     const int pix = (int)elem_size(src->type);
     dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
 
@@ -444,8 +456,9 @@ extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int int
         return B200CV_OK;
     }
     if (interpolation == B200CV_INTER_LINEAR_EXACT) return resize_exact_impl(s, d, depth, cn, interpolation, st);
-    // true area mode (both factors >= 1): resize_area.cu.  INTER_AREA enlargements are a bilinear variant in the reference: not built yet
+    // true area mode (both factors >= 1): resize_area.cu.  With an enlarging axis INTER_AREA is the bilinear kernel with area-mode weights
     if (interpolation == B200CV_INTER_AREA && p.scale_x >= 1 && p.scale_y >= 1) return resize_area_impl(s, d, depth, cn, st);
+    if (interpolation == B200CV_INTER_AREA) { p.area_mode = 1; interpolation = B200CV_INTER_LINEAR; }
     if (interpolation != B200CV_INTER_LINEAR && interpolation != B200CV_INTER_CUBIC) return B200CV_NOT_IMPLEMENTED;
     return depth == B200CV_8U ? launch_by_cn<uchar>(cn, interpolation, s, d, p, st) : launch_by_cn<float>(cn, interpolation, s, d, p, st);
 }

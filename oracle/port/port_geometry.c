@@ -131,7 +131,7 @@ PORT_API int port_resize(const void* src, size_t sstep, int sw, int sh, void* ds
          * (resizeAreaFast_Invoker :2969-3060; float sums in groups of four, CV_ENABLE_UNROLLED); otherwise the DecimateAlpha tables of
          * computeResizeAreaTab (:3334-3373) and ResizeArea_Invoker (:3183-3297): per source row buf = sum_k S*alpha_k, per destination
          * row sum = beta_0*buf_0, then sum += beta_j*buf_j; all in float, no fused operations; cvRound at the end for 8-bit data. */
-        if (scale_x < 1 || scale_y < 1) return 1;
+        if (scale_x < 1 || scale_y < 1) goto area_as_linear;      /* an enlarging axis: bilinear with area-mode weights, below */
         if (area_fast) {
             const int area = isx * isy;
             const float scale = 1.f / area;
@@ -201,6 +201,11 @@ PORT_API int port_resize(const void* src, size_t sstep, int sw, int sh, void* ds
         free(buf); free(tabs[0]); free(tabs[1]);
         return 0;
     }
+area_as_linear:;
+    /* INTER_AREA with a factor < 1 on either axis (resize.cpp:4071, :4104-4109, :4158-4163): the bilinear kernel with
+     * s = floor(d * scale), f = (d + 1) - (s + 1) * inv_scale, f = f <= 0 ? 0 : f - floor(f) on BOTH axes */
+    const int area_mode = interp == 3;
+    if (area_mode) interp = 1;
     if (interp != 1 && interp != 2) return 1;
     int cubic = interp == 2;
     /* tables */
@@ -209,8 +214,14 @@ PORT_API int port_resize(const void* src, size_t sstep, int sw, int sh, void* ds
     for (int pass = 0; pass < 2; pass++) {
         int dn = pass ? dh : dw, sn = pass ? sh : sw; double sc = pass ? scale_y : scale_x;
         for (int d = 0; d < dn; d++) {
-            float f = (float)((d + 0.5) * sc - 0.5);
-            int s = (int)floorf(f); f -= s;
+            float f; int s;
+            if (!area_mode) { f = (float)((d + 0.5) * sc - 0.5); s = (int)floorf(f); f -= s; }
+            else {
+                s = (int)floor(d * sc);
+                volatile double m = (s + 1) * (pass ? inv_y : inv_x);
+                f = (float)((d + 1) - m);
+                f = f <= 0 ? 0.f : f - floorf(f);
+            }
             if (!cubic && !pass) { if (s < 0) { f = 0; s = 0; } if (s >= sn - 1) { f = 0; s = sn - 1; } }
             float* c = (pass ? ya : xa) + 4 * d;
             if (cubic) cubic_c(f, c); else { c[0] = 1.f - f; c[1] = f; c[2] = c[3] = 0; }

@@ -36,8 +36,13 @@ def test_area_resize_8k_batch(cvb, ref, rng):
         assert_exact(out[1], ref.resize(batch[1], dsize, 3), "INTER_AREA 8K -> %s" % (dsize,))
 
 
-def test_area_enlargement_is_declined(cvb, rng):
-    """INTER_AREA with a factor < 1 is a bilinear variant in the reference (resize.cpp:4071-4127): not built, must fail loudly, never guess"""
-    img = gpu(rng.integers(0, 256, (50, 60), dtype=np.uint8))
-    with pytest.raises(Exception):
-        cvb.resize(img, (90, 75), interpolation=C.INTER_AREA)
+@pytest.mark.parametrize("ssize,dsize", [((40, 60), (120, 180)), ((40, 60), (97, 131)), ((100, 150), (237, 341)), ((97, 131), (98, 132)), ((64, 64), (160, 32)),
+                                         ((64, 64), (32, 160)), ((1, 47), (5, 90)), ((50, 1), (75, 23)), ((3, 5), (30, 50)), ((120, 160), (121, 100))])
+def test_area_resize_with_an_enlarging_axis(cvb, oracle, rng, ssize, dsize):
+    """INTER_AREA with a factor < 1 on either axis = the bilinear kernel with area-mode weights on both axes (resize.cpp:4104-4109, :4158-4163)"""
+    (sh, sw), (dh, dw) = ssize, dsize
+    for cn in (1, 3, 4):
+        shape = (sh, sw) if cn == 1 else (sh, sw, cn)
+        for img in (rng.integers(0, 256, shape, dtype=np.uint8), (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)):
+            got = cpu(cvb.resize(gpu(img), (dw, dh), interpolation=C.INTER_AREA))
+            assert_exact(got, oracle.resize(img, (dw, dh), 3), "INTER_AREA %s %s -> %s cn=%d" % (img.dtype, ssize, dsize, cn))

@@ -219,7 +219,10 @@ def _smooth(rng, h, w):
 def test_port_vs_reference_area_resize(ref, port, rng):
     """INTER_AREA, true area mode: integer factors (window sums; float sums in groups of four) and fractional factors (DecimateAlpha)"""
     cases = [((120, 180), (40, 60)), ((120, 180), (30, 90)), ((121, 183), (40, 61)), ((100, 150), (37, 41)), ((480, 640), (300, 400)),
-             ((97, 131), (96, 130)), ((64, 64), (16, 16)), ((90, 120), (30, 24)), ((50, 70), (49, 23)), ((33, 47), (1, 1)), ((300, 400), (7, 399))]
+             ((97, 131), (96, 130)), ((64, 64), (16, 16)), ((90, 120), (30, 24)), ((50, 70), (49, 23)), ((33, 47), (1, 1)), ((300, 400), (7, 399)),
+             # an enlarging axis: bilinear with area-mode weights
+             ((40, 60), (120, 180)), ((40, 60), (97, 131)), ((100, 150), (237, 341)), ((64, 64), (160, 32)), ((64, 64), (32, 160)), ((1, 47), (5, 90)),
+             ((50, 1), (75, 23)), ((120, 160), (121, 100))]
     for (sh, sw), (dh, dw) in cases:
         for cn in (1, 3, 4):
             shape = (sh, sw) if cn == 1 else (sh, sw, cn)
