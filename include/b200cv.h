@@ -77,6 +77,7 @@ extern "C" {
 #define B200CV_INTER_LINEAR 1
 #define B200CV_INTER_CUBIC 2
 #define B200CV_INTER_AREA 3
+#define B200CV_INTER_LANCZOS4 4
 #define B200CV_INTER_LINEAR_EXACT 5
 #define B200CV_INTER_NEAREST_EXACT 6
 #define B200CV_WARP_INVERSE_MAP 16

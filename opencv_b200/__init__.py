@@ -28,7 +28,7 @@ BORDER_DEFAULT = BORDER_REFLECT_101
 BORDER_REFLECT101 = BORDER_REFLECT_101
 BORDER_TRANSPARENT, BORDER_ISOLATED = 5, 16
 INTER_NEAREST, INTER_LINEAR, INTER_CUBIC, INTER_AREA = 0, 1, 2, 3
-INTER_LINEAR_EXACT, INTER_NEAREST_EXACT = 5, 6
+INTER_LANCZOS4, INTER_LINEAR_EXACT, INTER_NEAREST_EXACT = 4, 5, 6
 WARP_INVERSE_MAP = 16
 TM_SQDIFF, TM_SQDIFF_NORMED, TM_CCORR, TM_CCORR_NORMED, TM_CCOEFF, TM_CCOEFF_NORMED = range(6)
 COLOR_BGR2BGRA, COLOR_BGRA2BGR, COLOR_BGR2RGBA, COLOR_RGBA2BGR, COLOR_BGR2RGB, COLOR_BGRA2RGBA = range(6)

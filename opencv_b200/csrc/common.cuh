@@ -130,6 +130,7 @@ struct GU8Box {
     float scale_f;
     double scale;
 };
+int resize_lanczos_impl(const Img& s, const Img& d, int depth, int cn, cudaStream_t st);        // resize_lanczos.cu
 int resize_exact_impl(const Img& s, const Img& d, int depth, int cn, int interpolation, cudaStream_t st);   // resize_exact.cu
 int resize_area_impl(const Img& s, const Img& d, int depth, int cn, cudaStream_t st);           // resize_area.cu
 int cvt_color_yuv(const b200cvMat* src, const b200cvMat* dst, int code, cudaStream_t st);      // cvtcolor_yuv.cu

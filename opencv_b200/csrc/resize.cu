@@ -456,6 +456,7 @@ extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int int
         return B200CV_OK;
     }
     if (interpolation == B200CV_INTER_LINEAR_EXACT) return resize_exact_impl(s, d, depth, cn, interpolation, st);
+    if (interpolation == B200CV_INTER_LANCZOS4) return resize_lanczos_impl(s, d, depth, cn, st);
     // true area mode (both factors >= 1): resize_area.cu.  With an enlarging axis INTER_AREA is the bilinear kernel with area-mode weights
     if (interpolation == B200CV_INTER_AREA && p.scale_x >= 1 && p.scale_y >= 1) return resize_area_impl(s, d, depth, cn, st);
     if (interpolation == B200CV_INTER_AREA) { p.area_mode = 1; interpolation = B200CV_INTER_LINEAR; }

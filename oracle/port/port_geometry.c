@@ -21,6 +21,25 @@ static void cubic_c(float x, float* c)
     c[3] = 1.f - c[0] - c[1] - c[2];
 }
 
+/* interpolateLanczos4, resize.cpp:974-1003: sin / cos of the first tap's angle in double, the other seven by the 45-degree rotation table */
+static void lanczos4_c(float x, float* c)
+{
+    static const double s45 = 0.70710678118654752440084436210485;
+    static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+    float sum = 0;
+    double y0 = -(x + 3) * 3.1415926535897932384626433832795 * 0.25, s0 = sin(y0), c0 = cos(y0);
+    for (int i = 0; i < 8; i++) {
+        float y0_ = (x + 3 - i);
+        if (fabsf(y0_) >= 1e-6f) {
+            double y = -y0_ * 3.1415926535897932384626433832795 * 0.25;
+            c[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+        } else c[i] = 1e30f;
+        sum += c[i];
+    }
+    sum = 1.f / sum;
+    for (int i = 0; i < 8; i++) c[i] *= sum;
+}
+
 static short s16(float v) { return port_sat_s16i((int)lrintf(v)); }
 
 #define SRC(y, x, c) (depth == P_8U ? (float)((const uchar*)src + (size_t)(y) * sstep)[(x) * cn + (c)] : ((const float*)((const char*)src + (size_t)(y) * sstep))[(x) * cn + (c)])
@@ -199,6 +218,52 @@ PORT_API int port_resize(const void* src, size_t sstep, int sw, int sh, void* ds
             else for (int e = 0; e < dw * cn; e++) sum[e] += beta * buf[e];
         }
         free(buf); free(tabs[0]); free(tabs[1]);
+        return 0;
+    }
+    if (interp == 4) {
+        /* INTER_LANCZOS4 (resize.cpp:974-1003 weights, :2066-2116 rows, :2119-2157 + :1596-1621 columns): 8 taps at s-3 .. s+4 around
+         * s = floor((d + 0.5) * scale - 0.5), indices clamped to the image; 8-bit: weights cvRound(w * 2048) as shorts, int sums,
+         * (v + 2^21) >> 22; float: rows summed left to right, columns right to left in the 4-lane SIMD body
+         * (S0*b0 + (S1*b1 + ... (S6*b6 + S7*b7))) and left to right in the last (dw * cn) % 4 elements; no fused operations. */
+        int* os[2]; float* co[2];
+        for (int pass = 0; pass < 2; pass++) {
+            int dn = pass ? dh : dw; double sc = pass ? scale_y : scale_x;
+            os[pass] = (int*)malloc(sizeof(int) * (size_t)dn); co[pass] = (float*)malloc(sizeof(float) * 8 * (size_t)dn);
+            for (int d = 0; d < dn; d++) {
+                float f = (float)((d + 0.5) * sc - 0.5); int s = (int)floorf(f); f -= s;
+                os[pass][d] = s;
+                lanczos4_c(f, co[pass] + 8 * d);
+            }
+        }
+        const int body = ((dw * cn) / 4) * 4;
+        for (int y = 0; y < dh; y++)
+            for (int x = 0; x < dw; x++)
+                for (int c = 0; c < cn; c++) {
+                    int xi[8], yi[8], e = x * cn + c;
+                    for (int j = 0; j < 8; j++) { xi[j] = clipi(os[0][x] - 3 + j, 0, sw); yi[j] = clipi(os[1][y] - 3 + j, 0, sh); }
+                    const float* a = co[0] + 8 * x; const float* b = co[1] + 8 * y;
+                    if (depth == P_8U) {
+                        int t[8], v = 0;
+                        for (int k = 0; k < 8; k++) {
+                            const uchar* r = (const uchar*)src + (size_t)yi[k] * sstep; t[k] = 0;
+                            for (int j = 0; j < 8; j++) t[k] += r[xi[j] * cn + c] * s16(a[j] * 2048.f);
+                        }
+                        for (int k = 0; k < 8; k++) v = (int)((unsigned)v + (unsigned)t[k] * (unsigned)(int)s16(b[k] * 2048.f));
+                        ((uchar*)dst + (size_t)y * dstep)[e] = port_sat_u8i((int)((unsigned)v + (1u << 21)) >> 22);
+                    } else {
+                        float t[8], o;
+                        for (int k = 0; k < 8; k++) {
+                            const float* r = (const float*)((const char*)src + (size_t)yi[k] * sstep);
+                            float v = r[xi[0] * cn + c] * a[0];
+                            for (int j = 1; j < 8; j++) v += r[xi[j] * cn + c] * a[j];
+                            t[k] = v;
+                        }
+                        if (e < body) { o = t[7] * b[7]; for (int k = 6; k >= 0; k--) o = t[k] * b[k] + o; }
+                        else { o = t[0] * b[0]; for (int k = 1; k < 8; k++) o += t[k] * b[k]; }
+                        ((float*)((char*)dst + (size_t)y * dstep))[e] = o;
+                    }
+                }
+        free(os[0]); free(os[1]); free(co[0]); free(co[1]);
         return 0;
     }
 area_as_linear:;

@@ -9,6 +9,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define __global__
@@ -31,6 +32,10 @@ typedef void* cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+static inline cudaError_t cudaMallocAsync(void** p, size_t n, cudaStream_t) { *p = malloc(n); return *p ? cudaSuccess : 2; }
+static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 
 template <typename T> static inline T min(T a, T b) { return b < a ? b : a; }
 template <typename T> static inline T max(T a, T b) { return a < b ? b : a; }

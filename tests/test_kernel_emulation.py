@@ -198,3 +198,32 @@ def test_emulated_exact_resizers_vs_port(exact_emu, port, rng):
             assert np.array_equal(exact_emu(u8, (dw, dh), 5), port.resize(u8, (dw, dh), 5)), "LINEAR_EXACT %s -> %s cn=%d" % ((sh, sw), (dh, dw), cn)
             for img in (u8, f32):
                 assert np.array_equal(exact_emu(img, (dw, dh), 6), port.resize(img, (dw, dh), 6)), "NEAREST_EXACT %s %s -> %s cn=%d" % (img.dtype, (sh, sw), (dh, dw), cn)
+
+
+# ---- INTER_LANCZOS4 (resize_lanczos.cu): host-built weight tables + the per-element kernel ------------------------------------------------
+@pytest.fixture(scope="module")
+def lanczos_emu():
+    lib = build_emulation("resize_lanczos.cu", "int emu_resize_lanczos(const b200cvMat* s, const b200cvMat* d)",
+                          "    return b200cv::resize_lanczos_impl(b200cv::make_img(s), b200cv::make_img(d), B200CV_DEPTH(s->type), B200CV_CN(s->type), nullptr);")
+    lib.emu_resize_lanczos.argtypes = [ctypes.POINTER(Mat), ctypes.POINTER(Mat)]
+
+    def run(src, dsize):
+        dw, dh = dsize
+        dst = np.zeros((dh, dw) + src.shape[2:], src.dtype)
+        ms, md = mat_of(src), mat_of(dst)
+        if src.dtype == np.float32:
+            ms.type |= 5; md.type |= 5
+        rc = lib.emu_resize_lanczos(ctypes.byref(ms), ctypes.byref(md))
+        assert rc == 0, "emulated resize_lanczos_impl returned %d" % rc
+        return dst
+    return run
+
+
+def test_emulated_lanczos4_resize_vs_port(lanczos_emu, port, rng):
+    cases = [((40, 60), (120, 180)), ((40, 60), (97, 131)), ((100, 150), (237, 341)), ((97, 131), (98, 132)), ((64, 64), (160, 32)), ((120, 180), (40, 61)),
+             ((1, 47), (5, 90)), ((50, 1), (75, 23)), ((3, 5), (30, 50)), ((120, 160), (121, 100)), ((240, 320), (150, 201))]
+    for (sh, sw), (dh, dw) in cases:
+        for cn in (1, 3, 4):
+            shape = (sh, sw) if cn == 1 else (sh, sw, cn)
+            for img in (rng.integers(0, 256, shape, dtype=np.uint8), (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)):
+                assert np.array_equal(lanczos_emu(img, (dw, dh)), port.resize(img, (dw, dh), 4)), "LANCZOS4 %s %s -> %s cn=%d" % (img.dtype, (sh, sw), (dh, dw), cn)

@@ -245,6 +245,18 @@ def test_port_vs_reference_exact_resizers(ref, port, rng):
                         "interp %d %s %s -> %s cn=%d" % (interp, img.dtype, (sh, sw), (dh, dw), cn)
 
 
+def test_port_vs_reference_lanczos4_resize(ref, port, rng):
+    """INTER_LANCZOS4: 8 x 8 taps, weights from double sin / cos (the same libm as the reference's), 8-bit fixed point and float with the
+    reference's body / remainder summation orders"""
+    cases = [((40, 60), (120, 180)), ((40, 60), (97, 131)), ((100, 150), (237, 341)), ((97, 131), (98, 132)), ((64, 64), (160, 32)), ((120, 180), (40, 61)),
+             ((1, 47), (5, 90)), ((50, 1), (75, 23)), ((3, 5), (30, 50)), ((120, 160), (121, 100)), ((240, 320), (150, 201)), ((480, 640), (300, 402))]
+    for (sh, sw), (dh, dw) in cases:
+        for cn in (1, 3, 4):
+            shape = (sh, sw) if cn == 1 else (sh, sw, cn)
+            for img in (rng.integers(0, 256, shape, dtype=np.uint8), (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)):
+                assert np.array_equal(ref.resize(img, (dw, dh), 4), port.resize(img, (dw, dh), 4)), "LANCZOS4 %s %s -> %s cn=%d" % (img.dtype, (sh, sw), (dh, dw), cn)
+
+
 def test_port_vs_reference_remap(ref, port, rng):
     """cv::remap restated in the port: float planes, packed float pairs, fixed-point maps (incl. the NNDeltaTab_i quirk), NaN and
     out-of-range coordinates -- bit-exact against the reference for u8 and f32."""
