@@ -271,6 +271,16 @@ class Oracle:
         cnt = min(n.value, max_out)
         return pts[:cnt].copy(), q[:cnt].copy()
 
+    def sift_detect_and_compute(self, gray, nfeatures=0, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, max_kp=200000):
+        """the reference's cv::SIFT::detectAndCompute (real reference only): (keypoints[n,5] = x, y, size, angle, response; octave[n]; desc[n,128])"""
+        gray = np.ascontiguousarray(gray)
+        h, w = gray.shape
+        kp = np.zeros((max_kp, 6), np.float32); desc = np.zeros((max_kp, 128), np.float32); n = ctypes.c_int(0)
+        self._ok(self.fn("sift_detect_and_compute")(_p(gray), sz(gray.strides[0]), w, h, int(nfeatures), int(nOctaveLayers), dbl(contrastThreshold),
+                                                     dbl(edgeThreshold), dbl(sigma), int(max_kp), _p(kp), _p(desc), ctypes.byref(n)), "SIFT")
+        m = min(n.value, max_kp)
+        return kp[:m, :5].copy(), kp[:m, 5].copy().view(np.int32), desc[:m].copy()
+
     def sift_pyramid(self, gray, nOctaveLayers=3, sigma=1.6, upscale=True):
         """returns (gauss list-of-lists [octave][layer], dog list-of-lists)"""
         gray = np.ascontiguousarray(gray)

@@ -282,6 +282,29 @@ API int ref_good_features_to_track(const void* src, size_t sstep, int w, int h, 
     GUARD_END
 }
 
+// ---- the whole SIFT front end (detectAndCompute, sift.dispatch.cpp:501-580): keypoints + descriptors of the unmodified reference.
+// kp: 6 floats per keypoint (x, y, size, angle, response, octave as int bits), desc: 128 floats per keypoint; at most max_kp are written,
+// *n receives the number found.  The oracle for SURVEY 8(f) rank 1 (scale-space extrema, orientation, descriptors).
+API int ref_sift_detect_and_compute(const void* gray, size_t step, int w, int h, int nfeatures, int nOctaveLayers, double contrastThreshold,
+                                    double edgeThreshold, double sigma, int max_kp, float* kp, float* desc, int* n)
+{
+    GUARD_BEGIN
+    Mat image = hdr(gray, step, w, h, CV_8UC1);
+    Ptr<SIFT> sp = SIFT::create(nfeatures, nOctaveLayers, contrastThreshold, edgeThreshold, sigma);
+    std::vector<KeyPoint> kps;
+    Mat d;
+    sp->detectAndCompute(image, noArray(), kps, d);
+    *n = (int)kps.size();
+    for (int i = 0; i < (int)kps.size() && i < max_kp; i++) {
+        const KeyPoint& k = kps[i];
+        float* o = kp + 6 * i;
+        o[0] = k.pt.x; o[1] = k.pt.y; o[2] = k.size; o[3] = k.angle; o[4] = k.response;
+        std::memcpy(o + 5, &k.octave, 4);
+        if (desc) std::memcpy(desc + 128 * (size_t)i, d.ptr<float>(i), 128 * sizeof(float));
+    }
+    GUARD_END
+}
+
 // ---- SIFT Gaussian pyramid + DoG (sift.dispatch.cpp:176-310, :501-545 for the octave count) ----
 // gray: 8UC1 w x h.  Outputs are packed tightly, image after image, octave-major:
 //   gauss: nOctaves*(nOctaveLayers+3) images, dog: nOctaves*(nOctaveLayers+2) images, all CV_32F.

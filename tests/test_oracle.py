@@ -257,6 +257,18 @@ def test_port_vs_reference_lanczos4_resize(ref, port, rng):
                 assert np.array_equal(ref.resize(img, (dw, dh), 4), port.resize(img, (dw, dh), 4)), "LANCZOS4 %s %s -> %s cn=%d" % (img.dtype, (sh, sw), (dh, dw), cn)
 
 
+def test_reference_sift_front_end_is_reachable(ref, rng):
+    """the oracle for SURVEY 8(f) rank 1: cv::SIFT::detectAndCompute of the unmodified reference (keypoints + 128-float descriptors)"""
+    small = rng.random((30, 40)).astype(np.float32)
+    img = (np.kron(small, np.ones((8, 8), np.float32)) * 255).astype(np.uint8)
+    kp, octv, desc = ref.sift_detect_and_compute(img)
+    kp2, octv2, desc2 = ref.sift_detect_and_compute(img)
+    assert len(kp) > 20 and desc.shape == (len(kp), 128)
+    assert np.array_equal(kp, kp2) and np.array_equal(desc, desc2) and np.array_equal(octv, octv2), "the reference's SIFT is deterministic"
+    assert (kp[:, 0] >= 0).all() and (kp[:, 0] < img.shape[1]).all() and (kp[:, 1] >= 0).all() and (kp[:, 1] < img.shape[0]).all()
+    assert np.all(desc >= 0) and np.all(desc <= 255) and np.all(desc == np.round(desc)), "descriptors are 8-bit-valued floats (sift.simd.hpp:1018-1034)"
+
+
 def test_port_vs_reference_remap(ref, port, rng):
     """cv::remap restated in the port: float planes, packed float pairs, fixed-point maps (incl. the NNDeltaTab_i quirk), NaN and
     out-of-range coordinates -- bit-exact against the reference for u8 and f32."""
