@@ -232,6 +232,9 @@ def filter2D(src, ddepth, kernel, anchor=(-1, -1), delta=0.0, borderType=BORDER_
 
 def Sobel(src, ddepth, dx, dy, ksize=3, scale=1.0, delta=0.0, borderType=BORDER_DEFAULT, dst=None, stream=None):
     """cv::Sobel (imgproc.hpp:1862)"""
+    if not _is_torch(src):
+        from . import hal
+        return hal.Sobel(src, ddepth, dx, dy, ksize, scale, delta, borderType, dst)
     dst = dst if dst is not None else _new(src, dtype=_ddepth_dtype(src, ddepth))
     ms, md = _pair(src, dst)
     _check(lib().b200cv_sobel(ctypes.byref(ms), ctypes.byref(md), int(dx), int(dy), int(ksize), ctypes.c_double(scale),

@@ -94,6 +94,18 @@ def filter2D(src, ddepth, kernel, anchor=(-1, -1), delta=0.0, borderType=BORDER_
     return dst
 
 
+def Sobel(src, ddepth, dx, dy, ksize=3, scale=1.0, delta=0.0, borderType=BORDER_DEFAULT, dst=None):
+    dst = dst if dst is not None else _new(src, dtype=_ddt(src, ddepth))
+    ms, md = describe(src), describe(dst)
+    _check(lib().b200cv_host_sobel(ctypes.byref(ms), ctypes.byref(md), int(dx), int(dy), int(ksize), ctypes.c_double(scale), ctypes.c_double(delta),
+                                   int(borderType)), "Sobel")
+    return dst
+
+
+def Scharr(src, ddepth, dx, dy, scale=1.0, delta=0.0, borderType=BORDER_DEFAULT, dst=None):
+    return Sobel(src, ddepth, dx, dy, -1, scale, delta, borderType, dst)
+
+
 def cvtColor(src, code, dstCn=0, dst=None):
     m = describe(src)
     w, h, dcn = _cvt_dst_geometry(int(code), m.cols, m.rows, dstCn)

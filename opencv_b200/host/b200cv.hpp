@@ -36,7 +36,7 @@ struct Scalar { double val[4] = {0, 0, 0, 0}; Scalar() {} Scalar(double a, doubl
 enum { CV_8U = 0, CV_16S = 3, CV_32F = 5 };
 inline int makeType(int depth, int cn) { return B200CV_MAKETYPE(depth, cn); }
 enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_WRAP = 3, BORDER_REFLECT_101 = 4, BORDER_DEFAULT = 4 };
-enum { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2, INTER_AREA = 3, WARP_INVERSE_MAP = 16 };
+enum { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2, INTER_AREA = 3, INTER_LANCZOS4 = 4, INTER_LINEAR_EXACT = 5, INTER_NEAREST_EXACT = 6, WARP_INVERSE_MAP = 16 };
 
 class Event;
 class Stream {
@@ -156,8 +156,20 @@ inline void remap(const GpuMat& src, GpuMat& dst, const GpuMat& map1, const GpuM
     b200cvMat a = src.desc(), b = dst.desc(), m1 = map1.desc(), m2 = map2.desc();
     check(b200cv_remap(&a, &b, &m1, map2.data ? &m2 : nullptr, interpolation, borderMode, bv.val, s.cudaPtr()), "remap");
 }
-inline void cvtColor(const GpuMat& src, GpuMat& dst, int code, int dcn, Stream& s = Stream::Null())
-{ B200CV_DST(dst, src, makeType(B200CV_DEPTH(src.type()), dcn)); b200cvMat a = src.desc(), b = dst.desc(); check(b200cv_cvt_color(&a, &b, code, s.cudaPtr()), "cvtColor"); }
+// destination geometry of cv::cvtColor (color.cpp:323-372): the subsampled-YUV wire formats change the size, everything else keeps it
+inline void cvtColorGeometry(int code, int cols, int rows, int dcn, int& w, int& h, int& cn)
+{
+    w = cols; h = rows; cn = dcn;
+    if (code >= 90 && code <= 105) { h = rows * 2 / 3; cn = (code >= 94 && code <= 97) || code >= 102 ? 4 : 3; }
+    else if (code == 106) { h = rows * 2 / 3; cn = 1; }
+    else if (code >= 107 && code <= 122) cn = (code == 111 || code == 112 || code >= 119) ? 4 : 3;
+    else if (code == 123 || code == 124) cn = 1;
+    else if (code >= 127 && code <= 134) { h = rows * 3 / 2; cn = 1; }
+    else if (cn <= 0) cn = (code == 0 || code == 2 || code == 5 || code == 9) ? 4 : (code == 6 || code == 7 || code == 10 || code == 11) ? 1 : 3;
+}
+inline void cvtColor(const GpuMat& src, GpuMat& dst, int code, int dcn = 0, Stream& s = Stream::Null())
+{ int w, h, cn; cvtColorGeometry(code, src.cols, src.rows, dcn, w, h, cn);
+  dst.create(h, w, makeType(B200CV_DEPTH(src.type()), cn), src.frames); b200cvMat a = src.desc(), b = dst.desc(); check(b200cv_cvt_color(&a, &b, code, s.cudaPtr()), "cvtColor"); }
 inline void matchTemplate(const GpuMat& image, const GpuMat& templ, GpuMat& result, int method, Stream& s = Stream::Null())
 { result.create(image.rows - templ.rows + 1, image.cols - templ.cols + 1, makeType(CV_32F, 1), image.frames); b200cvMat a = image.desc(), t = templ.desc(), r = result.desc();
   check(b200cv_match_template(&a, &t, &r, method, s.cudaPtr()), "matchTemplate"); }
@@ -218,8 +230,9 @@ namespace b200cv {
 inline b200cvMat hostDesc(const cv::Mat& m) { b200cvMat d = {m.data, m.step, m.cols, m.rows, m.type(), 1, 0}; return d; }
 inline void GaussianBlur(const cv::Mat& src, cv::Mat& dst, cv::Size ksize, double sigmaX, double sigmaY = 0, int borderType = cv::BORDER_DEFAULT)
 { dst.create(src.size(), src.type()); b200cvMat a = hostDesc(src), b = hostDesc(dst); check(b200cv_host_gaussian_blur(&a, &b, ksize.width, ksize.height, sigmaX, sigmaY, borderType), "GaussianBlur"); }
-inline void cvtColor(const cv::Mat& src, cv::Mat& dst, int code, int dcn)
-{ dst.create(src.size(), CV_MAKETYPE(src.depth(), dcn)); b200cvMat a = hostDesc(src), b = hostDesc(dst); check(b200cv_host_cvt_color(&a, &b, code), "cvtColor"); }
+inline void cvtColor(const cv::Mat& src, cv::Mat& dst, int code, int dcn = 0)
+{ int w, h, cn; cvtColorGeometry(code, src.cols, src.rows, dcn, w, h, cn);
+  dst.create(h, w, CV_MAKETYPE(src.depth(), cn)); b200cvMat a = hostDesc(src), b = hostDesc(dst); check(b200cv_host_cvt_color(&a, &b, code), "cvtColor"); }
 inline void resize(const cv::Mat& src, cv::Mat& dst, cv::Size dsize, double = 0, double = 0, int interpolation = cv::INTER_LINEAR)
 { dst.create(dsize, src.type()); b200cvMat a = hostDesc(src), b = hostDesc(dst); check(b200cv_host_resize(&a, &b, interpolation), "resize"); }
 #endif
