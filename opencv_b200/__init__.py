@@ -296,6 +296,16 @@ def cvtColor(src, code, dstCn=0, dst=None, stream=None):
     return dst
 
 
+def cvtColorTwoPlane(src1, src2, code, dst=None, stream=None):
+    """cv::cvtColorTwoPlane: NV12 / NV21 with separate luma (H,W) and chroma (H/2,W/2,2) tensors (batches: (N,H,W,1) and (N,H/2,W/2,2))"""
+    m = describe(src1)
+    dcn = 4 if int(code) in (94, 95, 96, 97) else 3
+    dst = dst if dst is not None else _new(src1, channels=dcn)
+    my, muv, md = describe(src1), describe(src2), describe(dst)
+    _check(lib().b200cv_cvt_color_two_plane(ctypes.byref(my), ctypes.byref(muv), ctypes.byref(md), int(code), _stream_ptr(stream)), "cvtColorTwoPlane")
+    return dst
+
+
 def getGaussianKernel(ksize, sigma):
     """cv::getGaussianKernel as float64 (bit-exact softdouble arithmetic on the host)"""
     out = np.zeros(ksize, np.float64)

@@ -265,6 +265,14 @@ using namespace b200cv;
 // number of leading pixels per row that the reference converts in its 32-pixel AVX2 vector body (HSV2RGB_b)
 static inline int hsv_trunc_cols(int width) { return width >= 32 ? (width / 32) * 32 : 0; }
 
+extern "C" int b200cv_cvt_color_two_plane(const b200cvMat* ysrc, const b200cvMat* uvsrc, const b200cvMat* dst, int code, void* stream)
+{
+    int rc;
+    if ((rc = check_mat(ysrc, "src1")) || (rc = check_mat(uvsrc, "src2")) || (rc = check_mat(dst, "dst"))) return rc;
+    if (B200CV_DEPTH(ysrc->type) != B200CV_8U || B200CV_DEPTH(uvsrc->type) != B200CV_8U || B200CV_DEPTH(dst->type) != B200CV_8U) return B200CV_NOT_IMPLEMENTED;
+    return cvt_color_two_plane(ysrc, uvsrc, dst, code, as_stream(stream));
+}
+
 extern "C" int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int code, void* stream)
 {
     int rc;

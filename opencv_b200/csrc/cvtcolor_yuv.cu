@@ -102,8 +102,10 @@ __device__ __forceinline__ void yuv_pixel(int y, const UvTerm& t, int bidx, ucha
 }
 
 // ---- 4:2:0 -> BGR family ---------------------------------------------------------------------------------------------------------
+// ysrc: the H luma rows; csrc: the chroma rows that follow them (interleaved rows of W bytes, or planar half rows, two to a row) -- a view
+// into the same buffer for cv::cvtColor, a buffer of its own for cv::cvtColorTwoPlane
 template <int DCN, bool PLANAR>
-__global__ void __launch_bounds__(256) yuv420_to_bgr_kernel(Img src, Img dst, int W, int H, int bidx, int uidx)
+__global__ void __launch_bounds__(256) yuv420_to_bgr_kernel(Img ysrc, Img csrc, Img dst, int W, int H, int bidx, int uidx)
 {
     const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;              // row pair
@@ -111,18 +113,18 @@ __global__ void __launch_bounds__(256) yuv420_to_bgr_kernel(Img src, Img dst, in
     if (x0 >= W || 2 * j >= H) return;
     const int n = min(8, W - x0);                                     // even: W is even
     uchar ya[8], yb[8], cu[4], cv[4];
-    load_bytes<8>(src.row<uchar>(f, 2 * j) + x0, n, ya);
-    load_bytes<8>(src.row<uchar>(f, 2 * j + 1) + x0, n, yb);
+    load_bytes<8>(ysrc.row<uchar>(f, 2 * j) + x0, n, ya);
+    load_bytes<8>(ysrc.row<uchar>(f, 2 * j + 1) + x0, n, yb);
     if constexpr (PLANAR) {
         const int k0 = j, k1 = H / 2 + j;                             // half-row index in the first / second chroma plane
         uchar pa[4], pb[4];
-        load_bytes<4>(src.row<uchar>(f, H + k0 / 2) + (k0 & 1) * (W / 2) + x0 / 2, n / 2, pa);
-        load_bytes<4>(src.row<uchar>(f, H + k1 / 2) + (k1 & 1) * (W / 2) + x0 / 2, n / 2, pb);
+        load_bytes<4>(csrc.row<uchar>(f, k0 / 2) + (k0 & 1) * (W / 2) + x0 / 2, n / 2, pa);
+        load_bytes<4>(csrc.row<uchar>(f, k1 / 2) + (k1 & 1) * (W / 2) + x0 / 2, n / 2, pb);
 #pragma unroll
         for (int i = 0; i < 4; i++) { cu[i] = uidx ? pb[i] : pa[i]; cv[i] = uidx ? pa[i] : pb[i]; }
     } else {
         uchar c[8];
-        load_bytes<8>(src.row<uchar>(f, H + j) + x0, n, c);
+        load_bytes<8>(csrc.row<uchar>(f, j) + x0, n, c);
 #pragma unroll
         for (int i = 0; i < 4; i++) { cu[i] = uidx ? c[2 * i + 1] : c[2 * i]; cv[i] = uidx ? c[2 * i] : c[2 * i + 1]; }
     }
@@ -246,12 +248,14 @@ int cvt_color_yuv(const b200cvMat* src, const b200cvMat* dst, int code, cudaStre
         const int bidx = rgb ? 2 : 0;
         const dim3 grid = yuv_grid(W, H / 2, s.frames, block);
         if (grid.y >= 65536) return B200CV_NOT_IMPLEMENTED;
+        Img c = s;                                                     // the chroma rows follow the H luma rows in the same buffer
+        c.data += (size_t)H * s.step; c.rows = H / 2;
         if (planar) {
-            if (dcn == 3) yuv420_to_bgr_kernel<3, true><<<grid, block, 0, st>>>(s, d, W, H, bidx, uidx);
-            else yuv420_to_bgr_kernel<4, true><<<grid, block, 0, st>>>(s, d, W, H, bidx, uidx);
+            if (dcn == 3) yuv420_to_bgr_kernel<3, true><<<grid, block, 0, st>>>(s, c, d, W, H, bidx, uidx);
+            else yuv420_to_bgr_kernel<4, true><<<grid, block, 0, st>>>(s, c, d, W, H, bidx, uidx);
         } else {
-            if (dcn == 3) yuv420_to_bgr_kernel<3, false><<<grid, block, 0, st>>>(s, d, W, H, bidx, uidx);
-            else yuv420_to_bgr_kernel<4, false><<<grid, block, 0, st>>>(s, d, W, H, bidx, uidx);
+            if (dcn == 3) yuv420_to_bgr_kernel<3, false><<<grid, block, 0, st>>>(s, c, d, W, H, bidx, uidx);
+            else yuv420_to_bgr_kernel<4, false><<<grid, block, 0, st>>>(s, c, d, W, H, bidx, uidx);
         }
         B200_LAUNCH_CHECK();
         return B200CV_OK;
@@ -293,6 +297,29 @@ int cvt_color_yuv(const b200cvMat* src, const b200cvMat* dst, int code, cudaStre
         return B200CV_OK;
     }
     return B200CV_NOT_IMPLEMENTED;
+}
+
+// cv::cvtColorTwoPlane (color.cpp:171-185): NV12 / NV21 with the luma plane (8UC1, W x H) and the interleaved chroma plane (8UC2,
+// W/2 x H/2) in buffers of their own, each with its own pitch -- what hardware decoders hand out.  Codes 90-97 only, as in the reference.
+int cvt_color_two_plane(const b200cvMat* ysrc, const b200cvMat* uvsrc, const b200cvMat* dst, int code, cudaStream_t st)
+{
+    if (code < 90 || code > 97) return B200CV_NOT_IMPLEMENTED;
+    const int W = dst->cols, H = dst->rows, dcn = B200CV_CN(dst->type);
+    B200_REQUIRE(B200CV_CN(ysrc->type) == 1 && ysrc->cols == W && ysrc->rows == H && (W & 1) == 0 && (H & 1) == 0 && W > 0 && H > 0,
+                 "cvtColorTwoPlane: the luma plane must be 8UC1 of the destination's (even) size");
+    B200_REQUIRE(B200CV_CN(uvsrc->type) == 2 && uvsrc->cols == W / 2 && uvsrc->rows == H / 2, "cvtColorTwoPlane: the chroma plane must be 8UC2 of half the size");
+    const int c = code - 90, rgb = !(c & 1), uidx = (c >> 1) & 1;
+    B200_REQUIRE((c >= 4) == (dcn == 4) && (dcn == 3 || dcn == 4), "channel count does not match the colour code");
+    Img y = make_img(ysrc), uv = make_img(uvsrc), d = make_img(dst);
+    B200_REQUIRE(y.frames == uv.frames && y.frames == d.frames, "src/dst batch mismatch");
+    if (y.frames >= 65536) return B200CV_NOT_IMPLEMENTED;
+    const dim3 block(32, 8);
+    const dim3 grid = yuv_grid(W, H / 2, y.frames, block);
+    if (grid.y >= 65536) return B200CV_NOT_IMPLEMENTED;
+    if (dcn == 3) yuv420_to_bgr_kernel<3, false><<<grid, block, 0, st>>>(y, uv, d, W, H, rgb ? 2 : 0, uidx);
+    else yuv420_to_bgr_kernel<4, false><<<grid, block, 0, st>>>(y, uv, d, W, H, rgb ? 2 : 0, uidx);
+    B200_LAUNCH_CHECK();
+    return B200CV_OK;
 }
 
 }  // namespace b200cv

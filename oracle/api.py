@@ -232,6 +232,14 @@ class Oracle:
         self._ok(self.fn("cvt_color_yuv")(_p(src), sz(src.strides[0]), sw, sh, scn, _p(dst), sz(dst.strides[0]), dw, dh, dcn, int(code)), "cvtColor(YUV)")
         return dst
 
+    def cvtColorTwoPlane(self, y, uv, code):
+        y = np.ascontiguousarray(y); uv = np.ascontiguousarray(uv)
+        h, w = y.shape[:2]
+        dcn = 4 if int(code) in (94, 95, 96, 97) else 3
+        dst = np.zeros((h, w, dcn), np.uint8)
+        self._ok(self.fn("cvt_color_two_plane")(_p(y), sz(y.strides[0]), _p(uv), sz(uv.strides[0]), w, h, _p(dst), sz(dst.strides[0]), dcn, int(code)), "cvtColorTwoPlane")
+        return dst
+
     def matchTemplate(self, image, templ, method):
         image = np.ascontiguousarray(image)
         templ = np.ascontiguousarray(templ)

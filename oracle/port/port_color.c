@@ -130,6 +130,19 @@ static void yuv_px(int y, int u, int v, int bidx, int dcn, uchar* d)
     if (dcn == 4) d[3] = 255;
 }
 
+/* cv::cvtColorTwoPlane (color.cpp:171-185): NV12 / NV21 with separate luma / chroma buffers */
+PORT_API int port_cvt_color_two_plane(const void* y_, size_t ystep, const void* uv_, size_t uvstep, int w, int h, void* dst_, size_t dstep, int dcn, int code)
+{
+    if (code < 90 || code > 97 || (w & 1) || (h & 1) || (dcn != 3 && dcn != 4)) return -1;
+    const int c = code - 90, rgb = !(c & 1), uidx = (c >> 1) & 1, bidx = rgb ? 2 : 0;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uchar* uv = (const uchar*)uv_ + (size_t)(y / 2) * uvstep + (x & ~1);
+            yuv_px(((const uchar*)y_ + (size_t)y * ystep)[x], uv[uidx], uv[1 - uidx], bidx, dcn, (uchar*)dst_ + (size_t)y * dstep + x * dcn);
+        }
+    return 0;
+}
+
 PORT_API int port_cvt_color_yuv(const void* src_, size_t sstep, int sw, int sh, int scn, void* dst_, size_t dstep, int dw, int dh, int dcn, int code)
 {
     const uchar* src = (const uchar*)src_;

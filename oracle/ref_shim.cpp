@@ -232,6 +232,15 @@ API int ref_cvt_color_yuv(const void* src, size_t sstep, int sw, int sh, int scn
     GUARD_END
 }
 
+API int ref_cvt_color_two_plane(const void* y, size_t ystep, const void* uv, size_t uvstep, int w, int h, void* dst, size_t dstep, int dcn, int code)
+{
+    GUARD_BEGIN
+    Mat sy = hdr(y, ystep, w, h, CV_8UC1), suv = hdr(uv, uvstep, w / 2, h / 2, CV_8UC2), d = hdr(dst, dstep, w, h, CV_MAKETYPE(CV_8U, dcn));
+    cvtColorTwoPlane(sy, suv, d, code);
+    CV_Assert(d.data == (uchar*)dst);
+    GUARD_END
+}
+
 API int ref_match_template(const void* img, size_t istep, int iw, int ih, const void* templ, size_t tstep, int tw, int th,
                            int type, float* result, size_t rstep, int method)
 {

@@ -77,6 +77,20 @@ def test_yuv_padded_rows_and_batches(cvb, oracle, rng):
     assert torch.cuda.is_available()
 
 
+def test_two_plane(cvb, oracle, rng):
+    """cv::cvtColorTwoPlane: luma and interleaved chroma in buffers of their own (own pitches), single frames and a batch"""
+    for (h, w) in [(18, 34), (250, 322), (1080, 1920)]:
+        y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        wide = rng.integers(0, 256, (h // 2, w // 2 + 3, 2), dtype=np.uint8)
+        uv = gpu(wide)[:, 1:1 + w // 2]
+        for code in range(90, 98):
+            got = cpu(cvb.cvtColorTwoPlane(gpu(y), uv, code))
+            assert_exact(got, oracle.cvtColorTwoPlane(y, np.ascontiguousarray(wide[:, 1:1 + w // 2]), code), "two-plane code %d %dx%d" % (code, w, h))
+    yb = rng.integers(0, 256, (3, 240, 320, 1), dtype=np.uint8); uvb = rng.integers(0, 256, (3, 120, 160, 2), dtype=np.uint8)
+    out = cpu(cvb.cvtColorTwoPlane(gpu(yb), gpu(uvb), C.COLOR_YUV2BGR_NV12))
+    assert_exact(out[2], oracle.cvtColorTwoPlane(yb[2, :, :, 0], uvb[2], C.COLOR_YUV2BGR_NV12), "two-plane batch frame 2")
+
+
 def test_yuv_round_trip_4k(cvb, rng):
     """size-independent property at full size: BGR -> I420 -> BGR stays within the quantisation of the 4:2:0 format on a smooth image,
     and NV12 -> GRAY returns the luma plane untouched"""

@@ -32,8 +32,9 @@ def build_emulation(cu_name, entry_decl, entry_body):
     src = open(os.path.join(CSRC, cu_name)).read()
     translated, n = LAUNCH.subn(r"EMU_LAUNCH(grid, block, \1(\2));", src)
     assert n > 0 and "<<<" not in translated, "untranslated kernel launch left in %s" % cu_name
-    cpp = os.path.join(OUT, cu_name.replace(".cu", "_emu.cpp"))
-    so = os.path.join(OUT, cu_name.replace(".cu", "_emu.so"))
+    tag = re.search(r"(\w+)\(", entry_decl).group(1)            # one library per entry point: a loaded .so is never overwritten
+    cpp = os.path.join(OUT, tag + ".cpp")
+    so = os.path.join(OUT, tag + ".so")
     with open(cpp, "w") as f:
         f.write("#define B200CV_HOST_EMULATION 1\n" + translated + STUBS + 'extern "C" ' + entry_decl + "\n{\n" + entry_body + "\n}\n")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", CSRC, "-I", os.path.join(ROOT, "tests", "emu"), cpp, "-o", so])
@@ -76,6 +77,31 @@ def yuv_emu():
         assert rc == 0, "emulated cvt_color_yuv(code %d) returned %d" % (code, rc)
         return dst
     return run
+
+
+@pytest.fixture(scope="module")
+def two_plane_emu():
+    lib = build_emulation("cvtcolor_yuv.cu", "int emu_two_plane(const b200cvMat* y, const b200cvMat* uv, const b200cvMat* d, int code)",
+                          "    return b200cv::cvt_color_two_plane(y, uv, d, code, nullptr);")
+    lib.emu_two_plane.argtypes = [ctypes.POINTER(Mat)] * 3 + [ctypes.c_int]
+
+    def run(y, uv, code):
+        h, w = y.shape[:2]
+        dst = np.zeros((h, w, 4 if code >= 94 else 3), np.uint8)
+        my, muv, md = mat_of(y), mat_of(uv), mat_of(dst)
+        rc = lib.emu_two_plane(ctypes.byref(my), ctypes.byref(muv), ctypes.byref(md), int(code))
+        assert rc == 0, "emulated cvt_color_two_plane(code %d) returned %d" % (code, rc)
+        return dst
+    return run
+
+
+def test_emulated_two_plane_vs_port(two_plane_emu, port, rng):
+    for (h, w) in [(2, 2), (18, 34), (66, 130), (250, 322)]:
+        y = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        wide = rng.integers(0, 256, (h // 2, w // 2 + 3, 2), dtype=np.uint8)
+        uv = wide[:, 1:1 + w // 2]                                  # a pitch of its own, base address off by 2 bytes
+        for code in range(90, 98):
+            assert np.array_equal(two_plane_emu(y, uv, code), port.cvtColorTwoPlane(y, np.ascontiguousarray(uv), code)), "two-plane code %d %dx%d" % (code, w, h)
 
 
 KAT_YUV = {90: 0x46a1bb76, 91: 0x3843bb76, 92: 0xf3fdf2ea, 93: 0x6e84f2ea, 94: 0xb6a16bd3, 95: 0xa8436bd3, 96: 0x1c7fa347, 97: 0x96f7a347,

@@ -119,6 +119,17 @@ def test_port_vs_reference_yuv_wire_formats(ref, port, rng):
             assert np.array_equal(ref.cvtColorYUV(img, code), port.cvtColorYUV(img, code)), "to 4:2:0 code %d %dx%d" % (code, w, h)
 
 
+def test_port_vs_reference_two_plane(ref, port, rng):
+    """cv::cvtColorTwoPlane: the same arithmetic with separate luma / chroma buffers; also equal to cvtColor on the concatenated planes"""
+    for (h, w) in [(4, 6), (18, 34), (250, 322)]:
+        y = rng.integers(0, 256, (h, w), dtype=np.uint8); uv = rng.integers(0, 256, (h // 2, w // 2, 2), dtype=np.uint8)
+        one = np.concatenate([y, uv.reshape(h // 2, w)], axis=0)
+        for code in range(90, 98):
+            a = ref.cvtColorTwoPlane(y, uv, code)
+            assert np.array_equal(a, port.cvtColorTwoPlane(y, uv, code)), "two-plane code %d" % code
+            assert np.array_equal(a, ref.cvtColorYUV(one, code)), "two-plane == one buffer, code %d" % code
+
+
 def test_kat_input_is_the_reference_rng_stream(ref):
     """tests/golden/cvtcolor_kat_input.npy was generated by cv::RNG(0).fill(263x255 8UC3, UNIFORM, 0, 255) -- regenerate and compare"""
     img = np.load(os.path.join(GOLD, "cvtcolor_kat_input.npy"))
