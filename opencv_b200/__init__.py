@@ -444,6 +444,46 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, blockSize=
     return out if image.dim() == 4 else out[0]
 
 
+class GFTTDetector:
+    """cv::GFTTDetector (features2d.hpp; features2d/src/gftt.cpp:44-157): the Feature2D face of goodFeaturesToTrack.  detect() returns an
+    (n, 4) float32 array per frame: x, y, size (= blockSize, gftt.cpp:147), response (the corner quality); angle / octave are unset
+    in the reference (-1 / 0).  3- and 4-channel frames are converted with COLOR_BGR2GRAY first, as the reference does (gftt.cpp:139-140)."""
+
+    def __init__(self, maxCorners=1000, qualityLevel=0.01, minDistance=1, blockSize=3, gradientSize=3, useHarrisDetector=False, k=0.04):
+        self.maxCorners, self.qualityLevel, self.minDistance = int(maxCorners), float(qualityLevel), float(minDistance)
+        self.blockSize, self.gradientSize, self.useHarrisDetector, self.k = int(blockSize), int(gradientSize), bool(useHarrisDetector), float(k)
+
+    @staticmethod
+    def create(maxCorners=1000, qualityLevel=0.01, minDistance=1, blockSize=3, gradientSize=3, useHarrisDetector=False, k=0.04):
+        return GFTTDetector(maxCorners, qualityLevel, minDistance, blockSize, gradientSize, useHarrisDetector, k)
+
+    def setMaxFeatures(self, v): self.maxCorners = int(v)
+    def getMaxFeatures(self): return self.maxCorners
+    def setQualityLevel(self, v): self.qualityLevel = float(v)
+    def getQualityLevel(self): return self.qualityLevel
+    def setMinDistance(self, v): self.minDistance = float(v)
+    def getMinDistance(self): return self.minDistance
+    def setBlockSize(self, v): self.blockSize = int(v)
+    def getBlockSize(self): return self.blockSize
+    def setGradientSize(self, v): self.gradientSize = int(v)
+    def getGradientSize(self): return self.gradientSize
+    def setHarrisDetector(self, v): self.useHarrisDetector = bool(v)
+    def getHarrisDetector(self): return self.useHarrisDetector
+    def setK(self, v): self.k = float(v)
+    def getK(self): return self.k
+
+    def detect(self, image, stream=None):
+        m = describe(image)
+        if _cn(m) != 1:
+            image = cvtColor(image, COLOR_BGR2GRAY if _cn(m) == 3 else COLOR_BGRA2GRAY, stream=stream)
+        res = goodFeaturesToTrack(image, self.maxCorners, self.qualityLevel, self.minDistance, self.blockSize, self.gradientSize,
+                                  self.useHarrisDetector, self.k, stream=stream, with_quality=True)
+        def pack(r):
+            pts, q = r
+            return np.concatenate([pts, np.full((len(pts), 1), float(self.blockSize), np.float32), q[:, None]], axis=1).astype(np.float32)
+        return [pack(r) for r in res] if image.dim() == 4 else pack(res)
+
+
 def sift_pyramid_layout(width, height, nOctaveLayers=3, upscale=True):
     no = ctypes.c_int(0)
     ge, de = ctypes.c_size_t(0), ctypes.c_size_t(0)

@@ -1,0 +1,26 @@
+"""GPU: cv::GFTTDetector, the Feature2D wrapper over goodFeaturesToTrack (features2d/src/gftt.cpp:131-148).  It only composes calls that
+tests/test_gpu_features.py verifies (cvtColor + goodFeaturesToTrack); the wrapper itself was added after the round's GPU budget was spent,
+hence xfail(strict=False) until its first run."""
+import numpy as np
+import pytest
+
+import opencv_b200 as C
+from util import assert_close, gpu
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="GFTTDetector wrapper has not run on a B200 yet")]
+
+
+def test_gftt_detector(cvb, oracle, rng):
+    small = rng.random((32, 42)).astype(np.float32)
+    gray = (np.kron(small, np.ones((8, 8), np.float32)) * 255).astype(np.uint8)[:240, :320]
+    det = C.GFTTDetector.create(200, 0.01, 5, 3, 3, True, 0.04)
+    kp = det.detect(gpu(gray))
+    want, wq = oracle.goodFeaturesToTrack(gray, 200, 0.01, 5, 3, 3, True, 0.04)
+    assert kp.shape == (len(want), 4)
+    assert np.array_equal(kp[:, :2], want) and (kp[:, 2] == 3).all()
+    assert_close(kp[:, 3], wq, atol=5e-7 * float(np.abs(wq).max()), what="keypoint responses")
+    bgr = np.stack([gray, gray, gray], axis=-1)
+    kp3 = det.detect(gpu(bgr))                      # BGR2GRAY of an r = g = b image is the image itself
+    assert np.array_equal(kp3[:, :2], kp[:, :2])
+    det.setMaxFeatures(10)
+    assert len(det.detect(gpu(gray))) == 10 and det.getMaxFeatures() == 10
