@@ -101,6 +101,8 @@ B200CV_API int b200cv_hal_cvtThreePlaneYUVtoBGR(const b200cv_uchar* src_data, si
                                                 int dcn, bool swapBlue, int uIdx);
 B200CV_API int b200cv_hal_cvtBGRtoThreePlaneYUV(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                                 int scn, bool swapBlue, int uIdx);
+B200CV_API int b200cv_hal_cvtOnePlaneBGRtoYUV(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
+                                              int scn, bool swapBlue, int uIdx, int ycn);      /* hal_ni_cvtOnePlaneBGRtoYUV :866 */
 B200CV_API int b200cv_hal_cvtOnePlaneYUVtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                               int dcn, bool swapBlue, int uIdx, int ycn);
 

@@ -53,6 +53,9 @@ COLOR_YUV2GRAY_UYVY, COLOR_YUV2GRAY_YUY2 = 123, 124
 COLOR_RGB2YUV_I420, COLOR_BGR2YUV_I420, COLOR_RGBA2YUV_I420, COLOR_BGRA2YUV_I420 = 127, 128, 129, 130
 COLOR_RGB2YUV_IYUV, COLOR_BGR2YUV_IYUV, COLOR_RGBA2YUV_IYUV, COLOR_BGRA2YUV_IYUV = 127, 128, 129, 130
 COLOR_RGB2YUV_YV12, COLOR_BGR2YUV_YV12, COLOR_RGBA2YUV_YV12, COLOR_BGRA2YUV_YV12 = 131, 132, 133, 134
+COLOR_RGB2YUV_UYVY, COLOR_BGR2YUV_UYVY, COLOR_RGBA2YUV_UYVY, COLOR_BGRA2YUV_UYVY = 143, 144, 145, 146
+COLOR_RGB2YUV_YUY2, COLOR_BGR2YUV_YUY2, COLOR_RGB2YUV_YVYU, COLOR_BGR2YUV_YVYU = 147, 148, 149, 150
+COLOR_RGBA2YUV_YUY2, COLOR_BGRA2YUV_YUY2, COLOR_RGBA2YUV_YVYU, COLOR_BGRA2YUV_YVYU = 151, 152, 153, 154
 
 OK, NOT_IMPLEMENTED = 0, 1
 
@@ -280,6 +283,8 @@ def _cvt_dst_geometry(code, cols, rows, dstCn=0):
         return cols, rows, 1
     if 127 <= code <= 134:
         return cols, rows * 3 // 2, 1
+    if 143 <= code <= 154:
+        return cols, rows, 2
     return cols, rows, (dstCn if dstCn > 0 else _CVT_DCN.get(code, 3))
 
 

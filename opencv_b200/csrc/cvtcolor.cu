@@ -277,7 +277,7 @@ extern "C" int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int 
 {
     int rc;
     if ((rc = check_mat(src, "src")) || (rc = check_mat(dst, "dst"))) return rc;
-    if (code >= 90 && code <= 134) {      // subsampled-YUV wire formats: source and destination sizes differ (cvtcolor_yuv.cu)
+    if ((code >= 90 && code <= 134) || (code >= 143 && code <= 154)) {      // subsampled-YUV wire formats: source and destination sizes differ (cvtcolor_yuv.cu)
         B200_REQUIRE((src->frames > 1 ? src->frames : 1) == (dst->frames > 1 ? dst->frames : 1), "src/dst batch mismatch");
         if (B200CV_DEPTH(src->type) != B200CV_8U || B200CV_DEPTH(dst->type) != B200CV_8U) return B200CV_NOT_IMPLEMENTED;
         B200_REQUIRE(src->data != dst->data, "cvtColor: in-place is not supported");

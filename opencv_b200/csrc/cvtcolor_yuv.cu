@@ -5,6 +5,7 @@
 //   4:2:0 -> GRAY (the Y plane)                                    code 106       (color.cpp:337)
 //   4:2:2 UYVY / YUY2 / YVYU -> RGB / BGR / RGBA / BGRA, -> GRAY   codes 107-124  (:1733-1858, color.cpp:346-380)
 //   RGB / BGR / RGBA / BGRA -> IYUV (I420) / YV12                  codes 127-134  (:1473-1730)
+//   RGB / BGR / RGBA / BGRA -> UYVY / YUY2 / YVYU                  codes 143-154  (:1862-1958)
 //
 // BT.601 limited range in 20-bit fixed point, all integer, bit-exact (the reference's SIMD bodies and scalar tails agree):
 //   ruv = 2^19 + 1673527 (v-128);  guv = 2^19 - 852492 (v-128) - 409993 (u-128);  buv = 2^19 + 2116026 (u-128)
@@ -58,7 +59,7 @@ __device__ __forceinline__ void load_bytes(const uchar* p, int n, uchar (&o)[N])
 template <int N>
 __device__ __forceinline__ void store_bytes(uchar* p, int n, const uchar (&o)[N])
 {
-    static_assert(N == 4 || N == 8 || N == 24 || N == 32, "store_bytes");
+    static_assert(N == 4 || N == 8 || N == 16 || N == 24 || N == 32, "store_bytes");
     if (n == N && aligned_to(p, N % 8 == 0 ? 8 : 4)) {
         if constexpr (N % 8 == 0) {
 #pragma unroll
@@ -214,6 +215,36 @@ __global__ void __launch_bounds__(256) bgr_to_yuv420_kernel(Img src, Img dst, in
     store_bytes<4>(dst.row<uchar>(f, H + kv / 2) + (kv & 1) * (W / 2) + x0 / 2, n / 2, vo);
 }
 
+// ---- BGR family -> 4:2:2 (color_yuv.simd.hpp:1862-1958; 14-bit fixed point; U, V from the SUM of the two pixels with halved coefficients) ----
+// fmt 0 = YUY2 (Y0 U Y1 V), 1 = YVYU (Y0 V Y1 U), 2 = UYVY (U Y0 V Y1)
+template <int SCN>
+__global__ void __launch_bounds__(256) bgr_to_yuv422_kernel(Img src, Img dst, int W, int H, int bidx, int fmt)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int f = blockIdx.z;
+    if (x0 >= W || y >= H) return;
+    const int n = min(8, W - x0);
+    uchar a[8 * SCN], o[16];
+    load_bytes<8 * SCN>(src.row<uchar>(f, y) + x0 * SCN, n * SCN, a);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uchar* p = a + 2 * i * SCN;
+        const int b1 = bidx ? p[2] : p[0], g1 = p[1], r1 = bidx ? p[0] : p[2];
+        const int b2 = bidx ? p[SCN + 2] : p[SCN], g2 = p[SCN + 1], r2 = bidx ? p[SCN] : p[SCN + 2];
+        const uchar ya = sat_u8(((1 << 13) + r1 * 4211 + g1 * 8258 + b1 * 1606 + (1 << 14) * 16) >> 14);
+        const uchar yb = sat_u8(((1 << 13) + r2 * 4211 + g2 * 8258 + b2 * 1606 + (1 << 14) * 16) >> 14);
+        const int sr = r1 + r2, sg = g1 + g2, sb = b1 + b2;
+        const uchar u = sat_u8(((1 << 13) + sr * -1212 + sg * -2384 + sb * 3596 + (1 << 13) * 256) >> 14);
+        const uchar v = sat_u8(((1 << 13) + sr * 3596 + sg * -3015 + sb * -582 + (1 << 13) * 256) >> 14);
+        o[4 * i] = fmt == 2 ? u : ya;
+        o[4 * i + 1] = fmt == 2 ? ya : fmt == 1 ? v : u;
+        o[4 * i + 2] = fmt == 2 ? v : yb;
+        o[4 * i + 3] = fmt == 2 ? yb : fmt == 1 ? u : v;
+    }
+    store_bytes<16>(dst.row<uchar>(f, y) + x0 * 2, n * 2, o);
+}
+
 static dim3 yuv_grid(int W, int rows, int frames, dim3 block)
 {
     return dim3(div_up(div_up((unsigned)W, 8), block.x), div_up((unsigned)rows, block.y), (unsigned)frames);
@@ -293,6 +324,19 @@ int cvt_color_yuv(const b200cvMat* src, const b200cvMat* dst, int code, cudaStre
         if (grid.y >= 65536) return B200CV_NOT_IMPLEMENTED;
         if (scn == 3) bgr_to_yuv420_kernel<3><<<grid, block, 0, st>>>(s, d, W, H, bidx, yv12);
         else bgr_to_yuv420_kernel<4><<<grid, block, 0, st>>>(s, d, W, H, bidx, yv12);
+        B200_LAUNCH_CHECK();
+        return B200CV_OK;
+    }
+    if (code >= 143 && code <= 154) {
+        const int W = src->cols, H = src->rows;
+        B200_REQUIRE((scn == 3 || scn == 4) && dcn == 2 && dst->cols == W && dst->rows == H && (W & 1) == 0 && W > 0 && H > 0,
+                     "BGR -> 4:2:2 needs a 3-/4-channel source of even width and an 8UC2 destination of the same size");
+        const bool uyvy = code <= 146, yvyu = code == 149 || code == 150 || code == 153 || code == 154;
+        const int bidx = (code & 1) ? 2 : 0;                           // odd codes are the RGB(A) ones; the channel count is the source's
+        const dim3 grid = yuv_grid(W, H, s.frames, block);
+        if (grid.y >= 65536) return B200CV_NOT_IMPLEMENTED;
+        if (scn == 3) bgr_to_yuv422_kernel<3><<<grid, block, 0, st>>>(s, d, W, H, bidx, uyvy ? 2 : yvyu ? 1 : 0);
+        else bgr_to_yuv422_kernel<4><<<grid, block, 0, st>>>(s, d, W, H, bidx, uyvy ? 2 : yvyu ? 1 : 0);
         B200_LAUNCH_CHECK();
         return B200CV_OK;
     }

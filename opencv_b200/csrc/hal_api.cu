@@ -350,6 +350,14 @@ extern "C" int b200cv_hal_cvtOnePlaneYUVtoBGR(const uchar* src, size_t sstep, uc
     return cvt_yuv(src, sstep, w, h, 2, dst, dstep, w, h, dcn, base + (swapBlue ? 0 : 1));
 }
 
+extern "C" int b200cv_hal_cvtOnePlaneBGRtoYUV(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int scn, bool swapBlue, int uIdx, int ycn)
+{
+    if ((scn != 3 && scn != 4) || (uIdx != 0 && uIdx != 1) || (ycn != 0 && ycn != 1) || (ycn == 1 && uIdx == 1)) return B200CV_NOT_IMPLEMENTED;
+    // UYVY: 143 RGB 144 BGR 145 RGBA 146 BGRA; YUY2: 147 148 151 152; YVYU: 149 150 153 154
+    const int base = ycn == 1 ? (scn == 3 ? 143 : 145) : (scn == 3 ? 147 : 151) + (uIdx == 1 ? 2 : 0);
+    return cvt_yuv(src, sstep, w, h, scn, dst, dstep, w, h, 2, base + (swapBlue ? 0 : 1));
+}
+
 extern "C" int b200cv_hal_cvtBGRtoBGR(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, int dcn, bool swapBlue)
 {
     int code = scn == 3 ? (dcn == 4 ? (swapBlue ? 2 : 0) : (swapBlue ? 4 : -1)) : (dcn == 3 ? (swapBlue ? 3 : 1) : (swapBlue ? 5 : -1));

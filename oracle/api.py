@@ -52,6 +52,8 @@ def yuv_dst_shape(sw, sh, code):
         return sw, sh, 1
     if 127 <= code <= 134:
         return sw, sh * 3 // 2, 1
+    if 143 <= code <= 154:
+        return sw, sh, 2
     raise ValueError("not a subsampled-YUV code: %d" % code)
 
 

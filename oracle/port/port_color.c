@@ -195,6 +195,23 @@ PORT_API int port_cvt_color_yuv(const void* src_, size_t sstep, int sw, int sh, 
             }
         return 0;
     }
+    if (code >= 143 && code <= 154) {                        /* BGR family -> 4:2:2 UYVY / YUY2 / YVYU (color_yuv.simd.hpp:1862-1958, 14-bit fixed point) */
+        if (dcn != 2 || sw != dw || sh != dh || (sw & 1) || (scn != 3 && scn != 4)) return -1;
+        const int uyvy = code <= 146, yvyu = code == 149 || code == 150 || code == 153 || code == 154;
+        const int rgb = (code & 1), ycn = uyvy ? 1 : 0;      /* odd codes are the RGB(A) ones */
+        const int uoff = 1 - ycn + yvyu * 2, voff = (2 + uoff) % 4, bidx = rgb ? 2 : 0;
+        for (int y = 0; y < sh; y++)
+            for (int x = 0; x < sw; x += 2) {
+                const uchar* p = src + (size_t)y * sstep + x * scn; uchar* q = dst + (size_t)y * dstep + x * 2;
+                int r1 = p[2 - bidx], g1 = p[1], b1 = p[bidx], r2 = p[scn + 2 - bidx], g2 = p[scn + 1], b2 = p[scn + bidx];
+                q[ycn] = port_sat_u8i(((1 << 13) + r1 * 4211 + g1 * 8258 + b1 * 1606 + (1 << 14) * 16) >> 14);
+                q[ycn + 2] = port_sat_u8i(((1 << 13) + r2 * 4211 + g2 * 8258 + b2 * 1606 + (1 << 14) * 16) >> 14);
+                int sr = r1 + r2, sg = g1 + g2, sb = b1 + b2;
+                q[uoff] = port_sat_u8i(((1 << 13) + sr * -1212 + sg * -2384 + sb * 3596 + (1 << 13) * 256) >> 14);
+                q[voff] = port_sat_u8i(((1 << 13) + sr * 3596 + sg * -3015 + sb * -582 + (1 << 13) * 256) >> 14);
+            }
+        return 0;
+    }
     if (code >= 127 && code <= 134) {                        /* BGR family -> IYUV / YV12 */
         if (dcn != 1 || sw != dw || dh != sh * 3 / 2 || (sw & 1) || (sh & 1) || (scn != 3 && scn != 4)) return -1;
         const int c = (code - 127) & 3, rgb = !(c & 1), yv12 = code >= 131;   /* the channel count is the source's, whatever the code says (the reference's own KAT feeds 3 channels to the RGBA codes) */

@@ -29,6 +29,7 @@ KAT_YUV = {90: 0x46a1bb76, 91: 0x3843bb76, 92: 0xf3fdf2ea, 93: 0x6e84f2ea, 94: 0
 CODES_420 = list(range(90, 107))
 CODES_422 = [107, 108, 111, 112, 115, 116, 117, 118, 119, 120, 121, 122, 123, 124]
 CODES_TO_420 = list(range(127, 135))
+CODES_TO_422 = list(range(143, 155))
 
 
 def kat_input(code):
@@ -54,6 +55,10 @@ def test_yuv_vs_oracle(cvb, oracle, rng, size):
     for code in CODES_TO_420:
         img = rng.integers(0, 256, (h, w, 4 if (code - 127) & 2 else 3), dtype=np.uint8)
         assert_exact(cpu(cvb.cvtColor(gpu(img), code)), oracle.cvtColorYUV(img, code), "to 4:2:0 code %d %dx%d" % (code, w, h))
+    for code in CODES_TO_422:
+        for scn in (3, 4):
+            img = rng.integers(0, 256, (h, w, scn), dtype=np.uint8)
+            assert_exact(cpu(cvb.cvtColor(gpu(img), code)), oracle.cvtColorYUV(img, code), "to 4:2:2 code %d scn %d %dx%d" % (code, scn, w, h))
 
 
 def test_yuv_padded_rows_and_batches(cvb, oracle, rng):
@@ -118,6 +123,6 @@ def test_yuv_host_and_hal_paths(cvb, oracle, rng):
     y2 = rng.integers(0, 256, (480, 640, 2), dtype=np.uint8)
     bgr = rng.integers(0, 256, (480, 640, 3), dtype=np.uint8)
     n0 = cvb.launch_count()
-    for src, code in ((nv, 91), (nv, 96), (nv, 99), (nv, 104), (y2, 108), (y2, 117), (y2, 120), (bgr, 128), (bgr, 131)):
+    for src, code in ((nv, 91), (nv, 96), (nv, 99), (nv, 104), (y2, 108), (y2, 117), (y2, 120), (bgr, 128), (bgr, 131), (bgr, 144), (bgr, 147), (bgr, 150)):
         assert_exact(rh.cvtColorYUV(src, code), ref.cvtColorYUV(src, code), "cv::cvtColor code %d via HAL" % code)
-    assert cvb.launch_count() - n0 >= 9, "cv::cvtColor(YUV wire formats) did not reach the B200 HAL"
+    assert cvb.launch_count() - n0 >= 12, "cv::cvtColor(YUV wire formats) did not reach the B200 HAL"

@@ -132,6 +132,19 @@ def test_emulated_yuv_kernels_vs_port(yuv_emu, port, rng):
             assert np.array_equal(yuv_emu(img, code), port.cvtColorYUV(img, code)), "to 4:2:0 code %d %dx%d" % (code, w, h)
 
 
+def test_emulated_bgr_to_yuv422_vs_port(yuv_emu, port, rng):
+    for (h, w) in [(2, 2), (5, 6), (18, 34), (37, 130), (250, 322)]:
+        for code in range(143, 155):
+            for scn in (3, 4):
+                img = rng.integers(0, 256, (h, w, scn), dtype=np.uint8)
+                assert np.array_equal(yuv_emu(img, code), port.cvtColorYUV(img, code)), "to 4:2:2 code %d scn %d %dx%d" % (code, scn, w, h)
+    # round trip through the emulated kernels: BGR -> YUY2 -> BGR stays within the 4:2:2 quantisation on a smooth image
+    yy, xx = np.mgrid[0:64, 0:96]
+    img = np.stack([(xx * 2) % 256, (yy * 3) % 256, (xx + yy) % 256], axis=-1).astype(np.uint8)
+    back = yuv_emu(yuv_emu(img, 148), 116).astype(np.int32)
+    assert np.percentile(np.abs(back - img.astype(np.int32)), 90) <= 8
+
+
 def test_emulated_yuv_kernels_unaligned_pitches_and_batches(yuv_emu, port, rng):
     """odd base offsets / pitches force the byte paths; padded destinations must keep their padding; batches walk frame_step"""
     h, w = 34, 90

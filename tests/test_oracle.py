@@ -117,6 +117,10 @@ def test_port_vs_reference_yuv_wire_formats(ref, port, rng):
         for code in range(127, 135):
             img = rng.integers(0, 256, (h, w, 4 if (code - 127) & 2 else 3), dtype=np.uint8)
             assert np.array_equal(ref.cvtColorYUV(img, code), port.cvtColorYUV(img, code)), "to 4:2:0 code %d %dx%d" % (code, w, h)
+        for code in range(143, 155):                  # BGR family -> UYVY / YUY2 / YVYU; the channel count is the source's, whatever the code says
+            for scn in (3, 4):
+                img = rng.integers(0, 256, (h, w, scn), dtype=np.uint8)
+                assert np.array_equal(ref.cvtColorYUV(img, code), port.cvtColorYUV(img, code)), "to 4:2:2 code %d scn %d %dx%d" % (code, scn, w, h)
 
 
 def test_port_vs_reference_two_plane(ref, port, rng):
