@@ -290,6 +290,10 @@ extern "C" int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int 
     Img s = make_img(src), d = make_img(dst);
     cudaStream_t st = as_stream(stream);
 
+    if ((code >= 46 && code <= 49) || (code >= 139 && code <= 142)) {     // Bayer mosaics, bilinear (demosaic.cu)
+        B200_REQUIRE(src->data != dst->data, "cvtColor: in-place is not supported");
+        return demosaic_bilinear(src, dst, code, st);
+    }
 #define NEED(sc_ok, dc_ok) B200_REQUIRE((sc_ok) && (dc_ok), "channel count does not match the colour code")
     switch (code) {
     case 0: case 1: case 2: case 3: case 4: case 5: {   // BGR2BGRA BGRA2BGR BGR2RGBA RGBA2BGR BGR2RGB BGRA2RGBA

@@ -54,6 +54,8 @@ def yuv_dst_shape(sw, sh, code):
         return sw, sh * 3 // 2, 1
     if 143 <= code <= 154:
         return sw, sh, 2
+    if 46 <= code <= 49 or 139 <= code <= 142:
+        return sw, sh, (4 if code >= 139 else 3)
     raise ValueError("not a subsampled-YUV code: %d" % code)
 
 

@@ -195,6 +195,36 @@ PORT_API int port_cvt_color_yuv(const void* src_, size_t sstep, int sw, int sh, 
             }
         return 0;
     }
+    if ((code >= 46 && code <= 49) || (code >= 139 && code <= 142)) {
+        /* Bayer mosaic -> BGR / BGRA, bilinear (demosaicing.cpp:806-1056): interior rows / columns as the reference walks them (the
+         * non-green sites of a row carry `blue`-side colour, rows alternate), then first / last columns and rows copied from inside */
+        const int four = code >= 139, c = four ? code - 139 : code - 46;
+        if (scn != 1 || dcn != (four ? 4 : 3) || sw != dw || sh != dh || sw < 3 || sh < 3) return -1;
+        int blue = c < 2 ? -1 : 1, swg = c & 1;
+        for (int i = 0; i < sh - 2; i++, blue = -blue, swg = !swg) {
+            const uchar* b0 = src + (size_t)i * sstep; const uchar* b1 = b0 + sstep; const uchar* b2 = b1 + sstep;
+            uchar* drow = dst + (size_t)(i + 1) * dstep;
+            for (int k = 0; k < sw - 2; k++) {
+                uchar* d = drow + (k + 1) * dcn + 1;                    /* the green channel of interior pixel k */
+                int green = ((k & 1) == 0) == (swg != 0);
+                if (green) {
+                    d[-blue] = (uchar)((b0[k + 1] + b2[k + 1] + 1) >> 1);
+                    d[0] = b1[k + 1];
+                    d[blue] = (uchar)((b1[k] + b1[k + 2] + 1) >> 1);
+                } else {
+                    d[-blue] = (uchar)((b0[k] + b0[k + 2] + b2[k] + b2[k + 2] + 2) >> 2);
+                    d[0] = (uchar)((b0[k + 1] + b1[k] + b1[k + 2] + b2[k + 1] + 2) >> 2);
+                    d[blue] = b1[k + 1];
+                }
+                if (dcn == 4) d[2] = 255;
+            }
+            memcpy(drow, drow + dcn, dcn);
+            memcpy(drow + (sw - 1) * dcn, drow + (sw - 2) * dcn, dcn);
+        }
+        memcpy(dst, dst + dstep, (size_t)sw * dcn);
+        memcpy(dst + (size_t)(sh - 1) * dstep, dst + (size_t)(sh - 2) * dstep, (size_t)sw * dcn);
+        return 0;
+    }
     if (code >= 143 && code <= 154) {                        /* BGR family -> 4:2:2 UYVY / YUY2 / YVYU (color_yuv.simd.hpp:1862-1958, 14-bit fixed point) */
         if (dcn != 2 || sw != dw || sh != dh || (sw & 1) || (scn != 3 && scn != 4)) return -1;
         const int uyvy = code <= 146, yvyu = code == 149 || code == 150 || code == 153 || code == 154;

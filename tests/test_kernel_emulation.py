@@ -266,3 +266,31 @@ def test_emulated_lanczos4_resize_vs_port(lanczos_emu, port, rng):
             shape = (sh, sw) if cn == 1 else (sh, sw, cn)
             for img in (rng.integers(0, 256, shape, dtype=np.uint8), (rng.random(shape, dtype=np.float32) * 255).astype(np.float32)):
                 assert np.array_equal(lanczos_emu(img, (dw, dh)), port.resize(img, (dw, dh), 4)), "LANCZOS4 %s %s -> %s cn=%d" % (img.dtype, (sh, sw), (dh, dw), cn)
+
+
+# ---- Bayer mosaics, bilinear (demosaic.cu) --------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def bayer_emu():
+    lib = build_emulation("demosaic.cu", "int emu_demosaic(const b200cvMat* s, const b200cvMat* d, int code)",
+                          "    return b200cv::demosaic_bilinear(s, d, code, nullptr);")
+    lib.emu_demosaic.argtypes = [ctypes.POINTER(Mat), ctypes.POINTER(Mat), ctypes.c_int]
+
+    def run(src, code):
+        dcn = 4 if code >= 139 else 3
+        dst = np.full(src.shape[:-1] + (dcn,) if src.ndim == 4 else src.shape + (dcn,), 0xCD, np.uint8)
+        ms, md = mat_of(src), mat_of(dst)
+        rc = lib.emu_demosaic(ctypes.byref(ms), ctypes.byref(md), int(code))
+        assert rc == 0, "emulated demosaic_bilinear(code %d) returned %d" % (code, rc)
+        return dst
+    return run
+
+
+def test_emulated_bayer_demosaic_vs_port(bayer_emu, port, rng):
+    for (h, w) in [(3, 3), (4, 5), (5, 4), (17, 33), (18, 34), (64, 96), (241, 323)]:
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        for code in (46, 47, 48, 49, 139, 140, 141, 142):
+            assert np.array_equal(bayer_emu(img, code), port.cvtColorYUV(img, code)), "Bayer code %d %dx%d" % (code, w, h)
+    batch = rng.integers(0, 256, (3, 20, 26, 1), dtype=np.uint8)
+    out = bayer_emu(batch, 48)
+    for f in range(3):
+        assert np.array_equal(out[f], port.cvtColorYUV(batch[f, :, :, 0], 48)), "Bayer batch frame %d" % f

@@ -123,6 +123,14 @@ def test_port_vs_reference_yuv_wire_formats(ref, port, rng):
                 assert np.array_equal(ref.cvtColorYUV(img, code), port.cvtColorYUV(img, code)), "to 4:2:2 code %d scn %d %dx%d" % (code, scn, w, h)
 
 
+def test_port_vs_reference_bayer_demosaic(ref, port, rng):
+    """Bayer BG / GB / RG / GR -> BGR and BGRA, bilinear (demosaicing.cpp:806-1056), including the copied border columns / rows"""
+    for (h, w) in [(3, 3), (4, 5), (5, 4), (17, 33), (18, 34), (64, 96), (241, 323), (480, 640)]:
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        for code in (46, 47, 48, 49, 139, 140, 141, 142):
+            assert np.array_equal(ref.cvtColorYUV(img, code), port.cvtColorYUV(img, code)), "Bayer code %d %dx%d" % (code, w, h)
+
+
 def test_port_vs_reference_two_plane(ref, port, rng):
     """cv::cvtColorTwoPlane: the same arithmetic with separate luma / chroma buffers; also equal to cvtColor on the concatenated planes"""
     for (h, w) in [(4, 6), (18, 34), (250, 322)]:
