@@ -49,6 +49,8 @@
 #define cv_hal_cvtOnePlaneYUVtoBGR b200cv_hal_cvtOnePlaneYUVtoBGR
 #undef cv_hal_cvtOnePlaneBGRtoYUV
 #define cv_hal_cvtOnePlaneBGRtoYUV b200cv_hal_cvtOnePlaneBGRtoYUV
+#undef cv_hal_integral
+#define cv_hal_integral b200cv_hal_integral
 #undef cv_hal_boxFilter
 #define cv_hal_boxFilter b200cv_hal_boxFilter
 #undef cv_hal_cvtBGRtoBGR

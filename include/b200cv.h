@@ -60,7 +60,9 @@ extern "C" {
 #define B200CV_8U 0
 #define B200CV_16U 2
 #define B200CV_16S 3
+#define B200CV_32S 4
 #define B200CV_32F 5
+#define B200CV_64F 6
 #define B200CV_MAKETYPE(depth, cn) (((depth) & 7) + (((cn) - 1) << 3))
 #define B200CV_DEPTH(type) ((type) & 7)
 #define B200CV_CN(type) ((((type) >> 3) & 511) + 1)
@@ -161,6 +163,9 @@ B200CV_API int b200cv_sobel(const b200cvMat* src, const b200cvMat* dst, int dx, 
  * 8U->8U, 8U->32F, 32F->32F; anchor (-1,-1) = centre; borders CONSTANT (zeros), REPLICATE, REFLECT, REFLECT_101; ksize <= 128x128. */
 B200CV_API int b200cv_box_filter(const b200cvMat* src, const b200cvMat* dst, int ksize_w, int ksize_h, int anchor_x, int anchor_y,
                                  int normalize, int border, void* stream);
+/* replaces cv::integral (imgproc.hpp; sumpixels.dispatch.cpp:415-451) for 8UC1 sources: sum is 32SC1 of (W+1) x (H+1); sqsum is NULL or
+ * 64FC1 of the same size.  Tilted sums and other depth combinations: B200CV_NOT_IMPLEMENTED. */
+B200CV_API int b200cv_integral(const b200cvMat* src, const b200cvMat* sum, const b200cvMat* sqsum, void* stream);
 /* replaces cv::resize (imgproc.hpp:2422; resize.cpp:4201-4246).  Scale factors are dst/src sizes (fx=fy=0 form). */
 B200CV_API int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int interpolation, void* stream);
 /* replaces cv::warpAffine (imgproc.hpp:2450; imgwarp.cpp:2788-2902). M: 2x3 doubles; inverted unless WARP_INVERSE_MAP. */

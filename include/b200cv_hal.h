@@ -60,6 +60,9 @@ B200CV_API int b200cv_hal_scharr(const b200cv_uchar* src_data, size_t src_step, 
 B200CV_API int b200cv_hal_boxFilter(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                     int src_depth, int dst_depth, int cn, int margin_left, int margin_top, int margin_right, int margin_bottom,
                                     size_t ksize_width, size_t ksize_height, int anchor_x, int anchor_y, bool normalize, int border_type);
+/* hal_ni_integral, hal_replacement.hpp:977 (cv::integral, sumpixels.dispatch.cpp:375): 8UC1 -> 32S sum (+ 64F sqsum); no tilted sums */
+B200CV_API int b200cv_hal_integral(int depth, int sdepth, int sqdepth, const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* sum_data, size_t sum_step,
+                                   b200cv_uchar* sqsum_data, size_t sqsum_step, b200cv_uchar* tilted_data, size_t tilted_step, int width, int height, int cn);
 /* hal_ni_resize, hal_replacement.hpp:257 */
 B200CV_API int b200cv_hal_resize(int src_type, const b200cv_uchar* src_data, size_t src_step, int src_width, int src_height, b200cv_uchar* dst_data,
                                  size_t dst_step, int dst_width, int dst_height, double inv_scale_x, double inv_scale_y, int interpolation);
@@ -114,6 +117,7 @@ B200CV_API int b200cv_host_filter2d(const b200cvMat* src, const b200cvMat* dst, 
                                     double delta, int border);
 B200CV_API int b200cv_host_sobel(const b200cvMat* src, const b200cvMat* dst, int dx, int dy, int ksize, double scale, double delta, int border);
 B200CV_API int b200cv_host_box_filter(const b200cvMat* src, const b200cvMat* dst, int ksize_w, int ksize_h, int anchor_x, int anchor_y, int normalize, int border);
+B200CV_API int b200cv_host_integral(const b200cvMat* src, const b200cvMat* sum, const b200cvMat* sqsum);
 B200CV_API int b200cv_host_resize(const b200cvMat* src, const b200cvMat* dst, int interpolation);
 B200CV_API int b200cv_host_warp_affine(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags, int border, const double* border_value);
 B200CV_API int b200cv_host_warp_perspective(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags, int border, const double* border_value);

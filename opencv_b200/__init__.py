@@ -114,9 +114,10 @@ def launch_count():
     return int(lib().b200cv_launch_count())
 
 
-_DEPTH_OF = {"torch.uint8": CV_8U, "torch.int16": CV_16S, "torch.float32": CV_32F,
-             "uint8": CV_8U, "int16": CV_16S, "float32": CV_32F}
-_ESZ = {CV_8U: 1, CV_16S: 2, CV_32F: 4}
+CV_32S, CV_64F = 4, 6
+_DEPTH_OF = {"torch.uint8": CV_8U, "torch.int16": CV_16S, "torch.float32": CV_32F, "torch.int32": CV_32S, "torch.float64": CV_64F,
+             "uint8": CV_8U, "int16": CV_16S, "float32": CV_32F, "int32": CV_32S, "float64": CV_64F}
+_ESZ = {CV_8U: 1, CV_16S: 2, CV_32F: 4, CV_32S: 4, CV_64F: 8}
 
 
 def make_type(depth, cn):
@@ -315,6 +316,22 @@ def cvtColorTwoPlane(src1, src2, code, dst=None, stream=None):
     my, muv, md = describe(src1), describe(src2), describe(dst)
     _check(lib().b200cv_cvt_color_two_plane(ctypes.byref(my), ctypes.byref(muv), ctypes.byref(md), int(code), _stream_ptr(stream)), "cvtColorTwoPlane")
     return dst
+
+
+def integral(src, with_sqsum=False, stream=None):
+    """cv::integral for 8UC1 frames: the (H+1) x (W+1) int32 sum, and with with_sqsum=True also the float64 sum of squares.
+    (H,W) or (N,H,W,1) torch CUDA tensors; numpy arrays take the host path."""
+    if not _is_torch(src):
+        from . import hal
+        return hal.integral(src, with_sqsum)
+    import torch
+    m = describe(src)
+    s = _new(src, dtype=torch.int32, channels=1, size=(m.cols + 1, m.rows + 1))
+    q = _new(src, dtype=torch.float64, channels=1, size=(m.cols + 1, m.rows + 1)) if with_sqsum else None
+    ms, md = describe(src), describe(s)
+    mq = describe(q) if with_sqsum else None
+    _check(lib().b200cv_integral(ctypes.byref(ms), ctypes.byref(md), ctypes.byref(mq) if with_sqsum else None, _stream_ptr(stream)), "integral")
+    return (s, q) if with_sqsum else s
 
 
 def getGaussianKernel(ksize, sigma):

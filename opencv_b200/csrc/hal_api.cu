@@ -251,6 +251,36 @@ extern "C" int b200cv_hal_boxFilter(const uchar* src, size_t sstep, uchar* dst, 
     return b200cv_host_box_filter(&s, &d, (int)kw, (int)kh, ax, ay, normalize ? 1 : 0, border);
 }
 
+// cv::integral has two outputs: sum through the pipeline; sqsum (rare) as a second pass over the same source
+extern "C" int b200cv_host_integral(const b200cvMat* s, const b200cvMat* sum, const b200cvMat* sqsum)
+{
+    int rc = host_pipeline(s, sum, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_integral(a, b, nullptr, st); });
+    if (rc || !sqsum || !sqsum->data) return rc;
+    if (sqsum->type != B200CV_MAKETYPE(B200CV_64F, 1)) return B200CV_NOT_IMPLEMENTED;
+    // the device entry wants both outputs: give it a scratch sum next to the squares (stream-ordered, freed right after)
+    return host_pipeline(s, sqsum, [=](const b200cvMat* a, const b200cvMat* b, void* st) {
+        b200cvMat tmp = *b;
+        tmp.type = B200CV_MAKETYPE(B200CV_32S, 1);
+        tmp.step = (size_t)b->cols * 4; tmp.frame_step = tmp.step * b->rows;
+        void* p = nullptr;
+        const int frames = b->frames > 1 ? b->frames : 1;
+        if (cudaMallocAsync(&p, tmp.frame_step * frames, (cudaStream_t)st) != cudaSuccess) { cudaGetLastError(); return (int)B200CV_ERR_CUDA; }
+        tmp.data = p;
+        const int r = b200cv_integral(a, &tmp, b, st);
+        cudaFreeAsync(p, (cudaStream_t)st);
+        return r;
+    });
+}
+
+extern "C" int b200cv_hal_integral(int depth, int sdepth, int sqdepth, const uchar* src, size_t sstep, uchar* sum, size_t sumstep, uchar* sqsum, size_t sqstep,
+                                   uchar* tilted, size_t, int w, int h, int cn)
+{
+    if (depth != B200CV_8U || sdepth != B200CV_32S || cn != 1 || tilted || !sum || (sqsum && sqdepth != B200CV_64F)) return B200CV_NOT_IMPLEMENTED;
+    b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(B200CV_8U, 1)), d = hmat(sum, sumstep, w + 1, h + 1, B200CV_MAKETYPE(B200CV_32S, 1));
+    b200cvMat q = hmat(sqsum, sqstep, w + 1, h + 1, B200CV_MAKETYPE(B200CV_64F, 1));
+    return b200cv_host_integral(&s, &d, sqsum ? &q : nullptr);
+}
+
 extern "C" int b200cv_hal_resize(int type, const uchar* src, size_t sstep, int sw, int sh, uchar* dst, size_t dstep, int dw, int dh,
                                  double inv_x, double inv_y, int interp)
 {

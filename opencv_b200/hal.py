@@ -11,7 +11,8 @@ import numpy as np
 
 from . import (BORDER_CONSTANT, BORDER_DEFAULT, INTER_LINEAR, CV_8U, CV_16S, CV_32F, Mat, _check, lib, make_type, _CVT_DCN, _cvt_dst_geometry)
 
-_DEPTH = {np.dtype(np.uint8): CV_8U, np.dtype(np.uint16): 2, np.dtype(np.int16): CV_16S, np.dtype(np.float32): CV_32F}
+_DEPTH = {np.dtype(np.uint8): CV_8U, np.dtype(np.uint16): 2, np.dtype(np.int16): CV_16S, np.dtype(np.float32): CV_32F,
+          np.dtype(np.int32): 4, np.dtype(np.float64): 6}
 _NP = {CV_8U: np.uint8, CV_16S: np.int16, CV_32F: np.float32}
 
 
@@ -155,6 +156,16 @@ def boxFilter(src, ddepth, ksize, anchor=(-1, -1), normalize=True, borderType=BO
 
 def blur(src, ksize, anchor=(-1, -1), borderType=BORDER_DEFAULT, dst=None):
     return boxFilter(src, -1, ksize, anchor, True, borderType, dst)
+
+
+def integral(src, with_sqsum=False):
+    m = describe(src)
+    s = _new(src, dtype=np.int32, channels=1, size=(m.cols + 1, m.rows + 1))
+    q = _new(src, dtype=np.float64, channels=1, size=(m.cols + 1, m.rows + 1)) if with_sqsum else None
+    ms, md = describe(src), describe(s)
+    mq = describe(q) if with_sqsum else None
+    _check(lib().b200cv_host_integral(ctypes.byref(ms), ctypes.byref(md), ctypes.byref(mq) if with_sqsum else None), "integral")
+    return (s, q) if with_sqsum else s
 
 
 def pyrDown(src, dst=None, borderType=BORDER_DEFAULT):

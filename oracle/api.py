@@ -244,6 +244,15 @@ class Oracle:
         self._ok(self.fn("cvt_color_two_plane")(_p(y), sz(y.strides[0]), _p(uv), sz(uv.strides[0]), w, h, _p(dst), sz(dst.strides[0]), dcn, int(code)), "cvtColorTwoPlane")
         return dst
 
+    def integral(self, src, with_sqsum=False):
+        src = np.ascontiguousarray(src)
+        h, w = src.shape
+        s = np.zeros((h + 1, w + 1), np.int32)
+        q = np.zeros((h + 1, w + 1), np.float64) if with_sqsum else None
+        self._ok(self.fn("integral")(_p(src), sz(src.strides[0]), w, h, _p(s), sz(s.strides[0]), _p(q) if with_sqsum else None,
+                                     sz(q.strides[0]) if with_sqsum else sz(0)), "integral")
+        return (s, q) if with_sqsum else s
+
     def matchTemplate(self, image, templ, method):
         image = np.ascontiguousarray(image)
         templ = np.ascontiguousarray(templ)

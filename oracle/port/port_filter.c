@@ -307,6 +307,26 @@ PORT_API int port_sobel(const void* src, size_t sstep, void* dst, size_t dstep, 
     return port_sep_filter_core(src, sstep, dst, dstep, w, h, stype, ddepth, kx, nx, ky, ny, -1, -1, delta, border);
 }
 
+/* cv::integral, 8UC1 -> 32S sum (+ 64F sum of squares): sumpixels.dispatch.cpp:192-263.  sum[y+1][x+1] = sum[y][x+1] + row prefix. */
+PORT_API int port_integral(const void* src, size_t sstep, int w, int h, int* sum, size_t sumstep, double* sqsum, size_t sqstep)
+{
+    memset(sum, 0, sizeof(int) * (size_t)(w + 1));
+    if (sqsum) memset(sqsum, 0, sizeof(double) * (size_t)(w + 1));
+    for (int y = 0; y < h; y++) {
+        const uchar* s = (const uchar*)src + (size_t)y * sstep;
+        const int* prev = (const int*)((const char*)sum + (size_t)y * sumstep); int* cur = (int*)((char*)sum + (size_t)(y + 1) * sumstep);
+        unsigned run = 0; double qrun = 0;
+        cur[0] = 0;
+        for (int x = 0; x < w; x++) { run += s[x]; cur[x + 1] = (int)((unsigned)prev[x + 1] + run); }
+        if (sqsum) {
+            const double* qp = (const double*)((const char*)sqsum + (size_t)y * sqstep); double* qc = (double*)((char*)sqsum + (size_t)(y + 1) * sqstep);
+            qc[0] = 0;
+            for (int x = 0; x < w; x++) { qrun += (double)s[x] * s[x]; qc[x + 1] = qp[x + 1] + qrun; }
+        }
+    }
+    return 0;
+}
+
 /* ---- cv::boxFilter / cv::blur (box_filter.dispatch.cpp:440-498; box_filter.simd.hpp) ------------------------------------------------
  * Sum type as createBoxFilter picks it (simd.hpp:1250-1272): 8U->8U with kw*kh <= 256 -> 16-bit sums and the integer divide of
  * ColumnSum<ushort,uchar> (simd.hpp:430-600: d = cvRound(1/scale), (s + divDelta) * divScale >> 23); other 8U sources -> int sums,

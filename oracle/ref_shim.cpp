@@ -241,6 +241,19 @@ API int ref_cvt_color_two_plane(const void* y, size_t ystep, const void* uv, siz
     GUARD_END
 }
 
+API int ref_integral(const void* src, size_t sstep, int w, int h, int* sum, size_t sumstep, double* sqsum, size_t sqstep)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, w, h, CV_8UC1), o = hdr(sum, sumstep, w + 1, h + 1, CV_32SC1);
+    if (sqsum) {
+        Mat q = hdr(sqsum, sqstep, w + 1, h + 1, CV_64FC1);
+        integral(s, o, q, CV_32S, CV_64F);
+        CV_Assert(q.data == (uchar*)sqsum);
+    } else integral(s, o, CV_32S);
+    CV_Assert(o.data == (uchar*)sum);
+    GUARD_END
+}
+
 API int ref_match_template(const void* img, size_t istep, int iw, int ih, const void* templ, size_t tstep, int tw, int th,
                            int type, float* result, size_t rstep, int method)
 {

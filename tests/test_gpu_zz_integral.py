@@ -1,0 +1,44 @@
+"""GPU parity: cv::integral, 8UC1 -> 32S sum (+ 64F sum of squares): BIT-EXACT (integers; the doubles hold integers below 2^53).
+
+STATUS: opencv_b200/csrc/integral.cu was written after this round's GPU budget was spent.  The port equals the reference (tests/test_oracle.py)
+and the six kernels, compiled for the host, equal the port (tests/test_kernel_emulation.py); the sm_100a build has NOT yet run on a B200: the
+tests are xfail(strict=False) until it has (XPASS on success).  The file sorts last on purpose."""
+import numpy as np
+import pytest
+
+import opencv_b200 as C
+from util import assert_exact, cpu, gpu
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="integral.cu has not run on a B200 yet (written after the round's GPU budget was spent)")]
+
+
+@pytest.mark.parametrize("size", [(1, 1), (5, 7), (17, 15), (33, 65), (240, 321), (1080, 1920), (2160, 3840)])
+def test_integral(cvb, oracle, rng, size):
+    img = rng.integers(0, 256, size, dtype=np.uint8)
+    ws, wq = oracle.integral(img, True)
+    gs, gq = cvb.integral(gpu(img), with_sqsum=True)
+    assert_exact(cpu(gs), ws, "integral sum %s" % (size,))
+    assert_exact(cpu(gq), wq, "integral sqsum %s" % (size,))
+    assert_exact(cpu(cvb.integral(gpu(img))), ws, "integral sum only %s" % (size,))
+
+
+def test_integral_batch_host_and_hal(cvb, oracle, rng):
+    batch = rng.integers(0, 256, (6, 480, 640, 1), dtype=np.uint8)
+    out = cpu(cvb.integral(gpu(batch)))
+    assert out.shape == (6, 481, 641, 1)
+    for f in (0, 5):
+        assert_exact(out[f, :, :, 0], oracle.integral(batch[f, :, :, 0]), "integral batch frame %d" % f)
+    from opencv_b200 import hal
+    img = batch[2, :, :, 0].copy()
+    hs, hq = hal.integral(img, True)
+    ws, wq = oracle.integral(img, True)
+    assert_exact(hs, ws, "host integral sum"); assert_exact(hq, wq, "host integral sqsum")
+    from oracle.api import Oracle, available
+    if available("ref_hal") and Oracle("ref_hal").has("integral"):
+        n0 = cvb.launch_count()
+        rs, rq = Oracle("ref_hal").integral(img, True)
+        assert_exact(rs, ws, "cv::integral via HAL"); assert_exact(rq, wq, "cv::integral sqsum via HAL")
+        assert cvb.launch_count() > n0, "cv::integral did not reach the B200 HAL"
+    # size-independent property: any box sum from four corners of the integral equals the direct sum
+    s = ws.astype(np.int64)
+    assert s[300, 400] - s[100, 400] - s[300, 200] + s[100, 200] == int(img[100:300, 200:400].sum(dtype=np.int64))

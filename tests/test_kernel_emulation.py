@@ -23,6 +23,7 @@ namespace b200cv {
 void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); }
 int cuda_fail(cudaError_t, const char*, const char*, int) { return -1; }
 void count_launch(int) {}
+int check_mat(const b200cvMat* m, const char*) { return m && m->data && m->cols > 0 && m->rows > 0 ? 0 : B200CV_ERR_BAD_ARG; }
 }
 """
 
@@ -294,3 +295,37 @@ def test_emulated_bayer_demosaic_vs_port(bayer_emu, port, rng):
     out = bayer_emu(batch, 48)
     for f in range(3):
         assert np.array_equal(out[f], port.cvtColorYUV(batch[f, :, :, 0], 48)), "Bayer batch frame %d" % f
+
+
+# ---- cv::integral (integral.cu): six map-only kernels ----------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def integral_emu():
+    lib = build_emulation("integral.cu", "int emu_integral(const b200cvMat* s, const b200cvMat* sum, const b200cvMat* sq)",
+                          "    return b200cv::integral_impl(s, sum, sq, nullptr);")
+    lib.emu_integral.argtypes = [ctypes.POINTER(Mat)] * 3
+
+    def run(src, with_sq):
+        lead = src.shape[:1] if src.ndim == 4 else ()
+        h, w = src.shape[-3:-1] if src.ndim == 4 else src.shape
+        tail = (1,) if src.ndim == 4 else ()
+        s = np.full(lead + (h + 1, w + 1) + tail, -7, np.int32)
+        q = np.full(lead + (h + 1, w + 1) + tail, -7.0, np.float64)
+        ms, md, mq = mat_of(src), mat_of(s), mat_of(q)
+        md.type = 4; mq.type = 6
+        rc = lib.emu_integral(ctypes.byref(ms), ctypes.byref(md), ctypes.byref(mq) if with_sq else None)
+        assert rc == 0, "emulated integral_impl returned %d" % rc
+        return (s, q) if with_sq else s
+    return run
+
+
+def test_emulated_integral_vs_port(integral_emu, port, rng):
+    for (h, w) in [(1, 1), (5, 7), (16, 16), (17, 15), (33, 65), (100, 257), (240, 321)]:
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        ws, wq = port.integral(img, True)
+        gs, gq = integral_emu(img, True)
+        assert np.array_equal(gs, ws) and np.array_equal(gq, wq), "integral %dx%d" % (w, h)
+        assert np.array_equal(integral_emu(img, False), ws)
+    batch = rng.integers(0, 256, (3, 40, 50, 1), dtype=np.uint8)
+    gs = integral_emu(batch, False)
+    for f in range(3):
+        assert np.array_equal(gs[f, :, :, 0], port.integral(batch[f, :, :, 0])), "integral batch frame %d" % f

@@ -131,6 +131,16 @@ def test_port_vs_reference_bayer_demosaic(ref, port, rng):
             assert np.array_equal(ref.cvtColorYUV(img, code), port.cvtColorYUV(img, code)), "Bayer code %d %dx%d" % (code, w, h)
 
 
+def test_port_vs_reference_integral(ref, port, rng):
+    """cv::integral 8UC1 -> 32S sum and 64F sum of squares"""
+    for (h, w) in [(1, 1), (5, 7), (33, 65), (240, 321), (1080, 1920)]:
+        img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        a, aq = ref.integral(img, True)
+        b, bq = port.integral(img, True)
+        assert np.array_equal(a, b) and np.array_equal(aq, bq), "integral %dx%d" % (w, h)
+        assert a[-1, -1] == int(img.sum(dtype=np.int64)) and aq[-1, -1] == float((img.astype(np.int64) ** 2).sum())
+
+
 def test_port_vs_reference_two_plane(ref, port, rng):
     """cv::cvtColorTwoPlane: the same arithmetic with separate luma / chroma buffers; also equal to cvtColor on the concatenated planes"""
     for (h, w) in [(4, 6), (18, 34), (250, 322)]:
