@@ -24,6 +24,11 @@ def nbytes(*ts):
     return sum(t.numel() * t.element_size() for t in ts)
 
 
+nv12 = torch.randint(0, 256, (4, 4320 * 3 // 2, 7680, 1), dtype=torch.uint8, device=dev)      # 4 x 8K NV12 / I420 frames
+yuy2 = torch.randint(0, 256, (4, 4320, 7680, 2), dtype=torch.uint8, device=dev)
+k5 = torch.empty((4, 2880, 5120, 3), dtype=torch.uint8, device=dev)
+k25 = torch.empty((4, 1440, 2560, 3), dtype=torch.uint8, device=dev)
+
 ops = {
     "blur_u8_k3": (lambda: cvb.blur(u8, (3, 3), dst=o8), nbytes(u8, o8)),
     "blur_u8_k5": (lambda: cvb.blur(u8, (5, 5), dst=o8), nbytes(u8, o8)),
@@ -33,6 +38,18 @@ ops = {
     "box_u8_f32_k7": (lambda: cvb.boxFilter(u8[:8], 5, (7, 7), dst=o32), nbytes(u8[:8], o32)),
     "pyrdown_u8c3_8k": (lambda: cvb.pyrDown(bgr), nbytes(bgr) * 5 // 4),
     "scharr_u8_s16": (lambda: cvb.Scharr(u8, 3, 1, 0), nbytes(u8) * 3),
+    # written after the round-1 GPU budget was spent: first numbers belong to round 2
+    "nv12_to_bgr_8k": (lambda: cvb.cvtColor(nv12, cvb.COLOR_YUV2BGR_NV12, dst=obgr), nbytes(nv12, obgr)),
+    "i420_to_bgr_8k": (lambda: cvb.cvtColor(nv12, cvb.COLOR_YUV2BGR_I420, dst=obgr), nbytes(nv12, obgr)),
+    "yuy2_to_bgr_8k": (lambda: cvb.cvtColor(yuy2, cvb.COLOR_YUV2BGR_YUY2, dst=obgr), nbytes(yuy2, obgr)),
+    "bgr_to_i420_8k": (lambda: cvb.cvtColor(bgr, cvb.COLOR_BGR2YUV_I420, dst=nv12), nbytes(bgr, nv12)),
+    "bayer_to_bgr_4k": (lambda: cvb.cvtColor(u8, cvb.COLOR_BayerRG2BGR), nbytes(u8) * 4),
+    "area_8k_to_5k": (lambda: cvb.resize(bgr, (5120, 2880), interpolation=cvb.INTER_AREA, dst=k5), nbytes(bgr, k5)),
+    "area_8k_div3": (lambda: cvb.resize(bgr, (2560, 1440), interpolation=cvb.INTER_AREA, dst=k25), nbytes(bgr, k25)),
+    "lanczos4_8k_to_5k": (lambda: cvb.resize(bgr, (5120, 2880), interpolation=cvb.INTER_LANCZOS4, dst=k5), nbytes(bgr, k5)),
+    "linear_exact_8k_to_5k": (lambda: cvb.resize(bgr, (5120, 2880), interpolation=cvb.INTER_LINEAR_EXACT, dst=k5), nbytes(bgr, k5)),
+    "nearest_exact_8k_to_5k": (lambda: cvb.resize(bgr, (5120, 2880), interpolation=cvb.INTER_NEAREST_EXACT, dst=k5), nbytes(bgr, k5)),
+    "integral_4k": (lambda: cvb.integral(u8), nbytes(u8) * 5),
 }
 for name, (fn, nb) in ops.items():
     if which and name not in which:
