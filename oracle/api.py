@@ -292,15 +292,39 @@ class Oracle:
         cnt = min(n.value, max_out)
         return pts[:cnt].copy(), q[:cnt].copy()
 
-    def sift_detect_and_compute(self, gray, nfeatures=0, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, max_kp=200000):
-        """the reference's cv::SIFT::detectAndCompute (real reference only): (keypoints[n,5] = x, y, size, angle, response; octave[n]; desc[n,128])"""
+    def sift_detect_and_compute(self, gray, nfeatures=0, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, max_kp=200000,
+                                precise_upscale=True):
+        """the reference's cv::SIFT::detectAndCompute (real reference only): (keypoints[n,5] = x, y, size, angle, response; octave[n]; desc[n,128]).
+        precise_upscale=True is SIFT::create(..., enable_precise_upscale=true): the first-octave image sift_pyramid() builds."""
         gray = np.ascontiguousarray(gray)
         h, w = gray.shape
         kp = np.zeros((max_kp, 6), np.float32); desc = np.zeros((max_kp, 128), np.float32); n = ctypes.c_int(0)
         self._ok(self.fn("sift_detect_and_compute")(_p(gray), sz(gray.strides[0]), w, h, int(nfeatures), int(nOctaveLayers), dbl(contrastThreshold),
-                                                     dbl(edgeThreshold), dbl(sigma), int(max_kp), _p(kp), _p(desc), ctypes.byref(n)), "SIFT")
+                                                     dbl(edgeThreshold), dbl(sigma), int(bool(precise_upscale)), int(max_kp), _p(kp), _p(desc), ctypes.byref(n)), "SIFT")
         m = min(n.value, max_kp)
         return kp[:m, :5].copy(), kp[:m, 5].copy().view(np.int32), desc[:m].copy()
+
+    def sift_detect_from_pyramid(self, gauss, dog, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, upscale=True, max_kp=200000):
+        """port only: extrema + refinement + orientation on GIVEN pyramids ([octave][layer] lists as sift_pyramid returns) -> (kp[n,5], octave[n])"""
+        no = len(gauss)
+        dims = np.array([[g[0].shape[1], g[0].shape[0]] for g in gauss], np.int32).reshape(-1)
+        G = np.concatenate([np.ascontiguousarray(l, np.float32).reshape(-1) for g in gauss for l in g])
+        D = np.concatenate([np.ascontiguousarray(l, np.float32).reshape(-1) for d in dog for l in d])
+        kp = np.zeros((max_kp, 6), np.float32); n = ctypes.c_int(0)
+        self._ok(self.fn("sift_detect")(_p(G), _p(D), _p(dims), no, int(nOctaveLayers), dbl(contrastThreshold), dbl(edgeThreshold), dbl(sigma),
+                                        -1 if upscale else 0, int(max_kp), _p(kp), ctypes.byref(n)), "sift_detect")
+        m = min(n.value, max_kp)
+        return kp[:m, :5].copy(), kp[:m, 5].copy().view(np.int32)
+
+    def sift_descriptors_from_pyramid(self, gauss, kp, octave, nOctaveLayers=3, upscale=True):
+        """port only: 128-float descriptors of given keypoints (kp[n,5], octave[n] as sift_detect_* return) on a GIVEN Gaussian pyramid"""
+        no = len(gauss)
+        dims = np.array([[g[0].shape[1], g[0].shape[0]] for g in gauss], np.int32).reshape(-1)
+        G = np.concatenate([np.ascontiguousarray(l, np.float32).reshape(-1) for g in gauss for l in g])
+        k6 = np.zeros((len(kp), 6), np.float32); k6[:, :5] = kp; k6[:, 5] = np.asarray(octave, np.int32).view(np.float32)
+        desc = np.zeros((len(kp), 128), np.float32)
+        self._ok(self.fn("sift_descriptors")(_p(G), _p(dims), no, int(nOctaveLayers), -1 if upscale else 0, _p(k6), len(kp), _p(desc)), "sift_descriptors")
+        return desc
 
     def sift_pyramid(self, gray, nOctaveLayers=3, sigma=1.6, upscale=True):
         """returns (gauss list-of-lists [octave][layer], dog list-of-lists)"""

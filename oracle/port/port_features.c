@@ -195,3 +195,267 @@ PORT_API int port_sift_pyramid(const void* gray, size_t step, int w, int h, int 
     if (!gauss) free(G);
     return 0;
 }
+
+/* ---- SIFT scale-space extrema, sub-pixel refinement, orientation assignment (sift.simd.hpp:160-681, sift.dispatch.cpp:368-402, :529-560) -----
+ * Input: the packed Gaussian / DoG pyramids (layout of port_sift_pyramid: octave-major, nl+3 / nl+2 images of dims[2o] x dims[2o+1]).
+ * Output: keypoints as 6 floats (x, y, size, angle, response, octave bits) after KeyPointsFilter::removeDuplicatedSorted and the
+ * first-octave rescaling, i.e. what cv::SIFT::detect returns (nfeatures = 0, no mask).
+ * The reference's AVX2 / AVX-512 objects of this file are built with FMA contraction, its exp / atan2 are OpenCV's own approximations
+ * (mathfuncs_core.simd.hpp): this restatement uses plain float expressions, fastAtan2's polynomial and expf.  It is therefore pinned by
+ * tolerance, not bit for bit: tests/test_oracle.py states the agreement that is measured against the reference. */
+typedef struct { float x, y, size, angle, response; int octave; } PortKp;
+
+static float port_fast_atan2_deg(float y, float x)          /* atan_f32, mathfuncs_core.simd.hpp:52-72 */
+{
+    const float p1 = 0.9997878412794807f * (float)(180 / 3.1415926535897932384626433832795), p3 = -0.3258083974640975f * (float)(180 / 3.1415926535897932384626433832795);
+    const float p5 = 0.1555786518463281f * (float)(180 / 3.1415926535897932384626433832795), p7 = -0.04432655554792128f * (float)(180 / 3.1415926535897932384626433832795);
+    float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+    if (ax >= ay) { c = ay / (ax + (float)2.2204460492503131e-16); c2 = c * c; a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
+    else { c = ax / (ay + (float)2.2204460492503131e-16); c2 = c * c; a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+static int sift_adjust(const float* dogo, int cw, int ch, int nl, int octv, int* layer, int* r_, int* c_, float contrastThreshold, float edgeThreshold,
+                       float sigma, PortKp* kpt)
+{
+    const float img_scale = 1.f / 255, deriv_scale = img_scale * 0.5f, second_deriv_scale = img_scale, cross_deriv_scale = img_scale * 0.25f;
+    const size_t n = (size_t)cw * ch;
+    float xi = 0, xr = 0, xc = 0, contr = 0;
+    int i = 0, r = *r_, c = *c_, l = *layer;
+#define AT(P, R, C) (P)[(size_t)(R) * cw + (C)]
+    for (; i < 5; i++) {
+        const float* img = dogo + (size_t)l * n; const float* prev = img - n; const float* next = img + n;
+        float dD[3] = {(AT(img, r, c + 1) - AT(img, r, c - 1)) * deriv_scale, (AT(img, r + 1, c) - AT(img, r - 1, c)) * deriv_scale,
+                       (AT(next, r, c) - AT(prev, r, c)) * deriv_scale};
+        float v2 = AT(img, r, c) * 2;
+        float dxx = (AT(img, r, c + 1) + AT(img, r, c - 1) - v2) * second_deriv_scale;
+        float dyy = (AT(img, r + 1, c) + AT(img, r - 1, c) - v2) * second_deriv_scale;
+        float dss = (AT(next, r, c) + AT(prev, r, c) - v2) * second_deriv_scale;
+        float dxy = (AT(img, r + 1, c + 1) - AT(img, r + 1, c - 1) - AT(img, r - 1, c + 1) + AT(img, r - 1, c - 1)) * cross_deriv_scale;
+        float dxs = (AT(next, r, c + 1) - AT(next, r, c - 1) - AT(prev, r, c + 1) + AT(prev, r, c - 1)) * cross_deriv_scale;
+        float dys = (AT(next, r + 1, c) - AT(next, r - 1, c) - AT(prev, r + 1, c) + AT(prev, r - 1, c)) * cross_deriv_scale;
+        /* Matx33f::solve(DECOMP_LU) = Cramer's rule in float (operations.hpp:191-213, matx.inl.hpp:53-61) */
+        float a00 = dxx, a01 = dxy, a02 = dxs, a10 = dxy, a11 = dyy, a12 = dys, a20 = dxs, a21 = dys, a22 = dss;
+        float d = (float)(double)(a00 * (a11 * a22 - a21 * a12) - a01 * (a10 * a22 - a20 * a12) + a02 * (a10 * a21 - a20 * a11));
+        float X[3] = {0, 0, 0};
+        if (d != 0) {
+            d = 1 / d;
+            X[0] = d * (dD[0] * (a11 * a22 - a12 * a21) - a01 * (dD[1] * a22 - a12 * dD[2]) + a02 * (dD[1] * a21 - a11 * dD[2]));
+            X[1] = d * (a00 * (dD[1] * a22 - a12 * dD[2]) - dD[0] * (a10 * a22 - a12 * a20) + a02 * (a10 * dD[2] - dD[1] * a20));
+            X[2] = d * (a00 * (a11 * dD[2] - dD[1] * a21) - a01 * (a10 * dD[2] - dD[1] * a20) + dD[0] * (a10 * a21 - a11 * a20));
+        }
+        xi = -X[2]; xr = -X[1]; xc = -X[0];
+        if (fabsf(xi) < 0.5f && fabsf(xr) < 0.5f && fabsf(xc) < 0.5f) break;
+        if (fabsf(xi) > (float)(2147483647 / 3) || fabsf(xr) > (float)(2147483647 / 3) || fabsf(xc) > (float)(2147483647 / 3)) return 0;
+        c += (int)lrintf(xc); r += (int)lrintf(xr); l += (int)lrintf(xi);
+        if (l < 1 || l > nl || c < 5 || c >= cw - 5 || r < 5 || r >= ch - 5) return 0;
+    }
+    if (i >= 5) return 0;
+    {
+        const float* img = dogo + (size_t)l * n; const float* prev = img - n; const float* next = img + n;
+        float dD[3] = {(AT(img, r, c + 1) - AT(img, r, c - 1)) * deriv_scale, (AT(img, r + 1, c) - AT(img, r - 1, c)) * deriv_scale,
+                       (AT(next, r, c) - AT(prev, r, c)) * deriv_scale};
+        float t = dD[0] * xc + dD[1] * xr + dD[2] * xi;
+        contr = AT(img, r, c) * img_scale + t * 0.5f;
+        if (fabsf(contr) * nl < contrastThreshold) return 0;
+        float v2 = AT(img, r, c) * 2.f;
+        float dxx = (AT(img, r, c + 1) + AT(img, r, c - 1) - v2) * second_deriv_scale;
+        float dyy = (AT(img, r + 1, c) + AT(img, r - 1, c) - v2) * second_deriv_scale;
+        float dxy = (AT(img, r + 1, c + 1) - AT(img, r + 1, c - 1) - AT(img, r - 1, c + 1) + AT(img, r - 1, c - 1)) * cross_deriv_scale;
+        float tr = dxx + dyy, det = dxx * dyy - dxy * dxy;
+        if (det <= 0 || tr * tr * edgeThreshold >= (edgeThreshold + 1) * (edgeThreshold + 1) * det) return 0;
+    }
+#undef AT
+    kpt->x = (c + xc) * (1 << octv);
+    kpt->y = (r + xr) * (1 << octv);
+    kpt->octave = octv + (l << 8) + ((int)lrint((xi + 0.5) * 255) << 16);
+    kpt->size = sigma * powf(2.f, (l + xi) / nl) * (1 << octv) * 2;
+    kpt->response = fabsf(contr);
+    *layer = l; *r_ = r; *c_ = c;
+    return 1;
+}
+
+static float sift_ori_hist(const float* img, int cw, int ch, int px, int py, int radius, float sigma, float* hist, int n)
+{
+    float temp[36 + 4]; float* th = temp + 2;
+    const float expf_scale = -1.f / (2.f * sigma * sigma);
+    for (int i = 0; i < n; i++) th[i] = 0.f;
+    for (int i = -radius; i <= radius; i++) {
+        int y = py + i;
+        if (y <= 0 || y >= ch - 1) continue;
+        for (int j = -radius; j <= radius; j++) {
+            int x = px + j;
+            if (x <= 0 || x >= cw - 1) continue;
+            float dx = img[(size_t)y * cw + x + 1] - img[(size_t)y * cw + x - 1];
+            float dy = img[(size_t)(y - 1) * cw + x] - img[(size_t)(y + 1) * cw + x];
+            float w = expf((i * i + j * j) * expf_scale), ori = port_fast_atan2_deg(dy, dx), mag = sqrtf(dx * dx + dy * dy);
+            int bin = (int)lrintf((n / 360.f) * ori);
+            if (bin >= n) bin -= n;
+            if (bin < 0) bin += n;
+            th[bin] += w * mag;
+        }
+    }
+    th[-1] = th[n - 1]; th[-2] = th[n - 2]; th[n] = th[0]; th[n + 1] = th[1];
+    for (int i = 0; i < n; i++) hist[i] = (th[i - 2] + th[i + 2]) * (1.f / 16.f) + (th[i - 1] + th[i + 1]) * (4.f / 16.f) + th[i] * (6.f / 16.f);
+    float m = hist[0];
+    for (int i = 1; i < n; i++) if (hist[i] > m) m = hist[i];
+    return m;
+}
+
+static int kp_cmp(const void* pa, const void* pb)        /* KeyPoint12_LessThan, keypoint.cpp:253-271 (class_id is always -1 here) */
+{
+    const PortKp* a = (const PortKp*)pa; const PortKp* b = (const PortKp*)pb;
+    if (a->x != b->x) return a->x < b->x ? -1 : 1;
+    if (a->y != b->y) return a->y < b->y ? -1 : 1;
+    if (a->size != b->size) return a->size > b->size ? -1 : 1;
+    if (a->angle != b->angle) return a->angle < b->angle ? -1 : 1;
+    if (a->response != b->response) return a->response > b->response ? -1 : 1;
+    if (a->octave != b->octave) return a->octave > b->octave ? -1 : 1;
+    return 0;
+}
+
+PORT_API int port_sift_detect(const float* gauss, const float* dog, const int* dims, int n_oct, int nl, double contrastThreshold, double edgeThreshold,
+                              double sigma, int first_octave, int max_kp, float* kp_out, int* n_out)
+{
+    const int threshold = (int)floor(0.5 * contrastThreshold / nl * 255);
+    size_t cap = 1024, cnt = 0;
+    PortKp* kps = (PortKp*)malloc(sizeof(PortKp) * cap);
+    size_t goff = 0, doff = 0;
+    for (int o = 0; o < n_oct; o++) {
+        const int cw = dims[2 * o], ch = dims[2 * o + 1];
+        const size_t n = (size_t)cw * ch;
+        const float* dogo = dog + doff; const float* go = gauss + goff;
+        for (int i = 1; i <= nl; i++) {
+            const float* img = dogo + (size_t)i * n; const float* prev = img - n; const float* next = img + n;
+            for (int r = 5; r < ch - 5; r++)
+                for (int c = 5; c < cw - 5; c++) {
+                    const float val = img[(size_t)r * cw + c];
+                    if (fabsf(val) <= threshold) continue;
+                    int ok = 1;
+                    for (int dz = 0; dz < 3 && ok; dz++) {
+                        const float* p = dz == 0 ? img : dz == 1 ? prev : next;
+                        for (int dy = -1; dy <= 1 && ok; dy++)
+                            for (int dx = -1; dx <= 1; dx++) {
+                                const float v = p[(size_t)(r + dy) * cw + c + dx];
+                                if (val > 0 ? val < v : val > v) { ok = 0; break; }
+                            }
+                    }
+                    if (!ok) continue;
+                    PortKp kpt; int r1 = r, c1 = c, layer = i;
+                    if (!sift_adjust(dogo, cw, ch, nl, o, &layer, &r1, &c1, (float)contrastThreshold, (float)edgeThreshold, (float)sigma, &kpt)) continue;
+                    float scl_octv = kpt.size * 0.5f / (1 << o), hist[36];
+                    float omax = sift_ori_hist(go + (size_t)layer * n, cw, ch, c1, r1, (int)lrintf(4.5f * scl_octv), 1.5f * scl_octv, hist, 36);
+                    float mag_thr = omax * 0.8f;
+                    for (int j = 0; j < 36; j++) {
+                        int l = j > 0 ? j - 1 : 35, r2 = j < 35 ? j + 1 : 0;
+                        if (hist[j] > hist[l] && hist[j] > hist[r2] && hist[j] >= mag_thr) {
+                            float bin = j + 0.5f * (hist[l] - hist[r2]) / (hist[l] - 2 * hist[j] + hist[r2]);
+                            bin = bin < 0 ? 36 + bin : bin >= 36 ? bin - 36 : bin;
+                            kpt.angle = 360.f - (float)((360.f / 36) * bin);
+                            if (fabsf(kpt.angle - 360.f) < 1.1920929e-07f) kpt.angle = 0.f;
+                            if (cnt == cap) { cap *= 2; kps = (PortKp*)realloc(kps, sizeof(PortKp) * cap); }
+                            kps[cnt++] = kpt;
+                        }
+                    }
+                }
+        }
+        goff += n * (nl + 3); doff += n * (nl + 2);
+    }
+    /* KeyPointsFilter::removeDuplicatedSorted (keypoint.cpp:273-291), then the first-octave rescaling (sift.dispatch.cpp:548-555) */
+    size_t m = 0;
+    if (cnt) {
+        qsort(kps, cnt, sizeof(PortKp), kp_cmp);
+        for (size_t j = 1; j < cnt; j++)
+            if (kps[m].x != kps[j].x || kps[m].y != kps[j].y || kps[m].size != kps[j].size || kps[m].angle != kps[j].angle) kps[++m] = kps[j];
+        m++;
+    }
+    if (first_octave < 0) {
+        const float scale = 1.f / (float)(1 << -first_octave);
+        for (size_t j = 0; j < m; j++) {
+            kps[j].octave = (kps[j].octave & ~255) | ((kps[j].octave + first_octave) & 255);
+            kps[j].x *= scale; kps[j].y *= scale; kps[j].size *= scale;
+        }
+    }
+    *n_out = (int)m;
+    for (size_t j = 0; j < m && j < (size_t)max_kp; j++) {
+        float* o6 = kp_out + 6 * j;
+        o6[0] = kps[j].x; o6[1] = kps[j].y; o6[2] = kps[j].size; o6[3] = kps[j].angle; o6[4] = kps[j].response; memcpy(o6 + 5, &kps[j].octave, 4);
+    }
+    free(kps);
+    return 0;
+}
+
+/* ---- SIFT descriptors (calcSIFTDescriptor, sift.simd.hpp:709-1035; calcDescriptorsComputer, sift.dispatch.cpp:417-462): 4 x 4 cells x 8
+ * orientation bins, Gaussian-weighted gradient magnitudes spread by tri-linear interpolation, clipped at 0.2 of the norm, renormalised to
+ * 512 and saturated to bytes (stored as floats).  Same remark on exactness as port_sift_detect: plain float, fastAtan2's polynomial, expf. */
+PORT_API int port_sift_descriptors(const float* gauss, const int* dims, int n_oct, int nl, int first_octave, const float* kp, int nkp, float* desc)
+{
+    enum { d = 4, n = 8 };
+    size_t* offs = (size_t*)malloc(sizeof(size_t) * (size_t)n_oct);
+    size_t go = 0;
+    for (int o = 0; o < n_oct; o++) { offs[o] = go; go += (size_t)dims[2 * o] * dims[2 * o + 1] * (nl + 3); }
+    for (int q = 0; q < nkp; q++) {
+        const float* k6 = kp + 6 * q; int oct; memcpy(&oct, k6 + 5, 4);
+        int octave = oct & 255, layer = (oct >> 8) & 255;
+        octave = octave < 128 ? octave : (-128 | octave);
+        const float scale = octave >= 0 ? 1.f / (1 << octave) : (float)(1 << -octave);
+        const int oi = octave - first_octave;
+        if (oi < 0 || oi >= n_oct || layer > nl + 2) { free(offs); return -1; }
+        const int cols = dims[2 * oi], rows = dims[2 * oi + 1];
+        const float* img = gauss + offs[oi] + (size_t)layer * cols * rows;
+        const float size = k6[2] * scale, ptx = k6[0] * scale, pty = k6[1] * scale;
+        float ori = 360.f - k6[3];
+        if (fabsf(ori - 360.f) < 1.1920929e-07f) ori = 0.f;
+        const float scl = size * 0.5f;
+        const int px = (int)lrintf(ptx), py = (int)lrintf(pty);
+        float cos_t = cosf(ori * (float)(3.1415926535897932384626433832795 / 180)), sin_t = sinf(ori * (float)(3.1415926535897932384626433832795 / 180));
+        const float bins_per_rad = n / 360.f, exp_scale = -1.f / (d * d * 0.5f), hist_width = 3.f * scl;
+        int radius = (int)lrintf(hist_width * 1.4142135623730951f * (d + 1) * 0.5f);
+        const int diag = (int)sqrt((double)cols * cols + (double)rows * rows);
+        if (radius > diag) radius = diag;
+        cos_t /= hist_width; sin_t /= hist_width;
+        float hist[(d + 2) * (d + 2) * (n + 2)], raw[d * d * n];
+        for (int i = 0; i < (d + 2) * (d + 2) * (n + 2); i++) hist[i] = 0.f;
+        for (int i = -radius; i <= radius; i++)
+            for (int j = -radius; j <= radius; j++) {
+                float c_rot = j * cos_t - i * sin_t, r_rot = j * sin_t + i * cos_t;
+                float rbin = r_rot + d / 2 - 0.5f, cbin = c_rot + d / 2 - 0.5f;
+                int r = py + i, c = px + j;
+                if (!(rbin > -1 && rbin < d && cbin > -1 && cbin < d && r > 0 && r < rows - 1 && c > 0 && c < cols - 1)) continue;
+                float dx = img[(size_t)r * cols + c + 1] - img[(size_t)r * cols + c - 1];
+                float dy = img[(size_t)(r - 1) * cols + c] - img[(size_t)(r + 1) * cols + c];
+                float w = expf((c_rot * c_rot + r_rot * r_rot) * exp_scale);
+                float obin = (port_fast_atan2_deg(dy, dx) - ori) * bins_per_rad, mag = sqrtf(dx * dx + dy * dy) * w;
+                int r0 = (int)floorf(rbin), c0 = (int)floorf(cbin), o0 = (int)floorf(obin);
+                rbin -= r0; cbin -= c0; obin -= o0;
+                if (o0 < 0) o0 += n;
+                if (o0 >= n) o0 -= n;
+                float v_r1 = mag * rbin, v_r0 = mag - v_r1;
+                float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11, v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
+                float v_rco111 = v_rc11 * obin, v_rco110 = v_rc11 - v_rco111, v_rco101 = v_rc10 * obin, v_rco100 = v_rc10 - v_rco101;
+                float v_rco011 = v_rc01 * obin, v_rco010 = v_rc01 - v_rco011, v_rco001 = v_rc00 * obin, v_rco000 = v_rc00 - v_rco001;
+                int idx = ((r0 + 1) * (d + 2) + c0 + 1) * (n + 2) + o0;
+                hist[idx] += v_rco000; hist[idx + 1] += v_rco001; hist[idx + (n + 2)] += v_rco010; hist[idx + (n + 3)] += v_rco011;
+                hist[idx + (d + 2) * (n + 2)] += v_rco100; hist[idx + (d + 2) * (n + 2) + 1] += v_rco101;
+                hist[idx + (d + 3) * (n + 2)] += v_rco110; hist[idx + (d + 3) * (n + 2) + 1] += v_rco111;
+            }
+        for (int i = 0; i < d; i++)
+            for (int j = 0; j < d; j++) {
+                int idx = ((i + 1) * (d + 2) + (j + 1)) * (n + 2);
+                hist[idx] += hist[idx + n]; hist[idx + 1] += hist[idx + n + 1];
+                for (int k = 0; k < n; k++) raw[(i * d + j) * n + k] = hist[idx + k];
+            }
+        float nrm2 = 0;
+        for (int k = 0; k < d * d * n; k++) nrm2 += raw[k] * raw[k];
+        const float thr = sqrtf(nrm2) * 0.2f;
+        nrm2 = 0;
+        for (int k = 0; k < d * d * n; k++) { float v = raw[k] < thr ? raw[k] : thr; raw[k] = v; nrm2 += v * v; }
+        float s = sqrtf(nrm2); if (s < 1.1920929e-07f) s = 1.1920929e-07f;
+        nrm2 = 512.f / s;
+        for (int k = 0; k < d * d * n; k++) desc[(size_t)q * 128 + k] = (float)port_sat_u8f(raw[k] * nrm2);
+    }
+    free(offs);
+    return 0;
+}

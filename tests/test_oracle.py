@@ -302,6 +302,46 @@ def test_reference_sift_front_end_is_reachable(ref, rng):
     assert np.all(desc >= 0) and np.all(desc <= 255) and np.all(desc == np.round(desc)), "descriptors are 8-bit-valued floats (sift.simd.hpp:1018-1034)"
 
 
+def _sift_test_image(rng, h, w):
+    small = rng.random((h // 8 + 2, w // 8 + 2)).astype(np.float32)
+    img = np.kron(small, np.ones((8, 8), np.float32))[:h, :w] + 0.15 * rng.random((h, w)).astype(np.float32)
+    img = (img - img.min()) / (img.max() - img.min())
+    return (img * 255).astype(np.uint8)
+
+
+def match_keypoints(a, b, tol_xy=1e-3, tol_angle=1e-2):
+    """greedy one-to-one match of two (n,5) keypoint arrays on (x, y, size, angle): returns the number of matched pairs"""
+    used = np.zeros(len(b), bool)
+    hit = 0
+    order = np.lexsort((b[:, 1], b[:, 0]))
+    bx = b[order, 0]
+    for k in a:
+        lo, hi = np.searchsorted(bx, k[0] - tol_xy), np.searchsorted(bx, k[0] + tol_xy)
+        for j in order[lo:hi]:
+            if not used[j] and abs(b[j, 1] - k[1]) <= tol_xy and abs(b[j, 2] - k[2]) <= tol_xy and \
+                    min(abs(b[j, 3] - k[3]), 360 - abs(b[j, 3] - k[3])) <= tol_angle:
+                used[j] = True; hit += 1
+                break
+    return hit
+
+
+def test_port_sift_detector_and_descriptors_vs_reference(ref, port, rng):
+    """scale-space extrema + refinement + orientation + descriptors, restated; fed the reference's own pyramids so that only
+    this stage is compared.  The reference's SIFT objects are FMA-contracted AVX2 / AVX-512 builds with OpenCV's approximate exp / atan2: the
+    agreement is by tolerance.  Measured: >= 99% of the keypoints agree to 1e-3 px / 1e-2 deg (typically all but a handful of borderline
+    accept / reject decisions, differences ~3e-5 px); descriptors of identical keypoints differ in < 1e-4 of their entries, by 1."""
+    for (h, w) in [(240, 320), (300, 400)]:
+        img = _sift_test_image(rng, h, w)
+        kr, octr, dr = ref.sift_detect_and_compute(img)
+        G, D = ref.sift_pyramid(img)
+        kp, octp = port.sift_detect_from_pyramid(G, D)
+        assert abs(len(kp) - len(kr)) <= max(3, len(kr) // 100), "keypoint count %d vs %d" % (len(kp), len(kr))
+        assert match_keypoints(kr, kp) >= 0.99 * len(kr)
+        dp = port.sift_descriptors_from_pyramid(G, kr, octr)
+        diff = np.abs(dp - dr)
+        assert diff.max() <= 1 and (diff > 0).mean() < 1e-4, "descriptor entries differing: %d of %d, max %g" % ((diff > 0).sum(), diff.size, diff.max())
+
+
 def test_port_vs_reference_remap(ref, port, rng):
     """cv::remap restated in the port: float planes, packed float pairs, fixed-point maps (incl. the NNDeltaTab_i quirk), NaN and
     out-of-range coordinates -- bit-exact against the reference for u8 and f32."""
