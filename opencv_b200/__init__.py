@@ -472,6 +472,26 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, blockSize=
     return out if image.dim() == 4 else out[0]
 
 
+def sift_detectAndCompute(gray, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, max_keypoints=200000, with_descriptors=True,
+                          stream=None):
+    """cv::SIFT::create(0, nOctaveLayers, contrastThreshold, edgeThreshold, sigma, enable_precise_upscale=True)->detectAndCompute(gray) for one
+    (H,W) CV_8U frame: pyramid, extrema, refinement, orientation and descriptors all on the device.
+    Returns (keypoints[n,5] = x, y, size, angle, response; octave[n] int32; descriptors[n,128] float32 or None) as numpy arrays."""
+    assert gray.dim() == 2, "one frame at a time"
+    G, D, dims = sift_pyramid(gray, nOctaveLayers, sigma, True, True, stream)
+    dims32 = np.ascontiguousarray(dims, np.int32).reshape(-1)
+    kp = np.zeros((max_keypoints, 6), np.float32)
+    desc = np.zeros((max_keypoints, 128), np.float32) if with_descriptors else None
+    n = ctypes.c_int(0)
+    _check(lib().b200cv_sift_detect_and_compute(ctypes.c_void_p(G.data_ptr()), ctypes.c_void_p(D.data_ptr()), dims32.ctypes.data_as(ctypes.c_void_p),
+                                                len(dims32) // 2, int(nOctaveLayers), ctypes.c_double(contrastThreshold), ctypes.c_double(edgeThreshold),
+                                                ctypes.c_double(sigma), -1, int(max_keypoints), kp.ctypes.data_as(ctypes.c_void_p),
+                                                desc.ctypes.data_as(ctypes.c_void_p) if with_descriptors else None, ctypes.byref(n), _stream_ptr(stream)),
+           "sift_detectAndCompute")
+    m = min(n.value, max_keypoints)
+    return kp[:m, :5].copy(), kp[:m, 5].copy().view(np.int32), (desc[:m].copy() if with_descriptors else None)
+
+
 class GFTTDetector:
     """cv::GFTTDetector (features2d.hpp; features2d/src/gftt.cpp:44-157): the Feature2D face of goodFeaturesToTrack.  detect() returns an
     (n, 4) float32 array per frame: x, y, size (= blockSize, gftt.cpp:147), response (the corner quality); angle / octave are unset

@@ -329,3 +329,38 @@ def test_emulated_integral_vs_port(integral_emu, port, rng):
     gs = integral_emu(batch, False)
     for f in range(3):
         assert np.array_equal(gs[f, :, :, 0], port.integral(batch[f, :, :, 0])), "integral batch frame %d" % f
+
+
+# ---- SIFT extrema / refinement / orientation / descriptors (sift_detect.cu) -----------------------------------------------------------------
+@pytest.fixture(scope="module")
+def sift_emu():
+    lib = build_emulation("sift_detect.cu", "int emu_sift(const float* g, const float* d, const int* dims, int no, int nl, double ct, double et, double sigma, "
+                          "int first_octave, int max_kp, float* kp, float* desc, int* n)",
+                          "    return b200cv::sift_detect_impl(g, d, dims, no, nl, ct, et, sigma, first_octave, max_kp, kp, desc, n, nullptr);")
+
+    def run(gauss, dog, nl=3, ct=0.04, et=10.0, sigma=1.6, max_kp=100000):
+        no = len(gauss)
+        dims = np.array([[g[0].shape[1], g[0].shape[0]] for g in gauss], np.int32).reshape(-1)
+        G = np.concatenate([np.ascontiguousarray(l, np.float32).reshape(-1) for g in gauss for l in g])
+        D = np.concatenate([np.ascontiguousarray(l, np.float32).reshape(-1) for d in dog for l in d])
+        kp = np.zeros((max_kp, 6), np.float32); desc = np.zeros((max_kp, 128), np.float32); n = ctypes.c_int(0)
+        fp = ctypes.POINTER(ctypes.c_float)
+        rc = lib.emu_sift(G.ctypes.data_as(fp), D.ctypes.data_as(fp), dims.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), no, nl, ctypes.c_double(ct),
+                          ctypes.c_double(et), ctypes.c_double(sigma), -1, max_kp, kp.ctypes.data_as(fp), desc.ctypes.data_as(fp), ctypes.byref(n))
+        assert rc == 0, "emulated sift_detect_impl returned %d" % rc
+        return kp[:n.value, :5].copy(), kp[:n.value, 5].copy().view(np.int32), desc[:n.value].copy()
+    return run
+
+
+def test_emulated_sift_front_end_vs_port(sift_emu, port, rng):
+    """the three kernels + the host-side sort / duplicate removal, run on the host, against the port on the same (port-built) pyramids:
+    same float expressions, same libm -> identical keypoints and descriptors"""
+    small = rng.random((22, 30)).astype(np.float32)
+    img = np.kron(small, np.ones((8, 8), np.float32))[:160, :220] + 0.15 * rng.random((160, 220)).astype(np.float32)
+    img = ((img - img.min()) / (img.max() - img.min()) * 255).astype(np.uint8)
+    G, D = port.sift_pyramid(img)
+    kp, octv = port.sift_detect_from_pyramid(G, D)
+    gk, go, gd = sift_emu(G, D)
+    assert len(gk) == len(kp) and len(kp) > 100
+    assert np.array_equal(gk, kp) and np.array_equal(go, octv), "keypoints"
+    assert np.array_equal(gd, port.sift_descriptors_from_pyramid(G, kp, octv)), "descriptors"
