@@ -216,10 +216,11 @@ B200CV_API int b200cv_sift_pyramid_layout(int width, int height, int n_octave_la
  * sub-pixel refinement, orientation assignment, duplicate removal, first-octave rescaling and, if descriptors != NULL, the 128-float
  * descriptors.  gauss / dog: DEVICE pointers to ONE frame's packed pyramids as b200cv_sift_pyramid writes them; dims: the per-octave (w, h)
  * table of b200cv_sift_pyramid_layout (host); keypoints: HOST, 6 floats each (x, y, size, angle, response, packed octave as int bits);
- * descriptors: HOST, 128 floats each; at most max_keypoints are written, *n_keypoints receives the number found.  Synchronises the stream. */
+ * descriptors: HOST, 128 floats each; n_features > 0 keeps the strongest responses (KeyPointsFilter::retainBest, ties included); at most
+ * max_keypoints are written, *n_keypoints receives the number found.  Synchronises the stream. */
 B200CV_API int b200cv_sift_detect_and_compute(const float* gauss, const float* dog, const int* dims, int n_octaves, int n_octave_layers,
-                                              double contrast_threshold, double edge_threshold, double sigma, int first_octave, int max_keypoints,
-                                              float* keypoints, float* descriptors, int* n_keypoints, void* stream);
+                                              double contrast_threshold, double edge_threshold, double sigma, int first_octave, int n_features,
+                                              int max_keypoints, float* keypoints, float* descriptors, int* n_keypoints, void* stream);
 B200CV_API int b200cv_sift_pyramid(const b200cvMat* src, int n_octave_layers, double sigma, int upscale,
                                    float* gauss, size_t gauss_frame_elems, float* dog, size_t dog_frame_elems, void* stream);
 

@@ -472,9 +472,9 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, blockSize=
     return out if image.dim() == 4 else out[0]
 
 
-def sift_detectAndCompute(gray, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, max_keypoints=200000, with_descriptors=True,
-                          stream=None):
-    """cv::SIFT::create(0, nOctaveLayers, contrastThreshold, edgeThreshold, sigma, enable_precise_upscale=True)->detectAndCompute(gray) for one
+def sift_detectAndCompute(gray, nfeatures=0, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, max_keypoints=200000,
+                          with_descriptors=True, stream=None):
+    """cv::SIFT::create(nfeatures, nOctaveLayers, contrastThreshold, edgeThreshold, sigma, enable_precise_upscale=True)->detectAndCompute(gray) for one
     (H,W) CV_8U frame: pyramid, extrema, refinement, orientation and descriptors all on the device.
     Returns (keypoints[n,5] = x, y, size, angle, response; octave[n] int32; descriptors[n,128] float32 or None) as numpy arrays."""
     assert gray.dim() == 2, "one frame at a time"
@@ -485,7 +485,7 @@ def sift_detectAndCompute(gray, nOctaveLayers=3, contrastThreshold=0.04, edgeThr
     n = ctypes.c_int(0)
     _check(lib().b200cv_sift_detect_and_compute(ctypes.c_void_p(G.data_ptr()), ctypes.c_void_p(D.data_ptr()), dims32.ctypes.data_as(ctypes.c_void_p),
                                                 len(dims32) // 2, int(nOctaveLayers), ctypes.c_double(contrastThreshold), ctypes.c_double(edgeThreshold),
-                                                ctypes.c_double(sigma), -1, int(max_keypoints), kp.ctypes.data_as(ctypes.c_void_p),
+                                                ctypes.c_double(sigma), -1, int(nfeatures), int(max_keypoints), kp.ctypes.data_as(ctypes.c_void_p),
                                                 desc.ctypes.data_as(ctypes.c_void_p) if with_descriptors else None, ctypes.byref(n), _stream_ptr(stream)),
            "sift_detectAndCompute")
     m = min(n.value, max_keypoints)

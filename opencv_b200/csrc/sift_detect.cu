@@ -271,7 +271,7 @@ struct KpLess {      // KeyPoint12_LessThan, features2d/src/keypoint.cpp:253-271
 // gauss / dog: device pointers to ONE frame's packed pyramids (layout of b200cv_sift_pyramid_layout); kp_host: 6 floats per keypoint
 // (x, y, size, angle, response, octave bits), desc_host: 128 floats per keypoint or null; both host memory.  Synchronises the stream.
 int sift_detect_impl(const float* gauss, const float* dog, const int* dims, int n_oct, int nl, double contrastThreshold, double edgeThreshold, double sigma,
-                     int first_octave, int max_kp, float* kp_host, float* desc_host, int* n_out, cudaStream_t st)
+                     int first_octave, int nfeatures, int max_kp, float* kp_host, float* desc_host, int* n_out, cudaStream_t st)
 {
     B200_REQUIRE(gauss && dog && dims && kp_host && n_out && n_oct > 0 && n_oct <= SIFT_MAX_OCT && nl > 0 && nl <= 8 && max_kp > 0, "sift_detect: bad arguments");
     SiftPyr p;
@@ -335,6 +335,14 @@ int sift_detect_impl(const float* gauss, const float* dog, const int* dims, int 
         for (size_t j = 1; j < hk.size(); j++)
             if (hk[m].x != hk[j].x || hk[m].y != hk[j].y || hk[m].size != hk[j].size || hk[m].angle != hk[j].angle) hk[++m] = hk[j];
         hk.resize(m + 1);
+        // KeyPointsFilter::retainBest (keypoint.cpp:69-90): everything at least as strong as the nfeatures-th response; the same std:: calls on the
+        // same sequence, so the same order comes out
+        if (nfeatures > 0 && hk.size() > (size_t)nfeatures) {
+            std::nth_element(hk.begin(), hk.begin() + nfeatures - 1, hk.end(), [](const SiftKp& a, const SiftKp& b) { return a.response > b.response; });
+            const float ambiguous = hk[nfeatures - 1].response;
+            auto new_end = std::partition(hk.begin() + nfeatures, hk.end(), [ambiguous](const SiftKp& k) { return k.response >= ambiguous; });
+            hk.resize(new_end - hk.begin());
+        }
         if (first_octave < 0) {
             const float scale = 1.f / (float)(1 << -first_octave);
             for (SiftKp& k : hk) { k.octave = (k.octave & ~255) | ((k.octave + first_octave) & 255); k.x *= scale; k.y *= scale; k.size *= scale; }
@@ -373,9 +381,9 @@ int sift_detect_impl(const float* gauss, const float* dog, const int* dims, int 
 using namespace b200cv;
 
 extern "C" int b200cv_sift_detect_and_compute(const float* gauss, const float* dog, const int* dims, int n_octaves, int n_octave_layers, double contrast_threshold,
-                                              double edge_threshold, double sigma, int first_octave, int max_keypoints, float* keypoints, float* descriptors,
-                                              int* n_keypoints, void* stream)
+                                              double edge_threshold, double sigma, int first_octave, int n_features, int max_keypoints, float* keypoints,
+                                              float* descriptors, int* n_keypoints, void* stream)
 {
-    return sift_detect_impl(gauss, dog, dims, n_octaves, n_octave_layers, contrast_threshold, edge_threshold, sigma, first_octave, max_keypoints, keypoints,
-                            descriptors, n_keypoints, as_stream(stream));
+    return sift_detect_impl(gauss, dog, dims, n_octaves, n_octave_layers, contrast_threshold, edge_threshold, sigma, first_octave, n_features, max_keypoints,
+                            keypoints, descriptors, n_keypoints, as_stream(stream));
 }

@@ -304,7 +304,8 @@ class Oracle:
         m = min(n.value, max_kp)
         return kp[:m, :5].copy(), kp[:m, 5].copy().view(np.int32), desc[:m].copy()
 
-    def sift_detect_from_pyramid(self, gauss, dog, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, upscale=True, max_kp=200000):
+    def sift_detect_from_pyramid(self, gauss, dog, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, upscale=True, max_kp=200000,
+                                 nfeatures=0):
         """port only: extrema + refinement + orientation on GIVEN pyramids ([octave][layer] lists as sift_pyramid returns) -> (kp[n,5], octave[n])"""
         no = len(gauss)
         dims = np.array([[g[0].shape[1], g[0].shape[0]] for g in gauss], np.int32).reshape(-1)
@@ -312,7 +313,7 @@ class Oracle:
         D = np.concatenate([np.ascontiguousarray(l, np.float32).reshape(-1) for d in dog for l in d])
         kp = np.zeros((max_kp, 6), np.float32); n = ctypes.c_int(0)
         self._ok(self.fn("sift_detect")(_p(G), _p(D), _p(dims), no, int(nOctaveLayers), dbl(contrastThreshold), dbl(edgeThreshold), dbl(sigma),
-                                        -1 if upscale else 0, int(max_kp), _p(kp), ctypes.byref(n)), "sift_detect")
+                                        -1 if upscale else 0, int(nfeatures), int(max_kp), _p(kp), ctypes.byref(n)), "sift_detect")
         m = min(n.value, max_kp)
         return kp[:m, :5].copy(), kp[:m, 5].copy().view(np.int32)
 

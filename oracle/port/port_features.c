@@ -317,7 +317,7 @@ static int kp_cmp(const void* pa, const void* pb)        /* KeyPoint12_LessThan,
 }
 
 PORT_API int port_sift_detect(const float* gauss, const float* dog, const int* dims, int n_oct, int nl, double contrastThreshold, double edgeThreshold,
-                              double sigma, int first_octave, int max_kp, float* kp_out, int* n_out)
+                              double sigma, int first_octave, int nfeatures, int max_kp, float* kp_out, int* n_out)
 {
     const int threshold = (int)floor(0.5 * contrastThreshold / nl * 255);
     size_t cap = 1024, cnt = 0;
@@ -370,6 +370,22 @@ PORT_API int port_sift_detect(const float* gauss, const float* dog, const int* d
         for (size_t j = 1; j < cnt; j++)
             if (kps[m].x != kps[j].x || kps[m].y != kps[j].y || kps[m].size != kps[j].size || kps[m].angle != kps[j].angle) kps[++m] = kps[j];
         m++;
+    }
+    /* KeyPointsFilter::retainBest (keypoint.cpp:69-90): everything at least as strong as the nfeatures-th response.  The reference's order after
+     * std::nth_element / std::partition is the library's; here the survivors keep the sorted order: compare as sets. */
+    if (nfeatures > 0 && m > (size_t)nfeatures) {
+        float* resp = (float*)malloc(sizeof(float) * m);
+        for (size_t j = 0; j < m; j++) resp[j] = kps[j].response;
+        for (size_t a = 0; a < (size_t)nfeatures; a++) {        /* partial selection sort of the responses, descending */
+            size_t best = a;
+            for (size_t b2 = a + 1; b2 < m; b2++) if (resp[b2] > resp[best]) best = b2;
+            float t = resp[a]; resp[a] = resp[best]; resp[best] = t;
+        }
+        const float ambiguous = resp[nfeatures - 1];
+        free(resp);
+        size_t w = 0;
+        for (size_t j = 0; j < m; j++) if (kps[j].response >= ambiguous) kps[w++] = kps[j];
+        m = w;
     }
     if (first_octave < 0) {
         const float scale = 1.f / (float)(1 << -first_octave);

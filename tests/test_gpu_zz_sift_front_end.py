@@ -56,3 +56,8 @@ def test_sift_detect_and_compute(cvb, ref, rng, size):
     assert (diff <= 1).mean() >= 0.99, "descriptor entries within +-1: %.4f" % (diff <= 1).mean()
     # the keypoints come out in the reference's order (KeyPoint12_LessThan): sorted by x
     assert np.all(np.diff(kg[:, 0]) >= 0)
+    # nfeatures = retainBest: the strongest responses (ties included), the reference's selection
+    k500, _, d500 = cvb.sift_detectAndCompute(gpu(img), nfeatures=500)
+    r500, _, _ = ref.sift_detect_and_compute(img, nfeatures=500)
+    assert abs(len(k500) - len(r500)) <= 10 and len(match(r500, k500, 1e-2, 0.1)) >= 0.95 * len(r500)
+    assert d500.shape == (len(k500), 128)

@@ -335,10 +335,10 @@ def test_emulated_integral_vs_port(integral_emu, port, rng):
 @pytest.fixture(scope="module")
 def sift_emu():
     lib = build_emulation("sift_detect.cu", "int emu_sift(const float* g, const float* d, const int* dims, int no, int nl, double ct, double et, double sigma, "
-                          "int first_octave, int max_kp, float* kp, float* desc, int* n)",
-                          "    return b200cv::sift_detect_impl(g, d, dims, no, nl, ct, et, sigma, first_octave, max_kp, kp, desc, n, nullptr);")
+                          "int first_octave, int nfeatures, int max_kp, float* kp, float* desc, int* n)",
+                          "    return b200cv::sift_detect_impl(g, d, dims, no, nl, ct, et, sigma, first_octave, nfeatures, max_kp, kp, desc, n, nullptr);")
 
-    def run(gauss, dog, nl=3, ct=0.04, et=10.0, sigma=1.6, max_kp=100000):
+    def run(gauss, dog, nl=3, ct=0.04, et=10.0, sigma=1.6, max_kp=100000, nfeatures=0):
         no = len(gauss)
         dims = np.array([[g[0].shape[1], g[0].shape[0]] for g in gauss], np.int32).reshape(-1)
         G = np.concatenate([np.ascontiguousarray(l, np.float32).reshape(-1) for g in gauss for l in g])
@@ -346,7 +346,7 @@ def sift_emu():
         kp = np.zeros((max_kp, 6), np.float32); desc = np.zeros((max_kp, 128), np.float32); n = ctypes.c_int(0)
         fp = ctypes.POINTER(ctypes.c_float)
         rc = lib.emu_sift(G.ctypes.data_as(fp), D.ctypes.data_as(fp), dims.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), no, nl, ctypes.c_double(ct),
-                          ctypes.c_double(et), ctypes.c_double(sigma), -1, max_kp, kp.ctypes.data_as(fp), desc.ctypes.data_as(fp), ctypes.byref(n))
+                          ctypes.c_double(et), ctypes.c_double(sigma), -1, nfeatures, max_kp, kp.ctypes.data_as(fp), desc.ctypes.data_as(fp), ctypes.byref(n))
         assert rc == 0, "emulated sift_detect_impl returned %d" % rc
         return kp[:n.value, :5].copy(), kp[:n.value, 5].copy().view(np.int32), desc[:n.value].copy()
     return run
@@ -364,3 +364,8 @@ def test_emulated_sift_front_end_vs_port(sift_emu, port, rng):
     assert len(gk) == len(kp) and len(kp) > 100
     assert np.array_equal(gk, kp) and np.array_equal(go, octv), "keypoints"
     assert np.array_equal(gd, port.sift_descriptors_from_pyramid(G, kp, octv)), "descriptors"
+    # nfeatures: the strongest responses, ties included -- the same SET as the port's (the order after nth_element / partition is the library's)
+    bk, bo, bd = sift_emu(G, D, nfeatures=50)
+    pk, po = port.sift_detect_from_pyramid(G, D, nfeatures=50)
+    assert 50 <= len(bk) == len(pk) and sorted(map(tuple, bk.tolist())) == sorted(map(tuple, pk.tolist()))
+    assert bk[:, 4].min() >= np.sort(kp[:, 4])[-50]
