@@ -473,12 +473,12 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, blockSize=
 
 
 def sift_detectAndCompute(gray, nfeatures=0, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, max_keypoints=200000,
-                          with_descriptors=True, stream=None):
-    """cv::SIFT::create(nfeatures, nOctaveLayers, contrastThreshold, edgeThreshold, sigma, enable_precise_upscale=True)->detectAndCompute(gray) for one
+                          with_descriptors=True, stream=None, enable_precise_upscale=True):
+    """cv::SIFT::create(nfeatures, nOctaveLayers, contrastThreshold, edgeThreshold, sigma, enable_precise_upscale)->detectAndCompute(gray) for one
     (H,W) CV_8U frame: pyramid, extrema, refinement, orientation and descriptors all on the device.
     Returns (keypoints[n,5] = x, y, size, angle, response; octave[n] int32; descriptors[n,128] float32 or None) as numpy arrays."""
     assert gray.dim() == 2, "one frame at a time"
-    G, D, dims = sift_pyramid(gray, nOctaveLayers, sigma, True, True, stream)
+    G, D, dims = sift_pyramid(gray, nOctaveLayers, sigma, 1 if enable_precise_upscale else 2, True, stream)
     dims32 = np.ascontiguousarray(dims, np.int32).reshape(-1)
     kp = np.zeros((max_keypoints, 6), np.float32)
     desc = np.zeros((max_keypoints, 128), np.float32) if with_descriptors else None
@@ -553,7 +553,7 @@ def sift_pyramid(gray, nOctaveLayers=3, sigma=1.6, upscale=True, with_dog=True, 
     dstride = (de + 3) & ~3
     G = torch.empty((frames, gstride), dtype=torch.float32, device=gray.device)
     D = torch.empty((frames, dstride), dtype=torch.float32, device=gray.device) if with_dog else None
-    _check(lib().b200cv_sift_pyramid(ctypes.byref(ms), int(nOctaveLayers), ctypes.c_double(sigma), int(bool(upscale)),
+    _check(lib().b200cv_sift_pyramid(ctypes.byref(ms), int(nOctaveLayers), ctypes.c_double(sigma), int(upscale),      # 2: SIFT::create's default first octave
                                      ctypes.c_void_p(G.data_ptr()), ctypes.c_size_t(gstride),
                                      ctypes.c_void_p(D.data_ptr() if with_dog else 0), ctypes.c_size_t(dstride), _stream_ptr(stream)), "sift_pyramid")
     return G, D, dims

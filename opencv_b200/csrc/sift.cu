@@ -92,7 +92,9 @@ extern "C" int b200cv_sift_pyramid(const b200cvMat* src, int n_layers, double si
         float sig_diff = sqrtf(fmaxf(fsigma * fsigma - 0.5f * 0.5f * 4, 0.01f));
         b200cvMat dbl = level(tmp, tmp_frame, gray_elems, 2 * W, 2 * H);
         const double Mh[6] = {0.5, 0, 0, 0, 0.5, 0};
-        rc = b200cv_warp_affine(&gray, &dbl, Mh, B200CV_INTER_LINEAR | B200CV_WARP_INVERSE_MAP, B200CV_BORDER_REFLECT, nullptr, stream);
+        // upscale == 2: SIFT::create's default, enable_precise_upscale = false -> cv::resize(INTER_LINEAR) (sift.dispatch.cpp:203-208)
+        if (upscale == 2) rc = b200cv_resize(&gray, &dbl, B200CV_INTER_LINEAR, stream);
+        else rc = b200cv_warp_affine(&gray, &dbl, Mh, B200CV_INTER_LINEAR | B200CV_WARP_INVERSE_MAP, B200CV_BORDER_REFLECT, nullptr, stream);
         if (!rc) rc = gaussian_blur_impl(&dbl, &g00, 0, 0, sig_diff, sig_diff, B200CV_BORDER_REFLECT_101, stream, nullptr);
     } else {
         float sig_diff = sqrtf(fmaxf(fsigma * fsigma - 0.5f * 0.5f, 0.01f));

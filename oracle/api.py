@@ -333,12 +333,13 @@ class Oracle:
         h, w = gray.shape
         ge, de, no = sz(0), sz(0), ctypes.c_int(0)
         f = self.fn("sift_pyramid")
-        self._ok(f(_p(gray), sz(gray.strides[0]), w, h, int(nOctaveLayers), dbl(sigma), int(bool(upscale)), None, ctypes.byref(ge),
+        upscale = int(upscale)               # True / 1: precise first octave (warpAffine); 2: SIFT::create's default (resize); 0: no upscaling
+        self._ok(f(_p(gray), sz(gray.strides[0]), w, h, int(nOctaveLayers), dbl(sigma), upscale, None, ctypes.byref(ge),
                    None, ctypes.byref(de), ctypes.byref(no), None), "sift_pyramid(query)")
         G = np.zeros(ge.value, np.float32)
         D = np.zeros(de.value, np.float32)
         dims = np.zeros(2 * no.value, np.int32)
-        self._ok(f(_p(gray), sz(gray.strides[0]), w, h, int(nOctaveLayers), dbl(sigma), int(bool(upscale)), _p(G), ctypes.byref(ge),
+        self._ok(f(_p(gray), sz(gray.strides[0]), w, h, int(nOctaveLayers), dbl(sigma), upscale, _p(G), ctypes.byref(ge),
                    _p(D), ctypes.byref(de), ctypes.byref(no), _p(dims)), "sift_pyramid")
         return unpack_pyramid(G, D, dims, no.value, nOctaveLayers)
 

@@ -169,7 +169,8 @@ PORT_API int port_sift_pyramid(const void* gray, size_t step, int w, int h, int 
         float sd = sqrtf(fmaxf(fs * fs - 0.5f * 0.5f * 4, 0.01f));
         float* dbl = (float*)malloc(sizeof(float) * (size_t)bw * bh);
         const double Mh[6] = {0.5, 0, 0, 0, 0.5, 0}, zero[4] = {0, 0, 0, 0};
-        port_warp_affine(gf, (size_t)w * 4, w, h, dbl, (size_t)bw * 4, bw, bh, F32, Mh, 1 | 16, PB_REFLECT, zero);
+        if (upscale == 2) port_resize(gf, (size_t)w * 4, w, h, dbl, (size_t)bw * 4, bw, bh, F32, 1);      /* enable_precise_upscale = false: cv::resize LINEAR */
+        else port_warp_affine(gf, (size_t)w * 4, w, h, dbl, (size_t)bw * 4, bw, bh, F32, Mh, 1 | 16, PB_REFLECT, zero);
         port_gaussian_blur(dbl, (size_t)bw * 4, G, (size_t)bw * 4, bw, bh, F32, 0, 0, sd, sd, PB_REFLECT_101);
         free(dbl);
     } else {

@@ -341,7 +341,7 @@ API int ref_sift_pyramid(const void* gray, size_t step, int w, int h, int nOctav
     Ptr<SIFT> sp = SIFT::create(0, nOctaveLayers, 0.04, 10, sigma);
     SIFT_Impl* impl = dynamic_cast<SIFT_Impl*>(sp.get());
     CV_Assert(impl);
-    Mat base = createInitialImage(image, firstOctave < 0, (float)sigma, true);
+    Mat base = createInitialImage(image, firstOctave < 0, (float)sigma, firstOctave_upscale != 2);   // 2: SIFT::create's default (resize), 1: precise (warpAffine)
     int nOctaves = cvRound(std::log((double)std::min(base.cols, base.rows)) / std::log(2.) - 2) - firstOctave;
     // NB: the expression above mirrors sift.dispatch.cpp:538 (actualNOctaves == 0 branch)
     std::vector<Mat> gpyr, dogpyr;

@@ -42,6 +42,21 @@ def match(a, b, tol_xy, tol_angle):
     return pairs
 
 
+def test_sift_default_first_octave(cvb, ref, rng):
+    """enable_precise_upscale = false (SIFT::create's default): the first octave comes from cv::resize LINEAR"""
+    from oracle.api import unpack_pyramid
+    from util import assert_close, cpu
+    img = structured(rng, 240, 320)
+    wg, wd = ref.sift_pyramid(img, 3, 1.6, 2)
+    G, D, dims = cvb.sift_pyramid(gpu(img), 3, 1.6, 2)
+    gg, gd = unpack_pyramid(cpu(G)[0], cpu(D)[0], dims.reshape(-1), len(dims), 3)
+    for o in range(len(wg)):
+        assert_close(gg[o][5], wg[o][5], atol=1e-4, what="default first octave: gauss o=%d" % o)
+    kr, octr, dr = ref.sift_detect_and_compute(img, precise_upscale=False)
+    kg, octg, dg = cvb.sift_detectAndCompute(gpu(img), enable_precise_upscale=False)
+    assert abs(len(kg) - len(kr)) <= max(5, len(kr) // 50) and len(match(kr, kg, 1e-2, 0.1)) >= 0.97 * len(kr)
+
+
 @pytest.mark.parametrize("size", [(240, 320), (480, 640), (1080, 1920)])
 def test_sift_detect_and_compute(cvb, ref, rng, size):
     img = structured(rng, *size)

@@ -325,6 +325,22 @@ def match_keypoints(a, b, tol_xy=1e-3, tol_angle=1e-2):
     return hit
 
 
+def test_port_sift_pyramid_default_first_octave(ref, port, rng):
+    """upscale = 2: the first octave of SIFT::create's default (enable_precise_upscale = false: cv::resize LINEAR instead of warpAffine)"""
+    img = _sift_test_image(rng, 120, 160)
+    rg, rd = ref.sift_pyramid(img, 3, 1.6, 2)
+    pg, pd = port.sift_pyramid(img, 3, 1.6, 2)
+    assert len(rg) == len(pg)
+    for o in range(len(rg)):
+        for a, b in zip(rg[o], pg[o]):
+            assert_close(b, a, atol=1e-4, what="gauss octave %d" % o)
+    assert not np.array_equal(rg[0][0], ref.sift_pyramid(img, 3, 1.6, 1)[0][0][0]), "the two first octaves differ"
+    # and the reference's default detector sits on exactly this pyramid
+    kr, octr, _ = ref.sift_detect_and_compute(img, precise_upscale=False)
+    kp, octp = port.sift_detect_from_pyramid(rg, rd)
+    assert abs(len(kp) - len(kr)) <= max(3, len(kr) // 100) and match_keypoints(kr, kp) >= 0.99 * len(kr)
+
+
 def test_port_sift_detector_and_descriptors_vs_reference(ref, port, rng):
     """scale-space extrema + refinement + orientation + descriptors, restated; fed the reference's own pyramids so that only
     this stage is compared.  The reference's SIFT objects are FMA-contracted AVX2 / AVX-512 builds with OpenCV's approximate exp / atan2: the
