@@ -209,10 +209,12 @@ B200CV_API int b200cv_good_features_to_track(const b200cvMat* src, float* corner
 /* SIFT Gaussian pyramid + DoG (features2d/src/sift.dispatch.cpp:176-310).
  * src: 8UC1 batch.  gauss / dog: device float buffers, per frame packed image after image, octave-major
  * (n_octaves*(n_layers+3) Gaussian images, n_octaves*(n_layers+2) DoG images); per-frame strides in floats.
- * Query sizes first with b200cv_sift_pyramid_layout. dog may be NULL (Gaussian only). */
+ * Query sizes first with b200cv_sift_pyramid_layout. dog may be NULL (Gaussian only).
+ * upscale: 0 = first octave at the image size; 1 = doubled with the precise up-scaling (SIFT::create(..., enable_precise_upscale = true):
+ * warpAffine, sift.dispatch.cpp:196-202); 2 = doubled as SIFT::create's default does it (cv::resize INTER_LINEAR, :203-208). */
 B200CV_API int b200cv_sift_pyramid_layout(int width, int height, int n_octave_layers, int upscale,
                                           int* n_octaves, size_t* gauss_elems, size_t* dog_elems, int* dims /*2*n_octaves or NULL*/);
-/* the SIFT front end after the pyramid (cv::SIFT::detectAndCompute, sift.dispatch.cpp:501-580, without mask / nfeatures): scale-space extrema,
+/* the SIFT front end after the pyramid (cv::SIFT::detectAndCompute, sift.dispatch.cpp:501-580, without a mask): scale-space extrema,
  * sub-pixel refinement, orientation assignment, duplicate removal, first-octave rescaling and, if descriptors != NULL, the 128-float
  * descriptors.  gauss / dog: DEVICE pointers to ONE frame's packed pyramids as b200cv_sift_pyramid writes them; dims: the per-octave (w, h)
  * table of b200cv_sift_pyramid_layout (host); keypoints: HOST, 6 floats each (x, y, size, angle, response, packed octave as int bits);
