@@ -85,7 +85,7 @@ public:
     {
         if (data && r == rows && c == cols && t == type_ && nframes == frames) return;
         release();
-        size_t es = (size_t)B200CV_CN(t) * (B200CV_DEPTH(t) <= 1 ? 1 : B200CV_DEPTH(t) <= 3 ? 2 : 4);
+        size_t es = (size_t)B200CV_CN(t) * (B200CV_DEPTH(t) <= 1 ? 1 : B200CV_DEPTH(t) <= 3 ? 2 : B200CV_DEPTH(t) == 6 ? 8 : 4);
         void* p = nullptr;
         check(b200cv_malloc_pitch(&p, &step, (size_t)c * es, (size_t)r * nframes), "GpuMat::create");
         own_.reset((unsigned char*)p, [](unsigned char* q) { b200cv_free(q); });
@@ -127,6 +127,16 @@ inline void Sobel(const GpuMat& src, GpuMat& dst, int ddepth, int dx, int dy, in
                   Stream& s = Stream::Null())
 { B200CV_DST(dst, src, makeType(ddepth < 0 ? B200CV_DEPTH(src.type()) : ddepth, src.channels())); b200cvMat a = src.desc(), b = dst.desc();
   check(b200cv_sobel(&a, &b, dx, dy, ksize, scale, delta, borderType, s.cudaPtr()), "Sobel"); }
+// cv::integral (8UC1 -> 32SC1 sum of (rows+1) x (cols+1); optional 64FC1 sum of squares) and cv::cvtColorTwoPlane (NV12 / NV21, separate planes)
+inline void integral(const GpuMat& src, GpuMat& sum, Stream& s = Stream::Null())
+{ sum.create(src.rows + 1, src.cols + 1, makeType(B200CV_32S, 1), src.frames); b200cvMat a = src.desc(), b = sum.desc();
+  check(b200cv_integral(&a, &b, nullptr, s.cudaPtr()), "integral"); }
+inline void integral(const GpuMat& src, GpuMat& sum, GpuMat& sqsum, Stream& s = Stream::Null())
+{ sum.create(src.rows + 1, src.cols + 1, makeType(B200CV_32S, 1), src.frames); sqsum.create(src.rows + 1, src.cols + 1, makeType(B200CV_64F, 1), src.frames);
+  b200cvMat a = src.desc(), b = sum.desc(), q = sqsum.desc(); check(b200cv_integral(&a, &b, &q, s.cudaPtr()), "integral"); }
+inline void cvtColorTwoPlane(const GpuMat& src1, const GpuMat& src2, GpuMat& dst, int code, Stream& s = Stream::Null())
+{ dst.create(src1.rows, src1.cols, makeType(B200CV_8U, code >= 94 ? 4 : 3), src1.frames); b200cvMat y = src1.desc(), uv = src2.desc(), d = dst.desc();
+  check(b200cv_cvt_color_two_plane(&y, &uv, &d, code, s.cudaPtr()), "cvtColorTwoPlane"); }
 // cv::boxFilter / cv::blur (imgproc.hpp:1603, :1659)
 inline void boxFilter(const GpuMat& src, GpuMat& dst, int ddepth, Size ksize, Point anchor = Point(-1, -1), bool normalize = true, int borderType = BORDER_DEFAULT,
                       Stream& s = Stream::Null())
