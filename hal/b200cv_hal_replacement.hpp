@@ -51,6 +51,10 @@
 #define cv_hal_cvtOnePlaneBGRtoYUV b200cv_hal_cvtOnePlaneBGRtoYUV
 #undef cv_hal_integral
 #define cv_hal_integral b200cv_hal_integral
+#undef cv_hal_cvtBGRtoLab
+#define cv_hal_cvtBGRtoLab b200cv_hal_cvtBGRtoLab
+#undef cv_hal_cvtLabtoBGR
+#define cv_hal_cvtLabtoBGR b200cv_hal_cvtLabtoBGR
 #undef cv_hal_boxFilter
 #define cv_hal_boxFilter b200cv_hal_boxFilter
 #undef cv_hal_cvtBGRtoBGR

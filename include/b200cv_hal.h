@@ -95,6 +95,11 @@ B200CV_API int b200cv_hal_cvtBGRtoHSV(const b200cv_uchar* src_data, size_t src_s
                                       int depth, int scn, bool swapBlue, bool isFullRange, bool isHSV);
 B200CV_API int b200cv_hal_cvtHSVtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                       int depth, int dcn, bool swapBlue, bool isFullRange, bool isHSV);
+/* hal_ni_cvtBGRtoLab / hal_ni_cvtLabtoBGR (hal_replacement.hpp:630, :647): 8-bit Lab only (isLab; Luv and float data are declined) */
+B200CV_API int b200cv_hal_cvtBGRtoLab(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
+                                      int depth, int scn, bool swapBlue, bool isLab, bool srgb);
+B200CV_API int b200cv_hal_cvtLabtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
+                                      int depth, int dcn, bool swapBlue, bool isLab, bool srgb);
 /* subsampled YUV wire formats: hal_ni_cvtTwoPlaneYUVtoBGR :664 (NV12 uIdx 0 / NV21 uIdx 1, one buffer), cvtThreePlaneYUVtoBGR :763
  * (IYUV uIdx 0 / YV12 uIdx 1), cvtBGRtoThreePlaneYUV :797 (IYUV uIdx 1 / YV12 uIdx 2: color.hpp:162-176), cvtOnePlaneYUVtoBGR :833
  * (YUY2 uIdx 0 ycn 0, YVYU uIdx 1 ycn 0, UYVY uIdx 0 ycn 1) */

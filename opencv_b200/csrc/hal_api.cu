@@ -350,6 +350,17 @@ static int cvt(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, 
     return b200cv_host_cvt_color(&s, &d, code);
 }
 
+extern "C" int b200cv_hal_cvtBGRtoLab(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, bool swapBlue, bool isLab, bool srgb)
+{
+    if (!isLab || depth != B200CV_8U) return B200CV_NOT_IMPLEMENTED;      // Luv, float Lab: not on the device path
+    return cvt(src, sstep, dst, dstep, w, h, depth, scn, 3, srgb ? (swapBlue ? 45 : 44) : (swapBlue ? 75 : 74));
+}
+extern "C" int b200cv_hal_cvtLabtoBGR(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int dcn, bool swapBlue, bool isLab, bool srgb)
+{
+    if (!isLab || depth != B200CV_8U) return B200CV_NOT_IMPLEMENTED;
+    return cvt(src, sstep, dst, dstep, w, h, depth, 3, dcn, srgb ? (swapBlue ? 57 : 56) : (swapBlue ? 79 : 78));
+}
+
 // subsampled YUV wire formats (cvtcolor_yuv.cu); source and destination differ in size
 static int cvt_yuv(const uchar* src, size_t sstep, int sw, int sh, int scn, uchar* dst, size_t dstep, int dw, int dh, int dcn, int code)
 {

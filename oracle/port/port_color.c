@@ -263,3 +263,154 @@ PORT_API int port_cvt_color_yuv(const void* src_, size_t sstep, int sw, int sh, 
     }
     return -1;
 }
+
+/* ---- 8-bit BGR / RGB -> Lab (color_lab.cpp:1573-1890, RGB2Lab_b; tables :1225-1280): all integer after the two tables ------------------
+ *   g = gamma table (sRGB curve at 255 * 8 resolution, or linear), X/Y/Z = (R*C0 + G*C1 + B*C2 + 2^11) >> 12 with the XYZ matrix divided by
+ *   the white point, f = cube-root table at 2^15 scale, L = (296 f(Y) - Lshift' ) >> 15, a = (500 (fX - fY) + ...) >> 15, b likewise.
+ * The tables come from softfloat pow / cbrt in the reference; here from libm (double pow -> float, cbrtf): pinned by running the whole 2^24
+ * colour cube against the reference (tests/test_oracle.py). */
+/* cv::cbrt(softfloat) (core/src/softfloat.cpp:3897-3930): exponent split by three, a quartic rational polynomial of the mantissa in double
+ * (IEEE operations, no fusing), the result's mantissa TRUNCATED to 23 bits -- not the correctly rounded cbrtf, and the table needs its bits */
+static float soft_cbrtf(float x)
+{
+    uint32_t v; memcpy(&v, &x, 4);
+    if ((v & 0x7fffffffu) == 0) return 0.f;
+    const uint32_t s = v >> 31;
+    int ex = (int)((v >> 23) & 255) - 127, shx = ex % 3;
+    shx -= shx >= 0 ? 3 : 0;
+    ex = (ex - shx) / 3 - 1;
+    uint64_t fv = ((uint64_t)(shx + 1023) << 52) | ((uint64_t)(v & 0x7fffffu) << 29);
+    double fr; memcpy(&fr, &fv, 8);
+    static const uint64_t K[9] = {0x4046a09e6653ba70ull, 0x406808f46c6116e0ull, 0x405dca97439cae14ull, 0x402add70d2827500ull, 0x3fc4f15f83f55d2dull,
+                                  0x402d9e20660edb21ull, 0x4062ff15c0285815ull, 0x406510d06a8112ceull, 0x4040fecbc9e2c375ull};
+    double A[9]; memcpy(A, K, sizeof(A));
+    volatile double num = A[0] * fr; num = num + A[1]; num = num * fr; num = num + A[2]; num = num * fr; num = num + A[3]; num = num * fr; num = num + A[4];
+    volatile double den = A[5] * fr; den = den + A[6]; den = den * fr; den = den + A[7]; den = den * fr; den = den + A[8]; den = den * fr; den = den + 1.0;
+    double q = num / den;
+    uint64_t r; memcpy(&r, &q, 8);
+    uint32_t y = (s << 31) | ((uint32_t)(ex + 127) << 23) | (uint32_t)((r & 0xFFFFFFFFFFFFFull) >> 29);
+    float out; memcpy(&out, &y, 4);
+    return out;
+}
+
+static unsigned short g_lab_gamma[256], g_lab_lin[256], g_lab_cbrt[256 * 3 / 2 * 8];
+static int g_lab_ready = 0;
+static void lab_tabs(void)
+{
+    if (g_lab_ready) return;
+    const float intScale = 255 * 8;
+    for (int i = 0; i < 256; i++) {
+        float x = (float)i / 255.f;
+        double xd = x;
+        float g = (float)(xd <= 809. / 20000. ? xd / (323. / 25.) : pow((xd + 11. / 200.) / (1. + 11. / 200.), 12. / 5.));
+        g_lab_gamma[i] = (unsigned short)lrintf(intScale * g);
+        g_lab_lin[i] = (unsigned short)(i * 8);
+    }
+    const float cbScale = 1.f / (255.f * 8), lthresh = 216.f / 24389.f, lscale = 841.f / 108.f, lbias = 16.f / 116.f, lshift2 = 32768.f;
+    for (int i = 0; i < 256 * 3 / 2 * 8; i++) {
+        float x = cbScale * (float)i;
+        float f = x < lthresh ? fmaf(x, lscale, lbias) : soft_cbrtf(x);
+        g_lab_cbrt[i] = (unsigned short)lrintf(lshift2 * f);
+    }
+    g_lab_ready = 1;
+}
+
+PORT_API int port_cvt_color_lab(const void* src_, size_t sstep, void* dst_, size_t dstep, int w, int h, int scn, int code)
+{
+    /* 44 BGR2Lab, 45 RGB2Lab (sRGB gamma); 74 LBGR2Lab, 75 LRGB2Lab (linear) */
+    if ((code != 44 && code != 45 && code != 74 && code != 75) || (scn != 3 && scn != 4)) return -1;
+    lab_tabs();
+    const int bidx = (code == 44 || code == 74) ? 0 : 2, srgb = code < 70;
+    const unsigned short* tab = srgb ? g_lab_gamma : g_lab_lin;
+    static const double M[9] = {0.412453, 0.357580, 0.180423, 0.212671, 0.715160, 0.072169, 0.019334, 0.119193, 0.950227};
+    static const double wp[3] = {0.950456, 1., 1.088754};
+    int C[9];
+    for (int i = 0; i < 3; i++) {
+        C[i * 3 + (bidx ^ 2)] = port_round(4096. * M[i * 3] / wp[i]);
+        C[i * 3 + 1] = port_round(4096. * M[i * 3 + 1] / wp[i]);
+        C[i * 3 + bidx] = port_round(4096. * M[i * 3 + 2] / wp[i]);
+    }
+    const int Lscale = (116 * 255 + 50) / 100, Lshift = -((16 * 255 * (1 << 15) + 50) / 100);
+    for (int y = 0; y < h; y++) {
+        const uchar* s = (const uchar*)src_ + (size_t)y * sstep; uchar* d = (uchar*)dst_ + (size_t)y * dstep;
+        for (int x = 0; x < w; x++, s += scn, d += 3) {
+            int R = tab[s[0]], G = tab[s[1]], B = tab[s[2]];
+            int fX = g_lab_cbrt[(R * C[0] + G * C[1] + B * C[2] + (1 << 11)) >> 12];
+            int fY = g_lab_cbrt[(R * C[3] + G * C[4] + B * C[5] + (1 << 11)) >> 12];
+            int fZ = g_lab_cbrt[(R * C[6] + G * C[7] + B * C[8] + (1 << 11)) >> 12];
+            int L = (Lscale * fY + Lshift + (1 << 14)) >> 15;
+            int a = (500 * (fX - fY) + 128 * (1 << 15) + (1 << 14)) >> 15;
+            int b = (200 * (fY - fZ) + 128 * (1 << 15) + (1 << 14)) >> 15;
+            d[0] = port_sat_u8i(L); d[1] = port_sat_u8i(a); d[2] = port_sat_u8i(b);
+        }
+    }
+    return 0;
+}
+
+/* ---- 8-bit Lab -> BGR / RGB (Lab2RGBinteger, color_lab.cpp:2399-2700; tables :1263-1308, :1086-1107): integer after the tables ---------
+ *   (y, ify) = LabToYF_b[L];  x = abToXZ_b[ify + adiv(a)], z = abToXZ_b[ify - bdiv(b)]  (piecewise linear / cubic in 14-bit fixed point);
+ *   rgb = (C * xyz + 2^13) >> 14 clipped to [0, 4095], then the inverse-gamma table (sRGB) or (v * 255) >> 12 (linear). */
+static unsigned short g_lab_yf[512], g_lab_invgamma[4096];
+static int* g_lab_abxz = 0;
+static void lab_inv_tabs(void)
+{
+    if (g_lab_abxz) return;
+    const int BASE = 1 << 14;
+    for (int i = 0; i < 256; i++) {
+        int yv, ify;
+        if (i <= 20) {
+            yv = (int)lrintf((float)(i * BASE * 20 * 9) / (float)(17 * 29 * 29 * 29));
+            ify = (int)lrintf((float)BASE * ((float)16 / (float)116 + (float)(i * 5) / (float)(3 * 17 * 29)));
+        } else {
+            float fy = (float)(i * 100 * BASE) / (float)(255 * 116) + (float)(16 * BASE) / (float)116;
+            ify = (int)lrintf(fy);
+            volatile float f2 = fy * fy; volatile float f3 = f2 * fy;
+            yv = (int)lrintf(f3 / (float)(BASE * BASE));
+        }
+        g_lab_yf[2 * i] = (unsigned short)yv; g_lab_yf[2 * i + 1] = (unsigned short)ify;
+    }
+    for (int i = 0; i < 4096; i++) {
+        float x = (1.f / 4096.f) * (float)i;
+        double xd = x;
+        float ig = (float)(xd <= 7827. / 2500000. ? xd * (323. / 25.) : pow(xd, 1. / (12. / 5.)) * (1. + 11. / 200.) - 11. / 200.);
+        g_lab_invgamma[i] = (unsigned short)lrintf(255.f * ig);
+    }
+    const int minAB = -8145, n = BASE * 9 / 4;
+    int* t = (int*)malloc(sizeof(int) * (size_t)n);
+    for (int i = minAB; i < n + minAB; i++)
+        t[i - minAB] = i <= 3390 ? i * 108 / 841 - BASE * 16 / 116 * 108 / 841 : i * i / BASE * i / BASE;
+    g_lab_abxz = t;
+}
+
+PORT_API int port_cvt_color_lab_inv(const void* src_, size_t sstep, void* dst_, size_t dstep, int w, int h, int dcn, int code)
+{
+    /* 56 Lab2BGR, 57 Lab2RGB (sRGB); 78 Lab2LBGR, 79 Lab2LRGB (linear) */
+    if ((code != 56 && code != 57 && code != 78 && code != 79) || (dcn != 3 && dcn != 4)) return -1;
+    lab_inv_tabs();
+    const int bidx = (code == 56 || code == 78) ? 0 : 2, srgb = code < 70, BASE = 1 << 14, minAB = -8145;
+    static const double M[9] = {3.240479, -1.53715, -0.498535, -0.969256, 1.875991, 0.041556, 0.055648, -0.204043, 1.057311};
+    static const double wp[3] = {0.950456, 1., 1.088754};
+    int C[9];
+    for (int i = 0; i < 3; i++) {
+        C[i + bidx * 3] = port_round(4096. * M[i] * wp[i]);
+        C[i + 3] = port_round(4096. * M[i + 3] * wp[i]);
+        C[i + (bidx ^ 2) * 3] = port_round(4096. * M[i + 6] * wp[i]);
+    }
+    for (int y = 0; y < h; y++) {
+        const uchar* s = (const uchar*)src_ + (size_t)y * sstep; uchar* d = (uchar*)dst_ + (size_t)y * dstep;
+        for (int x = 0; x < w; x++, s += 3, d += dcn) {
+            const int LL = s[0], aa = s[1], bb = s[2];
+            const int yv = g_lab_yf[LL * 2], ify = g_lab_yf[LL * 2 + 1];
+            const int adiv = ((5 * aa * 53687 + (1 << 7)) >> 13) - 128 * BASE / 500, bdiv = ((bb * 41943 + (1 << 4)) >> 9) - 128 * BASE / 200 + 1;
+            const int xv = g_lab_abxz[ify + adiv - minAB], zv = g_lab_abxz[ify - bdiv - minAB];
+            int ro = (C[0] * xv + C[1] * yv + C[2] * zv + (1 << 13)) >> 14, go = (C[3] * xv + C[4] * yv + C[5] * zv + (1 << 13)) >> 14,
+                bo = (C[6] * xv + C[7] * yv + C[8] * zv + (1 << 13)) >> 14;
+            ro = ro < 0 ? 0 : ro > 4095 ? 4095 : ro; go = go < 0 ? 0 : go > 4095 ? 4095 : go; bo = bo < 0 ? 0 : bo > 4095 ? 4095 : bo;
+            if (srgb) { ro = g_lab_invgamma[ro]; go = g_lab_invgamma[go]; bo = g_lab_invgamma[bo]; }
+            else { ro = ((ro << 8) - ro) >> 12; go = ((go << 8) - go) >> 12; bo = ((bo << 8) - bo) >> 12; }
+            d[0] = (uchar)(bo > 255 ? 255 : bo); d[1] = (uchar)(go > 255 ? 255 : go); d[2] = (uchar)(ro > 255 ? 255 : ro);   /* rows are placed by blueIdx */
+            if (dcn == 4) d[3] = 255;
+        }
+    }
+    return 0;
+}

@@ -38,6 +38,7 @@ static inline cudaError_t cudaFreeAsync(void* p, cudaStream_t) { free(p); return
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+template <typename T> static inline cudaError_t cudaMemcpyToSymbol(T& sym, const void* src, size_t n) { memcpy(&sym, src, n); return cudaSuccess; }
 static inline int atomicAdd(int* p, int v) { const int old = *p; *p = old + v; return old; }      // threads run one after another
 
 template <typename T> static inline T min(T a, T b) { return b < a ? b : a; }

@@ -369,3 +369,34 @@ def test_emulated_sift_front_end_vs_port(sift_emu, port, rng):
     pk, po = port.sift_detect_from_pyramid(G, D, nfeatures=50)
     assert 50 <= len(bk) == len(pk) and sorted(map(tuple, bk.tolist())) == sorted(map(tuple, pk.tolist()))
     assert bk[:, 4].min() >= np.sort(kp[:, 4])[-50]
+
+
+# ---- BGR / RGB <-> Lab, 8-bit (cvtcolor_lab.cu): host-built tables + per-pixel kernels ----------------------------------------------------
+@pytest.fixture(scope="module")
+def lab_emu():
+    lib = build_emulation("cvtcolor_lab.cu", "int emu_lab(const b200cvMat* s, const b200cvMat* d, int code)",
+                          "    return b200cv::cvt_color_lab(s, d, code, nullptr);")
+    lib.emu_lab.argtypes = [ctypes.POINTER(Mat), ctypes.POINTER(Mat), ctypes.c_int]
+
+    def run(src, code, dcn=3):
+        dst = np.zeros(src.shape[:-1] + (dcn,), np.uint8)
+        ms, md = mat_of(src), mat_of(dst)
+        rc = lib.emu_lab(ctypes.byref(ms), ctypes.byref(md), int(code))
+        assert rc == 0, "emulated cvt_color_lab(code %d) returned %d" % (code, rc)
+        return dst
+    return run
+
+
+def test_emulated_lab_kernels_vs_port(lab_emu, port, rng):
+    """a 1/64 sample of the colour cube (every 4th level of each channel, 262 144 colours, all table regions) plus random data, both directions,
+    sRGB and linear; the port itself equals the reference on all 2^24 colours (tests/test_oracle.py)"""
+    v = np.arange(0, 256, 4, dtype=np.uint8)
+    cube = np.stack(np.meshgrid(v, v, v, indexing="ij"), axis=-1).reshape(512, 512, 3)
+    rnd = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    for img in (cube, rnd):
+        for code in (44, 45, 74, 75, 56, 57, 78, 79):
+            assert np.array_equal(lab_emu(img, code), port.cvtColorLab(img, code)), "Lab code %d" % code
+    bgra = rng.integers(0, 256, (40, 50, 4), dtype=np.uint8)
+    assert np.array_equal(lab_emu(bgra, 44), port.cvtColorLab(np.ascontiguousarray(bgra[:, :, :3]), 44)), "4-channel source"
+    out4 = lab_emu(rnd, 56, dcn=4)
+    assert np.array_equal(out4[:, :, :3], port.cvtColorLab(rnd, 56)) and (out4[:, :, 3] == 255).all()

@@ -141,6 +141,15 @@ def test_port_vs_reference_integral(ref, port, rng):
         assert a[-1, -1] == int(img.sum(dtype=np.int64)) and aq[-1, -1] == float((img.astype(np.int64) ** 2).sum())
 
 
+def test_port_lab_on_the_whole_colour_cube(ref, port):
+    """8-bit BGR / RGB <-> Lab, sRGB and linear: the port (libm pow, softfloat's cbrt restated bit for bit, the reference's integer formulas)
+    equals the reference on ALL 2^24 colours, in both directions"""
+    v = np.arange(1 << 24, dtype=np.uint32)
+    cube = np.stack([v & 255, (v >> 8) & 255, (v >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
+    for code in (44, 45, 74, 75, 56, 57, 78, 79):
+        assert np.array_equal(ref.cvtColor(cube, code, 3), port.cvtColorLab(cube, code)), "Lab code %d" % code
+
+
 def test_port_vs_reference_two_plane(ref, port, rng):
     """cv::cvtColorTwoPlane: the same arithmetic with separate luma / chroma buffers; also equal to cvtColor on the concatenated planes"""
     for (h, w) in [(4, 6), (18, 34), (250, 322)]:

@@ -49,6 +49,8 @@ ops = {
     "lanczos4_8k_to_5k": (lambda: cvb.resize(bgr, (5120, 2880), interpolation=cvb.INTER_LANCZOS4, dst=k5), nbytes(bgr, k5)),
     "linear_exact_8k_to_5k": (lambda: cvb.resize(bgr, (5120, 2880), interpolation=cvb.INTER_LINEAR_EXACT, dst=k5), nbytes(bgr, k5)),
     "nearest_exact_8k_to_5k": (lambda: cvb.resize(bgr, (5120, 2880), interpolation=cvb.INTER_NEAREST_EXACT, dst=k5), nbytes(bgr, k5)),
+    "bgr_to_lab_8k": (lambda: cvb.cvtColor(bgr, cvb.COLOR_BGR2Lab, dst=obgr), nbytes(bgr, obgr)),
+    "lab_to_bgr_8k": (lambda: cvb.cvtColor(bgr, cvb.COLOR_Lab2BGR, dst=obgr), nbytes(bgr, obgr)),
     "integral_4k": (lambda: cvb.integral(u8), nbytes(u8) * 5),
 }
 for name, (fn, nb) in ops.items():
