@@ -231,14 +231,21 @@ __global__ void __launch_bounds__(64) sift_descriptor_kernel(SiftPyr p, int firs
             rbin -= r0; cbin -= c0; obin -= o0;
             if (o0 < 0) o0 += n;
             if (o0 >= n) o0 -= n;
-            const float v_r1 = mag * rbin, v_r0 = mag - v_r1;
-            const float v_rc11 = v_r1 * cbin, v_rc10 = v_r1 - v_rc11, v_rc01 = v_r0 * cbin, v_rc00 = v_r0 - v_rc01;
-            const float v_rco111 = v_rc11 * obin, v_rco110 = v_rc11 - v_rco111, v_rco101 = v_rc10 * obin, v_rco100 = v_rc10 - v_rco101;
-            const float v_rco011 = v_rc01 * obin, v_rco010 = v_rc01 - v_rco011, v_rco001 = v_rc00 * obin, v_rco000 = v_rc00 - v_rco001;
+            // tri-linear split: the upper share of each axis is weight * fraction, the lower share the remainder (sift.simd.hpp:864-882)
             const int idx = ((r0 + 1) * (d + 2) + c0 + 1) * (n + 2) + o0;
-            hist[idx] += v_rco000; hist[idx + 1] += v_rco001; hist[idx + (n + 2)] += v_rco010; hist[idx + (n + 3)] += v_rco011;
-            hist[idx + (d + 2) * (n + 2)] += v_rco100; hist[idx + (d + 2) * (n + 2) + 1] += v_rco101;
-            hist[idx + (d + 3) * (n + 2)] += v_rco110; hist[idx + (d + 3) * (n + 2) + 1] += v_rco111;
+            const float up_r = mag * rbin;
+#pragma unroll
+            for (int ri = 0; ri < 2; ri++) {
+                const float w_r = ri ? up_r : mag - up_r;
+                const float up_c = w_r * cbin;
+#pragma unroll
+                for (int ci = 0; ci < 2; ci++) {
+                    const float w_c = ci ? up_c : w_r - up_c;
+                    const float up_o = w_c * obin;
+                    float* cell = hist + idx + ri * (d + 2) * (n + 2) + ci * (n + 2);
+                    cell[0] += w_c - up_o; cell[1] += up_o;
+                }
+            }
         }
     float nrm2 = 0;
     for (int i = 0; i < d; i++)
