@@ -29,6 +29,14 @@ def test_exact_resizers(cvb, oracle, rng, ssize, dsize, cn):
             assert_exact(got, oracle.resize(img, (dw, dh), interp), "interp %d %s %s -> %s cn=%d" % (interp, img.dtype, ssize, dsize, cn))
 
 
+def test_reference_goldens(cvb):
+    """Resize_Bitexact.Nearest8U (test_resize_bitexact.cpp:190-241) and the Imgproc_resize_area rounding regressions (test_imgwarp.cpp:1285-1317)"""
+    from test_oracle import resize_golden_cases
+    for src, dsize, interp, want, tol in resize_golden_cases():
+        got = cpu(cvb.resize(gpu(src), dsize, interpolation=interp))
+        assert np.abs(got.astype(int) - want.astype(int)).max() <= tol, "interp %d %s -> %s" % (interp, src.shape, dsize)
+
+
 def test_exact_resizers_8k(cvb, ref, rng):
     """BASELINE c3 geometry: 7680x4320 8UC3 -> 5120x2880 and 3840x2160 (LINEAR_EXACT 2 x 2 = the area fast path)"""
     img = rng.integers(0, 256, (4320, 7680, 3), dtype=np.uint8)

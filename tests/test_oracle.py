@@ -272,6 +272,41 @@ def test_port_vs_reference_area_resize(ref, port, rng):
                 assert np.array_equal(ref.resize(img, (dw, dh), 3), port.resize(img, (dw, dh), 3)), "INTER_AREA %s %s -> %s cn=%d" % (img.dtype, (sh, sw), (dh, dw), cn)
 
 
+# the reference's own golden vectors for the exact / area resizers (modules/imgproc/test/test_resize_bitexact.cpp:190-241, Resize_Bitexact.Nearest8U;
+# test_imgwarp.cpp:1285-1317, Imgproc_resize_area.regression_half_round / regression_quarter_round)
+NEAREST_EXACT_GOLDENS = [
+    ([[0, 1, 2, 3, 4, 5]], [[1, 3, 5]]),
+    ([[0, 1, 2, 3, 4]], [[2]]),
+    ([[0, 1, 2, 3, 4]], [[0, 2, 4]]),
+    ([[0, 1, 2, 3, 4]], [[1, 3]]),
+    ([[0, 1, 2, 3, 4], [5, 6, 7, 8, 9], [10, 11, 12, 13, 14]],
+     [[0, 1, 1, 2, 3, 3, 4], [0, 1, 1, 2, 3, 3, 4], [5, 6, 6, 7, 8, 8, 9], [10, 11, 11, 12, 13, 13, 14], [10, 11, 11, 12, 13, 13, 14]]),
+    ([[0, 1, 2], [3, 4, 5]], [[0, 0, 1, 1, 2, 2], [0, 0, 1, 1, 2, 2], [3, 3, 4, 4, 5, 5], [3, 3, 4, 4, 5, 5]]),
+]
+
+
+def resize_golden_cases():
+    """(src, dsize, interpolation, want, max |difference|) -- the goldens above, both orientations, plus the INTER_AREA rounding regressions"""
+    cases = []
+    for s, d in NEAREST_EXACT_GOLDENS:
+        s, d = np.array(s, np.uint8), np.array(d, np.uint8)
+        cases.append((s, (d.shape[1], d.shape[0]), 6, d, 0))
+        cases.append((np.ascontiguousarray(s.T), (d.shape[0], d.shape[1]), 6, np.ascontiguousarray(d.T), 0))
+    i = np.arange(32 * 32)
+    src = (i % 2 + 253 + i // (16 * 32)).astype(np.uint8).reshape(32, 32)
+    j = np.arange(16 * 16)
+    cases.append((src, (16, 16), 3, (254 + j // (16 * 8)).astype(np.uint8).reshape(16, 16), 0))     # check_resize_area(..., 0.5): exact for integers
+    cases.append((src, (8, 8), 3, np.full((8, 8), 254, np.uint8), 0))
+    return cases
+
+
+def test_port_reproduces_the_reference_resize_goldens(port, ref):
+    for src, dsize, interp, want, tol in resize_golden_cases():
+        for o in (port, ref):
+            got = o.resize(src, dsize, interp)
+            assert np.abs(got.astype(int) - want.astype(int)).max() <= tol, "%s interp %d %s -> %s" % (o.kind, interp, src.shape, dsize)
+
+
 def test_port_vs_reference_exact_resizers(ref, port, rng):
     """INTER_LINEAR_EXACT (8.8 fixed point; float data falls back to INTER_LINEAR, 2 x 2 decimation to the INTER_AREA fast path) and
     INTER_NEAREST_EXACT (16.16 pixel-centre coordinates)"""
