@@ -413,3 +413,41 @@ def test_emulated_lab_kernels_vs_port(lab_emu, port, rng):
     assert np.array_equal(lab_emu(bgra, 44), port.cvtColorLab(np.ascontiguousarray(bgra[:, :, :3]), 44)), "4-channel source"
     out4 = lab_emu(rnd, 56, dcn=4)
     assert np.array_equal(out4[:, :, :3], port.cvtColorLab(rnd, 56)) and (out4[:, :, 3] == 255).all()
+
+
+# ---- the one piece of the INTER_AREA enlargement that lives in resize.cu (not emulated as a whole: it uses IDP2A / PRMT): linear_coef() ----------
+def test_emulated_area_mode_weights_in_resize_cu():
+    """extract the device function linear_coef from resize.cu, compile it for the host and compare its area-mode branch with the reference's
+    expressions (resize.cpp:4104-4109, :4158-4163) evaluated in numpy: s = floor(d * scale), f = float((d + 1) - (s + 1) * inv_scale), f <= 0 -> 0,
+    else f - floor(f); and its default branch with f = float((d + 0.5) * scale - 0.5), s = floor(f), f -= s"""
+    os.makedirs(OUT, exist_ok=True)
+    src = open(os.path.join(CSRC, "resize.cu")).read()
+    m = re.search(r"__device__ __forceinline__ void linear_coef\(.*?\n}\n", src, re.S)
+    assert m, "linear_coef not found in resize.cu"
+    fn = m.group(0).replace("bool area_mode = false, double inv_scale = 0.", "bool area_mode, double inv_scale")
+    cpp = os.path.join(OUT, "emu_linear_coef.cpp")
+    so = os.path.join(OUT, "emu_linear_coef.so")
+    with open(cpp, "w") as f:
+        f.write('#include "cuda_emu.h"\nstatic inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }\n' + fn +
+                'extern "C" void emu_linear_coef(int n, double scale, int ssize, int clamp, int area, double inv, int* s, float* fr)\n'
+                "{ for (int d = 0; d < n; d++) linear_coef(d, scale, ssize, s[d], fr[d], clamp != 0, area != 0, inv); }\n")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", os.path.join(ROOT, "tests", "emu"), cpp, "-o", so])
+    lib = ctypes.CDLL(so)
+    for ssize, dsize in [(60, 180), (131, 997), (47, 90), (1, 23), (640, 641), (5, 50)]:
+        inv = dsize / ssize
+        scale = 1.0 / inv
+        s = np.zeros(dsize, np.int32); fr = np.zeros(dsize, np.float32)
+        for clamp in (0, 1):
+            lib.emu_linear_coef(dsize, ctypes.c_double(scale), ssize, clamp, 1, ctypes.c_double(inv), s.ctypes.data_as(ctypes.c_void_p), fr.ctypes.data_as(ctypes.c_void_p))
+            d = np.arange(dsize, dtype=np.float64)
+            ws = np.floor(d * scale).astype(np.int32)
+            wf = ((d + 1) - (ws + 1).astype(np.float64) * inv).astype(np.float32)
+            wf = np.where(wf <= 0, np.float32(0), wf - np.floor(wf)).astype(np.float32)
+            if clamp:
+                lo, hi = ws < 0, ws >= ssize - 1
+                wf = np.where(lo | hi, np.float32(0), wf); ws = np.where(lo, 0, np.where(hi, ssize - 1, ws))
+            assert np.array_equal(s, ws) and np.array_equal(fr, wf), "area-mode weights %d -> %d clamp=%d" % (ssize, dsize, clamp)
+        lib.emu_linear_coef(dsize, ctypes.c_double(scale), ssize, 0, 0, ctypes.c_double(inv), s.ctypes.data_as(ctypes.c_void_p), fr.ctypes.data_as(ctypes.c_void_p))
+        f0 = ((np.arange(dsize, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        s0 = np.floor(f0).astype(np.int32)
+        assert np.array_equal(s, s0) and np.array_equal(fr, (f0 - s0.astype(np.float32)).astype(np.float32)), "default weights %d -> %d" % (ssize, dsize)
