@@ -51,6 +51,10 @@
 #define cv_hal_cvtOnePlaneBGRtoYUV b200cv_hal_cvtOnePlaneBGRtoYUV
 #undef cv_hal_integral
 #define cv_hal_integral b200cv_hal_integral
+#undef cv_hal_cvtBGRtoXYZ
+#define cv_hal_cvtBGRtoXYZ b200cv_hal_cvtBGRtoXYZ
+#undef cv_hal_cvtXYZtoBGR
+#define cv_hal_cvtXYZtoBGR b200cv_hal_cvtXYZtoBGR
 #undef cv_hal_cvtBGRtoLab
 #define cv_hal_cvtBGRtoLab b200cv_hal_cvtBGRtoLab
 #undef cv_hal_cvtLabtoBGR

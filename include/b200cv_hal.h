@@ -95,6 +95,11 @@ B200CV_API int b200cv_hal_cvtBGRtoHSV(const b200cv_uchar* src_data, size_t src_s
                                       int depth, int scn, bool swapBlue, bool isFullRange, bool isHSV);
 B200CV_API int b200cv_hal_cvtHSVtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                       int depth, int dcn, bool swapBlue, bool isFullRange, bool isHSV);
+/* hal_ni_cvtBGRtoXYZ / hal_ni_cvtXYZtoBGR (hal_replacement.hpp:564, :579): 8-bit */
+B200CV_API int b200cv_hal_cvtBGRtoXYZ(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
+                                      int depth, int scn, bool swapBlue);
+B200CV_API int b200cv_hal_cvtXYZtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
+                                      int depth, int dcn, bool swapBlue);
 /* hal_ni_cvtBGRtoLab / hal_ni_cvtLabtoBGR (hal_replacement.hpp:630, :647): 8-bit Lab only (isLab; Luv and float data are declined) */
 B200CV_API int b200cv_hal_cvtBGRtoLab(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                       int depth, int scn, bool swapBlue, bool isLab, bool srgb);

@@ -290,6 +290,10 @@ extern "C" int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int 
     Img s = make_img(src), d = make_img(dst);
     cudaStream_t st = as_stream(stream);
 
+    if (code >= 32 && code <= 35) {                                       // CIE XYZ (cvtcolor_lab.cu)
+        B200_REQUIRE(src->data != dst->data, "cvtColor: in-place is not supported");
+        return cvt_color_xyz(src, dst, code, st);
+    }
     if (code == 44 || code == 45 || code == 74 || code == 75 || code == 56 || code == 57 || code == 78 || code == 79) {     // CIE Lab (cvtcolor_lab.cu)
         B200_REQUIRE(src->data != dst->data, "cvtColor: in-place is not supported");
         return cvt_color_lab(src, dst, code, st);

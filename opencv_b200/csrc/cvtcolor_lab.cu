@@ -13,6 +13,7 @@
 // One thread per pixel, table lookups through L1 / L2 (the tables total 165 KB): streaming, HBM-bound (6 bytes per pixel).
 #include <math.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 #include "common.cuh"
 
@@ -152,7 +153,46 @@ __global__ void __launch_bounds__(256) lab_to_bgr_kernel(Img src, Img dst, int W
     if constexpr (DCN == 4) d[3] = 255;
 }
 
+// BGR / RGB <-> CIE XYZ (RGB2XYZ_i<uchar> color_lab.cpp:250-330, XYZ2RGB_i<uchar> :650-730): out = saturate((M * in + 2^11) >> 12), 12-bit integer matrices
+template <int SCN, int DCN>
+__global__ void __launch_bounds__(256) xyz_matrix_kernel(Img src, Img dst, int W, LabCoef k)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, f = blockIdx.z;
+    if (x >= W) return;
+    const uchar* s = src.row<uchar>(f, y) + (size_t)x * SCN;
+    const int s0 = s[0], s1 = s[1], s2 = s[2];
+    uchar* d = dst.row<uchar>(f, y) + (size_t)x * DCN;
+#pragma unroll
+    for (int r = 0; r < 3; r++) d[r] = sat_u8((s0 * k.c[3 * r] + s1 * k.c[3 * r + 1] + s2 * k.c[3 * r + 2] + (1 << 11)) >> 12);
+    if constexpr (DCN == 4) d[3] = 255;
+}
+
 }  // namespace
+
+// codes 32 BGR2XYZ, 33 RGB2XYZ, 34 XYZ2BGR, 35 XYZ2RGB (8-bit)
+int cvt_color_xyz(const b200cvMat* src, const b200cvMat* dst, int code, cudaStream_t st)
+{
+    const int scn = B200CV_CN(src->type), dcn = B200CV_CN(dst->type);
+    const bool to_xyz = code == 32 || code == 33, bgr = code == 32 || code == 34;
+    B200_REQUIRE(to_xyz ? ((scn == 3 || scn == 4) && dcn == 3) : (scn == 3 && (dcn == 3 || dcn == 4)), "channel count does not match the colour code");
+    static const int fwd[9] = {1689, 1465, 739, 871, 2929, 296, 79, 488, 3892}, inv[9] = {13273, -6296, -2042, -3970, 7684, 170, 228, -836, 4331};   // color_lab.cpp:132-144
+    LabCoef k;
+    for (int i = 0; i < 9; i++) k.c[i] = to_xyz ? fwd[i] : inv[i];
+    if (bgr) {
+        if (to_xyz) for (int r = 0; r < 3; r++) std::swap(k.c[3 * r], k.c[3 * r + 2]);       // BGR source: swap the matrix columns
+        else for (int c = 0; c < 3; c++) std::swap(k.c[c], k.c[6 + c]);                     // BGR destination: swap the rows
+    }
+    Img s = make_img(src), d = make_img(dst);
+    if (s.rows >= 65536 || s.frames >= 65536) return B200CV_NOT_IMPLEMENTED;
+    const dim3 block(256);
+    const dim3 grid(div_up((unsigned)src->cols, 256), (unsigned)src->rows, (unsigned)s.frames);
+    if (scn == 3 && dcn == 3) xyz_matrix_kernel<3, 3><<<grid, block, 0, st>>>(s, d, src->cols, k);
+    else if (scn == 4) xyz_matrix_kernel<4, 3><<<grid, block, 0, st>>>(s, d, src->cols, k);
+    else xyz_matrix_kernel<3, 4><<<grid, block, 0, st>>>(s, d, src->cols, k);
+    B200_LAUNCH_CHECK();
+    return B200CV_OK;
+}
 
 // called by b200cv_cvt_color for codes 44, 45, 74, 75, 56, 57, 78, 79 (8-bit matrices of equal size and batch already checked)
 int cvt_color_lab(const b200cvMat* src, const b200cvMat* dst, int code, cudaStream_t st)

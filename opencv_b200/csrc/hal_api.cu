@@ -350,6 +350,10 @@ static int cvt(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, 
     return b200cv_host_cvt_color(&s, &d, code);
 }
 
+extern "C" int b200cv_hal_cvtBGRtoXYZ(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, bool swapBlue)
+{ return cvt(src, sstep, dst, dstep, w, h, depth, scn, 3, swapBlue ? 33 : 32); }
+extern "C" int b200cv_hal_cvtXYZtoBGR(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int dcn, bool swapBlue)
+{ return cvt(src, sstep, dst, dstep, w, h, depth, 3, dcn, swapBlue ? 35 : 34); }
 extern "C" int b200cv_hal_cvtBGRtoLab(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, bool swapBlue, bool isLab, bool srgb)
 {
     if (!isLab || depth != B200CV_8U) return B200CV_NOT_IMPLEMENTED;      // Luv, float Lab: not on the device path

@@ -227,13 +227,15 @@ class Oracle:
         return dst
 
     def cvtColorLab(self, src, code):
-        """8-bit BGR / RGB <-> Lab: codes 44, 45, 74, 75 (to Lab) and 56, 57, 78, 79 (from Lab).  The reference goes through cvtColor."""
+        """8-bit BGR / RGB <-> Lab: codes 44, 45, 74, 75 (to Lab) and 56, 57, 78, 79 (from Lab); <-> XYZ: 32-35.  The reference goes through cvtColor."""
         src = np.ascontiguousarray(src)
         h, w = src.shape[:2]
         dst = np.zeros((h, w, 3), np.uint8)
         if self.kind != "port":
             return self.cvtColor(src, code, 3)
-        if int(code) in (44, 45, 74, 75):
+        if int(code) in (32, 33, 34, 35):
+            self._ok(self.fn("cvt_color_xyz")(_p(src), sz(src.strides[0]), _p(dst), sz(dst.strides[0]), w, h, src.shape[2], 3, int(code)), "cvtColor(XYZ)")
+        elif int(code) in (44, 45, 74, 75):
             self._ok(self.fn("cvt_color_lab")(_p(src), sz(src.strides[0]), _p(dst), sz(dst.strides[0]), w, h, src.shape[2], int(code)), "cvtColor(Lab)")
         else:
             self._ok(self.fn("cvt_color_lab_inv")(_p(src), sz(src.strides[0]), _p(dst), sz(dst.strides[0]), w, h, 3, int(code)), "cvtColor(Lab inverse)")

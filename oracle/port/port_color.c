@@ -347,6 +347,34 @@ PORT_API int port_cvt_color_lab(const void* src_, size_t sstep, void* dst_, size
     return 0;
 }
 
+/* ---- 8-bit BGR / RGB <-> CIE XYZ (RGB2XYZ_i<uchar> color_lab.cpp:250-330, XYZ2RGB_i<uchar> :650-730; integer matrices :132-144, 12-bit) ------
+ * codes 32 BGR2XYZ, 33 RGB2XYZ, 34 XYZ2BGR, 35 XYZ2RGB: out = saturate((M * in + 2^11) >> 12); BGR order swaps matrix columns (to XYZ) or rows. */
+static void xyz_matrix(int code, int* k)
+{
+    static const int fwd[9] = {1689, 1465, 739, 871, 2929, 296, 79, 488, 3892}, inv[9] = {13273, -6296, -2042, -3970, 7684, 170, 228, -836, 4331};
+    const int to_xyz = code == 32 || code == 33, bgr = code == 32 || code == 34;
+    for (int i = 0; i < 9; i++) k[i] = to_xyz ? fwd[i] : inv[i];
+    if (bgr) {
+        if (to_xyz) for (int r = 0; r < 3; r++) { int t = k[3 * r]; k[3 * r] = k[3 * r + 2]; k[3 * r + 2] = t; }
+        else for (int c = 0; c < 3; c++) { int t = k[c]; k[c] = k[6 + c]; k[6 + c] = t; }
+    }
+}
+
+PORT_API int port_cvt_color_xyz(const void* src_, size_t sstep, void* dst_, size_t dstep, int w, int h, int scn, int dcn, int code)
+{
+    if (code < 32 || code > 35 || (scn != 3 && scn != 4) || (dcn != 3 && dcn != 4)) return -1;
+    if ((code <= 33 && dcn != 3) || (code >= 34 && scn != 3)) return -1;
+    int k[9]; xyz_matrix(code, k);
+    for (int y = 0; y < h; y++) {
+        const uchar* s = (const uchar*)src_ + (size_t)y * sstep; uchar* d = (uchar*)dst_ + (size_t)y * dstep;
+        for (int x = 0; x < w; x++, s += scn, d += dcn) {
+            for (int r = 0; r < 3; r++) d[r] = port_sat_u8i((s[0] * k[3 * r] + s[1] * k[3 * r + 1] + s[2] * k[3 * r + 2] + (1 << 11)) >> 12);
+            if (dcn == 4) d[3] = 255;
+        }
+    }
+    return 0;
+}
+
 /* ---- 8-bit Lab -> BGR / RGB (Lab2RGBinteger, color_lab.cpp:2399-2700; tables :1263-1308, :1086-1107): integer after the tables ---------
  *   (y, ify) = LabToYF_b[L];  x = abToXZ_b[ify + adiv(a)], z = abToXZ_b[ify - bdiv(b)]  (piecewise linear / cubic in 14-bit fixed point);
  *   rgb = (C * xyz + 2^13) >> 14 clipped to [0, 4095], then the inverse-gamma table (sRGB) or (v * 255) >> 12 (linear). */

@@ -388,7 +388,7 @@ def test_emulated_sift_front_end_vs_port(sift_emu, port, rng):
 @pytest.fixture(scope="module")
 def lab_emu():
     lib = build_emulation("cvtcolor_lab.cu", "int emu_lab(const b200cvMat* s, const b200cvMat* d, int code)",
-                          "    return b200cv::cvt_color_lab(s, d, code, nullptr);")
+                          "    return code >= 32 && code <= 35 ? b200cv::cvt_color_xyz(s, d, code, nullptr) : b200cv::cvt_color_lab(s, d, code, nullptr);")
     lib.emu_lab.argtypes = [ctypes.POINTER(Mat), ctypes.POINTER(Mat), ctypes.c_int]
 
     def run(src, code, dcn=3):
@@ -407,8 +407,8 @@ def test_emulated_lab_kernels_vs_port(lab_emu, port, rng):
     cube = np.stack(np.meshgrid(v, v, v, indexing="ij"), axis=-1).reshape(512, 512, 3)
     rnd = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
     for img in (cube, rnd):
-        for code in (44, 45, 74, 75, 56, 57, 78, 79):
-            assert np.array_equal(lab_emu(img, code), port.cvtColorLab(img, code)), "Lab code %d" % code
+        for code in (44, 45, 74, 75, 56, 57, 78, 79, 32, 33, 34, 35):
+            assert np.array_equal(lab_emu(img, code), port.cvtColorLab(img, code)), "Lab / XYZ code %d" % code
     bgra = rng.integers(0, 256, (40, 50, 4), dtype=np.uint8)
     assert np.array_equal(lab_emu(bgra, 44), port.cvtColorLab(np.ascontiguousarray(bgra[:, :, :3]), 44)), "4-channel source"
     out4 = lab_emu(rnd, 56, dcn=4)

@@ -146,8 +146,8 @@ def test_port_lab_on_the_whole_colour_cube(ref, port):
     equals the reference on ALL 2^24 colours, in both directions"""
     v = np.arange(1 << 24, dtype=np.uint32)
     cube = np.stack([v & 255, (v >> 8) & 255, (v >> 16) & 255], axis=-1).astype(np.uint8).reshape(4096, 4096, 3)
-    for code in (44, 45, 74, 75, 56, 57, 78, 79):
-        assert np.array_equal(ref.cvtColor(cube, code, 3), port.cvtColorLab(cube, code)), "Lab code %d" % code
+    for code in (44, 45, 74, 75, 56, 57, 78, 79, 32, 33, 34, 35):          # and CIE XYZ, both directions
+        assert np.array_equal(ref.cvtColor(cube, code, 3), port.cvtColorLab(cube, code)), "Lab / XYZ code %d" % code
 
 
 def test_port_vs_reference_two_plane(ref, port, rng):
