@@ -10,12 +10,14 @@
 // The tables (:1225-1308, :1086-1107) are built on the host once, with the reference's expressions; its softfloat cbrt (core/src/softfloat.cpp:
 // 3897-3930: a rational polynomial whose result mantissa is TRUNCATED) is restated bit for bit, pow goes through libm.  The port, which
 // shares these expressions, equals the reference on all 2^24 colours in both directions (tests/test_oracle.py): bit-exact.
-// One thread per pixel, table lookups through L1 / L2 (the tables total 165 KB): streaming, HBM-bound (6 bytes per pixel).
+// Eight pixels per thread (24- / 32-byte vector accesses when the addresses allow), table lookups through L1 / L2 (the tables total 165 KB):
+// streaming, HBM-bound (6 bytes per pixel).
 #include <math.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
+#include "bytes.cuh"
 
 namespace b200cv {
 
@@ -113,59 +115,78 @@ int ensure_lab_tables()
 
 struct LabCoef { int c[9]; };
 
+// 8 pixels per thread: 24- / 32-byte row pieces through bytes.cuh (vector accesses when aligned and complete, bytes otherwise)
+enum { LAB_PX = 8 };
+
 template <int SCN>
 __global__ void __launch_bounds__(256) bgr_to_lab_kernel(Img src, Img dst, int W, LabCoef k, int srgb)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * LAB_PX;
     const int y = blockIdx.y, f = blockIdx.z;
-    if (x >= W) return;
-    const uchar* s = src.row<uchar>(f, y) + (size_t)x * SCN;
-    const int R = srgb ? g_lab_gamma[s[0]] : s[0] * 8, G = srgb ? g_lab_gamma[s[1]] : s[1] * 8, B = srgb ? g_lab_gamma[s[2]] : s[2] * 8;
-    const int fX = g_lab_cbrt[(R * k.c[0] + G * k.c[1] + B * k.c[2] + (1 << 11)) >> 12];
-    const int fY = g_lab_cbrt[(R * k.c[3] + G * k.c[4] + B * k.c[5] + (1 << 11)) >> 12];
-    const int fZ = g_lab_cbrt[(R * k.c[6] + G * k.c[7] + B * k.c[8] + (1 << 11)) >> 12];
+    if (x0 >= W) return;
+    const int n = min((int)LAB_PX, W - x0);
+    uchar s[LAB_PX * SCN], o[LAB_PX * 3];
+    load_bytes<LAB_PX * SCN>(src.row<uchar>(f, y) + (size_t)x0 * SCN, n * SCN, s);
     const int Lscale = (116 * 255 + 50) / 100, Lshift = -((16 * 255 * (1 << 15) + 50) / 100);
-    uchar* d = dst.row<uchar>(f, y) + (size_t)x * 3;
-    d[0] = sat_u8((Lscale * fY + Lshift + (1 << 14)) >> 15);
-    d[1] = sat_u8((500 * (fX - fY) + 128 * (1 << 15) + (1 << 14)) >> 15);
-    d[2] = sat_u8((200 * (fY - fZ) + 128 * (1 << 15) + (1 << 14)) >> 15);
+#pragma unroll
+    for (int i = 0; i < LAB_PX; i++) {
+        const int c0 = s[i * SCN], c1 = s[i * SCN + 1], c2 = s[i * SCN + 2];
+        const int R = srgb ? g_lab_gamma[c0] : c0 * 8, G = srgb ? g_lab_gamma[c1] : c1 * 8, B = srgb ? g_lab_gamma[c2] : c2 * 8;
+        const int fX = g_lab_cbrt[(R * k.c[0] + G * k.c[1] + B * k.c[2] + (1 << 11)) >> 12];
+        const int fY = g_lab_cbrt[(R * k.c[3] + G * k.c[4] + B * k.c[5] + (1 << 11)) >> 12];
+        const int fZ = g_lab_cbrt[(R * k.c[6] + G * k.c[7] + B * k.c[8] + (1 << 11)) >> 12];
+        o[i * 3] = sat_u8((Lscale * fY + Lshift + (1 << 14)) >> 15);
+        o[i * 3 + 1] = sat_u8((500 * (fX - fY) + 128 * (1 << 15) + (1 << 14)) >> 15);
+        o[i * 3 + 2] = sat_u8((200 * (fY - fZ) + 128 * (1 << 15) + (1 << 14)) >> 15);
+    }
+    store_bytes<LAB_PX * 3>(dst.row<uchar>(f, y) + (size_t)x0 * 3, n * 3, o);
 }
 
 template <int DCN>
 __global__ void __launch_bounds__(256) lab_to_bgr_kernel(Img src, Img dst, int W, LabCoef k, int srgb)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * LAB_PX;
     const int y = blockIdx.y, f = blockIdx.z;
-    if (x >= W) return;
-    const uchar* s = src.row<uchar>(f, y) + (size_t)x * 3;
-    const int LL = s[0], aa = s[1], bb = s[2];
-    const int yv = g_lab_yf[LL * 2], ify = g_lab_yf[LL * 2 + 1];
-    const int adiv = ((5 * aa * 53687 + (1 << 7)) >> 13) - 128 * LAB_BASE / 500, bdiv = ((bb * 41943 + (1 << 4)) >> 9) - 128 * LAB_BASE / 200 + 1;
-    const int xv = g_lab_abxz[ify + adiv - LAB_MIN_AB], zv = g_lab_abxz[ify - bdiv - LAB_MIN_AB];
-    int ro = (k.c[0] * xv + k.c[1] * yv + k.c[2] * zv + (1 << 13)) >> 14;
-    int go = (k.c[3] * xv + k.c[4] * yv + k.c[5] * zv + (1 << 13)) >> 14;
-    int bo = (k.c[6] * xv + k.c[7] * yv + k.c[8] * zv + (1 << 13)) >> 14;
-    ro = min(max(ro, 0), LAB_INVG_N - 1); go = min(max(go, 0), LAB_INVG_N - 1); bo = min(max(bo, 0), LAB_INVG_N - 1);
-    if (srgb) { ro = g_lab_invgamma[ro]; go = g_lab_invgamma[go]; bo = g_lab_invgamma[bo]; }
-    else { ro = ((ro << 8) - ro) >> 12; go = ((go << 8) - go) >> 12; bo = ((bo << 8) - bo) >> 12; }
-    uchar* d = dst.row<uchar>(f, y) + (size_t)x * DCN;
-    d[0] = sat_u8(bo); d[1] = sat_u8(go); d[2] = sat_u8(ro);          // the matrix rows were placed by blueIdx (color_lab.cpp:2434-2436)
-    if constexpr (DCN == 4) d[3] = 255;
+    if (x0 >= W) return;
+    const int n = min((int)LAB_PX, W - x0);
+    uchar s[LAB_PX * 3], o[LAB_PX * DCN];
+    load_bytes<LAB_PX * 3>(src.row<uchar>(f, y) + (size_t)x0 * 3, n * 3, s);
+#pragma unroll
+    for (int i = 0; i < LAB_PX; i++) {
+        const int LL = s[i * 3], aa = s[i * 3 + 1], bb = s[i * 3 + 2];
+        const int yv = g_lab_yf[LL * 2], ify = g_lab_yf[LL * 2 + 1];
+        const int adiv = ((5 * aa * 53687 + (1 << 7)) >> 13) - 128 * LAB_BASE / 500, bdiv = ((bb * 41943 + (1 << 4)) >> 9) - 128 * LAB_BASE / 200 + 1;
+        const int xv = g_lab_abxz[ify + adiv - LAB_MIN_AB], zv = g_lab_abxz[ify - bdiv - LAB_MIN_AB];
+        int ro = (k.c[0] * xv + k.c[1] * yv + k.c[2] * zv + (1 << 13)) >> 14;
+        int go = (k.c[3] * xv + k.c[4] * yv + k.c[5] * zv + (1 << 13)) >> 14;
+        int bo = (k.c[6] * xv + k.c[7] * yv + k.c[8] * zv + (1 << 13)) >> 14;
+        ro = min(max(ro, 0), LAB_INVG_N - 1); go = min(max(go, 0), LAB_INVG_N - 1); bo = min(max(bo, 0), LAB_INVG_N - 1);
+        if (srgb) { ro = g_lab_invgamma[ro]; go = g_lab_invgamma[go]; bo = g_lab_invgamma[bo]; }
+        else { ro = ((ro << 8) - ro) >> 12; go = ((go << 8) - go) >> 12; bo = ((bo << 8) - bo) >> 12; }
+        o[i * DCN] = sat_u8(bo); o[i * DCN + 1] = sat_u8(go); o[i * DCN + 2] = sat_u8(ro);      // the matrix rows were placed by blueIdx (color_lab.cpp:2434-2436)
+        if constexpr (DCN == 4) o[i * DCN + 3] = 255;
+    }
+    store_bytes<LAB_PX * DCN>(dst.row<uchar>(f, y) + (size_t)x0 * DCN, n * DCN, o);
 }
 
 // BGR / RGB <-> CIE XYZ (RGB2XYZ_i<uchar> color_lab.cpp:250-330, XYZ2RGB_i<uchar> :650-730): out = saturate((M * in + 2^11) >> 12), 12-bit integer matrices
 template <int SCN, int DCN>
 __global__ void __launch_bounds__(256) xyz_matrix_kernel(Img src, Img dst, int W, LabCoef k)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * LAB_PX;
     const int y = blockIdx.y, f = blockIdx.z;
-    if (x >= W) return;
-    const uchar* s = src.row<uchar>(f, y) + (size_t)x * SCN;
-    const int s0 = s[0], s1 = s[1], s2 = s[2];
-    uchar* d = dst.row<uchar>(f, y) + (size_t)x * DCN;
+    if (x0 >= W) return;
+    const int n = min((int)LAB_PX, W - x0);
+    uchar s[LAB_PX * SCN], o[LAB_PX * DCN];
+    load_bytes<LAB_PX * SCN>(src.row<uchar>(f, y) + (size_t)x0 * SCN, n * SCN, s);
 #pragma unroll
-    for (int r = 0; r < 3; r++) d[r] = sat_u8((s0 * k.c[3 * r] + s1 * k.c[3 * r + 1] + s2 * k.c[3 * r + 2] + (1 << 11)) >> 12);
-    if constexpr (DCN == 4) d[3] = 255;
+    for (int i = 0; i < LAB_PX; i++) {
+        const int s0 = s[i * SCN], s1 = s[i * SCN + 1], s2 = s[i * SCN + 2];
+#pragma unroll
+        for (int r = 0; r < 3; r++) o[i * DCN + r] = sat_u8((s0 * k.c[3 * r] + s1 * k.c[3 * r + 1] + s2 * k.c[3 * r + 2] + (1 << 11)) >> 12);
+        if constexpr (DCN == 4) o[i * DCN + 3] = 255;
+    }
+    store_bytes<LAB_PX * DCN>(dst.row<uchar>(f, y) + (size_t)x0 * DCN, n * DCN, o);
 }
 
 }  // namespace
@@ -186,7 +207,7 @@ int cvt_color_xyz(const b200cvMat* src, const b200cvMat* dst, int code, cudaStre
     Img s = make_img(src), d = make_img(dst);
     if (s.rows >= 65536 || s.frames >= 65536) return B200CV_NOT_IMPLEMENTED;
     const dim3 block(256);
-    const dim3 grid(div_up((unsigned)src->cols, 256), (unsigned)src->rows, (unsigned)s.frames);
+    const dim3 grid(div_up(div_up((unsigned)src->cols, LAB_PX), 256), (unsigned)src->rows, (unsigned)s.frames);
     if (scn == 3 && dcn == 3) xyz_matrix_kernel<3, 3><<<grid, block, 0, st>>>(s, d, src->cols, k);
     else if (scn == 4) xyz_matrix_kernel<4, 3><<<grid, block, 0, st>>>(s, d, src->cols, k);
     else xyz_matrix_kernel<3, 4><<<grid, block, 0, st>>>(s, d, src->cols, k);
@@ -208,7 +229,7 @@ int cvt_color_lab(const b200cvMat* src, const b200cvMat* dst, int code, cudaStre
     static const double wp[3] = {0.950456, 1., 1.088754};
     LabCoef k;
     const dim3 block(256);
-    const dim3 grid(div_up((unsigned)src->cols, 256), (unsigned)src->rows, (unsigned)s.frames);
+    const dim3 grid(div_up(div_up((unsigned)src->cols, LAB_PX), 256), (unsigned)src->rows, (unsigned)s.frames);
     if (to_lab) {
         B200_REQUIRE((scn == 3 || scn == 4) && dcn == 3, "BGR -> Lab needs a 3-/4-channel source and a 3-channel destination");
         static const double M[9] = {0.412453, 0.357580, 0.180423, 0.212671, 0.715160, 0.072169, 0.019334, 0.119193, 0.950227};
