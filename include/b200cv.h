@@ -214,14 +214,16 @@ B200CV_API int b200cv_good_features_to_track(const b200cvMat* src, float* corner
  * warpAffine, sift.dispatch.cpp:196-202); 2 = doubled as SIFT::create's default does it (cv::resize INTER_LINEAR, :203-208). */
 B200CV_API int b200cv_sift_pyramid_layout(int width, int height, int n_octave_layers, int upscale,
                                           int* n_octaves, size_t* gauss_elems, size_t* dog_elems, int* dims /*2*n_octaves or NULL*/);
-/* the SIFT front end after the pyramid (cv::SIFT::detectAndCompute, sift.dispatch.cpp:501-580, without a mask): scale-space extrema,
+/* the SIFT front end after the pyramid (cv::SIFT::detectAndCompute, sift.dispatch.cpp:501-580): scale-space extrema,
  * sub-pixel refinement, orientation assignment, duplicate removal, first-octave rescaling and, if descriptors != NULL, the 128-float
  * descriptors.  gauss / dog: DEVICE pointers to ONE frame's packed pyramids as b200cv_sift_pyramid writes them; dims: the per-octave (w, h)
  * table of b200cv_sift_pyramid_layout (host); keypoints: HOST, 6 floats each (x, y, size, angle, response, packed octave as int bits);
- * descriptors: HOST, 128 floats each; n_features > 0 keeps the strongest responses (KeyPointsFilter::retainBest, ties included); at most
+ * descriptors: HOST, 128 floats each; n_features > 0 keeps the strongest responses (KeyPointsFilter::retainBest, ties included); mask: NULL or a HOST 8-bit image
+ * of the input frame's size, keypoints on zero bytes are dropped before the descriptors are computed (runByPixelsMask); at most
  * max_keypoints are written, *n_keypoints receives the number found.  Synchronises the stream. */
 B200CV_API int b200cv_sift_detect_and_compute(const float* gauss, const float* dog, const int* dims, int n_octaves, int n_octave_layers,
                                               double contrast_threshold, double edge_threshold, double sigma, int first_octave, int n_features,
+                                              const unsigned char* mask, size_t mask_step, int mask_width, int mask_height,
                                               int max_keypoints, float* keypoints, float* descriptors, int* n_keypoints, void* stream);
 B200CV_API int b200cv_sift_pyramid(const b200cvMat* src, int n_octave_layers, double sigma, int upscale,
                                    float* gauss, size_t gauss_frame_elems, float* dog, size_t dog_frame_elems, void* stream);

@@ -476,11 +476,15 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, blockSize=
 
 
 def sift_detectAndCompute(gray, nfeatures=0, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, max_keypoints=200000,
-                          with_descriptors=True, stream=None, enable_precise_upscale=True):
+                          with_descriptors=True, stream=None, enable_precise_upscale=True, mask=None):
     """cv::SIFT::create(nfeatures, nOctaveLayers, contrastThreshold, edgeThreshold, sigma, enable_precise_upscale)->detectAndCompute(gray) for one
     (H,W) CV_8U frame: pyramid, extrema, refinement, orientation and descriptors all on the device.
     Returns (keypoints[n,5] = x, y, size, angle, response; octave[n] int32; descriptors[n,128] float32 or None) as numpy arrays."""
-    assert gray.dim() == 2, "one frame at a time"
+    if gray.dim() == 4:           # a batch: frame by frame (the detector returns host data and synchronises per frame)
+        return [sift_detectAndCompute(gray[f, :, :, 0], nfeatures, nOctaveLayers, contrastThreshold, edgeThreshold, sigma, max_keypoints, with_descriptors,
+                                      stream, enable_precise_upscale, None if mask is None else (mask if mask.ndim == 2 else mask[f])) for f in range(gray.shape[0])]
+    assert gray.dim() == 2
+    m8 = None if mask is None else np.ascontiguousarray(mask, np.uint8)
     G, D, dims = sift_pyramid(gray, nOctaveLayers, sigma, 1 if enable_precise_upscale else 2, True, stream)
     dims32 = np.ascontiguousarray(dims, np.int32).reshape(-1)
     kp = np.zeros((max_keypoints, 6), np.float32)
@@ -488,7 +492,10 @@ def sift_detectAndCompute(gray, nfeatures=0, nOctaveLayers=3, contrastThreshold=
     n = ctypes.c_int(0)
     _check(lib().b200cv_sift_detect_and_compute(ctypes.c_void_p(G.data_ptr()), ctypes.c_void_p(D.data_ptr()), dims32.ctypes.data_as(ctypes.c_void_p),
                                                 len(dims32) // 2, int(nOctaveLayers), ctypes.c_double(contrastThreshold), ctypes.c_double(edgeThreshold),
-                                                ctypes.c_double(sigma), -1, int(nfeatures), int(max_keypoints), kp.ctypes.data_as(ctypes.c_void_p),
+                                                ctypes.c_double(sigma), -1, int(nfeatures),
+                                                m8.ctypes.data_as(ctypes.c_void_p) if m8 is not None else None, ctypes.c_size_t(m8.strides[0] if m8 is not None else 0),
+                                                int(m8.shape[1]) if m8 is not None else 0, int(m8.shape[0]) if m8 is not None else 0,
+                                                int(max_keypoints), kp.ctypes.data_as(ctypes.c_void_p),
                                                 desc.ctypes.data_as(ctypes.c_void_p) if with_descriptors else None, ctypes.byref(n), _stream_ptr(stream)),
            "sift_detectAndCompute")
     m = min(n.value, max_keypoints)

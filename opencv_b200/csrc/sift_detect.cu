@@ -278,7 +278,8 @@ struct KpLess {      // KeyPoint12_LessThan, features2d/src/keypoint.cpp:253-271
 // gauss / dog: device pointers to ONE frame's packed pyramids (layout of b200cv_sift_pyramid_layout); kp_host: 6 floats per keypoint
 // (x, y, size, angle, response, octave bits), desc_host: 128 floats per keypoint or null; both host memory.  Synchronises the stream.
 int sift_detect_impl(const float* gauss, const float* dog, const int* dims, int n_oct, int nl, double contrastThreshold, double edgeThreshold, double sigma,
-                     int first_octave, int nfeatures, int max_kp, float* kp_host, float* desc_host, int* n_out, cudaStream_t st)
+                     int first_octave, int nfeatures, const unsigned char* mask_host, size_t mask_step, int mask_w, int mask_h, int max_kp, float* kp_host,
+                     float* desc_host, int* n_out, cudaStream_t st)
 {
     B200_REQUIRE(gauss && dog && dims && kp_host && n_out && n_oct > 0 && n_oct <= SIFT_MAX_OCT && nl > 0 && nl <= 8 && max_kp > 0, "sift_detect: bad arguments");
     SiftPyr p;
@@ -354,6 +355,15 @@ int sift_detect_impl(const float* gauss, const float* dog, const int* dims, int 
             const float scale = 1.f / (float)(1 << -first_octave);
             for (SiftKp& k : hk) { k.octave = (k.octave & ~255) | ((k.octave + first_octave) & 255); k.x *= scale; k.y *= scale; k.size *= scale; }
         }
+        // KeyPointsFilter::runByPixelsMask (keypoint.cpp:144-169): drop keypoints whose rounded position has a zero mask byte
+        if (mask_host) {
+            size_t w = 0;
+            for (size_t j = 0; j < hk.size(); j++) {
+                const int my = (int)(hk[j].y + 0.5f), mx = (int)(hk[j].x + 0.5f);
+                if (my >= 0 && my < mask_h && mx >= 0 && mx < mask_w && mask_host[(size_t)my * mask_step + mx] != 0) hk[w++] = hk[j];
+            }
+            hk.resize(w);
+        }
     }
     *n_out = (int)hk.size();
     const size_t nret = std::min(hk.size(), (size_t)max_kp);
@@ -388,9 +398,10 @@ int sift_detect_impl(const float* gauss, const float* dog, const int* dims, int 
 using namespace b200cv;
 
 extern "C" int b200cv_sift_detect_and_compute(const float* gauss, const float* dog, const int* dims, int n_octaves, int n_octave_layers, double contrast_threshold,
-                                              double edge_threshold, double sigma, int first_octave, int n_features, int max_keypoints, float* keypoints,
-                                              float* descriptors, int* n_keypoints, void* stream)
+                                              double edge_threshold, double sigma, int first_octave, int n_features, const unsigned char* mask,
+                                              size_t mask_step, int mask_width, int mask_height, int max_keypoints, float* keypoints, float* descriptors,
+                                              int* n_keypoints, void* stream)
 {
-    return sift_detect_impl(gauss, dog, dims, n_octaves, n_octave_layers, contrast_threshold, edge_threshold, sigma, first_octave, n_features, max_keypoints,
-                            keypoints, descriptors, n_keypoints, as_stream(stream));
+    return sift_detect_impl(gauss, dog, dims, n_octaves, n_octave_layers, contrast_threshold, edge_threshold, sigma, first_octave, n_features, mask, mask_step,
+                            mask_width, mask_height, max_keypoints, keypoints, descriptors, n_keypoints, as_stream(stream));
 }

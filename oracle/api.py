@@ -308,14 +308,17 @@ class Oracle:
         return pts[:cnt].copy(), q[:cnt].copy()
 
     def sift_detect_and_compute(self, gray, nfeatures=0, nOctaveLayers=3, contrastThreshold=0.04, edgeThreshold=10, sigma=1.6, max_kp=200000,
-                                precise_upscale=True):
+                                precise_upscale=True, mask=None):
         """the reference's cv::SIFT::detectAndCompute (real reference only): (keypoints[n,5] = x, y, size, angle, response; octave[n]; desc[n,128]).
         precise_upscale=True is SIFT::create(..., enable_precise_upscale=true): the first-octave image sift_pyramid() builds."""
         gray = np.ascontiguousarray(gray)
+        mask = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         h, w = gray.shape
         kp = np.zeros((max_kp, 6), np.float32); desc = np.zeros((max_kp, 128), np.float32); n = ctypes.c_int(0)
         self._ok(self.fn("sift_detect_and_compute")(_p(gray), sz(gray.strides[0]), w, h, int(nfeatures), int(nOctaveLayers), dbl(contrastThreshold),
-                                                     dbl(edgeThreshold), dbl(sigma), int(bool(precise_upscale)), int(max_kp), _p(kp), _p(desc), ctypes.byref(n)), "SIFT")
+                                                     dbl(edgeThreshold), dbl(sigma), int(bool(precise_upscale)),
+                                                     _p(mask) if mask is not None else None, sz(mask.strides[0]) if mask is not None else sz(0),
+                                                     int(max_kp), _p(kp), _p(desc), ctypes.byref(n)), "SIFT")
         m = min(n.value, max_kp)
         return kp[:m, :5].copy(), kp[:m, 5].copy().view(np.int32), desc[:m].copy()
 

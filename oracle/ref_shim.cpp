@@ -308,14 +308,16 @@ API int ref_good_features_to_track(const void* src, size_t sstep, int w, int h, 
 // kp: 6 floats per keypoint (x, y, size, angle, response, octave as int bits), desc: 128 floats per keypoint; at most max_kp are written,
 // *n receives the number found.  The oracle for SURVEY 8(f) rank 1 (scale-space extrema, orientation, descriptors).
 API int ref_sift_detect_and_compute(const void* gray, size_t step, int w, int h, int nfeatures, int nOctaveLayers, double contrastThreshold,
-                                    double edgeThreshold, double sigma, int precise_upscale, int max_kp, float* kp, float* desc, int* n)
+                                    double edgeThreshold, double sigma, int precise_upscale, const void* mask, size_t mask_step, int max_kp, float* kp,
+                                    float* desc, int* n)
 {
     GUARD_BEGIN
     Mat image = hdr(gray, step, w, h, CV_8UC1);
     Ptr<SIFT> sp = SIFT::create(nfeatures, nOctaveLayers, contrastThreshold, edgeThreshold, sigma, precise_upscale != 0);
     std::vector<KeyPoint> kps;
     Mat d;
-    sp->detectAndCompute(image, noArray(), kps, d);
+    if (mask) sp->detectAndCompute(image, hdr(mask, mask_step, w, h, CV_8UC1), kps, d);
+    else sp->detectAndCompute(image, noArray(), kps, d);
     *n = (int)kps.size();
     for (int i = 0; i < (int)kps.size() && i < max_kp; i++) {
         const KeyPoint& k = kps[i];

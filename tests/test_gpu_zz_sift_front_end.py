@@ -76,3 +76,11 @@ def test_sift_detect_and_compute(cvb, ref, rng, size):
     r500, _, _ = ref.sift_detect_and_compute(img, nfeatures=500)
     assert abs(len(k500) - len(r500)) <= 10 and len(match(r500, k500, 1e-2, 0.1)) >= 0.95 * len(r500)
     assert d500.shape == (len(k500), 128)
+    # mask = runByPixelsMask on the rounded positions, before the descriptors; a batch is a list of per-frame results
+    mask = np.zeros(img.shape, np.uint8); mask[size[0] // 4: size[0] // 2, size[1] // 4: 3 * size[1] // 4] = 255
+    km, _, dm = cvb.sift_detectAndCompute(gpu(img), mask=mask)
+    keep = mask[(kg[:, 1] + 0.5).astype(np.int32), (kg[:, 0] + 0.5).astype(np.int32)] != 0
+    assert np.array_equal(km, kg[keep]) and np.array_equal(dm, dg[keep])
+    if size[0] <= 480:
+        res = cvb.sift_detectAndCompute(gpu(np.stack([img, img[::-1].copy()])[..., None]))
+        assert len(res) == 2 and np.array_equal(res[0][0], kg) and np.array_equal(res[0][2], dg)

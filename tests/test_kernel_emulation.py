@@ -348,10 +348,10 @@ def test_emulated_integral_vs_port(integral_emu, port, rng):
 @pytest.fixture(scope="module")
 def sift_emu():
     lib = build_emulation("sift_detect.cu", "int emu_sift(const float* g, const float* d, const int* dims, int no, int nl, double ct, double et, double sigma, "
-                          "int first_octave, int nfeatures, int max_kp, float* kp, float* desc, int* n)",
-                          "    return b200cv::sift_detect_impl(g, d, dims, no, nl, ct, et, sigma, first_octave, nfeatures, max_kp, kp, desc, n, nullptr);")
+                          "int first_octave, int nfeatures, const unsigned char* mask, size_t mstep, int mw, int mh, int max_kp, float* kp, float* desc, int* n)",
+                          "    return b200cv::sift_detect_impl(g, d, dims, no, nl, ct, et, sigma, first_octave, nfeatures, mask, mstep, mw, mh, max_kp, kp, desc, n, nullptr);")
 
-    def run(gauss, dog, nl=3, ct=0.04, et=10.0, sigma=1.6, max_kp=100000, nfeatures=0):
+    def run(gauss, dog, nl=3, ct=0.04, et=10.0, sigma=1.6, max_kp=100000, nfeatures=0, mask=None):
         no = len(gauss)
         dims = np.array([[g[0].shape[1], g[0].shape[0]] for g in gauss], np.int32).reshape(-1)
         G = np.concatenate([np.ascontiguousarray(l, np.float32).reshape(-1) for g in gauss for l in g])
@@ -359,7 +359,10 @@ def sift_emu():
         kp = np.zeros((max_kp, 6), np.float32); desc = np.zeros((max_kp, 128), np.float32); n = ctypes.c_int(0)
         fp = ctypes.POINTER(ctypes.c_float)
         rc = lib.emu_sift(G.ctypes.data_as(fp), D.ctypes.data_as(fp), dims.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), no, nl, ctypes.c_double(ct),
-                          ctypes.c_double(et), ctypes.c_double(sigma), -1, nfeatures, max_kp, kp.ctypes.data_as(fp), desc.ctypes.data_as(fp), ctypes.byref(n))
+                          ctypes.c_double(et), ctypes.c_double(sigma), -1, nfeatures,
+                          mask.ctypes.data_as(ctypes.c_void_p) if mask is not None else None, ctypes.c_size_t(mask.strides[0] if mask is not None else 0),
+                          mask.shape[1] if mask is not None else 0, mask.shape[0] if mask is not None else 0,
+                          max_kp, kp.ctypes.data_as(fp), desc.ctypes.data_as(fp), ctypes.byref(n))
         assert rc == 0, "emulated sift_detect_impl returned %d" % rc
         return kp[:n.value, :5].copy(), kp[:n.value, 5].copy().view(np.int32), desc[:n.value].copy()
     return run
@@ -382,6 +385,11 @@ def test_emulated_sift_front_end_vs_port(sift_emu, port, rng):
     pk, po = port.sift_detect_from_pyramid(G, D, nfeatures=50)
     assert 50 <= len(bk) == len(pk) and sorted(map(tuple, bk.tolist())) == sorted(map(tuple, pk.tolist()))
     assert bk[:, 4].min() >= np.sort(kp[:, 4])[-50]
+    # mask (KeyPointsFilter::runByPixelsMask): keypoints whose rounded position has a zero mask byte disappear, with their descriptors
+    mask = np.zeros(img.shape, np.uint8); mask[40:120, 60:180] = 255
+    mk, mo, md = sift_emu(G, D, mask=mask)
+    keep = mask[(kp[:, 1] + 0.5).astype(np.int32), (kp[:, 0] + 0.5).astype(np.int32)] != 0
+    assert 0 < keep.sum() < len(kp) and np.array_equal(mk, kp[keep]) and np.array_equal(md, gd[keep])
 
 
 # ---- BGR / RGB <-> Lab, 8-bit (cvtcolor_lab.cu): host-built tables + per-pixel kernels ----------------------------------------------------

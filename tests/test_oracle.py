@@ -150,6 +150,28 @@ def test_port_lab_on_the_whole_colour_cube(ref, port):
         assert np.array_equal(ref.cvtColor(cube, code, 3), port.cvtColorLab(cube, code)), "Lab / XYZ code %d" % code
 
 
+def test_wrapper_destination_geometry_matches_the_reference(ref):
+    """the Python wrappers size cv::cvtColor's destination themselves (opencv_b200._cvt_dst_geometry): it must be the reference's own
+    destination size and channel count for every code whose geometry changes, and the C++ mirror's table (host/b200cv.hpp) must agree"""
+    from oracle.api import yuv_dst_shape
+    for code in list(range(90, 109)) + [111, 112] + list(range(115, 125)) + list(range(127, 135)) + list(range(143, 155)) + [46, 47, 48, 49, 139, 140, 141, 142]:
+        if 90 <= code <= 106:
+            src = np.zeros((36, 48), np.uint8)
+        elif 107 <= code <= 124:
+            src = np.zeros((24, 48, 2), np.uint8)
+        elif code in (46, 47, 48, 49, 139, 140, 141, 142):
+            src = np.zeros((24, 48), np.uint8)
+        else:
+            src = np.zeros((24, 48, 3), np.uint8)
+        want = ref.cvtColorYUV(src, code)                     # cv::cvtColor with dcn = 0 would size it the same; the shim passes our dims and asserts
+        sh, sw = src.shape[:2]
+        w, h, cn = C._cvt_dst_geometry(code, sw, sh, 0)
+        assert (w, h, cn) == yuv_dst_shape(sw, sh, code)
+        assert want.shape[:2] == (h, w) and (want.shape[2] if want.ndim == 3 else 1) == cn, "code %d" % code
+    hpp = open(os.path.join(os.path.dirname(GOLD), "..", "opencv_b200", "host", "b200cv.hpp")).read()
+    assert "code >= 143 && code <= 154" in hpp and "code >= 127 && code <= 134" in hpp and "code >= 90 && code <= 105" in hpp
+
+
 def test_port_vs_reference_two_plane(ref, port, rng):
     """cv::cvtColorTwoPlane: the same arithmetic with separate luma / chroma buffers; also equal to cvtColor on the concatenated planes"""
     for (h, w) in [(4, 6), (18, 34), (250, 322)]:
@@ -342,6 +364,10 @@ def test_reference_sift_front_end_is_reachable(ref, rng):
     kp2, octv2, desc2 = ref.sift_detect_and_compute(img)
     assert len(kp) > 20 and desc.shape == (len(kp), 128)
     assert np.array_equal(kp, kp2) and np.array_equal(desc, desc2) and np.array_equal(octv, octv2), "the reference's SIFT is deterministic"
+    mask = np.zeros(img.shape, np.uint8); mask[50:150, 80:240] = 1
+    km, om, dm = ref.sift_detect_and_compute(img, mask=mask)
+    keep = mask[(kp[:, 1] + 0.5).astype(np.int32), (kp[:, 0] + 0.5).astype(np.int32)] != 0
+    assert 0 < len(km) < len(kp) and np.array_equal(km, kp[keep]) and np.array_equal(dm, desc[keep]), "mask = runByPixelsMask on the rounded positions"
     assert (kp[:, 0] >= 0).all() and (kp[:, 0] < img.shape[1]).all() and (kp[:, 1] >= 0).all() and (kp[:, 1] < img.shape[0]).all()
     assert np.all(desc >= 0) and np.all(desc <= 255) and np.all(desc == np.round(desc)), "descriptors are 8-bit-valued floats (sift.simd.hpp:1018-1034)"
 
