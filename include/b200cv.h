@@ -195,6 +195,9 @@ B200CV_API int b200cv_cvt_color_two_plane(const b200cvMat* src_y, const b200cvMa
  * result: CV_32FC1 (W-w+1) x (H-h+1).  The CCORR numerator of u8 images runs on tcgen05 tensor cores. */
 B200CV_API int b200cv_match_template(const b200cvMat* image, const b200cvMat* templ, const b200cvMat* result,
                                      int method, void* stream);
+/* cv::matchTemplate with a mask (templmatch.cpp:762-905): mask = 8UC1 (non-zero = 1) or 32FC1 (weights) of the template's size, one channel */
+B200CV_API int b200cv_match_template_masked(const b200cvMat* image, const b200cvMat* templ, const b200cvMat* mask, const b200cvMat* result, int method,
+                                            void* stream);
 /* replaces cv::cornerHarris / cv::cornerMinEigenVal (imgproc.hpp:1948,1921; corner.cpp:634-654,610-632) */
 B200CV_API int b200cv_corner_harris(const b200cvMat* src, const b200cvMat* dst, int block_size, int ksize, double k,
                                     int border, void* stream);

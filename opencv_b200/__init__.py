@@ -422,8 +422,8 @@ def pyrUp(src, dst=None, stream=None):
     return dst
 
 
-def matchTemplate(image, templ, method, result=None, stream=None):
-    """cv::matchTemplate (imgproc.hpp:3916): image (H,W) / (N,H,W,1), templ (h,w); result float32 (H-h+1, W-w+1)"""
+def matchTemplate(image, templ, method, result=None, stream=None, mask=None):
+    """cv::matchTemplate (imgproc.hpp:3916): image (H,W) / (N,H,W,1), templ (h,w); result float32 (H-h+1, W-w+1); mask: uint8 / float32 (h,w)"""
     import torch
     mi, mt = describe(image), describe(templ)
     ow, oh = mi.cols - mt.cols + 1, mi.rows - mt.rows + 1
@@ -431,6 +431,11 @@ def matchTemplate(image, templ, method, result=None, stream=None):
         shape = [max(mi.frames, 1), oh, ow, 1] if image.dim() == 4 else [oh, ow]
         result = torch.empty(shape, dtype=torch.float32, device=image.device)
     mr = describe(result)
+    if mask is not None:
+        mm = describe(mask)
+        _check(lib().b200cv_match_template_masked(ctypes.byref(mi), ctypes.byref(mt), ctypes.byref(mm), ctypes.byref(mr), int(method), _stream_ptr(stream)),
+               "matchTemplate(mask)")
+        return result
     _check(lib().b200cv_match_template(ctypes.byref(mi), ctypes.byref(mt), ctypes.byref(mr), int(method), _stream_ptr(stream)), "matchTemplate")
     return result
 

@@ -278,6 +278,15 @@ class Oracle:
                                            cvtype(image), _p(res), sz(res.strides[0]), int(method)), "matchTemplate")
         return res
 
+    def matchTemplateMasked(self, image, templ, method, mask):
+        image = np.ascontiguousarray(image); templ = np.ascontiguousarray(templ); mask = np.ascontiguousarray(mask)
+        ih, iw = image.shape[:2]
+        th, tw = templ.shape[:2]
+        res = np.empty((ih - th + 1, iw - tw + 1), np.float32)
+        self._ok(self.fn("match_template_masked")(_p(image), sz(image.strides[0]), iw, ih, _p(templ), sz(templ.strides[0]), tw, th, cvtype(image),
+                                                  _p(mask), sz(mask.strides[0]), cvtype(mask), _p(res), sz(res.strides[0]), int(method)), "matchTemplate(mask)")
+        return res
+
     def cornerHarris(self, src, blockSize, ksize, k, borderType=4):
         src = np.ascontiguousarray(src)
         h, w = src.shape[:2]

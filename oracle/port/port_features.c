@@ -479,3 +479,57 @@ PORT_API int port_sift_descriptors(const float* gauss, const int* dims, int n_oc
     free(offs);
     return 0;
 }
+
+/* ---- cv::matchTemplate with a mask (matchTemplateMask, templmatch.cpp:762-905), one channel ---------------------------------------------
+ * The reference turns everything into float and evaluates up to four cross-correlations with its block DFT:
+ *   S1 = CC(I, W1), S2 = CC(I^2, M^2), S3 = CC(I, M), S4 = CC(I, M^2);  W1 = T M^2 (SQDIFF / CCORR) or M^2 (T - mu), mu = sum(M T) / sum(M) (CCOEFF)
+ *   SQDIFF  -2 S1 + S2 + c              c = sum((T M)^2)            NORMED: / sqrt(c S2)
+ *   CCORR   S1                                                        NORMED: / sqrt(c S2)
+ *   CCOEFF  S1 - S3 sum(W1) / sum(M)                                  NORMED: / (sqrt(S2 + S3 / sum(M) (S3 sum(M^2) / sum(M) - 2 S4)) |M (T - mu)|)
+ * An 8-bit mask is binarised (non-zero -> 1), a float mask is a weight.  Here the sums are direct, in double: parity with the reference is by
+ * tolerance (its own test allows the DFT's error), as for the unmasked methods. */
+PORT_API int port_match_template_masked(const void* img, size_t istep, int iw, int ih, const void* tpl, size_t tstep, int tw, int th, int type,
+                                        const void* mask, size_t mstep, int mask_type, float* result, size_t rstep, int method)
+{
+    const int depth = P_DEPTH(type), mdepth = P_DEPTH(mask_type);
+    if (P_CN(type) != 1 || P_CN(mask_type) != 1 || (depth != P_8U && depth != P_32F) || (mdepth != P_8U && mdepth != P_32F) || method < 0 || method > 5) return 1;
+    const int ow = iw - tw + 1, oh = ih - th + 1, n = tw * th;
+    float* T = (float*)malloc(sizeof(float) * (size_t)n * 4); float* M = T + n; float* M2 = M + n; float* W1 = M2 + n;
+    for (int y = 0; y < th; y++)
+        for (int x = 0; x < tw; x++) {
+            T[y * tw + x] = depth == P_8U ? (float)((const uchar*)tpl + (size_t)y * tstep)[x] : ((const float*)((const char*)tpl + (size_t)y * tstep))[x];
+            M[y * tw + x] = mdepth == P_8U ? (((const uchar*)mask + (size_t)y * mstep)[x] ? 1.f : 0.f) : ((const float*)((const char*)mask + (size_t)y * mstep))[x];
+        }
+    double sumM = 0, sumMT = 0, sumM2 = 0, c = 0;
+    for (int i = 0; i < n; i++) { M2[i] = M[i] * M[i]; sumM += M[i]; sumMT += (double)(M[i] * T[i]); sumM2 += M2[i]; float tm = T[i] * M[i]; c += (double)tm * tm; }
+    const int coeff = method >= 4;
+    const float mu = (float)(sumMT / sumM);
+    double sumW1 = 0, nt2 = 0;
+    for (int i = 0; i < n; i++) {
+        W1[i] = coeff ? M[i] * (M[i] * (T[i] - mu)) : T[i] * M2[i];
+        sumW1 += W1[i];
+        float q = M[i] * (T[i] - mu); nt2 += (double)q * q;
+    }
+    const double norm_templx = sqrt(nt2);
+    for (int y = 0; y < oh; y++)
+        for (int x = 0; x < ow; x++) {
+            double S1 = 0, S2 = 0, S3 = 0, S4 = 0;
+            for (int v = 0; v < th; v++)
+                for (int u = 0; u < tw; u++) {
+                    const double I = depth == P_8U ? (double)((const uchar*)img + (size_t)(y + v) * istep)[x + u]
+                                                   : (double)((const float*)((const char*)img + (size_t)(y + v) * istep))[x + u];
+                    const int i = v * tw + u;
+                    S1 += I * W1[i]; S2 += I * I * M2[i]; S3 += I * M[i]; S4 += I * M2[i];
+                }
+            double r;
+            if (method <= 1) { r = -2 * S1 + S2 + c; if (method == 1) r /= sqrt(c * S2); }
+            else if (method <= 3) { r = S1; if (method == 3) r /= sqrt(c * S2); }
+            else {
+                r = S1 - S3 * (sumW1 / sumM);
+                if (method == 5) { const double nimg = S2 + (S3 / sumM) * (S3 * (sumM2 / sumM) - 2 * S4); r /= sqrt(nimg) * norm_templx; }
+            }
+            ((float*)((char*)result + (size_t)y * rstep))[x] = (float)r;
+        }
+    free(T);
+    return 0;
+}

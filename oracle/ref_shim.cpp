@@ -265,6 +265,17 @@ API int ref_match_template(const void* img, size_t istep, int iw, int ih, const 
     GUARD_END
 }
 
+API int ref_match_template_masked(const void* img, size_t istep, int iw, int ih, const void* templ, size_t tstep, int tw, int th, int type,
+                                  const void* mask, size_t mstep, int mask_type, float* result, size_t rstep, int method)
+{
+    GUARD_BEGIN
+    Mat i = hdr(img, istep, iw, ih, type), t = hdr(templ, tstep, tw, th, type), m = hdr(mask, mstep, tw, th, mask_type);
+    Mat r = hdr(result, rstep, iw - tw + 1, ih - th + 1, CV_32F);
+    matchTemplate(i, t, r, method, m);
+    CV_Assert(r.data == (uchar*)result);
+    GUARD_END
+}
+
 API int ref_corner_harris(const void* src, size_t sstep, int w, int h, int type, float* dst, size_t dstep,
                           int blockSize, int ksize, double k, int border)
 {

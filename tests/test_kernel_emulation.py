@@ -459,3 +459,34 @@ def test_emulated_area_mode_weights_in_resize_cu():
         f0 = ((np.arange(dsize, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
         s0 = np.floor(f0).astype(np.int32)
         assert np.array_equal(s, s0) and np.array_equal(fr, (f0 - s0.astype(np.float32)).astype(np.float32)), "default weights %d -> %d" % (ssize, dsize)
+
+
+# ---- cv::matchTemplate with a mask (matchtemplate_mask.cu): preparation kernel + one thread per result element -----------------------------
+@pytest.fixture(scope="module")
+def mtmask_emu():
+    lib = build_emulation("matchtemplate_mask.cu", "int emu_mt_mask(const b200cvMat* i, const b200cvMat* t, const b200cvMat* m, const b200cvMat* r, int method)",
+                          "    return b200cv::match_template_masked(i, t, m, r, method, nullptr);")
+    lib.emu_mt_mask.argtypes = [ctypes.POINTER(Mat)] * 4 + [ctypes.c_int]
+
+    def run(img, templ, mask, method):
+        res = np.zeros((img.shape[0] - templ.shape[0] + 1, img.shape[1] - templ.shape[1] + 1), np.float32)
+        mats = [mat_of(a) for a in (img, templ, mask, res)]
+        for a, m in zip((img, templ, mask, res), mats):
+            if a.dtype == np.float32:
+                m.type |= 5
+        rc = lib.emu_mt_mask(*[ctypes.byref(m) for m in mats], int(method))
+        assert rc == 0, "emulated match_template_masked returned %d" % rc
+        return res
+    return run
+
+
+def test_emulated_masked_match_template_vs_port(mtmask_emu, port, rng):
+    img = rng.integers(0, 256, (60, 80), dtype=np.uint8)
+    templ = img[20:33, 30:51].copy()
+    m8 = (rng.random(templ.shape) > 0.3).astype(np.uint8) * 255
+    mf = rng.random(templ.shape).astype(np.float32)
+    for im, tt in ((img, templ), (img.astype(np.float32), templ.astype(np.float32))):
+        for mk in (m8, mf):
+            for method in range(6):
+                got, want = mtmask_emu(im, tt, mk, method), port.matchTemplateMasked(im, tt, method, mk)
+                assert np.array_equal(got, want), "masked matchTemplate %s mask %s method %d" % (im.dtype, mk.dtype, method)

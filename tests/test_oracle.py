@@ -172,6 +172,26 @@ def test_wrapper_destination_geometry_matches_the_reference(ref):
     assert "code >= 143 && code <= 154" in hpp and "code >= 127 && code <= 134" in hpp and "code >= 90 && code <= 105" in hpp
 
 
+def test_port_vs_reference_masked_match_template(ref, port, rng):
+    """cv::matchTemplate with a mask, all six methods, 8-bit (binarised) and float (weight) masks: the port's direct double sums against the
+    reference's float DFT path, 1e-3 of the result range (the reference's own bar for matchTemplate, test_templmatch.cpp:333); measured ~2e-7"""
+    img = rng.integers(0, 256, (90, 120), dtype=np.uint8)
+    templ = img[20:41, 30:63].copy()
+    m8 = (rng.random(templ.shape) > 0.3).astype(np.uint8) * 255
+    mf = rng.random(templ.shape).astype(np.float32)
+    for im, tt in ((img, templ), (img.astype(np.float32), templ.astype(np.float32))):
+        for mk in (m8, mf):
+            for method in range(6):
+                a, b = ref.matchTemplateMasked(im, tt, method, mk), port.matchTemplateMasked(im, tt, method, mk)
+                assert_close(b, a, atol=1e-3 * max(1.0, float(np.abs(a).max())), what="masked matchTemplate %s %s method %d" % (im.dtype, mk.dtype, method))
+    big = rng.integers(0, 256, (300, 400), dtype=np.uint8)       # large enough for the reference's block DFT
+    tb = big[100:164, 150:214].copy(); mb = np.zeros(tb.shape, np.uint8); mb[8:56, 8:56] = 1
+    for method in (1, 3, 5):
+        a, b = ref.matchTemplateMasked(big, tb, method, mb), port.matchTemplateMasked(big, tb, method, mb)
+        assert_close(b, a, atol=1e-3 * max(1.0, float(np.abs(a).max())), what="masked matchTemplate 64x64 method %d" % method)
+        assert np.unravel_index(b.argmin() if method == 1 else b.argmax(), b.shape) == (100, 150)
+
+
 def test_port_vs_reference_two_plane(ref, port, rng):
     """cv::cvtColorTwoPlane: the same arithmetic with separate luma / chroma buffers; also equal to cvtColor on the concatenated planes"""
     for (h, w) in [(4, 6), (18, 34), (250, 322)]:

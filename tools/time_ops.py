@@ -51,6 +51,7 @@ ops = {
     "nearest_exact_8k_to_5k": (lambda: cvb.resize(bgr, (5120, 2880), interpolation=cvb.INTER_NEAREST_EXACT, dst=k5), nbytes(bgr, k5)),
     "bgr_to_lab_8k": (lambda: cvb.cvtColor(bgr, cvb.COLOR_BGR2Lab, dst=obgr), nbytes(bgr, obgr)),
     "lab_to_bgr_8k": (lambda: cvb.cvtColor(bgr, cvb.COLOR_Lab2BGR, dst=obgr), nbytes(bgr, obgr)),
+    "match_masked_4k_64": (lambda: cvb.matchTemplate(u8[:1], u8[0, 700:764, 1000:1064, 0].contiguous(), 5, mask=torch.ones((64, 64), dtype=torch.uint8, device=dev)), nbytes(u8[:1]) * 5),
     "integral_4k": (lambda: cvb.integral(u8), nbytes(u8) * 5),
 }
 for name, (fn, nb) in ops.items():
