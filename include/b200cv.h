@@ -140,6 +140,8 @@ B200CV_API int b200cv_event_elapsed_ms(void* start, void* end, float* ms);
 /* cv::getGaussianKernel (imgproc/src/smooth.dispatch.cpp:81-221): n taps as double, bit-exact softdouble arithmetic */
 B200CV_API int b200cv_get_gaussian_kernel(int n, double sigma, double* out);
 /* 8.8 fixed-point taps with error diffusion (smooth.dispatch.cpp:224-277) */
+/* the same taps with 8 (8-bit images) or 16 (16-bit images) fractional bits: getGaussianKernelFixedPoint_ED, smooth.dispatch.cpp:224-258 */
+B200CV_API int b200cv_get_gaussian_kernel_fixed(int ksize, double sigma, int bits, unsigned int* out);
 B200CV_API int b200cv_get_gaussian_kernel_fixed8(int n, double sigma, uint16_t* out);
 
 /* ---- device ops ------------------------------------------------------------------------------------------------

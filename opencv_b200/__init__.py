@@ -118,9 +118,9 @@ def launch_count():
 
 
 CV_32S, CV_64F = 4, 6
-_DEPTH_OF = {"torch.uint8": CV_8U, "torch.int16": CV_16S, "torch.float32": CV_32F, "torch.int32": CV_32S, "torch.float64": CV_64F,
+_DEPTH_OF = {"torch.uint8": CV_8U, "torch.uint16": 2, "uint16": 2, "torch.int16": CV_16S, "torch.float32": CV_32F, "torch.int32": CV_32S, "torch.float64": CV_64F,
              "uint8": CV_8U, "int16": CV_16S, "float32": CV_32F, "int32": CV_32S, "float64": CV_64F}
-_ESZ = {CV_8U: 1, CV_16S: 2, CV_32F: 4, CV_32S: 4, CV_64F: 8}
+_ESZ = {CV_8U: 1, 2: 2, CV_16S: 2, CV_32F: 4, CV_32S: 4, CV_64F: 8}
 
 
 def make_type(depth, cn):
@@ -342,6 +342,13 @@ def getGaussianKernel(ksize, sigma):
     out = np.zeros(ksize, np.float64)
     _check(lib().b200cv_get_gaussian_kernel(int(ksize), ctypes.c_double(sigma), out.ctypes.data_as(ctypes.POINTER(ctypes.c_double))),
            "getGaussianKernel")
+    return out
+
+
+def getGaussianKernelFixed(ksize, sigma, bits):
+    """the fixed-point taps GaussianBlur uses for 8-bit (bits = 8) and 16-bit (bits = 16) images"""
+    out = np.zeros(ksize, np.uint32)
+    _check(lib().b200cv_get_gaussian_kernel_fixed(int(ksize), ctypes.c_double(sigma), int(bits), out.ctypes.data_as(ctypes.c_void_p)), "getGaussianKernelFixed")
     return out
 
 

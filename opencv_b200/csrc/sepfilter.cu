@@ -654,6 +654,15 @@ extern "C" int b200cv_get_gaussian_kernel_fixed8(int n, double sigma, uint16_t* 
     return B200CV_OK;
 }
 
+extern "C" int b200cv_get_gaussian_kernel_fixed(int n, double sigma, int bits, uint32_t* out)
+{
+    B200_REQUIRE(n > 0 && (n & 1) && out && (bits == 8 || bits == 16), "bad arguments");
+    std::vector<int64_t> k;
+    gaussian_kernel_fixed(n, sigma, bits, k);
+    for (int i = 0; i < n; i++) out[i] = (uint32_t)k[i];
+    return B200CV_OK;
+}
+
 // cv::GaussianBlur (smooth.dispatch.cpp:609-826)
 namespace b200cv {
 int gaussian_blur_impl(const b200cvMat* src, const b200cvMat* dst, int kw, int kh, double sigma1, double sigma2, int border, void* stream,
@@ -673,7 +682,7 @@ int b200cv::gaussian_blur_impl(const b200cvMat* src, const b200cvMat* dst, int k
     if ((rc = check_mat(src, "src")) || (rc = check_mat(dst, "dst"))) return rc;
     B200_REQUIRE(src->type == dst->type, "GaussianBlur: dst type must equal src type");
     const int depth = B200CV_DEPTH(src->type);
-    if (depth != B200CV_8U && depth != B200CV_32F) return B200CV_NOT_IMPLEMENTED;
+    if (depth != B200CV_8U && depth != B200CV_32F && depth != B200CV_16U) return B200CV_NOT_IMPLEMENTED;
     int b = border & ~B200CV_BORDER_ISOLATED;
     if (b != B200CV_BORDER_CONSTANT) {           // :624-631
         if (src->rows == 1) kh = 1;
@@ -688,6 +697,19 @@ int b200cv::gaussian_blur_impl(const b200cvMat* src, const b200cvMat* dst, int k
     sigma1 = sigma1 > 0 ? sigma1 : 0;
     sigma2 = sigma2 > 0 ? sigma2 : 0;
     std::vector<float> kx(kw), ky(kh);
+    if (depth == B200CV_16U) {       // 16.16 fixed point, bit-exact (gauss_u16.cu)
+        if (dog) return B200CV_NOT_IMPLEMENTED;
+        std::vector<int64_t> fx, fy;
+        gaussian_kernel_fixed(kw, sigma1, 16, fx);
+        gaussian_kernel_fixed(kh, sigma2, 16, fy);
+        Img s = make_img(src), d = make_img(dst);
+        B200_REQUIRE(s.frames == d.frames, "src/dst batch mismatch");
+        B200_REQUIRE(src->data != dst->data, "in-place filtering is not supported: pass distinct buffers");
+        B200_REQUIRE(src->cols == dst->cols && src->rows == dst->rows, "src/dst size mismatch");
+        if (b < 0 || b > B200CV_BORDER_REFLECT_101) return B200CV_NOT_IMPLEMENTED;
+        std::vector<long long> lx(fx.begin(), fx.end()), ly(fy.begin(), fy.end());
+        return gauss_u16_impl(s, d, B200CV_CN(src->type), lx.data(), kw, ly.data(), kh, b, as_stream(stream));
+    }
     if (depth == B200CV_8U) {
         if (dog) return B200CV_NOT_IMPLEMENTED;
         std::vector<int64_t> fx, fy;

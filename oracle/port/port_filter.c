@@ -214,7 +214,7 @@ PORT_API int port_gaussian_blur(const void* src, size_t sstep, void* dst, size_t
     int b = border & ~16;
     if (b != PB_CONSTANT) { if (h == 1) kh = 1; if (w == 1) kw = 1; }
     if (kw == 1 && kh == 1) {
-        for (int y = 0; y < h; y++) memcpy((char*)dst + (size_t)y * dstep, (const char*)src + (size_t)y * sstep, (size_t)w * cn * port_esz(depth));
+        for (int y = 0; y < h; y++) memcpy((char*)dst + (size_t)y * dstep, (const char*)src + (size_t)y * sstep, (size_t)w * cn * (depth == 2 ? 2 : port_esz(depth)));
         return 0;
     }
     if (s2 <= 0) s2 = s1;
@@ -222,6 +222,37 @@ PORT_API int port_gaussian_blur(const void* src, size_t sstep, void* dst, size_t
     if (kh <= 0 && s2 > 0) kh = port_round(s2 * (depth == P_8U ? 3 : 4) * 2 + 1) | 1;
     if (kw <= 0 || kh <= 0 || !(kw & 1) || !(kh & 1) || kw > 255 || kh > 255) return -1;
     if (s1 < 0) s1 = 0; if (s2 < 0) s2 = 0;
+    if (depth == 2) {
+        /* CV_16U: the 16.16 fixed-point path (fixedSmoothInvoker<uint16_t, ufixedpoint32>, smooth.simd.hpp:1925-2197; fixedpoint.inl.hpp:...):
+         * rows   H = sum tap_x * p   in 32 bits (ufixedpoint32 * uint16 and + saturate; taps sum to 2^16, so nothing saturates for real taps)
+         * columns   sum tap_y * H   in 64 bits (32.32), result (v + 2^31) >> 32 saturated to 16 bits */
+        long long fx[256], fy[256];
+        port_gaussian_taps_fixed(kw, s1, 16, fx);
+        port_gaussian_taps_fixed(kh, s2, 16, fy);
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+                for (int c = 0; c < cn; c++) {
+                    unsigned long long acc = 0;
+                    for (int j = 0; j < kh; j++) {
+                        int sy = port_border(y + j - kh / 2, h, b);
+                        if (sy < 0) continue;
+                        const unsigned short* row = (const unsigned short*)((const char*)src + (size_t)sy * sstep);
+                        unsigned long long line = 0;
+                        for (int i = 0; i < kw; i++) {
+                            int sx = port_border(x + i - kw / 2, w, b);
+                            if (sx < 0) continue;
+                            unsigned long long pr = (unsigned long long)fx[i] * row[sx * cn + c];
+                            if (pr > 0xFFFFFFFFull) pr = 0xFFFFFFFFull;
+                            line += pr; if (line > 0xFFFFFFFFull) line = 0xFFFFFFFFull;
+                        }
+                        unsigned long long pr = (unsigned long long)fy[j] * line, s = acc + pr;
+                        acc = s < acc ? ~0ull : s;
+                    }
+                    unsigned long long r = (acc + (1ull << 31)) >> 32;
+                    ((unsigned short*)((char*)dst + (size_t)y * dstep))[x * cn + c] = (unsigned short)(r > 65535 ? 65535 : r);
+                }
+        return 0;
+    }
     if (depth == P_8U) {
         long long fx[256], fy[256];
         port_gaussian_taps_fixed(kw, s1, 8, fx);

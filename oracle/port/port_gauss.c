@@ -55,7 +55,7 @@ void port_gaussian_taps(int n, double sigma, double* out)
     if (!(n & 1)) out[half + 1] = inv;
 }
 
-void port_gaussian_taps_fixed(int n, double sigma, int bits, long long* out)
+PORT_API void port_gaussian_taps_fixed(int n, double sigma, int bits, long long* out)
 {
     double* k = (double*)malloc(sizeof(double) * n);
     port_gaussian_taps(n, sigma, k);

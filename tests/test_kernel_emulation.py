@@ -490,3 +490,40 @@ def test_emulated_masked_match_template_vs_port(mtmask_emu, port, rng):
             for method in range(6):
                 got, want = mtmask_emu(im, tt, mk, method), port.matchTemplateMasked(im, tt, method, mk)
                 assert np.array_equal(got, want), "masked matchTemplate %s mask %s method %d" % (im.dtype, mk.dtype, method)
+
+
+# ---- GaussianBlur CV_16U, 16.16 fixed point (gauss_u16.cu) ---------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gauss16_emu(port):
+    lib = build_emulation("gauss_u16.cu", "int emu_gauss_u16(const b200cvMat* s, const b200cvMat* d, const long long* fx, int kw, const long long* fy, int kh, int border)",
+                          "    return b200cv::gauss_u16_impl(b200cv::make_img(s), b200cv::make_img(d), B200CV_CN(s->type), fx, kw, fy, kh, border, nullptr);")
+
+    def run(img, k, sigma, border):
+        fx = np.zeros(k, np.int64)
+        port.lib.port_gaussian_taps_fixed(k, ctypes.c_double(sigma), 16, fx.ctypes.data_as(ctypes.c_void_p))
+        dst = np.zeros_like(img)
+        ms, md = mat_of(img), mat_of(dst)
+        ms.type |= 2; md.type |= 2
+        lp = ctypes.POINTER(ctypes.c_longlong)
+        rc = lib.emu_gauss_u16(ctypes.byref(ms), ctypes.byref(md), fx.ctypes.data_as(lp), k, fx.ctypes.data_as(lp), k, border)
+        assert rc == 0, "emulated gauss_u16_impl returned %d" % rc
+        return dst
+    return run
+
+
+def test_emulated_gaussian_u16_vs_port(gauss16_emu, port, rng):
+    import opencv_b200 as C
+    for shape in [(37, 53), (40, 66, 3), (20, 31, 4), (1, 40), (33, 1)]:
+        img = rng.integers(0, 65536, shape, dtype=np.uint16)
+        ext = np.where(rng.random(shape) < 0.5, 0, 65535).astype(np.uint16)
+        for im in (img, ext):
+            for k, s in [(3, 0), (5, 0), (7, 1.5), (15, 3.0), (31, 0)]:
+                if (shape[0] == 1 or shape[1] == 1):
+                    continue                              # 1-pixel dimensions shrink the kernel in the dispatcher (smooth.dispatch.cpp:624-631), not in this file
+                for border in (4, 1, 0, 2):
+                    assert np.array_equal(gauss16_emu(im, k, s, border), port.GaussianBlur(im, (k, k), s, s, border)), "u16 %s k=%d s=%g border=%d" % (shape, k, s, border)
+    # the product's own 16-bit taps (host_tables.cpp, softdouble exp) are the port's
+    for k, s in [(3, 0), (5, 0), (7, 1.5), (9, 0), (15, 3.0), (31, 0), (5, 0.3), (13, 2.2)]:
+        want = np.zeros(k, np.int64)
+        port.lib.port_gaussian_taps_fixed(k, ctypes.c_double(s), 16, want.ctypes.data_as(ctypes.c_void_p))
+        assert list(C.getGaussianKernelFixed(k, s, 16)) == list(want) and int(want.sum()) == 65536, "16-bit taps k=%d sigma=%g" % (k, s)

@@ -192,6 +192,18 @@ def test_port_vs_reference_masked_match_template(ref, port, rng):
         assert np.unravel_index(b.argmin() if method == 1 else b.argmax(), b.shape) == (100, 150)
 
 
+def test_port_vs_reference_gaussian_u16(ref, port, rng):
+    """GaussianBlur CV_16U: 16.16 fixed-point taps, 32-bit rows, 64-bit columns (fixedSmoothInvoker<uint16_t, ufixedpoint32>): bit-exact"""
+    for shape in [(37, 53), (64, 96, 3), (20, 31, 4), (1, 40), (33, 1)]:
+        img = rng.integers(0, 65536, shape, dtype=np.uint16)
+        ext = np.where(rng.random(shape) < 0.5, 0, 65535).astype(np.uint16)
+        for im in (img, ext):
+            for k, s in [(3, 0), (5, 0), (7, 1.5), (9, 0), (15, 3.0), (0, 1.2), (31, 0), (5, 0.3)]:
+                for border in (4, 1, 0, 2):
+                    assert np.array_equal(ref.GaussianBlur(im, (k, k), s, s, border), port.GaussianBlur(im, (k, k), s, s, border)), \
+                        "u16 %s k=%d s=%g border=%d" % (shape, k, s, border)
+
+
 def test_port_vs_reference_two_plane(ref, port, rng):
     """cv::cvtColorTwoPlane: the same arithmetic with separate luma / chroma buffers; also equal to cvtColor on the concatenated planes"""
     for (h, w) in [(4, 6), (18, 34), (250, 322)]:
