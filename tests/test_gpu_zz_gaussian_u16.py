@@ -18,7 +18,7 @@ def test_gaussian_u16(cvb, oracle, rng, shape):
     ext = np.where(rng.random(shape) < 0.5, 0, 65535).astype(np.uint16)
     for im in (img, ext):
         for k, s in [(3, 0), (5, 0), (7, 1.5), (9, 0), (15, 3.0), (0, 1.2), (31, 0), (5, 0.3)]:
-            for border in (4, 1, 0, 2):
+            for border in (4, 1, 0, 2, 3):
                 got = cpu(cvb.GaussianBlur(gpu(im), (k, k), s, s, border))
                 assert_exact(got, oracle.GaussianBlur(im, (k, k), s, s, border), "GaussianBlur u16 %s k=%d s=%g border=%d" % (shape, k, s, border))
 
