@@ -63,9 +63,6 @@ def test_host_batch_pipeline(cvb, oracle, rng):
     mx = (xx * 2.1 + 3).astype(np.float32); my = (yy * 2.3 + 5 * np.sin(xx / 17)).astype(np.float32)
     rm = hal.remap(batch[:3], mx, my, 2, 4)
     assert_exact(rm[2], oracle.remap(batch[2], mx, my, 2, 4), "host remap")
-    g8 = np.ascontiguousarray(batch[:4, :, :, 1:2])
-    sc = hal.Scharr(g8, 3, 1, 0)
-    assert_exact(sc[3, :, :, 0], oracle.Sobel(g8[3, :, :, 0], 3, 1, 0, -1), "host Scharr")
     bl = hal.blur(batch[:5], (11, 11))
     assert_exact(bl[4], oracle.blur(batch[4], (11, 11)), "host blur")
     w = hal.warpAffine(batch[:3], M, (640, 480))

@@ -10,6 +10,18 @@ from util import assert_close, gpu
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="GFTTDetector wrapper has not run on a B200 yet")]
 
 
+def test_host_sobel_scharr_wrappers(cvb, oracle, rng):
+    """opencv_b200.hal.Sobel / Scharr: numpy wrappers over b200cv_host_sobel (the call the HAL hook already makes)"""
+    from opencv_b200 import hal
+    from util import assert_exact
+    batch = rng.integers(0, 256, (4, 240, 320, 1), dtype=np.uint8)
+    sc = hal.Scharr(batch, 3, 1, 0)
+    assert_exact(sc[3, :, :, 0], oracle.Sobel(batch[3, :, :, 0], 3, 1, 0, -1), "host Scharr")
+    so = hal.Sobel(batch[0, :, :, 0].copy(), 5, 0, 1, 3, scale=0.5)
+    want = oracle.Sobel(batch[0, :, :, 0], 5, 0, 1, 3, scale=0.5)
+    assert np.abs(so - want).max() <= 1e-4
+
+
 def test_gftt_detector(cvb, oracle, rng):
     small = rng.random((32, 42)).astype(np.float32)
     gray = (np.kron(small, np.ones((8, 8), np.float32)) * 255).astype(np.uint8)[:240, :320]
