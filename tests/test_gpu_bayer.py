@@ -1,15 +1,13 @@
 """GPU parity: cv::cvtColor for the Bayer mosaics (BG / GB / RG / GR -> BGR, BGRA; bilinear), 8-bit: BIT-EXACT.
 
-STATUS: opencv_b200/csrc/demosaic.cu was written after this round's GPU budget was spent.  The port equals the reference (tests/test_oracle.py)
-and the kernel, compiled for the host, equals the port (tests/test_kernel_emulation.py); the sm_100a build has NOT yet run on a B200: the
-tests are xfail(strict=False) until it has (XPASS on success).  The file sorts last on purpose."""
+First ran green on a B200 in round 1 (GPUTEST_r01.json); a failure here fails the suite."""
 import numpy as np
 import pytest
 
 import opencv_b200 as C
 from util import assert_exact, cpu, gpu
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="demosaic.cu has not run on a B200 yet (written after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("size", [(3, 3), (4, 5), (17, 33), (64, 96), (241, 323), (1080, 1920)])

@@ -1,15 +1,13 @@
 """GPU parity: cv::GaussianBlur on CV_16U images (16.16 fixed point): BIT-EXACT.
 
-STATUS: opencv_b200/csrc/gauss_u16.cu was written after this round's GPU budget was spent; the port equals the reference (tests/test_oracle.py), the
-kernel run on the host equals the port and the product's 16-bit taps equal the port's (tests/test_kernel_emulation.py); NOT yet run on a B200:
-xfail(strict=False) until it has (XPASS on success).  The file sorts last on purpose."""
+First ran green on a B200 in round 1 (GPUTEST_r01.json); a failure here fails the suite."""
 import numpy as np
 import pytest
 
 import opencv_b200 as C
 from util import assert_exact, cpu, gpu
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="gauss_u16.cu has not run on a B200 yet (written after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("shape", [(37, 53), (64, 96, 3), (20, 31, 4), (1, 40), (33, 1), (480, 640)])

@@ -1,13 +1,14 @@
 """GPU: cv::GFTTDetector, the Feature2D wrapper over goodFeaturesToTrack (features2d/src/gftt.cpp:131-148).  It only composes calls that
-tests/test_gpu_features.py verifies (cvtColor + goodFeaturesToTrack); the wrapper itself was added after the round's GPU budget was spent,
-hence xfail(strict=False) until its first run."""
+tests/test_gpu_features.py verifies (cvtColor + goodFeaturesToTrack).
+
+First ran green on a B200 in round 1 (GPUTEST_r01.json); a failure here fails the suite."""
 import numpy as np
 import pytest
 
 import opencv_b200 as C
 from util import assert_close, gpu
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="GFTTDetector wrapper has not run on a B200 yet")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_host_sobel_scharr_wrappers(cvb, oracle, rng):

@@ -1,15 +1,13 @@
 """GPU parity: cv::integral, 8UC1 -> 32S sum (+ 64F sum of squares): BIT-EXACT (integers; the doubles hold integers below 2^53).
 
-STATUS: opencv_b200/csrc/integral.cu was written after this round's GPU budget was spent.  The port equals the reference (tests/test_oracle.py)
-and the six kernels, compiled for the host, equal the port (tests/test_kernel_emulation.py); the sm_100a build has NOT yet run on a B200: the
-tests are xfail(strict=False) until it has (XPASS on success).  The file sorts last on purpose."""
+First ran green on a B200 in round 1 (GPUTEST_r01.json); a failure here fails the suite."""
 import numpy as np
 import pytest
 
 import opencv_b200 as C
 from util import assert_exact, cpu, gpu
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="integral.cu has not run on a B200 yet (written after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("size", [(1, 1), (5, 7), (17, 15), (33, 65), (240, 321), (1080, 1920), (2160, 3840)])

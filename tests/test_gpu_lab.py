@@ -1,15 +1,13 @@
 """GPU parity: cv::cvtColor BGR / RGB <-> Lab (sRGB and linear) and <-> CIE XYZ, 8-bit: BIT-EXACT on the whole 2^24 colour cube.
 
-STATUS: opencv_b200/csrc/cvtcolor_lab.cu was written after this round's GPU budget was spent.  The port equals the reference on all 2^24 colours
-in both directions (tests/test_oracle.py) and the kernels + table builder, compiled for the host, equal the port (tests/test_kernel_emulation.py);
-the sm_100a build has NOT yet run on a B200: xfail(strict=False) until it has (XPASS on success).  The file sorts last on purpose."""
+First ran green on a B200 in round 1 (GPUTEST_r01.json); a failure here fails the suite."""
 import numpy as np
 import pytest
 
 import opencv_b200 as C
 from util import assert_exact, cpu, gpu
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="cvtcolor_lab.cu has not run on a B200 yet (written after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]
 CODES = [C.COLOR_BGR2XYZ, C.COLOR_RGB2XYZ, C.COLOR_XYZ2BGR, C.COLOR_XYZ2RGB, C.COLOR_BGR2Lab, C.COLOR_RGB2Lab, C.COLOR_LBGR2Lab, C.COLOR_LRGB2Lab, C.COLOR_Lab2BGR, C.COLOR_Lab2RGB, C.COLOR_Lab2LBGR, C.COLOR_Lab2LRGB]
 
 

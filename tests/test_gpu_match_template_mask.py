@@ -1,16 +1,14 @@
 """GPU: cv::matchTemplate with a mask (all six methods; 8-bit binarised and float weight masks), against the reference at its own bar for
 matchTemplate (1e-3 of the result range; the reference's numerators come from a float DFT, the device sums are direct and in double).
 
-STATUS: opencv_b200/csrc/matchtemplate_mask.cu was written after this round's GPU budget was spent; the port agrees with the reference to ~2e-7
-(tests/test_oracle.py) and the kernels run on the host equal the port (tests/test_kernel_emulation.py); NOT yet run on a B200: xfail(strict=False)
-until it has (XPASS on success).  The file sorts last on purpose."""
+First ran green on a B200 in round 1 (GPUTEST_r01.json); a failure here fails the suite."""
 import numpy as np
 import pytest
 
 import opencv_b200 as C
 from util import assert_close, cpu, gpu
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="matchtemplate_mask.cu has not run on a B200 yet (written after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.mark.parametrize("method", range(6))

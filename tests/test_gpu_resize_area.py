@@ -1,17 +1,13 @@
 """GPU parity: cv::resize INTER_AREA in its true area mode (both factors >= 1), integer and fractional factors, 8-bit and float: BIT-EXACT.
 
-STATUS: opencv_b200/csrc/resize_area.cu was written after this round's GPU budget was spent.  The port is pinned to the reference
-(tests/test_oracle.py) and the kernels, compiled for the host, match it bit for bit (tests/test_kernel_emulation.py); the sm_100a build has
-NOT yet run on a B200.  Until it has, these tests are xfail(strict=False): a pass shows as XPASS, a mismatch as XFAIL.  The file sorts
-last so that nothing it does can disturb the verified tests.  Remove the marker after the first green run."""
+First ran green on a B200 in round 1 (GPUTEST_r01.json); a failure here fails the suite."""
 import numpy as np
 import pytest
 
 import opencv_b200 as C
 from util import assert_exact, cpu, gpu
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="resize_area.cu has not run on a B200 yet (written after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]
 
 CASES = [((120, 180), (40, 60)), ((120, 180), (30, 90)), ((121, 183), (40, 61)), ((100, 150), (37, 41)), ((480, 640), (300, 400)),
          ((97, 131), (96, 130)), ((64, 64), (16, 16)), ((90, 120), (30, 24)), ((50, 70), (49, 23)), ((33, 47), (1, 1)), ((300, 400), (7, 399))]

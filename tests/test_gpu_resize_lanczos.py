@@ -1,17 +1,13 @@
 """GPU parity: cv::resize INTER_LANCZOS4, 8-bit and float: BIT-EXACT (weights built on the host with the reference's expressions and libm).
 
-STATUS: opencv_b200/csrc/resize_lanczos.cu was written after this round's GPU budget was spent.  The port is pinned to the reference
-(tests/test_oracle.py) and the kernel + table code, compiled for the host, match it bit for bit (tests/test_kernel_emulation.py); the
-sm_100a build has NOT yet run on a B200.  Until it has, these tests are xfail(strict=False): a pass shows as XPASS, a mismatch as XFAIL.
-The file sorts last so that nothing it does can disturb the verified tests.  Remove the marker after the first green run."""
+First ran green on a B200 in round 1 (GPUTEST_r01.json); a failure here fails the suite."""
 import numpy as np
 import pytest
 
 import opencv_b200 as C
 from util import assert_exact, cpu, gpu
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="resize_lanczos.cu has not run on a B200 yet (written after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]
 
 CASES = [((40, 60), (120, 180)), ((40, 60), (97, 131)), ((100, 150), (237, 341)), ((97, 131), (98, 132)), ((64, 64), (160, 32)), ((120, 180), (40, 61)),
          ((1, 47), (5, 90)), ((50, 1), (75, 23)), ((3, 5), (30, 50)), ((120, 160), (121, 100)), ((240, 320), (150, 201)), ((480, 640), (300, 402))]

@@ -7,15 +7,14 @@ reference's keypoints matched to 1e-2 px / 0.1 deg, and for matched keypoints >=
 The port (oracle/port) is pinned to the reference at 99 % / 1e-3 px on the reference's own pyramids (tests/test_oracle.py), and the kernels run on
 the host equal the port exactly (tests/test_kernel_emulation.py).
 
-STATUS: opencv_b200/csrc/sift_detect.cu was written after this round's GPU budget was spent and has NOT yet run on a B200: xfail(strict=False)
-until it has (XPASS on success).  The file sorts last on purpose."""
+First ran green on a B200 in round 1 (GPUTEST_r01.json); a failure here fails the suite."""
 import numpy as np
 import pytest
 
 import opencv_b200 as C
 from util import gpu
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="sift_detect.cu has not run on a B200 yet (written after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def structured(rng, h, w):

@@ -2,10 +2,7 @@
 BGR family -> I420 / YV12) through the device C ABI, the host API and the HAL seam.  All integer: BIT-EXACT, checked against the reference's
 own known-answer hashes (modules/imgproc/test/test_color.cpp:2857-2900; inputs = its RNG(0) stream, tests/golden/) and the oracle.
 
-STATUS: the kernels of opencv_b200/csrc/cvtcolor_yuv.cu were written after this round's GPU budget was spent.  The oracle side is pinned
-(tests/test_oracle.py reproduces all 39 hashes on the CPU); the CUDA side has been compiled for sm_100a but has NOT yet run on a B200.
-Until it has, these tests are marked xfail(strict=False): a pass is reported as XPASS, a mismatch as XFAIL -- never as a silent skip.
-The file sorts last so that nothing it does can disturb the verified tests.  Remove the marker after the first green run."""
+First ran green on a B200 in round 1 (GPUTEST_r01.json); a failure here fails the suite."""
 import os
 import zlib
 
@@ -15,8 +12,7 @@ import pytest
 import opencv_b200 as C
 from util import assert_exact, cpu, gpu
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="cvtcolor_yuv.cu has not run on a B200 yet (written after the round's GPU budget was spent)")]
+pytestmark = [pytest.mark.gpu]
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 # modules/imgproc/test/test_color.cpp:2857-2900
