@@ -291,6 +291,8 @@ int gauss_u8_fast(const Img& s, const Img& d, int cn, const int64_t* fx, int kw,
             for (int i = 0; i < 4; i++) { int j = 4 * g + i - o; if (j >= 0 && j < KB) w |= (uint32_t)ty[j] << (8 * i); }
             p.kyw[o][g] = w;
         }
+    // single channel, K <= 9, Gaussian / 8.8 sepFilter2D epilogues: the register-marching kernel (gauss_u8_march.cu)
+    if (cn == 1 && KB <= 9 && sep_mode <= 1) return gauss_u8_march(s, d, KB, tx, ty, border, st, sep_mode, even_limit);
     p.W = s.cols * cn; p.H = s.rows; p.border = border; p.sep_mode = sep_mode; p.even_limit = even_limit;      // W in byte elements
     if (box) p.box = *box;
     p.TH = ((64 - (KB - 1)) / 4) * 4;

@@ -48,12 +48,32 @@ static inline int __float2int_rn(float v) { return (int)lrintf(v); }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __int2float_rn(int a) { return (float)a; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __int_as_float(int a) { float f; memcpy(&f, &a, 4); return f; }
+static inline int __float_as_int(float f) { int a; memcpy(&a, &f, 4); return a; }
+static inline short sat_s16_emu(int v) { return (short)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline float __double2float_rn(double a) { return (float)a; }
 static inline int __double2int_rn(double a) { return (int)lrint(a); }
+
+// packed-integer intrinsics (PTX dp4a.u32.u32, dp2a.lo/hi.u32.u32, prmt) for kernels whose arithmetic core is host-testable
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c)
+{
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+    return c;
+}
+static inline unsigned __dp2a_lo(unsigned a, unsigned b, unsigned c) { return c + (a & 0xffffu) * (b & 0xffu) + (a >> 16) * ((b >> 8) & 0xffu); }
+static inline unsigned __dp2a_hi(unsigned a, unsigned b, unsigned c) { return c + (a & 0xffffu) * ((b >> 16) & 0xffu) + (a >> 16) * ((b >> 24) & 0xffu); }
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)
+{
+    const unsigned long long v = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((s >> (4 * i)) & 7))) & 0xffu) << (8 * i);
+    return r;
+}
 
 template <typename F>
 static inline void emu_launch(dim3 grid, dim3 block, F thread_body)

@@ -42,6 +42,20 @@ def build_emulation(cu_name, entry_decl, entry_body):
     return ctypes.CDLL(so)
 
 
+def build_emulation_raw(cu_name, entry_decl, entry_body):
+    """like build_emulation for sources whose __global__ kernels are compiled out on the host (TMA / shared memory): only their
+    __device__ arithmetic cores are built"""
+    os.makedirs(OUT, exist_ok=True)
+    src = open(os.path.join(CSRC, cu_name)).read()
+    tag = re.search(r"(\w+)\(", entry_decl).group(1)
+    cpp = os.path.join(OUT, tag + ".cpp")
+    so = os.path.join(OUT, tag + ".so")
+    with open(cpp, "w") as f:
+        f.write("#define B200CV_HOST_EMULATION 1\n" + src + STUBS + 'extern "C" ' + entry_decl + "\n{\n" + entry_body + "\n}\n")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", CSRC, "-I", os.path.join(ROOT, "tests", "emu"), cpp, "-o", so])
+    return ctypes.CDLL(so)
+
+
 class Mat(ctypes.Structure):
     _fields_ = [("data", ctypes.c_void_p), ("step", ctypes.c_size_t), ("cols", ctypes.c_int), ("rows", ctypes.c_int), ("type", ctypes.c_int),
                 ("frames", ctypes.c_int), ("frame_step", ctypes.c_size_t)]
@@ -429,14 +443,14 @@ def test_emulated_area_mode_weights_in_resize_cu():
     expressions (resize.cpp:4104-4109, :4158-4163) evaluated in numpy: s = floor(d * scale), f = float((d + 1) - (s + 1) * inv_scale), f <= 0 -> 0,
     else f - floor(f); and its default branch with f = float((d + 0.5) * scale - 0.5), s = floor(f), f -= s"""
     os.makedirs(OUT, exist_ok=True)
-    src = open(os.path.join(CSRC, "resize.cu")).read()
+    src = open(os.path.join(CSRC, "resize.cuh")).read()
     m = re.search(r"__device__ __forceinline__ void linear_coef\(.*?\n}\n", src, re.S)
-    assert m, "linear_coef not found in resize.cu"
+    assert m, "linear_coef not found in resize.cuh"
     fn = m.group(0).replace("bool area_mode = false, double inv_scale = 0.", "bool area_mode, double inv_scale")
     cpp = os.path.join(OUT, "emu_linear_coef.cpp")
     so = os.path.join(OUT, "emu_linear_coef.so")
     with open(cpp, "w") as f:
-        f.write('#include "cuda_emu.h"\nstatic inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }\n' + fn +
+        f.write('#include "cuda_emu.h"\n' + fn +
                 'extern "C" void emu_linear_coef(int n, double scale, int ssize, int clamp, int area, double inv, int* s, float* fr)\n'
                 "{ for (int d = 0; d < n; d++) linear_coef(d, scale, ssize, s[d], fr[d], clamp != 0, area != 0, inv); }\n")
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I", os.path.join(ROOT, "tests", "emu"), cpp, "-o", so])
@@ -527,3 +541,141 @@ def test_emulated_gaussian_u16_vs_port(gauss16_emu, port, rng):
         want = np.zeros(k, np.int64)
         port.lib.port_gaussian_taps_fixed(k, ctypes.c_double(s), 16, want.ctypes.data_as(ctypes.c_void_p))
         assert list(C.getGaussianKernelFixed(k, s, 16)) == list(want) and int(want.sum()) == 65536, "16-bit taps k=%d sigma=%g" % (k, s)
+
+
+# ---- GaussianBlur / 8.8 sepFilter2D CV_8UC1, K <= 9: the warp-streaming kernel (gauss_u8_march.cu) ------------------------------------------
+# TMA and mbarriers cannot run on the host; everything a lane does with a staged chunk can.  The test walks the kernel's own work
+# decomposition (items -> chunks), stages every 256 x CH chunk with cv::borderInterpolate (what the TMA zero fill, the row-wise mirrored
+# loads and the apron patch produce together) and runs gm_lane_chunk for the 32 lanes, each with its register window carried across chunks.
+@pytest.fixture(scope="module")
+def gauss_march_emu(port):
+    body = r"""
+    using namespace b200cv;
+    Img si = make_img(s), di = make_img(d);
+    GMParams p; gm_fill_params(p, KB, tx, ty);
+    p.W = si.cols; p.H = si.rows; p.border = border; p.sep_mode = sep_mode; p.even_limit = even_limit;
+    const int H = KB / 2, CH = KB == 3 ? GMCfg<3>::CH : KB == 5 ? GMCfg<5>::CH : KB == 7 ? GMCfg<7>::CH : GMCfg<9>::CH;
+    p.tiles_x = (p.W + GM_OW - 1) / GM_OW;
+    p.seg_rows = ((seg_rows + CH - 1) / CH) * CH; p.nseg = (p.H + p.seg_rows - 1) / p.seg_rows; p.nitems = p.tiles_x * p.nseg * si.frames;
+    unsigned char* buf = (unsigned char*)malloc((size_t)GM_IW * CH);
+#define RUN(K, SEP) do { for (int item = 0; item < p.nitems; item++) { const GMItem g = gm_item<K>(p, item); \
+        for (int lane = 0; lane < 32; lane++) { uint32_t win[GMCfg<K>::NP][8]; memset(win, 0x5A, sizeof(win)); \
+            for (int chunk = 0; chunk < g.nchunks; chunk++) { \
+                for (int r = 0; r < CH; r++) for (int c = 0; c < GM_IW; c++) { \
+                    const int gy = g.ys - H + chunk * CH + r, gx = g.x0 - GM_RA + c; \
+                    const int sy = border_interpolate(gy, p.H, border), sx = border_interpolate(gx, p.W, border); \
+                    buf[r * GM_IW + c] = (sy < 0 || sx < 0) ? 0 : si.row<unsigned char>(g.f, sy)[sx]; } \
+                gm_lane_chunk<K, SEP>(buf, lane, p, di, g, chunk, win); } } } } while (0)
+    if (sep_mode) { if (KB == 3) RUN(3, true); else if (KB == 5) RUN(5, true); else if (KB == 7) RUN(7, true); else RUN(9, true); }
+    else { if (KB == 3) RUN(3, false); else if (KB == 5) RUN(5, false); else if (KB == 7) RUN(7, false); else RUN(9, false); }
+    free(buf);
+    return 0;"""
+    lib = build_emulation_raw("gauss_u8_march.cu", "int emu_gauss_march(const b200cvMat* s, const b200cvMat* d, int KB, const unsigned char* tx, const unsigned char* ty, int border, int sep_mode, int even_limit, int seg_rows)", body)
+
+    def run(img, k, sigma, border, sep=False, seg_rows=64):
+        fx = np.zeros(k, np.int64)
+        port.lib.port_gaussian_taps_fixed(k, ctypes.c_double(sigma), 8, fx.ctypes.data_as(ctypes.c_void_p))
+        assert fx.sum() == 256 and fx.max() <= 255
+        t = fx.astype(np.uint8)
+        dst = np.full_like(img, 0xCD)
+        ms, md = mat_of(img), mat_of(dst)
+        even_limit = (img.shape[-1] // 16) * 16 if sep else 0           # sepfilter.cu: ((cols * cn) / 16) * 16
+        rc = lib.emu_gauss_march(ctypes.byref(ms), ctypes.byref(md), k, t.ctypes.data_as(ctypes.c_void_p), t.ctypes.data_as(ctypes.c_void_p), border, int(sep), even_limit, seg_rows)
+        assert rc == 0
+        return (dst, (t / 256.0).astype(np.float32)) if sep else dst
+    return run
+
+
+def test_emulated_gaussian_march_vs_port(gauss_march_emu, port, rng):
+    for shape in [(37, 53), (150, 250), (131, 224), (300, 449), (200, 448), (2, 40, 230, 1)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        ext = np.where(rng.random(shape) < 0.5, 0, 255).astype(np.uint8)
+        for im in (img, ext):
+            for k, s in [(3, 0), (5, 0), (7, 0), (9, 0), (5, 1.7), (9, 2.5)]:
+                for border in (4, 1, 0, 2):
+                    got = gauss_march_emu(im, k, s, border, seg_rows=(64 if border != 1 else 1000))
+                    if im.ndim == 4:
+                        want = np.stack([port.GaussianBlur(im[i, :, :, 0], (k, k), s, s, border) for i in range(im.shape[0])])[..., None]
+                    else:
+                        want = port.GaussianBlur(im, (k, k), s, s, border)
+                    assert np.array_equal(got, want), "u8 march %s k=%d s=%g border=%d" % (shape, k, s, border)
+
+
+def test_emulated_sepfilter_8p8_march_vs_port(gauss_march_emu, port, rng):
+    """sepFilter2D's 8.8 fixed-point mode on the same kernel: half-to-even in the reference's vector body, half-up in its tail"""
+    for shape in [(37, 53), (150, 250), (64, 241)]:
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        for k, s in [(3, 0), (5, 0), (7, 0), (9, 0)]:
+            for border in (4, 1, 0, 2):
+                got, taps = gauss_march_emu(img, k, s, border, sep=True)
+                want = port.sepFilter2D(img, -1, taps, taps, borderType=border)
+                assert np.array_equal(got, want), "u8 8.8 sepFilter2D march %s k=%d border=%d" % (shape, k, border)
+
+
+# ---- cv::resize INTER_LINEAR / INTER_CUBIC, 8-bit, tiled separable kernels (resize_sep.cu) ----------------------------------------------------
+# The kernel's shared-memory tile becomes a plain array; the H pass runs for all 256 threads, then the V pass (what the barrier separates).
+@pytest.fixture(scope="module")
+def resize_sep_emu():
+    body = r"""
+    using namespace b200cv;
+    Img si = make_img(s), di = make_img(d);
+    ResizeParams p;
+    p.sw = si.cols; p.sh = si.rows; p.dw = di.cols; p.dh = di.rows;
+    const double inv_x = (double)p.dw / p.sw, inv_y = (double)p.dh / p.sh;
+    p.ifx = 1. / inv_x; p.ify = 1. / inv_y; p.scale_x = 1. / inv_x; p.scale_y = 1. / inv_y; p.inv_x = inv_x; p.inv_y = inv_y; p.area_mode = area_mode;
+    ResTab* xt = (ResTab*)malloc(sizeof(ResTab) * (p.dw + p.dh)); ResTab* yt = xt + p.dw;
+    for (int i = 0; i < p.dw + p.dh; i++) {
+        const bool is_y = i >= p.dw; const int dd = is_y ? i - p.dw : i;
+        (is_y ? yt : xt)[dd] = cubic ? res_tab_entry<true, true>(dd, is_y, p) : res_tab_entry<false, true>(dd, is_y, p);
+    }
+    const int RMAX = rs_host_rmax(p, cubic != 0, DH);
+    int rc = 0;
+#define RUN(CN, CUBIC) do { typedef RSCfg<CN, CUBIC> C; \
+        unsigned char* mid = (unsigned char*)malloc((size_t)RMAX * C::E * C::MIDB); RSRow* yrow = (RSRow*)malloc(sizeof(RSRow) * DH); \
+        for (int f = 0; f < si.frames; f++) for (int y0 = 0; y0 < p.dh; y0 += DH) for (int x0 = 0; x0 < p.dw; x0 += C::DW) { \
+            const int nrows_out = min(DH, p.dh - y0), ncols_out = min((int)C::DW, p.dw - x0); int row_lo, R; \
+            rs_tile_rows<CUBIC>(yt, y0, nrows_out, p.sh, row_lo, R); if (R > RMAX) { rc = 77; R = RMAX; } \
+            memset(mid, 0xEE, (size_t)RMAX * C::E * C::MIDB); \
+            for (int tid = 0; tid < 256; tid++) { if (tid < nrows_out) rs_fill_row<CUBIC>(yrow[tid], yt[y0 + tid], row_lo, p.sh); \
+                const int col = tid % C::DW, rpar = tid / C::DW; \
+                if (col < ncols_out) rs_hpass_thread<CN, CUBIC>(si, f, p, xt[x0 + col], row_lo, R, rpar, 256 / C::DW, mid + (size_t)col * CN * C::MIDB); } \
+            for (int tid = 0; tid < 256; tid++) rs_vpass_thread<CN, CUBIC>(tid, 256, mid, yrow, di, f, p, x0, y0, nrows_out, ncols_out); } \
+        free(mid); free(yrow); } while (0)
+    const int cn = B200CV_CN(s->type);
+    if (cubic) { if (cn == 1) RUN(1, true); else if (cn == 3) RUN(3, true); else RUN(4, true); }
+    else { if (cn == 1) RUN(1, false); else if (cn == 3) RUN(3, false); else RUN(4, false); }
+    free(xt);
+    return rc;"""
+    lib = build_emulation_raw("resize_sep.cu", "int emu_resize_sep(const b200cvMat* s, const b200cvMat* d, int cubic, int area_mode, int DH)", body)
+
+    def run(src, dsize, cubic, DH=16, area_mode=0, pad=0):
+        dw, dh = dsize
+        shape = (dh, dw) if src.ndim == 2 else (dh, dw, src.shape[2])
+        if pad:        # odd pitch / base alignment: the byte paths
+            buf = np.full((shape[0], shape[1] * (1 if src.ndim == 2 else src.shape[2]) + pad), 0xCD, np.uint8)
+            dst = buf[:, :shape[1] * (1 if src.ndim == 2 else src.shape[2])].reshape(shape)
+        else:
+            dst = np.full(shape, 0xCD, np.uint8)
+        ms, md = mat_of(src), mat_of(dst)
+        rc = lib.emu_resize_sep(ctypes.byref(ms), ctypes.byref(md), int(cubic), int(area_mode), DH)
+        assert rc == 0, "emulated resize_sep returned %d" % rc
+        return dst
+    return run
+
+
+def test_emulated_tiled_resize_vs_port(resize_sep_emu, port, rng):
+    cases = [((64, 97), (61, 40)), ((48, 300), (517, 100)), ((33, 70), (140, 66)), ((120, 131), (87, 80)), ((20, 24), (300, 37)), ((301, 260), (173, 201))]
+    for cn in (1, 3, 4):
+        for (sh, sw), (dw, dh) in cases:
+            src = rng.integers(0, 256, (sh, sw) if cn == 1 else (sh, sw, cn), dtype=np.uint8)
+            for cubic in (0, 1):
+                for DH in (8, 16):
+                    got = resize_sep_emu(src, (dw, dh), cubic, DH)
+                    want = port.resize(src, (dw, dh), 2 if cubic else 1)
+                    assert np.array_equal(got, want), "tiled resize cn=%d %dx%d -> %dx%d cubic=%d DH=%d" % (cn, sw, sh, dw, dh, cubic, DH)
+    # unaligned source / destination pitches (byte paths)
+    base = rng.integers(0, 256, (50, 3 * 77 + 1), dtype=np.uint8)
+    src = base[:, 1:].reshape(50, 77, 3)
+    for cubic in (0, 1):
+        got = resize_sep_emu(src, (113, 41), cubic, 16, pad=3)
+        assert np.array_equal(got, port.resize(np.ascontiguousarray(src), (113, 41), 2 if cubic else 1)), "tiled resize, unaligned pitches, cubic=%d" % cubic
