@@ -170,6 +170,9 @@ B200CV_API int b200cv_box_filter(const b200cvMat* src, const b200cvMat* dst, int
 B200CV_API int b200cv_integral(const b200cvMat* src, const b200cvMat* sum, const b200cvMat* sqsum, void* stream);
 /* replaces cv::resize (imgproc.hpp:2422; resize.cpp:4201-4246).  Scale factors are dst/src sizes (fx=fy=0 form). */
 B200CV_API int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int interpolation, void* stream);
+/* cv::resize(src, dst, Size(), fx, fy) (imgproc.hpp:2422, resize.cpp:4214-4228): dst must be round(cols*fx) x round(rows*fy); the sampling
+   scale is fx, fy themselves (not dst/src).  NEAREST / LINEAR / CUBIC; other modes return NOT_IMPLEMENTED when fx, fy differ from the size ratio. */
+B200CV_API int b200cv_resize_scaled(const b200cvMat* src, const b200cvMat* dst, int interpolation, double fx, double fy, void* stream);
 /* replaces cv::warpAffine (imgproc.hpp:2450; imgwarp.cpp:2788-2902). M: 2x3 doubles; inverted unless WARP_INVERSE_MAP. */
 B200CV_API int b200cv_warp_affine(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags,
                                   int border, const double* border_value, void* stream);

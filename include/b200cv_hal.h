@@ -129,6 +129,7 @@ B200CV_API int b200cv_host_sobel(const b200cvMat* src, const b200cvMat* dst, int
 B200CV_API int b200cv_host_box_filter(const b200cvMat* src, const b200cvMat* dst, int ksize_w, int ksize_h, int anchor_x, int anchor_y, int normalize, int border);
 B200CV_API int b200cv_host_integral(const b200cvMat* src, const b200cvMat* sum, const b200cvMat* sqsum);
 B200CV_API int b200cv_host_resize(const b200cvMat* src, const b200cvMat* dst, int interpolation);
+B200CV_API int b200cv_host_resize_scaled(const b200cvMat* src, const b200cvMat* dst, int interpolation, double fx, double fy);
 B200CV_API int b200cv_host_warp_affine(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags, int border, const double* border_value);
 B200CV_API int b200cv_host_warp_perspective(const b200cvMat* src, const b200cvMat* dst, const double* M, int flags, int border, const double* border_value);
 B200CV_API int b200cv_host_pyr_down(const b200cvMat* src, const b200cvMat* dst, int border);

@@ -365,11 +365,15 @@ def resize(src, dsize, fx=0, fy=0, interpolation=INTER_LINEAR, dst=None, stream=
         from . import hal
         return hal.resize(src, dsize, fx, fy, interpolation)
     m = describe(src)
-    if not dsize or dsize[0] <= 0:
+    by_factor = not dsize or dsize[0] <= 0
+    if by_factor:
         dsize = (int(round(m.cols * fx)), int(round(m.rows * fy)))    # saturate_cast<int>(cols*fx): round-half-even like Python's round
     dst = dst if dst is not None else _new(src, size=(int(dsize[0]), int(dsize[1])))
     ms, md = _pair(src, dst)
-    _check(lib().b200cv_resize(ctypes.byref(ms), ctypes.byref(md), int(interpolation), _stream_ptr(stream)), "resize")
+    if by_factor:      # the sampling scale is fx, fy themselves, not dst / src (resize.cpp:4214-4228)
+        _check(lib().b200cv_resize_scaled(ctypes.byref(ms), ctypes.byref(md), int(interpolation), ctypes.c_double(fx), ctypes.c_double(fy), _stream_ptr(stream)), "resize")
+    else:
+        _check(lib().b200cv_resize(ctypes.byref(ms), ctypes.byref(md), int(interpolation), _stream_ptr(stream)), "resize")
     return dst
 
 

@@ -38,6 +38,16 @@ void count_launch(int n = 1);
 
 static inline cudaStream_t as_stream(void* s) { return (cudaStream_t)s; }
 int num_sms();
+#ifdef B200CV_HOST_EMULATION
+struct PerDeviceFlag { bool done = false; bool& cur() { return done; } };
+#else
+// "done once" state that exists PER DEVICE: kernel attributes (cudaFuncSetAttribute) and __device__ tables (cudaMemcpyToSymbol) belong to
+// the device that was current when they were set; a process that drives several GPUs needs them on each.
+struct PerDeviceFlag {
+    bool done[64] = {};
+    bool& cur() { int dev = 0; cudaGetDevice(&dev); return done[dev & 63]; }
+};
+#endif
 
 // ---- device image descriptor (kernel parameter) -----------------------------------------------------------------
 struct Img {

@@ -242,7 +242,7 @@ static int launch_cvt(const Img& src, const Img& dst, const Op& op, cudaStream_t
 
 static int ensure_hsv_tables()
 {
-    static bool done = false;     // benign race: every thread writes identical tables
+    static PerDeviceFlag done_pd; bool& done = done_pd.cur();     // benign race: every thread writes identical tables
     if (done) return B200CV_OK;
     int sdiv[256], h180[256], h256[256];
     sdiv[0] = h180[0] = h256[0] = 0;

@@ -100,7 +100,7 @@ void build_lab_tabs(LabHostTabs& t)          // createLabTabs, color_lab.cpp:122
 
 int ensure_lab_tables()
 {
-    static bool done = false;
+    static PerDeviceFlag done_pd; bool& done = done_pd.cur();
     if (done) return B200CV_OK;
     LabHostTabs t;
     build_lab_tabs(t);

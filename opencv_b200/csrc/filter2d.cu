@@ -17,6 +17,7 @@ namespace b200cv {
 
 int filter2d_tma(const Img& s, const Img& d, int sd, int dd, int cn, const float* k, int kw, int kh, int ax, int ay, float delta, int border, cudaStream_t st);
 int filter2d_u8_tensor(const Img& s, const Img& d, int dd, const float* k, int kw, int kh, int ax, int ay, float delta, int border, cudaStream_t st);
+int filter2d_f32_tensor(const Img& s, const Img& d, const float* k, int kw, int kh, int ax, int ay, float delta, int border, cudaStream_t st);   // filter2d_tc_f32.cu
 
 struct F2DParams {
     float k[33 * 33];    // row-major, row stride = kstride
@@ -127,7 +128,7 @@ static int launch_f2d_fast(const Img& s, const Img& d, const F2DParams& p, cudaS
     constexpr int RP = ((KB / 2 + 3) / 4) * 4;
     size_t smem = (size_t)(F2_TH + p.kh - 1) * (F2_TW + 2 * RP) * sizeof(float);
     auto kern = filter2d_fast_kernel<ST, DT, KB>;
-    static bool attr_done = false;
+    static PerDeviceFlag attr_done_pd; bool& attr_done = attr_done_pd.cur();
     if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_done = true; }
     dim3 grid(div_up((unsigned)s.cols, F2_TW), div_up((unsigned)s.rows, F2_TH), (unsigned)s.frames);
     kern<<<grid, 256, smem, st>>>(s, d, p);
@@ -169,7 +170,7 @@ static int f2d_dispatch(const Img& s, const Img& d, int cn, const float* k, int 
     size_t smem = (size_t)(G2_TH + kh - 1) * (G2_TPX + kw - 1) * cn * sizeof(float);
     if (smem > 100 * 1024) return B200CV_NOT_IMPLEMENTED;
     auto kern = filter2d_generic_kernel<ST, DT>;
-    static bool attr_done = false;
+    static PerDeviceFlag attr_done_pd; bool& attr_done = attr_done_pd.cur();
     if (!attr_done) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_done = true; }
     dim3 grid(div_up((unsigned)s.cols, G2_TPX), div_up((unsigned)s.rows, G2_TH), (unsigned)s.frames);
     kern<<<grid, 256, smem, st>>>(s, d, tp);
@@ -209,6 +210,14 @@ extern "C" int b200cv_filter2d(const b200cvMat* src, const b200cvMat* dst, const
         const char* path = getenv("B200CV_FILTER2D_PATH");
         if (!(path && !strcmp(path, "direct"))) {
             rc = filter2d_u8_tensor(s, d, dd, kernel, kw, kh, ax, ay, fd, border, st);
+            if (rc != B200CV_NOT_IMPLEMENTED) return rc;
+        }
+    }
+    // float images: same switch point (the reference's DFT regime), 3 x BF16 on tcgen05 with FP32 accumulation (filter2d_tc_f32.cu)
+    if (sd == B200CV_32F && dd == B200CV_32F && cn == 1 && kw * kh >= (tc_min_taps ? tc_min_taps : 130)) {
+        const char* path = getenv("B200CV_FILTER2D_PATH");
+        if (!(path && !strcmp(path, "direct"))) {
+            rc = filter2d_f32_tensor(s, d, kernel, kw, kh, ax, ay, fd, border, st);
             if (rc != B200CV_NOT_IMPLEMENTED) return rc;
         }
     }

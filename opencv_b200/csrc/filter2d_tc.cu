@@ -250,7 +250,7 @@ template <int EPI>
 static int launch_fc(const CUtensorMap& tm, const unsigned char* bglob, const Img& d, const FCParams& p, size_t smem, int grid, cudaStream_t st)
 {
     auto kern = filter2d_tc_kernel<EPI>;
-    static bool attr = false;
+    static PerDeviceFlag attr_pd; bool& attr = attr_pd.cur();
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_MAX)); attr = true; }
     kern<<<grid, FC_THREADS, smem, st>>>(tm, bglob, d, p);
     cudaError_t e = cudaGetLastError();
@@ -292,8 +292,7 @@ int filter2d_u8_tensor(const Img& s, const Img& d, int dd, const float* k, int k
     if ((size_t)kh * FC_BROW + 2 * abytes > (size_t)FC_SMEM_MAX) return B200CV_NOT_IMPLEMENTED;
     p.na = (int)std::min<size_t>(4, ((size_t)FC_SMEM_MAX - (size_t)kh * FC_BROW) / abytes);
     const size_t smem = (size_t)kh * FC_BROW + p.na * abytes;
-    static int n_sm = 0;
-    if (!n_sm) { int dev = 0; B200_CUDA(cudaGetDevice(&dev)); B200_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)); }
+    const int n_sm = num_sms();
     const int grid = (int)std::min<long long>(nt, n_sm);
 
     // border-extended source, rows padded to a multiple of 16 bytes (TMA)

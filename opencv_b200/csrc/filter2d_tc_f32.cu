@@ -1,0 +1,281 @@
+// filter2d_tc_f32.cu -- float single-channel cv::filter2D with >= 130 taps on 5th-generation tensor cores (tcgen05, kind::f16 with
+// BF16 operands and FP32 accumulators in TMEM): exactly the sizes at which the reference leaves its direct sum for a float DFT
+// (dft_filter_size, filter.dispatch.cpp:1288-1290; its own tolerance there is 1e-4 of the value range, test_filter.cpp:420-425).
+// Smaller kernels stay on the FP32 kernel of filter2d_tma.cu, which reproduces the reference's direct sum bit for bit.
+//
+// Arithmetic: 3 x BF16.  Every float is split into hi = bf16(a) and lo = bf16(a - hi) (|a - hi - lo| <= 2^-16 |a|); the product sum is
+//   sum a k  ~=  sum a_hi k_hi + sum a_hi k_lo + sum a_lo k_hi        (the dropped a_lo k_lo term is another 2^-16)
+// three MMAs into ONE FP32 accumulator.  Relative to sum |a| |k| the error is <= ~4e-5 worst case (all signs aligned), ~1e-6 typical --
+// inside the reference's bar for this regime and below what its float DFT itself loses on 31 x 31 kernels.  BF16 keeps float's exponent
+// range, so no data-dependent scaling (and no reduction pass over the image) is needed.
+//
+// Contraction = the Toeplitz form of filter2d_tc.cu / matchtemplate_tc.cu:
+//   D[m][j] = sum_v sum_k A_v[m][k] * B_v[k][j],   A_v[m][k] = P(y0 + m + v, x0 + k),   B_v[k][j] = K(v, k - j)   (0 outside 0 <= k-j < kw)
+// with P the border-extended image.  Tile = 256 rows x 16 columns (two M128 x N16 accumulators), K = kw + 15 rounded up to 16.
+// N = 16 keeps ALL Toeplitz operands (kh x 2 planes x K x 16 BF16 <= 99 KB) RESIDENT in shared memory next to two A stages, and wastes
+// the least MMA work on Toeplitz zeros (K / kw = 1.55 at 31 x 31).
+//
+// Roles (352 threads, one persistent CTA per SM):
+//   warp 0      producer: per tile the hi and lo strips (K columns x 256 + kh - 1 rows) by TMA in the K-major no-swizzle core-matrix
+//               layout (one 16-byte-wide box column per 8 K elements), ring of 2 stages
+//   warps 1, 2  MMA issuers, one per M-tile: kh x K/16 x 3 tcgen05.mma (M128 x N16 x K16) per tile; a kernel row's A operand is the
+//               same strip with the descriptor start address advanced by one 16-byte row
+//   warps 3-10  epilogue: tcgen05.ld of the other accumulator stage, + delta, 64-byte row stores
+// The border-extended BF16 planes are written once per call by pad_split_kernel (reads 4 B, writes 4 B per pixel).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <cuda_bf16.h>
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace b200cv {
+
+constexpr int FF_N = 16;                      // output columns per tile = MMA N
+constexpr int FF_MT = 2;                      // M-tiles (128 rows) per tile
+constexpr int FF_THREADS = 352;               // producer, 2 issuers, 8 epilogue warps
+constexpr int FF_SMEM_MAX = 227 * 1024 - 1024;
+constexpr int FF_NA = 2;                      // A stages
+
+struct FFTaps { float k[33 * 33]; };
+
+struct FFParams {
+    int kh, kch;                              // kernel rows; 16-byte K chunks per plane (K = 8 * kch, even)
+    int ra_alloc, box_h, nbox;
+    int ow, oh, frames, tiles_x, tiles_y, ntiles;
+    float delta;
+};
+
+// B in global/shared memory: [kernel row v][plane (hi, lo)][chunk c][column j (16)][8 bf16]: element e = plane(K(v, 8c + e - j))
+__global__ void ff_toeplitz_kernel(const __grid_constant__ FFTaps kp, int kw, int kch, __nv_bfloat16* out)
+{
+    const int v = blockIdx.x;
+    const int per_plane = kch * FF_N * 8;
+    for (int idx = threadIdx.x; idx < 2 * per_plane; idx += blockDim.x) {
+        const int pl = idx / per_plane, r = idx - pl * per_plane;
+        const int e = r & 7, j = (r >> 3) % FF_N, c = (r >> 3) / FF_N;
+        const int u = 8 * c + e - j;
+        const float t = (u >= 0 && u < kw) ? kp.k[v * kw + u] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(t);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(t - __bfloat162float(hi));
+        out[(size_t)v * 2 * per_plane + idx] = pl ? lo : hi;
+    }
+}
+
+// border-extended source as two BF16 planes: out[pl][f][y][x] = split(src(border(y - ay), border(x - ax)))
+__global__ void __launch_bounds__(256) ff_pad_split_kernel(Img src, __nv_bfloat16* out, int pw, int ph, int ax, int ay, int border, size_t plane_elems)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= pw) return;
+    const int sy = border_interpolate(y - ay, src.rows, border), sx = border_interpolate(x - ax, src.cols, border);
+    const float a = (sy < 0 || sx < 0) ? 0.f : src.row<float>(f, sy)[sx];        // BORDER_CONSTANT: zeros
+    const __nv_bfloat16 hi = __float2bfloat16_rn(a);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(a - __bfloat162float(hi));
+    const size_t o = ((size_t)f * ph + y) * pw + x;
+    out[o] = hi;
+    out[plane_elems + o] = lo;
+}
+
+__device__ __forceinline__ uint64_t ff_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    // K-major, no swizzle: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void ff_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void ff_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ff_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ff_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void ff_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ff_mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void ff_tmem_ld16(uint32_t taddr, uint32_t* r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+          "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+
+__global__ void __launch_bounds__(FF_THREADS, 1) filter2d_tc_f32_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ bglob,
+                                                                        Img dst, const __grid_constant__ FFParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const uint32_t brow = (uint32_t)2 * p.kch * FF_N * 16;                   // bytes of B per kernel row (both planes)
+    const uint32_t bplane = (uint32_t)p.kch * FF_N * 16;
+    const uint32_t lbo_a = (uint32_t)p.ra_alloc * 16u;                       // one 16-byte-wide column of the strip
+    const uint32_t aplane = (uint32_t)p.kch * lbo_a;
+    const uint32_t abytes = 2 * aplane;                                      // one A stage (hi + lo)
+    unsigned char* sB = smem;                                                // kh x brow, resident
+    unsigned char* sA = smem + (size_t)p.kh * brow;                          // FF_NA stages
+    __shared__ __align__(8) uint64_t b_full, a_full[FF_NA], a_empty[FF_NA], acc_full[2][FF_MT], acc_empty[2][FF_MT];
+    __shared__ uint32_t s_tmem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&b_full, 1);
+        for (int s = 0; s < FF_NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], FF_MT); }
+        for (int s = 0; s < 2; s++)
+            for (int m = 0; m < FF_MT; m++) { mbar_init(&acc_full[s][m], 1); mbar_init(&acc_empty[s][m], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {   // TMEM: 2 stages x FF_MT x 16 columns of FP32 accumulators = 64
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    ff_fence_before();
+    __syncthreads();
+    ff_fence_after();
+    const uint32_t tmem = s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- producer: all of B once, then the hi + lo strips of every tile ----
+            mbar_arrive_expect_tx(&b_full, (uint32_t)p.kh * brow);
+            for (int v = 0; v < p.kh; v++) ff_bulk_load(sB + (size_t)v * brow, bglob + (size_t)v * brow, brow, &b_full);
+            int i = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
+                const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, f = t / (p.tiles_x * p.tiles_y);
+                const int buf = i % FF_NA;
+                mbar_wait(&a_empty[buf], ((i / FF_NA) & 1) ^ 1);
+                mbar_arrive_expect_tx(&a_full[buf], abytes);
+                unsigned char* dstA = sA + (size_t)buf * abytes;
+                for (int pl = 0; pl < 2; pl++)
+                    for (int c = 0; c < p.kch; c++)
+                        for (int b = 0; b < p.nbox; b++)
+                            tma_load_3d(dstA + (size_t)pl * aplane + (size_t)c * lbo_a + (size_t)b * p.box_h * 16, &tmap, tx * FF_N + 8 * c,
+                                        ty * (128 * FF_MT) + b * p.box_h, f + pl * p.frames, &a_full[buf]);
+            }
+        }
+    } else if (warp <= FF_MT) {
+        if (lane == 0) {
+            // ---- MMA issuer of M-tile mt ----
+            const int mt = warp - 1;
+            // instruction descriptor: D = F32 (1 << 4), A = B = BF16 (1 at [7,10) and [10,13)), K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FF_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            mbar_wait(&b_full, 0);
+            const uint32_t b_base = smem_u32(sB);
+            int i = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
+                const int buf = i % FF_NA, acc = i & 1;
+                mbar_wait(&a_full[buf], (i / FF_NA) & 1);
+                mbar_wait(&acc_empty[acc][mt], ((i >> 1) & 1) ^ 1);
+                ff_fence_after();
+                const uint32_t a_base = smem_u32(sA + (size_t)buf * abytes) + (uint32_t)(mt * 128) * 16u;
+                const uint32_t d_addr = tmem + (uint32_t)(acc * FF_MT + mt) * FF_N;
+                for (int v = 0; v < p.kh; v++) {
+                    for (int ks = 0; ks < p.kch / 2; ks++) {
+                        const uint32_t aoff = a_base + (uint32_t)(2 * ks) * lbo_a + (uint32_t)v * 16u;
+                        const uint32_t boff = b_base + (uint32_t)v * brow + (uint32_t)(2 * ks) * (FF_N * 16);
+                        const uint64_t ah = ff_desc(aoff, lbo_a, 128u), al = ff_desc(aoff + aplane, lbo_a, 128u);
+                        const uint64_t bh = ff_desc(boff, FF_N * 16, 128u), bl = ff_desc(boff + bplane, FF_N * 16, 128u);
+                        ff_mma(d_addr, ah, bh, idesc, (v | ks) != 0);
+                        ff_mma(d_addr, ah, bl, idesc, 1);
+                        ff_mma(d_addr, al, bh, idesc, 1);
+                    }
+                }
+                ff_commit(&a_empty[buf]);          // both issuers arrive: the strip may be overwritten once their MMAs have read it
+                ff_commit(&acc_full[acc][mt]);
+            }
+        }
+    } else {
+        // ---- epilogue: warps 3..10; a warp may touch TMEM lanes 32 (warp % 4) .. +31 = accumulator rows; four warps per M-tile ----
+        const int quarter = warp & 3, mt = (warp - 3) >> 2;
+        int i = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
+            const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, f = t / (p.tiles_x * p.tiles_y);
+            const int acc = i & 1;
+            mbar_wait(&acc_full[acc][mt], (i >> 1) & 1);
+            ff_fence_after();
+            const int gx0 = tx * FF_N;
+            const int gy = ty * (128 * FF_MT) + mt * 128 + quarter * 32 + lane;
+            uint32_t r[16];
+            ff_tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * FF_MT + mt) * FF_N, r);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            ff_fence_before();
+            __syncwarp();
+            if (lane == 0) ff_mbar_arrive(&acc_empty[acc][mt]);       // 4 arrivals free the accumulator: the values are in registers
+            if (gy < p.oh) {
+                float* dp = dst.row<float>(f, gy) + gx0;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; j++) v[j] = __fadd_rn(__uint_as_float(r[j]), p.delta);
+                if (gx0 + 16 <= p.ow && ((uintptr_t)dp & 15) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) ((float4*)dp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; j++) if (gx0 + j < p.ow) dp[j] = v[j];
+                }
+            }
+        }
+    }
+    ff_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory");
+}
+
+// filter2D, float single-channel source and destination.
+// returns B200CV_NOT_IMPLEMENTED when the tensor-core path does not apply (the caller uses the direct-sum kernels)
+int filter2d_f32_tensor(const Img& s, const Img& d, const float* k, int kw, int kh, int ax, int ay, float delta, int border, cudaStream_t st)
+{
+    if (kw > 33 || kh > 33 || s.frames >= 32768) return B200CV_NOT_IMPLEMENTED;
+    static thread_local FFTaps taps;
+    for (int i = 0; i < kw * kh; i++) {
+        if (!std::isfinite(k[i])) return B200CV_NOT_IMPLEMENTED;
+        taps.k[i] = k[i];
+    }
+    FFParams p;
+    memset(&p, 0, sizeof(p));
+    p.kh = kh; p.ow = s.cols; p.oh = s.rows; p.frames = s.frames; p.delta = delta;
+    p.kch = 2 * (int)div_up((unsigned)(kw + FF_N - 1), 16);                 // K = kw + 15 rounded up to a multiple of 16 elements
+    p.tiles_x = (int)div_up((unsigned)p.ow, FF_N); p.tiles_y = (int)div_up((unsigned)p.oh, 128 * FF_MT);
+    const long long nt = (long long)p.tiles_x * p.tiles_y * p.frames;
+    if (nt > 0x7fffffff) return B200CV_NOT_IMPLEMENTED;
+    p.ntiles = (int)nt;
+    const int ra = 128 * FF_MT + kh - 1;
+    p.nbox = (ra + 255) / 256;
+    p.box_h = (((ra + p.nbox - 1) / p.nbox) + 7) & ~7;
+    p.ra_alloc = p.nbox * p.box_h;
+    const size_t brow = (size_t)2 * p.kch * FF_N * 16, abytes = (size_t)2 * p.kch * p.ra_alloc * 16;
+    const size_t smem = (size_t)kh * brow + FF_NA * abytes;
+    if (smem > (size_t)FF_SMEM_MAX) return B200CV_NOT_IMPLEMENTED;
+    const int grid = (int)std::min<long long>(nt, num_sms());
+
+    // border-extended source as BF16 hi / lo planes, rows padded to a multiple of 8 elements (16 bytes: TMA)
+    const int pw = (s.cols + kw - 1 + 7) & ~7, ph = s.rows + kh - 1;
+    const size_t plane_elems = (size_t)pw * ph * s.frames;
+    __nv_bfloat16* pbuf = nullptr; unsigned char* bglob = nullptr;
+    B200_CUDA(cudaMallocAsync(&pbuf, plane_elems * 2 * sizeof(__nv_bfloat16), st));
+    B200_CUDA(cudaMallocAsync(&bglob, (size_t)kh * brow, st));
+    ff_toeplitz_kernel<<<kh, 256, 0, st>>>(taps, kw, p.kch, (__nv_bfloat16*)bglob);
+    count_launch();
+    ff_pad_split_kernel<<<dim3(div_up((unsigned)pw, 256), (unsigned)ph, (unsigned)s.frames), 256, 0, st>>>(s, pbuf, pw, ph, ax, ay, border, plane_elems);
+    count_launch();
+    CUtensorMap tm;
+    int rc = make_tensor_map_3d(&tm, pbuf, 2, pw, ph, 2 * s.frames, (size_t)pw * 2, (size_t)pw * ph * 2, 8, p.box_h);
+    if (!rc) {
+        auto kern = filter2d_tc_f32_kernel;
+        static PerDeviceFlag attr_pd; bool& attr = attr_pd.cur();
+        if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_MAX)); attr = true; }
+        kern<<<grid, FF_THREADS, smem, st>>>(tm, bglob, d, p);
+        cudaError_t e = cudaGetLastError();
+        count_launch();
+        if (e != cudaSuccess) rc = cuda_fail(e, "kernel launch", __FILE__, __LINE__);
+    }
+    cudaFreeAsync(bglob, st);
+    cudaFreeAsync(pbuf, st);
+    return rc;
+}
+
+}  // namespace b200cv

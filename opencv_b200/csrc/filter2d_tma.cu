@@ -158,7 +158,7 @@ static int launch_ft(const CUtensorMap& tm, const Img& d, const FTParams& p, int
     constexpr int IH = FT_TH + KB - 1;
     const size_t smem = (size_t)IH * FT_IW * 4 + (size_t)IH * FT_IW * sizeof(ST);
     auto kern = filter2d_tma_kernel<KB, ST, DT>;
-    static bool attr = false;
+    static PerDeviceFlag attr_pd; bool& attr = attr_pd.cur();
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     dim3 grid(div_up((unsigned)p.W, FT_TW), div_up((unsigned)p.H, FT_TH), (unsigned)frames);
     kern<<<grid, 256, smem, st>>>(tm, d, p);

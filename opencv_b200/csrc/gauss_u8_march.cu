@@ -39,7 +39,7 @@ constexpr int GM_RA = 16;       // left / right apron staged (TMA: the box must 
 
 template <int KB> struct GMCfg {
     static constexpr int H = KB / 2, NP = H + 1;                                     // NP = pairs in the column window
-    static constexpr int CH = KB == 3 ? 16 : KB == 5 ? 18 : KB == 7 ? 16 : 20;       // rows per chunk: CH/2 is a multiple of NP
+    static constexpr int CH = KB == 3 ? 8 : KB == 5 ? 12 : KB == 7 ? 8 : 10;         // rows per chunk: CH/2 is a multiple of NP (small chunks: 4-5 KB per warp keep 32 warps per SM resident)
     static constexpr int BUFB = 256 * CH;                                            // bytes per chunk buffer
     static_assert((CH / 2) % NP == 0 && CH % 2 == 0 && CH / 2 >= H, "the window rotation needs CH/2 to be a multiple of K/2+1");
 };
@@ -89,6 +89,22 @@ __device__ __forceinline__ uint2 gm_pack8(const uint32_t a[8])      // byte 2 of
     return r;
 }
 
+// checked stores of two output rows (chunks at the ends of a segment, partial strips, unaligned destinations): out of line, the hot
+// loop stays small (the unrolled byte stores made the kernel 57 KB of code and the warps stalled on instruction fetch)
+__device__ __noinline__ void gm_store_checked(unsigned char* d0, size_t dstep, uint2 pe, uint2 po, int ncols, bool row1, bool vec)
+{
+    if (vec) {
+        *(uint2*)d0 = pe;
+        if (row1) *(uint2*)(d0 + dstep) = po;
+        return;
+    }
+#pragma unroll 1
+    for (int c = 0; c < ncols; c++) {
+        d0[c] = (unsigned char)((c < 4 ? pe.x : pe.y) >> (8 * (c & 3)));
+        if (row1) d0[dstep + c] = (unsigned char)((c < 4 ? po.x : po.y) >> (8 * (c & 3)));
+    }
+}
+
 // One chunk of CH rows for one lane.  rp = the lane's own 8 bytes in row 0 of the chunk buffer; win = the lane's window, which lives across
 // chunks; m_first = output row pair produced by the chunk's first source pair (negative in a segment's first chunk: the window is filling);
 // dp = destination of output row 2 * m_first at the lane's first column (never dereferenced for rows outside [0, nrows)).
@@ -128,14 +144,8 @@ __device__ __forceinline__ void gm_chunk(const unsigned char* rp, const GMParams
             if (FAST) {
                 *(uint2*)d0 = pe;
                 *(uint2*)(d0 + dstep) = po;
-            } else if (vec) {
-                *(uint2*)d0 = pe;
-                if (y + 1 < nrows) *(uint2*)(d0 + dstep) = po;
             } else {
-                for (int c = 0; c < ncols; c++) {
-                    d0[c] = (unsigned char)((c < 4 ? pe.x : pe.y) >> (8 * (c & 3)));
-                    if (y + 1 < nrows) d0[dstep + c] = (unsigned char)((c < 4 ? po.x : po.y) >> (8 * (c & 3)));
-                }
+                gm_store_checked(d0, dstep, pe, po, ncols, y + 1 < nrows, vec);
             }
         }
     }

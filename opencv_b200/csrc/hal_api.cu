@@ -134,6 +134,8 @@ extern "C" int b200cv_host_box_filter(const b200cvMat* s, const b200cvMat* d, in
 { return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_box_filter(a, b, kw, kh, ax, ay, normalize, border, st); }); }
 extern "C" int b200cv_host_resize(const b200cvMat* s, const b200cvMat* d, int interp)
 { return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_resize(a, b, interp, st); }); }
+extern "C" int b200cv_host_resize_scaled(const b200cvMat* s, const b200cvMat* d, int interp, double fx, double fy)
+{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_resize_scaled(a, b, interp, fx, fy, st); }); }
 extern "C" int b200cv_host_warp_affine(const b200cvMat* s, const b200cvMat* d, const double* M, int flags, int border, const double* bv)
 { return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_warp_affine(a, b, M, flags, border, bv, st); }); }
 extern "C" int b200cv_host_warp_perspective(const b200cvMat* s, const b200cvMat* d, const double* M, int flags, int border, const double* bv)
@@ -284,10 +286,9 @@ extern "C" int b200cv_hal_integral(int depth, int sdepth, int sqdepth, const uch
 extern "C" int b200cv_hal_resize(int type, const uchar* src, size_t sstep, int sw, int sh, uchar* dst, size_t dstep, int dw, int dh,
                                  double inv_x, double inv_y, int interp)
 {
-    // the device path derives the scale from the sizes (the fx = fy = 0 form of cv::resize); decline explicit, different factors
-    if (inv_x > 0 && inv_y > 0 && (inv_x != (double)dw / sw || inv_y != (double)dh / sh)) return B200CV_NOT_IMPLEMENTED;
+    // inv_x, inv_y = cv::resize's fx, fy when it was called with an empty dsize, else dsize / ssize (resize.cpp:4214-4228): passed through
     b200cvMat s = hmat(src, sstep, sw, sh, type), d = hmat(dst, dstep, dw, dh, type);
-    return b200cv_host_resize(&s, &d, interp);
+    return b200cv_host_resize_scaled(&s, &d, interp, inv_x, inv_y);
 }
 
 extern "C" int b200cv_hal_warpAffine(int type, const uchar* src, size_t sstep, int sw, int sh, uchar* dst, size_t dstep, int dw, int dh,

@@ -164,7 +164,7 @@ static int launch_harris(const Img& s, const Img& d, const HarrisParams& p, cuda
     const int rs = KS / 2, cw = H_TW + p.bs - 1, ch = H_TH + p.bs - 1, sw_ = cw + 2 * rs, sh_ = ch + 2 * rs;
     size_t smem = ((size_t)sw_ * sh_ + 2 * (size_t)sh_ * cw + 3 * (size_t)cw * ch) * sizeof(float);
     auto kern = harris_kernel<ST, KS, BS>;
-    static bool a = false;
+    static PerDeviceFlag a_pd; bool& a = a_pd.cur();
     if (!a) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a = true; }
     if (smem > 200 * 1024) return B200CV_NOT_IMPLEMENTED;
     dim3 grid(div_up((unsigned)s.cols, H_TW), div_up((unsigned)s.rows, H_TH), (unsigned)s.frames);

@@ -262,6 +262,116 @@ __global__ void __launch_bounds__(256) mt_normalize_kernel(Img res, const double
     *rp = (float)num;
 }
 
+
+// ---- 8-bit images: window sums + normalisation in ONE kernel, no intermediate planes ----------------------------------------------------
+// The window sums of an 8-bit image are exact integers (sum <= 255 w h, sum of squares <= 65025 w h < 2^32 for every template the numerator
+// kernels accept): the reference's f64 integral-image differences (templmatch.cpp:930-1004) have exactly these values.  One thread owns 4
+// adjacent result columns and walks down a segment of rows keeping the 4 window sums and sums of squares in u32 registers: a row enters
+// (and, h rows later, leaves) as 4 horizontal sums over w bytes, computed from the aligned words of the image row -- the words all 4 windows
+// share once (IDP4A against 1s for the sum, against the word itself for the squares), the one or two words at either end per window through
+// byte masks.  Every image row is read twice, the numerator once; nothing else touches HBM (the first version wrote and re-read four f64
+// planes: 0.3 ms per 4K frame against 0.09 ms for the tcgen05 numerator).
+__device__ __forceinline__ unsigned mt_mask_ge(int k) { return k >= 4 ? 0u : (k <= 0 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (8 * k)); }
+__device__ __forceinline__ unsigned mt_mask_lt(int n) { return n <= 0 ? 0u : (n >= 4 ? 0xFFFFFFFFu : (1u << (8 * n)) - 1u); }
+
+// sums over bytes [k, k + w) of the row for k = 0..3, relative to the aligned word pointer wp; words with index > jmax lie outside the row
+__device__ __forceinline__ void mt_row4(const unsigned* __restrict__ wp, int w, int jmax, unsigned s[4], unsigned q[4])
+{
+    const int nw = min((w + 2) / 4, jmax);            // last word index any of the 4 windows touches
+    const int jfull = min((w - 4) >> 2, jmax);        // words 1..jfull lie inside all 4 windows
+    unsigned ms = 0, mq = 0;
+#pragma unroll 4
+    for (int j = 1; j <= jfull; j++) {
+        const unsigned v = __ldg(wp + j);
+        ms = __dp4a(v, 0x01010101u, ms);
+        mq = __dp4a(v, v, mq);
+    }
+    const unsigned v0 = jmax >= 0 ? __ldg(wp) : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned vm = v0 & mt_mask_ge(k) & mt_mask_lt(k + w);
+        s[k] = __dp4a(vm, 0x01010101u, ms);
+        q[k] = __dp4a(vm, v0, mq);
+    }
+    for (int j = max(jfull + 1, 1); j <= nw; j++) {
+        const unsigned v = __ldg(wp + j);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned vm = v & mt_mask_lt(k + w - 4 * j);
+            s[k] = __dp4a(vm, 0x01010101u, s[k]);
+            q[k] = __dp4a(vm, v, q[k]);
+        }
+    }
+}
+
+__device__ __forceinline__ float mt_normalize_one(double num, double ws, double wq, int numType, bool isNormed, int method, const TemplStats& st)
+{
+    double t, wndMean2 = 0, wndSum2 = 0;
+    if (numType == 1) {
+        t = ws;
+        wndMean2 += t * t;
+        num -= t * st.mean;
+        wndMean2 *= st.inv_area;
+    }
+    if (isNormed || numType == 2) {
+        wndSum2 += wq;
+        if (numType == 2) { num = wndSum2 - 2 * num + st.sum2; num = fmax(num, 0.); }
+    }
+    if (isNormed) {
+        double diff2 = fmax(wndSum2 - wndMean2, 0.);
+        if (diff2 <= fmin(0.5, 10 * 1.1920928955078125e-07 * wndSum2)) t = 0;
+        else t = sqrt(diff2) * st.norm;
+        if (fabs(num) < t) num /= t;
+        else if (fabs(num) < t * 1.125) num = num > 0 ? 1 : -1;
+        else num = method != B200CV_TM_SQDIFF_NORMED ? 0 : 1;
+    }
+    return (float)num;
+}
+
+constexpr int MTF_SEG = 128;     // result rows per thread
+
+__global__ void __launch_bounds__(128) mt_fused_u8_kernel(Img img, Img res, int w, int h, int method, const TemplStats* __restrict__ stats)
+{
+    const int f = blockIdx.z;
+    const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+    const int ys = blockIdx.y * MTF_SEG, ye = min(ys + MTF_SEG, res.rows);
+    if (x0 >= res.cols) return;
+    const TemplStats st = *stats;
+    const int numType = (method == B200CV_TM_CCORR || method == B200CV_TM_CCORR_NORMED) ? 0 : (method == B200CV_TM_CCOEFF || method == B200CV_TM_CCOEFF_NORMED) ? 1 : 2;
+    const bool isNormed = method == B200CV_TM_CCORR_NORMED || method == B200CV_TM_SQDIFF_NORMED || method == B200CV_TM_CCOEFF_NORMED;
+    const int jmax = (img.cols - x0 + 3) / 4 - 1;                    // last word of the row that still holds image bytes
+    const int n = min(4, res.cols - x0);
+    unsigned ws[4] = {0, 0, 0, 0}, wq[4] = {0, 0, 0, 0};
+    for (int j = 0; j < h; j++) {
+        unsigned s[4], q[4];
+        mt_row4((const unsigned*)(img.row<uchar>(f, ys + j) + x0), w, jmax, s, q);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { ws[k] += s[k]; wq[k] += q[k]; }
+    }
+    for (int y = ys; y < ye; y++) {
+        float* rp = res.row<float>(f, y) + x0;
+        const bool vec = n == 4 && (((uintptr_t)rp) & 15) == 0;
+        float num[4];
+        if (vec) { const float4 t = *(const float4*)rp; num[0] = t.x; num[1] = t.y; num[2] = t.z; num[3] = t.w; }
+        else for (int k = 0; k < n; k++) num[k] = rp[k];
+        float out[4];
+        if (st.flat) { out[0] = out[1] = out[2] = out[3] = 1.f; }
+        else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) out[k] = k < n ? mt_normalize_one((double)num[k], (double)ws[k], (double)wq[k], numType, isNormed, method, st) : 0.f;
+        }
+        if (vec) *(float4*)rp = make_float4(out[0], out[1], out[2], out[3]);
+        else for (int k = 0; k < n; k++) rp[k] = out[k];
+        if (y + 1 < ye) {
+            unsigned s[4], q[4], s2[4], q2[4];
+            mt_row4((const unsigned*)(img.row<uchar>(f, y + h) + x0), w, jmax, s, q);
+            mt_row4((const unsigned*)(img.row<uchar>(f, y) + x0), w, jmax, s2, q2);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { ws[k] += s[k] - s2[k]; wq[k] += q[k] - q2[k]; }
+        }
+    }
+}
+
 }  // namespace b200cv
 
 using namespace b200cv;
@@ -300,19 +410,31 @@ extern "C" int b200cv_match_template(const b200cvMat* image, const b200cvMat* te
         int wpad = (w + 3) & ~3;
         size_t smem = (((size_t)h * wpad + 15) & ~(size_t)15) + (size_t)(MT_T + h - 1) * (MT_T + wpad + 4) + 16;
         if (smem > 200 * 1024) return B200CV_NOT_IMPLEMENTED;
-        static bool a = false;
+        static PerDeviceFlag a_pd; bool& a = a_pd.cur();
         if (!a) { B200_CUDA(cudaFuncSetAttribute(ccorr_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a = true; }
         ccorr_u8_kernel<<<grid, 256, smem, st>>>(im, tp, rs, w, h, wpad);
     } else {
         size_t smem = ((size_t)h * w + (size_t)(MT_T + h - 1) * (MT_T + w + 3)) * sizeof(float);
         if (smem > 200 * 1024) return B200CV_NOT_IMPLEMENTED;
-        static bool a = false;
+        static PerDeviceFlag a_pd; bool& a = a_pd.cur();
         if (!a) { B200_CUDA(cudaFuncSetAttribute(ccorr_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a = true; }
         ccorr_f32_kernel<<<grid, 256, smem, st>>>(im, tp, rs, w, h);
     }
     if (!done) B200_LAUNCH_CHECK();
     if (method == B200CV_TM_CCORR) return B200CV_OK;
 
+    const char* norm_env = getenv("B200CV_MATCHTEMPLATE_NORM");        // test hook: "planes" = the first version (f64 window-sum planes)
+    if (u8 && (((uintptr_t)im.data | im.step | im.fstep) & 3) == 0 && !(norm_env && !strcmp(norm_env, "planes"))) {
+        // 8-bit: exact u32 window sums and the normalisation fused into one pass (no intermediate planes)
+        TemplStats* d_stats = nullptr;
+        B200_CUDA(cudaMallocAsync(&d_stats, sizeof(TemplStats), st));
+        templ_stats_kernel<uchar><<<1, 256, 0, st>>>(tp, method, d_stats);
+        count_launch();
+        mt_fused_u8_kernel<<<dim3(div_up(div_up((unsigned)ow, 4), 128), div_up((unsigned)oh, MTF_SEG), frames), 128, 0, st>>>(im, rs, w, h, method, d_stats);
+        B200_LAUNCH_CHECK();
+        B200_CUDA(cudaFreeAsync(d_stats, st));
+        return B200CV_OK;
+    }
     // workspace (stream-ordered): row sums, window sums, template statistics
     const size_t pitch_d = ((size_t)ow + 31) & ~(size_t)31;
     double *d_rs = nullptr, *d_rq = nullptr, *d_ws = nullptr, *d_wq = nullptr;

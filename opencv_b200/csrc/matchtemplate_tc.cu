@@ -220,7 +220,7 @@ int ccorr_u8_tensor(const Img& im, const Img& tp, const Img& rs, int w, int h, c
     p.ra_alloc = p.nbox * p.box_h;
     size_t smem = (size_t)8 * p.ra_alloc * 16 + (size_t)TC_NS * TC_BBYTES;
     if (smem > 200 * 1024) return B200CV_NOT_IMPLEMENTED;
-    static bool attr = false;
+    static PerDeviceFlag attr_pd; bool& attr = attr_pd.cur();
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(ccorr_u8_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
     unsigned char* bglob = nullptr;
     B200_CUDA(cudaMallocAsync(&bglob, (size_t)h * TC_BBYTES, st));

@@ -341,7 +341,7 @@ int copy_impl(const b200cvMat* src, const b200cvMat* dst, void* stream);
 
 using namespace b200cv;
 
-extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int interpolation, void* stream)
+static int resize_impl(const b200cvMat* src, const b200cvMat* dst, int interpolation, double fx, double fy, void* stream)
 {
     int rc;
     if ((rc = check_mat(src, "src")) || (rc = check_mat(dst, "dst"))) return rc;
@@ -357,13 +357,19 @@ extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int int
 
     ResizeParams p;
     p.sw = src->cols; p.sh = src->rows; p.dw = dst->cols; p.dh = dst->rows;
-    const double inv_x = (double)p.dw / p.sw, inv_y = (double)p.dh / p.sh;   // hal::resize, resize.cpp:3835-3839
+    // hal::resize, resize.cpp:3835-3839: the scale is dsize / ssize -- unless the caller gave fx, fy (cv::resize with an empty dsize,
+    // resize.cpp:4214-4228), which then stay as they are even when cols * fx is not an integer
+    const double size_x = (double)p.dw / p.sw, size_y = (double)p.dh / p.sh;
+    const bool explicit_scale = fx > 0 && fy > 0 && (fx != size_x || fy != size_y);
+    const double inv_x = fx > 0 && fy > 0 ? fx : size_x, inv_y = fx > 0 && fy > 0 ? fy : size_y;
     p.ifx = 1. / inv_x; p.ify = 1. / inv_y;
     p.scale_x = 1. / inv_x; p.scale_y = 1. / inv_y;
     p.inv_x = inv_x; p.inv_y = inv_y; p.area_mode = 0;
     const int pix = (int)elem_size(src->type);
     dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
 
+    // the EXACT / AREA / LANCZOS4 kernels derive their scale from the sizes: decline factors that differ from it (a host OpenCV then runs its own code)
+    if (explicit_scale && interpolation != B200CV_INTER_NEAREST && interpolation != B200CV_INTER_LINEAR && interpolation != B200CV_INTER_CUBIC) return B200CV_NOT_IMPLEMENTED;
     if (interpolation == B200CV_INTER_NEAREST_EXACT) return resize_exact_impl(s, d, depth, cn, interpolation, st);
     if (interpolation == B200CV_INTER_LINEAR_EXACT && depth == B200CV_32F) interpolation = B200CV_INTER_LINEAR;      // cv::resize, resize.cpp:4223
     if (interpolation == B200CV_INTER_NEAREST) {
@@ -384,6 +390,8 @@ extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int int
     const int isx = (int)lrint(p.scale_x), isy = (int)lrint(p.scale_y);
     const bool area_fast = fabs(p.scale_x - isx) < 2.220446049250313e-16 && fabs(p.scale_y - isy) < 2.220446049250313e-16;
     if ((interpolation == B200CV_INTER_LINEAR || interpolation == B200CV_INTER_AREA || interpolation == B200CV_INTER_LINEAR_EXACT) && area_fast && isx == 2 && isy == 2) {   // LINEAR_EXACT: resize.cpp:3976-3981
+        // explicit fx = fy = 0.5 on odd sizes: the reference's partial last windows (resizeAreaFast_Invoker, resize.cpp:3028-3050) are not built here
+        if (2 * p.dw != p.sw || 2 * p.dh != p.sh) return B200CV_NOT_IMPLEMENTED;
         if (depth == B200CV_8U) {
             int vec_ok = (((uintptr_t)s.data | s.step | s.fstep | (uintptr_t)d.data | d.step | d.fstep) & 3) == 0;
             dim3 g4(div_up((unsigned)div_up((unsigned)p.dw, 4), 256), (unsigned)p.dh, (unsigned)s.frames);
@@ -405,4 +413,15 @@ extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int int
     if (interpolation == B200CV_INTER_AREA) { p.area_mode = 1; interpolation = B200CV_INTER_LINEAR; }
     if (interpolation != B200CV_INTER_LINEAR && interpolation != B200CV_INTER_CUBIC) return B200CV_NOT_IMPLEMENTED;
     return depth == B200CV_8U ? launch_by_cn<uchar>(cn, interpolation, s, d, p, st) : launch_by_cn<float>(cn, interpolation, s, d, p, st);
+}
+
+extern "C" int b200cv_resize(const b200cvMat* src, const b200cvMat* dst, int interpolation, void* stream)
+{
+    return resize_impl(src, dst, interpolation, 0., 0., stream);
+}
+
+// cv::resize(src, dst, Size(), fx, fy): dst is round(cols * fx) x round(rows * fy) and the sampling scale is fx, fy themselves
+extern "C" int b200cv_resize_scaled(const b200cvMat* src, const b200cvMat* dst, int interpolation, double fx, double fy, void* stream)
+{
+    return resize_impl(src, dst, interpolation, fx, fy, stream);
 }

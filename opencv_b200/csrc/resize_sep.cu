@@ -19,6 +19,7 @@
 // Tables (source index + taps per destination column / row) come from resize_tab_kernel (resize.cu), built with the reference's fp64 / float sequence.
 #include <string.h>
 #include <math.h>
+#include <type_traits>
 #include "resize.cuh"
 
 namespace b200cv {
@@ -71,61 +72,76 @@ constexpr float RS_MAGIC = 12582912.f;              // 1.5 * 2^23: float(0x4B400
 constexpr int RS_MAGIC_I = 0x4B400000;
 
 // ---- H pass: one destination pixel column, rows r = r_first, r_first + r_step, ... < R of the tile --------------------------------------
+// Rows are taken four at a time: all the loads of a group are issued before the first is consumed (the pass is latency bound otherwise), and
+// the global / shared pointers advance by additions (the first version recomputed 64-bit row addresses per row: 30 IMAD per pixel).
 template <int CN, bool CUBIC>
 __device__ __forceinline__ void rs_hpass_thread(const Img& src, int f, const ResizeParams& p, const ResTab& tx, int row_lo, int R, int r_first, int r_step,
                                                 unsigned char* mid_col /* &mid[0][col * CN] */)
 {
     constexpr int E = RSCfg<CN, CUBIC>::E;
+    constexpr int NT = CUBIC ? 4 : 2;
+    constexpr int NW = (NT * CN + 3) / 4;
+    typedef typename std::conditional<CUBIC, float, unsigned short>::type MidT;
     const bool words_ok = (((uintptr_t)src.data | src.step | src.fstep) & 3) == 0;
     const int row_bytes = p.sw * CN;
-    if constexpr (!CUBIC) {
-        const bool last_col = tx.last != 0;
-        const int xo = tx.s * CN;
-        const int a0 = tx.ic[0], a1 = tx.ic[1];
-        constexpr int NW = (2 * CN + 3) / 4;
-        const bool fast = words_ok && !last_col && xo + 2 * CN + 7 <= row_bytes;            // the NW + 1 words stay inside the row
-        const int a01 = (a0 & 0xffff) | (a1 << 16);
-        unsigned short* m = (unsigned short*)mid_col;
-#pragma unroll 4
-        for (int r = r_first; r < R; r += r_step) {
-            const uchar* srow = src.row<uchar>(f, row_lo + r);
-            int t[CN];
-            if (fast) {
-                unsigned w[NW];
-                rs_load_realigned<NW>(srow, (unsigned)xo, w);
+    const int A = CUBIC ? (tx.s - 1) * CN : tx.s * CN;                     // first source byte of the taps (before clamping)
+    const bool last_col = !CUBIC && tx.last != 0;
+    const bool fast = words_ok && (CUBIC ? (tx.s >= 1 && tx.s + 2 <= p.sw - 1) : !last_col) && A + NT * CN + 7 <= row_bytes;   // the NW + 1 words stay inside the row
+    const int c01 = (tx.ic[0] & 0xffff) | (tx.ic[1] << 16), c23 = CUBIC ? (tx.ic[2] & 0xffff) | (tx.ic[3] << 16) : 0;
+    const size_t gstep = (size_t)r_step * src.step;
+    const uchar* gp = src.data + (size_t)f * src.fstep + (size_t)(row_lo + r_first) * src.step;
+    MidT* m = (MidT*)mid_col + (size_t)r_first * E;
+    const int mstep = r_step * E;
+    int r = r_first;
+    if (fast) {
+        const uchar* wp = gp + (A & ~3);
+        const unsigned sh8 = 8u * ((unsigned)A & 3u);
+        auto finish = [&](const unsigned* t, MidT* mo) {
+            unsigned w[NW];
 #pragma unroll
-                for (int c = 0; c < CN; c++) t[c] = rs_dp2a_s(a01, rs_pair<CN>(w, c, 0), 0);
-            } else {
+            for (int i = 0; i < NW; i++) w[i] = rs_funnel_r(t[i], t[i + 1], sh8);
 #pragma unroll
-                for (int c = 0; c < CN; c++) t[c] = last_col ? srow[xo + c] * 2048 : srow[xo + c] * a0 + srow[xo + c + CN] * a1;
+            for (int c = 0; c < CN; c++) {
+                if constexpr (CUBIC) {
+                    const int v = rs_dp2a_s(c23, rs_pair<CN>(w, c, 2), rs_dp2a_s(c01, rs_pair<CN>(w, c, 0), RS_MAGIC_I));
+                    mo[c] = __fsub_rn(__int_as_float(v), RS_MAGIC);        // exact: |sum| < 2^22
+                } else {
+                    mo[c] = (unsigned short)(rs_dp2a_s(c01, rs_pair<CN>(w, c, 0), 0) >> 4);
+                }
             }
+        };
+        for (; r + 3 * r_step < R; r += 4 * r_step) {
+            unsigned t[4][NW + 1];
 #pragma unroll
-            for (int c = 0; c < CN; c++) m[(size_t)r * E + c] = (unsigned short)(t[c] >> 4);
+            for (int g = 0; g < 4; g++)
+#pragma unroll
+                for (int i = 0; i <= NW; i++) t[g][i] = ((const unsigned*)(wp + g * gstep))[i];
+#pragma unroll
+            for (int g = 0; g < 4; g++) finish(t[g], m + g * mstep);
+            wp += 4 * gstep; m += 4 * mstep;
+        }
+        for (; r < R; r += r_step) {
+            unsigned t[NW + 1];
+#pragma unroll
+            for (int i = 0; i <= NW; i++) t[i] = ((const unsigned*)wp)[i];
+            finish(t, m);
+            wp += gstep; m += mstep;
         }
     } else {
         int xi[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) xi[j] = min(max(tx.s - 1 + j, 0), p.sw - 1) * CN;          // per-tap clamping == the while-loops of HResizeCubic
-        constexpr int NW = (4 * CN + 3) / 4;
-        const bool fast = words_ok && tx.s >= 1 && tx.s + 2 <= p.sw - 1 && (tx.s - 1) * CN + 4 * CN + 7 <= row_bytes;
-        const int c01 = (tx.ic[0] & 0xffff) | (tx.ic[1] << 16), c23 = (tx.ic[2] & 0xffff) | (tx.ic[3] << 16);
-        float* m = (float*)mid_col;
-#pragma unroll 2
-        for (int r = r_first; r < R; r += r_step) {
-            const uchar* srow = src.row<uchar>(f, row_lo + r);
-            int t[CN];
-            if (fast) {
-                unsigned w[NW];
-                rs_load_realigned<NW>(srow, (unsigned)((tx.s - 1) * CN), w);
+        for (int j = 0; j < 4; j++) xi[j] = CUBIC ? min(max(tx.s - 1 + j, 0), p.sw - 1) * CN : (tx.s + (j & 1)) * CN;   // per-tap clamping == the while-loops of HResizeCubic
+        for (; r < R; r += r_step, gp += gstep, m += mstep) {
 #pragma unroll
-                for (int c = 0; c < CN; c++) t[c] = rs_dp2a_s(c23, rs_pair<CN>(w, c, 2), rs_dp2a_s(c01, rs_pair<CN>(w, c, 0), RS_MAGIC_I));
-            } else {
-#pragma unroll
-                for (int c = 0; c < CN; c++)
-                    t[c] = RS_MAGIC_I + srow[xi[0] + c] * tx.ic[0] + srow[xi[1] + c] * tx.ic[1] + srow[xi[2] + c] * tx.ic[2] + srow[xi[3] + c] * tx.ic[3];
+            for (int c = 0; c < CN; c++) {
+                if constexpr (CUBIC) {
+                    const int v = RS_MAGIC_I + gp[xi[0] + c] * tx.ic[0] + gp[xi[1] + c] * tx.ic[1] + gp[xi[2] + c] * tx.ic[2] + gp[xi[3] + c] * tx.ic[3];
+                    m[c] = __fsub_rn(__int_as_float(v), RS_MAGIC);
+                } else {
+                    const int v = last_col ? gp[xi[0] + c] * 2048 : gp[xi[0] + c] * tx.ic[0] + gp[xi[1] + c] * tx.ic[1];
+                    m[c] = (unsigned short)(v >> 4);
+                }
             }
-#pragma unroll
-            for (int c = 0; c < CN; c++) m[(size_t)r * E + c] = __fsub_rn(__int_as_float(t[c]), RS_MAGIC);     // exact: |sum| < 2^22
         }
     }
 }
@@ -198,6 +214,8 @@ __device__ __forceinline__ void rs_fill_row(RSRow& o, const ResTab& ty, int row_
     }
 }
 
+// a warp takes whole destination rows of the tile (its lanes the 4-element items of the row): the row record is read once per row,
+// pointers advance by additions, no divisions
 template <int CN, bool CUBIC>
 __device__ __forceinline__ void rs_vpass_thread(int tid, int nthreads, const unsigned char* mid, const RSRow* yrow, const Img& dst, int f, const ResizeParams& p,
                                                 int x0, int y0, int nrows_out, int ncols_out)
@@ -206,14 +224,19 @@ __device__ __forceinline__ void rs_vpass_thread(int tid, int nthreads, const uns
     const int vec_limit = ((p.dw * CN) / 8) * 8;
     const bool vec_store = (((uintptr_t)dst.data | dst.step | dst.fstep) & 3) == 0;
     const int ne = ncols_out * CN;                                   // valid elements per row of this tile
-    for (int it = tid; it < NQ * nrows_out; it += nthreads) {
-        const int row = it / NQ, q = it - row * NQ, e0 = 4 * q;
-        if (e0 >= ne) continue;
-        const int ge0 = x0 * CN + e0;
-        const unsigned out = rs_vpass_item<CN, CUBIC>(mid, yrow[row], e0, ge0, vec_limit);
-        uchar* d = dst.row<uchar>(f, y0 + row) + ge0;
-        if (vec_store && e0 + 4 <= ne) *(unsigned*)d = out;
-        else for (int i = 0; i < 4 && e0 + i < ne; i++) d[i] = (uchar)(out >> (8 * i));
+    const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+    const int nq = min(NQ, (ne + 3) >> 2);
+    uchar* drow = dst.data + (size_t)f * dst.fstep + (size_t)(y0 + warp) * dst.step + (size_t)x0 * CN;
+    const size_t dstep = (size_t)nwarps * dst.step;
+    for (int row = warp; row < nrows_out; row += nwarps, drow += dstep) {
+        const RSRow yr = yrow[row];
+        for (int q = lane; q < nq; q += 32) {
+            const int e0 = 4 * q;
+            const unsigned out = rs_vpass_item<CN, CUBIC>(mid, yr, e0, x0 * CN + e0, vec_limit);
+            uchar* d = drow + e0;
+            if (vec_store && e0 + 4 <= ne) *(unsigned*)d = out;
+            else for (int i = 0; i < 4 && e0 + i < ne; i++) d[i] = (uchar)(out >> (8 * i));
+        }
     }
 }
 

@@ -11,7 +11,7 @@ namespace b200cv {
 
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
-static int g_num_sms = 0;
+static int g_num_sms[64] = {};
 
 void set_error(const char* fmt, ...)
 {
@@ -31,14 +31,11 @@ void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memo
 
 int num_sms()
 {
-    if (g_num_sms == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            g_num_sms = n;
-        else
-            g_num_sms = 148;
-    }
-    return g_num_sms;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    int& slot = g_num_sms[dev & 63];
+    if (slot == 0) slot = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    return slot;
 }
 
 int check_mat(const b200cvMat* m, const char* name)
@@ -103,7 +100,7 @@ int b200cv_init(int device)
         set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, p.major, p.minor);
         return B200CV_ERR_NO_DEVICE;
     }
-    g_num_sms = p.multiProcessorCount;
+    g_num_sms[device & 63] = p.multiProcessorCount;
     B200_CUDA(cudaFree(0));
     configure_mem_pool();
     return B200CV_OK;

@@ -215,7 +215,7 @@ static int launch_sf32(const CUtensorMap& tm, const Img& d, const SF32Params& p,
     constexpr int IH = SF_TH + KB - 1;
     const size_t smem = (((size_t)IH * SF_IW * sizeof(ST) + 127) & ~(size_t)127) + (size_t)IH * SF_TW * sizeof(float);
     auto kern = sep_f32_tma_kernel<KB, ST, DT>;
-    static bool attr = false;
+    static PerDeviceFlag attr_pd; bool& attr = attr_pd.cur();
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     dim3 grid(div_up((unsigned)p.W, SF_TW), div_up((unsigned)p.H, SF_TH), (unsigned)frames);
     kern<<<grid, 256, smem, st>>>(tm, d, p);

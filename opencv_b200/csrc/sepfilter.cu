@@ -359,7 +359,7 @@ static int launch_fast(const Img& s, const Img& d, const SepParams& p, cudaStrea
     if (s.rows <= 8) TH = 8;
     size_t smem = smem_for(TH);
     auto kern = sep_fast_kernel<ST, DT, MODE, KB>;
-    static bool attr_done = false;
+    static PerDeviceFlag attr_done_pd; bool& attr_done = attr_done_pd.cur();
     if (!attr_done) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;
@@ -405,7 +405,7 @@ static int launch_generic(const Img& s, const Img& d, const SepParams& p, cudaSt
     size_t smem = ((size_t)tile_rows * tile_px * p.cn + (size_t)tile_rows * G_TPX * p.cn) * sizeof(float);
     if (smem > 200 * 1024) return B200CV_NOT_IMPLEMENTED;
     auto kern = sep_generic_kernel<ST, DT, MODE>;
-    static bool attr_done = false;
+    static PerDeviceFlag attr_done_pd; bool& attr_done = attr_done_pd.cur();
     if (!attr_done) {
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_done = true;

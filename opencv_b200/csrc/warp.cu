@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(Img src, Img dst, const 
 
 static int ensure_warp_tables()
 {
-    static bool done = false;
+    static PerDeviceFlag done_pd; bool& done = done_pd.cur();
     if (done) return B200CV_OK;
     std::vector<float> f; std::vector<short> q;
     bilinear_tab(f, q);
@@ -449,7 +449,7 @@ static int launch_warp_i(const Img& s, const Img& d, const WarpParams& p, cudaSt
     }
     int smem = (int)std::min<long long>(WT_SMEM_MAX, std::max<long long>(need + need / 8, 8 * 1024));
     auto kern = warp_tile_kernel<T, CN, INTERP>;
-    static bool attr = false;
+    static PerDeviceFlag attr_pd; bool& attr = attr_pd.cur();
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_MAX)); attr = true; }
     dim3 grid((unsigned)tx, (unsigned)ty, (unsigned)s.frames);
     kern<<<grid, 256, smem, st>>>(s, d, p, smem);

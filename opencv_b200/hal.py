@@ -23,6 +23,7 @@ def describe(a):
     if a.ndim == 2:
         n, h, w, c = 1, a.shape[0], a.shape[1], 1
         fs, rs = 0, a.strides[0]
+        assert a.strides[1] == es and a.strides[0] > 0, "rows must be dense and ascending (a[:, ::2], a.T and flipped views are not cv::Mat layouts)"
     elif a.ndim == 3:
         n, (h, w, c) = 1, a.shape
         fs, rs = 0, a.strides[0]
@@ -118,11 +119,15 @@ def cvtColor(src, code, dstCn=0, dst=None):
 
 def resize(src, dsize, fx=0, fy=0, interpolation=INTER_LINEAR, dst=None):
     m = describe(src)
-    if not dsize or dsize[0] <= 0:
+    by_factor = not dsize or dsize[0] <= 0
+    if by_factor:
         dsize = (int(round(m.cols * fx)), int(round(m.rows * fy)))
     dst = dst if dst is not None else _new(src, size=(int(dsize[0]), int(dsize[1])))
     ms, md = describe(src), describe(dst)
-    _check(lib().b200cv_host_resize(ctypes.byref(ms), ctypes.byref(md), int(interpolation)), "resize")
+    if by_factor:      # the sampling scale is fx, fy themselves, not dst / src (resize.cpp:4214-4228)
+        _check(lib().b200cv_host_resize_scaled(ctypes.byref(ms), ctypes.byref(md), int(interpolation), ctypes.c_double(fx), ctypes.c_double(fy)), "resize")
+    else:
+        _check(lib().b200cv_host_resize(ctypes.byref(ms), ctypes.byref(md), int(interpolation)), "resize")
     return dst
 
 

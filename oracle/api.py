@@ -153,6 +153,16 @@ class Oracle:
                                    int(interpolation)), "resize")
         return dst
 
+    def resize_fxfy(self, src, fx, fy, interpolation=1):
+        """cv::resize(src, dst, Size(), fx, fy): only the real reference has it"""
+        src = np.ascontiguousarray(src)
+        sh, sw = src.shape[:2]
+        dw, dh = int(round(sw * fx)), int(round(sh * fy))
+        dst = np.empty((dh, dw) + src.shape[2:], src.dtype)
+        self._ok(self.fn("resize_fxfy")(_p(src), sz(src.strides[0]), sw, sh, _p(dst), sz(dst.strides[0]), dw, dh, cvtype(src),
+                                        int(interpolation), ctypes.c_double(fx), ctypes.c_double(fy)), "resize_fxfy")
+        return dst
+
     def _warp(self, name, src, M, dsize, flags, borderMode, borderValue):
         src = np.ascontiguousarray(src)
         dw, dh = dsize

@@ -117,6 +117,16 @@ API int ref_resize(const void* src, size_t sstep, int sw, int sh, void* dst, siz
     GUARD_END
 }
 
+// cv::resize(src, dst, Size(), fx, fy): dst must be round(cols*fx) x round(rows*fy) (resize.cpp:4214-4228); the scale stays fx, fy
+API int ref_resize_fxfy(const void* src, size_t sstep, int sw, int sh, void* dst, size_t dstep, int dw, int dh, int type, int interp, double fx, double fy)
+{
+    GUARD_BEGIN
+    Mat s = hdr(src, sstep, sw, sh, type), d = hdr(dst, dstep, dw, dh, type);
+    resize(s, d, Size(), fx, fy, interp);
+    CV_Assert(d.data == (uchar*)dst && d.cols == dw && d.rows == dh);
+    GUARD_END
+}
+
 API int ref_warp_affine(const void* src, size_t sstep, int sw, int sh, void* dst, size_t dstep, int dw, int dh, int type,
                         const double* M, int flags, int border, const double* bv)
 {

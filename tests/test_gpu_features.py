@@ -40,6 +40,26 @@ def test_match_template_u8(cvb, oracle, rng, method, isz, tsz):
     assert_close(got, want, atol=1e-3 * scale, what="matchTemplate u8 method=%d %s %s" % (method, isz, tsz))
 
 
+@pytest.mark.parametrize("tsz", [(64, 64), (7, 13), (1, 3), (33, 2), (19, 130)])
+def test_match_template_fused_window_sums(cvb, rng, monkeypatch, tsz):
+    """8-bit images: the fused window-sum + normalisation kernel (exact u32 sums, one pass) against the first version (f64 planes of
+    sliding sums): the same exact integers enter the same f64 formula, so the results must be IDENTICAL -- all six methods, ragged sizes,
+    templates narrower than a word, a batch, an unaligned sub-view (which must take the planes path and agree too)."""
+    import torch
+    img = rng.integers(0, 256, (3, 211, 333, 1), dtype=np.uint8)
+    templ = np.ascontiguousarray(img[1, 40:40 + tsz[0], 50:50 + tsz[1], 0])
+    for method in range(6):
+        got = cpu(cvb.matchTemplate(gpu(img), gpu(templ), method))
+        monkeypatch.setenv("B200CV_MATCHTEMPLATE_NORM", "planes")
+        want = cpu(cvb.matchTemplate(gpu(img), gpu(templ), method))
+        monkeypatch.delenv("B200CV_MATCHTEMPLATE_NORM")
+        assert_exact(got, want, "matchTemplate fused vs planes method=%d templ=%s" % (method, tsz))
+    view = gpu(img)[:, 3:, 1:, :]               # base not 4-byte aligned: planes path
+    sub = np.ascontiguousarray(img[:, 3:, 1:, :])
+    if tsz[0] <= sub.shape[1] and tsz[1] <= sub.shape[2]:
+        assert_exact(cpu(cvb.matchTemplate(view, gpu(templ), C.TM_CCOEFF_NORMED)), cpu(cvb.matchTemplate(gpu(sub), gpu(templ), C.TM_CCOEFF_NORMED)), "matchTemplate unaligned view")
+
+
 @pytest.mark.parametrize("method", [C.TM_SQDIFF_NORMED, C.TM_CCORR, C.TM_CCORR_NORMED, C.TM_CCOEFF_NORMED])
 def test_match_template_f32(cvb, oracle, rng, method):
     img = rand_u8(rng, 128, 160).astype(np.float32)

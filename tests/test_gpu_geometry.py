@@ -40,6 +40,22 @@ def test_resize_f32(cvb, oracle, rng, ssz, dsz, cn, interp):
                  "resize f32 (fractional data) %s->%s cn=%d interp=%d" % (ssz, dsz, cn, interp))
 
 
+
+
+@pytest.mark.parametrize("fx,fy", [(0.333, 0.333), (1.7, 0.61), (0.25, 0.5), (2.0, 3.0), (0.4567, 1.234)])
+def test_resize_by_factor(cvb, ref, rng, fx, fy):
+    """cv::resize(src, dst, Size(), fx, fy): the destination is round(cols*fx) x round(rows*fy) but the sampling scale stays fx, fy -- so
+    whenever cols*fx is not an integer the coordinates differ from the dsize form (W=100, fx=0.333: 1/0.333 = 3.003 vs 100/33 = 3.0303).
+    Device ABI (torch), host ABI (numpy) and the HAL entry, against the reference called the same way: BIT-EXACT."""
+    from opencv_b200 import hal
+    for shape, dt in (((100, 131, 3), np.uint8), ((77, 100), np.uint8), ((60, 90), np.float32)):
+        img = (rng.random(shape) * 255).astype(dt)
+        for interp in (C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC):
+            want = ref.resize_fxfy(img, fx, fy, interp)
+            assert_exact(cpu(cvb.resize(gpu(img), None, fx, fy, interp)), want, "resize fx=%g fy=%g interp=%d %s (device ABI)" % (fx, fy, interp, dt.__name__))
+            assert_exact(hal.resize(img, None, fx, fy, interp), want, "resize fx=%g fy=%g interp=%d %s (host ABI)" % (fx, fy, interp, dt.__name__))
+
+
 @pytest.mark.parametrize("interp", [C.INTER_LINEAR, C.INTER_AREA])
 def test_resize_half_area(cvb, oracle, rng, interp):
     for cn in (1, 3, 4):
