@@ -70,6 +70,13 @@ __device__ __forceinline__ void fc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp (see matchtemplate_tc.cu: descriptors stay in uniform registers when the issuer loop is warp-uniform)
+__device__ __forceinline__ bool fc_elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fc_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -152,33 +159,38 @@ __global__ void __launch_bounds__(FC_THREADS, 1) filter2d_tc_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---- MMA issuer ----
-            // instruction descriptor: D = S32 (2<<4), A = u8 (0 at [7,10)), B = s8 (1 at [10,13)), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-            const uint32_t idesc = (2u << 4) | (1u << 10) | ((uint32_t)(FC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            mbar_wait(&b_full, 0);
-            const uint32_t b_base = smem_u32(sB);
-            int i = 0;
-            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
-                const int buf = i % p.na, acc = i & 1;
-                mbar_wait(&a_full[buf], (i / p.na) & 1);
-                mbar_wait(&acc_empty[acc], ((i >> 1) & 1) ^ 1);
-                fc_fence_after();
-                const uint32_t a_base = smem_u32(sA + (size_t)buf * abytes);
-                const uint32_t d_base = tmem + (uint32_t)acc * (FC_MT * FC_N);
+        // ---- MMA issuer: the whole warp runs the loops (uniform values), one elected lane issues ----
+        // instruction descriptor: D = S32 (2<<4), A = u8 (0 at [7,10)), B = s8 (1 at [10,13)), K-major both, N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (2u << 4) | (1u << 10) | ((uint32_t)(FC_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        mbar_wait(&b_full, 0);
+        // descriptors (K-major, no swizzle): low word = start >> 4 [0,14) | LBO >> 4 [16,30); high word = SBO >> 4 | version 1 at bit 14
+        const uint32_t hi = (128u >> 4) | (1u << 14);
+        const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (((uint32_t)(FC_N * 16) >> 4) << 16);
+        const uint32_t a_ks = (2u * lbo_a) >> 4;
+        int i = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
+            const int buf = i % p.na, acc = i & 1;
+            mbar_wait(&a_full[buf], (i / p.na) & 1);
+            mbar_wait(&acc_empty[acc], ((i >> 1) & 1) ^ 1);
+            fc_fence_after();
+            const uint32_t a_lo0 = ((smem_u32(sA + (size_t)buf * abytes) & 0x3FFFFu) >> 4) | ((lbo_a >> 4) << 16);
+            const uint32_t d_base = tmem + (uint32_t)acc * (FC_MT * FC_N);
+            if (fc_elect_one()) {
+#pragma unroll 1
                 for (int v = 0; v < p.kh; v++) {
 #pragma unroll
                     for (int mt = 0; mt < FC_MT; mt++)
 #pragma unroll
                         for (int ks = 0; ks < FC_K / 32; ks++) {
-                            const uint64_t ad = fc_desc(a_base + (uint32_t)(2 * ks) * lbo_a + (uint32_t)(mt * 128 + v) * 16u, lbo_a, 128u);
-                            const uint64_t bd = fc_desc(b_base + (uint32_t)v * FC_BROW + (uint32_t)(2 * ks) * (FC_N * 16), FC_N * 16, 128u);
+                            const uint64_t ad = ((uint64_t)hi << 32) | (a_lo0 + (uint32_t)ks * a_ks + (uint32_t)(mt * 128 + v));
+                            const uint64_t bd = ((uint64_t)hi << 32) | (b_lo0 + (uint32_t)v * (FC_BROW >> 4) + (uint32_t)ks * ((2u * FC_N * 16) >> 4));
                             fc_mma(d_base + mt * FC_N, ad, bd, idesc, (v | ks) != 0);
                         }
                 }
                 fc_commit(&a_empty[buf]);        // the A strip may be overwritten once these MMAs have read it
                 fc_commit(&acc_full[acc]);       // ... and the accumulator stage is complete
             }
+            __syncwarp();
         }
     } else {
         // ---- epilogue: warps 2..9; warp w may touch TMEM lanes 32 (w % 4) .. +31 = accumulator rows; the two warps of a quarter

@@ -15,15 +15,19 @@
 // N = 16 keeps ALL Toeplitz operands (kh x 2 planes x K x 16 BF16 <= 99 KB) RESIDENT in shared memory next to two A stages, and wastes
 // the least MMA work on Toeplitz zeros (K / kw = 1.55 at 31 x 31).
 //
-// Roles (352 threads, one persistent CTA per SM):
+// Roles (416 threads, one persistent CTA per SM):
 //   warp 0      producer: per tile the hi and lo strips (K columns x 256 + kh - 1 rows) by TMA in the K-major no-swizzle core-matrix
 //               layout (one 16-byte-wide box column per 8 K elements), ring of 2 stages
-//   warps 1, 2  MMA issuers, one per M-tile: kh x K/16 x 3 tcgen05.mma (M128 x N16 x K16) per tile; a kernel row's A operand is the
-//               same strip with the descriptor start address advanced by one 16-byte row
-//   warps 3-10  epilogue: tcgen05.ld of the other accumulator stage, + delta, 64-byte row stores
+//   warps 1-4   MMA issuers, two per M-tile (even / odd kernel rows, each into its own accumulator): kh/2 x K/16 x 3 tcgen05.mma
+//               (M128 x N16 x K16, 8 tensor-pipe cycles each) per tile; a kernel row's A operand is the same strip with the descriptor
+//               start address advanced by one 16-byte row.  One thread issues an MMA every ~25 cycles at best (the first version, one
+//               issuer per M-tile rebuilding four 64-bit descriptors per step, managed one per 55-80 cycles and ran SLOWER than the FP32
+//               kernel): descriptors are now a 32-bit add on the low word, the K loop is unrolled by template, four threads issue
+//   warps 5-12  epilogue: tcgen05.ld of the other accumulator stage (both issuers' partial sums), + delta, 64-byte row stores
 // The border-extended BF16 planes are written once per call by pad_split_kernel (reads 4 B, writes 4 B per pixel).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_bf16.h>
 #include "common.cuh"
@@ -33,7 +37,8 @@ namespace b200cv {
 
 constexpr int FF_N = 16;                      // output columns per tile = MMA N
 constexpr int FF_MT = 2;                      // M-tiles (128 rows) per tile
-constexpr int FF_THREADS = 352;               // producer, 2 issuers, 8 epilogue warps
+constexpr int FF_NI = 2;                      // MMA issuer warps per M-tile (kernel rows v = t, t + 2, ...)
+constexpr int FF_THREADS = 32 * (1 + FF_MT * FF_NI + 8);   // producer, 4 issuers, 8 epilogue warps
 constexpr int FF_SMEM_MAX = 227 * 1024 - 1024;
 constexpr int FF_NA = 2;                      // A stages
 
@@ -62,18 +67,38 @@ __global__ void ff_toeplitz_kernel(const __grid_constant__ FFTaps kp, int kw, in
     }
 }
 
-// border-extended source as two BF16 planes: out[pl][f][y][x] = split(src(border(y - ay), border(x - ax)))
-__global__ void __launch_bounds__(256) ff_pad_split_kernel(Img src, __nv_bfloat16* out, int pw, int ph, int ax, int ay, int border, size_t plane_elems)
+// border-extended source as two BF16 planes: out[pl][f][y][x] = split(src(border(y - ay), border(x - ax))).  One thread = 8 adjacent
+// elements of a row (pw is a multiple of 8): two 16-byte stores; the border rule per element only in the strips that leave the image
+// (the first version, one element and two 2-byte stores per thread, took 0.23 ms for 8 4K frames -- a third of the whole op).
+__global__ void __launch_bounds__(128) ff_pad_split_kernel(Img src, __nv_bfloat16* out, int pw, int ph, int ax, int ay, int border, size_t plane_elems)
 {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
-    if (x >= pw) return;
-    const int sy = border_interpolate(y - ay, src.rows, border), sx = border_interpolate(x - ax, src.cols, border);
-    const float a = (sy < 0 || sx < 0) ? 0.f : src.row<float>(f, sy)[sx];        // BORDER_CONSTANT: zeros
-    const __nv_bfloat16 hi = __float2bfloat16_rn(a);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(a - __bfloat162float(hi));
-    const size_t o = ((size_t)f * ph + y) * pw + x;
-    out[o] = hi;
-    out[plane_elems + o] = lo;
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8, y = blockIdx.y, f = blockIdx.z;
+    if (x0 >= pw) return;
+    const int sy = border_interpolate(y - ay, src.rows, border);
+    float a[8];
+    const int sx0 = x0 - ax;
+    if (sy >= 0 && sx0 >= 0 && sx0 + 8 <= src.cols) {
+        const float* sp = src.row<float>(f, sy) + sx0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = __ldg(sp + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int sx = border_interpolate(sx0 + i, src.cols, border);
+            a[i] = (sy < 0 || sx < 0) ? 0.f : src.row<float>(f, sy)[sx];        // BORDER_CONSTANT: zeros
+        }
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(a[2 * i]), h1 = __float2bfloat16_rn(a[2 * i + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(a[2 * i] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(a[2 * i + 1] - __bfloat162float(h1));
+        hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const size_t o = ((size_t)f * ph + y) * pw + x0;
+    *(uint4*)(out + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *(uint4*)(out + plane_elems + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 __device__ __forceinline__ uint64_t ff_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
@@ -85,6 +110,14 @@ __device__ __forceinline__ void ff_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// one lane of a converged warp (elect.sync): the MMA issuers run their loops warp-uniformly and elect the thread that issues, so the
+// descriptors live in uniform registers (under `if (lane == 0)` every operand went through an R2UR waterfall loop: ~15 instructions per MMA)
+__device__ __forceinline__ bool ff_elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void ff_commit(uint64_t* bar)
 {
@@ -107,30 +140,33 @@ __device__ __forceinline__ void ff_tmem_ld16(uint32_t taddr, uint32_t* r)
         : "r"(taddr) : "memory");
 }
 
+template <int KS>      // K / 16: MMA steps per kernel row
 __global__ void __launch_bounds__(FF_THREADS, 1) filter2d_tc_f32_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ bglob,
                                                                         Img dst, const __grid_constant__ FFParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const uint32_t brow = (uint32_t)2 * p.kch * FF_N * 16;                   // bytes of B per kernel row (both planes)
-    const uint32_t bplane = (uint32_t)p.kch * FF_N * 16;
+    constexpr int KCH = 2 * KS;
+    constexpr uint32_t brow = 2u * KCH * FF_N * 16;                          // bytes of B per kernel row (both planes)
+    constexpr uint32_t bplane = (uint32_t)KCH * FF_N * 16;
     const uint32_t lbo_a = (uint32_t)p.ra_alloc * 16u;                       // one 16-byte-wide column of the strip
-    const uint32_t aplane = (uint32_t)p.kch * lbo_a;
+    const uint32_t aplane = (uint32_t)KCH * lbo_a;
     const uint32_t abytes = 2 * aplane;                                      // one A stage (hi + lo)
     unsigned char* sB = smem;                                                // kh x brow, resident
     unsigned char* sA = smem + (size_t)p.kh * brow;                          // FF_NA stages
     __shared__ __align__(8) uint64_t b_full, a_full[FF_NA], a_empty[FF_NA], acc_full[2][FF_MT], acc_empty[2][FF_MT];
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int TM_COLS = 2 * FF_MT * FF_NI * FF_N;                        // 2 stages x M-tiles x issuers x 16 columns = 128
 
     if (threadIdx.x == 0) {
         mbar_init(&b_full, 1);
-        for (int s = 0; s < FF_NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], FF_MT); }
+        for (int s = 0; s < FF_NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], FF_MT * FF_NI); }
         for (int s = 0; s < 2; s++)
-            for (int m = 0; m < FF_MT; m++) { mbar_init(&acc_full[s][m], 1); mbar_init(&acc_empty[s][m], 4); }
+            for (int m = 0; m < FF_MT; m++) { mbar_init(&acc_full[s][m], FF_NI); mbar_init(&acc_empty[s][m], 4); }
         fence_barrier_init();
     }
-    if (warp == 1) {   // TMEM: 2 stages x FF_MT x 16 columns of FP32 accumulators = 64
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(64) : "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     ff_fence_before();
@@ -151,46 +187,60 @@ __global__ void __launch_bounds__(FF_THREADS, 1) filter2d_tc_f32_kernel(const __
                 mbar_arrive_expect_tx(&a_full[buf], abytes);
                 unsigned char* dstA = sA + (size_t)buf * abytes;
                 for (int pl = 0; pl < 2; pl++)
-                    for (int c = 0; c < p.kch; c++)
+                    for (int c = 0; c < KCH; c++)
                         for (int b = 0; b < p.nbox; b++)
                             tma_load_3d(dstA + (size_t)pl * aplane + (size_t)c * lbo_a + (size_t)b * p.box_h * 16, &tmap, tx * FF_N + 8 * c,
                                         ty * (128 * FF_MT) + b * p.box_h, f + pl * p.frames, &a_full[buf]);
             }
         }
-    } else if (warp <= FF_MT) {
-        if (lane == 0) {
-            // ---- MMA issuer of M-tile mt ----
-            const int mt = warp - 1;
-            // instruction descriptor: D = F32 (1 << 4), A = B = BF16 (1 at [7,10) and [10,13)), K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FF_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            mbar_wait(&b_full, 0);
-            const uint32_t b_base = smem_u32(sB);
-            int i = 0;
-            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
-                const int buf = i % FF_NA, acc = i & 1;
-                mbar_wait(&a_full[buf], (i / FF_NA) & 1);
-                mbar_wait(&acc_empty[acc][mt], ((i >> 1) & 1) ^ 1);
-                ff_fence_after();
-                const uint32_t a_base = smem_u32(sA + (size_t)buf * abytes) + (uint32_t)(mt * 128) * 16u;
-                const uint32_t d_addr = tmem + (uint32_t)(acc * FF_MT + mt) * FF_N;
-                for (int v = 0; v < p.kh; v++) {
-                    for (int ks = 0; ks < p.kch / 2; ks++) {
-                        const uint32_t aoff = a_base + (uint32_t)(2 * ks) * lbo_a + (uint32_t)v * 16u;
-                        const uint32_t boff = b_base + (uint32_t)v * brow + (uint32_t)(2 * ks) * (FF_N * 16);
-                        const uint64_t ah = ff_desc(aoff, lbo_a, 128u), al = ff_desc(aoff + aplane, lbo_a, 128u);
-                        const uint64_t bh = ff_desc(boff, FF_N * 16, 128u), bl = ff_desc(boff + bplane, FF_N * 16, 128u);
-                        ff_mma(d_addr, ah, bh, idesc, (v | ks) != 0);
-                        ff_mma(d_addr, ah, bl, idesc, 1);
-                        ff_mma(d_addr, al, bh, idesc, 1);
+    } else if (warp <= FF_MT * FF_NI) {
+        // ---- MMA issuer (mt, ti): kernel rows ti, ti + FF_NI, ... of M-tile mt into accumulator (acc, mt, ti).  The whole warp runs the loops
+        //      (uniform values), one elected lane issues ----
+        const int wu = __shfl_sync(0xffffffffu, warp, 0);
+        const int mt = (wu - 1) % FF_MT, ti = (wu - 1) / FF_MT;
+        // instruction descriptor: D = F32 (1 << 4), A = B = BF16 (1 at [7,10) and [10,13)), K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FF_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // shared-memory descriptors (K-major, no swizzle): low word = start >> 4 [0,14) | LBO >> 4 [16,30); high word = SBO >> 4 [0,14) | version 1 at bit 14.
+        // Everything that changes from MMA to MMA is the start address: a 32-bit add on the low word.
+        const uint32_t hi = (128u >> 4) | (1u << 14);
+        const uint32_t a_lbo = (lbo_a >> 4) << 16, b_lbo = ((uint32_t)(FF_N * 16) >> 4) << 16;
+        const uint32_t a_ks = (2u * lbo_a) >> 4, a_pl = aplane >> 4;                // per K step / hi -> lo plane
+        constexpr uint32_t b_ks = (2u * FF_N * 16) >> 4, b_pl = bplane >> 4, b_row = brow >> 4;
+        mbar_wait(&b_full, 0);
+        const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | b_lbo;
+        int i = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
+            const int buf = i % FF_NA, acc = i & 1;
+            mbar_wait(&a_full[buf], (i / FF_NA) & 1);
+            mbar_wait(&acc_empty[acc][mt], ((i >> 1) & 1) ^ 1);
+            ff_fence_after();
+            const uint32_t d_addr = tmem + (uint32_t)((acc * FF_MT + mt) * FF_NI + ti) * FF_N;
+            uint32_t a_lo = (((smem_u32(sA + (size_t)buf * abytes) + (uint32_t)(mt * 128) * 16u) & 0x3FFFFu) >> 4 | a_lbo) + (uint32_t)ti;   // + v rows
+            uint32_t b_lo = b_lo0 + (uint32_t)ti * b_row;
+            uint32_t first = 0;
+#pragma unroll 1
+            for (int v = ti; v < p.kh; v += FF_NI, a_lo += FF_NI, b_lo += FF_NI * b_row) {
+                if (ff_elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++) {
+                        const uint64_t ah = ((uint64_t)hi << 32) | (a_lo + ks * a_ks), al = ((uint64_t)hi << 32) | (a_lo + ks * a_ks + a_pl);
+                        const uint64_t bh = ((uint64_t)hi << 32) | (b_lo + ks * b_ks), bl = ((uint64_t)hi << 32) | (b_lo + ks * b_ks + b_pl);
+                        ff_mma(d_addr, ah, bh, idesc, ks == 0 ? first : 1u);
+                        ff_mma(d_addr, ah, bl, idesc, 1u);
+                        ff_mma(d_addr, al, bh, idesc, 1u);
                     }
                 }
-                ff_commit(&a_empty[buf]);          // both issuers arrive: the strip may be overwritten once their MMAs have read it
+                first = 1;
+            }
+            if (ff_elect_one()) {
+                ff_commit(&a_empty[buf]);          // all four issuers arrive: the strip may be overwritten once their MMAs have read it
                 ff_commit(&acc_full[acc][mt]);
             }
+            __syncwarp();
         }
     } else {
-        // ---- epilogue: warps 3..10; a warp may touch TMEM lanes 32 (warp % 4) .. +31 = accumulator rows; four warps per M-tile ----
-        const int quarter = warp & 3, mt = (warp - 3) >> 2;
+        // ---- epilogue: warps 5..12; a warp may touch TMEM lanes 32 (warp % 4) .. +31 = accumulator rows; four warps per M-tile ----
+        const int quarter = warp & 3, mt = (warp - 1 - FF_MT * FF_NI) >> 2;
         int i = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
             const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, f = t / (p.tiles_x * p.tiles_y);
@@ -199,17 +249,20 @@ __global__ void __launch_bounds__(FF_THREADS, 1) filter2d_tc_f32_kernel(const __
             ff_fence_after();
             const int gx0 = tx * FF_N;
             const int gy = ty * (128 * FF_MT) + mt * 128 + quarter * 32 + lane;
-            uint32_t r[16];
-            ff_tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * FF_MT + mt) * FF_N, r);
+            uint32_t r0[16], r1[16];
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * FF_MT + mt) * FF_NI) * FF_N;
+            ff_tmem_ld16(taddr, r0);
+            ff_tmem_ld16(taddr + FF_N, r1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             ff_fence_before();
             __syncwarp();
-            if (lane == 0) ff_mbar_arrive(&acc_empty[acc][mt]);       // 4 arrivals free the accumulator: the values are in registers
+            if (lane == 0) ff_mbar_arrive(&acc_empty[acc][mt]);       // 4 arrivals free the accumulators: the values are in registers
             if (gy < p.oh) {
                 float* dp = dst.row<float>(f, gy) + gx0;
                 float v[16];
+                // kernels with a single row leave the odd-row accumulator untouched (stale): it must not be added then
 #pragma unroll
-                for (int j = 0; j < 16; j++) v[j] = __fadd_rn(__uint_as_float(r[j]), p.delta);
+                for (int j = 0; j < 16; j++) v[j] = __fadd_rn(p.kh > 1 ? __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j])) : __uint_as_float(r0[j]), p.delta);
                 if (gx0 + 16 <= p.ow && ((uintptr_t)dp & 15) == 0) {
 #pragma unroll
                     for (int j = 0; j < 4; j++) ((float4*)dp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -222,7 +275,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) filter2d_tc_f32_kernel(const __
     }
     ff_fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
 }
 
 // filter2D, float single-channel source and destination.
@@ -230,6 +283,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) filter2d_tc_f32_kernel(const __
 int filter2d_f32_tensor(const Img& s, const Img& d, const float* k, int kw, int kh, int ax, int ay, float delta, int border, cudaStream_t st)
 {
     if (kw > 33 || kh > 33 || s.frames >= 32768) return B200CV_NOT_IMPLEMENTED;
+    // the cost is ~0.05 ms per kernel ROW (8 4K frames) whatever the width: below 15 rows the direct FP32 sum is at least as fast
+    if (kh < 15 && !getenv("B200CV_FILTER2D_TC_MIN_TAPS")) return B200CV_NOT_IMPLEMENTED;
     static thread_local FFTaps taps;
     for (int i = 0; i < kw * kh; i++) {
         if (!std::isfinite(k[i])) return B200CV_NOT_IMPLEMENTED;
@@ -260,15 +315,21 @@ int filter2d_f32_tensor(const Img& s, const Img& d, const float* k, int kw, int 
     B200_CUDA(cudaMallocAsync(&bglob, (size_t)kh * brow, st));
     ff_toeplitz_kernel<<<kh, 256, 0, st>>>(taps, kw, p.kch, (__nv_bfloat16*)bglob);
     count_launch();
-    ff_pad_split_kernel<<<dim3(div_up((unsigned)pw, 256), (unsigned)ph, (unsigned)s.frames), 256, 0, st>>>(s, pbuf, pw, ph, ax, ay, border, plane_elems);
+    ff_pad_split_kernel<<<dim3(div_up((unsigned)pw / 8, 128), (unsigned)ph, (unsigned)s.frames), 128, 0, st>>>(s, pbuf, pw, ph, ax, ay, border, plane_elems);
     count_launch();
     CUtensorMap tm;
     int rc = make_tensor_map_3d(&tm, pbuf, 2, pw, ph, 2 * s.frames, (size_t)pw * 2, (size_t)pw * ph * 2, 8, p.box_h);
     if (!rc) {
-        auto kern = filter2d_tc_f32_kernel;
         static PerDeviceFlag attr_pd; bool& attr = attr_pd.cur();
-        if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_MAX)); attr = true; }
-        kern<<<grid, FF_THREADS, smem, st>>>(tm, bglob, d, p);
+        if (!attr) {
+            B200_CUDA(cudaFuncSetAttribute(filter2d_tc_f32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_MAX));
+            B200_CUDA(cudaFuncSetAttribute(filter2d_tc_f32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_MAX));
+            B200_CUDA(cudaFuncSetAttribute(filter2d_tc_f32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_MAX));
+            attr = true;
+        }
+        if (p.kch == 2) filter2d_tc_f32_kernel<1><<<grid, FF_THREADS, smem, st>>>(tm, bglob, d, p);
+        else if (p.kch == 4) filter2d_tc_f32_kernel<2><<<grid, FF_THREADS, smem, st>>>(tm, bglob, d, p);
+        else filter2d_tc_f32_kernel<3><<<grid, FF_THREADS, smem, st>>>(tm, bglob, d, p);
         cudaError_t e = cudaGetLastError();
         count_launch();
         if (e != cudaSuccess) rc = cuda_fail(e, "kernel launch", __FILE__, __LINE__);

@@ -26,6 +26,7 @@
 // IDP runs on the half-rate FMA-heavy pipe: 3.5 / 5 / 6.5 / 8 IDP per pixel at K = 3 / 5 / 7 / 9 bound K = 7 and 9 below the HBM
 // roofline whatever else is done.
 #include <string.h>
+#include <algorithm>
 #include "common.cuh"
 #ifndef B200CV_HOST_EMULATION
 #include "tma.cuh"
@@ -51,6 +52,7 @@ struct GMParams {
     int W, H, border;
     int sep_mode, even_limit;   // sepFilter2D's 8.8 mode: columns < even_limit round half-to-even, the rest half-up (filter.simd.hpp:1011-1100)
     int tiles_x, nseg, seg_rows, nitems;   // work decomposition: item = (frame, strip, segment), item = (f * nseg + seg) * tiles_x + strip
+    int* queue;                            // dynamic distribution: items beyond the first wave are drawn from this counter (zeroed per launch)
 };
 
 // 16-bit row sums of the lane's 8 columns for one staged row.  rp = the lane's own 8 bytes of that row.
@@ -218,7 +220,7 @@ gauss_u8_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     };
 
     GMItem g = gm_item<KB>(p, item);
-    GMItem gn = g;                       // producer side: one chunk ahead
+    GMItem gn = g;                       // producer side: one chunk ahead of the consumer
     int n_item = item, n_chunk = 0;
     if (lane == 0) issue(g, 0, 0);
     uint32_t win[NP][8];
@@ -229,9 +231,15 @@ gauss_u8_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
     int seq = 0;                         // chunks consumed so far: buffer = seq & 1, parity = (seq >> 1) & 1
     int chunk = 0;
     while (true) {
-        // ---- prefetch the next chunk (this item's or the next item's first) into the other buffer ----
+        // ---- prefetch the next chunk (this item's, or the first of the next item drawn from the queue) into the other buffer ----
         if (n_chunk + 1 < gn.nchunks) n_chunk++;
-        else { n_item += nwk; n_chunk = 0; if (n_item < p.nitems) gn = gm_item<KB>(p, n_item); }
+        else {
+            int v = 0;
+            if (lane == 0) v = nwk + atomicAdd(p.queue, 1);            // the first nwk items were dealt out statically
+            n_item = __shfl_sync(0xffffffffu, v, 0);
+            n_chunk = 0;
+            if (n_item < p.nitems) gn = gm_item<KB>(p, n_item);
+        }
         __syncwarp();                    // every lane is done reading the other buffer (chunk seq - 1)
         if (n_item < p.nitems && lane == 0) { fence_proxy_async(); issue(gn, n_chunk, (seq + 1) & 1); }
         // ---- wait for this chunk ----
@@ -254,12 +262,12 @@ gauss_u8_stream_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_co
             __syncwarp();
         }
         gm_lane_chunk<KB, SEP>(cb, lane, p, dst, g, chunk, win);
-        // ---- advance ----
+        // ---- advance: after an item's last chunk the producer already stands on the next item ----
         seq++;
         if (++chunk == g.nchunks) {
-            item += nwk; chunk = 0;
+            item = n_item; chunk = 0;
             if (item >= p.nitems) break;
-            g = gm_item<KB>(p, item);
+            g = gn;
         }
     }
 }
@@ -274,21 +282,27 @@ static int launch_gm(const CUtensorMap& tm, const CUtensorMap& tm_row, const Img
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cps, p.sep_mode ? k1 : k0, GM_WARPS * 32, 0));
     if (cps < 1) cps = 1;
     const int capacity = num_sms() * cps * GM_WARPS;            // workers in one wave
-    // decomposition: strips x frames x segments; segments sized so that all items fit ONE wave when the image allows it
+    // decomposition: strips x frames x segments of ~64 rows.  One wave of CTAs; a warp that finishes its item draws the next from an atomic
+    // counter.  (A static split into exactly one item per warp left the SMs idle for 30 % of the kernel: warps that share an SM with more
+    // or slower neighbours finish late, and nothing can be moved to the SMs that are already done.)
     p.tiles_x = (int)div_up((unsigned)p.W, GM_OW);
     const long strips = (long)p.tiles_x * frames;
-    int nseg = (int)(capacity / strips);
-    if (nseg < 1) nseg = 1;
-    int seg_rows = (int)div_up(div_up((unsigned)p.H, (unsigned)nseg), CH) * CH;
-    p.seg_rows = seg_rows;
-    p.nseg = (int)div_up((unsigned)p.H, (unsigned)seg_rows);
+    p.seg_rows = (int)div_up(64u, CH) * CH;
+    if (strips * div_up((unsigned)p.H, (unsigned)p.seg_rows) < 2L * capacity)         // small images: shorter segments, so that every warp gets work
+        p.seg_rows = (int)std::max<long>(CH, (long)div_up((unsigned)std::max<long>(1, (long)p.H * strips / (2L * capacity)), CH) * CH);
+    p.nseg = (int)div_up((unsigned)p.H, (unsigned)p.seg_rows);
     const long nitems = strips * p.nseg;
     if (nitems >= (1L << 30)) return B200CV_NOT_IMPLEMENTED;
     p.nitems = (int)nitems;
     const unsigned grid = (unsigned)((nitems < capacity ? nitems : capacity) + GM_WARPS - 1) / GM_WARPS;
+    int* queue = nullptr;
+    B200_CUDA(cudaMallocAsync(&queue, sizeof(int), st));
+    B200_CUDA(cudaMemsetAsync(queue, 0, sizeof(int), st));
+    p.queue = queue;
     if (p.sep_mode) k1<<<grid, GM_WARPS * 32, 0, st>>>(tm, tm_row, d, p);
     else k0<<<grid, GM_WARPS * 32, 0, st>>>(tm, tm_row, d, p);
     cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(queue, st);
     count_launch();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
     return B200CV_OK;

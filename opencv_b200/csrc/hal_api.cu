@@ -89,6 +89,49 @@ static int host_pipeline(const b200cvMat* hsrc, const b200cvMat* hdst, const Dev
     return B200CV_OK;
 }
 
+// ROI of a larger cv::Mat (row a5 of the scope table: FilterEngine's wholeSize / ofs, filterengine.hpp:68-246; HAL arguments
+// full_width / full_height / offset_x / offset_y, hal_replacement.hpp:125, and margin_*, :1146): the pixels around the ROI are REAL and the
+// border rule only applies at the edges of the parent image.  A filter with reach (l, t, r, b) needs at most that many parent pixels on each
+// side: upload the ROI extended by min(reach, available margin), run the same device op on the extended image and download the ROI part.
+// Where the extension was clipped by the parent's edge the extended image's edge IS the parent's edge (the border rule lands where the
+// reference applies it); where it was not, no output pixel of the ROI reaches the artificial edge.  One frame (what the HAL passes).
+static int host_roi_call(const b200cvMat* hsrc, const b200cvMat* hdst, int l, int t, int r, int b, const DevOp& op)
+{
+    int rc;
+    configure_mem_pool();
+    if ((rc = check_mat(hsrc, "src")) || (rc = check_mat(hdst, "dst"))) return rc;
+    B200_REQUIRE(hsrc->frames <= 1 && hdst->frames <= 1, "ROI context is a single-frame path");
+    B200_REQUIRE(hsrc->cols == hdst->cols && hsrc->rows == hdst->rows, "ROI context: src/dst size mismatch");
+    const size_t es_s = elem_size(hsrc->type), es_d = elem_size(hdst->type);
+    b200cvMat es = *hsrc, ed = *hdst;
+    es.cols += l + r; es.rows += t + b; ed.cols = es.cols; ed.rows = es.rows;
+    const char* hs = (const char*)hsrc->data - (size_t)t * hsrc->step - (size_t)l * es_s;
+    const size_t sp = pitch_of(&es), dp = pitch_of(&ed);
+    HostCtx& c = g_ctx;
+    if (!c.st[0]) B200_CUDA(cudaStreamCreateWithFlags(&c.st[0], cudaStreamNonBlocking));
+    if ((rc = ensure(&c.dbuf[0][0], &c.cap[0][0], sp * es.rows)) || (rc = ensure(&c.dbuf[0][1], &c.cap[0][1], dp * ed.rows))) return rc;
+    cudaStream_t st = c.st[0];
+    B200_CUDA(cudaMemcpy2DAsync(c.dbuf[0][0], sp, hs, hsrc->step, (size_t)es.cols * es_s, es.rows, cudaMemcpyHostToDevice, st));
+    b200cvMat ds = {c.dbuf[0][0], sp, es.cols, es.rows, hsrc->type, 1, 0};
+    b200cvMat dd = {c.dbuf[0][1], dp, ed.cols, ed.rows, hdst->type, 1, 0};
+    if ((rc = op(&ds, &dd, (void*)st))) { cudaStreamSynchronize(st); return rc; }
+    B200_CUDA(cudaMemcpy2DAsync(hdst->data, hdst->step, (const char*)c.dbuf[0][1] + (size_t)t * dp + (size_t)l * es_d, dp, (size_t)hdst->cols * es_d, hdst->rows,
+                                cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200CV_OK;
+}
+
+// how much of the filter's reach the parent image can supply on each side; all zero -> the plain pipeline.  BORDER_ISOLATED: the ROI is the image.
+struct RoiExt { int l, t, r, b; bool any() const { return (l | t | r | b) != 0; } };
+static inline RoiExt roi_ext(size_t ml, size_t mt, size_t mr, size_t mb, int rl, int rt, int rr, int rb, int border)
+{
+    RoiExt e = {0, 0, 0, 0};
+    if (border & B200CV_BORDER_ISOLATED) return e;
+    e.l = (int)std::min<size_t>(ml, (size_t)std::max(rl, 0)); e.t = (int)std::min<size_t>(mt, (size_t)std::max(rt, 0));
+    e.r = (int)std::min<size_t>(mr, (size_t)std::max(rr, 0)); e.b = (int)std::min<size_t>(mb, (size_t)std::max(rb, 0));
+    return e;
+}
+
 static inline b200cvMat hmat(const void* p, size_t step, int w, int h, int type)
 {
     b200cvMat m = {const_cast<void*>(p), step, w, h, type, 1, 0};
@@ -155,29 +198,33 @@ extern "C" int b200cv_host_match_template(const b200cvMat* image, const b200cvMa
     const size_t tp = pitch_of(templ);
     if ((rc = ensure(&c.daux, &c.caux, tp * templ->rows))) return rc;
     B200_CUDA(cudaMemcpy2D(c.daux, tp, templ->data, templ->step, (size_t)templ->cols * elem_size(templ->type), templ->rows, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaStreamSynchronize(cudaStreamLegacy));          // pageable source: the call may return once the data is STAGED; the pipeline streams are non-blocking
     b200cvMat dt = {c.daux, tp, templ->cols, templ->rows, templ->type, 1, 0};
     return host_pipeline(image, result, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_match_template(a, &dt, b, method, st); });
 }
 
 // ---- cv_hal_* replacements ----------------------------------------------------------------------------------------------
-#define NO_MARGINS(l, t, r, b, border) \
-    if (((l) | (t) | (r) | (b)) != 0 && !((border) & B200CV_BORDER_ISOLATED)) return B200CV_NOT_IMPLEMENTED   /* ROI of a larger Mat: let OpenCV handle it */
-
 extern "C" int b200cv_hal_gaussianBlur(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int cn,
                                        size_t ml, size_t mt, size_t mr, size_t mb, size_t kw, size_t kh, double sx, double sy, int border)
 {
-    NO_MARGINS(ml, mt, mr, mb, border);
-    if (src == dst) return B200CV_NOT_IMPLEMENTED;
+    // in place (src == dst) is fine on this path: the source is on the device before the result comes back
     b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(depth, cn)), d = hmat(dst, dstep, w, h, B200CV_MAKETYPE(depth, cn));
+    if ((ml | mt | mr | mb) != 0 && !(border & B200CV_BORDER_ISOLATED)) {
+        if (kw < 1 || kh < 1) return B200CV_NOT_IMPLEMENTED;      // size left to be derived from sigma: the reach is not known here
+        const RoiExt e = roi_ext(ml, mt, mr, mb, (int)kw / 2, (int)kh / 2, (int)kw / 2, (int)kh / 2, border);
+        if (e.any())
+            return host_roi_call(&s, &d, e.l, e.t, e.r, e.b, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_gaussian_blur(a, b, (int)kw, (int)kh, sx, sy, border, st); });
+    }
     return b200cv_host_gaussian_blur(&s, &d, (int)kw, (int)kh, sx, sy, border);
 }
 
 extern "C" int b200cv_hal_gaussianBlurBinomial(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int cn,
                                                size_t ml, size_t mt, size_t mr, size_t mb, size_t ksize, int border)
 {
-    NO_MARGINS(ml, mt, mr, mb, border);
-    if (src == dst) return B200CV_NOT_IMPLEMENTED;
     b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(depth, cn)), d = hmat(dst, dstep, w, h, B200CV_MAKETYPE(depth, cn));
+    const RoiExt e = roi_ext(ml, mt, mr, mb, (int)ksize / 2, (int)ksize / 2, (int)ksize / 2, (int)ksize / 2, border);
+    if (e.any())
+        return host_roi_call(&s, &d, e.l, e.t, e.r, e.b, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_gaussian_blur(a, b, (int)ksize, (int)ksize, 0, 0, border, st); });
     return b200cv_host_gaussian_blur(&s, &d, (int)ksize, (int)ksize, 0, 0, border);
 }
 
@@ -197,10 +244,15 @@ extern "C" int b200cv_hal_sepFilter(b200cvFilterCtx* context, uchar* src, size_t
 {
     FilterCtxImpl* c = (FilterCtxImpl*)context;
     if (!c) return B200CV_ERR_BAD_ARG;
-    if ((fw != w || fh != h || ox || oy) && !(c->border & B200CV_BORDER_ISOLATED)) return B200CV_NOT_IMPLEMENTED;
-    if (src == dst) return B200CV_NOT_IMPLEMENTED;
     b200cvMat s = hmat(src, sstep, w, h, c->src_type), d = hmat(dst, dstep, w, h, c->dst_type);
-    return b200cv_host_sep_filter2d(&s, &d, c->kx.data(), (int)c->kx.size(), c->ky.data(), (int)c->ky.size(), c->ax, c->ay, c->delta, c->border);
+    const int nx = (int)c->kx.size(), ny = (int)c->ky.size(), ax = c->ax < 0 ? nx / 2 : c->ax, ay = c->ay < 0 ? ny / 2 : c->ay;
+    if (ox < 0 || oy < 0 || fw < ox + w || fh < oy + h) return B200CV_NOT_IMPLEMENTED;
+    const RoiExt e = roi_ext((size_t)ox, (size_t)oy, (size_t)(fw - w - ox), (size_t)(fh - h - oy), ax, ay, nx - 1 - ax, ny - 1 - ay, c->border);
+    const float *kx = c->kx.data(), *ky = c->ky.data();
+    const int cax = c->ax, cay = c->ay, cb = c->border; const double cd = c->delta;
+    if (e.any())
+        return host_roi_call(&s, &d, e.l, e.t, e.r, e.b, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_sep_filter2d(a, b, kx, nx, ky, ny, cax, cay, cd, cb, st); });
+    return b200cv_host_sep_filter2d(&s, &d, kx, nx, ky, ny, cax, cay, cd, cb);
 }
 
 extern "C" int b200cv_hal_sepFilterFree(b200cvFilterCtx* context) { delete (FilterCtxImpl*)context; return B200CV_OK; }
@@ -221,10 +273,15 @@ extern "C" int b200cv_hal_filter(b200cvFilterCtx* context, uchar* src, size_t ss
 {
     FilterCtxImpl* c = (FilterCtxImpl*)context;
     if (!c) return B200CV_ERR_BAD_ARG;
-    if ((fw != w || fh != h || ox || oy) && !(c->border & B200CV_BORDER_ISOLATED)) return B200CV_NOT_IMPLEMENTED;
-    if (src == dst) return B200CV_NOT_IMPLEMENTED;
     b200cvMat s = hmat(src, sstep, w, h, c->src_type), d = hmat(dst, dstep, w, h, c->dst_type);
-    return b200cv_host_filter2d(&s, &d, c->k2d.data(), c->kw, c->kh, c->ax, c->ay, c->delta, c->border);
+    const int ax = c->ax < 0 ? c->kw / 2 : c->ax, ay = c->ay < 0 ? c->kh / 2 : c->ay;
+    if (ox < 0 || oy < 0 || fw < ox + w || fh < oy + h) return B200CV_NOT_IMPLEMENTED;
+    const RoiExt e = roi_ext((size_t)ox, (size_t)oy, (size_t)(fw - w - ox), (size_t)(fh - h - oy), ax, ay, c->kw - 1 - ax, c->kh - 1 - ay, c->border);
+    const float* k2 = c->k2d.data();
+    const int kw = c->kw, kh = c->kh, cax = c->ax, cay = c->ay, cb = c->border; const double cd = c->delta;
+    if (e.any())
+        return host_roi_call(&s, &d, e.l, e.t, e.r, e.b, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_filter2d(a, b, k2, kw, kh, cax, cay, cd, cb, st); });
+    return b200cv_host_filter2d(&s, &d, k2, kw, kh, cax, cay, cd, cb);
 }
 
 extern "C" int b200cv_hal_filterFree(b200cvFilterCtx* context) { delete (FilterCtxImpl*)context; return B200CV_OK; }
@@ -232,9 +289,12 @@ extern "C" int b200cv_hal_filterFree(b200cvFilterCtx* context) { delete (FilterC
 extern "C" int b200cv_hal_sobel(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int sdepth, int ddepth, int cn,
                                 int ml, int mt, int mr, int mb, int dx, int dy, int ksize, double scale, double delta, int border)
 {
-    NO_MARGINS(ml, mt, mr, mb, border);
-    if (src == dst) return B200CV_NOT_IMPLEMENTED;
+    if (src == dst && sdepth != ddepth) return B200CV_NOT_IMPLEMENTED;
     b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(sdepth, cn)), d = hmat(dst, dstep, w, h, B200CV_MAKETYPE(ddepth, cn));
+    const int rr = ksize <= 0 ? 1 : ksize / 2;                 // Scharr (ksize -1) and 1 x 3 / 3 x 1 kernels reach one pixel
+    const RoiExt e = roi_ext((size_t)std::max(ml, 0), (size_t)std::max(mt, 0), (size_t)std::max(mr, 0), (size_t)std::max(mb, 0), rr, rr, rr, rr, border);
+    if (e.any())
+        return host_roi_call(&s, &d, e.l, e.t, e.r, e.b, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_sobel(a, b, dx, dy, ksize, scale, delta, border, st); });
     return b200cv_host_sobel(&s, &d, dx, dy, ksize, scale, delta, border);
 }
 
@@ -247,10 +307,14 @@ extern "C" int b200cv_hal_scharr(const uchar* src, size_t sstep, uchar* dst, siz
 extern "C" int b200cv_hal_boxFilter(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int sdepth, int ddepth, int cn,
                                     int ml, int mt, int mr, int mb, size_t kw, size_t kh, int ax, int ay, bool normalize, int border)
 {
-    NO_MARGINS(ml, mt, mr, mb, border);
-    if (src == dst || kw > 128 || kh > 128) return B200CV_NOT_IMPLEMENTED;
+    if ((src == dst && sdepth != ddepth) || kw > 128 || kh > 128) return B200CV_NOT_IMPLEMENTED;
     b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(sdepth, cn)), d = hmat(dst, dstep, w, h, B200CV_MAKETYPE(ddepth, cn));
-    return b200cv_host_box_filter(&s, &d, (int)kw, (int)kh, ax, ay, normalize ? 1 : 0, border);
+    const int bax = ax < 0 ? (int)kw / 2 : ax, bay = ay < 0 ? (int)kh / 2 : ay;
+    const RoiExt e = roi_ext((size_t)std::max(ml, 0), (size_t)std::max(mt, 0), (size_t)std::max(mr, 0), (size_t)std::max(mb, 0), bax, bay, (int)kw - 1 - bax, (int)kh - 1 - bay, border);
+    const int ikw = (int)kw, ikh = (int)kh, nrm = normalize ? 1 : 0;
+    if (e.any())
+        return host_roi_call(&s, &d, e.l, e.t, e.r, e.b, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_box_filter(a, b, ikw, ikh, ax, ay, nrm, border, st); });
+    return b200cv_host_box_filter(&s, &d, ikw, ikh, ax, ay, nrm, border);
 }
 
 // cv::integral has two outputs: sum through the pipeline; sqsum (rare) as a second pass over the same source
@@ -330,6 +394,7 @@ extern "C" int b200cv_host_remap(const b200cvMat* src, const b200cvMat* dst, con
     if ((rc = ensure(&c.daux, &c.caux, b1 + b2))) return rc;
     B200_CUDA(cudaMemcpy2D(c.daux, p1, map1->data, map1->step, (size_t)map1->cols * elem_size(map1->type), map1->rows, cudaMemcpyHostToDevice));
     if (has2) B200_CUDA(cudaMemcpy2D((char*)c.daux + b1, p2, map2->data, map2->step, (size_t)map2->cols * elem_size(map2->type), map2->rows, cudaMemcpyHostToDevice));
+    B200_CUDA(cudaStreamSynchronize(cudaStreamLegacy));          // pageable sources: see b200cv_host_match_template
     b200cvMat d1 = {c.daux, p1, map1->cols, map1->rows, map1->type, 1, 0};
     b200cvMat d2 = {has2 ? (void*)((char*)c.daux + b1) : nullptr, p2, has2 ? map2->cols : 0, has2 ? map2->rows : 0, has2 ? map2->type : 0, 1, 0};
     return host_pipeline(src, dst, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_remap(a, b, &d1, has2 ? &d2 : nullptr, interp, border, bv, st); });

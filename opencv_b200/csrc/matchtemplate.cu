@@ -304,6 +304,26 @@ __device__ __forceinline__ void mt_row4(const unsigned* __restrict__ wp, int w, 
     }
 }
 
+// the same for a template width of 4 * WW bytes, everything at compile time: words 1 .. WW-1 lie inside all four windows, word 0 loses its
+// first k bytes and word WW contributes its first k bytes (no loop, no run-time masks; the caller guarantees that word WW is inside the row)
+template <int WW>
+__device__ __forceinline__ void mt_row4_fixed(const unsigned* __restrict__ wp, unsigned s[4], unsigned q[4])
+{
+    unsigned v[WW + 1];
+#pragma unroll
+    for (int j = 0; j <= WW; j++) v[j] = __ldg(wp + j);
+    unsigned ms = 0, mq = 0;
+#pragma unroll
+    for (int j = 1; j < WW; j++) { ms = __dp4a(v[j], 0x01010101u, ms); mq = __dp4a(v[j], v[j], mq); }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const unsigned m0 = k == 0 ? 0xFFFFFFFFu : 0xFFFFFFFFu << (8 * k), m1 = ~m0;
+        const unsigned a = v[0] & m0, b = v[WW] & m1;
+        s[k] = __dp4a(b, 0x01010101u, __dp4a(a, 0x01010101u, ms));
+        q[k] = __dp4a(b, v[WW], __dp4a(a, v[0], mq));
+    }
+}
+
 __device__ __forceinline__ float mt_normalize_one(double num, double ws, double wq, int numType, bool isNormed, int method, const TemplStats& st)
 {
     double t, wndMean2 = 0, wndSum2 = 0;
@@ -330,6 +350,7 @@ __device__ __forceinline__ float mt_normalize_one(double num, double ws, double 
 
 constexpr int MTF_SEG = 128;     // result rows per thread
 
+template <int WW>      // template width / 4 when it is a multiple of 4 in {16, 32, 64, 128} bytes, 0 = any width
 __global__ void __launch_bounds__(128) mt_fused_u8_kernel(Img img, Img res, int w, int h, int method, const TemplStats* __restrict__ stats)
 {
     const int f = blockIdx.z;
@@ -341,10 +362,16 @@ __global__ void __launch_bounds__(128) mt_fused_u8_kernel(Img img, Img res, int 
     const bool isNormed = method == B200CV_TM_CCORR_NORMED || method == B200CV_TM_SQDIFF_NORMED || method == B200CV_TM_CCOEFF_NORMED;
     const int jmax = (img.cols - x0 + 3) / 4 - 1;                    // last word of the row that still holds image bytes
     const int n = min(4, res.cols - x0);
+    const bool fixed = WW > 0 && jmax >= WW;                          // all WW + 1 words inside the row: the compile-time variant
+    auto row4 = [&](int y, unsigned* s, unsigned* q) {
+        const unsigned* wp = (const unsigned*)(img.row<uchar>(f, y) + x0);
+        if constexpr (WW > 0) { if (fixed) { mt_row4_fixed<WW>(wp, s, q); return; } }
+        mt_row4(wp, w, jmax, s, q);
+    };
     unsigned ws[4] = {0, 0, 0, 0}, wq[4] = {0, 0, 0, 0};
     for (int j = 0; j < h; j++) {
         unsigned s[4], q[4];
-        mt_row4((const unsigned*)(img.row<uchar>(f, ys + j) + x0), w, jmax, s, q);
+        row4(ys + j, s, q);
 #pragma unroll
         for (int k = 0; k < 4; k++) { ws[k] += s[k]; wq[k] += q[k]; }
     }
@@ -364,8 +391,8 @@ __global__ void __launch_bounds__(128) mt_fused_u8_kernel(Img img, Img res, int 
         else for (int k = 0; k < n; k++) rp[k] = out[k];
         if (y + 1 < ye) {
             unsigned s[4], q[4], s2[4], q2[4];
-            mt_row4((const unsigned*)(img.row<uchar>(f, y + h) + x0), w, jmax, s, q);
-            mt_row4((const unsigned*)(img.row<uchar>(f, y) + x0), w, jmax, s2, q2);
+            row4(y + h, s, q);
+            row4(y, s2, q2);
 #pragma unroll
             for (int k = 0; k < 4; k++) { ws[k] += s[k] - s2[k]; wq[k] += q[k] - q2[k]; }
         }
@@ -430,7 +457,14 @@ extern "C" int b200cv_match_template(const b200cvMat* image, const b200cvMat* te
         B200_CUDA(cudaMallocAsync(&d_stats, sizeof(TemplStats), st));
         templ_stats_kernel<uchar><<<1, 256, 0, st>>>(tp, method, d_stats);
         count_launch();
-        mt_fused_u8_kernel<<<dim3(div_up(div_up((unsigned)ow, 4), 128), div_up((unsigned)oh, MTF_SEG), frames), 128, 0, st>>>(im, rs, w, h, method, d_stats);
+        const dim3 fg(div_up(div_up((unsigned)ow, 4), 128), div_up((unsigned)oh, MTF_SEG), frames);
+        switch (w) {
+        case 16: mt_fused_u8_kernel<4><<<fg, 128, 0, st>>>(im, rs, w, h, method, d_stats); break;
+        case 32: mt_fused_u8_kernel<8><<<fg, 128, 0, st>>>(im, rs, w, h, method, d_stats); break;
+        case 64: mt_fused_u8_kernel<16><<<fg, 128, 0, st>>>(im, rs, w, h, method, d_stats); break;
+        case 128: mt_fused_u8_kernel<32><<<fg, 128, 0, st>>>(im, rs, w, h, method, d_stats); break;
+        default: mt_fused_u8_kernel<0><<<fg, 128, 0, st>>>(im, rs, w, h, method, d_stats); break;
+        }
         B200_LAUNCH_CHECK();
         B200_CUDA(cudaFreeAsync(d_stats, st));
         return B200CV_OK;

@@ -85,6 +85,14 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp: the issuer warp runs its loop warp-uniformly and elects the issuing thread, so the descriptors stay in
+// uniform registers (issued from inside `if (lane == 0)` every operand went through an R2UR waterfall: ~15 instructions per MMA)
+__device__ __forceinline__ bool umma_elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -153,31 +161,38 @@ __global__ void __launch_bounds__(128) ccorr_u8_tc_kernel(const __grid_constant_
             mbar_arrive_expect_tx(&full[s], bbytes);
             bulk_load(sB + (size_t)s * bbytes, bglob + (size_t)v * bbytes, bbytes, &full[s]);
         }
-    } else if (warp == 1 && lane == 0) {
-        // ---- MMA issuer ----
+    } else if (warp == 1) {
+        // ---- MMA issuer: the whole warp runs the loop (uniform values), one elected lane issues ----
         // instruction descriptor: D = S32 (2<<4), A = B = unsigned 8 bit (0 at [7,10) and [10,13)),
         // K-major both, N>>3 at [17,23), M>>4 at [24,29)
         const uint32_t idesc = (2u << 4) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         mbar_wait(&a_full, 0);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+        // descriptors (K-major, no swizzle): low word = start >> 4 [0,14) | LBO >> 4 [16,30); high word = SBO >> 4 | version 1 at bit 14
+        const uint32_t hi = (128u >> 4) | (1u << 14);
+        const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | ((lbo_a >> 4) << 16);
+        const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (((uint32_t)(NN * 16) >> 4) << 16);
+        const uint32_t a_ks = (2u * lbo_a) >> 4;
         for (int v = 0; v < p.h; v++) {
             const int s = v % TC_NS;
             mbar_wait(&full[s], (v / TC_NS) & 1);
             tc_fence_after();
+            if (umma_elect_one()) {
 #pragma unroll
-            for (int mt = 0; mt < TC_MT; mt++)
+                for (int mt = 0; mt < TC_MT; mt++)
 #pragma unroll
-                for (int ks = 0; ks < TC_K / 32; ks++) {
-                    if (ks < p.kch) {
-                        uint64_t ad = umma_desc(a_base + (uint32_t)(2 * ks) * lbo_a + (uint32_t)(mt * 128 + v) * 16u, lbo_a, 128u);
-                        uint64_t bd = umma_desc(b_base + (uint32_t)s * bbytes + (uint32_t)(2 * ks) * (NN * 16), NN * 16, 128u);
-                        umma_i8(tmem + mt * NN, ad, bd, idesc, (v | ks) != 0);
+                    for (int ks = 0; ks < TC_K / 32; ks++) {
+                        if (ks < p.kch) {
+                            const uint64_t ad = ((uint64_t)hi << 32) | (a_lo0 + (uint32_t)ks * a_ks + (uint32_t)(mt * 128 + v));
+                            const uint64_t bd = ((uint64_t)hi << 32) | (b_lo0 + (((uint32_t)s * bbytes) >> 4) + (uint32_t)ks * ((2u * NN * 16) >> 4));
+                            umma_i8(tmem + mt * NN, ad, bd, idesc, (v | ks) != 0);
+                        }
                     }
-                }
-            umma_commit(&empty[s]);
+                umma_commit(&empty[s]);
+            }
+            __syncwarp();
         }
-        umma_commit(&acc_full);
+        if (umma_elect_one()) umma_commit(&acc_full);
     }
     // ---- epilogue: all four warps; warp w owns TMEM lanes (= accumulator rows) 32w .. 32w+31 ----
     __syncwarp();

@@ -148,12 +148,11 @@ __device__ __forceinline__ void rs_hpass_thread(const Img& src, int f, const Res
 
 // ---- V pass: item = 4 adjacent byte elements (tile element e0 .. e0+3) of destination row `row` of the tile -------------------------------
 template <int CN, bool CUBIC>
-__device__ __forceinline__ unsigned rs_vpass_item(const unsigned char* mid, const RSRow& yr, int e0, int ge0, int vec_limit)
+__device__ __forceinline__ unsigned rs_vpass_item(const unsigned char* const* mrow /* filtered row per tap */, const RSRow& yr, int e0, int ge0, int vec_limit)
 {
-    constexpr int E = RSCfg<CN, CUBIC>::E;
     unsigned out = 0;
     if constexpr (!CUBIC) {
-        const uint2 m0 = *(const uint2*)(mid + ((size_t)yr.r[0] * E + e0) * 2), m1 = *(const uint2*)(mid + ((size_t)yr.r[1] * E + e0) * 2);
+        const uint2 m0 = *(const uint2*)(mrow[0] + e0 * 2), m1 = *(const uint2*)(mrow[1] + e0 * 2);
         const unsigned T0[4] = {m0.x & 0xffffu, m0.x >> 16, m0.y & 0xffffu, m0.y >> 16}, T1[4] = {m1.x & 0xffffu, m1.x >> 16, m1.y & 0xffffu, m1.y >> 16};
         unsigned v[4];
 #pragma unroll
@@ -163,7 +162,7 @@ __device__ __forceinline__ unsigned rs_vpass_item(const unsigned char* mid, cons
         float S[4][4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const uint4 q = *(const uint4*)(mid + ((size_t)yr.r[k] * E + e0) * 4);
+            const uint4 q = *(const uint4*)(mrow[k] + e0 * 4);
             S[k][0] = __int_as_float((int)q.x); S[k][1] = __int_as_float((int)q.y); S[k][2] = __int_as_float((int)q.z); S[k][3] = __int_as_float((int)q.w);
         }
         int v[4];
@@ -230,9 +229,12 @@ __device__ __forceinline__ void rs_vpass_thread(int tid, int nthreads, const uns
     const size_t dstep = (size_t)nwarps * dst.step;
     for (int row = warp; row < nrows_out; row += nwarps, drow += dstep) {
         const RSRow yr = yrow[row];
+        const unsigned char* mrow[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) mrow[k] = mid + (size_t)yr.r[k] * (RSCfg<CN, CUBIC>::E * RSCfg<CN, CUBIC>::MIDB);
         for (int q = lane; q < nq; q += 32) {
             const int e0 = 4 * q;
-            const unsigned out = rs_vpass_item<CN, CUBIC>(mid, yr, e0, x0 * CN + e0, vec_limit);
+            const unsigned out = rs_vpass_item<CN, CUBIC>(mrow, yr, e0, x0 * CN + e0, vec_limit);
             uchar* d = drow + e0;
             if (vec_store && e0 + 4 <= ne) *(unsigned*)d = out;
             else for (int i = 0; i < 4 && e0 + i < ne; i++) d[i] = (uchar)(out >> (8 * i));

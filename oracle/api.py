@@ -163,6 +163,16 @@ class Oracle:
                                         int(interpolation), ctypes.c_double(fx), ctypes.c_double(fy)), "resize_fxfy")
         return dst
 
+    def roi_filter(self, parent, rect, op, k, sigma=0.0, border=4, inplace=False):
+        """op on parent(rect) as a cv::Mat ROI (0 GaussianBlur, 1 blur, 2 sepFilter2D, 3 filter2D, 4 Sobel); only the real reference has it"""
+        parent = np.ascontiguousarray(parent)
+        ph, pw = parent.shape[:2]
+        rx, ry, rw, rh = rect
+        dst = np.empty((rh, rw) + parent.shape[2:], parent.dtype)
+        self._ok(self.fn("roi_filter")(_p(parent), sz(parent.strides[0]), pw, ph, cvtype(parent), rx, ry, rw, rh, _p(dst), sz(dst.strides[0]),
+                                       int(op), int(k), dbl(sigma), int(border), int(bool(inplace))), "roi_filter")
+        return dst
+
     def _warp(self, name, src, M, dsize, flags, borderMode, borderValue):
         src = np.ascontiguousarray(src)
         dw, dh = dsize

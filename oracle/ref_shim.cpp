@@ -199,6 +199,33 @@ API int ref_box_filter(const void* src, size_t sstep, int w, int h, int stype, v
     GUARD_END
 }
 
+// Filters on a ROI of a larger Mat (row a5: FilterEngine's wholeSize / ofs; the HAL sees margins / offsets): op 0 GaussianBlur(k, sigma),
+// 1 blur(k), 2 sepFilter2D with getGaussianKernel(k, sigma) as CV_32F taps, 3 filter2D with a normalised k x k ramp, 4 Sobel(1, 0, k) (same depth).
+// inplace != 0: the destination IS the ROI (then copied out), the case cv::filter2D / boxFilter allow.
+API int ref_roi_filter(const void* parent, size_t pstep, int pw, int ph, int type, int rx, int ry, int rw, int rh, void* dst, size_t dstep,
+                       int op, int k, double sigma, int border, int inplace)
+{
+    GUARD_BEGIN
+    Mat par = hdr(parent, pstep, pw, ph, type).clone();
+    Mat roi = par(Rect(rx, ry, rw, rh));
+    Mat out = hdr(dst, dstep, rw, rh, type);
+    Mat d = inplace ? roi : out;
+    if (op == 0) GaussianBlur(roi, d, Size(k, k), sigma, sigma, border);
+    else if (op == 1) blur(roi, d, Size(k, k), Point(-1, -1), border);
+    else if (op == 2) { Mat kx = getGaussianKernel(k, sigma, CV_32F); sepFilter2D(roi, d, -1, kx, kx, Point(-1, -1), 0, border); }
+    else if (op == 3) {
+        Mat ker(k, k, CV_32F);
+        float sum = 0;
+        for (int i = 0; i < k * k; i++) { ker.at<float>(i / k, i % k) = (float)(1 + (i * 7) % 5); sum += ker.at<float>(i / k, i % k); }
+        ker /= sum;
+        filter2D(roi, d, -1, ker, Point(-1, -1), 0, border);
+    } else if (op == 4) Sobel(roi, d, -1, 1, 0, k, 1, 0, border);
+    else return -2;
+    if (inplace) roi.copyTo(out);
+    CV_Assert(out.data == (uchar*)dst);
+    GUARD_END
+}
+
 API int ref_invert_affine(const double* M, double* iM)
 {
     GUARD_BEGIN

@@ -40,7 +40,7 @@ def test_match_template_u8(cvb, oracle, rng, method, isz, tsz):
     assert_close(got, want, atol=1e-3 * scale, what="matchTemplate u8 method=%d %s %s" % (method, isz, tsz))
 
 
-@pytest.mark.parametrize("tsz", [(64, 64), (7, 13), (1, 3), (33, 2), (19, 130)])
+@pytest.mark.parametrize("tsz", [(64, 64), (7, 13), (1, 3), (33, 2), (19, 130), (20, 32), (5, 16), (9, 128)])
 def test_match_template_fused_window_sums(cvb, rng, monkeypatch, tsz):
     """8-bit images: the fused window-sum + normalisation kernel (exact u32 sums, one pass) against the first version (f64 planes of
     sliding sums): the same exact integers enter the same f64 formula, so the results must be IDENTICAL -- all six methods, ragged sizes,

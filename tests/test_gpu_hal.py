@@ -24,10 +24,25 @@ def test_hal_signatures(cvb, oracle, rng):
                                    ctypes.c_double(0), ctypes.c_double(0), 4)
     assert rc == 0
     assert_exact(dst, oracle.GaussianBlur(img, (5, 5), 0), "hal gaussianBlur")
-    # a ROI (non-zero margins) must be declined so OpenCV falls back to its own code
-    rc = L.b200cv_hal_gaussianBlur(p(img), sz(img.strides[0]), p(dst), sz(dst.strides[0]), 161, 120, 0, 3, sz(1), sz(0), sz(0), sz(0), sz(5), sz(5),
+    # a ROI of a larger Mat (non-zero margins): the pixels around it are real and must be used -- equal to blurring the parent and cropping
+    par = rand_u8(rng, 140, 181, 3)
+    roi = par[7:7 + 120, 9:9 + 161]
+    out = np.empty((120, 161, 3), np.uint8)
+    rc = L.b200cv_hal_gaussianBlur(p(roi), sz(par.strides[0]), p(out), sz(out.strides[0]), 161, 120, 0, 3, sz(9), sz(7), sz(181 - 161 - 9), sz(140 - 120 - 7),
+                                   sz(7), sz(7), ctypes.c_double(0), ctypes.c_double(0), 4)
+    assert rc == 0
+    assert_exact(out, oracle.GaussianBlur(par, (7, 7), 0)[7:127, 9:170], "hal gaussianBlur on a ROI with context")
+    # ... unless the border is BORDER_ISOLATED: then the ROI is the image
+    rc = L.b200cv_hal_gaussianBlur(p(roi), sz(par.strides[0]), p(out), sz(out.strides[0]), 161, 120, 0, 3, sz(9), sz(7), sz(11), sz(13),
+                                   sz(7), sz(7), ctypes.c_double(0), ctypes.c_double(0), 4 | 16)
+    assert rc == 0
+    assert_exact(out, oracle.GaussianBlur(np.ascontiguousarray(roi), (7, 7), 0), "hal gaussianBlur, BORDER_ISOLATED")
+    # in place
+    tmp = img.copy()
+    rc = L.b200cv_hal_gaussianBlur(p(tmp), sz(tmp.strides[0]), p(tmp), sz(tmp.strides[0]), 161, 120, 0, 3, sz(0), sz(0), sz(0), sz(0), sz(5), sz(5),
                                    ctypes.c_double(0), ctypes.c_double(0), 4)
-    assert rc == 1
+    assert rc == 0
+    assert_exact(tmp, oracle.GaussianBlur(img, (5, 5), 0), "hal gaussianBlur in place")
     gray = np.empty((120, 161), np.uint8)
     assert L.b200cv_hal_cvtBGRtoGray(p(img), sz(img.strides[0]), p(gray), sz(gray.strides[0]), 161, 120, 0, 3, ctypes.c_bool(False)) == 0
     assert_exact(gray, oracle.cvtColor(img, C.COLOR_BGR2GRAY, 1), "hal cvtBGRtoGray")
@@ -112,6 +127,34 @@ def test_opencv_built_with_b200_hal(cvb, ref, rng):
     # cornerHarris has no HAL hook of its own but its Sobel calls go through the seam
     a = ref.cornerHarris(g, 2, 3, 0.04)
     assert_close(hal.cornerHarris(g, 2, 3, 0.04), a, atol=3e-6 * float(np.abs(a).max()), what="cv::cornerHarris (Sobel via HAL)")
+
+
+@pytest.mark.parametrize("inplace", [False, True])
+def test_opencv_hal_roi_with_context(cvb, ref, rng, inplace):
+    """Row a5 of the scope table (FilterEngine's wholeSize / ofs): a cv::Mat that is a ROI of a larger Mat, filtered by the UNMODIFIED reference
+    built with the B200 HAL, must equal the stock reference -- the border rule applies at the PARENT's edges, the pixels around the ROI are real --
+    and the call must have reached the device (launch counter).  ROIs in a corner (margins clipped by the parent), in the middle, flush with
+    one side; 8-bit and float; in place."""
+    from oracle.api import Oracle, available
+    if not available("ref_hal"):
+        pytest.skip("libocvref_hal.so not built (python oracle/build_ref.py --hal)")
+    hal = Oracle("ref_hal")
+    par8 = rand_u8(rng, 200, 260, 3)
+    parf = (rng.random((200, 260)) * 255).astype(np.float32)
+    for rect in ((0, 0, 100, 80), (31, 17, 160, 120), (100, 2, 160, 190), (3, 120, 250, 80)):
+        for border in (4, 1, 0):
+            cases = [(par8, 0, 5, 0.0), (parf, 0, 9, 2.0), (par8, 1, 7, 0.0), (par8, 2, 7, 1.6), (parf, 2, 11, 2.2), (par8, 3, 5, 0.0), (parf, 3, 5, 0.0), (parf, 4, 3, 0.0)]
+            for par, op, k, sigma in cases:
+                n0 = cvb.launch_count()
+                got = hal.roi_filter(par, rect, op, k, sigma, border, inplace)
+                assert cvb.launch_count() > n0, "ROI op %d did not reach the B200 HAL (rect %s border %d)" % (op, rect, border)
+                want = ref.roi_filter(par, rect, op, k, sigma, border, inplace)
+                what = "cv:: op %d k=%d on ROI %s of a %s parent, border %d, inplace %s" % (op, k, rect, par.dtype, border, inplace)
+                if par.dtype == np.uint8:     # bit-exact in the reference's vector body; its scalar remainder columns (width mod 32) may round the other way
+                    assert_close(got, want, atol=1, what=what)
+                    assert (got != want).mean() < 5e-3, what + ": %d bytes differ" % int((got != want).sum())
+                else:
+                    assert_close(got, want, atol=1e-3, rtol=1e-5, what=what)
 
 
 def test_cpp_host_mirror(cvb):
