@@ -167,3 +167,27 @@ def test_sift_pyramid_batch_1080p(cvb, ref, rng):
             else:
                 assert_close(gg[o][5], wg[o][5], atol=1e-4, what="frame %d gauss o=%d" % (f, o))
                 assert_close(gd[o][4], wd[o][4], atol=1e-4, what="frame %d dog o=%d" % (f, o))
+
+
+def test_sift_pyramid_4k(cvb, ref, rng):
+    """BASELINE config C5 frame size: the whole Gaussian + DoG pyramid of one 3840x2160 8UC1 frame against the reference's
+    buildGaussianPyramid / buildDoGPyramid (sift.dispatch.cpp:176-310).  7680 ... 120 wide octaves (W % 8 == 0): bit for bit, all levels."""
+    from oracle.api import unpack_pyramid
+    img = smooth_img(rng, 2160, 3840)
+    wg, wd = ref.sift_pyramid(img, 3, 1.6, True)
+    G, D, dims = cvb.sift_pyramid(gpu(img), 3, 1.6, True)
+    gg, gd = unpack_pyramid(cpu(G)[0], cpu(D)[0], dims.reshape(-1), len(dims), 3)
+    assert len(dims) == len(wg)
+    exact = True
+    for o in range(len(dims)):
+        exact = exact and wg[o][0].shape[1] % 8 == 0
+        for i in range(6):
+            if exact:
+                assert_exact(gg[o][i], wg[o][i], "4K gauss o=%d i=%d" % (o, i))
+            else:
+                assert_close(gg[o][i], wg[o][i], atol=1e-4, what="4K gauss o=%d i=%d" % (o, i))
+        for i in range(5):
+            if exact:
+                assert_exact(gd[o][i], wd[o][i], "4K dog o=%d i=%d" % (o, i))
+            else:
+                assert_close(gd[o][i], wd[o][i], atol=1e-4, what="4K dog o=%d i=%d" % (o, i))

@@ -83,3 +83,18 @@ def test_sift_detect_and_compute(cvb, ref, rng, size):
     if size[0] <= 480:
         res = cvb.sift_detectAndCompute(gpu(np.stack([img, img[::-1].copy()])[..., None]))
         assert len(res) == 2 and np.array_equal(res[0][0], kg) and np.array_equal(res[0][2], dg)
+
+
+def test_sift_detect_4k(cvb, ref, rng):
+    """BASELINE config C5 frame size: detectAndCompute on one 3840x2160 8UC1 frame against cv::SIFT (sift.dispatch.cpp:176-310, 405-472)"""
+    img = structured(rng, 2160, 3840)
+    kr, octr, dr = ref.sift_detect_and_compute(img)
+    kg, octg, dg = cvb.sift_detectAndCompute(gpu(img))
+    assert abs(len(kg) - len(kr)) <= max(5, len(kr) // 50), "keypoint count %d vs %d" % (len(kg), len(kr))
+    pairs = match(kr, kg, 1e-2, 0.1)
+    assert len(pairs) >= 0.97 * len(kr), "%d of %d reference keypoints matched" % (len(pairs), len(kr))
+    i, j = np.array(pairs).T
+    assert (octr[i] == octg[j]).mean() >= 0.99
+    diff = np.abs(dr[i] - dg[j])
+    assert (diff <= 1).mean() >= 0.99, "descriptor entries within +-1: %.4f" % (diff <= 1).mean()
+    assert np.all(np.diff(kg[:, 0]) >= 0)

@@ -3,7 +3,7 @@
 #   gpurun --timeout 900 -- 'bash tools/gpu_baseline.sh'
 mkdir -p gpurun_out
 nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
-timeout 600 python -m pytest tests -q -m gpu -x -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
+timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/gpu_tests.log 2>&1
 tail -5 gpurun_out/gpu_tests.log
 for w in c2 c3 c4 c5; do
   timeout 200 python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_$w.json 2> gpurun_out/bench_$w.err
