@@ -255,63 +255,13 @@ def make_extra(ops, rng, need_device):
     return extra
 
 
-def main():
-    # keep stdout clean for the ONE JSON line: libraries (e.g. the NCCL version banner) write to fd 1 -> send that to stderr
-    json_fd = os.dup(1)
-    os.dup2(2, 1)
-    sys.stdout = os.fdopen(json_fd, "w")
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="issue every launch from the host each step instead of replaying a captured CUDA graph")
-    ap.add_argument("--no-cpu", action="store_true")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    rng = np.random.default_rng(0x5EED0000 + 2 + rank)
-    ops, desc = build_ops(args.workload, rng)
-    W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-
-    # ---------------- reference arm: the reference's own CPU implementation on the host cores ----------------
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        orc, kind = reference_oracle()
-        extra = make_extra(ops, rng, False)
-        if orc.has("gaussian_kernel"):
-            for k in K_SWEEP:
-                extra["taps"][k] = orc.getGaussianKernel(k, 0).astype(np.float32)
-        cpu_frames(ops, rng)
-        if args.workload == "c4":
-            extra["templ_np"] = ops[0]["_cpu_src"][700:764, 1000:1064].copy()
-        cores = orc.num_threads() if orc.has("get_num_threads") else 1
-        for _ in range(args.warmup):
-            cpu_pass(orc, ops, extra)
-        t = 0.0; px = 0
-        for _ in range(args.steps):
-            dt, p = cpu_pass(orc, ops, extra)
-            t += dt; px += p
-        v = px / t / 1e6
-        print(json.dumps({"impl": "reference", "metric": "Mpix/s", "value": v, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32",
-                          "data": "synthetic", "config": {"workload": desc, "sample": "1 frame per op per step (bounded sample of the same op list)"},
-                          "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": "every op of the workload on one frame per step"},
-                          "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
-        return
-
-    # ---------------- our arm -------------------------------------------------------------------------------------
+def measure_device(workload, steps, W, use_graph, rank, world, local, rng, sample_clocks=True):
+    """device-resident pass of one workload: returns (result dict, ops, extra, bufs).  value = Mpix/s over `steps` steps (CUDA events, max over ranks)"""
     import torch
     import torch.distributed as dist
     import opencv_b200 as cvb
-    from opencv_b200 import hal
-    torch.cuda.set_device(local)
-    cvb.init(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    ops, desc = build_ops(workload, rng)
     extra = make_extra(ops, rng, True)
 
     # device-resident inputs / outputs: one buffer per distinct spec (every op's in+out working set > L2)
@@ -333,7 +283,7 @@ def main():
     for op in ops:
         op["_src"] = buf(op["src"], True)
         op["_dst"] = buf(op["dst"], False) if op["dst"] is not None else None
-    if args.workload == "c4":
+    if workload == "c4":
         extra["templ"] = ops[0]["_src"][0, 700:764, 1000:1064, 0].contiguous()
 
     # The one collective of the path: rank 0's filter taps / kernels / template, NCCL broadcast once per step (= per batch).
@@ -400,7 +350,7 @@ def main():
     # (goodFeaturesToTrack returns host data) cannot be captured: those workloads run eagerly.
     graph, graph_note = None, "eager launches"
     n_before = cvb.launch_count()
-    if not args.no_graph and not any(op["kind"] in ("gftt",) for op in ops):
+    if not (not use_graph) and not any(op["kind"] in ("gftt",) for op in ops):
         try:
             shared_operands()
             g = torch.cuda.CUDAGraph()
@@ -428,20 +378,22 @@ def main():
         step()
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if sample_clocks:
+        sampler.start()
     per_op_ms = np.zeros(len(ops))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     t_host0 = time.perf_counter()
-    for s in range(args.steps):
+    for s in range(steps):
         step()
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps
     e1.record()
     barrier()
     total_ms = e0.elapsed_time(e1)
     sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if sample_clocks:
+        sampler.join(timeout=2)
     # per-op times: eager steps with an event pair around every op (outside the timed region; the first pass re-warms the
     # stream-ordered allocator after the graph replays)
     shared_operands()
@@ -452,13 +404,13 @@ def main():
     barrier()
     for i in range(len(ops)):
         per_op_ms[i] = ev[i][0].elapsed_time(ev[i][1])
-    launches = launches_per_step * args.steps
+    launches = launches_per_step * steps
     if world > 1:
         t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     px_step_rank = sum(op["px"] * op["frames"] for op in ops)
-    value = px_step_rank * world * args.steps / (total_ms * 1e-3) / 1e6
+    value = px_step_rank * world * steps / (total_ms * 1e-3) / 1e6
     peak, peak_src = peaks()
     per_op = {}
     for op, ms in zip(ops, per_op_ms):
@@ -484,61 +436,179 @@ def main():
         roofline["fp32"] = {"achieved": round(tfl, 1), "peak": round(fp32_peak, 1), "unit": "TFLOP/s", "frac": round(tfl / fp32_peak, 3),
                             "note": "148 SM x 128 FMA lanes x 2 x 1.965 GHz; this op is FMA-issue bound (k*k MAC per pixel), its HBM fraction is not the limiter"}
 
-    # ---------------- e2e: the same ops through the host C ABI (pinned host memory, H2D+D2H in the timed region) --------------
-    e2e = None
-    if not args.no_e2e:
-        hops = [op for op in ops if op["kind"] not in ("gftt", "sift")]
-        hb = {}
-        # page-locked buffers are placed on the NUMA node of the allocating thread: run this section on the CPUs next to the GPU
-        # (what `numactl --cpunodebind` does for a production host process), and put the mask back afterwards
-        old_aff = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            old_aff = os.sched_getaffinity(0)
-            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
-        except Exception:                          # noqa: BLE001 -- affinity is an optimisation, never a requirement
-            old_aff = None
+    res = {"value": value, "total_ms": total_ms, "ms_per_step": total_ms / steps, "per_op": per_op, "roofline": roofline, "launches": int(launches),
+           "launches_per_step": int(launches_per_step), "graph_note": graph_note, "host_enqueue_ms": host_enqueue_ms, "clocks": sampler.summary() if sample_clocks else None, "desc": desc}
+    return res, ops, extra, bufs
 
-        def hbuf(spec, fill):
-            key = (spec[0], np.dtype(spec[1]).str, fill)
-            if key not in hb:
-                a = hal.pinned_empty(spec[0], spec[1])
-                if fill:
-                    a[...] = bufs[(spec[0], np.dtype(spec[1]).str, True)].cpu().numpy()
-                hb[key] = a
-            return hb[key]
+
+def measure_e2e(workload, ops, extra, bufs, steps, rank, world, local):
+    """the workload through the batch driver over HOST buffers (this rank's GPU): H2D + kernels + D2H inside the timed region (wall clock, max over ranks).
+    The batch driver (include/b200cv_batch.h): its worker thread runs on the CPUs next to the GPU and first-touches the page-locked frame buffers
+    there (NUMA-local staging); frames flow through the 3-stream upload / kernel / download pipeline."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    from opencv_b200.batch import BatchDriver
+    drv = BatchDriver([local])
+    hb = {}
+
+    def hbuf(spec, fill, src_t=None):
+        key = (spec[0], np.dtype(spec[1]).str, fill)
+        if key not in hb:
+            a = drv.pinned_frames(spec[0], spec[1])
+            if fill:
+                t = bufs[(spec[0], np.dtype(spec[1]).str, True)] if src_t is None else src_t
+                a[...] = t.cpu().numpy()
+            hb[key] = a
+        return hb[key]
+    hextra = dict(extra)
+    if "templ" in extra:
+        hextra["templ"] = extra["templ"].cpu().numpy()
+    hsteps = max(1, min(steps, 3))
+    if workload == "c5":
+        # C5 end to end: host frames in, waves of pyramids + DoG kept on the device for the consumer of the wave (SURVEY 7.2: 1.9 GB per
+        # frame cannot come back over PCIe), Harris responses downloaded.  32 frames per rank per step; 1024 frames = 4 steps on 8 ranks.
+        nf = 32
+        sspec = ((nf, H4K, W4K, 1), np.uint8)
+        base = ops[0]["_src"]
+        hsrc = hbuf(sspec, True, torch.cat([torch.roll(base, shifts=(17 * i, 31 * i), dims=(1, 2)) for i in range(nf // base.shape[0])]))
+        hdst = hbuf(((nf, H4K, W4K, 1), np.float32), False)
+
+        def hstep():
+            drv.sift_harris(hsrc, hdst, 3, 1.6, 1, 2, 3, 0.04, wave=4)
+        hpx = 2 * nf * W4K * H4K
+        h2d, d2h, nops = hsrc.nbytes, hdst.nbytes, 2
+        api = "b200cv_batch_sift_harris (include/b200cv_batch.h): %d host frames per rank per step in waves of 4, Harris responses downloaded, pyramids kept for the wave" % nf
+    else:
+        hops = [op for op in ops if op["kind"] not in ("gftt", "sift")]
         for op in hops:
             op["_hsrc"] = hbuf(op["src"], True); op["_hdst"] = hbuf(op["dst"], False)
-        hextra = dict(extra)
-        if "templ" in extra:
-            hextra["templ"] = extra["templ"].cpu().numpy()
 
         def hstep():
             for op in hops:
-                run_op(hal, op, op["_hsrc"], op["_hdst"], hextra)
-        hsteps = max(1, min(args.steps, 3))
-        hstep()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(hsteps):
-            hstep()
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        if old_aff is not None:
-            try:
-                os.sched_setaffinity(0, old_aff)
-            except OSError:
-                pass
+                run_op(drv, op, op["_hsrc"], op["_hdst"], hextra)
         hpx = sum(op["px"] * op["frames"] for op in hops)
-        e2e = {"value": hpx * world * hsteps / dt / 1e6, "unit": "Mpix/s",
-               "h2d_bytes_per_step": int(sum(op["_hsrc"].nbytes for op in hops)), "d2h_bytes_per_step": int(sum(op["_hdst"].nbytes for op in hops)),
-               "steps": hsteps, "api": "b200cv_host_* (include/b200cv_hal.h) over page-locked cv::Mat-layout buffers, 3-stream upload/kernel/download pipeline",
-               "ops": len(hops)}
+        h2d = int(sum(op["_hsrc"].nbytes for op in hops)); d2h = int(sum(op["_hdst"].nbytes for op in hops)); nops = len(hops)
+        api = "b200cv_batch_* (include/b200cv_batch.h) over page-locked cv::Mat-layout buffers: per-device worker thread, NUMA-local staging, 3-stream upload/kernel/download pipeline"
+    hstep()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(hsteps):
+        hstep()
+    barrier()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": hpx * world * hsteps / dt / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "h2d_gbs_per_rank": round(h2d * hsteps / dt / 1e9, 2), "d2h_gbs_per_rank": round(d2h * hsteps / dt / 1e9, 2),
+           "steps": hsteps, "api": api, "ops": nops}
+    hb.clear()
+    drv.close()
+
+    return e2e
+
+
+def main():
+    # keep stdout clean for the ONE JSON line: libraries (e.g. the NCCL version banner) write to fd 1 -> send that to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w")
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue every launch from the host each step instead of replaying a captured CUDA graph")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short C3/C4/C5 passes that ride along with the default (C2) workload")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    rng = np.random.default_rng(0x5EED0000 + 2 + rank)
+    ops, desc = build_ops(args.workload, rng)
+    W = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    # ---------------- reference arm: the reference's own CPU implementation on the host cores ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        orc, kind = reference_oracle()
+        extra = make_extra(ops, rng, False)
+        if orc.has("gaussian_kernel"):
+            for k in K_SWEEP:
+                extra["taps"][k] = orc.getGaussianKernel(k, 0).astype(np.float32)
+        cpu_frames(ops, rng)
+        if args.workload == "c4":
+            extra["templ_np"] = ops[0]["_cpu_src"][700:764, 1000:1064].copy()
+        cores = orc.num_threads() if orc.has("get_num_threads") else 1
+        for _ in range(args.warmup):
+            cpu_pass(orc, ops, extra)
+        t = 0.0; px = 0
+        for _ in range(args.steps):
+            dt, p = cpu_pass(orc, ops, extra)
+            t += dt; px += p
+        v = px / t / 1e6
+        print(json.dumps({"impl": "reference", "metric": "Mpix/s", "value": v, "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/f32",
+                          "data": "synthetic", "config": {"workload": desc, "sample": "1 frame per op per step (bounded sample of the same op list)"},
+                          "cpu_baseline": {"value": v, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": "every op of the workload on one frame per step"},
+                          "e2e": {"value": v, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ---------------- our arm -------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    import opencv_b200 as cvb
+    from opencv_b200 import hal
+    torch.cuda.set_device(local)
+    cvb.init(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    res, ops, extra, bufs = measure_device(args.workload, args.steps, W, not args.no_graph, rank, world, local, rng)
+    value, total_ms, per_op, roofline, launches = res["value"], res["total_ms"], res["per_op"], res["roofline"], res["launches"]
+    graph_note, host_enqueue_ms, desc = res["graph_note"], res["host_enqueue_ms"], res["desc"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- e2e: the same ops through the host C ABI (pinned host memory, H2D+D2H in the timed region) --------------
+    e2e = None if args.no_e2e else measure_e2e(args.workload, ops, extra, bufs, args.steps, rank, world, local)
+
+    # ---------------- the other BASELINE configs (C3, C4, C5) measured in the same run: short device-resident passes with per-op tables --------
+    extra_workloads = None
+    if args.workload == "c2" and not args.no_extra:
+        for op in ops:                                  # release the main workload's device and pinned buffers first
+            for k in ("_src", "_dst", "_hsrc", "_hdst"):
+                op.pop(k, None)
+        bufs.clear()
+        torch.cuda.empty_cache()
+        extra_workloads = {}
+        for w in ("c3", "c4", "c5"):
+            try:
+                r, o2, x2, b2 = measure_device(w, max(1, min(args.steps, 3)), 3, not args.no_graph, rank, world, local, np.random.default_rng(0x5EED0000 + ord(w[1]) + rank), sample_clocks=False)
+                extra_workloads[w] = {"workload": r["desc"], "value": r["value"], "unit": "Mpix/s", "ms_per_step": r["ms_per_step"], "launch": r["graph_note"],
+                                      "gpu_launches_per_step": r["launches_per_step"], "per_op": r["per_op"]}
+                if not args.no_e2e:
+                    extra_workloads[w]["e2e"] = measure_e2e(w, o2, x2, b2, 2, rank, world, local)
+                for op in o2:
+                    for k in ("_src", "_dst", "_hsrc", "_hdst"):
+                        op.pop(k, None)
+                b2.clear(); x2.clear(); del o2, b2, x2
+                torch.cuda.empty_cache()
+            except Exception as exc:                    # noqa: BLE001 -- an extra table must never take the headline line down with it
+                extra_workloads[w] = {"error": repr(exc)[:300]}
+                torch.cuda.synchronize()
 
     # ---------------- cpu baseline: the reference's own CPU path on this box's host cores (rank 0, N == 1) ----------------
     cpu = None
@@ -563,11 +633,13 @@ def main():
                "data": "synthetic", "config": {"workload": desc, "l2": "every op streams a batch whose input+output exceed the 126 MB L2",
                                                 "parallelism": "frames sharded across %d rank(s); NCCL broadcast of taps/kernels per step" % world,
                                                 "launch": graph_note, "host_enqueue_ms_per_step": round(host_enqueue_ms, 3)},
-               "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "per_op": per_op}
+               "gpu_launches": int(launches), "clocks": res["clocks"], "roofline": roofline, "per_op": per_op}
         if e2e:
             out["e2e"] = e2e
         if cpu:
             out["cpu_baseline"] = cpu
+        if extra_workloads:
+            out["config"]["extra_workloads"] = extra_workloads
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

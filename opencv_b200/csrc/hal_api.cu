@@ -160,6 +160,12 @@ static bool taps_to_float(const uchar* data, size_t step, int type, int w, int h
     return true;
 }
 
+// matchTemplate over host frames with the template ALREADY on the device (batch.cu: the template arrives by ncclBroadcast)
+int host_match_template_dev(const b200cvMat* image, const b200cvMat* dtempl, const b200cvMat* result, int method)
+{
+    return host_pipeline(image, result, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_match_template(a, dtempl, b, method, st); });
+}
+
 }  // namespace b200cv
 
 using namespace b200cv;

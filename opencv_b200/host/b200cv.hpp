@@ -7,9 +7,13 @@
 //   b200cv::GaussianBlur, sepFilter2D, filter2D, Sobel, resize, warpAffine, warpPerspective, cvtColor, matchTemplate, cornerHarris,
 //   cornerMinEigenVal, goodFeaturesToTrack      same argument order and meaning as imgproc.hpp:1544,1723,1702,1862,2422,2450,2482,3736,
 //                                               3916,1948,1921,2096, with a trailing Stream& like the cv::cuda:: functions
-// With -DB200CV_WITH_OPENCV (OpenCV headers on the include path) the same names also accept cv::Mat (host path, b200cv_host_*).
+// With -DB200CV_WITH_OPENCV (OpenCV headers on the include path) b200cv_opencv.hpp adds namespace b200cv::cuda: the same operations over
+// cv::InputArray / cv::OutputArray (cv::Mat, cv::cuda::GpuMat, cv::cuda::HostMem) with cv::cuda's Filter / Stream& shapes.
 // Errors: the C ABI status is turned into b200cv::Error (std::runtime_error); NOT_IMPLEMENTED is b200cv::NotImplemented.
 #pragma once
+#ifdef B200CV_WITH_OPENCV
+#include <opencv2/core.hpp>
+#endif
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -33,7 +37,9 @@ struct Point { int x = -1, y = -1; Point() {} Point(int x_, int y_) : x(x_), y(y
 struct Point2f { float x, y; };
 struct Scalar { double val[4] = {0, 0, 0, 0}; Scalar() {} Scalar(double a, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; } };
 
+#ifndef CV_8U      // OpenCV's own depth macros when its headers came first (B200CV_WITH_OPENCV)
 enum { CV_8U = 0, CV_16S = 3, CV_32F = 5 };
+#endif
 inline int makeType(int depth, int cn) { return B200CV_MAKETYPE(depth, cn); }
 enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_WRAP = 3, BORDER_REFLECT_101 = 4, BORDER_DEFAULT = 4 };
 enum { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2, INTER_AREA = 3, INTER_LANCZOS4 = 4, INTER_LINEAR_EXACT = 5, INTER_NEAREST_EXACT = 6, WARP_INVERSE_MAP = 16 };
@@ -234,19 +240,10 @@ inline FilterPtr createSobelFilter(int srcType, int dstType, int dx, int dy, int
     auto f = std::make_shared<F>(); f->dd = B200CV_DEPTH(dstType); f->dx = dx; f->dy = dy; f->ks = ksize; f->sc = scale; f->b = rowBorderMode; return f;
 }
 
-#ifdef B200CV_WITH_OPENCV
-}  // namespace b200cv
-#include <opencv2/core.hpp>
-namespace b200cv {
-// cv::Mat (host memory) overloads: the synchronous host path (upload, kernel, download) -- same names, cv:: argument order
-inline b200cvMat hostDesc(const cv::Mat& m) { b200cvMat d = {m.data, m.step, m.cols, m.rows, m.type(), 1, 0}; return d; }
-inline void GaussianBlur(const cv::Mat& src, cv::Mat& dst, cv::Size ksize, double sigmaX, double sigmaY = 0, int borderType = cv::BORDER_DEFAULT)
-{ dst.create(src.size(), src.type()); b200cvMat a = hostDesc(src), b = hostDesc(dst); check(b200cv_host_gaussian_blur(&a, &b, ksize.width, ksize.height, sigmaX, sigmaY, borderType), "GaussianBlur"); }
-inline void cvtColor(const cv::Mat& src, cv::Mat& dst, int code, int dcn = 0)
-{ int w, h, cn; cvtColorGeometry(code, src.cols, src.rows, dcn, w, h, cn);
-  dst.create(h, w, CV_MAKETYPE(src.depth(), cn)); b200cvMat a = hostDesc(src), b = hostDesc(dst); check(b200cv_host_cvt_color(&a, &b, code), "cvtColor"); }
-inline void resize(const cv::Mat& src, cv::Mat& dst, cv::Size dsize, double = 0, double = 0, int interpolation = cv::INTER_LINEAR)
-{ dst.create(dsize, src.type()); b200cvMat a = hostDesc(src), b = hostDesc(dst); check(b200cv_host_resize(&a, &b, interpolation), "resize"); }
-#endif
+
 
 }  // namespace b200cv
+
+#ifdef B200CV_WITH_OPENCV
+#include "b200cv_opencv.hpp"     // cv::InputArray / cv::OutputArray face (b200cv::cuda::*), DeviceMat, PinnedMat, DeviceAllocator
+#endif

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     names = []
-    for h in ("b200cv.h", "b200cv_hal.h"):
+    for h in ("b200cv.h", "b200cv_hal.h", "b200cv_batch.h"):
         txt = open(os.path.join(ROOT, "include", h)).read()
         txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
         names += re.findall(r"B200CV_API\s+[\w\s\*]+?\b(b200cv_\w+)\s*\(", txt)

@@ -38,3 +38,30 @@ def test_shard_and_broadcast_world2():
     for r in res:
         assert r[3] == list(map(float, range(31)))       # every rank holds rank 0's operand
         assert r[4] == [514, 513]
+
+
+def test_c_abi_shard_matches_python():
+    """b200cv_batch_shard (the batch driver's frame blocks, include/b200cv_batch.h) = shard_range: pure host arithmetic, no GPU"""
+    import ctypes
+    import opencv_b200 as cvb
+    from opencv_b200 import batch
+    L = cvb.lib()
+    f, c = ctypes.c_int(), ctypes.c_int()
+    for frames, n in ((10, 4), (1027, 2), (1024, 8), (3, 8), (0, 2), (1, 1)):
+        got = []
+        for i in range(n):
+            assert L.b200cv_batch_shard(frames, i, n, ctypes.byref(f), ctypes.byref(c)) == 0
+            got.append((f.value, f.value + c.value))
+        assert got == [batch.shard_range(frames, i, n) for i in range(n)]
+    assert L.b200cv_batch_shard(5, 2, 2, ctypes.byref(f), ctypes.byref(c)) == -2
+
+
+def test_batch_driver_refuses_without_gpu():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import opencv_b200 as cvb
+    from opencv_b200.batch import BatchDriver
+    with pytest.raises(cvb.B200cvError, match="no CPU fallback"):
+        BatchDriver()
