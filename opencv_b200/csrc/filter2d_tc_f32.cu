@@ -11,19 +11,25 @@
 //
 // Contraction = the Toeplitz form of filter2d_tc.cu / matchtemplate_tc.cu:
 //   D[m][j] = sum_v sum_k A_v[m][k] * B_v[k][j],   A_v[m][k] = P(y0 + m + v, x0 + k),   B_v[k][j] = K(v, k - j)   (0 outside 0 <= k-j < kw)
-// with P the border-extended image.  Tile = 256 rows x 16 columns (two M128 x N16 accumulators), K = kw + 15 rounded up to 16.
-// N = 16 keeps ALL Toeplitz operands (kh x 2 planes x K x 16 BF16 <= 99 KB) RESIDENT in shared memory next to two A stages, and wastes
-// the least MMA work on Toeplitz zeros (K / kw = 1.55 at 31 x 31).
+// with P the border-extended image.  Tile = 256 rows x 32 columns (two M128 accumulators), K = kw + 31 rounded up to 16.
 //
-// Roles (416 threads, one persistent CTA per SM):
-//   warp 0      producer: per tile the hi and lo strips (K columns x 256 + kh - 1 rows) by TMA in the K-major no-swizzle core-matrix
+// What bounds it (profiles/r02_prof_filter2d_tc_f32_before_ncu_full_summary.txt): the first version used N = 16 tiles and three N16 MMAs per
+// K step; the tensor pipe was active 20 % of the time while l1tex__data_pipe_tc_wavefronts_mem_shared sat at 90 % of peak -- every
+// tcgen05.mma re-reads its M128 x K16 BF16 A operand (4 KB = 32 cycles of shared-memory bandwidth) whatever N is, so an N16 MMA costs ~40
+// cycles for 8 cycles of math.  This version amortises the A reads: per K step TWO MMAs instead of three,
+//     D[:, 0:64)  += A_hi x [B_hi | B_lo]      (N = 64: the hi and lo Toeplitz planes side by side in N)
+//     D[:, 0:32)  += A_lo x  B_hi              (N = 32: the same operand, first half)
+// and the epilogue adds the two column groups.  Per output column and kernel row that is ~11 cycles of operand traffic instead of ~25.
+// The Toeplitz operands no longer fit shared memory for 31 rows (8 KB per kernel row): they stream through a ring from L2 (16 B/clk/SM).
+//
+// Roles (384 threads, one persistent CTA per SM):
+//   warp 0      A producer: per tile the hi and lo strips (K columns x 256 + kh - 1 rows) by TMA in the K-major no-swizzle core-matrix
 //               layout (one 16-byte-wide box column per 8 K elements), ring of 2 stages
-//   warps 1-4   MMA issuers, two per M-tile (even / odd kernel rows, each into its own accumulator): kh/2 x K/16 x 3 tcgen05.mma
-//               (M128 x N16 x K16, 8 tensor-pipe cycles each) per tile; a kernel row's A operand is the same strip with the descriptor
-//               start address advanced by one 16-byte row.  One thread issues an MMA every ~25 cycles at best (the first version, one
-//               issuer per M-tile rebuilding four 64-bit descriptors per step, managed one per 55-80 cycles and ran SLOWER than the FP32
-//               kernel): descriptors are now a 32-bit add on the low word, the K loop is unrolled by template, four threads issue
-//   warps 5-12  epilogue: tcgen05.ld of the other accumulator stage (both issuers' partial sums), + delta, 64-byte row stores
+//   warp 1      B producer: one kernel row of Toeplitz operands (8 KB) per cp.async.bulk into a ring of 4, in the order the issuers use them
+//   warps 2-3   MMA issuers, one per M-tile: kh x K/16 x 2 tcgen05.mma per tile; a kernel row's A operand is the same strip with the
+//               descriptor start address advanced by one 16-byte row; descriptors are a 32-bit add on the low word, the K loop is unrolled
+//               by template, the warp runs the loops uniformly and an elected lane issues; tcgen05.commit frees the B stage per kernel row
+//   warps 4-11  epilogue: tcgen05.ld of the other accumulator stage (64 columns), group 0 + group 1 + delta, 128-byte row stores
 // The border-extended BF16 planes are written once per call by pad_split_kernel (reads 4 B, writes 4 B per pixel).
 #include <algorithm>
 #include <cmath>
@@ -35,12 +41,12 @@
 
 namespace b200cv {
 
-constexpr int FF_N = 16;                      // output columns per tile = MMA N
+constexpr int FF_N = 32;                      // output columns per tile; the MMAs are N = 64 (hi | lo Toeplitz planes) and N = 32 (hi)
 constexpr int FF_MT = 2;                      // M-tiles (128 rows) per tile
-constexpr int FF_NI = 2;                      // MMA issuer warps per M-tile (kernel rows v = t, t + 2, ...)
-constexpr int FF_THREADS = 32 * (1 + FF_MT * FF_NI + 8);   // producer, 4 issuers, 8 epilogue warps
+constexpr int FF_THREADS = 32 * (2 + FF_MT + 8);   // A producer, B producer, 2 issuers, 8 epilogue warps
 constexpr int FF_SMEM_MAX = 227 * 1024 - 1024;
 constexpr int FF_NA = 2;                      // A stages
+constexpr int FF_NB = 4;                      // B stages (kernel rows in flight)
 
 struct FFTaps { float k[33 * 33]; };
 
@@ -51,19 +57,20 @@ struct FFParams {
     float delta;
 };
 
-// B in global/shared memory: [kernel row v][plane (hi, lo)][chunk c][column j (16)][8 bf16]: element e = plane(K(v, 8c + e - j))
+// B in global/shared memory: [kernel row v][chunk c][column n (64: 0..31 hi plane, 32..63 lo plane)][8 bf16]: element e of column j = n & 31
+// = plane(K(v, 8c + e - j)): K-major core matrices of 8 columns x 16 bytes, 128 bytes apart in N, 1024 bytes apart in K
 __global__ void ff_toeplitz_kernel(const __grid_constant__ FFTaps kp, int kw, int kch, __nv_bfloat16* out)
 {
     const int v = blockIdx.x;
-    const int per_plane = kch * FF_N * 8;
-    for (int idx = threadIdx.x; idx < 2 * per_plane; idx += blockDim.x) {
-        const int pl = idx / per_plane, r = idx - pl * per_plane;
-        const int e = r & 7, j = (r >> 3) % FF_N, c = (r >> 3) / FF_N;
+    const int per_row = kch * 2 * FF_N * 8;
+    for (int idx = threadIdx.x; idx < per_row; idx += blockDim.x) {
+        const int e = idx & 7, n = (idx >> 3) % (2 * FF_N), c = (idx >> 3) / (2 * FF_N);
+        const int pl = n / FF_N, j = n % FF_N;
         const int u = 8 * c + e - j;
         const float t = (u >= 0 && u < kw) ? kp.k[v * kw + u] : 0.f;
         const __nv_bfloat16 hi = __float2bfloat16_rn(t);
         const __nv_bfloat16 lo = __float2bfloat16_rn(t - __bfloat162float(hi));
-        out[(size_t)v * 2 * per_plane + idx] = pl ? lo : hi;
+        out[(size_t)v * per_row + idx] = pl ? lo : hi;
     }
 }
 
@@ -140,32 +147,41 @@ __device__ __forceinline__ void ff_tmem_ld16(uint32_t taddr, uint32_t* r)
         : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void ff_tmem_ld32(uint32_t taddr, uint32_t* r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+          "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
 template <int KS>      // K / 16: MMA steps per kernel row
 __global__ void __launch_bounds__(FF_THREADS, 1) filter2d_tc_f32_kernel(const __grid_constant__ CUtensorMap tmap, const unsigned char* __restrict__ bglob,
                                                                         Img dst, const __grid_constant__ FFParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int KCH = 2 * KS;
-    constexpr uint32_t brow = 2u * KCH * FF_N * 16;                          // bytes of B per kernel row (both planes)
-    constexpr uint32_t bplane = (uint32_t)KCH * FF_N * 16;
+    constexpr uint32_t brow = (uint32_t)KCH * 2 * FF_N * 16;                 // bytes of B per kernel row (hi | lo side by side in N)
     const uint32_t lbo_a = (uint32_t)p.ra_alloc * 16u;                       // one 16-byte-wide column of the strip
     const uint32_t aplane = (uint32_t)KCH * lbo_a;
     const uint32_t abytes = 2 * aplane;                                      // one A stage (hi + lo)
-    unsigned char* sB = smem;                                                // kh x brow, resident
-    unsigned char* sA = smem + (size_t)p.kh * brow;                          // FF_NA stages
-    __shared__ __align__(8) uint64_t b_full, a_full[FF_NA], a_empty[FF_NA], acc_full[2][FF_MT], acc_empty[2][FF_MT];
+    unsigned char* sB = smem;                                                // FF_NB stages of one kernel row
+    unsigned char* sA = smem + (size_t)FF_NB * brow;                         // FF_NA stages
+    __shared__ __align__(8) uint64_t b_full[FF_NB], b_empty[FF_NB], a_full[FF_NA], a_empty[FF_NA], acc_full[2][FF_MT], acc_empty[2][FF_MT];
     __shared__ uint32_t s_tmem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int TM_COLS = 2 * FF_MT * FF_NI * FF_N;                        // 2 stages x M-tiles x issuers x 16 columns = 128
+    constexpr int TM_COLS = 2 * FF_MT * 2 * FF_N;                            // 2 stages x M-tiles x 64 columns = 256
 
     if (threadIdx.x == 0) {
-        mbar_init(&b_full, 1);
-        for (int s = 0; s < FF_NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], FF_MT * FF_NI); }
+        for (int s = 0; s < FF_NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], FF_MT); }
+        for (int s = 0; s < FF_NA; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], FF_MT); }
         for (int s = 0; s < 2; s++)
-            for (int m = 0; m < FF_MT; m++) { mbar_init(&acc_full[s][m], FF_NI); mbar_init(&acc_empty[s][m], 4); }
+            for (int m = 0; m < FF_MT; m++) { mbar_init(&acc_full[s][m], 1); mbar_init(&acc_empty[s][m], 4); }
         fence_barrier_init();
     }
-    if (warp == 1) {
+    if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(TM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -176,9 +192,7 @@ __global__ void __launch_bounds__(FF_THREADS, 1) filter2d_tc_f32_kernel(const __
 
     if (warp == 0) {
         if (lane == 0) {
-            // ---- producer: all of B once, then the hi + lo strips of every tile ----
-            mbar_arrive_expect_tx(&b_full, (uint32_t)p.kh * brow);
-            for (int v = 0; v < p.kh; v++) ff_bulk_load(sB + (size_t)v * brow, bglob + (size_t)v * brow, brow, &b_full);
+            // ---- A producer: the hi + lo strips of every tile ----
             int i = 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
                 const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, f = t / (p.tiles_x * p.tiles_y);
@@ -193,54 +207,66 @@ __global__ void __launch_bounds__(FF_THREADS, 1) filter2d_tc_f32_kernel(const __
                                         ty * (128 * FF_MT) + b * p.box_h, f + pl * p.frames, &a_full[buf]);
             }
         }
-    } else if (warp <= FF_MT * FF_NI) {
-        // ---- MMA issuer (mt, ti): kernel rows ti, ti + FF_NI, ... of M-tile mt into accumulator (acc, mt, ti).  The whole warp runs the loops
-        //      (uniform values), one elected lane issues ----
-        const int wu = __shfl_sync(0xffffffffu, warp, 0);
-        const int mt = (wu - 1) % FF_MT, ti = (wu - 1) / FF_MT;
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- B producer: kernel row after kernel row, tile after tile, in the issuers' order ----
+            int g = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x)
+                for (int v = 0; v < p.kh; v++, g++) {
+                    const int s = g % FF_NB;
+                    mbar_wait(&b_empty[s], ((g / FF_NB) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&b_full[s], brow);
+                    ff_bulk_load(sB + (size_t)s * brow, bglob + (size_t)v * brow, brow, &b_full[s]);
+                }
+        }
+    } else if (warp < 2 + FF_MT) {
+        // ---- MMA issuer of M-tile mt.  The whole warp runs the loops (uniform values), one elected lane issues ----
+        const int mt = __shfl_sync(0xffffffffu, warp, 0) - 2;
         // instruction descriptor: D = F32 (1 << 4), A = B = BF16 (1 at [7,10) and [10,13)), K-major both, N >> 3 at [17,23), M >> 4 at [24,29)
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FF_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t idesc64 = idesc_base | ((uint32_t)((2 * FF_N) >> 3) << 17), idesc32 = idesc_base | ((uint32_t)(FF_N >> 3) << 17);
         // shared-memory descriptors (K-major, no swizzle): low word = start >> 4 [0,14) | LBO >> 4 [16,30); high word = SBO >> 4 [0,14) | version 1 at bit 14.
         // Everything that changes from MMA to MMA is the start address: a 32-bit add on the low word.
         const uint32_t hi = (128u >> 4) | (1u << 14);
-        const uint32_t a_lbo = (lbo_a >> 4) << 16, b_lbo = ((uint32_t)(FF_N * 16) >> 4) << 16;
+        const uint32_t a_lbo = (lbo_a >> 4) << 16, b_lbo = ((uint32_t)(2 * FF_N * 16) >> 4) << 16;
         const uint32_t a_ks = (2u * lbo_a) >> 4, a_pl = aplane >> 4;                // per K step / hi -> lo plane
-        constexpr uint32_t b_ks = (2u * FF_N * 16) >> 4, b_pl = bplane >> 4, b_row = brow >> 4;
-        mbar_wait(&b_full, 0);
-        const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | b_lbo;
-        int i = 0;
+        constexpr uint32_t b_ks = (2u * 2 * FF_N * 16) >> 4;
+        const uint32_t b_base = (smem_u32(sB) & 0x3FFFFu) >> 4;
+        int i = 0, g = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
             const int buf = i % FF_NA, acc = i & 1;
             mbar_wait(&a_full[buf], (i / FF_NA) & 1);
             mbar_wait(&acc_empty[acc][mt], ((i >> 1) & 1) ^ 1);
             ff_fence_after();
-            const uint32_t d_addr = tmem + (uint32_t)((acc * FF_MT + mt) * FF_NI + ti) * FF_N;
-            uint32_t a_lo = (((smem_u32(sA + (size_t)buf * abytes) + (uint32_t)(mt * 128) * 16u) & 0x3FFFFu) >> 4 | a_lbo) + (uint32_t)ti;   // + v rows
-            uint32_t b_lo = b_lo0 + (uint32_t)ti * b_row;
-            uint32_t first = 0;
+            const uint32_t d_addr = tmem + (uint32_t)(acc * FF_MT + mt) * (2 * FF_N);
+            uint32_t a_lo = ((smem_u32(sA + (size_t)buf * abytes) + (uint32_t)(mt * 128) * 16u) & 0x3FFFFu) >> 4 | a_lbo;      // + v rows
 #pragma unroll 1
-            for (int v = ti; v < p.kh; v += FF_NI, a_lo += FF_NI, b_lo += FF_NI * b_row) {
+            for (int v = 0; v < p.kh; v++, g++, a_lo++) {
+                const int s = g % FF_NB;
+                mbar_wait(&b_full[s], (g / FF_NB) & 1);
+                ff_fence_after();
                 if (ff_elect_one()) {
+                    const uint32_t b_lo = (b_base + (uint32_t)s * (brow >> 4)) | b_lbo;
 #pragma unroll
                     for (int ks = 0; ks < KS; ks++) {
                         const uint64_t ah = ((uint64_t)hi << 32) | (a_lo + ks * a_ks), al = ((uint64_t)hi << 32) | (a_lo + ks * a_ks + a_pl);
-                        const uint64_t bh = ((uint64_t)hi << 32) | (b_lo + ks * b_ks), bl = ((uint64_t)hi << 32) | (b_lo + ks * b_ks + b_pl);
-                        ff_mma(d_addr, ah, bh, idesc, ks == 0 ? first : 1u);
-                        ff_mma(d_addr, ah, bl, idesc, 1u);
-                        ff_mma(d_addr, al, bh, idesc, 1u);
+                        const uint64_t bd = ((uint64_t)hi << 32) | (b_lo + ks * b_ks);
+                        ff_mma(d_addr, ah, bd, idesc64, (v == 0 && ks == 0) ? 0u : 1u);      // A_hi x [B_hi | B_lo] -> columns 0..63
+                        ff_mma(d_addr, al, bd, idesc32, 1u);                                  // A_lo x B_hi        -> columns 0..31
                     }
+                    ff_commit(&b_empty[s]);        // both issuers arrive: the B stage may be overwritten once their MMAs have read it
                 }
-                first = 1;
+                __syncwarp();
             }
             if (ff_elect_one()) {
-                ff_commit(&a_empty[buf]);          // all four issuers arrive: the strip may be overwritten once their MMAs have read it
+                ff_commit(&a_empty[buf]);          // both issuers arrive: the strip may be overwritten once their MMAs have read it
                 ff_commit(&acc_full[acc][mt]);
             }
             __syncwarp();
         }
     } else {
-        // ---- epilogue: warps 5..12; a warp may touch TMEM lanes 32 (warp % 4) .. +31 = accumulator rows; four warps per M-tile ----
-        const int quarter = warp & 3, mt = (warp - 1 - FF_MT * FF_NI) >> 2;
+        // ---- epilogue: warps 4..11; a warp may touch TMEM lanes 32 (warp % 4) .. +31 = accumulator rows; four warps per M-tile ----
+        const int quarter = warp & 3, mt = (warp - 2 - FF_MT) >> 2;
         int i = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, i++) {
             const int tx = t % p.tiles_x, ty = (t / p.tiles_x) % p.tiles_y, f = t / (p.tiles_x * p.tiles_y);
@@ -249,33 +275,37 @@ __global__ void __launch_bounds__(FF_THREADS, 1) filter2d_tc_f32_kernel(const __
             ff_fence_after();
             const int gx0 = tx * FF_N;
             const int gy = ty * (128 * FF_MT) + mt * 128 + quarter * 32 + lane;
-            uint32_t r0[16], r1[16];
-            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((acc * FF_MT + mt) * FF_NI) * FF_N;
-            ff_tmem_ld16(taddr, r0);
-            ff_tmem_ld16(taddr + FF_N, r1);
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * FF_MT + mt) * (2 * FF_N);
+            ff_tmem_ld32(taddr, r0);
+            ff_tmem_ld32(taddr + FF_N, r1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             ff_fence_before();
             __syncwarp();
             if (lane == 0) ff_mbar_arrive(&acc_empty[acc][mt]);       // 4 arrivals free the accumulators: the values are in registers
             if (gy < p.oh) {
                 float* dp = dst.row<float>(f, gy) + gx0;
-                float v[16];
-                // kernels with a single row leave the odd-row accumulator untouched (stale): it must not be added then
+                if (gx0 + FF_N <= p.ow && ((uintptr_t)dp & 15) == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; j++) v[j] = __fadd_rn(p.kh > 1 ? __fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j])) : __uint_as_float(r0[j]), p.delta);
-                if (gx0 + 16 <= p.ow && ((uintptr_t)dp & 15) == 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) ((float4*)dp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < FF_N / 4; j++) {
+                        float4 o;
+                        o.x = __fadd_rn(__fadd_rn(__uint_as_float(r0[4 * j]), __uint_as_float(r1[4 * j])), p.delta);
+                        o.y = __fadd_rn(__fadd_rn(__uint_as_float(r0[4 * j + 1]), __uint_as_float(r1[4 * j + 1])), p.delta);
+                        o.z = __fadd_rn(__fadd_rn(__uint_as_float(r0[4 * j + 2]), __uint_as_float(r1[4 * j + 2])), p.delta);
+                        o.w = __fadd_rn(__fadd_rn(__uint_as_float(r0[4 * j + 3]), __uint_as_float(r1[4 * j + 3])), p.delta);
+                        ((float4*)dp)[j] = o;
+                    }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; j++) if (gx0 + j < p.ow) dp[j] = v[j];
+                    for (int j = 0; j < FF_N; j++)
+                        if (gx0 + j < p.ow) dp[j] = __fadd_rn(__fadd_rn(__uint_as_float(r0[j]), __uint_as_float(r1[j])), p.delta);
                 }
             }
         }
     }
     ff_fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TM_COLS) : "memory");
 }
 
 // filter2D, float single-channel source and destination.
@@ -283,8 +313,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) filter2d_tc_f32_kernel(const __
 int filter2d_f32_tensor(const Img& s, const Img& d, const float* k, int kw, int kh, int ax, int ay, float delta, int border, cudaStream_t st)
 {
     if (kw > 33 || kh > 33 || s.frames >= 32768) return B200CV_NOT_IMPLEMENTED;
-    // the cost is ~0.05 ms per kernel ROW (8 4K frames) whatever the width: below 15 rows the direct FP32 sum is at least as fast
-    if (kh < 15 && !getenv("B200CV_FILTER2D_TC_MIN_TAPS")) return B200CV_NOT_IMPLEMENTED;
+    // the cost grows with the kernel ROWS whatever the width: below 13 rows the direct FP32 sum is at least as fast
+    if (kh < 13 && !getenv("B200CV_FILTER2D_TC_MIN_TAPS")) return B200CV_NOT_IMPLEMENTED;
     static thread_local FFTaps taps;
     for (int i = 0; i < kw * kh; i++) {
         if (!std::isfinite(k[i])) return B200CV_NOT_IMPLEMENTED;
@@ -293,7 +323,7 @@ int filter2d_f32_tensor(const Img& s, const Img& d, const float* k, int kw, int 
     FFParams p;
     memset(&p, 0, sizeof(p));
     p.kh = kh; p.ow = s.cols; p.oh = s.rows; p.frames = s.frames; p.delta = delta;
-    p.kch = 2 * (int)div_up((unsigned)(kw + FF_N - 1), 16);                 // K = kw + 15 rounded up to a multiple of 16 elements
+    p.kch = 2 * (int)div_up((unsigned)(kw + FF_N - 1), 16);                 // K = kw + 31 rounded up to a multiple of 16 elements
     p.tiles_x = (int)div_up((unsigned)p.ow, FF_N); p.tiles_y = (int)div_up((unsigned)p.oh, 128 * FF_MT);
     const long long nt = (long long)p.tiles_x * p.tiles_y * p.frames;
     if (nt > 0x7fffffff) return B200CV_NOT_IMPLEMENTED;
@@ -302,8 +332,8 @@ int filter2d_f32_tensor(const Img& s, const Img& d, const float* k, int kw, int 
     p.nbox = (ra + 255) / 256;
     p.box_h = (((ra + p.nbox - 1) / p.nbox) + 7) & ~7;
     p.ra_alloc = p.nbox * p.box_h;
-    const size_t brow = (size_t)2 * p.kch * FF_N * 16, abytes = (size_t)2 * p.kch * p.ra_alloc * 16;
-    const size_t smem = (size_t)kh * brow + FF_NA * abytes;
+    const size_t brow = (size_t)p.kch * 2 * FF_N * 16, abytes = (size_t)2 * p.kch * p.ra_alloc * 16;
+    const size_t smem = (size_t)FF_NB * brow + FF_NA * abytes;
     if (smem > (size_t)FF_SMEM_MAX) return B200CV_NOT_IMPLEMENTED;
     const int grid = (int)std::min<long long>(nt, num_sms());
 
@@ -322,14 +352,14 @@ int filter2d_f32_tensor(const Img& s, const Img& d, const float* k, int kw, int 
     if (!rc) {
         static PerDeviceFlag attr_pd; bool& attr = attr_pd.cur();
         if (!attr) {
-            B200_CUDA(cudaFuncSetAttribute(filter2d_tc_f32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_MAX));
             B200_CUDA(cudaFuncSetAttribute(filter2d_tc_f32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_MAX));
             B200_CUDA(cudaFuncSetAttribute(filter2d_tc_f32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_MAX));
+            B200_CUDA(cudaFuncSetAttribute(filter2d_tc_f32_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FF_SMEM_MAX));
             attr = true;
         }
-        if (p.kch == 2) filter2d_tc_f32_kernel<1><<<grid, FF_THREADS, smem, st>>>(tm, bglob, d, p);
-        else if (p.kch == 4) filter2d_tc_f32_kernel<2><<<grid, FF_THREADS, smem, st>>>(tm, bglob, d, p);
-        else filter2d_tc_f32_kernel<3><<<grid, FF_THREADS, smem, st>>>(tm, bglob, d, p);
+        if (p.kch == 4) filter2d_tc_f32_kernel<2><<<grid, FF_THREADS, smem, st>>>(tm, bglob, d, p);          // kw = 1
+        else if (p.kch == 6) filter2d_tc_f32_kernel<3><<<grid, FF_THREADS, smem, st>>>(tm, bglob, d, p);     // kw <= 17
+        else filter2d_tc_f32_kernel<4><<<grid, FF_THREADS, smem, st>>>(tm, bglob, d, p);                     // kw <= 33
         cudaError_t e = cudaGetLastError();
         count_launch();
         if (e != cudaSuccess) rc = cuda_fail(e, "kernel launch", __FILE__, __LINE__);

@@ -46,9 +46,13 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
     float* s_src = smem;                                          // sh_ x sw_
     float* s_rx = s_src + sw_ * sh_;                              // sh_ x cw : row pass with the Dx row taps
     float* s_ry = s_rx + sh_ * cw;                                // sh_ x cw : row pass with the Dy row taps
-    float* s_a = s_ry + sh_ * cw;                                 // ch x cw : dx*dx
-    float* s_b = s_a + cw * ch;                                   //           dx*dy
-    float* s_c = s_b + cw * ch;                                   //           dy*dy
+    // the three product images as DOUBLES (the box filter accumulates in f64, box_filter.simd.hpp:1255-1264): every product is converted
+    // once where it is made instead of BS^2 times where it is summed (F2F.F64.F32 issues at 16 lanes / clk / SM: 12 conversions per pixel
+    // at BS = 2 were a third of the kernel); rows padded to an even length so that pairs load as 128-bit words
+    const int cwp = cw + (cw & 1);
+    double* s_a = (double*)(smem + (((size_t)sw_ * sh_ + 2 * (size_t)sh_ * cw + 3) & ~(size_t)3));   // ch x cwp : dx*dx  (16-byte aligned)
+    double* s_b = s_a + cwp * ch;                                 //            dx*dy
+    double* s_c = s_b + cwp * ch;                                 //            dy*dy
     const int f = blockIdx.z, x0 = blockIdx.x * H_TW, y0 = blockIdx.y * H_TH;
     const int cx0 = x0 - p.ba, cy0 = y0 - p.ba;                   // image coordinates of cov region origin
     const int W = src.cols, H = src.rows;
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
     // column pass + products at the in-image positions of the cov region
     for (int r = warp; r < ch; r += 8)
     for (int c = lane; c < cw; c += 32) {
-        const int idx = r * cw + c;
+        const int idx = r * cwp + c;
         int gx = cx0 + c, gy = cy0 + r;
         if ((unsigned)gx >= (unsigned)W || (unsigned)gy >= (unsigned)H) continue;
         // columns: mirrored rows first (Dx column kernel symmetric, Dy column kernel antisymmetric; delta = 0)
@@ -103,58 +107,83 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
             dx = fmaf(p.dxk_y[m + j], __fadd_rn(s_rx[(r + m + j) * cw + c], s_rx[(r + m - j) * cw + c]), dx);
             dy = fmaf(p.dyk_y[m + j], __fsub_rn(s_ry[(r + m + j) * cw + c], s_ry[(r + m - j) * cw + c]), dy);
         }
-        s_a[idx] = __fmul_rn(dx, dx); s_b[idx] = __fmul_rn(dx, dy); s_c[idx] = __fmul_rn(dy, dy);
+        s_a[idx] = (double)__fmul_rn(dx, dx); s_b[idx] = (double)__fmul_rn(dx, dy); s_c[idx] = (double)__fmul_rn(dy, dy);
     }
     __syncthreads();
     // the box filter's border: out-of-image positions take the products of the border-interpolated position (or 0);
     // only CTAs on the image boundary have any
     if (cx0 < 0 || cy0 < 0 || cx0 + cw > W || cy0 + ch > H) {
-        for (int idx = threadIdx.x; idx < cw * ch; idx += 256) {
-            int r = idx / cw, c = idx - r * cw;
+        for (int i = threadIdx.x; i < cw * ch; i += 256) {
+            int r = i / cw, c = i - r * cw;
+            const int idx = r * cwp + c;
             int gx = cx0 + c, gy = cy0 + r;
             if ((unsigned)gx < (unsigned)W && (unsigned)gy < (unsigned)H) continue;
             int qx = border_interpolate(gx, W, p.border), qy = border_interpolate(gy, H, p.border);
             int qc = qx - cx0, qr = qy - cy0;
-            if (qx < 0 || qy < 0 || qc < 0 || qc >= cw || qr < 0 || qr >= ch) { s_a[idx] = s_b[idx] = s_c[idx] = 0.f; continue; }
-            int q = qr * cw + qc;
+            if (qx < 0 || qy < 0 || qc < 0 || qc >= cw || qr < 0 || qr >= ch) { s_a[idx] = s_b[idx] = s_c[idx] = 0.0; continue; }
+            int q = qr * cwp + qc;
             s_a[idx] = s_a[q]; s_b[idx] = s_b[q]; s_c[idx] = s_c[q];
         }
         __syncthreads();
     }
-    for (int idx = threadIdx.x; idx < H_TW * H_TH; idx += 256) {
-        int r = idx / H_TW, c = idx - r * H_TW;
-        int gx = x0 + c, gy = y0 + r;
-        if (gx >= W || gy >= H) continue;
-        double a = 0, b = 0, cc = 0;
-        if constexpr (BS != 0) {
-#pragma unroll
-            for (int j = 0; j < BS; j++) {
-                int o = (r + j) * cw + c;
-                double ra = 0, rb = 0, rc = 0;
-#pragma unroll
-                for (int i = 0; i < BS; i++) { ra += (double)s_a[o + i]; rb += (double)s_b[o + i]; rc += (double)s_c[o + i]; }
-                a += ra; b += rb; cc += rc;
-            }
-        } else {
-            for (int j = 0; j < bs; j++) {
-                int o = (r + j) * cw + c;
-                double ra = 0, rb = 0, rc = 0;
-                for (int i = 0; i < bs; i++) { ra += (double)s_a[o + i]; rb += (double)s_b[o + i]; rc += (double)s_c[o + i]; }
-                a += ra; b += rb; cc += rc;
-            }
-        }
-        float fa = (float)a, fb = (float)b, fc = (float)cc, out;
+    auto response = [&](double a, double b, double cc) -> float {
+        float fa = (float)a, fb = (float)b, fc = (float)cc;
         if (p.op == 0) {
             float acbb = __fsub_rn(__fmul_rn(fa, fc), __fmul_rn(fb, fb));
             float ac = __fadd_rn(fa, fc);
-            out = __fsub_rn(acbb, __fmul_rn(p.k, __fmul_rn(ac, ac)));     // calcHarrisLine_AVX: k * ((a+c)*(a+c)), no FMA (corner.avx.cpp:145-160)
-        } else {
-            float ha = __fmul_rn(fa, 0.5f), hc = __fmul_rn(fc, 0.5f);
-            float t = __fsub_rn(ha, hc);
-            t = __fadd_rn(__fmul_rn(fb, fb), __fmul_rn(t, t));
-            out = __fsub_rn(__fadd_rn(ha, hc), __fsqrt_rn(t));
+            return __fsub_rn(acbb, __fmul_rn(p.k, __fmul_rn(ac, ac)));     // calcHarrisLine_AVX: k * ((a+c)*(a+c)), no FMA (corner.avx.cpp:145-160)
         }
-        dst.row<float>(f, gy)[gx] = out;
+        float ha = __fmul_rn(fa, 0.5f), hc = __fmul_rn(fc, 0.5f);
+        float t = __fsub_rn(ha, hc);
+        t = __fadd_rn(__fmul_rn(fb, fb), __fmul_rn(t, t));
+        return __fsub_rn(__fadd_rn(ha, hc), __fsqrt_rn(t));
+    };
+    if constexpr (BS == 2 || BS == 3) {
+        // four adjacent outputs per thread: the 4 + BS - 1 products of a row are loaded once (128-bit words) and shared by the four
+        // horizontal sums (added left to right, then rows top to bottom: the order above); one 16-byte store
+        for (int item = threadIdx.x; item < (H_TW / 4) * H_TH; item += 256) {
+            const int r = item / (H_TW / 4), c = (item - r * (H_TW / 4)) * 4;
+            const int gx = x0 + c, gy = y0 + r;
+            if (gx >= W || gy >= H) continue;
+            double sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0}, sc[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int j = 0; j < BS; j++) {
+                const int o = (r + j) * cwp + c;                  // even: 16-byte aligned
+                double va[6], vb[6], vc[6];
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const double2 ta = *(const double2*)(s_a + o + 2 * q), tb = *(const double2*)(s_b + o + 2 * q), tc = *(const double2*)(s_c + o + 2 * q);
+                    va[2 * q] = ta.x; va[2 * q + 1] = ta.y; vb[2 * q] = tb.x; vb[2 * q + 1] = tb.y; vc[2 * q] = tc.x; vc[2 * q + 1] = tc.y;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    double ra = va[i], rb = vb[i], rc = vc[i];
+#pragma unroll
+                    for (int t = 1; t < BS; t++) { ra += va[i + t]; rb += vb[i + t]; rc += vc[i + t]; }
+                    sa[i] += ra; sb[i] += rb; sc[i] += rc;
+                }
+            }
+            float o4[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) o4[i] = response(sa[i], sb[i], sc[i]);
+            float* dp = dst.row<float>(f, gy) + gx;
+            if (gx + 4 <= W && ((uintptr_t)dp & 15) == 0) *(float4*)dp = make_float4(o4[0], o4[1], o4[2], o4[3]);
+            else for (int i = 0; i < 4 && gx + i < W; i++) dp[i] = o4[i];
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < H_TW * H_TH; idx += 256) {
+            int r = idx / H_TW, c = idx - r * H_TW;
+            int gx = x0 + c, gy = y0 + r;
+            if (gx >= W || gy >= H) continue;
+            double a = 0, b = 0, cc = 0;
+            for (int j = 0; j < bs; j++) {
+                int o = (r + j) * cwp + c;
+                double ra = 0, rb = 0, rc = 0;
+                for (int i = 0; i < bs; i++) { ra += s_a[o + i]; rb += s_b[o + i]; rc += s_c[o + i]; }
+                a += ra; b += rb; cc += rc;
+            }
+            dst.row<float>(f, gy)[gx] = response(a, b, cc);
+        }
     }
 }
 
@@ -162,7 +191,8 @@ template <typename ST, int KS, int BS>
 static int launch_harris(const Img& s, const Img& d, const HarrisParams& p, cudaStream_t st)
 {
     const int rs = KS / 2, cw = H_TW + p.bs - 1, ch = H_TH + p.bs - 1, sw_ = cw + 2 * rs, sh_ = ch + 2 * rs;
-    size_t smem = ((size_t)sw_ * sh_ + 2 * (size_t)sh_ * cw + 3 * (size_t)cw * ch) * sizeof(float);
+    const int cwp = cw + (cw & 1);
+    size_t smem = ((((size_t)sw_ * sh_ + 2 * (size_t)sh_ * cw + 3) & ~(size_t)3)) * sizeof(float) + 3 * (size_t)cwp * ch * sizeof(double);
     auto kern = harris_kernel<ST, KS, BS>;
     static PerDeviceFlag a_pd; bool& a = a_pd.cur();
     if (!a) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a = true; }
@@ -350,19 +380,36 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
                 count_launch();
             }
     }
-    const int CHUNK = 1 << 15;
+    // the strongest CHUNK candidates of EVERY frame come back with one synchronisation (page-locked staging: the copies queue behind the
+    // sorts and overlap them); the walk fetches further chunks only if it gets that far (it normally stops after a short prefix)
+    const int CHUNK = 1 << 14;
+    static thread_local CandKey* h_stage = nullptr;
+    static thread_local size_t h_stage_cap = 0;
+    const size_t need = (size_t)CHUNK * frames;
+    if (h_stage_cap < need) {
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr; h_stage_cap = 0;
+        TRY(cudaHostAlloc((void**)&h_stage, need * sizeof(CandKey), cudaHostAllocDefault));
+        h_stage_cap = need;
+    }
+    for (int f = 0; f < frames; f++)
+        if (hcnt[f]) TRY(cudaMemcpyAsync(h_stage + (size_t)f * CHUNK, d_sorted + (size_t)f * cap, sizeof(CandKey) * std::min(CHUNK, hcnt[f]), cudaMemcpyDeviceToHost, st));
+    TRY(cudaStreamSynchronize(st));
     std::vector<CandKey> chunk;
+    std::vector<int> head, nxt;                  // accepted corners per grid cell: singly linked lists in flat arrays
+    std::vector<float> ax, ay;
     for (int f = 0; f < frames; f++) {
         const int n = hcnt[f];
-        int fetched = 0;
-        // next(): the i-th strongest candidate; fetches another chunk when the walk gets there
+        int fetched = std::min(CHUNK, n), base = 0;                  // candidates [base, fetched) are in `cur`
+        const CandKey* cur = h_stage + (size_t)f * CHUNK;
+        // the i-th strongest candidate; fetches another chunk when the walk gets there
         auto fetch = [&](int i) -> cudaError_t {
             if (i < fetched) return cudaSuccess;
-            int m = std::min(CHUNK, n - fetched);
+            const int m = std::min(CHUNK, n - fetched);
             chunk.resize(m);
             cudaError_t ce = cudaMemcpyAsync(chunk.data(), d_sorted + (size_t)f * cap + fetched, sizeof(CandKey) * m, cudaMemcpyDeviceToHost, st);
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-            fetched += m;
+            base = fetched; fetched += m; cur = chunk.data();
             return ce;
         };
         float* outp = corners + (size_t)f * max_out * 2;
@@ -375,30 +422,33 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
         if (min_distance >= 1) {
             const int cell = (int)lrint(min_distance);
             const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
-            std::vector<std::vector<std::pair<float, float>>> grid((size_t)gw * gh);
+            head.assign((size_t)gw * gh, -1);
+            nxt.clear(); ax.clear(); ay.clear();
             const double md2 = min_distance * min_distance;
             for (int i = 0; i < n; i++) {
                 TRY(fetch(i));
-                const CandKey key = chunk[i - (fetched - (int)chunk.size())];
+                const CandKey key = cur[i - base];
                 const int pos = (int)(unsigned)key;
                 int y = pos / W, x = pos - y * W;
                 int cx = x / cell, cy = y / cell;
                 bool keep = true;
                 for (int yy = std::max(0, cy - 1); keep && yy <= std::min(gh - 1, cy + 1); yy++)
                     for (int xx = std::max(0, cx - 1); keep && xx <= std::min(gw - 1, cx + 1); xx++)
-                        for (const auto& q : grid[(size_t)yy * gw + xx]) {
-                            float ddx = x - q.first, ddy = y - q.second;
+                        for (int q = head[(size_t)yy * gw + xx]; q >= 0; q = nxt[q]) {
+                            float ddx = x - ax[q], ddy = y - ay[q];
                             if (ddx * ddx + ddy * ddy < md2) { keep = false; break; }
                         }
                 if (!keep) continue;
-                grid[(size_t)cy * gw + cx].emplace_back((float)x, (float)y);
+                nxt.push_back(head[(size_t)cy * gw + cx]);
+                head[(size_t)cy * gw + cx] = (int)ax.size();
+                ax.push_back((float)x); ay.push_back((float)y);
                 emit(x, y, ord2f((unsigned)(key >> 32)));
                 if (max_corners > 0 && accepted == max_corners) break;
             }
         } else {
             for (int i = 0; i < n; i++) {
                 TRY(fetch(i));
-                const CandKey key = chunk[i - (fetched - (int)chunk.size())];
+                const CandKey key = cur[i - base];
                 const int pos = (int)(unsigned)key;
                 int y = pos / W, x = pos - y * W;
                 emit(x, y, ord2f((unsigned)(key >> 32)));

@@ -60,3 +60,20 @@ def test_cpp_host_mirror_compiles_against_the_c_abi():
     if not torch.cuda.is_available():
         run = subprocess.run([exe], capture_output=True, text=True)
         assert run.returncode == 1 and "no CPU fallback" in run.stderr      # loud failure without a device
+
+
+def test_cv_typed_surface_compiles_against_the_reference_headers():
+    """b200cv_opencv.hpp (cv::InputArray / OutputArray / cv::cuda::GpuMat / HostMem) builds against /root/reference's headers and links with
+    the reference's core + imgproc; without a device the binary fails loudly"""
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference/modules/core/include") or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libocvref.so")):
+        pytest.skip("needs /root/reference and oracle/_ref")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "cpp"))
+    import build_cv_surface
+    exe = build_cv_surface.build()
+    assert exe and os.path.exists(exe)
+    import torch
+    if not torch.cuda.is_available():
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode == 1 and "no CPU fallback" in run.stderr
