@@ -46,13 +46,11 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
     float* s_src = smem;                                          // sh_ x sw_
     float* s_rx = s_src + sw_ * sh_;                              // sh_ x cw : row pass with the Dx row taps
     float* s_ry = s_rx + sh_ * cw;                                // sh_ x cw : row pass with the Dy row taps
-    // the three product images as DOUBLES (the box filter accumulates in f64, box_filter.simd.hpp:1255-1264): every product is converted
-    // once where it is made instead of BS^2 times where it is summed (F2F.F64.F32 issues at 16 lanes / clk / SM: 12 conversions per pixel
-    // at BS = 2 were a third of the kernel); rows padded to an even length so that pairs load as 128-bit words
+    // the three product images (float); rows padded to an even length so that pairs load as 64-bit words
     const int cwp = cw + (cw & 1);
-    double* s_a = (double*)(smem + (((size_t)sw_ * sh_ + 2 * (size_t)sh_ * cw + 3) & ~(size_t)3));   // ch x cwp : dx*dx  (16-byte aligned)
-    double* s_b = s_a + cwp * ch;                                 //            dx*dy
-    double* s_c = s_b + cwp * ch;                                 //            dy*dy
+    float* s_a = s_ry + sh_ * cw + ((sw_ * sh_ + 2 * sh_ * cw) & 1);   // ch x cwp : dx*dx   (8-byte aligned)
+    float* s_b = s_a + cwp * ch;                                  //            dx*dy
+    float* s_c = s_b + cwp * ch;                                  //            dy*dy
     const int f = blockIdx.z, x0 = blockIdx.x * H_TW, y0 = blockIdx.y * H_TH;
     const int cx0 = x0 - p.ba, cy0 = y0 - p.ba;                   // image coordinates of cov region origin
     const int W = src.cols, H = src.rows;
@@ -66,7 +64,12 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
         float* drow = s_src + r * sw_;
         for (int c = lane; c < sw_; c += 32) {
             const int sx = interior ? cx0 - rs + c : border_interpolate(cx0 - rs + c, W, p.border);
-            drow[c] = (srow && sx >= 0) ? (float)srow[sx] : 0.f;
+            float v = 0.f;
+            if (srow && sx >= 0) {
+                if constexpr (sizeof(ST) == 1) v = __fsub_rn(__uint_as_float(0x4B000000u | (uint32_t)srow[sx]), 8388608.0f);   // byte -> float through the mantissa of 2^23 (I2F is quarter rate)
+                else v = (float)srow[sx];
+            }
+            drow[c] = v;
         }
     }
     __syncthreads();
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
             dx = fmaf(p.dxk_y[m + j], __fadd_rn(s_rx[(r + m + j) * cw + c], s_rx[(r + m - j) * cw + c]), dx);
             dy = fmaf(p.dyk_y[m + j], __fsub_rn(s_ry[(r + m + j) * cw + c], s_ry[(r + m - j) * cw + c]), dy);
         }
-        s_a[idx] = (double)__fmul_rn(dx, dx); s_b[idx] = (double)__fmul_rn(dx, dy); s_c[idx] = (double)__fmul_rn(dy, dy);
+        s_a[idx] = __fmul_rn(dx, dx); s_b[idx] = __fmul_rn(dx, dy); s_c[idx] = __fmul_rn(dy, dy);
     }
     __syncthreads();
     // the box filter's border: out-of-image positions take the products of the border-interpolated position (or 0);
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
             if ((unsigned)gx < (unsigned)W && (unsigned)gy < (unsigned)H) continue;
             int qx = border_interpolate(gx, W, p.border), qy = border_interpolate(gy, H, p.border);
             int qc = qx - cx0, qr = qy - cy0;
-            if (qx < 0 || qy < 0 || qc < 0 || qc >= cw || qr < 0 || qr >= ch) { s_a[idx] = s_b[idx] = s_c[idx] = 0.0; continue; }
+            if (qx < 0 || qy < 0 || qc < 0 || qc >= cw || qr < 0 || qr >= ch) { s_a[idx] = s_b[idx] = s_c[idx] = 0.f; continue; }
             int q = qr * cwp + qc;
             s_a[idx] = s_a[q]; s_b[idx] = s_b[q]; s_c[idx] = s_c[q];
         }
@@ -139,8 +142,9 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
         return __fsub_rn(__fadd_rn(ha, hc), __fsqrt_rn(t));
     };
     if constexpr (BS == 2 || BS == 3) {
-        // four adjacent outputs per thread: the 4 + BS - 1 products of a row are loaded once (128-bit words) and shared by the four
-        // horizontal sums (added left to right, then rows top to bottom: the order above); one 16-byte store
+        // four adjacent outputs per thread: the 4 + BS - 1 products of a row are loaded once (64-bit words), converted once (F2F.F64.F32 issues at
+        // 16 lanes / clk / SM: 4 BS^2 conversions per pixel and array were a third of the kernel) and shared by the four horizontal sums
+        // (added left to right, then rows top to bottom: the order of the scalar loop below); one 16-byte store
         for (int item = threadIdx.x; item < (H_TW / 4) * H_TH; item += 256) {
             const int r = item / (H_TW / 4), c = (item - r * (H_TW / 4)) * 4;
             const int gx = x0 + c, gy = y0 + r;
@@ -148,12 +152,13 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
             double sa[4] = {0, 0, 0, 0}, sb[4] = {0, 0, 0, 0}, sc[4] = {0, 0, 0, 0};
 #pragma unroll
             for (int j = 0; j < BS; j++) {
-                const int o = (r + j) * cwp + c;                  // even: 16-byte aligned
+                const int o = (r + j) * cwp + c;                  // even: 8-byte aligned
                 double va[6], vb[6], vc[6];
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
-                    const double2 ta = *(const double2*)(s_a + o + 2 * q), tb = *(const double2*)(s_b + o + 2 * q), tc = *(const double2*)(s_c + o + 2 * q);
-                    va[2 * q] = ta.x; va[2 * q + 1] = ta.y; vb[2 * q] = tb.x; vb[2 * q + 1] = tb.y; vc[2 * q] = tc.x; vc[2 * q + 1] = tc.y;
+                    const float2 ta = *(const float2*)(s_a + o + 2 * q), tb = *(const float2*)(s_b + o + 2 * q), tc = *(const float2*)(s_c + o + 2 * q);
+                    va[2 * q] = ta.x; vb[2 * q] = tb.x; vc[2 * q] = tc.x;
+                    if (2 * q + 1 < 4 + BS - 1) { va[2 * q + 1] = ta.y; vb[2 * q + 1] = tb.y; vc[2 * q + 1] = tc.y; }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
             for (int j = 0; j < bs; j++) {
                 int o = (r + j) * cwp + c;
                 double ra = 0, rb = 0, rc = 0;
-                for (int i = 0; i < bs; i++) { ra += s_a[o + i]; rb += s_b[o + i]; rc += s_c[o + i]; }
+                for (int i = 0; i < bs; i++) { ra += (double)s_a[o + i]; rb += (double)s_b[o + i]; rc += (double)s_c[o + i]; }
                 a += ra; b += rb; cc += rc;
             }
             dst.row<float>(f, gy)[gx] = response(a, b, cc);
@@ -192,7 +197,7 @@ static int launch_harris(const Img& s, const Img& d, const HarrisParams& p, cuda
 {
     const int rs = KS / 2, cw = H_TW + p.bs - 1, ch = H_TH + p.bs - 1, sw_ = cw + 2 * rs, sh_ = ch + 2 * rs;
     const int cwp = cw + (cw & 1);
-    size_t smem = ((((size_t)sw_ * sh_ + 2 * (size_t)sh_ * cw + 3) & ~(size_t)3)) * sizeof(float) + 3 * (size_t)cwp * ch * sizeof(double);
+    size_t smem = ((size_t)sw_ * sh_ + 2 * (size_t)sh_ * cw + 1 + 3 * (size_t)cwp * ch) * sizeof(float);
     auto kern = harris_kernel<ST, KS, BS>;
     static PerDeviceFlag a_pd; bool& a = a_pd.cur();
     if (!a) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); a = true; }
