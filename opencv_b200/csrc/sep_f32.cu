@@ -12,6 +12,7 @@
 // arithmetic of the other CTAs resident on the SM instead of stalling every thread on its own LDG (the generic kernel was
 // long-scoreboard bound: ncu profiles/r01_prof1_summary.txt).  TMA zero-fills outside the image (= BORDER_CONSTANT); for
 // REPLICATE / REFLECT / REFLECT_101 only boundary CTAs patch their apron from the mirrored in-tile cells.
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "tma.cuh"
@@ -28,47 +29,59 @@ struct SF32Params {
     int has_dog;
     int row_small;             // float source, 3/5 (anti)symmetric taps: 1 symmetric, 2 antisymmetric (centre-out order), 0 tap order
     unsigned col_sign;         // 0: symmetric column kernel, 0x80000000: antisymmetric (S[c+k] - S[c-k])
+    int nch;                   // chunks of SF_TH output rows one CTA walks down (1 = the plain tile kernel)
 };
 
+// Kernels of 13 taps and more WALK DOWN a column strip (p.nch chunks of SF_TH output rows per CTA): the SF_TH + KB - 1 row-filtered rows behind
+// a chunk stay in shared memory, the last KB - 1 of them move to the top for the next chunk (a 20-word copy per thread), and every chunk after
+// the first stages and row-filters only its SF_TH new source rows -- the plain tile kernel filtered SF_TH + KB - 1 rows for SF_TH outputs
+// (1.9x the row-pass work at 27 taps: profiles/r02_prof_sift_sep_f32_before.txt, FFMA 63 per pixel).  The next chunk's TMA load is issued
+// right after the row pass and lands during the column pass.  Rows above / below the image (mirroring borders): the row filter commutes
+// with the vertical mirror, so those filtered rows are copies of the mirrored rows' filtered rows.
 template <int KB, typename ST, typename DT>
-__global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(const __grid_constant__ CUtensorMap tmap, Img dst, const __grid_constant__ SF32Params p)
+__global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail, Img src, Img dst,
+                                                                              const __grid_constant__ SF32Params p)
 {
     constexpr int RB = KB / 2;
     constexpr int RA = sizeof(ST) == 1 ? 16 : ((RB + 3) / 4) * 4;   // left apron staged: TMA needs the box to start on a 16-byte boundary
     constexpr int OFF = RA - RB;
-    constexpr int IH = SF_TH + KB - 1;
+    constexpr int IH = SF_TH + KB - 1;                    // ring rows = source rows behind one chunk of outputs
+    constexpr bool MARCH = KB >= 13;                      // tmap boxes: SF_TH rows (MARCH; tmap_tail: KB - 1 rows) or the whole IH-row tile
+    const int nch = MARCH ? p.nch : 1;                    // up to 11 taps: the plain tile kernel (3 CTAs per SM at 80 registers: no room for the walk's state)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ST* s_in = (ST*)smem_raw;                             // IH x SF_IW
-    float* s_mid = (float*)(smem_raw + (((size_t)IH * SF_IW * sizeof(ST) + 127) & ~(size_t)127));    // IH x SF_TW
+    float* s_mid = (float*)(smem_raw + (((size_t)IH * SF_IW * sizeof(ST) + 127) & ~(size_t)127));    // IH x SF_TW: row r = strip-relative source row SF_TH * ch + r
     __shared__ __align__(8) uint64_t s_bar;
-    const int f = blockIdx.z, x0 = blockIdx.x * SF_TW, y0 = blockIdx.y * SF_TH;
+    const int f = blockIdx.z, x0 = blockIdx.x * SF_TW, y00 = blockIdx.y * (SF_TH * nch);
     const int tid = threadIdx.x;
+    const int tx0 = x0 - RA;
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         fence_barrier_init();
         mbar_arrive_expect_tx(&s_bar, (uint32_t)(SF_IW * IH * sizeof(ST)));
-        tma_load_3d(s_in, &tmap, x0 - RA, y0 - RB, f, &s_bar);
-        // only this thread polls the barrier; the others sleep in bar.sync instead of spending issue slots on a spin loop
-        mbar_wait(&s_bar, 0);
+        tma_load_3d(s_in, &tmap, tx0, y00 - RB, f, &s_bar);
+        if constexpr (MARCH) tma_load_3d(s_in + SF_TH * SF_IW, &tmap_tail, tx0, y00 - RB + SF_TH, f, &s_bar);       // the first chunk: SF_TH + (KB - 1) rows
     }
+#pragma unroll 1
+  for (int ch = 0; ch < nch; ch++) {
+    const int y0 = y00 + ch * SF_TH;
+    if (y0 >= p.H) break;
+    const int mrow0 = ch == 0 ? 0 : KB - 1;                         // first filtered row this chunk produces (rows above it come from the previous chunk)
+    const int nrows = ch == 0 ? IH : SF_TH;
+    if (ch > 0) {
+        // the previous chunk's last KB - 1 filtered rows are this chunk's first (the barrier that ended its column pass is behind us)
+        for (int idx = tid; idx < (KB - 1) * (SF_TW / 4); idx += 256) ((float4*)s_mid)[idx] = ((const float4*)(s_mid + SF_TH * SF_TW))[idx];
+    }
+    // only thread 0 polls the barrier; the others sleep in bar.sync instead of spending issue slots on a spin loop
+    if (tid == 0) mbar_wait(&s_bar, (uint32_t)(ch & 1));
     __syncthreads();
 
-    const int tx0 = x0 - RA;
-    const bool edge = (tx0 < 0) || (y0 - RB < 0) || (tx0 + SF_IW > p.W) || (y0 - RB + IH > p.H);
-    if (edge && p.border != B200CV_BORDER_CONSTANT) {
-        for (int idx = tid; idx < IH * SF_IW; idx += 256) {
-            int r = idx / SF_IW, c = idx - r * SF_IW;
-            int gy = y0 - RB + r;
-            if ((unsigned)gy < (unsigned)p.H) continue;
-            int sr = border_interpolate(gy, p.H, p.border) - (y0 - RB);
-            if ((unsigned)sr < (unsigned)IH) s_in[idx] = s_in[sr * SF_IW + c];   // rows beyond the apron feed no valid output
-        }
-        __syncthreads();
+    if (p.border != B200CV_BORDER_CONSTANT && (tx0 < 0 || tx0 + SF_IW > p.W)) {
         const int c_first = p.W - tx0;                        // first tile column right of the image (may be >= SF_IW)
         const int nright = c_first < SF_IW ? min(SF_IW - c_first, RB + 4) : 0;
         const int nleft = tx0 < 0 ? RA : 0;
         const int ncol = nleft + nright;
-        for (int idx = tid; idx < IH * ncol; idx += 256) {
+        for (int idx = tid; idx < nrows * ncol; idx += 256) {
             int r = idx / ncol, k = idx - r * ncol;
             int c = k < nleft ? k : c_first + (k - nleft);
             int sc = border_interpolate(tx0 + c, p.W, p.border) - tx0;
@@ -85,7 +98,7 @@ __global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(co
         constexpr int NEED = NO + KB - 1;
         constexpr int NV = (OFF + NEED + 3) / 4;
 #pragma unroll 1
-        for (int it = tid; it < IH * GPR; it += 256) {
+        for (int it = tid; it < nrows * GPR; it += 256) {
             const int r = it / GPR, g = it - r * GPR;
             float win[NV * 4];                            // the item's window (+ alignment slack), all indices compile-time
 #pragma unroll
@@ -126,12 +139,34 @@ __global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(co
                     acc[o] = t;
                 }
             }
-            float4* mp = (float4*)(s_mid + r * SF_TW + g * NO);
+            float4* mp = (float4*)(s_mid + (mrow0 + r) * SF_TW + g * NO);
             mp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
             if constexpr (NO == 8) mp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
     }
     __syncthreads();
+    // the staging buffer is free: the next chunk's source rows land during the column pass
+    if (tid == 0 && ch + 1 < nch && y0 + SF_TH < p.H) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(&s_bar, (uint32_t)(SF_IW * SF_TH * sizeof(ST)));
+        tma_load_3d(s_in, &tmap, tx0, y00 - RB + IH + SF_TH * ch, f, &s_bar);
+    }
+    {
+        // filtered rows of this chunk whose source row lies above / below the image = the filtered row of the mirrored source row (in this
+        // window: at most KB - 1 rows away, and already filtered)
+        const int g0 = y00 - RB + SF_TH * ch;                         // image row of the window's first row
+        if (p.border != B200CV_BORDER_CONSTANT && (g0 + mrow0 < 0 || g0 + IH > p.H)) {
+            for (int idx = tid; idx < nrows * (SF_TW / 4); idx += 256) {
+                const int r = mrow0 + idx / (SF_TW / 4), c4 = idx % (SF_TW / 4);
+                const int gy = g0 + r;
+                if ((unsigned)gy < (unsigned)p.H) continue;
+                const int sr = border_interpolate(gy, p.H, p.border) - g0;      // window row of the mirrored source row
+                if (sr < 0 || sr >= IH) continue;                               // outside the window: feeds no valid output
+                ((float4*)(s_mid + r * SF_TW))[c4] = ((const float4*)(s_mid + sr * SF_TW))[c4];
+            }
+            __syncthreads();
+        }
+    }
 
     // ---- column pass: item = CW columns x R rows; the R + KB - 1 mid rows it needs are held in registers ----
     {
@@ -160,6 +195,27 @@ __global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(co
             for (int o = 0; o < R; o++) {
                 const int gy = y0 + q * R + o;
                 if (gy >= p.H) break;
+                // difference of Gaussians: the centre value (the blur's own input).  The plain tile kernel still has it staged; a walking CTA staged
+                // it a chunk ago (the buffer is being refilled): from global memory (L2), loaded BEFORE the FMA chains so the latency hides behind them
+                float ctr[CW] = {};
+                if constexpr (sizeof(ST) == 4) {
+                    if (p.has_dog) {
+                        if (nch == 1) {
+                            const float* cp = (const float*)s_in + (q * R + o + RB) * SF_IW + RA + cg * CW;
+#pragma unroll
+                            for (int c = 0; c < CW; c++) ctr[c] = cp[c];
+                        } else {
+                            const float* cp = src.row<float>(f, gy) + gx;
+                            if (gx + CW <= p.W) {            // 16-byte aligned rows (TMA requirement), gx a multiple of CW
+                                if constexpr (CW == 4) { const float4 v = __ldg((const float4*)cp); ctr[0] = v.x; ctr[1] = v.y; ctr[2] = v.z; ctr[3] = v.w; }
+                                else { const float2 v = __ldg((const float2*)cp); ctr[0] = v.x; ctr[1] = v.y; }
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < CW; c++) if (gx + c < p.W) ctr[c] = cp[c];
+                            }
+                        }
+                    }
+                }
                 float acc[CW];
 #pragma unroll
                 for (int c = 0; c < CW; c++) {
@@ -191,7 +247,6 @@ __global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(co
                     }
                     if constexpr (sizeof(ST) == 4) {
                         if (p.has_dog) {
-                            const float* ctr = (const float*)s_in + (q * R + o + RB) * SF_IW + RA + cg * CW;
                             float* gp = p.dog.row<float>(f, gy) + gx;
                             if (gvec && gx + CW <= p.W) {
                                 if constexpr (CW == 4)
@@ -207,18 +262,24 @@ __global__ void __launch_bounds__(256, (KB <= 11 ? 3 : 2)) sep_f32_tma_kernel(co
             }
         }
     }
+    __syncthreads();            // the next chunk moves and overwrites filtered rows this column pass has read
+  }
 }
 
 template <int KB, typename ST, typename DT>
-static int launch_sf32(const CUtensorMap& tm, const Img& d, const SF32Params& p, int frames, cudaStream_t st)
+static int launch_sf32(const CUtensorMap& tm, const CUtensorMap& tm_tail, const Img& s, const Img& d, SF32Params& p, int frames, cudaStream_t st)
 {
     constexpr int IH = SF_TH + KB - 1;
     const size_t smem = (((size_t)IH * SF_IW * sizeof(ST) + 127) & ~(size_t)127) + (size_t)IH * SF_TW * sizeof(float);
+    // chunks per CTA: 4 (128 rows) for 13 taps and more when the grid stays several waves deep; small kernels keep the plain tile form
+    const long tiles = (long)div_up((unsigned)p.W, SF_TW) * div_up((unsigned)p.H, SF_TH) * frames;
+    p.nch = (KB >= 13 && tiles >= 8L * 2 * num_sms()) ? 4 : (KB >= 13 && tiles >= 4L * 2 * num_sms()) ? 2 : 1;
+    if (p.has_dog && getenv("B200CV_SEP_DOG_TILE")) p.nch = 1;      // measurement switch: the plain tile kernel for the fused-DoG blurs
     auto kern = sep_f32_tma_kernel<KB, ST, DT>;
     static PerDeviceFlag attr_pd; bool& attr = attr_pd.cur();
     if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    dim3 grid(div_up((unsigned)p.W, SF_TW), div_up((unsigned)p.H, SF_TH), (unsigned)frames);
-    kern<<<grid, 256, smem, st>>>(tm, d, p);
+    dim3 grid(div_up((unsigned)p.W, SF_TW), div_up((unsigned)p.H, (unsigned)(SF_TH * p.nch)), (unsigned)frames);
+    kern<<<grid, 256, smem, st>>>(tm, tm_tail, s, d, p);
     cudaError_t e = cudaGetLastError();
     count_launch();
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
@@ -253,22 +314,24 @@ static int sep_float_fast(const Img& s, const Img& d, const float* kx, int nx, c
     p.delta = delta; p.W = s.cols; p.H = s.rows; p.border = border;
     p.row_small = rsym; p.col_sign = csym == 2 ? 0x80000000u : 0u;
     if (dog) { p.dog = *dog; p.has_dog = 1; }
-    CUtensorMap tm;
-    int rc = make_tensor_map_3d(&tm, s.data, (int)sizeof(ST), s.cols, s.rows, s.frames, s.step, s.fstep, SF_IW, SF_TH + KB - 1);
+    CUtensorMap tm, tm_tail;
+    const bool march = KB >= 13;
+    int rc = make_tensor_map_3d(&tm, s.data, (int)sizeof(ST), s.cols, s.rows, s.frames, s.step, s.fstep, SF_IW, march ? SF_TH : SF_TH + KB - 1);
     if (rc) return rc;
+    if ((rc = make_tensor_map_3d(&tm_tail, s.data, (int)sizeof(ST), s.cols, s.rows, s.frames, s.step, s.fstep, SF_IW, KB - 1))) return rc;
     switch (KB) {
-    case 3: return launch_sf32<3, ST, DT>(tm, d, p, s.frames, st);
-    case 5: return launch_sf32<5, ST, DT>(tm, d, p, s.frames, st);
-    case 7: return launch_sf32<7, ST, DT>(tm, d, p, s.frames, st);
-    case 9: return launch_sf32<9, ST, DT>(tm, d, p, s.frames, st);
-    case 11: return launch_sf32<11, ST, DT>(tm, d, p, s.frames, st);
-    case 13: return launch_sf32<13, ST, DT>(tm, d, p, s.frames, st);
-    case 15: return launch_sf32<15, ST, DT>(tm, d, p, s.frames, st);
-    case 17: return launch_sf32<17, ST, DT>(tm, d, p, s.frames, st);
-    case 21: return launch_sf32<21, ST, DT>(tm, d, p, s.frames, st);
-    case 25: return launch_sf32<25, ST, DT>(tm, d, p, s.frames, st);
-    case 27: return launch_sf32<27, ST, DT>(tm, d, p, s.frames, st);
-    case 31: return launch_sf32<31, ST, DT>(tm, d, p, s.frames, st);
+    case 3: return launch_sf32<3, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 5: return launch_sf32<5, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 7: return launch_sf32<7, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 9: return launch_sf32<9, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 11: return launch_sf32<11, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 13: return launch_sf32<13, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 15: return launch_sf32<15, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 17: return launch_sf32<17, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 21: return launch_sf32<21, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 25: return launch_sf32<25, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 27: return launch_sf32<27, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 31: return launch_sf32<31, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
     }
     return B200CV_NOT_IMPLEMENTED;
 }

@@ -264,6 +264,11 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(Img src, Img dst, const 
         const bool aligned = (((uintptr_t)src.data | src.step | src.fstep) & 15) == 0;
         const int gb0 = bx0 * ES;                                               // byte offset of the staged row start inside a source row
         const int row_bytes = sw * ES;
+        // tiles that look outside the image (a rotation about the centre leaves ~20 % of the destination there): whole vectors of border value
+        bool cfill = border == B200CV_BORDER_CONSTANT;
+        unsigned cword;
+        if constexpr (sizeof(T) == 1) { cfill = cfill && p.cval_i[0] == p.cval_i[1] && p.cval_i[1] == p.cval_i[2] && p.cval_i[2] == p.cval_i[3]; cword = (unsigned)(p.cval_i[0] & 255) * 0x01010101u; }
+        else { cfill = cfill && p.cval_f[0] == p.cval_f[1] && p.cval_f[1] == p.cval_f[2] && p.cval_f[2] == p.cval_f[3]; cword = __float_as_uint(p.cval_f[0]); }
         for (int r = tid >> 5; r < bh; r += 8) {
             int sy = by0 + r;
             if ((unsigned)sy >= (unsigned)sh) sy = border == B200CV_BORDER_REPLICATE ? clipi(sy, 0, sh) : border_interpolate(sy, sh, border);
@@ -274,6 +279,8 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(Img src, Img dst, const 
                 uint4 val;
                 if (srow && aligned && gb >= 0 && gb + 16 <= row_bytes) {
                     val = *(const uint4*)(srow + gb);
+                } else if (cfill && (!srow || gb + 16 <= 0 || gb >= row_bytes)) {
+                    val = make_uint4(cword, cword, cword, cword);        // wholly outside the image under BORDER_CONSTANT with one value for all channels
                 } else {
                     T e[16 / sizeof(T)];
 #pragma unroll

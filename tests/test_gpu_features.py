@@ -191,3 +191,21 @@ def test_sift_pyramid_4k(cvb, ref, rng):
                 assert_exact(gd[o][i], wd[o][i], "4K dog o=%d i=%d" % (o, i))
             else:
                 assert_close(gd[o][i], wd[o][i], atol=1e-4, what="4K dog o=%d i=%d" % (o, i))
+
+
+@pytest.mark.parametrize("shape", [(135, 241), (64, 96), (211, 77), (540, 960)])
+@pytest.mark.parametrize("switch", ["B200CV_SIFT_UPSCALE_WARP", "B200CV_SIFT_NO_SMALL_OCTAVES"])
+def test_sift_fused_stages_equal_the_composition(cvb, rng, monkeypatch, shape, switch):
+    """Two fused stages of the pyramid against the reference's own composition of calls (sift.dispatch.cpp:196-202, 224-310), which stays
+    reachable through a switch: (1) createInitialImage's precise 2x upscale as one u8 -> f32 + upsample kernel vs the general warpAffine kernel;
+    (2) the small octaves (levels that fit shared memory) as ONE launch vs resize(NEAREST) + GaussianBlur per level.  Every level of both
+    pyramids must be identical -- odd widths / heights, a batch, with and without the doubled base."""
+    img = rng.integers(0, 256, (2,) + shape + (1,), dtype=np.uint8)
+    for upscale in (True, False):
+        G, D, dims = cvb.sift_pyramid(gpu(img), 3, 1.6, upscale)
+        monkeypatch.setenv(switch, "1")
+        G2, D2, dims2 = cvb.sift_pyramid(gpu(img), 3, 1.6, upscale)
+        monkeypatch.delenv(switch)
+        assert np.array_equal(dims, dims2)
+        assert_exact(cpu(G), cpu(G2), "Gaussian pyramid with and without %s (upscale=%s)" % (switch, upscale))
+        assert_exact(cpu(D), cpu(D2), "DoG pyramid with and without %s (upscale=%s)" % (switch, upscale))
