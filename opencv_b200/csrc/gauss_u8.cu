@@ -17,6 +17,8 @@
 //      32-bit store.
 // Instruction budget (K=3): ~1 IDP4A + 2 IDP2A and ~6 other instructions per pixel, against ~46 for the generic float kernel.
 #include <vector>
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -291,8 +293,14 @@ int gauss_u8_fast(const Img& s, const Img& d, int cn, const int64_t* fx, int kw,
             for (int i = 0; i < 4; i++) { int j = 4 * g + i - o; if (j >= 0 && j < KB) w |= (uint32_t)ty[j] << (8 * i); }
             p.kyw[o][g] = w;
         }
-    // single channel, K <= 9, Gaussian / 8.8 sepFilter2D epilogues: the register-marching kernel (gauss_u8_march.cu)
-    if (cn == 1 && KB <= 9 && sep_mode <= 1) return gauss_u8_march(s, d, KB, tx, ty, border, st, sep_mode, even_limit);
+    // single channel, K <= 9, Gaussian / 8.8 sepFilter2D epilogues: the warp-streaming register kernel (gauss_u8_march.cu) exists as a second
+    // version; measured on a B200 (profiles/r02_notes.md) it executes fewer instructions (8.9 vs 12.1 per pixel at K = 3) but is 3-7 % SLOWER for
+    // GaussianBlur and 10-28 % slower in sepFilter2D's 8.8 mode (IDP on the half-rate pipe is the bound in both; its per-warp chunks give the
+    // memory system less in flight), so the tile kernel below stays the default; B200CV_GAUSS_U8_PATH=stream selects it (tests run both)
+    {
+        const char* e = getenv("B200CV_GAUSS_U8_PATH");
+        if (e && !strcmp(e, "stream") && cn == 1 && KB <= 9 && sep_mode <= 1) return gauss_u8_march(s, d, KB, tx, ty, border, st, sep_mode, even_limit);
+    }
     p.W = s.cols * cn; p.H = s.rows; p.border = border; p.sep_mode = sep_mode; p.even_limit = even_limit;      // W in byte elements
     if (box) p.box = *box;
     p.TH = ((64 - (KB - 1)) / 4) * 4;

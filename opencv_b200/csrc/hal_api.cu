@@ -185,10 +185,13 @@ extern "C" int b200cv_host_resize(const b200cvMat* s, const b200cvMat* d, int in
 { return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_resize(a, b, interp, st); }); }
 extern "C" int b200cv_host_resize_scaled(const b200cvMat* s, const b200cvMat* d, int interp, double fx, double fy)
 { return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_resize_scaled(a, b, interp, fx, fy, st); }); }
+// BORDER_TRANSPARENT keeps destination pixels: the host path would have to upload the destination too -- declined (the caller's CPU path runs)
 extern "C" int b200cv_host_warp_affine(const b200cvMat* s, const b200cvMat* d, const double* M, int flags, int border, const double* bv)
-{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_warp_affine(a, b, M, flags, border, bv, st); }); }
+{ if ((border & ~B200CV_BORDER_ISOLATED) == B200CV_BORDER_TRANSPARENT) return B200CV_NOT_IMPLEMENTED;
+  return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_warp_affine(a, b, M, flags, border, bv, st); }); }
 extern "C" int b200cv_host_warp_perspective(const b200cvMat* s, const b200cvMat* d, const double* M, int flags, int border, const double* bv)
-{ return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_warp_perspective(a, b, M, flags, border, bv, st); }); }
+{ if ((border & ~B200CV_BORDER_ISOLATED) == B200CV_BORDER_TRANSPARENT) return B200CV_NOT_IMPLEMENTED;
+  return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_warp_perspective(a, b, M, flags, border, bv, st); }); }
 extern "C" int b200cv_host_cvt_color(const b200cvMat* s, const b200cvMat* d, int code)
 { return host_pipeline(s, d, [=](const b200cvMat* a, const b200cvMat* b, void* st) { return b200cv_cvt_color(a, b, code, st); }); }
 extern "C" int b200cv_host_corner_harris(const b200cvMat* s, const b200cvMat* d, int bs, int ks, double k, int border)
@@ -390,6 +393,7 @@ extern "C" int b200cv_hal_pyrdown(const uchar* src, size_t sstep, int sw, int sh
 extern "C" int b200cv_host_remap(const b200cvMat* src, const b200cvMat* dst, const b200cvMat* map1, const b200cvMat* map2, int interp, int border, const double* bv)
 {
     int rc;
+    if ((border & ~B200CV_BORDER_ISOLATED) == B200CV_BORDER_TRANSPARENT) return B200CV_NOT_IMPLEMENTED;
     if ((rc = check_mat(map1, "map1"))) return rc;
     const bool has2 = map2 && map2->data;
     if (has2 && (rc = check_mat(map2, "map2"))) return rc;

@@ -32,6 +32,204 @@ struct SF32Params {
     int nch;                   // chunks of SF_TH output rows one CTA walks down (1 = the plain tile kernel)
 };
 
+// ---- up to 11 taps: the plain tile kernel (one 192 x 32 tile per CTA, 3 CTAs per SM at 80 registers) -- the walking kernel below carries
+//      state that does not fit that register budget (its tile form ran 8-15 % slower at 3 and 9 taps on a B200) ----
+template <int KB, typename ST, typename DT>
+__global__ void __launch_bounds__(256, 3) sep_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, Img dst, const __grid_constant__ SF32Params p)
+{
+    constexpr int RB = KB / 2;
+    constexpr int RA = sizeof(ST) == 1 ? 16 : ((RB + 3) / 4) * 4;   // left apron staged: TMA needs the box to start on a 16-byte boundary
+    constexpr int OFF = RA - RB;
+    constexpr int IH = SF_TH + KB - 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ST* s_in = (ST*)smem_raw;                             // IH x SF_IW
+    float* s_mid = (float*)(smem_raw + (((size_t)IH * SF_IW * sizeof(ST) + 127) & ~(size_t)127));    // IH x SF_TW
+    __shared__ __align__(8) uint64_t s_bar;
+    const int f = blockIdx.z, x0 = blockIdx.x * SF_TW, y0 = blockIdx.y * SF_TH;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        fence_barrier_init();
+        mbar_arrive_expect_tx(&s_bar, (uint32_t)(SF_IW * IH * sizeof(ST)));
+        tma_load_3d(s_in, &tmap, x0 - RA, y0 - RB, f, &s_bar);
+        // only this thread polls the barrier; the others sleep in bar.sync instead of spending issue slots on a spin loop
+        mbar_wait(&s_bar, 0);
+    }
+    __syncthreads();
+
+    const int tx0 = x0 - RA;
+    const bool edge = (tx0 < 0) || (y0 - RB < 0) || (tx0 + SF_IW > p.W) || (y0 - RB + IH > p.H);
+    if (edge && p.border != B200CV_BORDER_CONSTANT) {
+        for (int idx = tid; idx < IH * SF_IW; idx += 256) {
+            int r = idx / SF_IW, c = idx - r * SF_IW;
+            int gy = y0 - RB + r;
+            if ((unsigned)gy < (unsigned)p.H) continue;
+            int sr = border_interpolate(gy, p.H, p.border) - (y0 - RB);
+            if ((unsigned)sr < (unsigned)IH) s_in[idx] = s_in[sr * SF_IW + c];   // rows beyond the apron feed no valid output
+        }
+        __syncthreads();
+        const int c_first = p.W - tx0;                        // first tile column right of the image (may be >= SF_IW)
+        const int nright = c_first < SF_IW ? min(SF_IW - c_first, RB + 4) : 0;
+        const int nleft = tx0 < 0 ? RA : 0;
+        const int ncol = nleft + nright;
+        for (int idx = tid; idx < IH * ncol; idx += 256) {
+            int r = idx / ncol, k = idx - r * ncol;
+            int c = k < nleft ? k : c_first + (k - nleft);
+            int sc = border_interpolate(tx0 + c, p.W, p.border) - tx0;
+            if ((unsigned)sc < (unsigned)SF_IW) s_in[r * SF_IW + c] = s_in[r * SF_IW + sc];
+        }
+        __syncthreads();
+    }
+
+    // ---- row pass: item = NO consecutive outputs of one staged row.  Float rows: NO = 4, so that neighbouring lanes read neighbouring
+    //      16-byte chunks (8 outputs = 32-byte lane stride made every 128-bit shared load a 2-way bank conflict); byte rows: NO = 8 ----
+    {
+        constexpr int NO = sizeof(ST) == 4 ? 4 : 8;
+        constexpr int GPR = SF_TW / NO;                   // items per row
+        constexpr int NEED = NO + KB - 1;
+        constexpr int NV = (OFF + NEED + 3) / 4;
+#pragma unroll 1
+        for (int it = tid; it < IH * GPR; it += 256) {
+            const int r = it / GPR, g = it - r * GPR;
+            float win[NV * 4];                            // the item's window (+ alignment slack), all indices compile-time
+#pragma unroll
+            for (int w = 0; w < NV; w++) {
+                if constexpr (sizeof(ST) == 1) {
+                    // bytes -> floats through the mantissa of 2^23 (PRMT + FADD instead of the quarter-rate I2F)
+                    const uint32_t q = ((const uint32_t*)(s_in + r * SF_IW + g * NO))[w];
+#pragma unroll
+                    for (int b = 0; b < 4; b++) win[w * 4 + b] = __fsub_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7650 + b)), 8388608.0f);
+                } else {
+                    const float4 q = ((const float4*)(s_in + r * SF_IW + g * NO))[w];
+                    win[w * 4] = q.x; win[w * 4 + 1] = q.y; win[w * 4 + 2] = q.z; win[w * 4 + 3] = q.w;
+                }
+            }
+            float acc[NO];
+            bool done = false;
+            if constexpr (KB <= 5 && sizeof(ST) == 4) {
+                if (p.row_small) {
+                    const unsigned sg = p.row_small == 2 ? 0x80000000u : 0u;
+#pragma unroll
+                    for (int o = 0; o < NO; o++) {
+                        const float* x = win + OFF + o + RB;      // centre tap
+                        // symmetric: fma(x0, k0, (x-1 + x1) k1); antisymmetric: (x1 - x-1) k1  (k0 = 0: fma(x0, 0, t) = t)
+                        float t = __fmul_rn(__fadd_rn(x[1], __uint_as_float(__float_as_uint(x[-1]) ^ sg)), p.kx[RB + 1]);
+                        t = fmaf(x[0], p.kx[RB], t);
+                        if constexpr (KB == 5) t = fmaf(__fadd_rn(x[2], __uint_as_float(__float_as_uint(x[-2]) ^ sg)), p.kx[RB + 2], t);
+                        acc[o] = t;
+                    }
+                    done = true;
+                }
+            }
+            if (!done) {
+#pragma unroll
+                for (int o = 0; o < NO; o++) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int i = 0; i < KB; i++) t = fmaf(win[OFF + o + i], p.kx[i], t);
+                    acc[o] = t;
+                }
+            }
+            float4* mp = (float4*)(s_mid + r * SF_TW + g * NO);
+            mp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            if constexpr (NO == 8) mp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+    }
+    __syncthreads();
+
+    // ---- column pass: item = CW columns x R rows; the R + KB - 1 mid rows it needs are held in registers ----
+    {
+        constexpr int CW = KB <= 15 ? 4 : 2, R = KB == 11 ? 4 : 8;   // window: (R + KB - 1) x CW registers, sized for 3 (KB <= 11) or 2 CTAs per SM
+        constexpr int IPR = SF_TW / CW;                   // items per row group
+        const bool dvec = (((uintptr_t)dst.data | dst.step | dst.fstep) & (CW * sizeof(DT) - 1)) == 0;
+        const bool gvec = p.has_dog && (((uintptr_t)p.dog.data | p.dog.step | p.dog.fstep) & (CW * 4 - 1)) == 0;
+#pragma unroll 1
+        for (int it = tid; it < IPR * (SF_TH / R); it += 256) {
+            const int q = it / IPR, cg = it - q * IPR;
+            const float* mbase = s_mid + (q * R) * SF_TW + cg * CW;
+            float win[R + KB - 1][CW];
+#pragma unroll
+            for (int m = 0; m < R + KB - 1; m++) {
+                if constexpr (CW == 4) {
+                    const float4 v = *(const float4*)(mbase + m * SF_TW);
+                    win[m][0] = v.x; win[m][1] = v.y; win[m][2] = v.z; win[m][3] = v.w;
+                } else {
+                    const float2 v = *(const float2*)(mbase + m * SF_TW);
+                    win[m][0] = v.x; win[m][1] = v.y;
+                }
+            }
+            const int gx = x0 + cg * CW;
+            if (gx >= p.W) continue;
+#pragma unroll
+            for (int o = 0; o < R; o++) {
+                const int gy = y0 + q * R + o;
+                if (gy >= p.H) break;
+                float acc[CW];
+#pragma unroll
+                for (int c = 0; c < CW; c++) {
+                    float t = fmaf(p.ky[RB], win[o + RB][c], p.delta);
+#pragma unroll
+                    for (int k = 1; k <= RB; k++)
+                        t = fmaf(p.ky[RB + k], __fadd_rn(win[o + RB + k][c], __uint_as_float(__float_as_uint(win[o + RB - k][c]) ^ p.col_sign)), t);
+                    acc[c] = t;
+                }
+                if constexpr (sizeof(DT) == 1) {
+                    uchar* dp = dst.row<uchar>(f, gy) + gx;
+                    uint32_t pk = 0;
+#pragma unroll
+                    for (int c = 0; c < CW; c++) pk |= (uint32_t)sat_u8(acc[c]) << (8 * c);
+                    if (dvec && gx + CW <= p.W) {
+                        if constexpr (CW == 4) *(uint32_t*)dp = pk; else *(unsigned short*)dp = (unsigned short)pk;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CW; c++) if (gx + c < p.W) dp[c] = (uchar)(pk >> (8 * c));
+                    }
+                } else {
+                    float* dp = dst.row<float>(f, gy) + gx;
+                    if (dvec && gx + CW <= p.W) {
+                        if constexpr (CW == 4) *(float4*)dp = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        else *(float2*)dp = make_float2(acc[0], acc[1]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CW; c++) if (gx + c < p.W) dp[c] = acc[c];
+                    }
+                    if constexpr (sizeof(ST) == 4) {
+                        if (p.has_dog) {
+                            const float* ctr = (const float*)s_in + (q * R + o + RB) * SF_IW + RA + cg * CW;
+                            float* gp = p.dog.row<float>(f, gy) + gx;
+                            if (gvec && gx + CW <= p.W) {
+                                if constexpr (CW == 4)
+                                    *(float4*)gp = make_float4(__fsub_rn(acc[0], ctr[0]), __fsub_rn(acc[1], ctr[1]), __fsub_rn(acc[2], ctr[2]), __fsub_rn(acc[3], ctr[3]));
+                                else *(float2*)gp = make_float2(__fsub_rn(acc[0], ctr[0]), __fsub_rn(acc[1], ctr[1]));
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < CW; c++) if (gx + c < p.W) gp[c] = __fsub_rn(acc[c], ctr[c]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int KB, typename ST, typename DT>
+static int launch_sf32_tile(const CUtensorMap& tm, const Img& d, const SF32Params& p, int frames, cudaStream_t st)
+{
+    constexpr int IH = SF_TH + KB - 1;
+    const size_t smem = (((size_t)IH * SF_IW * sizeof(ST) + 127) & ~(size_t)127) + (size_t)IH * SF_TW * sizeof(float);
+    auto kern = sep_f32_tile_kernel<KB, ST, DT>;
+    static PerDeviceFlag attr_pd; bool& attr = attr_pd.cur();
+    if (!attr) { B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    dim3 grid(div_up((unsigned)p.W, SF_TW), div_up((unsigned)p.H, SF_TH), (unsigned)frames);
+    kern<<<grid, 256, smem, st>>>(tm, d, p);
+    cudaError_t e = cudaGetLastError();
+    count_launch();
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch", __FILE__, __LINE__);
+    return B200CV_OK;
+}
+
+
 // Kernels of 13 taps and more WALK DOWN a column strip (p.nch chunks of SF_TH output rows per CTA): the SF_TH + KB - 1 row-filtered rows behind
 // a chunk stay in shared memory, the last KB - 1 of them move to the top for the next chunk (a 20-word copy per thread), and every chunk after
 // the first stages and row-filters only its SF_TH new source rows -- the plain tile kernel filtered SF_TH + KB - 1 rows for SF_TH outputs
@@ -320,11 +518,11 @@ static int sep_float_fast(const Img& s, const Img& d, const float* kx, int nx, c
     if (rc) return rc;
     if ((rc = make_tensor_map_3d(&tm_tail, s.data, (int)sizeof(ST), s.cols, s.rows, s.frames, s.step, s.fstep, SF_IW, KB - 1))) return rc;
     switch (KB) {
-    case 3: return launch_sf32<3, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
-    case 5: return launch_sf32<5, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
-    case 7: return launch_sf32<7, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
-    case 9: return launch_sf32<9, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
-    case 11: return launch_sf32<11, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
+    case 3: return launch_sf32_tile<3, ST, DT>(tm, d, p, s.frames, st);
+    case 5: return launch_sf32_tile<5, ST, DT>(tm, d, p, s.frames, st);
+    case 7: return launch_sf32_tile<7, ST, DT>(tm, d, p, s.frames, st);
+    case 9: return launch_sf32_tile<9, ST, DT>(tm, d, p, s.frames, st);
+    case 11: return launch_sf32_tile<11, ST, DT>(tm, d, p, s.frames, st);
     case 13: return launch_sf32<13, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
     case 15: return launch_sf32<15, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);
     case 17: return launch_sf32<17, ST, DT>(tm, tm_tail, s, d, p, s.frames, st);

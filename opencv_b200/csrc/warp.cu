@@ -77,11 +77,15 @@ __device__ __forceinline__ void warp_coords(const WarpParams& p, int x, int y, i
     }
 }
 
-// one destination pixel gathered straight from global memory, all border modes
+// one destination pixel gathered straight from global memory, all border modes.  Returns false when the pixel is to be left untouched
+// (BORDER_TRANSPARENT: remapNearest imgwarp.cpp:373,408; remapBilinear :788-815 -- a point inside the image that lacks some of its four
+// neighbours is blended from the ones that exist, re-normalised; remapBicubic :925,965-968 -- centre outside: untouched, else REFLECT_101 taps)
 template <typename T, int CN, int INTERP>
-__device__ __forceinline__ void sample_direct(const Img& src, int f, const WarpParams& p, int sx, int sy, int a, T* d)
+__device__ __forceinline__ bool sample_direct(const Img& src, int f, const WarpParams& p, int sx, int sy, int a, T* d)
 {
-    const int sw = p.sw, sh = p.sh, border = p.border;
+    const int sw = p.sw, sh = p.sh;
+    const bool transparent = p.border == B200CV_BORDER_TRANSPARENT;
+    const int border = (transparent && INTERP == W_CUB) ? B200CV_BORDER_REFLECT_101 : p.border;
     T cval[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) { if constexpr (sizeof(T) == 1) cval[c] = (T)p.cval_i[c]; else cval[c] = p.cval_f[c]; }
@@ -89,21 +93,58 @@ __device__ __forceinline__ void sample_direct(const Img& src, int f, const WarpP
     if constexpr (INTERP == W_NN) {
         const T* s;
         if ((unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh) s = src.row<T>(f, sy) + (size_t)sx * CN;
+        else if (transparent) return false;
         else if (border == B200CV_BORDER_REPLICATE) s = src.row<T>(f, clipi(sy, 0, sh)) + (size_t)clipi(sx, 0, sw) * CN;
         else if (border == B200CV_BORDER_CONSTANT) s = nullptr;
         else s = src.row<T>(f, border_interpolate(sy, sh, border)) + (size_t)border_interpolate(sx, sw, border) * CN;
 #pragma unroll
         for (int c = 0; c < CN; c++) d[c] = s ? s[c] : cval[c];
+        return true;
     } else if constexpr (INTERP == W_LIN) {
         typedef typename TabOf<T>::type AT;
         const AT* w = TabOf<T>::lin() + a * 4;
         if (border == B200CV_BORDER_CONSTANT && (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0)) {
 #pragma unroll
             for (int c = 0; c < CN; c++) d[c] = cval[c];
-            return;
+            return true;
+        }
+        const bool inl = (unsigned)sx < (unsigned)max(sw - 1, 0) && (unsigned)sy < (unsigned)max(sh - 1, 0);
+        if (transparent && !inl) {
+            if (!(sx >= 0 && sx <= sw - 1 && sy >= 0 && sy <= sh - 1)) return false;
+            const bool e1 = sx < sw - 1, e2 = sy < sh - 1;
+            const T* S = src.row<T>(f, sy) + (size_t)sx * CN;
+            const T* S1 = e2 ? src.row<T>(f, sy + 1) + (size_t)sx * CN : S;
+            if constexpr (sizeof(T) == 1) {
+                int w_tot = w[0]; if (e1) w_tot += w[1]; if (e2) w_tot += w[2]; if (e1 && e2) w_tot += w[3];
+                if (w_tot == 0) return false;
+                const int w_ini = (int)w[0] + w[1] + w[2] + w[3];
+#pragma unroll
+                for (int c = 0; c < CN; c++) {
+                    int t0 = S[c] * w[0];
+                    if (e1) t0 += S[c + CN] * w[1];
+                    if (e2) t0 += S1[c] * w[2];
+                    if (e1 && e2) t0 += S1[c + CN] * w[3];
+                    t0 = (int)__fdiv_rn(__fmul_rn((float)t0, (float)w_ini), (float)w_tot);      // (WT)(t0 * (float)w_tot_ini / w_tot), WT = int: truncation
+                    d[c] = sat_u8((t0 + (1 << 14)) >> 15);
+                }
+            } else {
+                float w_tot = 0.f;
+                w_tot = __fadd_rn(w_tot, w[0]); if (e1) w_tot = __fadd_rn(w_tot, w[1]); if (e2) w_tot = __fadd_rn(w_tot, w[2]); if (e1 && e2) w_tot = __fadd_rn(w_tot, w[3]);
+                if (w_tot == 0.f) return false;
+                const float w_ini = __fadd_rn(__fadd_rn(__fadd_rn(w[0], w[1]), w[2]), w[3]);
+#pragma unroll
+                for (int c = 0; c < CN; c++) {
+                    float t0 = __fadd_rn(0.f, __fmul_rn(S[c], w[0]));
+                    if (e1) t0 = __fadd_rn(t0, __fmul_rn(S[c + CN], w[1]));
+                    if (e2) t0 = __fadd_rn(t0, __fmul_rn(S1[c], w[2]));
+                    if (e1 && e2) t0 = __fadd_rn(t0, __fmul_rn(S1[c + CN], w[3]));
+                    d[c] = __fdiv_rn(__fmul_rn(t0, w_ini), w_tot);
+                }
+            }
+            return true;
         }
         int sx0, sx1, sy0, sy1;
-        if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) { sx0 = sx; sx1 = sx + 1; sy0 = sy; sy1 = sy + 1; }
+        if (inl) { sx0 = sx; sx1 = sx + 1; sy0 = sy; sy1 = sy + 1; }
         else if (border == B200CV_BORDER_REPLICATE) { sx0 = clipi(sx, 0, sw); sx1 = clipi(sx + 1, 0, sw); sy0 = clipi(sy, 0, sh); sy1 = clipi(sy + 1, 0, sh); }
         else {
             sx0 = border_interpolate(sx, sw, border); sx1 = border_interpolate(sx + 1, sw, border);
@@ -120,15 +161,17 @@ __device__ __forceinline__ void sample_direct(const Img& src, int f, const WarpP
             if constexpr (sizeof(T) == 1) d[c] = sat_u8((v0 * w[0] + v1 * w[1] + v2 * w[2] + v3 * w[3] + (1 << 14)) >> 15);
             else d[c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(v0, w[0]), __fmul_rn(v1, w[1])), __fmul_rn(v2, w[2])), __fmul_rn(v3, w[3]));
         }
+        return true;
     } else {
         typedef typename TabOf<T>::type AT;
         const AT* w = TabOf<T>::cub() + a * 16;
         sx -= 1; sy -= 1;
         const bool inlier = (unsigned)sx < (unsigned)max(sw - 3, 0) && (unsigned)sy < (unsigned)max(sh - 3, 0);
+        if (!inlier && transparent && ((unsigned)(sx + 1) >= (unsigned)sw || (unsigned)(sy + 1) >= (unsigned)sh)) return false;
         if (!inlier && border == B200CV_BORDER_CONSTANT && (sx >= sw || sx + 4 <= 0 || sy >= sh || sy + 4 <= 0)) {
 #pragma unroll
             for (int c = 0; c < CN; c++) d[c] = cval[c];
-            return;
+            return true;
         }
         int xs[4], ys[4];
 #pragma unroll
@@ -176,6 +219,7 @@ __device__ __forceinline__ void sample_direct(const Img& src, int f, const WarpP
             }
         }
     }
+    return true;
 }
 
 template <typename T, int CN, int INTERP>
@@ -186,7 +230,12 @@ __global__ void __launch_bounds__(256) warp_kernel(Img src, Img dst, const __gri
     if (x >= p.dw) return;
     int sx, sy, a;
     warp_coords<INTERP>(p, x, y, sx, sy, a);
-    sample_direct<T, CN, INTERP>(src, f, p, sx, sy, a, dst.row<T>(f, y) + (size_t)x * CN);
+    T v[4];
+    if (sample_direct<T, CN, INTERP>(src, f, p, sx, sy, a, v)) {        // false: BORDER_TRANSPARENT leaves the destination pixel as it is
+        T* d = dst.row<T>(f, y) + (size_t)x * CN;
+#pragma unroll
+        for (int c = 0; c < CN; c++) d[c] = v[c];
+    }
 }
 
 
@@ -399,6 +448,198 @@ __global__ void __launch_bounds__(256) warp_tile_kernel(Img src, Img dst, const 
     }
 }
 
+// ---- 8-bit LINEAR / CUBIC, second version of the tiled kernel -------------------------------------------------------------------------------
+// Same staging and the same sampling arithmetic as warp_tile_kernel; what changes is how the work is cut (profiles/r02_prof_c3_geom: the first
+// version executed 203 (LINEAR) to 345 (CUBIC, projective) thread instructions per pixel at 85 % issue utilisation, most of them not sampling):
+//   * tile 128 x 32 instead of 64 x 16: the per-thread fixed costs (corner coordinates, tables, staged-row pointers and border tests) are
+//     spread over 16 pixels per thread instead of 4; the footprint of an 8UC3 tile is still only ~25 KB
+//   * a thread produces 4 consecutive pixels of a row: their bytes leave as CN aligned 32-bit stores (12 bytes of an 8UC3 row per thread, a
+//     warp writes 384 contiguous bytes) instead of 4 CN byte stores
+//   * projective maps: X0, Y0, W0 = M * (x_block, y, 1) are per (row, 64-column block) values (the reference evaluates them once per block
+//     line, imgwarp.cpp:3182-3206): built once per tile in shared memory; per pixel remain the divide and two multiply-adds in fp64
+constexpr int WQ_W = 128, WQ_H = 32, WQ_NB = 4;      // WQ_NB: 64-column blocks a tile row can touch (+1 for maps with other block widths)
+
+template <int CN, int INTERP>
+__device__ __forceinline__ void sample_staged_u8(const unsigned char* s_src, int pitch, int lx, int ly, int a, unsigned char* d)
+{
+    if constexpr (INTERP == W_LIN) {
+        const int2 w = __ldg((const int2*)(g_bilin_i + a * 4));           // (w0, w1), (w2, w3) as s16 pairs
+        const unsigned A = (unsigned)(ly * pitch + lx * CN), sh8 = 8 * (A & 3);
+        constexpr int NW = (2 * CN + 3) / 4;                              // words that hold one realigned tap row
+        unsigned r0[4], r1[4];
+        const unsigned* q0 = (const unsigned*)(s_src + (A & ~3u));
+        const unsigned* q1 = (const unsigned*)(s_src + (A & ~3u) + pitch);
+#pragma unroll
+        for (int i = 0; i < NW; i++) { r0[i] = __funnelshift_r(q0[i], q0[i + 1], sh8); r1[i] = __funnelshift_r(q1[i], q1[i + 1], sh8); }
+#pragma unroll
+        for (int c = 0; c < CN; c++) {
+            int sum = dp2a_lo_su(w.x, tap_pair<CN>(r0, c, 0), 1 << 14);
+            sum = dp2a_lo_su(w.y, tap_pair<CN>(r1, c, 0), sum);
+            d[c] = sat_u8(sum >> 15);
+        }
+    } else {
+        int w[8];                                                          // 16 s16 weights: row i = (w[2i], w[2i+1])
+        *(uint4*)w = __ldg((const uint4*)(g_bicub_i + a * 16));
+        *(uint4*)(w + 4) = __ldg((const uint4*)(g_bicub_i + a * 16 + 8));
+        const unsigned A = (unsigned)(ly * pitch + lx * CN), sh8 = 8 * (A & 3);
+        constexpr int NW = (4 * CN + 3) / 4;
+        int sum[CN];
+#pragma unroll
+        for (int c = 0; c < CN; c++) sum[c] = 1 << 14;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned* q = (const unsigned*)(s_src + (A & ~3u) + i * pitch);
+            unsigned r[4];
+#pragma unroll
+            for (int k = 0; k < NW; k++) r[k] = __funnelshift_r(q[k], q[k + 1], sh8);
+#pragma unroll
+            for (int c = 0; c < CN; c++) sum[c] = dp2a_lo_su(w[2 * i + 1], tap_pair<CN>(r, c, 2), dp2a_lo_su(w[2 * i], tap_pair<CN>(r, c, 0), sum[c]));
+        }
+#pragma unroll
+        for (int c = 0; c < CN; c++) d[c] = sat_u8(sum[c] >> 15);
+    }
+}
+
+template <int CN, int INTERP>
+__global__ void __launch_bounds__(256) warp_tile4_kernel(Img src, Img dst, const __grid_constant__ WarpParams p, int smem_cap)
+{
+    typedef unsigned char T;
+    extern __shared__ __align__(16) unsigned char s_src[];
+    __shared__ int s_box[4];
+    __shared__ __align__(16) int s_ad[WQ_W], s_bd[WQ_W];
+    __shared__ int s_X0[WQ_H], s_Y0[WQ_H];                               // affine: the reference's adelta / bdelta and per-row X0 / Y0 tables
+    __shared__ double s_pX[WQ_H][WQ_NB], s_pY[WQ_H][WQ_NB], s_pW[WQ_H][WQ_NB];   // projective: M * (x_block, y, 1) per row and column block
+    constexpr int ES = CN;
+    constexpr int K0 = INTERP == W_CUB ? -1 : 0, K1 = INTERP == W_LIN ? 1 : 2;
+    const int f = blockIdx.z, x0 = blockIdx.x * WQ_W, y0 = blockIdx.y * WQ_H;
+    const int tid = threadIdx.x;
+    const int blk0 = x0 / p.bw0;
+    if (tid < 32) {
+        const int cx = (tid & 1) ? min(x0 + WQ_W, p.dw) - 1 : x0, cy = (tid & 2) ? min(y0 + WQ_H, p.dh) - 1 : y0;
+        int sx, sy, a;
+        warp_coords<INTERP>(p, cx, cy, sx, sy, a);
+        int mnx = sx, mxx = sx, mny = sy, mxy = sy;
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        }
+        if (tid == 0) { s_box[0] = (mnx + K0) & ~15; s_box[1] = mny + K0; s_box[2] = mxx + K1; s_box[3] = mxy + K1; }
+    } else if (!p.persp) {
+        // fp64 once per tile column / row instead of once per pixel (hal::warpAffine builds the same tables on the host, imgwarp.cpp:2673-2700)
+        const int t = tid - 32;
+        if (t < WQ_W) {
+            const double x = (double)(x0 + t);
+            s_ad[t] = __double2int_rn(__dmul_rn(__dmul_rn(p.M[0], x), 1024.0));
+            s_bd[t] = __double2int_rn(__dmul_rn(__dmul_rn(p.M[3], x), 1024.0));
+        } else if (t < WQ_W + WQ_H) {
+            const double y = (double)(y0 + t - WQ_W);
+            s_X0[t - WQ_W] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(p.M[1], y), p.M[2]), 1024.0)) + 16;
+            s_Y0[t - WQ_W] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(p.M[4], y), p.M[5]), 1024.0)) + 16;
+        }
+    } else {
+        const int t = tid - 32;
+        if (t < WQ_H * WQ_NB) {
+            const int yy = t / WQ_NB, b = t - yy * WQ_NB;
+            const double xb = (double)((blk0 + b) * p.bw0), y = (double)(y0 + yy);
+            s_pX[yy][b] = __dadd_rn(__dadd_rn(__dmul_rn(p.M[0], xb), __dmul_rn(p.M[1], y)), p.M[2]);
+            s_pY[yy][b] = __dadd_rn(__dadd_rn(__dmul_rn(p.M[3], xb), __dmul_rn(p.M[4], y)), p.M[5]);
+            s_pW[yy][b] = __dadd_rn(__dadd_rn(__dmul_rn(p.M[6], xb), __dmul_rn(p.M[7], y)), p.M[8]);
+        }
+    }
+    __syncthreads();
+    const int bx0 = s_box[0], by0 = s_box[1];
+    const int bw = (s_box[2] - bx0 + 16) & ~15, bh = s_box[3] - by0 + 1;        // staged pixels per row (multiple of 16), rows
+    const int nvec = bw * ES / 16;                                              // 16-byte vectors per staged row
+    const int pitch = (nvec | 1) * 16;                                          // odd number of vectors: rows start on different banks
+    const bool staged = (long long)pitch * bh <= smem_cap;
+    const int sw = p.sw, sh = p.sh, border = p.border;
+
+    if (staged) {
+        // one warp per staged row (row-uniform work hoisted), lanes over its 16-byte vectors
+        const bool aligned = (((uintptr_t)src.data | src.step | src.fstep) & 15) == 0;
+        const int gb0 = bx0 * ES;                                               // byte offset of the staged row start inside a source row
+        const int row_bytes = sw * ES;
+        const bool cfill = border == B200CV_BORDER_CONSTANT && p.cval_i[0] == p.cval_i[1] && p.cval_i[1] == p.cval_i[2] && p.cval_i[2] == p.cval_i[3];
+        const unsigned cword = (unsigned)(p.cval_i[0] & 255) * 0x01010101u;
+        for (int r = tid >> 5; r < bh; r += 8) {
+            int sy = by0 + r;
+            if ((unsigned)sy >= (unsigned)sh) sy = border == B200CV_BORDER_REPLICATE ? clipi(sy, 0, sh) : border_interpolate(sy, sh, border);
+            const unsigned char* srow = sy >= 0 ? (const unsigned char*)src.row<T>(f, sy) : nullptr;
+            unsigned char* drow = s_src + r * pitch;
+            for (int j = tid & 31; j < nvec; j += 32) {
+                const int gb = gb0 + j * 16;                                    // first byte of this vector within the source row
+                uint4 val;
+                if (srow && aligned && gb >= 0 && gb + 16 <= row_bytes) {
+                    val = *(const uint4*)(srow + gb);
+                } else if (cfill && (!srow || gb + 16 <= 0 || gb >= row_bytes)) {
+                    val = make_uint4(cword, cword, cword, cword);
+                } else {
+                    T e[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int ge = gb + i;                                  // element index in the row (may be negative; gb is a multiple of 16)
+                        const int px = ge >= 0 ? ge / CN : -((-ge + CN - 1) / CN);
+                        const int c = ge - px * CN;
+                        int sx = px;
+                        if ((unsigned)sx >= (unsigned)sw) sx = border == B200CV_BORDER_REPLICATE ? clipi(sx, 0, sw) : border_interpolate(sx, sw, border);
+                        e[i] = (srow && sx >= 0) ? srow[sx * CN + c] : (T)p.cval_i[c];
+                    }
+                    val = *(const uint4*)e;
+                }
+                *(uint4*)(drow + j * 16) = val;
+            }
+        }
+    }
+    __syncthreads();
+
+    const bool dvec = (((uintptr_t)dst.data | dst.step | dst.fstep) & 3) == 0;
+#pragma unroll 1
+    for (int g = tid; g < (WQ_W / 4) * WQ_H; g += 256) {
+        const int yy = g / (WQ_W / 4), xq = (g - yy * (WQ_W / 4)) * 4;
+        const int y = y0 + yy, x = x0 + xq;
+        if (y >= p.dh || x >= p.dw) continue;
+        int4 ad = make_int4(0, 0, 0, 0), bd = ad;
+        int X0r = 0, Y0r = 0;
+        if (!p.persp) { ad = *(const int4*)(s_ad + xq); bd = *(const int4*)(s_bd + xq); X0r = s_X0[yy]; Y0r = s_Y0[yy]; }
+        const int adv[4] = {ad.x, ad.y, ad.z, ad.w}, bdv[4] = {bd.x, bd.y, bd.z, bd.w};
+        unsigned char ob[4 * CN];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int sx, sy, a;
+            if (p.persp) {
+                const int xx = x + k, b = xx / p.bw0 - blk0, x1 = xx - (blk0 + b) * p.bw0;
+                double W = __dadd_rn(s_pW[yy][b], __dmul_rn(p.M[6], (double)x1));
+                W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
+                const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(s_pX[yy][b], __dmul_rn(p.M[0], (double)x1)), W)));
+                const double fY = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(s_pY[yy][b], __dmul_rn(p.M[3], (double)x1)), W)));
+                const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+                sx = sat_s16(X >> 5); sy = sat_s16(Y >> 5); a = (Y & 31) * 32 + (X & 31);
+            } else {
+                const int XX = X0r + adv[k], YY = Y0r + bdv[k];
+                sx = sat_s16(XX >> 10); sy = sat_s16(YY >> 10); a = ((YY >> 5) & 31) * 32 + ((XX >> 5) & 31);
+            }
+            const int lx = sx + K0 - bx0, ly = sy + K0 - by0;            // first tap, staged coordinates
+            unsigned char px[4] = {0, 0, 0, 0};
+            if (x + k < p.dw) {
+                if (!staged || lx < 0 || ly < 0 || lx + (K1 - K0) >= bw || ly + (K1 - K0) >= bh) sample_direct<T, CN, INTERP>(src, f, p, sx, sy, a, px);
+                else sample_staged_u8<CN, INTERP>(s_src, pitch, lx, ly, a, px);
+            }
+#pragma unroll
+            for (int c = 0; c < CN; c++) ob[k * CN + c] = px[c];
+        }
+        unsigned char* dp = dst.row<T>(f, y) + (size_t)x * CN;
+        if (dvec && x + 4 <= p.dw) {
+#pragma unroll
+            for (int i = 0; i < CN; i++)
+                ((unsigned*)dp)[i] = (unsigned)ob[4 * i] | ((unsigned)ob[4 * i + 1] << 8) | ((unsigned)ob[4 * i + 2] << 16) | ((unsigned)ob[4 * i + 3] << 24);
+        } else {
+            const int n = min(4, p.dw - x);
+            for (int i = 0; i < n * CN; i++) dp[i] = ob[i];
+        }
+    }
+}
+
 static int ensure_warp_tables()
 {
     static PerDeviceFlag done_pd; bool& done = done_pd.cur();
@@ -415,11 +656,11 @@ static int ensure_warp_tables()
 }
 
 // host estimate of the staged footprint (bytes) of one 64x16 tile whose first pixel is (x0, y0); < 0: do not stage
-static long long tile_footprint(const WarpParams& p, int x0, int y0, int es, int taps)
+static long long tile_footprint(const WarpParams& p, int x0, int y0, int es, int taps, int TW = WT_W, int TH = WT_H)
 {
     double mnx = 1e300, mxx = -1e300, mny = 1e300, mxy = -1e300;
     for (int k = 0; k < 4; k++) {
-        double x = (k & 1) ? std::min(x0 + WT_W, p.dw) - 1 : x0, y = (k & 2) ? std::min(y0 + WT_H, p.dh) - 1 : y0;
+        double x = (k & 1) ? std::min(x0 + TW, p.dw) - 1 : x0, y = (k & 2) ? std::min(y0 + TH, p.dh) - 1 : y0;
         double X = p.M[0] * x + p.M[1] * y + p.M[2], Y = p.M[3] * x + p.M[4] * y + p.M[5], W = p.persp ? p.M[6] * x + p.M[7] * y + p.M[8] : 1.0;
         if (!(fabs(W) > 1e-12)) return -1;
         X /= W; Y /= W;
@@ -448,11 +689,35 @@ static int launch_warp_i(const Img& s, const Img& d, const WarpParams& p, cudaSt
         }
     const char* path = getenv("B200CV_WARP_PATH");
     // one tap per pixel (NEAREST) does not repay the staging pass
-    if (INTERP == W_NN || need < 0 || need > WT_SMEM_MAX || (path && !strcmp(path, "direct"))) {          // heavy minification / degenerate map: direct gather
+    // BORDER_TRANSPARENT: per-pixel keep / blend decisions, the direct kernel only
+    if (INTERP == W_NN || need < 0 || need > WT_SMEM_MAX || p.border == B200CV_BORDER_TRANSPARENT || (path && !strcmp(path, "direct"))) {          // heavy minification / degenerate map: direct gather
         dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
         warp_kernel<T, CN, INTERP><<<grid, 256, 0, st>>>(s, d, p);
         B200_LAUNCH_CHECK();
         return B200CV_OK;
+    }
+    if constexpr (sizeof(T) == 1 && INTERP != W_NN) {
+        // 8-bit LINEAR / CUBIC: the 128 x 32 tile kernel when its footprint fits and a tile row touches at most WQ_NB column blocks
+        const int qx = (int)div_up((unsigned)p.dw, WQ_W), qy = (int)div_up((unsigned)p.dh, WQ_H);
+        long long need4 = 0;
+        const int msx = p.persp ? std::min(qx, 9) : 1, msy = p.persp ? std::min(qy, 9) : 1;
+        for (int j = 0; j < msy && need4 >= 0; j++)
+            for (int i = 0; i < msx; i++) {
+                int bx = msx > 1 ? (int)((long long)i * (qx - 1) / (msx - 1)) : 0, by = msy > 1 ? (int)((long long)j * (qy - 1) / (msy - 1)) : 0;
+                long long fp = tile_footprint(p, bx * WQ_W, by * WQ_H, es, taps, WQ_W, WQ_H);
+                if (fp < 0) { need4 = -1; break; }
+                need4 = std::max(need4, fp);
+            }
+        const bool blocks_ok = !p.persp || (p.bw0 > 0 && (WQ_W + p.bw0 - 1) / p.bw0 + 1 <= WQ_NB);
+        if (need4 > 0 && need4 <= WT_SMEM_MAX && blocks_ok && !(path && !strcmp(path, "tile64"))) {
+            int smem4 = (int)std::min<long long>(WT_SMEM_MAX, std::max<long long>(need4 + need4 / 8, 8 * 1024));
+            auto kern4 = warp_tile4_kernel<CN, INTERP>;
+            static PerDeviceFlag attr4_pd; bool& attr4 = attr4_pd.cur();
+            if (!attr4) { B200_CUDA(cudaFuncSetAttribute(kern4, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_MAX)); attr4 = true; }
+            kern4<<<dim3((unsigned)qx, (unsigned)qy, (unsigned)s.frames), 256, smem4, st>>>(s, d, p, smem4);
+            B200_LAUNCH_CHECK();
+            return B200CV_OK;
+        }
     }
     int smem = (int)std::min<long long>(WT_SMEM_MAX, std::max<long long>(need + need / 8, 8 * 1024));
     auto kern = warp_tile_kernel<T, CN, INTERP>;
@@ -503,7 +768,12 @@ __global__ void __launch_bounds__(256) remap_kernel(Img src, Img dst, Img m1, Im
             a = (iy & 31) * 32 + (ix & 31);
         }
     }
-    sample_direct<T, CN, INTERP>(src, f, p, sx, sy, a, dst.row<T>(f, y) + (size_t)x * CN);
+    T v[4];
+    if (sample_direct<T, CN, INTERP>(src, f, p, sx, sy, a, v)) {
+        T* d = dst.row<T>(f, y) + (size_t)x * CN;
+#pragma unroll
+        for (int c = 0; c < CN; c++) d[c] = v[c];
+    }
 }
 
 template <typename T, int CN>
@@ -530,7 +800,7 @@ static int warp_common(const b200cvMat* src, const b200cvMat* dst, const double*
     if (interp == B200CV_INTER_AREA) interp = B200CV_INTER_LINEAR;            // imgwarp.cpp:2816, :3393
     if (interp > B200CV_INTER_CUBIC) return B200CV_NOT_IMPLEMENTED;
     border &= ~B200CV_BORDER_ISOLATED;
-    if (border < 0 || border > B200CV_BORDER_REFLECT_101) return B200CV_NOT_IMPLEMENTED;   // BORDER_TRANSPARENT: not on the device path
+    if (border < 0 || border > B200CV_BORDER_TRANSPARENT) return B200CV_NOT_IMPLEMENTED;
     if (src->cols >= 32767 || src->rows >= 32767 || dst->rows >= 65536) return B200CV_NOT_IMPLEMENTED;   // CV_Assert(cols,rows < SHRT_MAX) imgwarp.cpp:1813
     if ((rc = ensure_warp_tables())) return rc;
     Img s = make_img(src), d = make_img(dst);
@@ -628,7 +898,7 @@ extern "C" int b200cv_remap(const b200cvMat* src, const b200cvMat* dst, const b2
     if (interp > B200CV_INTER_CUBIC) return B200CV_NOT_IMPLEMENTED;
     if (kind == MAP_FIXED && !has2 && interp != B200CV_INTER_NEAREST) return B200CV_ERR_BAD_ARG;
     border &= ~B200CV_BORDER_ISOLATED;
-    if (border < 0 || border > B200CV_BORDER_REFLECT_101) return B200CV_NOT_IMPLEMENTED;
+    if (border < 0 || border > B200CV_BORDER_TRANSPARENT) return B200CV_NOT_IMPLEMENTED;
     if (src->cols >= 32767 || src->rows >= 32767 || dst->cols >= 32767 || dst->rows >= 32767) return B200CV_NOT_IMPLEMENTED;   // CV_Assert(... < SHRT_MAX), :1810
     if ((rc = ensure_warp_tables())) return rc;
     Img s = make_img(src), d = make_img(dst), m1 = make_img(map1), m2;

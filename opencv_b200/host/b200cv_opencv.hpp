@@ -5,7 +5,7 @@
 //   namespace b200cv::cuda   what a user of cv::cuda:: switches to (rename the namespace, keep the code): the reference signatures of
 //       GaussianBlur / sepFilter2D / filter2D / Sobel / resize / warpAffine / warpPerspective / cvtColor / matchTemplate / cornerHarris /
 //       cornerMinEigenVal / goodFeaturesToTrack (imgproc.hpp:1544,1723,1702,1862,2422,2450,2482,3736,3916,1948,1921,2096) + Stream&, and
-//       createGaussianFilter / createSeparableLinearFilter / createLinearFilter / createSobelFilter -> Ptr<Filter>, Filter::apply(InputArray,
+//       GFTTDetector (features2d/src/gftt.cpp), createGaussianFilter / createSeparableLinearFilter / createLinearFilter / createSobelFilter -> Ptr<Filter>, Filter::apply(InputArray,
 //       OutputArray, Stream&) -- the usage of samples/cpp/tutorial_code/gpu/gpu-basics-similarity/gpu-basics-similarity.cpp:392-404.
 //   Array kinds accepted (core/include/opencv2/core/mat.hpp:163-188):
 //       CUDA_GPU_MAT   cv::cuda::GpuMat (fields read directly: data, step, rows, cols, flags) -> device path, asynchronous on the Stream
@@ -25,6 +25,7 @@
 #include <unordered_map>
 #include <opencv2/core.hpp>
 #include <opencv2/core/cuda.hpp>
+#include <opencv2/imgproc.hpp>       // the cv:: enums (interpolation, border, colour codes) the signatures default to
 
 namespace b200cv {
 
@@ -324,6 +325,55 @@ inline cv::Ptr<Filter> createSobelFilter(int srcType, int dstType, int dx, int d
     (void)srcType; (void)columnBorderMode;
     cv::Ptr<F> f = cv::makePtr<F>(); f->dd = dstType < 0 ? -1 : CV_MAT_DEPTH(dstType); f->dx = dx; f->dy = dy; f->ks = ksize; f->sc = scale; f->b = rowBorderMode; return f;
 }
+
+// ---- cv::GFTTDetector (features2d/include/opencv2/features2d.hpp; features2d/src/gftt.cpp:33-176): the Feature2D face of goodFeaturesToTrack ------
+// create(...) with the reference's two argument lists, the set / get pairs, detect(image, keypoints, mask): colour images go through BGR2GRAY first,
+// keypoints[i] = KeyPoint(corner, (float)blockSize, -1, quality) (gftt.cpp:131-151).  The image may be a cv::Mat or a cv::cuda::GpuMat.
+class GFTTDetector : public cv::Algorithm {
+public:
+    static cv::Ptr<GFTTDetector> create(int maxCorners = 1000, double qualityLevel = 0.01, double minDistance = 1, int blockSize = 3, bool useHarrisDetector = false, double k = 0.04)
+    { return create(maxCorners, qualityLevel, minDistance, blockSize, 3, useHarrisDetector, k); }
+    static cv::Ptr<GFTTDetector> create(int maxCorners, double qualityLevel, double minDistance, int blockSize, int gradiantSize, bool useHarrisDetector = false, double k = 0.04)
+    {
+        cv::Ptr<GFTTDetector> d = cv::makePtr<GFTTDetector>();
+        d->nfeatures = maxCorners; d->qualityLevel = qualityLevel; d->minDistance = minDistance; d->blockSize = blockSize; d->gradSize = gradiantSize;
+        d->useHarrisDetector = useHarrisDetector; d->k = k;
+        return d;
+    }
+    void setMaxFeatures(int v) { nfeatures = v; }            int getMaxFeatures() const { return nfeatures; }
+    void setQualityLevel(double v) { qualityLevel = v; }     double getQualityLevel() const { return qualityLevel; }
+    void setMinDistance(double v) { minDistance = v; }       double getMinDistance() const { return minDistance; }
+    void setBlockSize(int v) { blockSize = v; }              int getBlockSize() const { return blockSize; }
+    void setGradientSize(int v) { gradSize = v; }            int getGradientSize() { return gradSize; }
+    void setHarrisDetector(bool v) { useHarrisDetector = v; } bool getHarrisDetector() const { return useHarrisDetector; }
+    void setK(double v) { k = v; }                           double getK() const { return k; }
+    cv::String getDefaultName() const override { return "Feature2D.GFTTDetector"; }
+
+    void detect(cv::InputArray image, std::vector<cv::KeyPoint>& keypoints, cv::InputArray mask = cv::noArray(), Stream& s = Stream::Null())
+    {
+        keypoints.clear();
+        if (image.empty()) return;
+        if (!mask.empty()) throw NotImplemented(B200CV_NOT_IMPLEMENTED, "GFTTDetector::detect: mask");
+        Arr a = input(image, "GFTTDetector::detect");
+        DeviceMat up, gray;
+        if (!a.device) { up.upload(image, s); a = input(up, "GFTTDetector::detect"); }
+        if (a.m.type != CV_8UC1) {                      // gftt.cpp:138-140
+            b200cv::cuda::cvtColor(a.device && up.empty() ? image : cv::InputArray(up), gray, cv::COLOR_BGR2GRAY, 0, s);
+            a = input(gray, "GFTTDetector::detect");
+        }
+        const int cap = nfeatures > 0 ? nfeatures : a.m.rows * a.m.cols;
+        std::vector<float> pts((size_t)2 * cap), q((size_t)cap);
+        int cnt = 0;
+        check(b200cv_good_features_to_track(&a.m, pts.data(), q.data(), cap, &cnt, nfeatures, qualityLevel, minDistance, blockSize, gradSize, useHarrisDetector ? 1 : 0, k, s.cudaPtr()),
+              "GFTTDetector::detect");
+        cnt = std::min(cnt, cap);
+        keypoints.resize(cnt);
+        for (int i = 0; i < cnt; i++) keypoints[i] = cv::KeyPoint(cv::Point2f(pts[2 * i], pts[2 * i + 1]), (float)blockSize, -1, q[i]);
+    }
+    int nfeatures = 1000, blockSize = 3, gradSize = 3;
+    double qualityLevel = 0.01, minDistance = 1, k = 0.04;
+    bool useHarrisDetector = false;
+};
 
 }  // namespace cuda
 }  // namespace b200cv

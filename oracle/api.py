@@ -173,10 +173,12 @@ class Oracle:
                                        int(op), int(k), dbl(sigma), int(border), int(bool(inplace))), "roi_filter")
         return dst
 
-    def _warp(self, name, src, M, dsize, flags, borderMode, borderValue):
+    def _warp(self, name, src, M, dsize, flags, borderMode, borderValue, dst0=None):
         src = np.ascontiguousarray(src)
         dw, dh = dsize
         dst = np.zeros((dh, dw) + src.shape[2:], src.dtype)
+        if dst0 is not None:            # BORDER_TRANSPARENT: the destination's previous content shows through
+            dst[...] = dst0
         sh, sw = src.shape[:2]
         M = np.ascontiguousarray(M, np.float64)
         bv = np.zeros(4, np.float64)
@@ -185,17 +187,20 @@ class Oracle:
                                _p(M), int(flags), int(borderMode), _p(bv)), name)
         return dst
 
-    def warpAffine(self, src, M, dsize, flags=1, borderMode=0, borderValue=0):
-        return self._warp("warp_affine", src, M, dsize, flags, borderMode, borderValue)
+    def warpAffine(self, src, M, dsize, flags=1, borderMode=0, borderValue=0, dst=None):
+        return self._warp("warp_affine", src, M, dsize, flags, borderMode, borderValue, dst)
 
-    def warpPerspective(self, src, M, dsize, flags=1, borderMode=0, borderValue=0):
-        return self._warp("warp_perspective", src, M, dsize, flags, borderMode, borderValue)
+    def warpPerspective(self, src, M, dsize, flags=1, borderMode=0, borderValue=0, dst=None):
+        return self._warp("warp_perspective", src, M, dsize, flags, borderMode, borderValue, dst)
 
-    def remap(self, src, map1, map2, interpolation, borderMode=0, borderValue=0):
+    def remap(self, src, map1, map2, interpolation, borderMode=0, borderValue=0, dst=None):
         src = np.ascontiguousarray(src); map1 = np.ascontiguousarray(map1)
         map2 = np.ascontiguousarray(map2) if map2 is not None else None
         dh, dw = map1.shape[:2]
+        dst0 = dst
         dst = np.zeros((dh, dw) + src.shape[2:], src.dtype)
+        if dst0 is not None:
+            dst[...] = dst0
         sh, sw = src.shape[:2]
         bv = np.zeros(4, np.float64)
         bv[:len(np.atleast_1d(borderValue))] = np.atleast_1d(borderValue)

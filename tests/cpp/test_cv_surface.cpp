@@ -91,6 +91,24 @@ int main()
         size_t same = 0;
         for (size_t i = 0; i < std::min(corners.size(), corners_ref.size()); i++) same += corners[i] == corners_ref[i];
         EXPECT(corners.size() == corners_ref.size() && same + 4 >= corners_ref.size(), "goodFeaturesToTrack -> std::vector<Point2f> ~ cv::goodFeaturesToTrack");
+        // cv::GFTTDetector (features2d/src/gftt.cpp:131-151): keypoints = (corner, size = blockSize, angle -1, response = quality); BGR input -> BGR2GRAY
+        cv::Ptr<bc::GFTTDetector> det = bc::GFTTDetector::create(200, 0.01, 10, 3, 3, true, 0.04);
+        std::vector<cv::KeyPoint> kps;
+        det->detect(blurred, kps);
+        bool kp_ok = kps.size() == corners_ref.size();
+        size_t kp_same = 0;
+        for (size_t i = 0; kp_ok && i < kps.size(); i++) { kp_same += kps[i].pt == corners_ref[i]; kp_ok = kps[i].size == 3.f && kps[i].angle == -1.f && kps[i].response > 0; }
+        EXPECT(kp_ok && kp_same + 4 >= corners_ref.size(), "GFTTDetector::detect(Mat) ~ cv::goodFeaturesToTrack corners, KeyPoint fields as gftt.cpp");
+        cv::Mat bl3; cv::cvtColor(blurred, bl3, cv::COLOR_GRAY2BGR);
+        b200cv::DeviceMat d_bl3; d_bl3.upload(bl3);
+        std::vector<cv::KeyPoint> kps3;
+        det->detect(d_bl3, kps3);
+        bool same3 = kps3.size() == kps.size();
+        for (size_t i = 0; same3 && i < kps.size(); i++) same3 = kps3[i].pt == kps[i].pt;
+        EXPECT(same3, "GFTTDetector::detect(GpuMat 8UC3) == detect(gray)");
+        det->setMaxFeatures(10);
+        det->detect(blurred, kps);
+        EXPECT(kps.size() == 10 && det->getMaxFeatures() == 10, "GFTTDetector::setMaxFeatures");
         bool threw = false;
         try { bc::GaussianBlur(d_src, got, cv::Size(3, 3), 0); } catch (const b200cv::Error&) { threw = true; }
         EXPECT(threw, "device source with a host destination is refused");

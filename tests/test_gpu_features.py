@@ -207,5 +207,6 @@ def test_sift_fused_stages_equal_the_composition(cvb, rng, monkeypatch, shape, s
         G2, D2, dims2 = cvb.sift_pyramid(gpu(img), 3, 1.6, upscale)
         monkeypatch.delenv(switch)
         assert np.array_equal(dims, dims2)
-        assert_exact(cpu(G), cpu(G2), "Gaussian pyramid with and without %s (upscale=%s)" % (switch, upscale))
-        assert_exact(cpu(D), cpu(D2), "DoG pyramid with and without %s (upscale=%s)" % (switch, upscale))
+        _, ge, de, _ = C.sift_pyramid_layout(shape[1], shape[0], 3, upscale)        # the frame stride is rounded up: compare the pyramids, not the padding
+        assert_exact(cpu(G)[:, :ge], cpu(G2)[:, :ge], "Gaussian pyramid with and without %s (upscale=%s)" % (switch, upscale))
+        assert_exact(cpu(D)[:, :de], cpu(D2)[:, :de], "DoG pyramid with and without %s (upscale=%s)" % (switch, upscale))

@@ -340,3 +340,19 @@ def test_filter2d_generic(cvb, oracle, rng):
     ker = rng.random((4, 6)).astype(np.float32) - 0.3
     assert_exact(cpu(cvb.filter2D(gpu(img3), -1, ker, anchor=(1, 2), delta=7)), oracle.filter2D(img3, -1, ker, anchor=(1, 2), delta=7), "filter2D generic")
     assert_exact(cpu(cvb.filter2D(gpu(img3), 5, ker)), oracle.filter2D(img3, 5, ker), "filter2D u8->f32 (24 taps: direct sum, scalar order)")
+
+
+@pytest.mark.parametrize("k", [3, 5, 7, 9])
+def test_gaussian_u8_streaming_kernel(cvb, oracle, rng, monkeypatch, k):
+    """the warp-streaming second version of the 8-bit Gaussian (gauss_u8_march.cu; B200CV_GAUSS_U8_PATH=stream -- the tile kernel is the faster
+    one on a B200 and stays the default): bit-exact like the default path, every border, ragged sizes, a batch, and sepFilter2D's 8.8 mode"""
+    monkeypatch.setenv("B200CV_GAUSS_U8_PATH", "stream")
+    for shape in ((3, 211, 333, 1), (1, 64, 224, 1), (2, 37, 1000, 1)):
+        img = rng.integers(0, 256, shape, dtype=np.uint8)
+        for border in (4, 1, 0, 2):      # REFLECT_101, REPLICATE, CONSTANT, REFLECT
+            got = cpu(cvb.GaussianBlur(gpu(img), (k, k), 0, borderType=border))
+            for f in range(shape[0]):
+                assert_exact(got[f, :, :, 0], oracle.GaussianBlur(img[f, :, :, 0], (k, k), 0, borderType=border), "stream Gaussian k=%d border=%d" % (k, border))
+    t = cvb.getGaussianKernel(k, 0).astype(np.float32)
+    img = rng.integers(0, 256, (180, 300), dtype=np.uint8)
+    assert_exact(cpu(cvb.sepFilter2D(gpu(img), -1, t, t)), oracle.sepFilter2D(img, -1, t, t), "stream sepFilter2D 8.8 mode k=%d" % k)

@@ -122,6 +122,32 @@ def test_warp_f32(cvb, oracle, rng, interp, border):
                  "warpPerspective f32 interp=%d border=%d" % (interp, border))
 
 
+@pytest.mark.parametrize("interp", [C.INTER_NEAREST, C.INTER_LINEAR, C.INTER_CUBIC])
+@pytest.mark.parametrize("cn", [1, 3])
+def test_warp_border_transparent(cvb, ref, rng, interp, cn):
+    """BORDER_TRANSPARENT (imgwarp.cpp:373,408 / :788-815 / :925,965-968): destination pixels whose source lies outside keep their previous content;
+    a bilinear point inside the image that lacks some of its four neighbours is blended from the ones that exist, re-normalised; a bicubic point
+    with its centre inside takes its missing taps by REFLECT_101.  Bit for bit against the reference, 8-bit and float, affine / projective / remap."""
+    for dt in (np.uint8, np.float32):
+        img = rand_u8(rng, 131, 157, cn)
+        img = img if dt == np.uint8 else (img.astype(np.float32) + 0.37) * 0.731
+        back = rand_u8(rng, 140, 170, cn)
+        back = back if dt == np.uint8 else back.astype(np.float32) * 0.5
+        M = _rot(ref, 157, 131)
+        want = ref.warpAffine(img, M, (170, 140), interp, C.BORDER_TRANSPARENT, 0, dst=back)
+        got = cpu(cvb.warpAffine(gpu(img), M, (170, 140), interp, C.BORDER_TRANSPARENT, 0, dst=gpu(back.copy())))
+        assert_exact(got, want, "warpAffine TRANSPARENT %s cn=%d interp=%d" % (np.dtype(dt).name, cn, interp))
+        assert (want == back).mean() > 0.02 and (want != back).mean() > 0.3       # both kinds of pixels exist
+        want = ref.warpPerspective(img, H0, (170, 140), interp, C.BORDER_TRANSPARENT, 0, dst=back)
+        got = cpu(cvb.warpPerspective(gpu(img), H0, (170, 140), interp, C.BORDER_TRANSPARENT, 0, dst=gpu(back.copy())))
+        assert_exact(got, want, "warpPerspective TRANSPARENT %s cn=%d interp=%d" % (np.dtype(dt).name, cn, interp))
+        yy, xx = np.mgrid[0:140, 0:170].astype(np.float32)
+        mx = (xx * 1.05 - 9.3 + 0.02 * yy).astype(np.float32); my = (yy * 0.97 - 4.6 + 0.03 * xx).astype(np.float32)
+        want = ref.remap(img, mx, my, interp, C.BORDER_TRANSPARENT, 0, dst=back)
+        got = cpu(cvb.remap(gpu(img), gpu(mx), gpu(my), interp, C.BORDER_TRANSPARENT, 0, dst=gpu(back.copy())))
+        assert_exact(got, want, "remap TRANSPARENT %s cn=%d interp=%d" % (np.dtype(dt).name, cn, interp))
+
+
 def test_sift_upsample_warp(cvb, oracle, rng):
     """the 2x upsample SIFT uses: warpAffine(INTER_LINEAR | WARP_INVERSE_MAP, BORDER_REFLECT) on f32 (sift.dispatch.cpp:196-202)"""
     img = rand_u8(rng, 67, 91, 1).astype(np.float32)
