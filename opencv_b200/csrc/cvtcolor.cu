@@ -193,7 +193,10 @@ __global__ void __launch_bounds__(256) cvt_kernel(Img src, Img dst, Op op, int n
     uchar* dp = dst.row<uchar>(f, (int)y) + (size_t)x0 * DCN;
     const int n = min(PPT, src.cols - x0);
 
-    if (vec_ok && n == PPT) {
+    // the vector path below exchanges data inside the warp when DCN >= 3: it is taken by whole warps only (a warp that holds a row's ragged last
+    // item or runs past the last row goes the scalar way for all its lanes -- a few warps per image)
+    const bool vec_warp = DCN >= 3 ? __all_sync(__activemask(), vec_ok && n == PPT) && __activemask() == 0xffffffffu : (vec_ok && n == PPT);
+    if (vec_warp) {
         if constexpr (POS) {
             // position-dependent ops switch behaviour at a multiple of 32 pixels: uniform over this thread's 16 pixels
             if (x0 < op.trunc_cols) op.trunc_cols = 0x7fffffff; else op.trunc_cols = 0;
@@ -212,6 +215,25 @@ __global__ void __launch_bounds__(256) cvt_kernel(Img src, Img dst, Op op, int n
             convert_px<SCN, DCN, Op, POS>(op, s, d, x0 + p);
 #pragma unroll
             for (int c = 0; c < DCN; c++) ob[p * DCN + c] = d[c];
+        }
+        if constexpr (DCN >= 3) {
+            // A thread's DCN vectors are 16 DCN bytes apart from its neighbour's: stored directly, every store instruction touches 32 separate
+            // 16-byte pieces (half or a quarter of each sector).  When the whole warp sits in one row on the vector path its output is one
+            // contiguous 512 DCN-byte run: exchange through shared memory and let store i write 32 ADJACENT vectors (full lines).
+            __shared__ __align__(16) uint4 s_out[256 * DCN];
+            const unsigned y0w = __shfl_sync(0xffffffffu, y, 0);
+            const bool whole = __all_sync(0xffffffffu, y == y0w);                 // every lane took this branch (checked by the caller's ballot below)
+            if (whole) {
+                const int lane = threadIdx.x & 31, wbase = (threadIdx.x >> 5) * 32 * DCN;
+#pragma unroll
+                for (int i = 0; i < DCN; i++) s_out[wbase + lane * DCN + i] = out[i];
+                __syncwarp();
+                uint4* wp = (uint4*)(dp - (size_t)lane * PPT * DCN);              // the warp's first output byte
+#pragma unroll
+                for (int i = 0; i < DCN; i++) stg_stream(wp + i * 32 + lane, s_out[wbase + i * 32 + lane]);
+                __syncwarp();
+                return;
+            }
         }
 #pragma unroll
         for (int i = 0; i < DCN; i++) stg_stream((uint4*)dp + i, out[i]);

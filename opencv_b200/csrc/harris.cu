@@ -14,6 +14,8 @@
 // acceptance on a cell grid) runs on the host over the compacted list, as it is inherently sequential.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 #include <cub/device/device_radix_sort.cuh>
 #include "common.cuh"
@@ -30,9 +32,17 @@ struct HarrisParams {
     int border;
     float k;
     int op;                     // 0 = Harris, 1 = min eigen value
+    int skip_interior;          // the tile kernel leaves the tiles harris_fast_kernel owns alone
 };
 
 constexpr int H_TW = 128, H_TH = 16;
+// tiles of harris_fast_kernel (below): columns per warp (32 lanes x 4), rows per warp; the predicate says which tiles it owns
+constexpr int HF_W = 128, HF_SEG = 64;
+__host__ __device__ __forceinline__ bool harris_fast_tile(int x0, int y0, int W, int H, int bs)
+{
+    const int R = bs + 2;                    // products reach bs - 1 - ba <= bs, the Sobel one more
+    return x0 - R - 4 >= 0 && x0 + HF_W + R + 4 <= W && y0 - R >= 0 && y0 + HF_SEG + R <= H;
+}
 
 // KS = Sobel taps per direction (3 / 5 / 7), BS = box size when small (2 / 3 / 5), 0 = run-time box size
 template <typename ST, int KS, int BS>
@@ -192,6 +202,145 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
     }
 }
 
+// ---- second version for the common case (3-tap Sobel, block size 2 or 3): register marching, interior tiles only ------------------------------
+// The tile kernel above spends ~140 thread instructions per pixel on staging, three shared-memory passes and 4 BS^2 float -> double conversions
+// (profiles/r02_prof_harris_*.txt: issue-bound at 25 % occupancy).  Here a THREAD owns 4 adjacent output columns and walks down HF_SEG rows:
+// the 3-row windows of the two row-filtered derivative images, the current product row and the horizontal box sums of the previous BS - 1
+// product rows all live in registers (the row loop is unrolled by 6 = lcm(3, 2) so every ring index is a compile-time constant); a product is
+// converted to double once; no shared memory, no barrier; one 16-byte store per thread and row.  Arithmetic and operation order are the tile
+// kernel's (= the reference's): same Sobel chains, products rounded to float, box sums left to right then top to bottom in f64.
+// Tiles that touch the image border (where the box filter's border rule lands on the PRODUCT image) stay with the tile kernel: it skips the
+// tiles this kernel owns (HarrisParams::skip_interior).
+template <typename ST, int BS>
+__global__ void __launch_bounds__(128) harris_fast_kernel(Img src, Img dst, const __grid_constant__ HarrisParams p)
+{
+    constexpr int BA = BS / 2, NP = 4 + BS - 1, NS = NP + 2;           // product columns / source columns per thread
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tx = blockIdx.x * 4 + warp;                                 // 4 strips per CTA
+    const int x0 = tx * HF_W, y0 = blockIdx.y * HF_SEG, f = blockIdx.z;
+    if (x0 >= src.cols || !harris_fast_tile(x0, y0, src.cols, src.rows, BS)) return;
+    const int X = x0 + 4 * lane;                                          // first output column
+    const int xs = X - BA - 1;                                            // first source column
+    // source row -> NS floats (bytes through the mantissa of 2^23; the thread's bytes sit in 3 aligned words)
+    auto load_row = [&](int gy, float* sv) {
+        if constexpr (sizeof(ST) == 1) {
+            const uchar* rp = src.row<uchar>(f, gy);
+            const int a0 = (xs & ~3);
+            const bool al = (((uintptr_t)rp) & 3) == 0;
+            unsigned w[4];
+            if (al) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) w[i] = __ldg((const unsigned*)(rp + a0) + i);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) w[i] = (unsigned)rp[a0 + 4 * i] | ((unsigned)rp[a0 + 4 * i + 1] << 8) | ((unsigned)rp[a0 + 4 * i + 2] << 16) | ((unsigned)rp[a0 + 4 * i + 3] << 24);
+            }
+            const unsigned sh8 = 8u * (unsigned)(xs - a0);                // the same for every lane (X % 4 == 0): realign once, then compile-time bytes
+            unsigned v[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) v[i] = __funnelshift_r(w[i], w[i + 1], sh8);
+#pragma unroll
+            for (int j = 0; j < NS; j++)                                  // byte j of the realigned string next to the exponent of 2^23: one PRMT, one FADD
+                sv[j] = __fsub_rn(__uint_as_float(__byte_perm(v[j >> 2], 0x4B000000u, 0x7650 + (j & 3))), 8388608.0f);
+        } else {
+            const float* rp = src.row<float>(f, gy) + xs;
+#pragma unroll
+            for (int j = 0; j < NS; j++) sv[j] = __ldg(rp + j);
+        }
+    };
+    // row pass of one source row: the two derivative row filters at the NP product columns
+    auto row_pass = [&](const float* sv, float* rx, float* ry) {
+#pragma unroll
+        for (int j = 0; j < NP; j++) {
+            if constexpr (sizeof(ST) == 4) {       // float source, 3 taps: centre-out (SymmRowSmallVec_32f order, as the tile kernel)
+                rx[j] = __fmul_rn(__fsub_rn(sv[j + 2], sv[j]), p.dxk_x[2]);
+                ry[j] = fmaf(sv[j + 1], p.dyk_x[1], __fmul_rn(__fadd_rn(sv[j], sv[j + 2]), p.dyk_x[2]));
+            } else {                               // 8-bit source: tap order with FMA from 0
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int i = 0; i < 3; i++) { a = fmaf(sv[j + i], p.dxk_x[i], a); b = fmaf(sv[j + i], p.dyk_x[i], b); }
+                rx[j] = a; ry[j] = b;
+            }
+        }
+    };
+    float rxw[3][NP], ryw[3][NP];                  // row-filtered rows r - 2, r - 1, r (ring by r % 3)
+    double hb[BS > 1 ? BS - 1 : 1][4][3];          // horizontal box sums of the previous BS - 1 product rows (ring by q % (BS - 1))
+    // source rows: products exist from row y0 - BA (needs source rows y0 - BA - 1 ..); walk r = first source row ...
+    const int r_first = y0 - BA - 1, r_last = y0 + HF_SEG - 1 + (BS - 1 - BA) + 1;      // inclusive
+    float sv[NS];
+    int r = r_first;
+    // the unrolled-by-6 loop body handles source row r with compile-time ring slots it % 3 and it % (BS - 1)
+#pragma unroll 1
+    for (int base = 0; r <= r_last; base += 6) {
+#pragma unroll
+        for (int it = 0; it < 6; it++, r++) {
+            if (r > r_last) break;
+            load_row(r, sv);
+            row_pass(sv, rxw[it % 3], ryw[it % 3]);
+            const int n = base + it;                                  // source rows seen before this one
+            if (n < 2) continue;                                      // need rows r - 2 .. r
+            // product row q = r - 1: column pass (mirrored rows first) + products
+            const int q = r - 1;
+            const float* rm = rxw[(it + 1) % 3]; const float* rc = rxw[(it + 2) % 3]; const float* rp_ = rxw[it % 3];       // rows r - 2, r - 1, r
+            const float* sm = ryw[(it + 1) % 3]; const float* sp_ = ryw[it % 3];
+            double pa[NP], pb[NP], pc[NP];
+#pragma unroll
+            for (int j = 0; j < NP; j++) {
+                float dx = fmaf(p.dxk_y[1], rc[j], 0.f);
+                dx = fmaf(p.dxk_y[2], __fadd_rn(rp_[j], rm[j]), dx);
+                float dy = fmaf(p.dyk_y[2], __fsub_rn(sp_[j], sm[j]), 0.f);
+                pa[j] = (double)__fmul_rn(dx, dx); pb[j] = (double)__fmul_rn(dx, dy); pc[j] = (double)__fmul_rn(dy, dy);
+            }
+            // horizontal sums of this product row at the 4 output columns
+            double ha[4], hbv[4], hc[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                double a = pa[i], b = pb[i], c = pc[i];
+#pragma unroll
+                for (int t = 1; t < BS; t++) { a += pa[i + t]; b += pb[i + t]; c += pc[i + t]; }
+                ha[i] = a; hbv[i] = b; hc[i] = c;
+            }
+            // output row y = q - (BS - 1 - BA): its box = product rows y - BA .. q, top to bottom
+            const int y = q - (BS - 1 - BA);
+            const int nq = n - 2;                                     // product rows seen before this one
+            if (nq >= BS - 1 && y >= y0 && y < y0 + HF_SEG) {
+                float o4[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    double a = 0, b = 0, c = 0;
+#pragma unroll
+                    for (int t = BS - 1; t >= 1; t--) {               // oldest first: product row q - t sits in ring slot (nq - t) % (BS - 1)
+                        constexpr int M = BS > 1 ? BS - 1 : 1;
+                        const int slot = ((it + 6 * 4 - 2 - t) % M);   // (nq - t) % M with nq = base + it - 2 and base % 6 == 0, 6 % M == 0
+                        a += hb[slot][i][0]; b += hb[slot][i][1]; c += hb[slot][i][2];
+                    }
+                    a += ha[i]; b += hbv[i]; c += hc[i];
+                    const float fa = (float)a, fb = (float)b, fc = (float)c;
+                    if (p.op == 0) {
+                        const float acbb = __fsub_rn(__fmul_rn(fa, fc), __fmul_rn(fb, fb));
+                        const float ac = __fadd_rn(fa, fc);
+                        o4[i] = __fsub_rn(acbb, __fmul_rn(p.k, __fmul_rn(ac, ac)));
+                    } else {
+                        const float hA = __fmul_rn(fa, 0.5f), hC = __fmul_rn(fc, 0.5f);
+                        float t = __fsub_rn(hA, hC);
+                        t = __fadd_rn(__fmul_rn(fb, fb), __fmul_rn(t, t));
+                        o4[i] = __fsub_rn(__fadd_rn(hA, hC), __fsqrt_rn(t));
+                    }
+                }
+                float* dp = dst.row<float>(f, y) + X;
+                if ((((uintptr_t)dp) & 15) == 0) *(float4*)dp = make_float4(o4[0], o4[1], o4[2], o4[3]);
+                else { dp[0] = o4[0]; dp[1] = o4[1]; dp[2] = o4[2]; dp[3] = o4[3]; }
+            }
+            if constexpr (BS > 1) {
+                constexpr int M = BS - 1;
+                const int slot = (it + 6 * 4 - 2) % M;                // nq % M
+#pragma unroll
+                for (int i = 0; i < 4; i++) { hb[slot][i][0] = ha[i]; hb[slot][i][1] = hbv[i]; hb[slot][i][2] = hc[i]; }
+            }
+        }
+    }
+}
+
 template <typename ST, int KS, int BS>
 static int launch_harris(const Img& s, const Img& d, const HarrisParams& p, cudaStream_t st)
 {
@@ -211,6 +360,21 @@ static int launch_harris(const Img& s, const Img& d, const HarrisParams& p, cuda
 template <typename ST, int KS>
 static int launch_harris_bs(const Img& s, const Img& d, const HarrisParams& p, cudaStream_t st)
 {
+    if constexpr (KS == 3) {
+        // 3-tap Sobel with a 2 x 2 or 3 x 3 block (cornerHarris / goodFeaturesToTrack defaults): interior tiles on the register-marching kernel,
+        // the border ring on the tile kernel (B200CV_HARRIS_PATH=tile: everything on the tile kernel)
+        const char* path = getenv("B200CV_HARRIS_PATH");
+        const bool any_fast = s.cols >= HF_W + 2 * (p.bs + 6) && s.rows >= HF_SEG + 2 * (p.bs + 2);
+        if ((p.bs == 2 || p.bs == 3) && any_fast && !(path && !strcmp(path, "tile"))) {
+            HarrisParams q = p;
+            q.skip_interior = 1;
+            dim3 grid(div_up(div_up((unsigned)s.cols, HF_W), 4), div_up((unsigned)s.rows, HF_SEG), (unsigned)s.frames);
+            if (p.bs == 2) harris_fast_kernel<ST, 2><<<grid, 128, 0, st>>>(s, d, q);
+            else harris_fast_kernel<ST, 3><<<grid, 128, 0, st>>>(s, d, q);
+            B200_LAUNCH_CHECK();
+            return p.bs == 2 ? launch_harris<ST, KS, 2>(s, d, q, st) : launch_harris<ST, KS, 3>(s, d, q, st);
+        }
+    }
     switch (p.bs) {
     case 2: return launch_harris<ST, KS, 2>(s, d, p, st);
     case 3: return launch_harris<ST, KS, 3>(s, d, p, st);

@@ -475,7 +475,7 @@ __device__ __forceinline__ void sample_staged_u8(const unsigned char* s_src, int
         for (int c = 0; c < CN; c++) {
             int sum = dp2a_lo_su(w.x, tap_pair<CN>(r0, c, 0), 1 << 14);
             sum = dp2a_lo_su(w.y, tap_pair<CN>(r1, c, 0), sum);
-            d[c] = sat_u8(sum >> 15);
+            d[c] = (unsigned char)(sum >> 15);           // bilinear table weights are >= 0 and add up to 2^15 (initInterTab2D): the blend of bytes is a byte
         }
     } else {
         int w[8];                                                          // 16 s16 weights: row i = (w[2i], w[2i+1])
@@ -604,11 +604,14 @@ __global__ void __launch_bounds__(256) warp_tile4_kernel(Img src, Img dst, const
         if (!p.persp) { ad = *(const int4*)(s_ad + xq); bd = *(const int4*)(s_bd + xq); X0r = s_X0[yy]; Y0r = s_Y0[yy]; }
         const int adv[4] = {ad.x, ad.y, ad.z, ad.w}, bdv[4] = {bd.x, bd.y, bd.z, bd.w};
         unsigned char ob[4 * CN];
+        int pb = 0, px1 = 0;                                   // projective: column block (relative to the tile's first) and offset inside it
+        if (p.persp) { pb = x / p.bw0 - blk0; px1 = x - (blk0 + pb) * p.bw0; }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             int sx, sy, a;
             if (p.persp) {
-                const int xx = x + k, b = xx / p.bw0 - blk0, x1 = xx - (blk0 + b) * p.bw0;
+                const int b = pb, x1 = px1;
+                if (++px1 == p.bw0) { px1 = 0; pb++; }
                 double W = __dadd_rn(s_pW[yy][b], __dmul_rn(p.M[6], (double)x1));
                 W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
                 const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(s_pX[yy][b], __dmul_rn(p.M[0], (double)x1)), W)));

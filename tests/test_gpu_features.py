@@ -210,3 +210,20 @@ def test_sift_fused_stages_equal_the_composition(cvb, rng, monkeypatch, shape, s
         _, ge, de, _ = C.sift_pyramid_layout(shape[1], shape[0], 3, upscale)        # the frame stride is rounded up: compare the pyramids, not the padding
         assert_exact(cpu(G)[:, :ge], cpu(G2)[:, :ge], "Gaussian pyramid with and without %s (upscale=%s)" % (switch, upscale))
         assert_exact(cpu(D)[:, :de], cpu(D2)[:, :de], "DoG pyramid with and without %s (upscale=%s)" % (switch, upscale))
+
+
+@pytest.mark.parametrize("bs", [2, 3])
+@pytest.mark.parametrize("shape", [(2, 333, 517), (1, 200, 1031), (3, 131, 290)])
+def test_corner_response_fast_kernel_equals_tile_kernel(cvb, rng, monkeypatch, bs, shape):
+    """cornerHarris / cornerMinEigenVal with the 3-tap Sobel and a 2 x 2 or 3 x 3 block: interior tiles run on the register-marching kernel,
+    the border ring on the tile kernel (harris.cu).  Same operations in the same order: the two must agree bit for bit (8-bit and float
+    sources, a batch, sizes that leave partial tiles), and the composite must equal the all-tile result."""
+    for dt in (np.uint8, np.float32):
+        img = smooth_img(rng, shape[1], shape[2] * shape[0]).reshape(shape[1], shape[0], shape[2]).transpose(1, 0, 2).copy()[..., None]
+        img = img if dt == np.uint8 else img.astype(np.float32) / 255.0
+        for fn, args in ((cvb.cornerHarris, (bs, 3, 0.04)), (cvb.cornerMinEigenVal, (bs, 3))):
+            got = cpu(fn(gpu(img), *args))
+            monkeypatch.setenv("B200CV_HARRIS_PATH", "tile")
+            want = cpu(fn(gpu(img), *args))
+            monkeypatch.delenv("B200CV_HARRIS_PATH")
+            assert_exact(got, want, "%s bs=%d %s %s: fast + border tiles vs tile kernel" % (fn.__name__, bs, np.dtype(dt).name, shape))
