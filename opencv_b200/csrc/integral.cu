@@ -8,9 +8,13 @@
 //   rows:     H1 sum of every 16-pixel chunk            H2 exclusive scan of the chunk sums of a row      H3 prefix inside the chunk + offset -> sum
 //   columns:  V1 sum of every 32-row block of a column  V2 exclusive scan of the block sums of a column   V3 prefix inside the block + offset, in place
 // Algorithmic traffic: 1 byte read + 4 (12 with squares) written per pixel; this version re-reads the source once and the output twice.
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace b200cv {
+
+int integral_scan_run(const Img& s, const Img& o, int squares, cudaStream_t st);      // integral_scan.cu
 
 namespace {
 
@@ -101,6 +105,13 @@ int integral_run(const Img& s, const Img& o, cudaStream_t st)
     IgDims g;
     g.W = s.cols; g.H = s.rows; g.NC = (int)div_up((unsigned)g.W, IG_CHUNK); g.NB = (int)div_up((unsigned)g.H, IG_ROWS);
     const int frames = s.frames;
+#ifndef B200CV_HOST_EMULATION
+    {
+        // second version (integral_scan.cu): two kernels with warp scans; B200CV_INTEGRAL_PATH=v1 keeps the six map-only kernels below
+        const char* path = getenv("B200CV_INTEGRAL_PATH");
+        if (!(path && !strcmp(path, "v1"))) return integral_scan_run(s, o, SQ ? 1 : 0, st);
+    }
+#endif
     T* scratch = nullptr;
     const size_t ncs = (size_t)frames * g.H * g.NC, nbs = (size_t)frames * g.NB * g.W;
     B200_CUDA(cudaMallocAsync((void**)&scratch, sizeof(T) * (ncs + nbs), st));

@@ -40,3 +40,15 @@ def test_integral_batch_host_and_hal(cvb, oracle, rng):
     # size-independent property: any box sum from four corners of the integral equals the direct sum
     s = ws.astype(np.int64)
     assert s[300, 400] - s[100, 400] - s[300, 200] + s[100, 200] == int(img[100:300, 200:400].sum(dtype=np.int64))
+
+
+def test_integral_first_version_still_agrees(cvb, oracle, rng, monkeypatch):
+    """B200CV_INTEGRAL_PATH=v1: the six map-only kernels (the ones the host emulation runs) against the warp-scan kernels and the oracle"""
+    img = rng.integers(0, 256, (3, 333, 517, 1), dtype=np.uint8)
+    s2, q2 = cvb.integral(gpu(img), with_sqsum=True)
+    monkeypatch.setenv("B200CV_INTEGRAL_PATH", "v1")
+    s1, q1 = cvb.integral(gpu(img), with_sqsum=True)
+    monkeypatch.delenv("B200CV_INTEGRAL_PATH")
+    assert_exact(cpu(s2), cpu(s1), "integral sum: scan kernels vs map-only kernels")
+    assert_exact(cpu(q2), cpu(q1), "integral sqsum: scan kernels vs map-only kernels")
+    assert_exact(cpu(s2)[1, :, :, 0], oracle.integral(img[1, :, :, 0]), "integral sum vs oracle")
