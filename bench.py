@@ -538,6 +538,29 @@ def measure_e2e(workload, ops, extra, bufs, steps, rank, world, local):
     return e2e
 
 
+def measure_hal_per_call():
+    """synchronous single-frame calls through the host entry points on ordinary (pageable) numpy arrays: the shape of a cv_hal_* call"""
+    from opencv_b200 import hal
+    rng = np.random.default_rng(3)
+    g4k = rng.integers(0, 256, (H4K, W4K), dtype=np.uint8)
+    f4k = g4k.astype(np.float32)
+    bgr8k = rng.integers(0, 256, (H8K, W8K, 3), dtype=np.uint8)
+    cases = (("GaussianBlur_5x5_8UC1_4K", lambda: hal.GaussianBlur(g4k, (5, 5), 0), W4K * H4K),
+             ("GaussianBlur_5x5_32FC1_4K", lambda: hal.GaussianBlur(f4k, (5, 5), 0), W4K * H4K),
+             ("cvtColor_BGR2GRAY_8UC3_8K", lambda: hal.cvtColor(bgr8k, 6), W8K * H8K),
+             ("resize_8Kto4K_LINEAR_8UC3", lambda: hal.resize(bgr8k, (W4K, H4K), interpolation=1), W4K * H4K))
+    out = {"note": "one frame per call, pageable host memory, synchronous (upload + kernel + download + the destination's allocation): the cost of a cv:: call routed through the HAL seam"}
+    for name, fn, px in cases:
+        fn(); fn()
+        t0 = time.perf_counter()
+        n = 8
+        for _ in range(n):
+            fn()
+        dt = (time.perf_counter() - t0) / n
+        out[name] = {"ms_per_call": round(dt * 1e3, 3), "mpix_s": round(px / dt / 1e6, 1)}
+    return out
+
+
 def main():
     # keep stdout clean for the ONE JSON line: libraries (e.g. the NCCL version banner) write to fd 1 -> send that to stderr
     json_fd = os.dup(1)
@@ -607,6 +630,14 @@ def main():
 
     # ---------------- e2e: the same ops through the host C ABI (pinned host memory, H2D+D2H in the timed region) --------------
     e2e = None if args.no_e2e else measure_e2e(args.workload, ops, extra, bufs, args.steps, rank, world, local)
+
+    # ---------------- the per-call HAL seam: what ONE cv:: call of a stock OpenCV built with the HAL header costs (pageable cv::Mat memory,
+    # upload -> kernel -> download synchronously per frame, b200cv_hal_* = opencv_b200.hal over a single frame) -- rank 0 only, a handful of calls
+    if e2e is not None and rank == 0 and args.workload == "c2":
+        try:
+            e2e["per_call_hal"] = measure_hal_per_call()
+        except Exception as exc:                        # noqa: BLE001
+            e2e["per_call_hal"] = {"error": repr(exc)[:200]}
 
     # ---------------- the other BASELINE configs (C3, C4, C5) measured in the same run: short device-resident passes with per-op tables --------
     extra_workloads = None

@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) harris_kernel(Img src, Img dst, const __g
     const int f = blockIdx.z, x0 = blockIdx.x * H_TW, y0 = blockIdx.y * H_TH;
     const int cx0 = x0 - p.ba, cy0 = y0 - p.ba;                   // image coordinates of cov region origin
     const int W = src.cols, H = src.rows;
+    if (p.skip_interior && harris_fast_tile(x0, (y0 / HF_SEG) * HF_SEG, W, H, bs)) return;       // harris_fast_kernel's tile
 
     // one warp per staged row, lanes over columns (no per-element division); interior tiles skip the border arithmetic
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,31 +222,38 @@ __global__ void __launch_bounds__(128) harris_fast_kernel(Img src, Img dst, cons
     if (x0 >= src.cols || !harris_fast_tile(x0, y0, src.cols, src.rows, BS)) return;
     const int X = x0 + 4 * lane;                                          // first output column
     const int xs = X - BA - 1;                                            // first source column
-    // source row -> NS floats (bytes through the mantissa of 2^23; the thread's bytes sit in 3 aligned words)
-    auto load_row = [&](int gy, float* sv) {
+    // source row -> NS floats in two steps, so that the NEXT row's loads are in flight while this row is processed (the first version consumed
+    // each load at once: 43 % of its stall samples sat on the first instruction after the LDG): fetch = raw words / floats, decode = bytes
+    // through the mantissa of 2^23 (the thread's bytes sit in 3 aligned words: one funnel shift each, then compile-time PRMTs)
+    constexpr int NRAW = sizeof(ST) == 1 ? 4 : NS;
+    const int a0 = (xs & ~3);
+    auto fetch = [&](int gy, unsigned* raw) {
         if constexpr (sizeof(ST) == 1) {
             const uchar* rp = src.row<uchar>(f, gy);
-            const int a0 = (xs & ~3);
-            const bool al = (((uintptr_t)rp) & 3) == 0;
-            unsigned w[4];
-            if (al) {
+            if ((((uintptr_t)rp) & 3) == 0) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) w[i] = __ldg((const unsigned*)(rp + a0) + i);
+                for (int i = 0; i < 4; i++) raw[i] = __ldg((const unsigned*)(rp + a0) + i);
             } else {
 #pragma unroll
-                for (int i = 0; i < 4; i++) w[i] = (unsigned)rp[a0 + 4 * i] | ((unsigned)rp[a0 + 4 * i + 1] << 8) | ((unsigned)rp[a0 + 4 * i + 2] << 16) | ((unsigned)rp[a0 + 4 * i + 3] << 24);
+                for (int i = 0; i < 4; i++) raw[i] = (unsigned)rp[a0 + 4 * i] | ((unsigned)rp[a0 + 4 * i + 1] << 8) | ((unsigned)rp[a0 + 4 * i + 2] << 16) | ((unsigned)rp[a0 + 4 * i + 3] << 24);
             }
-            const unsigned sh8 = 8u * (unsigned)(xs - a0);                // the same for every lane (X % 4 == 0): realign once, then compile-time bytes
-            unsigned v[3];
-#pragma unroll
-            for (int i = 0; i < 3; i++) v[i] = __funnelshift_r(w[i], w[i + 1], sh8);
-#pragma unroll
-            for (int j = 0; j < NS; j++)                                  // byte j of the realigned string next to the exponent of 2^23: one PRMT, one FADD
-                sv[j] = __fsub_rn(__uint_as_float(__byte_perm(v[j >> 2], 0x4B000000u, 0x7650 + (j & 3))), 8388608.0f);
         } else {
             const float* rp = src.row<float>(f, gy) + xs;
 #pragma unroll
-            for (int j = 0; j < NS; j++) sv[j] = __ldg(rp + j);
+            for (int j = 0; j < NS; j++) raw[j] = __float_as_uint(__ldg(rp + j));
+        }
+    };
+    auto decode = [&](const unsigned* raw, float* sv) {
+        if constexpr (sizeof(ST) == 1) {
+            const unsigned sh8 = 8u * (unsigned)(xs - a0);                // the same for every lane (X % 4 == 0)
+            unsigned v[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) v[i] = __funnelshift_r(raw[i], raw[i + 1], sh8);
+#pragma unroll
+            for (int j = 0; j < NS; j++) sv[j] = __fsub_rn(__uint_as_float(__byte_perm(v[j >> 2], 0x4B000000u, 0x7650 + (j & 3))), 8388608.0f);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NS; j++) sv[j] = __uint_as_float(raw[j]);
         }
     };
     // row pass of one source row: the two derivative row filters at the NP product columns
@@ -268,14 +276,17 @@ __global__ void __launch_bounds__(128) harris_fast_kernel(Img src, Img dst, cons
     // source rows: products exist from row y0 - BA (needs source rows y0 - BA - 1 ..); walk r = first source row ...
     const int r_first = y0 - BA - 1, r_last = y0 + HF_SEG - 1 + (BS - 1 - BA) + 1;      // inclusive
     float sv[NS];
+    unsigned raw[2][NRAW];
     int r = r_first;
+    fetch(r, raw[0]);
     // the unrolled-by-6 loop body handles source row r with compile-time ring slots it % 3 and it % (BS - 1)
 #pragma unroll 1
     for (int base = 0; r <= r_last; base += 6) {
 #pragma unroll
         for (int it = 0; it < 6; it++, r++) {
             if (r > r_last) break;
-            load_row(r, sv);
+            if (r < r_last) fetch(r + 1, raw[(it + 1) % 2]);
+            decode(raw[it % 2], sv);
             row_pass(sv, rxw[it % 3], ryw[it % 3]);
             const int n = base + it;                                  // source rows seen before this one
             if (n < 2) continue;                                      // need rows r - 2 .. r

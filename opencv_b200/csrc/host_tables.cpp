@@ -149,6 +149,28 @@ static void cubic_taps(float x, float* c)
     c[3] = 1.f - c[0] - c[1] - c[2];
 }
 
+// interpolateLanczos4 as cv::remap's tables use it (imgwarp.cpp:162-188): sin / cos of the first tap's angle in double, the other seven by
+// the 45-degree rotation table, normalised in float; x < FLT_EPSILON is the unit tap
+static void lanczos4_taps_remap(float x, float* c)
+{
+    static const double s45 = 0.70710678118654752440084436210485;
+    static const double cs[][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+    if (x < 1.1920928955078125e-07f) {
+        for (int i = 0; i < 8; i++) c[i] = 0;
+        c[3] = 1;
+        return;
+    }
+    float sum = 0;
+    const double y0 = -(x + 3) * 3.1415926535897932384626433832795 * 0.25, s0 = std::sin(y0), c0 = std::cos(y0);
+    for (int i = 0; i < 8; i++) {
+        const double y = -(x + 3 - i) * 3.1415926535897932384626433832795 * 0.25;
+        c[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+        sum += c[i];
+    }
+    sum = 1.f / sum;
+    for (int i = 0; i < 8; i++) c[i] *= sum;
+}
+
 static void inter_tab_2d(int ksize, std::vector<float>& ftab, std::vector<short>& itab)
 {
     const int N = 32;
@@ -157,7 +179,8 @@ static void inter_tab_2d(int ksize, std::vector<float>& ftab, std::vector<short>
     for (int i = 0; i < N; i++) {
         float x = i * step;
         if (ksize == 2) { t1[i * 2] = 1.f - x; t1[i * 2 + 1] = x; }
-        else cubic_taps(x, &t1[i * 4]);
+        else if (ksize == 4) cubic_taps(x, &t1[i * 4]);
+        else lanczos4_taps_remap(x, &t1[i * 8]);
     }
     const int kk = ksize * ksize, c0 = ksize / 2;
     ftab.assign((size_t)N * N * kk, 0.f);
@@ -197,5 +220,6 @@ static void inter_tab_2d(int ksize, std::vector<float>& ftab, std::vector<short>
 
 void bilinear_tab(std::vector<float>& f, std::vector<short>& i) { inter_tab_2d(2, f, i); }
 void bicubic_tab(std::vector<float>& f, std::vector<short>& i) { inter_tab_2d(4, f, i); }
+void lanczos4_tab(std::vector<float>& f, std::vector<short>& i) { inter_tab_2d(8, f, i); }
 
 }  // namespace b200cv

@@ -13,5 +13,6 @@ int gaussian_auto_ksize(double sigma, bool is_u8);
 // cv::remap interpolation tables (imgwarp.cpp:213-287): 32x32 sub-pixel positions x (ksize*ksize) taps, float and 2^15 fixed point
 void bilinear_tab(std::vector<float>& f, std::vector<short>& i);
 void bicubic_tab(std::vector<float>& f, std::vector<short>& i);
+void lanczos4_tab(std::vector<float>& f, std::vector<short>& i);
 
 }  // namespace b200cv

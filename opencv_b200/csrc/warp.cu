@@ -26,6 +26,8 @@ __device__ short g_bilin_i[1024 * 4];
 __device__ float g_bilin_f[1024 * 4];
 __device__ short g_bicub_i[1024 * 16];
 __device__ float g_bicub_f[1024 * 16];
+__device__ short g_lanc_i[1024 * 64];      // INTER_LANCZOS4: 8 x 8 taps per sub-pixel position (remapLanczos4, imgwarp.cpp:1012-1113)
+__device__ float g_lanc_f[1024 * 64];
 
 struct WarpParams {
     double M[9];
@@ -35,11 +37,11 @@ struct WarpParams {
     int border, persp, bw0;
 };
 
-enum { W_NN = 0, W_LIN = 1, W_CUB = 2 };
+enum { W_NN = 0, W_LIN = 1, W_CUB = 2, W_LAN = 3 };
 
 template <typename T> struct TabOf;
-template <> struct TabOf<uchar> { typedef short type; __device__ static const short* lin() { return g_bilin_i; } __device__ static const short* cub() { return g_bicub_i; } };
-template <> struct TabOf<float> { typedef float type; __device__ static const float* lin() { return g_bilin_f; } __device__ static const float* cub() { return g_bicub_f; } };
+template <> struct TabOf<uchar> { typedef short type; __device__ static const short* lin() { return g_bilin_i; } __device__ static const short* cub() { return g_bicub_i; } __device__ static const short* lan() { return g_lanc_i; } };
+template <> struct TabOf<float> { typedef float type; __device__ static const float* lin() { return g_bilin_f; } __device__ static const float* cub() { return g_bicub_f; } __device__ static const float* lan() { return g_lanc_f; } };
 
 __device__ __forceinline__ int clipi(int x, int a, int b) { return x >= a ? (x < b ? x : b - 1) : a; }
 
@@ -85,7 +87,7 @@ __device__ __forceinline__ bool sample_direct(const Img& src, int f, const WarpP
 {
     const int sw = p.sw, sh = p.sh;
     const bool transparent = p.border == B200CV_BORDER_TRANSPARENT;
-    const int border = (transparent && INTERP == W_CUB) ? B200CV_BORDER_REFLECT_101 : p.border;
+    const int border = (transparent && (INTERP == W_CUB || INTERP == W_LAN)) ? B200CV_BORDER_REFLECT_101 : p.border;
     T cval[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) { if constexpr (sizeof(T) == 1) cval[c] = (T)p.cval_i[c]; else cval[c] = p.cval_f[c]; }
@@ -163,19 +165,21 @@ __device__ __forceinline__ bool sample_direct(const Img& src, int f, const WarpP
         }
         return true;
     } else {
+        // INTER_CUBIC (4 x 4 taps, remapBicubic imgwarp.cpp:907-1010) and INTER_LANCZOS4 (8 x 8 taps, remapLanczos4 :1012-1113): the same structure
         typedef typename TabOf<T>::type AT;
-        const AT* w = TabOf<T>::cub() + a * 16;
-        sx -= 1; sy -= 1;
-        const bool inlier = (unsigned)sx < (unsigned)max(sw - 3, 0) && (unsigned)sy < (unsigned)max(sh - 3, 0);
-        if (!inlier && transparent && ((unsigned)(sx + 1) >= (unsigned)sw || (unsigned)(sy + 1) >= (unsigned)sh)) return false;
-        if (!inlier && border == B200CV_BORDER_CONSTANT && (sx >= sw || sx + 4 <= 0 || sy >= sh || sy + 4 <= 0)) {
+        constexpr int NT = INTERP == W_CUB ? 4 : 8, OFS = NT / 2 - 1;
+        const AT* w = (INTERP == W_CUB ? TabOf<T>::cub() : TabOf<T>::lan()) + a * (NT * NT);
+        sx -= OFS; sy -= OFS;
+        const bool inlier = (unsigned)sx < (unsigned)max(sw - (NT - 1), 0) && (unsigned)sy < (unsigned)max(sh - (NT - 1), 0);
+        if (!inlier && transparent && ((unsigned)(sx + OFS) >= (unsigned)sw || (unsigned)(sy + OFS) >= (unsigned)sh)) return false;
+        if (!inlier && border == B200CV_BORDER_CONSTANT && (sx >= sw || sx + NT <= 0 || sy >= sh || sy + NT <= 0)) {
 #pragma unroll
             for (int c = 0; c < CN; c++) d[c] = cval[c];
             return true;
         }
-        int xs[4], ys[4];
+        int xs[NT], ys[NT];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < NT; i++) {
             xs[i] = inlier ? sx + i : border_interpolate(sx + i, sw, border);
             ys[i] = inlier ? sy + i : border_interpolate(sy + i, sh, border);
         }
@@ -184,35 +188,37 @@ __device__ __forceinline__ bool sample_direct(const Img& src, int f, const WarpP
             if constexpr (sizeof(T) == 1) {
                 int sum = 0;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
+                for (int i = 0; i < NT; i++) {
                     const uchar* r = ys[i] >= 0 ? src.row<uchar>(f, ys[i]) : nullptr;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
+                    for (int j = 0; j < NT; j++) {
                         int v = (r && xs[j] >= 0) ? r[xs[j] * CN + c] : cval[c];
-                        sum += v * w[i * 4 + j];
+                        sum += v * w[i * NT + j];
                     }
                 }
                 d[c] = sat_u8((sum + (1 << 14)) >> 15);
             } else {
                 if (inlier) {
+                    // rows left to right; cubic: sum = row0, then += row_i; lanczos: sum = 0, then += row_i for every row
                     float sum = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
+                    for (int i = 0; i < NT; i++) {
                         const float* r = src.row<float>(f, ys[i]) + (size_t)xs[0] * CN + c;
-                        float rs = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r[0], w[i * 4]), __fmul_rn(r[CN], w[i * 4 + 1])),
-                                                       __fmul_rn(r[2 * CN], w[i * 4 + 2])), __fmul_rn(r[3 * CN], w[i * 4 + 3]));
-                        sum = i == 0 ? rs : __fadd_rn(sum, rs);
+                        float rs = __fmul_rn(r[0], w[i * NT]);
+#pragma unroll
+                        for (int j = 1; j < NT; j++) rs = __fadd_rn(rs, __fmul_rn(r[j * CN], w[i * NT + j]));
+                        sum = (i == 0 && INTERP == W_CUB) ? rs : __fadd_rn(sum, rs);
                     }
                     d[c] = sum;
                 } else {
                     float cv = cval[c], sum = cv;
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
+                    for (int i = 0; i < NT; i++) {
                         if (ys[i] < 0) continue;
                         const float* r = src.row<float>(f, ys[i]);
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if (xs[j] >= 0) sum = __fadd_rn(sum, __fmul_rn(__fsub_rn(r[xs[j] * CN + c], cv), w[i * 4 + j]));
+                        for (int j = 0; j < NT; j++)
+                            if (xs[j] >= 0) sum = __fadd_rn(sum, __fmul_rn(__fsub_rn(r[xs[j] * CN + c], cv), w[i * NT + j]));
                     }
                     d[c] = sum;
                 }
@@ -654,6 +660,9 @@ static int ensure_warp_tables()
     bicubic_tab(f, q);
     B200_CUDA(cudaMemcpyToSymbol(g_bicub_f, f.data(), f.size() * sizeof(float)));
     B200_CUDA(cudaMemcpyToSymbol(g_bicub_i, q.data(), q.size() * sizeof(short)));
+    lanczos4_tab(f, q);
+    B200_CUDA(cudaMemcpyToSymbol(g_lanc_f, f.data(), f.size() * sizeof(float)));
+    B200_CUDA(cudaMemcpyToSymbol(g_lanc_i, q.data(), q.size() * sizeof(short)));
     done = true;
     return B200CV_OK;
 }
@@ -678,6 +687,12 @@ static long long tile_footprint(const WarpParams& p, int x0, int y0, int es, int
 template <typename T, int CN, int INTERP>
 static int launch_warp_i(const Img& s, const Img& d, const WarpParams& p, cudaStream_t st)
 {
+    if constexpr (INTERP == W_LAN) {          // 8 x 8 taps: the direct gather (no staged variant)
+        dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
+        warp_kernel<T, CN, INTERP><<<grid, 256, 0, st>>>(s, d, p);
+        B200_LAUNCH_CHECK();
+        return B200CV_OK;
+    } else {
     const int es = CN * (int)sizeof(T), taps = INTERP == W_NN ? 1 : INTERP == W_LIN ? 2 : 4;
     // shared memory to request: the largest footprint over a coarse sample of tiles (an affine map has the same footprint everywhere)
     long long need = 0;
@@ -730,6 +745,7 @@ static int launch_warp_i(const Img& s, const Img& d, const WarpParams& p, cudaSt
     kern<<<grid, 256, smem, st>>>(s, d, p, smem);
     B200_LAUNCH_CHECK();
     return B200CV_OK;
+    }
 }
 
 template <typename T, int CN>
@@ -737,6 +753,7 @@ static int launch_warp(int interp, const Img& s, const Img& d, const WarpParams&
 {
     if (interp == W_NN) return launch_warp_i<T, CN, W_NN>(s, d, p, st);
     if (interp == W_LIN) return launch_warp_i<T, CN, W_LIN>(s, d, p, st);
+    if (interp == W_LAN) return launch_warp_i<T, CN, W_LAN>(s, d, p, st);
     return launch_warp_i<T, CN, W_CUB>(s, d, p, st);
 }
 
@@ -785,6 +802,7 @@ static int launch_remap(int interp, const Img& s, const Img& d, const Img& m1, c
     dim3 grid(div_up((unsigned)p.dw, 256), (unsigned)p.dh, (unsigned)s.frames);
     if (interp == W_NN) remap_kernel<T, CN, W_NN><<<grid, 256, 0, st>>>(s, d, m1, m2, p, kind);
     else if (interp == W_LIN) remap_kernel<T, CN, W_LIN><<<grid, 256, 0, st>>>(s, d, m1, m2, p, kind);
+    else if (interp == W_LAN) remap_kernel<T, CN, W_LAN><<<grid, 256, 0, st>>>(s, d, m1, m2, p, kind);
     else remap_kernel<T, CN, W_CUB><<<grid, 256, 0, st>>>(s, d, m1, m2, p, kind);
     B200_LAUNCH_CHECK();
     return B200CV_OK;

@@ -28,6 +28,10 @@ nv12 = torch.randint(0, 256, (4, 4320 * 3 // 2, 7680, 1), dtype=torch.uint8, dev
 yuy2 = torch.randint(0, 256, (4, 4320, 7680, 2), dtype=torch.uint8, device=dev)
 k5 = torch.empty((4, 2880, 5120, 3), dtype=torch.uint8, device=dev)
 k25 = torch.empty((4, 1440, 2560, 3), dtype=torch.uint8, device=dev)
+u16 = (torch.randint(0, 65536, (8, 2160, 3840, 1), dtype=torch.int32, device=dev)).to(torch.uint16)
+o16 = torch.empty_like(u16)
+_sm = torch.nn.functional.interpolate(torch.rand((1, 1, 135, 240), device=dev), size=(1080, 1920), mode="bilinear")
+sift_img = (_sm[0, 0] * 255).to(torch.uint8).contiguous()
 
 ops = {
     "blur_u8_k3": (lambda: cvb.blur(u8, (3, 3), dst=o8), nbytes(u8, o8)),
@@ -53,6 +57,10 @@ ops = {
     "lab_to_bgr_8k": (lambda: cvb.cvtColor(bgr, cvb.COLOR_Lab2BGR, dst=obgr), nbytes(bgr, obgr)),
     "match_masked_4k_64": (lambda: cvb.matchTemplate(u8[:1], u8[0, 700:764, 1000:1064, 0].contiguous(), 5, mask=torch.ones((64, 64), dtype=torch.uint8, device=dev)), nbytes(u8[:1]) * 5),
     "integral_4k": (lambda: cvb.integral(u8), nbytes(u8) * 5),
+    "integral_sq_4k": (lambda: cvb.integral(u8[:4], with_sqsum=True), nbytes(u8[:4]) * 13),
+    "gauss_u16_k5": (lambda: cvb.GaussianBlur(u16, (5, 5), 0, dst=o16), nbytes(u16, o16)),
+    "gauss_u16_k15": (lambda: cvb.GaussianBlur(u16, (15, 15), 0, dst=o16), nbytes(u16, o16)),
+    "sift_detect_1080p": (lambda: cvb.sift_detectAndCompute(sift_img), nbytes(sift_img) * 5),
 }
 for name, (fn, nb) in ops.items():
     if which and name not in which:
