@@ -15,40 +15,18 @@
 // Three kernels, one thread per DoG pixel / candidate / keypoint; candidates and keypoints are appended with atomics and the final order
 // is fixed by the reference's own sort (KeyPoint12_LessThan) on the host, where the reference also does it.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <vector>
 #include "common.cuh"
+#include "sift_detect.cuh"
 
 namespace b200cv {
 
+int sift_descriptors_warp(const SiftPyr& p, int first_octave, const SiftKp* kps, int nkp, float* desc, cudaStream_t st);   // sift_desc_warp.cu
+
 namespace {
-
-enum { SIFT_MAX_OCT = 16, SIFT_BORDER = 5, SIFT_ORI_BINS = 36 };
-
-struct SiftPyr {
-    const float* gauss;
-    const float* dog;
-    int n_oct, nl;
-    int w[SIFT_MAX_OCT], h[SIFT_MAX_OCT];
-    unsigned long long goff[SIFT_MAX_OCT], doff[SIFT_MAX_OCT];      // element offsets of octave o in the packed buffers
-};
-
-struct SiftCand { int o, layer, r, c; };
-struct SiftKp { float x, y, size, angle, response; int octave; };
-
-__device__ __forceinline__ float fast_atan2_deg(float y, float x)            // atan_f32, mathfuncs_core.simd.hpp:52-72
-{
-    const float p1 = 0.9997878412794807f * (float)(180 / 3.1415926535897932384626433832795), p3 = -0.3258083974640975f * (float)(180 / 3.1415926535897932384626433832795);
-    const float p5 = 0.1555786518463281f * (float)(180 / 3.1415926535897932384626433832795), p7 = -0.04432655554792128f * (float)(180 / 3.1415926535897932384626433832795);
-    const float ax = fabsf(x), ay = fabsf(y);
-    float a, c, c2;
-    if (ax >= ay) { c = ay / (ax + (float)2.2204460492503131e-16); c2 = c * c; a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
-    else { c = ax / (ay + (float)2.2204460492503131e-16); c2 = c * c; a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c; }
-    if (x < 0) a = 180.f - a;
-    if (y < 0) a = 360.f - a;
-    return a;
-}
 
 // ---- 1. extrema: one thread per interior pixel of DoG layer `layer` (1..nl) of octave o ------------------------------------------------
 __global__ void __launch_bounds__(256) sift_extrema_kernel(SiftPyr p, int o, float threshold, SiftCand* cand, int* ncand, int cap)
@@ -377,7 +355,15 @@ int sift_detect_impl(const float* gauss, const float* dog, const int* dims, int 
         float* ddesc = nullptr;
         ce = cudaMallocAsync((void**)&ddesc, sizeof(float) * 128 * nret, st);
         if (ce == cudaSuccess) ce = cudaMemcpyAsync(kps, hk.data(), sizeof(SiftKp) * nret, cudaMemcpyHostToDevice, st);
-        if (ce == cudaSuccess) {
+        bool warp_path = false;
+#ifndef B200CV_HOST_EMULATION
+        {   // second version: a warp per keypoint (sift_desc_warp.cu); B200CV_SIFT_DESC_PATH=v1 keeps the thread-per-keypoint kernel below
+            const char* path = getenv("B200CV_SIFT_DESC_PATH");
+            warp_path = !(path && !strcmp(path, "v1"));
+            if (ce == cudaSuccess && warp_path && sift_descriptors_warp(p, first_octave, kps, (int)nret, ddesc, st) != B200CV_OK) ce = cudaErrorUnknown;
+        }
+#endif
+        if (ce == cudaSuccess && !warp_path) {
             const dim3 block(64);
             const dim3 grid(div_up((unsigned)nret, 64));
             sift_descriptor_kernel<<<grid, block, 0, st>>>(p, first_octave, kps, (int)nret, ddesc);

@@ -819,7 +819,8 @@ static int warp_common(const b200cvMat* src, const b200cvMat* dst, const double*
     if ((depth != B200CV_8U && depth != B200CV_32F) || (cn != 1 && cn != 3 && cn != 4)) return B200CV_NOT_IMPLEMENTED;
     int interp = flags & 7;
     if (interp == B200CV_INTER_AREA) interp = B200CV_INTER_LINEAR;            // imgwarp.cpp:2816, :3393
-    if (interp > B200CV_INTER_CUBIC) return B200CV_NOT_IMPLEMENTED;
+    if (interp > B200CV_INTER_CUBIC && interp != B200CV_INTER_LANCZOS4) return B200CV_NOT_IMPLEMENTED;
+    if (interp == B200CV_INTER_LANCZOS4) interp = W_LAN;
     border &= ~B200CV_BORDER_ISOLATED;
     if (border < 0 || border > B200CV_BORDER_TRANSPARENT) return B200CV_NOT_IMPLEMENTED;
     if (src->cols >= 32767 || src->rows >= 32767 || dst->rows >= 65536) return B200CV_NOT_IMPLEMENTED;   // CV_Assert(cols,rows < SHRT_MAX) imgwarp.cpp:1813
@@ -916,7 +917,8 @@ extern "C" int b200cv_remap(const b200cvMat* src, const b200cvMat* dst, const b2
     if ((depth != B200CV_8U && depth != B200CV_32F) || (cn != 1 && cn != 3 && cn != 4)) return B200CV_NOT_IMPLEMENTED;
     int interp = interpolation & 7;
     if (interp == B200CV_INTER_AREA) interp = B200CV_INTER_LINEAR;            // imgwarp.cpp:1826
-    if (interp > B200CV_INTER_CUBIC) return B200CV_NOT_IMPLEMENTED;
+    if (interp > B200CV_INTER_CUBIC && interp != B200CV_INTER_LANCZOS4) return B200CV_NOT_IMPLEMENTED;
+    if (interp == B200CV_INTER_LANCZOS4) interp = W_LAN;
     if (kind == MAP_FIXED && !has2 && interp != B200CV_INTER_NEAREST) return B200CV_ERR_BAD_ARG;
     border &= ~B200CV_BORDER_ISOLATED;
     if (border < 0 || border > B200CV_BORDER_TRANSPARENT) return B200CV_NOT_IMPLEMENTED;

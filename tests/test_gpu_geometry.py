@@ -148,6 +148,32 @@ def test_warp_border_transparent(cvb, ref, rng, interp, cn):
         assert_exact(got, want, "remap TRANSPARENT %s cn=%d interp=%d" % (np.dtype(dt).name, cn, interp))
 
 
+@pytest.mark.parametrize("cn", [1, 3])
+@pytest.mark.parametrize("border", [C.BORDER_CONSTANT, C.BORDER_REPLICATE, C.BORDER_REFLECT_101, C.BORDER_TRANSPARENT])
+def test_warp_lanczos4(cvb, ref, rng, cn, border):
+    """INTER_LANCZOS4 in warpAffine / warpPerspective / remap (remapLanczos4, imgwarp.cpp:1012-1113; tables initInterTab2D :213-287 with
+    interpolateLanczos4 :162-188): 8 x 8 taps, 8-bit fixed point (bit for bit) and float (the reference's summation order; the table's sin / cos
+    come from the host's libm on both sides)"""
+    for dt in (np.uint8, np.float32):
+        img = rand_u8(rng, 131, 157, cn)
+        img = img if dt == np.uint8 else (img.astype(np.float32) + 0.37) * 0.731
+        back = rand_u8(rng, 140, 170, cn).astype(dt)
+        M = _rot(ref, 157, 131)
+        kw = dict(dst=back) if border == C.BORDER_TRANSPARENT else {}
+        gk = (lambda: dict(dst=gpu(back.copy()))) if border == C.BORDER_TRANSPARENT else (lambda: {})
+        want = ref.warpAffine(img, M, (170, 140), C.INTER_LANCZOS4, border, (10, 20, 30, 40), **kw)
+        got = cpu(cvb.warpAffine(gpu(img), M, (170, 140), C.INTER_LANCZOS4, border, (10, 20, 30, 40), **gk()))
+        assert_exact(got, want, "warpAffine LANCZOS4 %s cn=%d border=%d" % (np.dtype(dt).name, cn, border))
+        want = ref.warpPerspective(img, H0, (170, 140), C.INTER_LANCZOS4 | C.WARP_INVERSE_MAP, border, 7, **kw)
+        got = cpu(cvb.warpPerspective(gpu(img), H0, (170, 140), C.INTER_LANCZOS4 | C.WARP_INVERSE_MAP, border, 7, **gk()))
+        assert_exact(got, want, "warpPerspective LANCZOS4 %s cn=%d border=%d" % (np.dtype(dt).name, cn, border))
+        yy, xx = np.mgrid[0:140, 0:170].astype(np.float32)
+        mx = (xx * 1.05 - 9.3 + 0.02 * yy).astype(np.float32); my = (yy * 0.97 - 4.6 + 0.03 * xx).astype(np.float32)
+        want = ref.remap(img, mx, my, C.INTER_LANCZOS4, border, 5, **kw)
+        got = cpu(cvb.remap(gpu(img), gpu(mx), gpu(my), C.INTER_LANCZOS4, border, 5, **gk()))
+        assert_exact(got, want, "remap LANCZOS4 %s cn=%d border=%d" % (np.dtype(dt).name, cn, border))
+
+
 def test_sift_upsample_warp(cvb, oracle, rng):
     """the 2x upsample SIFT uses: warpAffine(INTER_LINEAR | WARP_INVERSE_MAP, BORDER_REFLECT) on f32 (sift.dispatch.cpp:196-202)"""
     img = rand_u8(rng, 67, 91, 1).astype(np.float32)
