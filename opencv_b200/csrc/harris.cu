@@ -493,6 +493,41 @@ __global__ void __launch_bounds__(256) gftt_candidates_kernel(Img eig, const uns
     if (slot < cap) out[(size_t)f * cap + slot] = ((CandKey)f2ord(v) << 32) | (unsigned)(y * W + x);
 }
 
+// ---- top-K preselection: the greedy walk normally stops after a few thousand candidates, a noisy 4K frame has ~10^6 -----------------------
+// histogram of the top 12 bits of the (order-preserving) response code -> the highest bins that hold at least GF_TOP_MIN candidates ->
+// compaction of exactly those candidates.  Sorting them gives the PREFIX of the full descending order (every stronger candidate is in), so
+// the walk is the reference's as long as it ends inside the prefix; if it runs out, the frame is redone with the full sort.
+constexpr int GF_BINS = 4096, GF_TOP_MIN = 1 << 15, GF_TOP_CAP = 1 << 17;
+
+__global__ void __launch_bounds__(256) gftt_hist_kernel(const CandKey* cand, const int* counts, int cap, unsigned* hist)
+{
+    const int f = blockIdx.y, n = min(counts[f], cap);
+    const CandKey* c = cand + (size_t)f * cap;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) atomicAdd(hist + (size_t)f * GF_BINS + (unsigned)(c[i] >> 52), 1u);
+}
+__global__ void gftt_select_kernel(const unsigned* hist, int* thr_bin)
+{
+    const int f = blockIdx.x;
+    if (threadIdx.x) return;
+    const unsigned* h = hist + (size_t)f * GF_BINS;
+    unsigned cum = 0;
+    int b = GF_BINS - 1;
+    for (; b > 0; b--) { cum += h[b]; if (cum >= (unsigned)GF_TOP_MIN) break; }
+    thr_bin[f] = b;
+}
+__global__ void __launch_bounds__(256) gftt_filter_kernel(const CandKey* cand, const int* counts, int cap, const int* thr_bin, CandKey* top, int* top_cnt)
+{
+    const int f = blockIdx.y, n = min(counts[f], cap), tb = thr_bin[f];
+    const CandKey* c = cand + (size_t)f * cap;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const CandKey k = c[i];
+        if ((int)(k >> 52) >= tb) {
+            const int slot = atomicAdd(top_cnt + f, 1);
+            if (slot < GF_TOP_CAP) top[(size_t)f * GF_TOP_CAP + slot] = k;
+        }
+    }
+}
+
 }  // namespace b200cv
 
 using namespace b200cv;
@@ -542,21 +577,49 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
     gftt_candidates_kernel<<<dim3(div_up(W, 32), div_up(H, 8), frames), 256, 0, st>>>(e, d_max, quality_level, d_cand, cap, d_cnt);
     count_launch();
     TRY(cudaGetLastError());
-    std::vector<int> hcnt(frames);
+    // top-K preselection (all frames, before the one synchronisation that brings the counts back)
+    unsigned* d_hist = nullptr; int* d_thr = nullptr; int* d_topcnt = nullptr; CandKey* d_top = nullptr;
+    auto cleanup2 = [&]() { cudaFreeAsync(d_hist, st); cudaFreeAsync(d_thr, st); cudaFreeAsync(d_topcnt, st); cudaFreeAsync(d_top, st); cleanup(); };
+#undef TRY
+#define TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup2(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
+    const bool preselect = max_corners > 0;
+    if (preselect) {
+        TRY(cudaMallocAsync(&d_hist, sizeof(unsigned) * GF_BINS * frames, st));
+        TRY(cudaMallocAsync(&d_thr, sizeof(int) * frames, st));
+        TRY(cudaMallocAsync(&d_topcnt, sizeof(int) * frames, st));
+        TRY(cudaMallocAsync(&d_top, sizeof(CandKey) * (size_t)GF_TOP_CAP * frames, st));
+        TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * GF_BINS * frames, st));
+        TRY(cudaMemsetAsync(d_topcnt, 0, sizeof(int) * frames, st));
+        gftt_hist_kernel<<<dim3(128, frames), 256, 0, st>>>(d_cand, d_cnt, cap, d_hist);
+        gftt_select_kernel<<<frames, 32, 0, st>>>(d_hist, d_thr);
+        gftt_filter_kernel<<<dim3(128, frames), 256, 0, st>>>(d_cand, d_cnt, cap, d_thr, d_top, d_topcnt);
+        count_launch(3);
+        TRY(cudaGetLastError());
+    }
+    std::vector<int> hcnt(frames), hsel(frames, 0);
     TRY(cudaMemcpyAsync(hcnt.data(), d_cnt, sizeof(int) * frames, cudaMemcpyDeviceToHost, st));
+    if (preselect) TRY(cudaMemcpyAsync(hsel.data(), d_topcnt, sizeof(int) * frames, cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
     // order the candidates on the device (library radix sort: not per-pixel work), then walk them on the host in chunks --
     // the greedy minimum-distance selection is sequential and normally stops after a short prefix
     int nmax = 0;
-    for (int f = 0; f < frames; f++) { hcnt[f] = std::min(hcnt[f], cap); nmax = std::max(nmax, hcnt[f]); }
+    std::vector<int> nwalk(frames);
+    std::vector<char> partial(frames, 0);
+    for (int f = 0; f < frames; f++) {
+        hcnt[f] = std::min(hcnt[f], cap);
+        nwalk[f] = hcnt[f];
+        if (preselect && hsel[f] < hcnt[f] && hsel[f] <= GF_TOP_CAP && hsel[f] > 0) { partial[f] = 1; nwalk[f] = hsel[f]; }
+        nmax = std::max(nmax, hcnt[f]);
+    }
     size_t tmp_bytes = 0;
     if (nmax) {
         TRY(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, d_cand, d_sorted, nmax, 0, 64, st));
         TRY(cudaMallocAsync(&d_tmp, tmp_bytes, st));
         TRY(cudaMallocAsync(&d_sorted, sizeof(CandKey) * (size_t)cap * frames, st));
         for (int f = 0; f < frames; f++)
-            if (hcnt[f]) {
-                TRY(cub::DeviceRadixSort::SortKeysDescending(d_tmp, tmp_bytes, d_cand + (size_t)f * cap, d_sorted + (size_t)f * cap, hcnt[f], 0, 64, st));
+            if (nwalk[f]) {
+                const CandKey* in = partial[f] ? d_top + (size_t)f * GF_TOP_CAP : d_cand + (size_t)f * cap;
+                TRY(cub::DeviceRadixSort::SortKeysDescending(d_tmp, tmp_bytes, in, d_sorted + (size_t)f * cap, nwalk[f], 0, 64, st));
                 count_launch();
             }
     }
@@ -573,13 +636,14 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
         h_stage_cap = need;
     }
     for (int f = 0; f < frames; f++)
-        if (hcnt[f]) TRY(cudaMemcpyAsync(h_stage + (size_t)f * CHUNK, d_sorted + (size_t)f * cap, sizeof(CandKey) * std::min(CHUNK, hcnt[f]), cudaMemcpyDeviceToHost, st));
+        if (nwalk[f]) TRY(cudaMemcpyAsync(h_stage + (size_t)f * CHUNK, d_sorted + (size_t)f * cap, sizeof(CandKey) * std::min(CHUNK, nwalk[f]), cudaMemcpyDeviceToHost, st));
     TRY(cudaStreamSynchronize(st));
     std::vector<CandKey> chunk;
     std::vector<int> head, nxt;                  // accepted corners per grid cell: singly linked lists in flat arrays
     std::vector<float> ax, ay;
     for (int f = 0; f < frames; f++) {
-        const int n = hcnt[f];
+      for (int attempt = 0; attempt < 2; attempt++) {
+        const int n = nwalk[f];
         int fetched = std::min(CHUNK, n), base = 0;                  // candidates [base, fetched) are in `cur`
         const CandKey* cur = h_stage + (size_t)f * CHUNK;
         // the i-th strongest candidate; fetches another chunk when the walk gets there
@@ -636,8 +700,16 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
             }
         }
         counts[f] = accepted;
+        if (!partial[f] || accepted >= max_corners) break;
+        // the preselected prefix ran out before max_corners corners were accepted: this frame again, with every candidate in order
+        partial[f] = 0; nwalk[f] = hcnt[f];
+        TRY(cub::DeviceRadixSort::SortKeysDescending(d_tmp, tmp_bytes, d_cand + (size_t)f * cap, d_sorted + (size_t)f * cap, hcnt[f], 0, 64, st));
+        count_launch();
+        TRY(cudaMemcpyAsync(h_stage + (size_t)f * CHUNK, d_sorted + (size_t)f * cap, sizeof(CandKey) * std::min(CHUNK, hcnt[f]), cudaMemcpyDeviceToHost, st));
+        TRY(cudaStreamSynchronize(st));
+      }
     }
 #undef TRY
-    cleanup();
+    cleanup2();
     return B200CV_OK;
 }

@@ -649,6 +649,82 @@ __global__ void __launch_bounds__(256) warp_tile4_kernel(Img src, Img dst, const
     }
 }
 
+// ---- NEAREST, 8-bit: the coordinate tables of warp_tile4_kernel without the staging pass ---------------------------------------------------
+// The direct kernel evaluates the fp64 coordinate pipeline per pixel (96 thread instructions per pixel for an affine map, 174 for a projective
+// one: profiles/r02_prof_c3_geometry_before_*): here the affine adelta / bdelta / X0 / Y0 tables and the projective per-(row, column block)
+// terms are built once per 128 x 32 tile, a thread gathers 4 consecutive pixels and stores them as CN 32-bit words.
+template <int CN>
+__global__ void __launch_bounds__(256) warp_nn4_kernel(Img src, Img dst, const __grid_constant__ WarpParams p)
+{
+    typedef unsigned char T;
+    __shared__ __align__(16) int s_ad[WQ_W], s_bd[WQ_W];
+    __shared__ int s_X0[WQ_H], s_Y0[WQ_H];
+    __shared__ double s_pX[WQ_H][WQ_NB], s_pY[WQ_H][WQ_NB], s_pW[WQ_H][WQ_NB];
+    const int f = blockIdx.z, x0 = blockIdx.x * WQ_W, y0 = blockIdx.y * WQ_H;
+    const int tid = threadIdx.x;
+    const int blk0 = x0 / p.bw0;
+    if (!p.persp) {
+        if (tid < WQ_W) {
+            const double x = (double)(x0 + tid);
+            s_ad[tid] = __double2int_rn(__dmul_rn(__dmul_rn(p.M[0], x), 1024.0));
+            s_bd[tid] = __double2int_rn(__dmul_rn(__dmul_rn(p.M[3], x), 1024.0));
+        } else if (tid < WQ_W + WQ_H) {
+            const double y = (double)(y0 + tid - WQ_W);
+            s_X0[tid - WQ_W] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(p.M[1], y), p.M[2]), 1024.0)) + 512;
+            s_Y0[tid - WQ_W] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(p.M[4], y), p.M[5]), 1024.0)) + 512;
+        }
+    } else if (tid < WQ_H * WQ_NB) {
+        const int yy = tid / WQ_NB, b = tid - yy * WQ_NB;
+        const double xb = (double)((blk0 + b) * p.bw0), y = (double)(y0 + yy);
+        s_pX[yy][b] = __dadd_rn(__dadd_rn(__dmul_rn(p.M[0], xb), __dmul_rn(p.M[1], y)), p.M[2]);
+        s_pY[yy][b] = __dadd_rn(__dadd_rn(__dmul_rn(p.M[3], xb), __dmul_rn(p.M[4], y)), p.M[5]);
+        s_pW[yy][b] = __dadd_rn(__dadd_rn(__dmul_rn(p.M[6], xb), __dmul_rn(p.M[7], y)), p.M[8]);
+    }
+    __syncthreads();
+    const bool dvec = (((uintptr_t)dst.data | dst.step | dst.fstep) & 3) == 0;
+#pragma unroll 1
+    for (int g = tid; g < (WQ_W / 4) * WQ_H; g += 256) {
+        const int yy = g / (WQ_W / 4), xq = (g - yy * (WQ_W / 4)) * 4;
+        const int y = y0 + yy, x = x0 + xq;
+        if (y >= p.dh || x >= p.dw) continue;
+        int4 ad = make_int4(0, 0, 0, 0), bd = ad;
+        int X0r = 0, Y0r = 0;
+        if (!p.persp) { ad = *(const int4*)(s_ad + xq); bd = *(const int4*)(s_bd + xq); X0r = s_X0[yy]; Y0r = s_Y0[yy]; }
+        const int adv[4] = {ad.x, ad.y, ad.z, ad.w}, bdv[4] = {bd.x, bd.y, bd.z, bd.w};
+        int pb = 0, px1 = 0;
+        if (p.persp) { pb = x / p.bw0 - blk0; px1 = x - (blk0 + pb) * p.bw0; }
+        unsigned char ob[4 * CN];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int sx, sy;
+            if (p.persp) {
+                const int b = pb, x1 = px1;
+                if (++px1 == p.bw0) { px1 = 0; pb++; }
+                double W = __dadd_rn(s_pW[yy][b], __dmul_rn(p.M[6], (double)x1));
+                W = W != 0.0 ? __ddiv_rn(1.0, W) : 0.0;
+                const double fX = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(s_pX[yy][b], __dmul_rn(p.M[0], (double)x1)), W)));
+                const double fY = fmax(-2147483648.0, fmin(2147483647.0, __dmul_rn(__dadd_rn(s_pY[yy][b], __dmul_rn(p.M[3], (double)x1)), W)));
+                sx = sat_s16(__double2int_rn(fX)); sy = sat_s16(__double2int_rn(fY));
+            } else {
+                sx = sat_s16((X0r + adv[k]) >> 10); sy = sat_s16((Y0r + bdv[k]) >> 10);
+            }
+            unsigned char px[4] = {0, 0, 0, 0};
+            if (x + k < p.dw) sample_direct<T, CN, W_NN>(src, f, p, sx, sy, 0, px);
+#pragma unroll
+            for (int c = 0; c < CN; c++) ob[k * CN + c] = px[c];
+        }
+        unsigned char* dp = dst.row<T>(f, y) + (size_t)x * CN;
+        if (dvec && x + 4 <= p.dw) {
+#pragma unroll
+            for (int i = 0; i < CN; i++)
+                ((unsigned*)dp)[i] = (unsigned)ob[4 * i] | ((unsigned)ob[4 * i + 1] << 8) | ((unsigned)ob[4 * i + 2] << 16) | ((unsigned)ob[4 * i + 3] << 24);
+        } else {
+            const int n = min(4, p.dw - x);
+            for (int i = 0; i < n * CN; i++) dp[i] = ob[i];
+        }
+    }
+}
+
 static int ensure_warp_tables()
 {
     static PerDeviceFlag done_pd; bool& done = done_pd.cur();
@@ -706,6 +782,16 @@ static int launch_warp_i(const Img& s, const Img& d, const WarpParams& p, cudaSt
             need = std::max(need, fp);
         }
     const char* path = getenv("B200CV_WARP_PATH");
+    if constexpr (sizeof(T) == 1 && INTERP == W_NN) {
+        // 8-bit NEAREST: table-driven coordinates, 4 pixels per thread (BORDER_TRANSPARENT needs the per-pixel keep decision: direct kernel)
+        const bool blocks_ok = !p.persp || (p.bw0 > 0 && (WQ_W + p.bw0 - 1) / p.bw0 + 1 <= WQ_NB);
+        if (blocks_ok && p.border != B200CV_BORDER_TRANSPARENT && !(path && !strcmp(path, "direct"))) {
+            dim3 grid(div_up((unsigned)p.dw, WQ_W), div_up((unsigned)p.dh, WQ_H), (unsigned)s.frames);
+            warp_nn4_kernel<CN><<<grid, 256, 0, st>>>(s, d, p);
+            B200_LAUNCH_CHECK();
+            return B200CV_OK;
+        }
+    }
     // one tap per pixel (NEAREST) does not repay the staging pass
     // BORDER_TRANSPARENT: per-pixel keep / blend decisions, the direct kernel only
     if (INTERP == W_NN || need < 0 || need > WT_SMEM_MAX || p.border == B200CV_BORDER_TRANSPARENT || (path && !strcmp(path, "direct"))) {          // heavy minification / degenerate map: direct gather
