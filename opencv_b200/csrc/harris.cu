@@ -13,6 +13,8 @@
 // (value, position) candidates on the device; the ordered part (sort by value then address, greedy min-distance
 // acceptance on a cell grid) runs on the host over the compacted list, as it is inherently sequential.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -448,14 +450,29 @@ __host__ __device__ __forceinline__ float ord2f(unsigned o) {
 #endif
 }
 
+// eig is the function's own response map: base and pitch are multiples of 256 bytes, so 4-column groups load as one float4
+__device__ __forceinline__ float4 eig_ld4(const float* r, int x, int W)
+{
+    if (x + 3 < W) return __ldg(reinterpret_cast<const float4*>(r + x));
+    float4 v = {0.f, 0.f, 0.f, 0.f};
+    if (x < W) v.x = __ldg(r + x);
+    if (x + 1 < W) v.y = __ldg(r + x + 1);
+    if (x + 2 < W) v.z = __ldg(r + x + 2);
+    return v;
+}
 __global__ void __launch_bounds__(256) frame_max_kernel(Img eig, unsigned* maxord)
 {
-    const int f = blockIdx.y;
+    const int f = blockIdx.y, W = eig.cols;
     unsigned best = 0;    // below every real value's code
-    const long long total = (long long)eig.rows * eig.cols;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        int y = (int)(i / eig.cols), x = (int)(i - (long long)y * eig.cols);
-        best = max(best, f2ord(eig.row<float>(f, y)[x]));
+    for (int y = blockIdx.x; y < eig.rows; y += gridDim.x) {
+        const float* r = eig.row<float>(f, y);
+        for (int x = threadIdx.x * 4; x < W; x += 1024) {
+            if (x + 3 < W) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(r + x));
+                best = max(max(best, f2ord(v.x)), max(f2ord(v.y), max(f2ord(v.z), f2ord(v.w))));
+            } else
+                for (int i = x; i < W; i++) best = max(best, f2ord(__ldg(r + i)));
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -465,54 +482,116 @@ __global__ void __launch_bounds__(256) frame_max_kernel(Img eig, unsigned* maxor
 // candidate key: order-preserving bits of the response in the high word, row-major position in the low word.  Sorting keys
 // descending = strongest first, equal responses: larger address first (featureselect.cpp:55-60).
 typedef unsigned long long CandKey;
+constexpr int GF_BINS = 4096, GF_TOP_MIN = 1 << 15, GF_TOP_CAP = 1 << 17;
+constexpr int GC_R = 8;        // rows per tile of the candidate kernel (4 columns x GC_R rows per thread: one bit each in a 32-bit mask)
 
-__global__ void __launch_bounds__(256) gftt_candidates_kernel(Img eig, const unsigned* maxord, double quality, CandKey* out, int cap, int* counts)
+// Candidates = pixels that survive threshold(eig, max * quality, TOZERO) and equal the 3x3 maximum of the thresholded map (dilate + compare,
+// modules/imgproc/src/featureselect.cpp:127-166), 1-pixel frame excluded.  A thread walks down GC_R rows of 4 columns with the three window rows in
+// registers; the block reserves its output range with ONE atomic per 1024 x GC_R tile (a per-candidate atomic on the frame's counter serialises:
+// 10^6 candidates on a noisy 4K frame cost 0.16 ms per frame that way); the histogram of the response codes' top 12 bits (for the top-K
+// preselection below) is kept in shared memory and flushed once per block.
+__global__ void __launch_bounds__(256) gftt_candidates_kernel(Img eig, const unsigned* maxord, double quality, CandKey* out, int cap, int* counts, unsigned* hist)
 {
-    const int f = blockIdx.z;
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    const int W = eig.cols, H = eig.rows;
-    if (x < 1 || y < 1 || x >= W - 1 || y >= H - 1) return;
-    const float maxv = ord2f(maxord[f]);
-    const float thr = (float)((double)maxv * quality);            // threshold(eig, maxVal*qualityLevel, TOZERO) compares in float
-    float v = eig.row<float>(f, y)[x];
-    if (!(v > thr)) return;                                       // TOZERO: becomes 0 and can never be a candidate
-    if (v == 0.f) return;
-    bool ismax = true;
+    __shared__ unsigned s_hist[GF_BINS];
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int f = blockIdx.y, W = eig.cols, H = eig.rows;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (hist) {
+        for (int i = tid; i < GF_BINS; i += 256) s_hist[i] = 0;
+        __syncthreads();
+    }
+    const float thr = (float)((double)ord2f(maxord[f]) * quality);            // threshold(eig, maxVal*qualityLevel, TOZERO) compares in float
+    const int tx = (W + 1023) / 1024, ty = (H + GC_R - 1) / GC_R;
+    // columns x0-1 .. x0+4 of row y, thresholded; rows / columns outside the image only feed centres that are excluded anyway
+    auto load_row = [&](int y, int x0, float (&a)[6]) {
+        if (y < 0 || y >= H || x0 >= W) { a[0] = a[1] = a[2] = a[3] = a[4] = a[5] = 0.f; return; }
+        const float* r = eig.row<float>(f, y);
+        const float4 v = eig_ld4(r, x0, W);
+        a[0] = x0 > 0 ? __ldg(r + x0 - 1) : 0.f;
+        a[1] = v.x; a[2] = v.y; a[3] = v.z; a[4] = v.w;
+        a[5] = x0 + 4 < W ? __ldg(r + x0 + 4) : 0.f;
 #pragma unroll
-    for (int dy = -1; dy <= 1; dy++) {
-        const float* r = eig.row<float>(f, y + dy);
+        for (int i = 0; i < 6; i++) a[i] = a[i] > thr ? a[i] : 0.f;
+    };
+    for (int t = blockIdx.x; t < tx * ty; t += gridDim.x) {
+        const int y0 = (t / tx) * GC_R, x0 = (t % tx) * 1024 + tid * 4;
+        unsigned mask = 0;
+        if (x0 < W) {
+            float a[6], b[6], c[6];
+            load_row(y0 - 1, x0, a);
+            load_row(y0, x0, b);
 #pragma unroll
-        for (int dx = -1; dx <= 1; dx++) {
-            float n = r[x + dx];
-            n = n > thr ? n : 0.f;
-            if (n > v) ismax = false;
+            for (int r = 0; r < GC_R; r++) {
+                const int y = y0 + r;
+                load_row(y + 1, x0, c);
+                float m[6];
+#pragma unroll
+                for (int i = 0; i < 6; i++) m[i] = fmaxf(fmaxf(a[i], b[i]), c[i]);
+                if (y >= 1 && y < H - 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const float v = b[j + 1];
+                        const int x = x0 + j;
+                        if (v != 0.f && x >= 1 && x < W - 1 && !(fmaxf(fmaxf(m[j], m[j + 1]), m[j + 2]) > v)) mask |= 1u << (r * 4 + j);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 6; i++) { a[i] = b[i]; b[i] = c[i]; }
+            }
+        }
+        const int cnt = __popc(mask);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { const int c = s_warp[w]; s_warp[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(counts + f, tot) : 0;
+        }
+        __syncthreads();
+        int slot = s_base + s_warp[wid] + incl - cnt;
+        while (mask) {
+            const int bit = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int y = y0 + (bit >> 2), x = x0 + (bit & 3);
+            const unsigned code = f2ord(__ldg(eig.row<float>(f, y) + x));
+            if (slot < cap) {
+                out[(size_t)f * cap + slot] = ((CandKey)code << 32) | (unsigned)(y * W + x);
+                if (hist) atomicAdd(&s_hist[code >> 20], 1u);
+            }
+            slot++;
         }
     }
-    if (!ismax) return;
-    int slot = atomicAdd(counts + f, 1);
-    if (slot < cap) out[(size_t)f * cap + slot] = ((CandKey)f2ord(v) << 32) | (unsigned)(y * W + x);
+    if (hist) {
+        __syncthreads();
+        for (int i = tid; i < GF_BINS; i += 256)
+            if (s_hist[i]) atomicAdd(hist + (size_t)f * GF_BINS + i, s_hist[i]);
+    }
 }
 
 // ---- top-K preselection: the greedy walk normally stops after a few thousand candidates, a noisy 4K frame has ~10^6 -----------------------
 // histogram of the top 12 bits of the (order-preserving) response code -> the highest bins that hold at least GF_TOP_MIN candidates ->
 // compaction of exactly those candidates.  Sorting them gives the PREFIX of the full descending order (every stronger candidate is in), so
 // the walk is the reference's as long as it ends inside the prefix; if it runs out, the frame is redone with the full sort.
-constexpr int GF_BINS = 4096, GF_TOP_MIN = 1 << 15, GF_TOP_CAP = 1 << 17;
-
-__global__ void __launch_bounds__(256) gftt_hist_kernel(const CandKey* cand, const int* counts, int cap, unsigned* hist)
+__global__ void __launch_bounds__(128) gftt_select_kernel(const unsigned* hist, int* thr_bin)
 {
-    const int f = blockIdx.y, n = min(counts[f], cap);
-    const CandKey* c = cand + (size_t)f * cap;
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) atomicAdd(hist + (size_t)f * GF_BINS + (unsigned)(c[i] >> 52), 1u);
-}
-__global__ void gftt_select_kernel(const unsigned* hist, int* thr_bin)
-{
-    const int f = blockIdx.x;
-    if (threadIdx.x) return;
+    __shared__ unsigned part[128];
+    const int f = blockIdx.x, t = threadIdx.x;
     const unsigned* h = hist + (size_t)f * GF_BINS;
+    unsigned sum = 0;
+    for (int i = 0; i < 32; i++) sum += h[t * 32 + i];
+    part[t] = sum;
+    __syncthreads();
+    if (t) return;
     unsigned cum = 0;
-    int b = GF_BINS - 1;
-    for (; b > 0; b--) { cum += h[b]; if (cum >= (unsigned)GF_TOP_MIN) break; }
+    int g = 127;
+    for (; g > 0 && cum + part[g] < (unsigned)GF_TOP_MIN; g--) cum += part[g];
+    int b = g * 32 + 31;
+    for (; b > g * 32; b--) { cum += h[b]; if (cum >= (unsigned)GF_TOP_MIN) break; }
     thr_bin[f] = b;
 }
 __global__ void __launch_bounds__(256) gftt_filter_kernel(const CandKey* cand, const int* counts, int cap, const int* thr_bin, CandKey* top, int* top_cnt)
@@ -549,6 +628,9 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
     int rc;
     if ((rc = check_mat(src, "src"))) return rc;
     B200_REQUIRE(corners && counts && max_out > 0, "bad output arguments");
+    const bool trace = getenv("B200CV_GFTT_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (!trace) return; auto t = std::chrono::steady_clock::now(); fprintf(stderr, "gftt %-14s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_last).count()); t_last = t; };
     B200_REQUIRE(quality_level > 0 && min_distance >= 0 && max_corners >= 0, "bad parameters");
     const int W = src->cols, H = src->rows, frames = src->frames > 1 ? src->frames : 1;
     cudaStream_t st = as_stream(stream);
@@ -572,17 +654,15 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
     rc = corner_response(src, &eig, block_size, gradient_size, k, B200CV_BORDER_REFLECT_101, use_harris ? 0 : 1, stream);
     if (rc) { cleanup(); return rc; }
     Img e = make_img(&eig);
-    frame_max_kernel<<<dim3(std::min(1024u, div_up((unsigned)((long long)W * H), 256)), frames), 256, 0, st>>>(e, d_max);
+    frame_max_kernel<<<dim3(std::min((unsigned)H, 148u * 8u), frames), 256, 0, st>>>(e, d_max);
     count_launch();
-    gftt_candidates_kernel<<<dim3(div_up(W, 32), div_up(H, 8), frames), 256, 0, st>>>(e, d_max, quality_level, d_cand, cap, d_cnt);
-    count_launch();
-    TRY(cudaGetLastError());
     // top-K preselection (all frames, before the one synchronisation that brings the counts back)
     unsigned* d_hist = nullptr; int* d_thr = nullptr; int* d_topcnt = nullptr; CandKey* d_top = nullptr;
     auto cleanup2 = [&]() { cudaFreeAsync(d_hist, st); cudaFreeAsync(d_thr, st); cudaFreeAsync(d_topcnt, st); cudaFreeAsync(d_top, st); cleanup(); };
 #undef TRY
 #define TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup2(); return cuda_fail(e_, #call, __FILE__, __LINE__); } } while (0)
-    const bool preselect = max_corners > 0;
+    const char* ps_env = getenv("B200CV_GFTT_PRESELECT");                        // "0": always sort every candidate (A/B and the parity test)
+    const bool preselect = max_corners > 0 && !(ps_env && ps_env[0] == '0');
     if (preselect) {
         TRY(cudaMallocAsync(&d_hist, sizeof(unsigned) * GF_BINS * frames, st));
         TRY(cudaMallocAsync(&d_thr, sizeof(int) * frames, st));
@@ -590,16 +670,25 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
         TRY(cudaMallocAsync(&d_top, sizeof(CandKey) * (size_t)GF_TOP_CAP * frames, st));
         TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * GF_BINS * frames, st));
         TRY(cudaMemsetAsync(d_topcnt, 0, sizeof(int) * frames, st));
-        gftt_hist_kernel<<<dim3(128, frames), 256, 0, st>>>(d_cand, d_cnt, cap, d_hist);
-        gftt_select_kernel<<<frames, 32, 0, st>>>(d_hist, d_thr);
+    }
+    {
+        const unsigned tiles = div_up(W, 1024) * div_up(H, GC_R);
+        gftt_candidates_kernel<<<dim3(std::min(tiles, 148u * 8u), frames), 256, 0, st>>>(e, d_max, quality_level, d_cand, cap, d_cnt, d_hist);
+        count_launch();
+        TRY(cudaGetLastError());
+    }
+    if (preselect) {
+        gftt_select_kernel<<<frames, 128, 0, st>>>(d_hist, d_thr);
         gftt_filter_kernel<<<dim3(128, frames), 256, 0, st>>>(d_cand, d_cnt, cap, d_thr, d_top, d_topcnt);
-        count_launch(3);
+        count_launch(2);
         TRY(cudaGetLastError());
     }
     std::vector<int> hcnt(frames), hsel(frames, 0);
     TRY(cudaMemcpyAsync(hcnt.data(), d_cnt, sizeof(int) * frames, cudaMemcpyDeviceToHost, st));
     if (preselect) TRY(cudaMemcpyAsync(hsel.data(), d_topcnt, sizeof(int) * frames, cudaMemcpyDeviceToHost, st));
+    lap("enqueue 1");
     TRY(cudaStreamSynchronize(st));
+    lap("sync 1");
     // order the candidates on the device (library radix sort: not per-pixel work), then walk them on the host in chunks --
     // the greedy minimum-distance selection is sequential and normally stops after a short prefix
     int nmax = 0;
@@ -611,20 +700,8 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
         if (preselect && hsel[f] < hcnt[f] && hsel[f] <= GF_TOP_CAP && hsel[f] > 0) { partial[f] = 1; nwalk[f] = hsel[f]; }
         nmax = std::max(nmax, hcnt[f]);
     }
-    size_t tmp_bytes = 0;
-    if (nmax) {
-        TRY(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, d_cand, d_sorted, nmax, 0, 64, st));
-        TRY(cudaMallocAsync(&d_tmp, tmp_bytes, st));
-        TRY(cudaMallocAsync(&d_sorted, sizeof(CandKey) * (size_t)cap * frames, st));
-        for (int f = 0; f < frames; f++)
-            if (nwalk[f]) {
-                const CandKey* in = partial[f] ? d_top + (size_t)f * GF_TOP_CAP : d_cand + (size_t)f * cap;
-                TRY(cub::DeviceRadixSort::SortKeysDescending(d_tmp, tmp_bytes, in, d_sorted + (size_t)f * cap, nwalk[f], 0, 64, st));
-                count_launch();
-            }
-    }
-    // the strongest CHUNK candidates of EVERY frame come back with one synchronisation (page-locked staging: the copies queue behind the
-    // sorts and overlap them); the walk fetches further chunks only if it gets that far (it normally stops after a short prefix)
+    // the strongest CHUNK candidates of EVERY frame come back with one synchronisation (page-locked staging); the walk fetches further chunks
+    // only if it gets that far (it normally stops after a short prefix)
     const int CHUNK = 1 << 14;
     static thread_local CandKey* h_stage = nullptr;
     static thread_local size_t h_stage_cap = 0;
@@ -635,9 +712,45 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
         TRY(cudaHostAlloc((void**)&h_stage, need * sizeof(CandKey), cudaHostAllocDefault));
         h_stage_cap = need;
     }
-    for (int f = 0; f < frames; f++)
-        if (nwalk[f]) TRY(cudaMemcpyAsync(h_stage + (size_t)f * CHUNK, d_sorted + (size_t)f * cap, sizeof(CandKey) * std::min(CHUNK, nwalk[f]), cudaMemcpyDeviceToHost, st));
+    // a radix sort of 10^4..10^5 keys is ten launches of a few microseconds each: the frames' sorts (and the copies of their heads) run on
+    // side streams next to each other, forked from / joined to the caller's stream with events
+    constexpr int NSIDE = 4;
+    struct Side { int dev = -1; cudaStream_t s[NSIDE]; cudaEvent_t fork, join[NSIDE]; };
+    static thread_local Side side;
+    int cur_dev = 0;
+    TRY(cudaGetDevice(&cur_dev));
+    const char* ss_env = getenv("B200CV_GFTT_STREAMS");                          // "1": the sorts queue on the caller's stream one after the other
+    const int ns = (ss_env && ss_env[0] == '1') ? 1 : std::min(frames, NSIDE);
+    if (ns > 1 && side.dev != cur_dev) {
+        if (side.dev >= 0) { for (int i = 0; i < NSIDE; i++) { cudaStreamDestroy(side.s[i]); cudaEventDestroy(side.join[i]); } cudaEventDestroy(side.fork); side.dev = -1; }
+        for (int i = 0; i < NSIDE; i++) { TRY(cudaStreamCreateWithFlags(&side.s[i], cudaStreamNonBlocking)); TRY(cudaEventCreateWithFlags(&side.join[i], cudaEventDisableTiming)); }
+        TRY(cudaEventCreateWithFlags(&side.fork, cudaEventDisableTiming));
+        side.dev = cur_dev;
+    }
+    size_t tmp_bytes = 0;
+    if (nmax) {
+        TRY(cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp_bytes, d_cand, d_sorted, nmax, 0, 64, st));
+        tmp_bytes = (tmp_bytes + 255) & ~(size_t)255;
+        TRY(cudaMallocAsync(&d_tmp, tmp_bytes * ns, st));
+        TRY(cudaMallocAsync(&d_sorted, sizeof(CandKey) * (size_t)cap * frames, st));
+        if (ns > 1) {
+            TRY(cudaEventRecord(side.fork, st));
+            for (int i = 0; i < ns; i++) TRY(cudaStreamWaitEvent(side.s[i], side.fork, 0));
+        }
+        for (int f = 0; f < frames; f++)
+            if (nwalk[f]) {
+                cudaStream_t sf = ns > 1 ? side.s[f % ns] : st;
+                const CandKey* in = partial[f] ? d_top + (size_t)f * GF_TOP_CAP : d_cand + (size_t)f * cap;
+                TRY(cub::DeviceRadixSort::SortKeysDescending((char*)d_tmp + tmp_bytes * (f % ns), tmp_bytes, in, d_sorted + (size_t)f * cap, nwalk[f], 0, 64, sf));
+                count_launch();
+                TRY(cudaMemcpyAsync(h_stage + (size_t)f * CHUNK, d_sorted + (size_t)f * cap, sizeof(CandKey) * std::min(CHUNK, nwalk[f]), cudaMemcpyDeviceToHost, sf));
+            }
+        if (ns > 1)
+            for (int i = 0; i < ns; i++) { TRY(cudaEventRecord(side.join[i], side.s[i])); TRY(cudaStreamWaitEvent(st, side.join[i], 0)); }
+    }
+    lap("enqueue 2");
     TRY(cudaStreamSynchronize(st));
+    lap("sync 2");
     std::vector<CandKey> chunk;
     std::vector<int> head, nxt;                  // accepted corners per grid cell: singly linked lists in flat arrays
     std::vector<float> ax, ay;
@@ -710,6 +823,8 @@ extern "C" int b200cv_good_features_to_track(const b200cvMat* src, float* corner
       }
     }
 #undef TRY
+    lap("walk");
     cleanup2();
+    lap("free");
     return B200CV_OK;
 }

@@ -42,11 +42,14 @@ struct RSRow {              // per destination row of the tile (shared memory)
 static inline int rs_dp2a_s(int a, unsigned b, int c) { return c + (int)(short)(a & 0xffff) * (int)(b & 0xffu) + (a >> 16) * (int)((b >> 8) & 0xffu); }
 static inline unsigned rs_umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline unsigned rs_funnel_r(unsigned lo, unsigned hi, unsigned sh) { return sh ? (lo >> sh) | (hi << (32 - sh)) : lo; }
+static inline unsigned rs_madhi(unsigned a, unsigned b, unsigned c) { return rs_umulhi(a, b) + c; }
 #else
 // dp2a.lo.s32.u32: a = two s16 taps, b = bytes 0 and 1: c + a.lo * b.byte0 + a.hi * b.byte1
 __device__ __forceinline__ int rs_dp2a_s(int a, unsigned b, int c) { int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 __device__ __forceinline__ unsigned rs_umulhi(unsigned a, unsigned b) { return __umulhi(a, b); }
 __device__ __forceinline__ unsigned rs_funnel_r(unsigned lo, unsigned hi, unsigned sh) { return __funnelshift_r(lo, hi, sh); }
+// hi(a * b) + c in one IMAD.HI (the compiler fuses one addend on its own, not the rounding constant)
+__device__ __forceinline__ unsigned rs_madhi(unsigned a, unsigned b, unsigned c) { unsigned d; asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 #endif
 
 // NW words starting AT byte A of the row (A need not be aligned): NW + 1 aligned loads + funnel shifts
@@ -154,10 +157,13 @@ __device__ __forceinline__ unsigned rs_vpass_item(const unsigned char* const* mr
     if constexpr (!CUBIC) {
         const uint2 m0 = *(const uint2*)(mrow[0] + e0 * 2), m1 = *(const uint2*)(mrow[1] + e0 * 2);
         const unsigned T0[4] = {m0.x & 0xffffu, m0.x >> 16, m0.y & 0xffffu, m0.y >> 16}, T1[4] = {m1.x & 0xffffu, m1.x >> 16, m1.y & 0xffffu, m1.y >> 16};
-        unsigned v[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = (rs_umulhi(yr.bs[0], T0[i]) + rs_umulhi(yr.bs[1], T1[i]) + 2u) >> 2;      // <= 255: b0 + b1 = 2048, T <= 32640
-        out = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+        // (b * T) >> 16 per tap and element (VResizeLinear's two separately floored products): the products fit 32 bits (b <= 2048, T <= 32640), so
+        // a plain IMAD and the upper half-word do it -- IMAD.HI issues at a fraction of IMAD's rate.  One PRMT takes the upper halves of TWO
+        // elements' products into one register; the sums (<= 1023 + 2) of two elements are then added, rounded and shifted together.
+        const unsigned b0 = yr.bs[0] >> 16, b1 = yr.bs[1] >> 16;
+        const unsigned s01 = __byte_perm(b0 * T0[0], b0 * T0[1], 0x7632) + __byte_perm(b1 * T1[0], b1 * T1[1], 0x7632) + 0x00020002u;
+        const unsigned s23 = __byte_perm(b0 * T0[2], b0 * T0[3], 0x7632) + __byte_perm(b1 * T1[2], b1 * T1[3], 0x7632) + 0x00020002u;
+        out = __byte_perm(s01 >> 2, s23 >> 2, 0x6420);                     // ((sum + 2) >> 2) <= 255: bytes 0 and 2 of each pair, no mask
     } else {
         float S[4][4];
 #pragma unroll
@@ -232,6 +238,14 @@ __device__ __forceinline__ void rs_vpass_thread(int tid, int nthreads, const uns
         const unsigned char* mrow[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) mrow[k] = mid + (size_t)yr.r[k] * (RSCfg<CN, CUBIC>::E * RSCfg<CN, CUBIC>::MIDB);
+        if (vec_store && ne == RSCfg<CN, CUBIC>::E) {          // full-width tile: every offset of the row is a compile-time constant past the lane's base
+#pragma unroll
+            for (int i = 0; i < NQ / 32; i++) {
+                const int e0 = 4 * (lane + 32 * i);
+                *(unsigned*)(drow + e0) = rs_vpass_item<CN, CUBIC>(mrow, yr, e0, x0 * CN + e0, vec_limit);
+            }
+            continue;
+        }
         for (int q = lane; q < nq; q += 32) {
             const int e0 = 4 * q;
             const unsigned out = rs_vpass_item<CN, CUBIC>(mrow, yr, e0, x0 * CN + e0, vec_limit);

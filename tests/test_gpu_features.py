@@ -124,6 +124,20 @@ def test_good_features_4k(cvb, ref, rng):
     assert len(gs ^ ws) <= 20, "corner sets differ in %d entries" % len(gs ^ ws)
 
 
+@pytest.mark.parametrize("max_corners,mind", [(1000, 10), (300, 0), (6000, 60), (50000, 3)])
+def test_good_features_preselection_equals_full_sort(cvb, rng, monkeypatch, max_corners, mind):
+    """the top-K preselection (histogram of the response code, compaction, sort of the prefix) gives the corner list of the full sort:
+    the walk ending inside the prefix (1000/10, 300/0), the prefix running out -> redone with every candidate (6000/60), more corners
+    asked for than the prefix holds (50000/3)"""
+    img = rng.integers(0, 256, (2160, 3840), dtype=np.uint8)              # noise: ~10^6 local maxima above the quality level
+    d = gpu(img)
+    got, gq = cvb.goodFeaturesToTrack(d, max_corners, 0.01, mind, 3, 3, True, 0.04, with_quality=True)
+    monkeypatch.setenv("B200CV_GFTT_PRESELECT", "0")
+    want, wq = cvb.goodFeaturesToTrack(d, max_corners, 0.01, mind, 3, 3, True, 0.04, with_quality=True)
+    assert len(got) == len(want) and len(got) > 0
+    assert np.array_equal(got, want) and np.array_equal(gq, wq)
+
+
 @pytest.mark.parametrize("shape,upscale", [((135, 240), True), ((100, 75), True), ((96, 128), False)])
 def test_sift_pyramid(cvb, oracle, rng, shape, upscale):
     from oracle.api import unpack_pyramid

@@ -32,6 +32,7 @@ u16 = (torch.randint(0, 65536, (8, 2160, 3840, 1), dtype=torch.int32, device=dev
 o16 = torch.empty_like(u16)
 _sm = torch.nn.functional.interpolate(torch.rand((1, 1, 135, 240), device=dev), size=(1080, 1920), mode="bilinear")
 sift_img = (_sm[0, 0] * 255).to(torch.uint8).contiguous()
+smooth4k = (torch.nn.functional.interpolate(torch.rand((4, 1, 270, 480), device=dev), size=(2160, 3840), mode="bicubic").clamp(0, 1) * 255).to(torch.uint8).reshape(4, 2160, 3840, 1).contiguous()
 
 ops = {
     "blur_u8_k3": (lambda: cvb.blur(u8, (3, 3), dst=o8), nbytes(u8, o8)),
@@ -60,6 +61,8 @@ ops = {
     "integral_sq_4k": (lambda: cvb.integral(u8[:4], with_sqsum=True), nbytes(u8[:4]) * 13),
     "gauss_u16_k5": (lambda: cvb.GaussianBlur(u16, (5, 5), 0, dst=o16), nbytes(u16, o16)),
     "gauss_u16_k15": (lambda: cvb.GaussianBlur(u16, (15, 15), 0, dst=o16), nbytes(u16, o16)),
+    "gftt_4k_noise": (lambda: cvb.goodFeaturesToTrack(u8[:4], 1000, 0.01, 10, 3, 3, True, 0.04), nbytes(u8[:4])),
+    "gftt_4k_smooth": (lambda: cvb.goodFeaturesToTrack(smooth4k, 1000, 0.01, 10, 3, 3, True, 0.04), nbytes(smooth4k)),
     "sift_detect_1080p": (lambda: cvb.sift_detectAndCompute(sift_img), nbytes(sift_img) * 5),
 }
 for name, (fn, nb) in ops.items():
