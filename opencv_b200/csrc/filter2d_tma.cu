@@ -125,10 +125,9 @@ __global__ void __launch_bounds__(256, 2) filter2d_tma_kernel(const __grid_const
         float acc[8];
 #pragma unroll
         for (int o = 0; o < 8; o++) acc[o] = p.delta;
-#pragma unroll 1
-        for (int ky = p.ky0; ky < p.ky1; ky++) {
+        // one kernel row: the thread's window (128-bit shared loads, swizzled chunks) against the row's KB taps
+        auto kernel_row = [&](int ky, const float* kr) {
             const float4* vp = (const float4*)(s_f + (r + ky) * FT_IW);
-            const float* kr = p.k + ky * KB;
             float win[NV * 4];
 #pragma unroll
             for (int w = 0; w < NV; w++) {
@@ -147,6 +146,15 @@ __global__ void __launch_bounds__(256, 2) filter2d_tma_kernel(const __grid_const
                     else acc[o] = fmaf(t, win[OFF + o + i], acc[o]);
                 }
             }
+        };
+        if constexpr (KB <= 7) {
+            // small kernels: every row unrolled, the taps are FFMA constant-bank operands at compile-time offsets (no LDC, no loop); rows of
+            // zeros are not skipped -- fma(0, x, s) == s for the finite x of an image
+#pragma unroll
+            for (int ky = 0; ky < KB; ky++) kernel_row(ky, p.k + ky * KB);
+        } else {
+#pragma unroll 1
+            for (int ky = p.ky0; ky < p.ky1; ky++) kernel_row(ky, p.k + ky * KB);
         }
         ft_store8<DT>(dst.row<DT>(f, gy) + gx, acc, dvec, min(8, p.W - gx));
     }

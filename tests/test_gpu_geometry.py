@@ -79,6 +79,17 @@ def test_resize_4k_to_8k(cvb, ref, rng):
         assert_exact(cpu(cvb.resize(gpu(img), (7680, 4320), interpolation=interp)), ref.resize(img, (7680, 4320), interp), "4K->8K interp %d" % interp)
 
 
+@pytest.mark.parametrize("cn", [1, 3, 4])
+def test_resize_nearest_first_version(cvb, rng, monkeypatch, cn):
+    """the per-pixel NEAREST kernel (B200CV_RESIZE_NN_PATH=v1; the default when shrinking, for float and for unaligned images) == the walking kernel"""
+    img = gpu(rand_u8(rng, 211, 333, cn))
+    for dsz in ((500, 317), (96, 100), (666, 422)):
+        monkeypatch.setenv("B200CV_RESIZE_NN_PATH", "walk")
+        got = cpu(cvb.resize(img, dsz, interpolation=C.INTER_NEAREST))
+        monkeypatch.setenv("B200CV_RESIZE_NN_PATH", "v1")
+        assert_exact(cpu(cvb.resize(img, dsz, interpolation=C.INTER_NEAREST)), got, "NEAREST v1 vs walking kernel %s cn=%d" % (dsz, cn))
+
+
 def _rot(oracle, w, h, ang=7.0, sc=0.9):
     return oracle.getRotationMatrix2D((w / 2.0, h / 2.0), ang, sc) if oracle.has("get_rotation_matrix2d") else \
         np.array([[sc * np.cos(np.deg2rad(ang)), sc * np.sin(np.deg2rad(ang)), 3.0], [-sc * np.sin(np.deg2rad(ang)), sc * np.cos(np.deg2rad(ang)), 5.0]])
