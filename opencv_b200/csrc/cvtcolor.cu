@@ -307,7 +307,7 @@ extern "C" int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int 
     }
     B200_REQUIRE(src->cols == dst->cols && src->rows == dst->rows, "src/dst size mismatch");
     B200_REQUIRE((src->frames > 1 ? src->frames : 1) == (dst->frames > 1 ? dst->frames : 1), "src/dst batch mismatch");
-    if (B200CV_DEPTH(src->type) != B200CV_8U || B200CV_DEPTH(dst->type) != B200CV_8U) return B200CV_NOT_IMPLEMENTED;
+    if (B200CV_DEPTH(src->type) != B200CV_8U || B200CV_DEPTH(dst->type) != B200CV_8U) return cvt_color_depth(src, dst, code, as_stream(stream));   // 16U / 32F: cvtcolor_depth.cu
     const int scn = B200CV_CN(src->type), dcn = B200CV_CN(dst->type);
     Img s = make_img(src), d = make_img(dst);
     cudaStream_t st = as_stream(stream);

@@ -1,0 +1,54 @@
+"""GPU parity: cvtColor on CV_16U and CV_32F images (cvtcolor_depth.cu) against the compiled reference -- BIT-EXACT, floats included: the
+kernel reproduces the reference's vector-body / scalar-tail split of every row (the last width % 8 float pixels run GCC's contraction of
+the scalar statement).  Widths with and without tails, 3 and 4 channels, through the device ABI and through the host (HAL) path."""
+import numpy as np
+import pytest
+
+import opencv_b200 as C
+from util import assert_exact, cpu, gpu
+
+pytestmark = pytest.mark.gpu
+
+FROM3 = [(C.COLOR_BGR2BGRA, 4), (C.COLOR_BGR2RGBA, 4), (C.COLOR_BGR2RGB, 3), (C.COLOR_BGR2GRAY, 1), (C.COLOR_RGB2GRAY, 1),
+         (C.COLOR_BGR2YCrCb, 3), (C.COLOR_RGB2YCrCb, 3), (C.COLOR_BGR2YUV, 3), (C.COLOR_RGB2YUV, 3),
+         (C.COLOR_YCrCb2BGR, 3), (C.COLOR_YCrCb2RGB, 3), (C.COLOR_YUV2BGR, 3), (C.COLOR_YUV2RGB, 3), (C.COLOR_YCrCb2BGR, 4), (C.COLOR_YUV2RGB, 4)]
+FROM4 = [(C.COLOR_BGRA2BGR, 3), (C.COLOR_RGBA2BGR, 3), (C.COLOR_BGRA2RGBA, 4), (C.COLOR_BGRA2GRAY, 1), (C.COLOR_RGBA2GRAY, 1),
+         (C.COLOR_BGR2YCrCb, 3), (C.COLOR_RGB2YUV, 3)]
+FROM1 = [(C.COLOR_GRAY2BGR, 3), (C.COLOR_GRAY2BGRA, 4)]
+SHAPES = [(37, 29), (64, 1024), (255, 263), (1, 1), (3, 8)]
+
+
+def _img(rng, dtype, h, w, cn):
+    if dtype == np.uint16:
+        a = rng.integers(0, 65536, (h, w, cn), dtype=np.uint16)
+    else:
+        a = (rng.random((h, w, cn), dtype=np.float32) * 1.5 - 0.25).astype(np.float32)       # beyond [0, 1] on both sides: nothing clamps
+    return a[..., 0] if cn == 1 else a
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32])
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("scn,code,dcn", [(3,) + c for c in FROM3] + [(4,) + c for c in FROM4] + [(1,) + c for c in FROM1])
+def test_cvt_depths(cvb, ref, rng, dtype, shape, scn, code, dcn):
+    img = _img(rng, dtype, shape[0], shape[1], scn)
+    got = cpu(cvb.cvtColor(gpu(img), code, dcn))
+    assert got.dtype == dtype
+    assert_exact(got, ref.cvtColor(img, code, dcn), "cvtColor %s code=%d scn=%d dcn=%d %s" % (np.dtype(dtype).name, code, scn, dcn, shape))
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32])
+def test_cvt_depths_host_path_and_4k(cvb, ref, rng, dtype):
+    """numpy in, numpy out (b200cv_host_cvt_color = what the HAL entries call) on a 4K frame"""
+    img = _img(rng, dtype, 2160, 3840, 3)
+    for code, dcn in ((C.COLOR_BGR2GRAY, 1), (C.COLOR_BGR2YUV, 3), (C.COLOR_YCrCb2RGB, 3)):
+        got = cvb.cvtColor(img, code, dcn)
+        assert isinstance(got, np.ndarray)
+        assert_exact(got, ref.cvtColor(img, code, dcn), "host cvtColor %s code=%d" % (np.dtype(dtype).name, code))
+
+
+def test_cvt_depths_declined(cvb, rng):
+    """families that exist only for 8-bit images say so (a stock OpenCV then runs its own code)"""
+    img = gpu(_img(rng, np.float32, 16, 16, 3))
+    for code in (C.COLOR_BGR2HSV, C.COLOR_BGR2Lab, C.COLOR_BGR2XYZ):
+        with pytest.raises(Exception):
+            cvb.cvtColor(img, code, 3)

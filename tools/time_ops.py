@@ -32,6 +32,10 @@ u16 = (torch.randint(0, 65536, (8, 2160, 3840, 1), dtype=torch.int32, device=dev
 o16 = torch.empty_like(u16)
 _sm = torch.nn.functional.interpolate(torch.rand((1, 1, 135, 240), device=dev), size=(1080, 1920), mode="bilinear")
 sift_img = (_sm[0, 0] * 255).to(torch.uint8).contiguous()
+f32c3 = torch.rand((4, 2160, 3840, 3), device=dev)
+of32c3 = torch.empty_like(f32c3)
+u16c3 = torch.randint(0, 65536, (8, 2160, 3840, 3), dtype=torch.int32, device=dev).to(torch.uint16)
+ou16c3 = torch.empty_like(u16c3)
 smooth4k = (torch.nn.functional.interpolate(torch.rand((4, 1, 270, 480), device=dev), size=(2160, 3840), mode="bicubic").clamp(0, 1) * 255).to(torch.uint8).reshape(4, 2160, 3840, 1).contiguous()
 
 ops = {
@@ -63,6 +67,12 @@ ops = {
     "gauss_u16_k15": (lambda: cvb.GaussianBlur(u16, (15, 15), 0, dst=o16), nbytes(u16, o16)),
     "gftt_4k_noise": (lambda: cvb.goodFeaturesToTrack(u8[:4], 1000, 0.01, 10, 3, 3, True, 0.04), nbytes(u8[:4])),
     "gftt_4k_smooth": (lambda: cvb.goodFeaturesToTrack(smooth4k, 1000, 0.01, 10, 3, 3, True, 0.04), nbytes(smooth4k)),
+    "cvt_f32_bgr2gray_4k": (lambda: cvb.cvtColor(f32c3, cvb.COLOR_BGR2GRAY, dst=o32[:4]), nbytes(f32c3, o32[:4])),
+    "cvt_f32_bgr2yuv_4k": (lambda: cvb.cvtColor(f32c3, cvb.COLOR_BGR2YUV, dst=of32c3), nbytes(f32c3, of32c3)),
+    "cvt_f32_yuv2bgr_4k": (lambda: cvb.cvtColor(f32c3, cvb.COLOR_YUV2BGR, dst=of32c3), nbytes(f32c3, of32c3)),
+    "cvt_u16_bgr2gray_4k": (lambda: cvb.cvtColor(u16c3, cvb.COLOR_BGR2GRAY, dst=o16), nbytes(u16c3, o16)),
+    "cvt_u16_bgr2ycrcb_4k": (lambda: cvb.cvtColor(u16c3, cvb.COLOR_BGR2YCrCb, dst=ou16c3), nbytes(u16c3, ou16c3)),
+    "cvt_u16_bgr2rgb_4k": (lambda: cvb.cvtColor(u16c3, cvb.COLOR_BGR2RGB, dst=ou16c3), nbytes(u16c3, ou16c3)),
     "sift_detect_1080p": (lambda: cvb.sift_detectAndCompute(sift_img), nbytes(sift_img) * 5),
 }
 for name, (fn, nb) in ops.items():
