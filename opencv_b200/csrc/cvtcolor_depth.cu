@@ -12,6 +12,8 @@
 //   RGB2YCrCb_i<ushort>   Y = DESCALE(c0*C0 + c1*C1 + c2*C2, 14), Cr = DESCALE((R - Y)*C3 + 2^29, 14), saturate_cast<ushort>   (:214-396)
 //   YCrCb2RGB_f<float>    b = fma(Cb - .5, C3, Y), g = fma(Cr - .5, C1, fma(Cb - .5, C2, Y)), r = fma(Cr - .5, C0, Y)          (:616-689)
 //   YCrCb2RGB_i<ushort>   b = Y + DESCALE((Cb - 32768)*C3, 14) ..., saturate_cast<ushort>                                      (:692-735, :880-1013)
+//   RGB2XYZ_f / XYZ2RGB_f, RGB2XYZ_i / XYZ2RGB_i<ushort>   3x3 matrix; float: 4-lane vectors c0*C0 + (c1*C1 + c2*C2), tail (c0*C0 + c1*C1) + c2*C2, no FMA;
+//                         16-bit: DESCALE(.., 12), saturate_cast<ushort>                                                        (color_lab.cpp:172-700)
 // Pure streaming: a thread converts 4 adjacent pixels (8-byte vector accesses when the row allows), nothing is staged.
 #include "common.cuh"
 
@@ -93,6 +95,29 @@ template <int BIDX, int YUV, int DCN> struct DOpFromYCC32 {
     }
 };
 
+// CIE XYZ (color_lab.cpp is not a dispatched unit: it is compiled for the baseline ISA, so the float vectors have 4 lanes and v_fma is mul + add)
+template <int SCN, int DCN> struct DOpXYZ16 {      // rows = output channels, columns = input channels, 12-bit fixed point
+    int c[9];
+    __device__ __forceinline__ void operator()(const unsigned short* s, unsigned short* d, bool) const
+    {
+#pragma unroll
+        for (int r = 0; r < 3; r++) d[r] = sat_u16((s[0] * c[3 * r] + s[1] * c[3 * r + 1] + s[2] * c[3 * r + 2] + (1 << 11)) >> 12);
+        if (DCN == 4) d[3] = 65535;
+    }
+};
+template <int SCN, int DCN> struct DOpXYZ32 {
+    float c[9];
+    __device__ __forceinline__ void operator()(const float* s, float* d, bool vec) const
+    {
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const float p0 = __fmul_rn(s[0], c[3 * r]), p1 = __fmul_rn(s[1], c[3 * r + 1]), p2 = __fmul_rn(s[2], c[3 * r + 2]);
+            d[r] = vec ? __fadd_rn(p0, __fadd_rn(p1, p2)) : __fadd_rn(__fadd_rn(p0, p1), p2);
+        }
+        if (DCN == 4) d[3] = 1.0f;
+    }
+};
+
 // thread = 4 adjacent pixels of one row; 4 * CN * sizeof(T) is a multiple of 8 for every case (of 16 for float): aligned rows move as uint2 / uint4
 template <typename T, int SCN, int DCN, class Op>
 __global__ void __launch_bounds__(256) cvt_depth_kernel(Img src, Img dst, Op op, int vec_cols)
@@ -137,11 +162,11 @@ __global__ void __launch_bounds__(256) cvt_depth_kernel(Img src, Img dst, Op op,
 }
 
 template <typename T, int SCN, int DCN, class Op>
-int launch_depth(const Img& s, const Img& d, const Op& op, cudaStream_t st)
+int launch_depth(const Img& s, const Img& d, const Op& op, cudaStream_t st, int lanes = 8)      // lanes of the reference's float vector: 8 (AVX2 units), 4 (baseline units)
 {
     if (s.rows > 65535 || s.frames > 65535) return B200CV_NOT_IMPLEMENTED;
     dim3 grid(div_up((unsigned)s.cols, 1024), (unsigned)s.rows, (unsigned)s.frames);
-    cvt_depth_kernel<T, SCN, DCN, Op><<<grid, 256, 0, st>>>(s, d, op, (s.cols / 8) * 8);     // 8 floats = the reference's AVX2 vector
+    cvt_depth_kernel<T, SCN, DCN, Op><<<grid, 256, 0, st>>>(s, d, op, (s.cols / lanes) * lanes);
     B200_LAUNCH_CHECK();
     return B200CV_OK;
 }
@@ -212,6 +237,25 @@ int cvt_depth_typed(const Img& s, const Img& d, int scn, int dcn, int code, cuda
             if (crcb) GO(DOpFromYCC16, 2, 0, c0, c1, c2, c3);
             GO(DOpFromYCC16, 2, 1, c0, c1, c2, c3);
         }
+#undef GO
+    }
+    case 32: case 33: case 34: case 35: {                                                                       // BGR2XYZ RGB2XYZ XYZ2BGR XYZ2RGB
+        const bool fwd = code <= 33;
+        NEED(fwd ? (scn == 3 || scn == 4) : scn == 3, fwd ? dcn == 3 : (dcn == 3 || dcn == 4));
+        // sRGB2XYZ_D65 / XYZ2sRGB_D65 (color_lab.cpp:103-144) as float(softdouble) and as 12-bit integers; blue-first images swap the
+        // matrix's columns (to XYZ) or rows (from XYZ)
+        static const float FWD_F[9] = {0.412453f, 0.357580f, 0.180423f, 0.212671f, 0.715160f, 0.072169f, 0.019334f, 0.119193f, 0.950227f};
+        static const float INV_F[9] = {3.240479f, -1.53715f, -0.498535f, -0.969256f, 1.875991f, 0.041556f, 0.055648f, -0.204043f, 1.057311f};
+        static const int FWD_I[9] = {1689, 1465, 739, 871, 2929, 296, 79, 488, 3892}, INV_I[9] = {13273, -6296, -2042, -3970, 7684, 170, 228, -836, 4331};
+        const bool blue_first = code == 32 || code == 34;
+        int idx[9];
+        for (int r = 0; r < 3; r++)
+            for (int k = 0; k < 3; k++) idx[3 * r + k] = fwd ? 3 * r + (blue_first ? 2 - k : k) : 3 * (blue_first ? 2 - r : r) + k;
+#define GO(OPT, TAB, ...) do { if (scn == 3 && dcn == 3) { OPT<3, 3> op; for (int i = 0; i < 9; i++) op.c[i] = TAB[idx[i]]; return launch_depth<T, 3, 3>(s, d, op, st, __VA_ARGS__); } \
+                               if (scn == 4) { OPT<4, 3> op; for (int i = 0; i < 9; i++) op.c[i] = TAB[idx[i]]; return launch_depth<T, 4, 3>(s, d, op, st, __VA_ARGS__); } \
+                               OPT<3, 4> op; for (int i = 0; i < 9; i++) op.c[i] = TAB[idx[i]]; return launch_depth<T, 3, 4>(s, d, op, st, __VA_ARGS__); } while (0)
+        if constexpr (F) { if (fwd) GO(DOpXYZ32, FWD_F, 4); else GO(DOpXYZ32, INV_F, 4); }
+        else { if (fwd) GO(DOpXYZ16, FWD_I, 8); else GO(DOpXYZ16, INV_I, 8); }
 #undef GO
     }
     default: return B200CV_NOT_IMPLEMENTED;

@@ -421,8 +421,8 @@ extern "C" int b200cv_hal_remap32f(int type, const uchar* src, size_t sstep, int
 
 static int cvt(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, int h, int depth, int scn, int dcn, int code)
 {
-    // 16-bit and float images: the channel reorders, GRAY and YCrCb / YUV families (cvtcolor_depth.cu); everything else is 8-bit only
-    const bool depth_family = code <= 11 || (code >= 36 && code <= 39) || (code >= 82 && code <= 85);
+    // 16-bit and float images: the channel reorders, GRAY, XYZ and YCrCb / YUV families (cvtcolor_depth.cu); everything else is 8-bit only
+    const bool depth_family = code <= 11 || (code >= 32 && code <= 39) || (code >= 82 && code <= 85);
     if (depth != B200CV_8U && !((depth == B200CV_16U || depth == B200CV_32F) && depth_family)) return B200CV_NOT_IMPLEMENTED;
     b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(depth, scn)), d = hmat(dst, dstep, w, h, B200CV_MAKETYPE(depth, dcn));
     return b200cv_host_cvt_color(&s, &d, code);

@@ -1,6 +1,6 @@
 """GPU parity: cvtColor on CV_16U and CV_32F images (cvtcolor_depth.cu) against the compiled reference -- BIT-EXACT, floats included: the
 kernel reproduces the reference's vector-body / scalar-tail split of every row (the last width % 8 float pixels run GCC's contraction of
-the scalar statement).  Widths with and without tails, 3 and 4 channels, through the device ABI and through the host (HAL) path."""
+the scalar statement; XYZ lives in a baseline-ISA unit: 4 lanes, no FMA).  Widths with and without tails, 3 and 4 channels, through the device ABI and through the host (HAL) path."""
 import numpy as np
 import pytest
 
@@ -11,11 +11,12 @@ pytestmark = pytest.mark.gpu
 
 FROM3 = [(C.COLOR_BGR2BGRA, 4), (C.COLOR_BGR2RGBA, 4), (C.COLOR_BGR2RGB, 3), (C.COLOR_BGR2GRAY, 1), (C.COLOR_RGB2GRAY, 1),
          (C.COLOR_BGR2YCrCb, 3), (C.COLOR_RGB2YCrCb, 3), (C.COLOR_BGR2YUV, 3), (C.COLOR_RGB2YUV, 3),
-         (C.COLOR_YCrCb2BGR, 3), (C.COLOR_YCrCb2RGB, 3), (C.COLOR_YUV2BGR, 3), (C.COLOR_YUV2RGB, 3), (C.COLOR_YCrCb2BGR, 4), (C.COLOR_YUV2RGB, 4)]
+         (C.COLOR_YCrCb2BGR, 3), (C.COLOR_YCrCb2RGB, 3), (C.COLOR_YUV2BGR, 3), (C.COLOR_YUV2RGB, 3), (C.COLOR_YCrCb2BGR, 4), (C.COLOR_YUV2RGB, 4),
+         (C.COLOR_BGR2XYZ, 3), (C.COLOR_RGB2XYZ, 3), (C.COLOR_XYZ2BGR, 3), (C.COLOR_XYZ2RGB, 3), (C.COLOR_XYZ2BGR, 4)]
 FROM4 = [(C.COLOR_BGRA2BGR, 3), (C.COLOR_RGBA2BGR, 3), (C.COLOR_BGRA2RGBA, 4), (C.COLOR_BGRA2GRAY, 1), (C.COLOR_RGBA2GRAY, 1),
-         (C.COLOR_BGR2YCrCb, 3), (C.COLOR_RGB2YUV, 3)]
+         (C.COLOR_BGR2YCrCb, 3), (C.COLOR_RGB2YUV, 3), (C.COLOR_BGR2XYZ, 3)]
 FROM1 = [(C.COLOR_GRAY2BGR, 3), (C.COLOR_GRAY2BGRA, 4)]
-SHAPES = [(37, 29), (64, 1024), (255, 263), (1, 1), (3, 8)]
+SHAPES = [(37, 29), (64, 1024), (255, 263), (1, 1), (3, 8), (5, 6)]
 
 
 def _img(rng, dtype, h, w, cn):
@@ -49,6 +50,6 @@ def test_cvt_depths_host_path_and_4k(cvb, ref, rng, dtype):
 def test_cvt_depths_declined(cvb, rng):
     """families that exist only for 8-bit images say so (a stock OpenCV then runs its own code)"""
     img = gpu(_img(rng, np.float32, 16, 16, 3))
-    for code in (C.COLOR_BGR2HSV, C.COLOR_BGR2Lab, C.COLOR_BGR2XYZ):
+    for code in (C.COLOR_BGR2HSV, C.COLOR_BGR2Lab, C.COLOR_HSV2BGR):
         with pytest.raises(Exception):
             cvb.cvtColor(img, code, 3)
