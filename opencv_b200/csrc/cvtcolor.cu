@@ -307,6 +307,10 @@ extern "C" int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int 
     }
     B200_REQUIRE(src->cols == dst->cols && src->rows == dst->rows, "src/dst size mismatch");
     B200_REQUIRE((src->frames > 1 ? src->frames : 1) == (dst->frames > 1 ? dst->frames : 1), "src/dst batch mismatch");
+    if ((code >= 46 && code <= 49) || (code >= 135 && code <= 142)) {     // Bayer mosaics, bilinear and edge-aware, 8- and 16-bit (demosaic.cu)
+        B200_REQUIRE(src->data != dst->data, "cvtColor: in-place is not supported");
+        return demosaic_bilinear(src, dst, code, as_stream(stream));
+    }
     if (B200CV_DEPTH(src->type) != B200CV_8U || B200CV_DEPTH(dst->type) != B200CV_8U) return cvt_color_depth(src, dst, code, as_stream(stream));   // 16U / 32F: cvtcolor_depth.cu
     const int scn = B200CV_CN(src->type), dcn = B200CV_CN(dst->type);
     Img s = make_img(src), d = make_img(dst);
@@ -319,10 +323,6 @@ extern "C" int b200cv_cvt_color(const b200cvMat* src, const b200cvMat* dst, int 
     if (code == 44 || code == 45 || code == 74 || code == 75 || code == 56 || code == 57 || code == 78 || code == 79) {     // CIE Lab (cvtcolor_lab.cu)
         B200_REQUIRE(src->data != dst->data, "cvtColor: in-place is not supported");
         return cvt_color_lab(src, dst, code, st);
-    }
-    if ((code >= 46 && code <= 49) || (code >= 139 && code <= 142)) {     // Bayer mosaics, bilinear (demosaic.cu)
-        B200_REQUIRE(src->data != dst->data, "cvtColor: in-place is not supported");
-        return demosaic_bilinear(src, dst, code, st);
     }
 #define NEED(sc_ok, dc_ok) B200_REQUIRE((sc_ok) && (dc_ok), "channel count does not match the colour code")
     switch (code) {
