@@ -21,6 +21,16 @@ struct ResTab {            // 32 bytes
     union { int ic[4]; float fc[4]; };
 };
 
+// INTER_LANCZOS4 tables (resize_lanczos.cu builds them on the host; resize_lanczos_sep.cu reads them too)
+struct LzTap {
+    int s;                 // source index of tap 3 (floor of the source coordinate)
+    float fc[8];
+    short ic[8];
+    short pad[2];
+};
+__host__ __device__ __forceinline__ int lz_clip(int x, int n) { return x < 0 ? 0 : (x < n ? x : n - 1); }
+bool resize_lanczos_sep_u8(const Img& s, const Img& d, int cn, const LzTap* host_yt, const LzTap* xt, const LzTap* yt, cudaStream_t st);   // resize_lanczos_sep.cu
+
 __host__ __device__ __forceinline__ int clip_i(int x, int a, int b) { return x >= a ? (x < b ? x : b - 1) : a; }
 
 // ---- coefficient helpers -------------------------------------------------------------------------------------------

@@ -8,21 +8,20 @@
 //           and left to right in the last (dw * cn) % 4 elements (:2131-2156); multiply and add rounded separately (no FMA in that unit)
 // The weights need the host's libm sin / cos to be the reference's, bit for bit: the two tables (dw + dh entries of an offset and 8
 // weights) are built on the host with the reference's expressions and uploaded with the call (<= 0.5 MB for 8K); everything per pixel
-// runs on the device.  One thread per destination element, 64 taps: gather / issue bound, like CUBIC.
+// runs on the device.  Float: one thread per destination element, 64 taps (gather / issue bound, like CUBIC); 8-bit: the tiled separable
+// kernel below (B200CV_RESIZE_LANCZOS_PATH=v1 keeps the per-element kernel).
 #include <math.h>
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "common.cuh"
+#include "resize.cuh"
 
 namespace b200cv {
 
 namespace {
 
-struct LzTap {
-    int s;                 // source index of tap 3 (floor of the source coordinate)
-    float fc[8];
-    short ic[8];
-    short pad[2];
-};
 
 // interpolateLanczos4, resize.cpp:974-1003 (host; this file is compiled with -ffp-contract=off)
 void lanczos4_weights(float x, float* c)
@@ -61,7 +60,6 @@ void lanczos4_table(int dn, double scale, LzTap* tab)
     }
 }
 
-__device__ __forceinline__ int lz_clip(int x, int n) { return x < 0 ? 0 : (x < n ? x : n - 1); }
 
 template <typename T, int CN>
 __global__ void __launch_bounds__(256) resize_lanczos4_kernel(Img src, Img dst, const LzTap* __restrict__ xt, const LzTap* __restrict__ yt, int sw, int sh, int dw)
@@ -127,7 +125,14 @@ int resize_lanczos_impl(const Img& s, const Img& d, int depth, int cn, cudaStrea
     const LzTap *xt = dtab, *yt = dtab + dw;
     const dim3 block(256);
     const dim3 grid(div_up((unsigned)(dw * cn), 256), (unsigned)dh, (unsigned)s.frames);
-    if (depth == B200CV_8U) {
+    bool done = false;
+#ifndef B200CV_HOST_EMULATION
+    const char* lz_env = getenv("B200CV_RESIZE_LANCZOS_PATH");                 // "v1": the per-element kernel for 8-bit images too
+    if (depth == B200CV_8U && !(lz_env && !strcmp(lz_env, "v1")))
+        done = resize_lanczos_sep_u8(s, d, cn, tab.data() + dw, xt, yt, st);    // resize_lanczos_sep.cu: tiled, separable
+#endif
+    if (done) {
+    } else if (depth == B200CV_8U) {
         if (cn == 1) resize_lanczos4_kernel<uchar, 1><<<grid, block, 0, st>>>(s, d, xt, yt, sw, sh, dw);
         else if (cn == 3) resize_lanczos4_kernel<uchar, 3><<<grid, block, 0, st>>>(s, d, xt, yt, sw, sh, dw);
         else resize_lanczos4_kernel<uchar, 4><<<grid, block, 0, st>>>(s, d, xt, yt, sw, sh, dw);

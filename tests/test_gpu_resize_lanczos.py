@@ -28,3 +28,16 @@ def test_lanczos4_resize_8k_batch(cvb, ref, rng):
     batch = np.stack([base, np.roll(base, 5, axis=0)])
     out = cpu(cvb.resize(gpu(batch), (5120, 2880), interpolation=C.INTER_LANCZOS4))
     assert_exact(out[1], ref.resize(batch[1], (5120, 2880), 4), "LANCZOS4 8K -> 5K")
+
+
+@pytest.mark.parametrize("cn", [1, 3, 4])
+def test_lanczos4_first_version_equals_tiled_kernel(cvb, rng, monkeypatch, cn):
+    """B200CV_RESIZE_LANCZOS_PATH=v1 (one thread per element, 64 gathers) == the tiled separable kernel; includes a strong decimation
+    whose tiles do not fit shared memory and stay on the first version either way"""
+    shape = (211, 333) if cn == 1 else (211, 333, cn)
+    img = gpu(rng.integers(0, 256, shape, dtype=np.uint8))
+    for dsz in ((500, 317), (96, 100), (666, 422), (33, 7)):
+        monkeypatch.delenv("B200CV_RESIZE_LANCZOS_PATH", raising=False)
+        got = cpu(cvb.resize(img, dsz, interpolation=C.INTER_LANCZOS4))
+        monkeypatch.setenv("B200CV_RESIZE_LANCZOS_PATH", "v1")
+        assert_exact(cpu(cvb.resize(img, dsz, interpolation=C.INTER_LANCZOS4)), got, "LANCZOS4 v1 vs tiled %s cn=%d" % (dsz, cn))
