@@ -12,6 +12,7 @@
 //   RGB2YCrCb_i<ushort>   Y = DESCALE(c0*C0 + c1*C1 + c2*C2, 14), Cr = DESCALE((R - Y)*C3 + 2^29, 14), saturate_cast<ushort>   (:214-396)
 //   YCrCb2RGB_f<float>    b = fma(Cb - .5, C3, Y), g = fma(Cr - .5, C1, fma(Cb - .5, C2, Y)), r = fma(Cr - .5, C0, Y)          (:616-689)
 //   YCrCb2RGB_i<ushort>   b = Y + DESCALE((Cb - 32768)*C3, 14) ..., saturate_cast<ushort>                                      (:692-735, :880-1013)
+//   RGB2HSV_f / HSV2RGB_f  float only; see the operators below                                                                  (color_hsv.simd.hpp:269-515)
 //   RGB2XYZ_f / XYZ2RGB_f, RGB2XYZ_i / XYZ2RGB_i<ushort>   3x3 matrix; float: 4-lane vectors c0*C0 + (c1*C1 + c2*C2), tail (c0*C0 + c1*C1) + c2*C2, no FMA;
 //                         16-bit: DESCALE(.., 12), saturate_cast<ushort>                                                        (color_lab.cpp:172-700)
 // Pure streaming: a thread converts 4 adjacent pixels (8-byte vector accesses when the row allows), nothing is staged.
@@ -91,6 +92,67 @@ template <int BIDX, int YUV, int DCN> struct DOpFromYCC32 {
         d[BIDX] = fmaf(cb, c3, Y);
         d[1] = fmaf(cr, c1, fmaf(cb, c2, Y));
         d[BIDX ^ 2] = fmaf(cr, c0, Y);
+        if (DCN == 4) d[3] = 1.0f;
+    }
+};
+
+// float HSV (color_hsv.simd.hpp:269-368 RGB2HSV_f, :371-515 HSV2RGB_f; hue range 360 for float images, the _FULL codes are the same).
+// Vector body (8 lanes): s = diff / (|max| + eps), h = fma(hsel, 60 / (diff + eps), res) * hscale with res in {0, 360, 120, 240};
+// scalar tail: 60. / (diff + eps) in DOUBLE, rounded to float; h = (g - b) * d, or fma(b - r, d, 120), fma(r - g, d, 240) (GCC's contraction), + 360 if negative.
+template <int BIDX> struct DOpToHSV32 {
+    float hscale;
+    __device__ __forceinline__ void operator()(const float* sp, float* d, bool vec) const
+    {
+        const float b = sp[BIDX], g = sp[1], r = sp[BIDX ^ 2];
+        const float vmax = fmaxf(fmaxf(r, g), b), vmin = fminf(fminf(r, g), b);
+        const float diff = __fsub_rn(vmax, vmin);
+        const float s = __fdiv_rn(diff, __fadd_rn(fabsf(vmax), 1.1920929e-07f));
+        const bool req = r == vmax, geq = g == vmax;
+        float h;
+        if (vec) {
+            const float hsel = req ? __fsub_rn(g, b) : geq ? __fsub_rn(b, r) : __fsub_rn(r, g);
+            const float res = req ? (g < b ? 360.f : 0.f) : geq ? 120.f : 240.f;
+            h = fmaf(hsel, __fdiv_rn(60.f, __fadd_rn(diff, 1.1920929e-07f)), res);
+        } else {
+            const float dd = __double2float_rn(__ddiv_rn(60.0, (double)__fadd_rn(diff, 1.1920929e-07f)));
+            h = req ? __fmul_rn(__fsub_rn(g, b), dd) : geq ? fmaf(__fsub_rn(b, r), dd, 120.f) : fmaf(__fsub_rn(r, g), dd, 240.f);
+            if (h < 0.f) h = __fadd_rn(h, 360.f);
+        }
+        d[0] = __fmul_rn(h, hscale); d[1] = s; d[2] = vmax;
+    }
+};
+// inverse: tab1 = v(1 - s), tab2 = v * fma(-s, h, 1), tab3 = v * fma(-s, 1 - h, 1) (the compiler's contraction in both the vector unit and the tail);
+// vector body: sector from TRUNCATED h through float arithmetic and a chain of selects (negative hues fall through it as written);
+// tail (HSV2RGB_native): s == 0 -> grey, FLOORED h, sector mod 6 made non-negative, table look-up
+template <int BIDX, int DCN> struct DOpFromHSV32 {
+    float hscale;
+    __device__ __forceinline__ void operator()(const float* sp, float* d, bool vec) const
+    {
+        float h = __fmul_rn(sp[0], hscale);
+        const float s = sp[1], v = sp[2];
+        float b, g, r;
+        if (vec) {
+            const float pre = truncf(h);
+            h = __fsub_rn(h, pre);
+            const float tab0 = v, tab1 = __fmul_rn(v, __fsub_rn(1.f, s)), tab2 = __fmul_rn(v, fmaf(-s, h, 1.f)), tab3 = __fmul_rn(v, fmaf(-s, __fsub_rn(1.f, h), 1.f));
+            const float sec = fmaf(-truncf(__fmul_rn(pre, 1.0f / 6.0f)), 6.f, pre);       // exact: small integers
+            b = sec < 2.f ? tab1 : 0.f; b = sec == 2.f ? tab3 : b; b = sec == 3.f ? tab0 : b; b = sec == 4.f ? tab0 : b; b = sec > 4.f ? tab2 : b;
+            g = sec < 1.f ? tab3 : s; g = sec == 1.f ? tab0 : g; g = sec == 2.f ? tab0 : g; g = sec == 3.f ? tab2 : g; g = sec > 3.f ? tab1 : g;
+            r = sec < 1.f ? tab0 : v; r = sec == 1.f ? tab2 : r; r = sec == 2.f ? tab1 : r; r = sec == 3.f ? tab1 : r; r = sec == 4.f ? tab3 : r; r = sec > 4.f ? tab0 : r;
+        } else if (s == 0.f) {
+            b = g = r = v;
+        } else {
+            const float fl = floorf(h);
+            h = __fsub_rn(h, fl);
+            int sector = (int)fl % 6;
+            sector += sector < 0 ? 6 : 0;
+            const float tab0 = v, tab1 = __fmul_rn(v, __fsub_rn(1.f, s)), tab2 = __fmul_rn(v, fmaf(-s, h, 1.f)), tab3 = __fmul_rn(v, fmaf(-s, __fsub_rn(1.f, h), 1.f));
+            // sector_data rows {b, g, r} = {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}
+            b = sector < 2 ? tab1 : sector == 2 ? tab3 : sector < 5 ? tab0 : tab2;
+            g = sector == 0 ? tab3 : sector < 3 ? tab0 : sector == 3 ? tab2 : tab1;
+            r = sector == 0 ? tab0 : sector == 1 ? tab2 : sector < 4 ? tab1 : sector == 4 ? tab3 : tab0;
+        }
+        d[BIDX] = b; d[1] = g; d[BIDX ^ 2] = r;
         if (DCN == 4) d[3] = 1.0f;
     }
 };
@@ -238,6 +300,26 @@ int cvt_depth_typed(const Img& s, const Img& d, int scn, int dcn, int code, cuda
             GO(DOpFromYCC16, 2, 1, c0, c1, c2, c3);
         }
 #undef GO
+    }
+    case 40: case 41: case 66: case 67: case 54: case 55: case 70: case 71: {                                   // BGR/RGB <-> HSV (_FULL): float only
+        if constexpr (!F) return B200CV_NOT_IMPLEMENTED;
+        else {
+            const bool fwd = code == 40 || code == 41 || code == 66 || code == 67;
+            const bool blue_first = code == 40 || code == 66 || code == 54 || code == 70;
+            NEED(fwd ? (scn == 3 || scn == 4) : scn == 3, fwd ? dcn == 3 : (dcn == 3 || dcn == 4));
+            if (fwd) {
+                const float hscale = 360.f * (1.f / 360.f);        // hrange * (1.f / 360.f), hrange = 360 for float images (color_hsv.simd.hpp:308, color_hsv.dispatch.cpp)
+                if (blue_first) { DOpToHSV32<0> op = {hscale}; return scn == 3 ? launch_depth<T, 3, 3>(s, d, op, st) : launch_depth<T, 4, 3>(s, d, op, st); }
+                DOpToHSV32<2> op = {hscale};
+                return scn == 3 ? launch_depth<T, 3, 3>(s, d, op, st) : launch_depth<T, 4, 3>(s, d, op, st);
+            }
+            const float hscale = 6.f / 360.f;
+            if (blue_first && dcn == 3) { DOpFromHSV32<0, 3> op = {hscale}; return launch_depth<T, 3, 3>(s, d, op, st); }
+            if (blue_first) { DOpFromHSV32<0, 4> op = {hscale}; return launch_depth<T, 3, 4>(s, d, op, st); }
+            if (dcn == 3) { DOpFromHSV32<2, 3> op = {hscale}; return launch_depth<T, 3, 3>(s, d, op, st); }
+            DOpFromHSV32<2, 4> op = {hscale};
+            return launch_depth<T, 3, 4>(s, d, op, st);
+        }
     }
     case 32: case 33: case 34: case 35: {                                                                       // BGR2XYZ RGB2XYZ XYZ2BGR XYZ2RGB
         const bool fwd = code <= 33;

@@ -423,7 +423,8 @@ static int cvt(const uchar* src, size_t sstep, uchar* dst, size_t dstep, int w, 
 {
     // 16-bit and float images: the channel reorders, GRAY, XYZ and YCrCb / YUV families (cvtcolor_depth.cu); everything else is 8-bit only
     const bool depth_family = code <= 11 || (code >= 32 && code <= 39) || (code >= 82 && code <= 85);
-    if (depth != B200CV_8U && !((depth == B200CV_16U || depth == B200CV_32F) && depth_family)) return B200CV_NOT_IMPLEMENTED;
+    const bool hsv = code == 40 || code == 41 || code == 54 || code == 55 || code == 66 || code == 67 || code == 70 || code == 71;      // float only
+    if (depth != B200CV_8U && !((depth == B200CV_16U || depth == B200CV_32F) && depth_family) && !(depth == B200CV_32F && hsv)) return B200CV_NOT_IMPLEMENTED;
     b200cvMat s = hmat(src, sstep, w, h, B200CV_MAKETYPE(depth, scn)), d = hmat(dst, dstep, w, h, B200CV_MAKETYPE(depth, dcn));
     return b200cv_host_cvt_color(&s, &d, code);
 }

@@ -47,9 +47,35 @@ def test_cvt_depths_host_path_and_4k(cvb, ref, rng, dtype):
         assert_exact(got, ref.cvtColor(img, code, dcn), "host cvtColor %s code=%d" % (np.dtype(dtype).name, code))
 
 
+HSV_FWD = [(C.COLOR_BGR2HSV, 3), (C.COLOR_RGB2HSV, 3), (C.COLOR_BGR2HSV_FULL, 3), (C.COLOR_RGB2HSV_FULL, 3)]
+HSV_INV = [(C.COLOR_HSV2BGR, 3), (C.COLOR_HSV2RGB, 3), (C.COLOR_HSV2BGR_FULL, 3), (C.COLOR_HSV2RGB_FULL, 4), (C.COLOR_HSV2BGR, 4)]
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(480, 640)])
+def test_cvt_float_hsv(cvb, ref, rng, shape):
+    """float HSV both ways, bit-exact: 8-lane vector body (fma(hsel, 60 / (diff + eps), res)) and the scalar tail (double division, the
+    compiler's contractions, + 360 for negative hues; s == 0 shortcut, floored hue) are separate code paths in the reference and in the kernel"""
+    h, w = shape
+    bgr = _img(rng, np.float32, h, w, 3)
+    if h > 8 and w > 8:
+        bgr[2:5, 1:7] = bgr[2:5, 1:7, :1]                        # greys: diff == 0
+        bgr[5, :6] = [[.2, .2, .7], [.7, .2, .2], [.2, .7, .7], [.7, .7, .2], [0, 0, 0], [1, 1, 1]]       # ties between the maxima
+    for scn in (3, 4):
+        src = bgr if scn == 3 else np.concatenate([bgr, bgr[..., :1]], -1)
+        for code, dcn in HSV_FWD:
+            assert_exact(cpu(cvb.cvtColor(gpu(src), code, dcn)), ref.cvtColor(src, code, dcn), "f32 to HSV code=%d scn=%d %s" % (code, scn, shape))
+    hsv = np.stack([rng.random((h, w), dtype=np.float32) * np.float32(420) - np.float32(30),       # hues outside [0, 360) on both sides
+                    rng.random((h, w), dtype=np.float32), rng.random((h, w), dtype=np.float32)], -1).astype(np.float32)
+    if h > 8 and w > 8:
+        hsv[3, :, 1] = 0                                          # s == 0
+        hsv[4, :6, 0] = [0, 60, 120, 359.99997, 360, 720]
+    for code, dcn in HSV_INV:
+        assert_exact(cpu(cvb.cvtColor(gpu(hsv), code, dcn)), ref.cvtColor(hsv, code, dcn), "f32 from HSV code=%d dcn=%d %s" % (code, dcn, shape))
+
+
 def test_cvt_depths_declined(cvb, rng):
     """families that exist only for 8-bit images say so (a stock OpenCV then runs its own code)"""
-    img = gpu(_img(rng, np.float32, 16, 16, 3))
+    img = gpu(_img(rng, np.uint16, 16, 16, 3))
     for code in (C.COLOR_BGR2HSV, C.COLOR_BGR2Lab, C.COLOR_HSV2BGR):
         with pytest.raises(Exception):
             cvb.cvtColor(img, code, 3)

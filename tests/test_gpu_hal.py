@@ -100,6 +100,14 @@ def test_opencv_built_with_b200_hal(cvb, ref, rng):
     assert_exact(hal.cvtColor(img, C.COLOR_BGR2YUV, 3), ref.cvtColor(img, C.COLOR_BGR2YUV, 3), "cv::cvtColor via HAL")
     n1 = cvb.launch_count()
     assert n1 > n0, "cv::cvtColor did not reach the B200 HAL"
+    # 16-bit and float images reach the device too (cvtcolor_depth.cu) -- bit-exact incl. the float vector-body / scalar-tail split
+    f3 = (rng.random((241, 323, 3), dtype=np.float32) * 1.2).astype(np.float32)
+    w3 = rng.integers(0, 65536, (241, 323, 3), dtype=np.uint16)
+    nb = cvb.launch_count()
+    for src_img in (f3, w3):
+        for code, dcn in ((C.COLOR_BGR2GRAY, 1), (C.COLOR_RGB2YCrCb, 3), (C.COLOR_YUV2BGR, 3), (C.COLOR_BGR2RGBA, 4), (C.COLOR_BGR2XYZ, 3)):
+            assert_exact(hal.cvtColor(src_img, code, dcn), ref.cvtColor(src_img, code, dcn), "cv::cvtColor %s code %d via HAL" % (src_img.dtype, code))
+    assert cvb.launch_count() - nb >= 10, "16-bit / float cv::cvtColor did not reach the B200 HAL"
     assert_exact(hal.resize(img, (320, 240), 1), ref.resize(img, (320, 240), 1), "cv::resize via HAL")
     assert_exact(hal.resize(img, (427, 321), 2), ref.resize(img, (427, 321), 2), "cv::resize CUBIC via HAL")
     M = np.array([[0.9, 0.1, 5], [-0.1, 0.9, 7]])
