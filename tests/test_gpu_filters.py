@@ -356,3 +356,23 @@ def test_gaussian_u8_streaming_kernel(cvb, oracle, rng, monkeypatch, k):
     t = cvb.getGaussianKernel(k, 0).astype(np.float32)
     img = rng.integers(0, 256, (180, 300), dtype=np.uint8)
     assert_exact(cpu(cvb.sepFilter2D(gpu(img), -1, t, t)), oracle.sepFilter2D(img, -1, t, t), "stream sepFilter2D 8.8 mode k=%d" % k)
+
+
+@pytest.mark.parametrize("k", [3, 5])
+@pytest.mark.parametrize("width", [8, 9, 10, 11, 131, 257, 1022])
+def test_gaussian_u8_binomial_kernel(cvb, oracle, rng, monkeypatch, k, width):
+    """3 x 3 / 5 x 5 sigma = 0 on one channel: the packed 16-bit binomial kernel (gauss_u8_binomial.cu; opt-in, B200CV_GAUSS_U8_PATH=binomial).  Rows with an aligned pitch and a width
+    that is not a multiple of 4 (views of a wider buffer) reach its tail path; every border mode; equal to the oracle and to the tile kernel"""
+    import torch
+    h = 70
+    base = gpu(rand_u8(rng, h, ((width + 3) // 4) * 4 + 8))
+    view = base[:, :width]
+    img = cpu(view)
+    outb = torch.zeros_like(base)
+    for b in (0, 1, 2, 4):
+        want = oracle.GaussianBlur(img, (k, k), 0, 0, b)
+        monkeypatch.setenv("B200CV_GAUSS_U8_PATH", "binomial")
+        got = cpu(cvb.GaussianBlur(view, (k, k), 0, 0, b, dst=outb[:, :width]))
+        assert_exact(got, want, "binomial k=%d w=%d border=%d" % (k, width, b))
+        monkeypatch.delenv("B200CV_GAUSS_U8_PATH", raising=False)
+        assert_exact(cpu(cvb.GaussianBlur(view, (k, k), 0, 0, b)), want, "default kernel k=%d w=%d border=%d" % (k, width, b))

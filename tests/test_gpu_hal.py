@@ -190,3 +190,36 @@ def test_cv_typed_surface_against_real_opencv_headers(cvb):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "cv surface ok" in r.stdout
+
+
+def test_host_entries_from_concurrent_threads(cvb, oracle, rng):
+    """OpenCV calls its HAL from many threads at once (parallel_for_ bodies, user threads): the host entries keep one context (streams + staging)
+    per calling thread.  Eight threads, different image sizes and ops, repeated: every result equals the oracle's."""
+    import threading
+    from opencv_b200 import hal as H
+    imgs = [rand_u8(rng, 200 + 17 * i, 300 + 13 * i, 3) for i in range(8)]
+    M = np.array([[0.9, 0.1, 5], [-0.1, 0.9, 7]])
+    want = [(oracle.GaussianBlur(im, (5, 5), 0), oracle.cvtColor(im, C.COLOR_BGR2YUV, 3), oracle.resize(im, (im.shape[1] // 2 + 3, im.shape[0] // 2 + 1), 1),
+             oracle.warpAffine(im, M, (im.shape[1], im.shape[0]), 1, 1), oracle.matchTemplate(im[:, :, 0].copy(), im[20:36, 30:54, 0].copy(), 3)) for im in imgs]
+    errors = []
+
+    def work(i):
+        try:
+            im = imgs[i]
+            for _ in range(12):
+                got = (H.GaussianBlur(im, (5, 5), 0), H.cvtColor(im, C.COLOR_BGR2YUV, 3), H.resize(im, (im.shape[1] // 2 + 3, im.shape[0] // 2 + 1), interpolation=1),
+                       H.warpAffine(im, M, (im.shape[1], im.shape[0]), 1, 1), H.matchTemplate(im[:, :, 0].copy(), im[20:36, 30:54, 0].copy(), 3))
+                for k in range(4):
+                    if not np.array_equal(got[k], want[i][k]):
+                        errors.append("thread %d op %d differs" % (i, k))
+                if not np.allclose(got[4], want[i][4], atol=1e-4):
+                    errors.append("thread %d matchTemplate differs" % i)
+        except Exception as e:      # noqa: BLE001 -- reported below
+            errors.append("thread %d: %r" % (i, e))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
