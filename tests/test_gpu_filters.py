@@ -359,13 +359,14 @@ def test_gaussian_u8_streaming_kernel(cvb, oracle, rng, monkeypatch, k):
 
 
 @pytest.mark.parametrize("k", [3, 5])
-@pytest.mark.parametrize("width", [8, 9, 10, 11, 131, 257, 1022])
+@pytest.mark.parametrize("width", [32, 48, 131, 512, 528, 1022, 2064])
 def test_gaussian_u8_binomial_kernel(cvb, oracle, rng, monkeypatch, k, width):
-    """3 x 3 / 5 x 5 sigma = 0 on one channel: the packed 16-bit binomial kernel (gauss_u8_binomial.cu; opt-in, B200CV_GAUSS_U8_PATH=binomial).  Rows with an aligned pitch and a width
-    that is not a multiple of 4 (views of a wider buffer) reach its tail path; every border mode; equal to the oracle and to the tile kernel"""
+    """3 x 3 / 5 x 5 sigma = 0 on one channel: the packed 16-bit binomial kernel (gauss_u8_binomial.cu; opt-in, B200CV_GAUSS_U8_PATH=binomial) on views of a wider
+    buffer (16-byte aligned rows; widths that are multiples of 16 run it, the others fall through to the tile kernel); every border mode it takes;
+    part-filled last warps (48, 528, 2064); equal to the oracle and to the default kernel"""
     import torch
     h = 70
-    base = gpu(rand_u8(rng, h, ((width + 3) // 4) * 4 + 8))
+    base = gpu(rand_u8(rng, h, ((width + 15) // 16) * 16 + 16))
     view = base[:, :width]
     img = cpu(view)
     outb = torch.zeros_like(base)

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_filters.py -q -p no:cacheprovider -k "gaussian_u8" > gpurun_out/gb_tests.log 2>&1; tail -8 gpurun_out/gb_tests.log
-timeout 600 python bench.py --workload c2 --steps 5 --warmup 3 --no-extra --no-cpu --no-e2e > gpurun_out/bench_c2_n.json 2> gpurun_out/bench_c2_n.err
+B200CV_GAUSS_U8_PATH=binomial timeout 600 python bench.py --workload c2 --steps 5 --warmup 3 --no-extra --no-cpu --no-e2e > gpurun_out/bench_c2_n.json 2> gpurun_out/bench_c2_n.err
 python - <<PY
 import json
 try:
