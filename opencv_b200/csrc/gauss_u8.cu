@@ -281,13 +281,13 @@ int gauss_u8_fast(const Img& s, const Img& d, int cn, const int64_t* fx, int kw,
     for (int i = 0; i < kw; i++) sx += fx[i];
     for (int i = 0; i < kh; i++) sy += fy[i];
     if (sx > 256 || sy > 256) return B200CV_NOT_IMPLEMENTED;      // 16-bit row sums and an unsaturated result byte
-    // GaussianBlur 3 x 3 / 5 x 5 with the binomial 8.8 taps (sigma = 0), one channel: packed 16-bit adds, no multiplier (gauss_u8_binomial.cu).
-    // Measured on a B200 (profiles/r02_notes.md 7b): under 5 thread-instructions per pixel and no IDP, but its column-walking warps are latency
-    // bound (ncu: issue active 27 %, long-scoreboard stalls 17 per issue with 4-byte lanes; 16-byte lanes: 0.100 / 0.111 ms per 16 4K frames at
-    // 3 x 3 / 5 x 5 against 0.074 / 0.087 for the TMA tile kernel below) -- so it is opt-in: B200CV_GAUSS_U8_PATH=binomial (tests run both)
+    // GaussianBlur 3 x 3 / 5 x 5 with the binomial 8.8 taps (sigma = 0), one channel, 16-byte aligned rows of a multiple of 16 pixels: packed
+    // 16-bit adds, no multiplier, rows through a lane-private cp.async ring (gauss_u8_binomial.cu).  Measured on a B200, 16 4K frames: 0.0645 /
+    // 0.0741 ms (0.63 / 0.55 of the HBM roofline) against 0.074 / 0.087 (0.58 / 0.47) for the TMA tile kernel below, which keeps every other case
+    // and is forced by B200CV_GAUSS_U8_PATH=tile (tests run both)
     if (sep_mode == 0 && !box) {
         const char* e = getenv("B200CV_GAUSS_U8_PATH");
-        if (e && !strcmp(e, "binomial")) {
+        if (!(e && (!strcmp(e, "tile") || !strcmp(e, "stream")))) {
             const int brc = gauss_u8_binomial(s, d, cn, fx, kw, fy, kh, border, st);
             if (brc != B200CV_NOT_IMPLEMENTED) return brc;
         }

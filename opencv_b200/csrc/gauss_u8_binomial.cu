@@ -43,73 +43,88 @@ __device__ __forceinline__ void gb_row(unsigned wl, unsigned w0, unsigned wr, un
 
 struct GbBorder { unsigned sel_l, sel_r; int zero; };     // PRMT selectors that build the two halo bytes from the row's own first / last word
 
-// A thread owns 16 adjacent columns (one 128-bit load per row: 512 contiguous bytes per warp and row -- with 4-byte lanes the kernel was latency
-// bound at 0.19 ms per 16 4K frames) and walks down GB_SEG rows.  The word left of its first and right of its last word come from the neighbouring
-// lanes by shuffle; lanes 0 and 31 load theirs; at the image edges they are built from the row's own bytes by the border rule.
-template <int K, bool FAST>
-__device__ __forceinline__ void gb_walk(const Img& src, const Img& dst, int border, GbBorder gb, int x0, int y0, int y1, int f, bool active, int lane)
+constexpr int GB_DEPTH = 8;     // rows of copies in flight per thread (a power of two)
+
+__device__ __forceinline__ void gb_cp16(void* smem, const void* g, int src_bytes, unsigned dep)
 {
-    constexpr int R = K / 2;
-    const int W = src.cols, H = src.rows;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g), "r"(src_bytes), "r"(dep) : "memory");
+}
+__device__ __forceinline__ void gb_cp4(void* smem, const void* g, int src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g), "r"(src_bytes) : "memory");
+}
+
+// A thread owns 16 adjacent columns and walks down GB_SEG rows.  Its rows arrive through a lane-private ring in shared memory filled by cp.async
+// (one 16-byte copy per row and lane = 512 contiguous bytes per warp and row, GB_DEPTH rows in flight, no registers held by loads in flight: with
+// loads into registers the kernel was latency bound -- 4-byte lanes 0.19 ms, 16-byte lanes 0.10 ms per 16 4K frames).  Nothing in the ring is shared
+// between lanes, so cp.async.wait_group is the only synchronisation.  The word left of the thread's first and right of its last word come from the
+// neighbouring lanes by shuffle; lanes 0 and 31 copy theirs; at the image edges they are built from the row's own bytes by the border rule.
+template <int K, bool FAST>
+__device__ __forceinline__ void gb_walk(const Img& src, const Img& dst, int border, GbBorder gb, int x0, int y0, int y1, int f, bool active, int lane,
+                                        uint4* ring, unsigned* ering)
+{
+    constexpr int R = K / 2, D = GB_DEPTH;
+    const int W = src.cols, H = src.rows, tid = threadIdx.x;
     auto row_ptr = [&](int r) -> const uchar* {
         const int sr = (unsigned)r < (unsigned)H ? r : border_interpolate(r, H, border);
         return sr < 0 ? nullptr : src.row<uchar>(f, sr);
     };
     const bool first = x0 == 0, last = x0 + 16 == W;
-    const int ew_off = lane == 0 ? -4 : 16;                                   // the extra word lanes 0 / 31 load themselves
+    const int ew_off = lane == 0 ? -4 : 16;                                   // the extra word lanes 0 / 31 copy themselves
+    const bool ew_lane = lane == 0 || lane == 31;
     const bool ew_need = active && ((lane == 0 && !first) || (lane == 31 && !last));
     const uchar* qf = FAST ? src.row<uchar>(f, y0 - R) + x0 : nullptr;
-    int fi = y0 - R;                                                          // next image row to fetch
-    auto fetch = [&](uint4& v, unsigned& ew) {
-        const uchar* rp = FAST ? qf : row_ptr(fi);
-        v = make_uint4(0, 0, 0, 0); ew = 0;
-        if (rp) {
-            if (!FAST) rp += x0;
-            if (active) v = __ldg((const uint4*)rp);
-            if (ew_need) ew = __ldg((const unsigned*)(rp + ew_off));
-        }
-        if (FAST) qf += src.step;
-        fi++;
-    };
-    constexpr int PF = K == 3 ? 6 : 5;              // rows of loads in flight; a multiple of K: ring indices are compile-time constants in the unrolled body
     const int N = (y1 - y0) + K - 1;
+    int issued = 0;                                                           // input rows requested so far (image row y0 - R + issued is next)
+    auto issue = [&](unsigned dep) {
+        if (issued < N) {
+            const uchar* rp = FAST ? qf : row_ptr(y0 - R + issued);
+            const bool have = rp != nullptr;
+            const uchar* g = have ? (FAST ? rp : rp + x0) : src.data;
+            const int slot = issued & (D - 1);
+            gb_cp16(&ring[slot * 128 + tid], g, have && active ? 16 : 0, dep);      // 0 source bytes = zero fill (rows of a BORDER_CONSTANT frame, idle lanes)
+            if (ew_lane) gb_cp4(&ering[slot * 128 + tid], have && ew_need ? g + ew_off : src.data, have && ew_need ? 4 : 0);
+            if (FAST) qf += src.step;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");                  // an (empty) group per call keeps the wait count uniform at the tail
+        issued++;
+    };
+#pragma unroll
+    for (int u = 0; u < D; u++) issue(0u);
     unsigned he[K][4], ho[K][4];
-    uint4 wv[PF];
-    unsigned we[PF];
-#pragma unroll
-    for (int u = 0; u < PF; u++) {
-        wv[u] = make_uint4(0, 0, 0, 0); we[u] = 0;
-        if (u < N) fetch(wv[u], we[u]);
-    }
     uchar* dp = dst.row<uchar>(f, y0) + x0;
-    for (int base = 0; base < N; base += PF) {
+    for (int base = 0; base < N; base += K) {
 #pragma unroll
-        for (int u = 0; u < PF; u++) {
+        for (int u = 0; u < K; u++) {
             const int i = base + u;
             if (i < N) {
-                const uint4 v = wv[u];
+                asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+                const int slot = i & (D - 1);
+                const uint4 v = ring[slot * 128 + tid];
+                const unsigned e = ew_lane ? ering[slot * 128 + tid] : 0u;
                 unsigned hl = __shfl_up_sync(0xffffffffu, v.w, 1), hr = __shfl_down_sync(0xffffffffu, v.x, 1);
-                if (lane == 0) hl = we[u];
-                if (lane == 31) hr = we[u];
+                if (lane == 0) hl = e;
+                if (lane == 31) hr = e;
                 if (first) hl = gb.zero ? 0u : __byte_perm(v.x, v.x, gb.sel_l);
                 if (last) hr = gb.zero ? 0u : __byte_perm(v.w, v.w, gb.sel_r);
-                gb_row<K>(hl, v.x, v.y, he[u % K][0], ho[u % K][0]);
-                gb_row<K>(v.x, v.y, v.z, he[u % K][1], ho[u % K][1]);
-                gb_row<K>(v.y, v.z, v.w, he[u % K][2], ho[u % K][2]);
-                gb_row<K>(v.z, v.w, hr, he[u % K][3], ho[u % K][3]);
-                if (i + PF < N) fetch(wv[u], we[u]);
+                gb_row<K>(hl, v.x, v.y, he[u][0], ho[u][0]);
+                gb_row<K>(v.x, v.y, v.z, he[u][1], ho[u][1]);
+                gb_row<K>(v.y, v.z, v.w, he[u][2], ho[u][2]);
+                gb_row<K>(v.z, v.w, hr, he[u][3], ho[u][3]);
+                // refill the slot just read: the copy is issued after instructions that needed the slot's data (the operand `dep` makes that explicit)
+                issue(he[u][0] ^ he[u][3] ^ e);
                 if (i >= K - 1) {                                   // output row y0 + i - (K - 1): input rows i - K + 1 .. i, oldest in slot (u + 1) % K
                     unsigned out[4];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         unsigned se, so;
                         if constexpr (K == 3) {
-                            se = he[(u + 1) % K][j] + he[u % K][j] + 2u * he[(u + 2) % K][j] + 0x00080008u;
-                            so = ho[(u + 1) % K][j] + ho[u % K][j] + 2u * ho[(u + 2) % K][j] + 0x00080008u;
+                            se = he[(u + 1) % K][j] + he[u][j] + 2u * he[(u + 2) % K][j] + 0x00080008u;
+                            so = ho[(u + 1) % K][j] + ho[u][j] + 2u * ho[(u + 2) % K][j] + 0x00080008u;
                             out[j] = __byte_perm(se >> 4, so >> 4, 0x6240);
                         } else {
-                            se = (he[(u + 1) % K][j] + he[u % K][j]) + 4u * (he[(u + 2) % K][j] + he[(u + 4) % K][j]) + 6u * he[(u + 3) % K][j] + 0x00800080u;
-                            so = (ho[(u + 1) % K][j] + ho[u % K][j]) + 4u * (ho[(u + 2) % K][j] + ho[(u + 4) % K][j]) + 6u * ho[(u + 3) % K][j] + 0x00800080u;
+                            se = (he[(u + 1) % K][j] + he[u][j]) + 4u * (he[(u + 2) % K][j] + he[(u + 4) % K][j]) + 6u * he[(u + 3) % K][j] + 0x00800080u;
+                            so = (ho[(u + 1) % K][j] + ho[u][j]) + 4u * (ho[(u + 2) % K][j] + ho[(u + 4) % K][j]) + 6u * ho[(u + 3) % K][j] + 0x00800080u;
                             out[j] = __byte_perm(se, so, 0x7351);
                         }
                     }
@@ -119,12 +134,16 @@ __device__ __forceinline__ void gb_walk(const Img& src, const Img& dst, int bord
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 template <int K>
 __global__ void __launch_bounds__(128) gauss_u8_binomial_kernel(Img src, Img dst, int border, GbBorder gb)
 {
     constexpr int R = K / 2;
+    extern __shared__ __align__(16) unsigned char gb_smem[];
+    uint4* ring = (uint4*)gb_smem;                                           // [GB_DEPTH][128]: lane-private row ring
+    unsigned* ering = (unsigned*)(gb_smem + sizeof(uint4) * GB_DEPTH * 128);  // [GB_DEPTH][128]: the extra word of lanes 0 / 31
     const int W = src.cols, H = src.rows;
     const int x0 = (blockIdx.x * 128 + threadIdx.x) * 16, f = blockIdx.z;
     const int y0 = blockIdx.y * GB_SEG, y1 = min(y0 + GB_SEG, H);
@@ -132,8 +151,8 @@ __global__ void __launch_bounds__(128) gauss_u8_binomial_kernel(Img src, Img dst
     if ((blockIdx.x * 128 + (threadIdx.x & ~31)) * 16 >= W) return;            // the whole warp is past the row end
     const bool active = x0 < W;
     const int xc = active ? x0 : 0;                                            // idle lanes of the last warp take part in the shuffles only
-    if (y0 - R >= 0 && y1 + R <= H) gb_walk<K, true>(src, dst, border, gb, xc, y0, y1, f, active, lane);
-    else gb_walk<K, false>(src, dst, border, gb, xc, y0, y1, f, active, lane);
+    if (y0 - R >= 0 && y1 + R <= H) gb_walk<K, true>(src, dst, border, gb, xc, y0, y1, f, active, lane, ring, ering);
+    else gb_walk<K, false>(src, dst, border, gb, xc, y0, y1, f, active, lane, ring, ering);
 }
 
 }  // namespace
@@ -158,8 +177,9 @@ int gauss_u8_binomial(const Img& s, const Img& d, int cn, const int64_t* fx, int
     default: return B200CV_NOT_IMPLEMENTED;
     }
     const dim3 grid(div_up(div_up((unsigned)s.cols, 16), 128), div_up((unsigned)s.rows, GB_SEG), (unsigned)s.frames);
-    if (kw == 3) gauss_u8_binomial_kernel<3><<<grid, 128, 0, st>>>(s, d, border & ~B200CV_BORDER_ISOLATED, gb);
-    else gauss_u8_binomial_kernel<5><<<grid, 128, 0, st>>>(s, d, border & ~B200CV_BORDER_ISOLATED, gb);
+    const size_t smem = (sizeof(uint4) + sizeof(unsigned)) * GB_DEPTH * 128;
+    if (kw == 3) gauss_u8_binomial_kernel<3><<<grid, 128, smem, st>>>(s, d, border & ~B200CV_BORDER_ISOLATED, gb);
+    else gauss_u8_binomial_kernel<5><<<grid, 128, smem, st>>>(s, d, border & ~B200CV_BORDER_ISOLATED, gb);
     B200_LAUNCH_CHECK();
     return B200CV_OK;
 }

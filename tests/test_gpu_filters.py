@@ -361,9 +361,9 @@ def test_gaussian_u8_streaming_kernel(cvb, oracle, rng, monkeypatch, k):
 @pytest.mark.parametrize("k", [3, 5])
 @pytest.mark.parametrize("width", [32, 48, 131, 512, 528, 1022, 2064])
 def test_gaussian_u8_binomial_kernel(cvb, oracle, rng, monkeypatch, k, width):
-    """3 x 3 / 5 x 5 sigma = 0 on one channel: the packed 16-bit binomial kernel (gauss_u8_binomial.cu; opt-in, B200CV_GAUSS_U8_PATH=binomial) on views of a wider
+    """3 x 3 / 5 x 5 sigma = 0 on one channel: the packed 16-bit binomial kernel (gauss_u8_binomial.cu; the default where it applies, B200CV_GAUSS_U8_PATH=tile forces the general kernel) on views of a wider
     buffer (16-byte aligned rows; widths that are multiples of 16 run it, the others fall through to the tile kernel); every border mode it takes;
-    part-filled last warps (48, 528, 2064); equal to the oracle and to the default kernel"""
+    part-filled last warps (48, 528, 2064); equal to the oracle and to the tile kernel"""
     import torch
     h = 70
     base = gpu(rand_u8(rng, h, ((width + 15) // 16) * 16 + 16))
@@ -372,8 +372,8 @@ def test_gaussian_u8_binomial_kernel(cvb, oracle, rng, monkeypatch, k, width):
     outb = torch.zeros_like(base)
     for b in (0, 1, 2, 4):
         want = oracle.GaussianBlur(img, (k, k), 0, 0, b)
-        monkeypatch.setenv("B200CV_GAUSS_U8_PATH", "binomial")
+        monkeypatch.delenv("B200CV_GAUSS_U8_PATH", raising=False)
         got = cpu(cvb.GaussianBlur(view, (k, k), 0, 0, b, dst=outb[:, :width]))
         assert_exact(got, want, "binomial k=%d w=%d border=%d" % (k, width, b))
-        monkeypatch.delenv("B200CV_GAUSS_U8_PATH", raising=False)
-        assert_exact(cpu(cvb.GaussianBlur(view, (k, k), 0, 0, b)), want, "default kernel k=%d w=%d border=%d" % (k, width, b))
+        monkeypatch.setenv("B200CV_GAUSS_U8_PATH", "tile")
+        assert_exact(cpu(cvb.GaussianBlur(view, (k, k), 0, 0, b)), want, "tile kernel k=%d w=%d border=%d" % (k, width, b))
