@@ -79,3 +79,12 @@ def test_cvt_depths_declined(cvb, rng):
     for code in (C.COLOR_BGR2HSV, C.COLOR_BGR2Lab, C.COLOR_HSV2BGR):
         with pytest.raises(Exception):
             cvb.cvtColor(img, code, 3)
+
+
+def test_depth_known_answer_hashes(cvb):
+    """the committed constants of tests/kat_depth.py (adler32 of the reference's output on inputs derived from the reference's own RNG(0) fixture):
+    parity that does not need the reference library on the box"""
+    from kat_depth import KAT_DEPTH, kat_dcn, kat_hash, kat_input
+    for (code, kind), want in sorted(KAT_DEPTH.items()):
+        got = cpu(cvb.cvtColor(gpu(kat_input(kind)), code, kat_dcn(code)))
+        assert kat_hash(got) == want, "cvtColor code %d on %s: hash differs from the reference's" % (code, kind)

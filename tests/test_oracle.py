@@ -537,3 +537,10 @@ def test_port_vs_reference_features(ref, port, rng):
             assert_close(pg[o][i], wg[o][i], atol=1e-3, what="sift gauss")
         for i in range(5):
             assert_close(pd[o][i], wd[o][i], atol=1e-3, what="sift dog")
+
+
+def test_reference_reproduces_the_depth_cvtcolor_hashes(ref):
+    """tests/kat_depth.py: the constants the GPU tests compare against were generated from this very library"""
+    from kat_depth import KAT_DEPTH, kat_dcn, kat_hash, kat_input
+    for (code, kind), want in sorted(KAT_DEPTH.items()):
+        assert kat_hash(ref.cvtColor(kat_input(kind), code, kat_dcn(code))) == want, "reference hash changed: code %d on %s" % (code, kind)
