@@ -227,8 +227,8 @@ template <typename T, int SCN, int DCN, class Op>
 int launch_depth(const Img& s, const Img& d, const Op& op, cudaStream_t st, int lanes = 8)      // lanes of the reference's float vector: 8 (AVX2 units), 4 (baseline units)
 {
     if (s.rows > 65535 || s.frames > 65535) return B200CV_NOT_IMPLEMENTED;
-    dim3 grid(div_up((unsigned)s.cols, 1024), (unsigned)s.rows, (unsigned)s.frames);
-    cvt_depth_kernel<T, SCN, DCN, Op><<<grid, 256, 0, st>>>(s, d, op, (s.cols / lanes) * lanes);
+    const dim3 grid(div_up((unsigned)s.cols, 1024), (unsigned)s.rows, (unsigned)s.frames), block(256);
+    cvt_depth_kernel<T, SCN, DCN, Op><<<grid, block, 0, st>>>(s, d, op, (s.cols / lanes) * lanes);
     B200_LAUNCH_CHECK();
     return B200CV_OK;
 }

@@ -58,6 +58,8 @@ static inline double __dadd_rn(double a, double b) { volatile double r = a + b; 
 static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
 static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
 static inline float __double2float_rn(double a) { return (float)a; }
+static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline int __double2int_rn(double a) { return (int)lrint(a); }
 
 // packed-integer intrinsics (PTX dp4a.u32.u32, dp2a.lo/hi.u32.u32, prmt) for kernels whose arithmetic core is host-testable

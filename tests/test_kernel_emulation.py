@@ -324,6 +324,67 @@ def test_emulated_bayer_demosaic_vs_port(bayer_emu, port, rng):
         assert np.array_equal(out[f], port.cvtColorYUV(batch[f, :, :, 0], 48)), "Bayer batch frame %d" % f
 
 
+# ---- cvtColor on 16-bit / float images (cvtcolor_depth.cu) and the edge-aware / 16-bit Bayer codes (demosaic.cu) against the compiled reference ----
+@pytest.fixture(scope="module")
+def depth_emu():
+    lib = build_emulation("cvtcolor_depth.cu", "int emu_cvt_depth(const b200cvMat* s, const b200cvMat* d, int code)",
+                          "    return b200cv::cvt_color_depth(s, d, code, nullptr);")
+    lib.emu_cvt_depth.argtypes = [ctypes.POINTER(Mat), ctypes.POINTER(Mat), ctypes.c_int]
+
+    def run(src, code, dcn):
+        dst = np.zeros(src.shape[:2] if dcn == 1 else src.shape[:2] + (dcn,), src.dtype)
+        depth = {np.dtype(np.uint16): 2, np.dtype(np.float32): 5}[src.dtype]
+        ms, md = mat_of(src), mat_of(dst)
+        ms.type = depth | (((1 if src.ndim == 2 else src.shape[2]) - 1) << 3)
+        md.type = depth | ((dcn - 1) << 3)
+        rc = lib.emu_cvt_depth(ctypes.byref(ms), ctypes.byref(md), int(code))
+        assert rc == 0, "emulated cvt_color_depth(code %d) returned %d" % (code, rc)
+        return dst
+    return run
+
+
+def test_emulated_depth_cvtcolor_vs_reference(depth_emu, rng):
+    """the kernel source of cvtcolor_depth.cu compiled for the host == the compiled reference, bit for bit (vector bodies and scalar tails)"""
+    from oracle.api import Oracle, available
+    if not available("ref"):
+        pytest.skip("oracle/_ref/libocvref.so not built")
+    ref = Oracle("ref")
+    for (h, w) in [(9, 29), (5, 64), (3, 7)]:
+        f3 = (rng.random((h, w, 3), dtype=np.float32) * 1.5 - 0.25).astype(np.float32)
+        w3 = rng.integers(0, 65536, (h, w, 3), dtype=np.uint16)
+        for src in (f3, w3):
+            for code, dcn in ((0, 4), (4, 3), (6, 1), (7, 1), (36, 3), (37, 3), (82, 3), (83, 3), (38, 3), (39, 4), (84, 3), (85, 3), (32, 3), (33, 3), (34, 3), (35, 4)):
+                assert np.array_equal(depth_emu(src, code, dcn), ref.cvtColor(src, code, dcn)), "%s code %d %dx%d" % (src.dtype, code, w, h)
+        hsv = np.stack([rng.random((h, w), dtype=np.float32) * np.float32(420) - np.float32(30), rng.random((h, w), dtype=np.float32),
+                        rng.random((h, w), dtype=np.float32)], -1).astype(np.float32)
+        hsv[0, :, 1] = 0
+        for code, dcn in ((40, 3), (41, 3), (66, 3), (67, 3)):
+            assert np.array_equal(depth_emu(f3, code, dcn), ref.cvtColor(f3, code, dcn)), "f32 to HSV code %d %dx%d" % (code, w, h)
+        for code, dcn in ((54, 3), (55, 3), (70, 4), (71, 3)):
+            assert np.array_equal(depth_emu(hsv, code, dcn), ref.cvtColor(hsv, code, dcn)), "f32 from HSV code %d %dx%d" % (code, w, h)
+        g = rng.integers(0, 65536, (h, w), dtype=np.uint16)
+        assert np.array_equal(depth_emu(g, 8, 3), ref.cvtColor(g, 8, 3)) and np.array_equal(depth_emu(g.astype(np.float32), 9, 4), ref.cvtColor(g.astype(np.float32), 9, 4))
+
+
+def test_emulated_bayer_edge_aware_and_16bit_vs_reference(rng):
+    from oracle.api import Oracle, available
+    if not available("ref"):
+        pytest.skip("oracle/_ref/libocvref.so not built")
+    ref = Oracle("ref")
+    lib = build_emulation("demosaic.cu", "int emu_demosaic_any(const b200cvMat* s, const b200cvMat* d, int code)",
+                          "    return b200cv::demosaic_bilinear(s, d, code, nullptr);")
+    lib.emu_demosaic_any.argtypes = [ctypes.POINTER(Mat), ctypes.POINTER(Mat), ctypes.c_int]
+    for dtype, depth in ((np.uint8, 0), (np.uint16, 2)):
+        for (h, w) in [(3, 3), (4, 5), (17, 33), (18, 34)]:
+            img = rng.integers(0, 256 if depth == 0 else 65536, (h, w)).astype(dtype)
+            for code, dcn in ((135, 3), (136, 3), (137, 3), (138, 3)) + (((46, 3), (49, 3), (140, 4)) if depth else ()):
+                dst = np.zeros((h, w, dcn), dtype)
+                ms, md = mat_of(img), mat_of(dst)
+                ms.type = depth; md.type = depth | ((dcn - 1) << 3)
+                assert lib.emu_demosaic_any(ctypes.byref(ms), ctypes.byref(md), code) == 0
+                assert np.array_equal(dst, ref.cvtColor(img, code, dcn)), "Bayer %s code %d %dx%d" % (np.dtype(dtype).name, code, w, h)
+
+
 # ---- cv::integral (integral.cu): six map-only kernels ----------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def integral_emu():
