@@ -80,7 +80,8 @@ B200CV_API int b200cv_hal_remap32f(int src_type, const b200cv_uchar* src_data, s
 /* hal_ni_pyrdown, hal_replacement.hpp:1244 (cv::pyrDown on a whole Mat, pyramids.cpp:1377) */
 B200CV_API int b200cv_hal_pyrdown(const b200cv_uchar* src_data, size_t src_step, int src_width, int src_height, b200cv_uchar* dst_data, size_t dst_step,
                                   int dst_width, int dst_height, int depth, int cn, int border_type);
-/* colour: hal_ni_cvtBGRtoBGR :395, cvtBGRtoGray :442, cvtGraytoBGR :456, cvtBGRtoYUV :500, cvtYUVtoBGR :533, cvtBGRtoHSV :596, cvtHSVtoBGR :613 */
+/* colour: hal_ni_cvtBGRtoBGR :395, cvtBGRtoGray :442, cvtGraytoBGR :456, cvtBGRtoYUV :500, cvtYUVtoBGR :533, cvtBGRtoHSV :596, cvtHSVtoBGR :613.
+ * depth: CV_8U for all; CV_16U and CV_32F for BGRtoBGR / BGRtoGray / GraytoBGR / BGRtoYUV / YUVtoBGR / XYZ; CV_32F for HSV (HLS: not implemented) */
 B200CV_API int b200cv_hal_cvtBGRtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                       int depth, int scn, int dcn, bool swapBlue);
 B200CV_API int b200cv_hal_cvtBGRtoGray(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
@@ -95,7 +96,7 @@ B200CV_API int b200cv_hal_cvtBGRtoHSV(const b200cv_uchar* src_data, size_t src_s
                                       int depth, int scn, bool swapBlue, bool isFullRange, bool isHSV);
 B200CV_API int b200cv_hal_cvtHSVtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                       int depth, int dcn, bool swapBlue, bool isFullRange, bool isHSV);
-/* hal_ni_cvtBGRtoXYZ / hal_ni_cvtXYZtoBGR (hal_replacement.hpp:564, :579): 8-bit */
+/* hal_ni_cvtBGRtoXYZ / hal_ni_cvtXYZtoBGR (hal_replacement.hpp:564, :579): 8-bit, 16-bit, float */
 B200CV_API int b200cv_hal_cvtBGRtoXYZ(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
                                       int depth, int scn, bool swapBlue);
 B200CV_API int b200cv_hal_cvtXYZtoBGR(const b200cv_uchar* src_data, size_t src_step, b200cv_uchar* dst_data, size_t dst_step, int width, int height,
